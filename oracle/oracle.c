@@ -1,0 +1,458 @@
+/*
+ * oracle.c -- CPU restatement of the csdr block-DSP hot path.  TEST INFRASTRUCTURE (see oracle.h).
+ *
+ * Compiled strictly (gcc -O2 -fno-fast-math -ffp-contract=off): every float/double promotion below is
+ * deliberate and mirrors the C promotion rules the reference source is subject to.  Comments of the
+ * form [ref file:line] name the reference lines each block follows.
+ */
+#include "oracle.h"
+#include <limits.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+static const float kPi = (float)3.14159265358979323846;          /* [ref libcsdr.h:65] PI is a float */
+
+/* ------------------------------------------------------------------------------------------------
+ * sample-format conversion
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:2363-2366] byte -> float; the divide by 127.5 and the -1.0 happen in double. */
+void oracle_convert_u8_f(const unsigned char *in, float *out, int n)
+{
+    for (int k = 0; k < n; k++) {
+        double v = (double)(float)in[k];
+        out[k] = (float)(v / (UCHAR_MAX / 2.0) - 1.0);
+    }
+}
+
+/* [ref libcsdr.c:2373-2376] short -> float, `(float)x/SHRT_MAX`.  The reference's own build flags
+ * (Makefile:38 -ffast-math) turn the divide into a multiply by the float-rounded reciprocal; that is
+ * what every shipped libcsdr does, so it is what we pin (differs from a true divide by 1 ulp on 2.3 %
+ * of the 65536 codes; verified bit-exact against oracle/_ref for all of them). */
+void oracle_convert_s16_f(const short *in, float *out, int n)
+{
+    const float recip = 1.0f / (float)SHRT_MAX;
+    for (int k = 0; k < n; k++) out[k] = (float)in[k] * recip;
+}
+
+/* [ref libcsdr.c:2390-2398] float -> short; single-precision multiply, truncation toward zero.
+ * Out-of-range inputs follow what x86 does (cvttss2si to int32, keep the low 16 bits). */
+void oracle_convert_f_s16(const float *in, short *out, int n)
+{
+    for (int k = 0; k < n; k++) {
+        float scaled = in[k] * (float)SHRT_MAX;
+        int wide = (scaled >= 2147483648.0f || scaled < -2147483648.0f || scaled != scaled) ? INT_MIN : (int)scaled;
+        out[k] = (short)(unsigned short)(wide & 0xffff);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * filter design
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:169-174] */
+int oracle_firdes_filter_len(float transition_bw)
+{
+    int len = (int)(4.0 / transition_bw);
+    return (len % 2 == 0) ? len + 1 : len;
+}
+
+/* [ref libcsdr.c:76-96] window kernels; argument in [-1,1] is remapped to [0,1] first. */
+float oracle_window(int window, float rate)
+{
+    if (window == ORACLE_WINDOW_BOXCAR) return 1.0f;
+    rate = (float)(0.5 + (double)(rate / 2));
+    if (window == ORACLE_WINDOW_BLACKMAN)
+        return (float)(0.42 - 0.5 * cos((double)(2 * kPi * rate)) + 0.08 * cos((double)(4 * kPi * rate)));
+    return (float)(0.54 - 0.46 * cos((double)(2 * kPi * rate)));     /* HAMMING, also the default */
+}
+
+/* [ref libcsdr.c:117-125 normalize_fir_f, 127-142 firdes_lowpass_f] windowed sinc, unity DC gain. */
+void oracle_firdes_lowpass_f(float *taps, int length, float cutoff_rate, int window)
+{
+    int mid = length / 2;
+    taps[mid] = 2 * kPi * cutoff_rate * oracle_window(window, 0);
+    for (int k = 1; k <= mid; k++) {
+        double sinc = sin((double)(2 * kPi * cutoff_rate * k)) / k;
+        float t = (float)(sinc * (double)oracle_window(window, (float)k / mid));
+        taps[mid - k] = t;
+        taps[mid + k] = t;
+    }
+    float sum = 0;
+    for (int k = 0; k < length; k++) sum += taps[k];
+    for (int k = 0; k < length; k++) taps[k] = taps[k] / sum;
+}
+
+/* [ref libcsdr.c:144-167] real low-pass of half the width, heterodyned to the band centre with a
+ * float phase accumulator that is wrapped into [0, 2pi]. */
+void oracle_firdes_bandpass_c(ocf32 *taps, int length, float lowcut, float highcut, int window)
+{
+    float *real_taps = malloc(sizeof(float) * (size_t)length);
+    oracle_firdes_lowpass_f(real_taps, length, (highcut - lowcut) / 2, window);
+    float centre = (highcut + lowcut) / 2;
+    float phase = 0;
+    for (int k = 0; k < length; k++) {
+        float c = (float)cos((double)phase), s = (float)sin((double)phase);
+        phase += 2 * kPi * centre;
+        while (phase > 2 * kPi) phase -= 2 * kPi;
+        while (phase < 0) phase += 2 * kPi;
+        taps[k].i = c * real_taps[k];
+        taps[k].q = s * real_taps[k];
+    }
+    free(real_taps);
+}
+
+/* [ref libcsdr.c:1234-1243] smallest power of two strictly greater than x. */
+int oracle_next_pow2(int x)
+{
+    for (int b = 0; b < 31; b++) if (x < (1 << b)) return 1 << b;
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * NCO shift by phasor recursion
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr_gpl.c:81-89] */
+oracle_shift_t oracle_shift_addition_init(float rate)
+{
+    oracle_shift_t d;
+    rate *= 2;
+    d.sindelta = (float)sin((double)(rate * kPi));
+    d.cosdelta = (float)cos((double)(rate * kPi));
+    d.rate = rate;
+    return d;
+}
+
+static float wrap_pm_pi(float phase)
+{
+    while (phase > kPi) phase -= 2 * kPi;
+    while (phase < -kPi) phase += 2 * kPi;
+    return phase;
+}
+
+/* [ref libcsdr_gpl.c:27-52] rotate by a phasor advanced with the angle-addition identities, all in
+ * float; the phase returned is advanced arithmetically and wrapped to (-pi, pi]. */
+float oracle_shift_addition_cc(const ocf32 *in, ocf32 *out, int n, oracle_shift_t d, float starting_phase)
+{
+    float c = (float)cos((double)starting_phase), s = (float)sin((double)starting_phase);
+    for (int k = 0; k < n; k++) {
+        float xi = in[k].i, xq = in[k].q;
+        out[k].i = c * xi - s * xq;
+        out[k].q = s * xi + c * xq;
+        float c_next = c * d.cosdelta - s * d.sindelta;
+        float s_next = s * d.cosdelta + c * d.sindelta;
+        c = c_next; s = s_next;
+    }
+    return wrap_pm_pi(starting_phase + d.rate * kPi * n);
+}
+
+/* [ref libcsdr_gpl.c:126-129] */
+oracle_shift_t oracle_decimating_shift_addition_init(float rate, int decimation)
+{
+    return oracle_shift_addition_init(rate * decimation);
+}
+
+/* [ref libcsdr_gpl.c:131-160] same rotation applied to every decimation-th sample only. */
+oracle_dshift_status_t oracle_decimating_shift_addition_cc(const ocf32 *in, ocf32 *out, int n, oracle_shift_t d,
+                                                          int decimation, oracle_dshift_status_t st)
+{
+    float c = (float)cos((double)st.starting_phase), s = (float)sin((double)st.starting_phase);
+    int produced = 0, pos;
+    for (pos = st.decimation_remain; pos < n; pos += decimation) {
+        float xi = in[pos].i, xq = in[pos].q;
+        out[produced].i = c * xi - s * xq;
+        out[produced].q = s * xi + c * xq;
+        produced++;
+        float c_next = c * d.cosdelta - s * d.sindelta;
+        float s_next = s * d.cosdelta + c * d.sindelta;
+        c = c_next; s = s_next;
+    }
+    st.decimation_remain = pos - n;
+    st.starting_phase = wrap_pm_pi(st.starting_phase + d.rate * kPi * produced);
+    st.output_size = produced;
+    return st;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * decimating FIR
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:528-549] one output per `decimation` inputs while a full tap window still fits;
+ * I and Q are accumulated separately, taps in ascending order. */
+int oracle_fir_decimate_cc(const ocf32 *in, ocf32 *out, int n, int decimation, const float *taps, int taps_length)
+{
+    int produced = 0;
+    for (int start = 0; start < n && start + taps_length <= n; start += decimation) {
+        float acc_i = 0, acc_q = 0;
+        for (int t = 0; t < taps_length; t++) acc_i += in[start + t].i * taps[t];
+        for (int t = 0; t < taps_length; t++) acc_q += in[start + t].q * taps[t];
+        out[produced].i = acc_i;
+        out[produced].q = acc_q;
+        produced++;
+    }
+    return produced;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FM demodulator
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:1021] */
+static const double kQuadriK = 0.340447550238101026565118445432744920253753662109375;
+
+/* [ref libcsdr.c:1040-1071] K*(I*dQ - Q*dI)/(I^2+Q^2); differences against the previous sample
+ * (last_sample for the first one); 0 where the power is exactly 0; the final scale/divide is in double. */
+ocf32 oracle_fmdemod_quadri_cf(const ocf32 *in, float *out, int n, ocf32 last_sample)
+{
+    ocf32 prev = last_sample;
+    for (int k = 0; k < n; k++) {
+        float dq = in[k].q - prev.q;
+        float di = in[k].i - prev.i;
+        float num = in[k].i * dq - in[k].q * di;
+        float den = in[k].i * in[k].i + in[k].q * in[k].q;
+        out[k] = den ? (float)(kQuadriK * (double)num / (double)den) : 0;
+        prev = in[k];
+    }
+    return n > 0 ? in[n - 1] : last_sample;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * fractional decimator
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:715-748] */
+void oracle_fractional_decimator_ff_init(oracle_fracdec_t *d, float rate, int num_poly_points,
+                                         const float *taps, int taps_length)
+{
+    memset(d, 0, sizeof(*d));
+    d->num_poly_points = num_poly_points & ~1;
+    d->xifirst = -(num_poly_points / 2) + 1;
+    d->xilast = num_poly_points / 2;
+    int slot = 0;
+    for (int xi = d->xifirst; xi <= d->xilast; xi++, slot++) {
+        float prod = 1;
+        for (int xj = d->xifirst; xj <= d->xilast; xj++)
+            if (xi != xj) prod *= (float)(xi - xj);
+        d->denom[slot] = prod;
+    }
+    d->where = (float)(-d->xifirst);
+    d->rate = rate;
+    d->taps = taps;
+    d->taps_length = taps_length;
+    d->input_processed = 0;
+}
+
+static float fir_dot(const float *x, const float *taps, int len)     /* [ref libcsdr.c fir_one_pass_ff] */
+{
+    float acc = 0;
+    for (int t = 0; t < len; t++) acc += x[t] * taps[t];
+    return acc;
+}
+
+/* [ref libcsdr.c:751-793] positions advance by a float accumulator; each output is a Lagrange
+ * polynomial through num_poly_points neighbours of ceil(where)-1 (optionally FIR-prefiltered). */
+void oracle_fractional_decimator_ff(const float *in, float *out, int n, oracle_fracdec_t *d)
+{
+    int produced = 0, index_high;
+    float pts[ORACLE_FD_MAX_POINTS], coef[ORACLE_FD_MAX_POINTS];
+    for (; (index_high = (int)ceilf(d->where)) + d->num_poly_points + d->taps_length < n; d->where += d->rate) {
+        int low = index_high - 1;
+        for (int w = 0; w < d->num_poly_points; w++)
+            pts[w] = d->taps ? fir_dot(in + low + w, d->taps, d->taps_length) : in[low + w];
+        float x = d->where - (float)low;
+        int slot = 0;
+        for (int xi = d->xifirst; xi <= d->xilast; xi++, slot++) {
+            float prod = 1;
+            for (int xj = d->xifirst; xj <= d->xilast; xj++)
+                if (xi != xj) prod *= (x - (float)xj);
+            coef[slot] = prod;
+        }
+        float acc = 0;
+        for (int w = 0; w < d->num_poly_points; w++) acc += (coef[w] / d->denom[w]) * pts[w];
+        out[produced++] = acc;
+    }
+    d->input_processed = (index_high - 1) + d->xifirst;
+    d->where -= (float)d->input_processed;
+    d->output_size = produced;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * fastagc
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:944-991] gain = reference / max(peak of this and the two previous blocks), capped
+ * at 50, ramped linearly from the previous gain across the block that is two calls old. */
+void oracle_fastagc_ff(oracle_fastagc_t *st, float *hist1, float *hist2, const float *in, float *out)
+{
+    int n = st->block;
+    float peak_in = 0;
+    for (int k = 0; k < n; k++) { float a = fabsf(in[k]); if (a > peak_in) peak_in = a; }
+    float peak = peak_in;
+    if (peak < st->peak_2) peak = st->peak_2;
+    if (peak < st->peak_1) peak = st->peak_1;
+    float target = st->reference / peak;
+    if (target > 50) target = 50;                                /* FASTAGC_MAX_GAIN */
+    for (int k = 0; k < n; k++) {
+        float r = (float)k / n;
+        float gain = (float)((double)st->last_gain * (1.0 - (double)r) + (double)(target * r));
+        out[k] = hist1[k] * gain;
+    }
+    memcpy(hist1, hist2, sizeof(float) * (size_t)n);             /* buffer_1 <- buffer_2 <- input */
+    memcpy(hist2, in, sizeof(float) * (size_t)n);
+    st->peak_1 = st->peak_2;
+    st->peak_2 = peak_in;
+    st->last_gain = target;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * DFT (stands in for FFTW3f)
+ * ---------------------------------------------------------------------------------------------- */
+
+static void dft64(double *re, double *im, int n, int sign)
+{
+    if (n > 0 && (n & (n - 1)) == 0) {
+        for (int a = 1, b = 0; a < n; a++) {
+            int bit = n >> 1;
+            for (; b & bit; bit >>= 1) b ^= bit;
+            b ^= bit;
+            if (a < b) { double t = re[a]; re[a] = re[b]; re[b] = t; t = im[a]; im[a] = im[b]; im[b] = t; }
+        }
+        for (int span = 2; span <= n; span <<= 1) {
+            int half = span / 2, stride = n / span;
+            for (int k = 0; k < half; k++) {
+                double ang = sign * 2.0 * M_PI * (double)(k * stride) / (double)n;
+                double wr = cos(ang), wi = sin(ang);
+                for (int base = 0; base < n; base += span) {
+                    int lo = base + k, hi = lo + half;
+                    double tr = re[hi] * wr - im[hi] * wi, ti = re[hi] * wi + im[hi] * wr;
+                    re[hi] = re[lo] - tr; im[hi] = im[lo] - ti;
+                    re[lo] += tr; im[lo] += ti;
+                }
+            }
+        }
+        return;
+    }
+    double *yr = malloc(sizeof(double) * (size_t)n), *yi = malloc(sizeof(double) * (size_t)n);
+    for (int k = 0; k < n; k++) {
+        double sr = 0, si = 0;
+        for (int t = 0; t < n; t++) {
+            double ang = sign * 2.0 * M_PI * (double)(((long long)k * t) % n) / (double)n;
+            sr += re[t] * cos(ang) - im[t] * sin(ang);
+            si += re[t] * sin(ang) + im[t] * cos(ang);
+        }
+        yr[k] = sr; yi[k] = si;
+    }
+    memcpy(re, yr, sizeof(double) * (size_t)n); memcpy(im, yi, sizeof(double) * (size_t)n);
+    free(yr); free(yi);
+}
+
+/* unnormalised DFT, exponent sign -1 when forward, +1 when backward [ref fft_fftw.c:9 FFTW_FORWARD/BACKWARD] */
+void oracle_dft_c2c(const ocf32 *in, ocf32 *out, int n, int forward)
+{
+    double *re = malloc(sizeof(double) * 2 * (size_t)n), *im = re + n;
+    for (int k = 0; k < n; k++) { re[k] = in[k].i; im[k] = in[k].q; }
+    dft64(re, im, n, forward ? -1 : +1);
+    for (int k = 0; k < n; k++) { out[k].i = (float)re[k]; out[k].q = (float)im[k]; }
+    free(re);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * overlap-add FFT filter
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:814-849] spectrum x taps_fft, inverse, /N, then add the previous block's tail. */
+void oracle_apply_fir_fft_cc(const ocf32 *in_padded, const ocf32 *taps_fft, const ocf32 *last_overlap,
+                             int overlap_size, ocf32 *result, int fft_size)
+{
+    ocf32 *spec = malloc(sizeof(ocf32) * (size_t)fft_size);
+    oracle_dft_c2c(in_padded, spec, fft_size, 1);
+    for (int k = 0; k < fft_size; k++) {
+        ocf32 x = spec[k], h = taps_fft[k];
+        spec[k].i = x.i * h.i - x.q * h.q;
+        spec[k].q = x.i * h.q + x.q * h.i;
+    }
+    oracle_dft_c2c(spec, result, fft_size, 0);
+    for (int k = 0; k < fft_size; k++) { result[k].i /= (float)fft_size; result[k].q /= (float)fft_size; }
+    for (int k = 0; k < overlap_size; k++) { result[k].i += last_overlap[k].i; result[k].q += last_overlap[k].q; }
+    free(spec);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * fastddc
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref fastddc.c:38-72] */
+int oracle_fastddc_init(oracle_fastddc_t *ddc, float transition_bw, int decimation, float shift_rate)
+{
+    ddc->pre_decimation = 1;
+    ddc->post_decimation = decimation;
+    while (ddc->post_decimation % 2 == 0 && ddc->post_decimation / 2 != 1) {     /* is_integer(post/2.f) */
+        ddc->post_decimation /= 2;
+        ddc->pre_decimation *= 2;
+    }
+    ddc->taps_min_length = oracle_firdes_filter_len(transition_bw);
+    ddc->taps_length = oracle_next_pow2((int)(ceil(ddc->taps_min_length / (float)ddc->pre_decimation) * ddc->pre_decimation)) + 1;
+    ddc->fft_size = oracle_next_pow2(ddc->taps_length * 4);
+    while (ddc->fft_size < ddc->pre_decimation) ddc->fft_size *= 2;
+    ddc->overlap_length = ddc->taps_length - 1;
+    ddc->input_size = ddc->fft_size - ddc->overlap_length;
+    ddc->fft_inv_size = ddc->fft_size / ddc->pre_decimation;
+    ddc->v = ddc->fft_size / ddc->overlap_length;
+    int middlebin = ddc->fft_size / 2;
+    ddc->startbin = (int)(middlebin + middlebin * (-shift_rate) * 2);
+    ddc->startbin = (int)(ddc->v * round(ddc->startbin / (float)ddc->v));
+    ddc->offsetbin = ddc->startbin - middlebin;
+    ddc->post_shift = (ddc->pre_decimation) * (shift_rate + ((float)ddc->offsetbin / ddc->fft_size));
+    ddc->pre_shift = ddc->offsetbin / (float)ddc->fft_size;
+    ddc->dsadata = oracle_decimating_shift_addition_init(ddc->post_shift, ddc->post_decimation);
+    ddc->scrap = ddc->overlap_length / ddc->pre_decimation;
+    ddc->post_input_size = ddc->fft_inv_size - ddc->scrap;
+    return ddc->fft_size <= 2;
+}
+
+/* [ref fastddc.c:91-104] exchange the lower and upper halves (fftshift for even sizes). */
+void oracle_fft_swap_sides(ocf32 *io, int fft_size)
+{
+    int half = fft_size / 2;
+    for (int k = 0; k < half; k++) { ocf32 t = io[k]; io[k] = io[k + half]; io[k + half] = t; }
+}
+
+/* [ref csdr.c:2342-2351] */
+void oracle_fastddc_make_taps_fft(const oracle_fastddc_t *ddc, float shift_rate, int decimation, int window, ocf32 *taps_fft)
+{
+    ocf32 *taps = calloc((size_t)ddc->fft_size, sizeof(ocf32));
+    float half_bw = (float)(0.5 / decimation);
+    oracle_firdes_bandpass_c(taps, ddc->taps_length, (-shift_rate) - half_bw, (-shift_rate) + half_bw, window);
+    oracle_dft_c2c(taps, taps_fft, ddc->fft_size, 1);
+    oracle_fft_swap_sides(taps_fft, ddc->fft_size);
+    free(taps);
+}
+
+/* [ref fastddc.c:106-166] fold the (centre-swapped) wide spectrum times the filter response into
+ * fft_inv_size aliasing bins, scale, un-swap, inverse transform, scale, discard the scrap, then
+ * fine-shift and decimate in the time domain. */
+oracle_dshift_status_t oracle_fastddc_inv_cc(const ocf32 *spectrum, ocf32 *out, const oracle_fastddc_t *ddc,
+                                             const ocf32 *taps_fft, oracle_dshift_status_t st)
+{
+    int N = ddc->fft_size, M = ddc->fft_inv_size;
+    ocf32 *wide = malloc(sizeof(ocf32) * (size_t)N);
+    ocf32 *fold = calloc((size_t)M, sizeof(ocf32));
+    ocf32 *time = malloc(sizeof(ocf32) * (size_t)M);
+    memcpy(wide, spectrum, sizeof(ocf32) * (size_t)N);
+    oracle_fft_swap_sides(wide, N);
+    for (int b = 0; b < N; b++) {
+        int dst = (N + b - ddc->offsetbin + M / 2) % M;
+        fold[dst].i += wide[b].i * taps_fft[b].i - wide[b].q * taps_fft[b].q;
+        fold[dst].q += wide[b].i * taps_fft[b].q + wide[b].q * taps_fft[b].i;
+    }
+    for (int b = 0; b < M; b++) { fold[b].i /= (float)ddc->pre_decimation; fold[b].q /= (float)ddc->pre_decimation; }
+    oracle_fft_swap_sides(fold, M);
+    oracle_dft_c2c(fold, time, M, 0);
+    for (int b = 0; b < M; b++) { time[b].i /= (float)M; time[b].q /= (float)M; }
+    st = oracle_decimating_shift_addition_cc(time + ddc->scrap, out, ddc->post_input_size, ddc->dsadata,
+                                             ddc->post_decimation, st);
+    free(wide); free(fold); free(time);
+    return st;
+}

@@ -1,0 +1,467 @@
+"""ctypes front-ends for the two CPU checkers.  TEST INFRASTRUCTURE -- never imported by csdr_b200.
+
+* ``Oracle``  -> oracle/liboracle.so        our strict-IEEE C restatement (oracle.c)
+* ``Ref``     -> oracle/_ref/libcsdr_ref.so the unmodified reference compiled from /root/reference
+                                             (``make -C oracle ref``; travels to the GPU box as a binary)
+
+Both expose the same numpy-level API so a test can be parametrised over them.
+complex samples are numpy complex64 arrays (= interleaved float32 I,Q = reference ``complexf``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "liboracle.so"
+REF_SO = HERE / "_ref" / "libcsdr_ref.so"
+REF_CLI = HERE / "_ref" / "csdr_ref"
+
+WINDOWS = {"BOXCAR": 0, "BLACKMAN": 1, "HAMMING": 2}
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the checkers.  ``ref`` defaults to "only where /root/reference exists"."""
+    subprocess.run(["make", "-s", "-C", str(HERE), "oracle"], check=True)
+    if ref is None:
+        ref = Path(os.environ.get("CSDR_REFERENCE", "/root/reference")).is_dir()
+    if ref:
+        subprocess.run(["make", "-s", "-C", str(HERE), "ref"], check=True)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class _CF(C.Structure):
+    _fields_ = [("i", C.c_float), ("q", C.c_float)]
+
+
+class _Shift(C.Structure):
+    _fields_ = [("sindelta", C.c_float), ("cosdelta", C.c_float), ("rate", C.c_float)]
+
+
+class _DShiftStatus(C.Structure):
+    _fields_ = [("decimation_remain", C.c_int), ("starting_phase", C.c_float), ("output_size", C.c_int)]
+
+
+def _c64(a):
+    a = np.ascontiguousarray(a, dtype=np.complex64)
+    return a
+
+
+# ======================================================================================================
+class Oracle:
+    """Binding of oracle/liboracle.so (see oracle.h)."""
+
+    name = "oracle"
+
+    class _FracDec(C.Structure):
+        _fields_ = [("where", C.c_float), ("input_processed", C.c_int), ("output_size", C.c_int),
+                    ("num_poly_points", C.c_int), ("xifirst", C.c_int), ("xilast", C.c_int),
+                    ("rate", C.c_float), ("denom", C.c_float * 64),
+                    ("taps", C.POINTER(C.c_float)), ("taps_length", C.c_int)]
+
+    class _Agc(C.Structure):
+        _fields_ = [("peak_1", C.c_float), ("peak_2", C.c_float), ("reference", C.c_float),
+                    ("last_gain", C.c_float), ("block", C.c_int)]
+
+    class _Ddc(C.Structure):
+        _fields_ = [(n, C.c_int) for n in ("pre_decimation", "post_decimation", "taps_length", "taps_min_length",
+                                           "overlap_length", "fft_size", "fft_inv_size", "input_size",
+                                           "post_input_size")] + \
+                   [("pre_shift", C.c_float), ("startbin", C.c_int), ("v", C.c_int), ("offsetbin", C.c_int),
+                    ("post_shift", C.c_float), ("scrap", C.c_int), ("dsadata", _Shift)]
+
+    def __init__(self, path: Path = ORACLE_SO):
+        if not path.exists():
+            build(ref=False)
+        L = self.L = C.CDLL(str(path))
+        L.oracle_firdes_filter_len.argtypes = [C.c_float]
+        L.oracle_window.argtypes = [C.c_int, C.c_float]; L.oracle_window.restype = C.c_float
+        L.oracle_firdes_lowpass_f.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int]
+        L.oracle_firdes_bandpass_c.argtypes = [C.POINTER(_CF), C.c_int, C.c_float, C.c_float, C.c_int]
+        L.oracle_shift_addition_init.argtypes = [C.c_float]; L.oracle_shift_addition_init.restype = _Shift
+        L.oracle_shift_addition_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, _Shift, C.c_float]
+        L.oracle_shift_addition_cc.restype = C.c_float
+        L.oracle_decimating_shift_addition_init.argtypes = [C.c_float, C.c_int]
+        L.oracle_decimating_shift_addition_init.restype = _Shift
+        L.oracle_decimating_shift_addition_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, _Shift, C.c_int, _DShiftStatus]
+        L.oracle_decimating_shift_addition_cc.restype = _DShiftStatus
+        L.oracle_fir_decimate_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.oracle_fmdemod_quadri_cf.argtypes = [C.POINTER(_CF), C.POINTER(C.c_float), C.c_int, _CF]
+        L.oracle_fmdemod_quadri_cf.restype = _CF
+        L.oracle_fractional_decimator_ff_init.argtypes = [C.POINTER(self._FracDec), C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.oracle_fractional_decimator_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(self._FracDec)]
+        L.oracle_fastagc_ff.argtypes = [C.POINTER(self._Agc)] + [C.POINTER(C.c_float)] * 4
+        L.oracle_dft_c2c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int]
+        L.oracle_apply_fir_fft_cc.argtypes = [C.POINTER(_CF)] * 3 + [C.c_int, C.POINTER(_CF), C.c_int]
+        L.oracle_fastddc_init.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_float]
+        L.oracle_fastddc_make_taps_fft.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_int, C.POINTER(_CF)]
+        L.oracle_fastddc_inv_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.POINTER(self._Ddc), C.POINTER(_CF), _DShiftStatus]
+        L.oracle_fastddc_inv_cc.restype = _DShiftStatus
+
+    # ---- conversions
+    def convert_u8_f(self, x):
+        x = np.ascontiguousarray(x, np.uint8); y = np.empty(x.size, np.float32)
+        self.L.oracle_convert_u8_f(_p(x, C.c_ubyte), _p(y, C.c_float), x.size); return y
+
+    def convert_s16_f(self, x):
+        x = np.ascontiguousarray(x, np.int16); y = np.empty(x.size, np.float32)
+        self.L.oracle_convert_s16_f(_p(x, C.c_short), _p(y, C.c_float), x.size); return y
+
+    def convert_f_s16(self, x):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty(x.size, np.int16)
+        self.L.oracle_convert_f_s16(_p(x, C.c_float), _p(y, C.c_short), x.size); return y
+
+    # ---- filter design
+    def firdes_filter_len(self, bw): return int(self.L.oracle_firdes_filter_len(bw))
+
+    def firdes_lowpass_f(self, length, cutoff, window="HAMMING"):
+        t = np.empty(length, np.float32)
+        self.L.oracle_firdes_lowpass_f(_p(t, C.c_float), length, cutoff, WINDOWS[window]); return t
+
+    def firdes_bandpass_c(self, length, lo, hi, window="HAMMING"):
+        t = np.empty(length, np.complex64)
+        self.L.oracle_firdes_bandpass_c(_p(t, _CF), length, lo, hi, WINDOWS[window]); return t
+
+    # ---- shift
+    def shift_addition_init(self, rate):
+        d = self.L.oracle_shift_addition_init(rate); return (d.sindelta, d.cosdelta, d.rate)
+
+    def shift_addition_cc(self, x, rate, phase=0.0, chunk=None):
+        """Returns (y, final_phase).  ``chunk`` reproduces the CLI's <=1024-sample sub-calls (csdr.c:911-918)."""
+        x = _c64(x); y = np.empty_like(x); d = self.L.oracle_shift_addition_init(rate)
+        chunk = chunk or max(x.size, 1)
+        for s in range(0, x.size, chunk):
+            n = min(chunk, x.size - s)
+            phase = self.L.oracle_shift_addition_cc(_p(x[s:], _CF), _p(y[s:], _CF), n, d, phase)
+        return y, float(np.float32(phase))
+
+    def decimating_shift_addition_cc(self, x, rate, decimation, remain=0, phase=0.0):
+        x = _c64(x); y = np.empty(x.size // decimation + 2, np.complex64)
+        d = self.L.oracle_decimating_shift_addition_init(rate, decimation)
+        st = self.L.oracle_decimating_shift_addition_cc(_p(x, _CF), _p(y, _CF), x.size, d, decimation,
+                                                        _DShiftStatus(remain, phase, 0))
+        return y[:st.output_size].copy(), (st.decimation_remain, st.starting_phase)
+
+    # ---- FIR
+    def fir_decimate_cc(self, x, decimation, taps):
+        x = _c64(x); taps = np.ascontiguousarray(taps, np.float32)
+        y = np.empty(max(x.size // decimation + 1, 1), np.complex64)
+        n = self.L.oracle_fir_decimate_cc(_p(x, _CF), _p(y, _CF), x.size, decimation, _p(taps, C.c_float), taps.size)
+        return y[:n].copy()
+
+    # ---- fmdemod
+    def fmdemod_quadri_cf(self, x, last=0j):
+        x = _c64(x); y = np.empty(x.size, np.float32)
+        r = self.L.oracle_fmdemod_quadri_cf(_p(x, _CF), _p(y, C.c_float), x.size, _CF(np.float32(last.real), np.float32(last.imag)))
+        return y, complex(r.i, r.q)
+
+    # ---- fractional decimator (streamed block by block like csdr.c:1510-1522 when block is given)
+    def fractional_decimator_ff(self, x, rate, num_poly_points=12, taps=None, block=None):
+        x = np.ascontiguousarray(x, np.float32)
+        tp = np.ascontiguousarray(taps, np.float32) if taps is not None else None
+        d = self._FracDec()
+        self.L.oracle_fractional_decimator_ff_init(C.byref(d), rate, num_poly_points,
+                                                   _p(tp, C.c_float) if tp is not None else None,
+                                                   tp.size if tp is not None else 0)
+        return _stream_fracdec(lambda buf, out, n: self.L.oracle_fractional_decimator_ff(_p(buf, C.c_float), _p(out, C.c_float), n, C.byref(d)),
+                               d, x, block)
+
+    # ---- fastagc (streamed)
+    def fastagc_ff(self, x, block=1024, reference=1.0):
+        x = np.ascontiguousarray(x, np.float32); nblk = x.size // block
+        st = self._Agc(0, 0, reference, 0, block)
+        h1 = np.zeros(block, np.float32); h2 = np.zeros(block, np.float32); y = np.empty(nblk * block, np.float32)
+        for b in range(nblk):
+            self.L.oracle_fastagc_ff(C.byref(st), _p(h1, C.c_float), _p(h2, C.c_float),
+                                     _p(x[b * block:], C.c_float), _p(y[b * block:], C.c_float))
+        return y
+
+    # ---- FFT family
+    def dft(self, x, forward=True):
+        x = _c64(x); y = np.empty_like(x)
+        self.L.oracle_dft_c2c(_p(x, _CF), _p(y, _CF), x.size, 1 if forward else 0); return y
+
+    def bandpass_fir_fft_cc(self, x, lo, hi, bw, window="HAMMING"):
+        """Whole-stream overlap-add exactly as the CLI loop csdr.c:1833-1883 (complete blocks only)."""
+        x = _c64(x)
+        T = self.firdes_filter_len(bw); N = next_pow2(T)
+        if N - T < 200: N <<= 1
+        isz = N - T + 1; ov = T - 1
+        taps = np.zeros(N, np.complex64); taps[:T] = self.firdes_bandpass_c(T, lo, hi, window)
+        taps_fft = self.dft(taps)
+        prev = np.zeros(N, np.complex64); out = []
+        for b in range(x.size // isz):
+            buf = np.zeros(N, np.complex64); buf[:isz] = x[b * isz:(b + 1) * isz]
+            res = np.empty(N, np.complex64); tail = np.ascontiguousarray(prev[isz:])
+            self.L.oracle_apply_fir_fft_cc(_p(buf, _CF), _p(taps_fft, _CF), _p(tail, _CF), ov, _p(res, _CF), N)
+            out.append(res[:isz].copy()); prev = res
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+    def fastddc_init(self, bw, decimation, shift):
+        d = self._Ddc()
+        err = self.L.oracle_fastddc_init(C.byref(d), bw, decimation, shift)
+        return d, err
+
+    def fastddc_geometry(self, bw, decimation, shift):
+        d, _ = self.fastddc_init(bw, decimation, shift)
+        return {n: getattr(d, n) for n, _t in d._fields_ if n != "dsadata"}
+
+    def fastddc_fwd(self, x, ddc):
+        """csdr.c:2288-2299: slide overlap, append input_size new samples, FFT, emit all bins (complete blocks)."""
+        x = _c64(x); buf = np.zeros(ddc.fft_size, np.complex64); out = []
+        for b in range(x.size // ddc.input_size):
+            buf[:ddc.overlap_length] = buf[ddc.input_size:ddc.input_size + ddc.overlap_length].copy()
+            buf[ddc.overlap_length:] = x[b * ddc.input_size:(b + 1) * ddc.input_size]
+            out.append(self.dft(buf))
+        return out
+
+    def fastddc_inv(self, spectra, bw, decimation, shift, window="HAMMING"):
+        ddc, _ = self.fastddc_init(bw, decimation, shift)
+        tf = np.empty(ddc.fft_size, np.complex64)
+        self.L.oracle_fastddc_make_taps_fft(C.byref(ddc), shift, decimation, WINDOWS[window], _p(tf, _CF))
+        st = _DShiftStatus(0, 0.0, 0); out = []
+        for sp in spectra:
+            sp = _c64(sp); y = np.empty(ddc.post_input_size, np.complex64)
+            st = self.L.oracle_fastddc_inv_cc(_p(sp, _CF), _p(y, _CF), C.byref(ddc), _p(tf, _CF), st)
+            out.append(y[:st.output_size].copy())
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+
+def next_pow2(x: int) -> int:
+    for b in range(31):
+        if x < (1 << b):
+            return 1 << b
+    return -1
+
+
+def _stream_fracdec(call, d, x, block):
+    """Drive a fractional decimator over ``x``.  block=None: one call on the whole array.
+    Otherwise reproduce the CLI's re-feeding of the unconsumed tail (csdr.c:1510-1522), complete reads only."""
+    if block is None:
+        out = np.empty(int(x.size / max(d.rate, 1.0)) + 16, np.float32)
+        call(x, out, x.size)
+        return out[:d.output_size].copy()
+    buf = np.zeros(block, np.float32); outs = []; pos = 0
+    out = np.empty(block, np.float32)
+    while True:
+        if d.input_processed == 0:
+            need = block; keep = 0
+        else:
+            need = d.input_processed; keep = block - need
+            buf[:keep] = buf[need:].copy()
+        if pos + need > x.size:
+            break
+        buf[keep:] = x[pos:pos + need]; pos += need
+        if d.input_processed == 0:
+            d.input_processed = block
+        call(buf, out, block)
+        outs.append(out[:d.output_size].copy())
+    return np.concatenate(outs) if outs else np.zeros(0, np.float32)
+
+
+# ======================================================================================================
+class Ref:
+    """Binding of the compiled, unmodified reference library (libcsdr.h / libcsdr_gpl.h / fastddc.h ABI)."""
+
+    name = "reference"
+
+    class _FracDec(C.Structure):            # libcsdr.h:151-168
+        _fields_ = [("where", C.c_float), ("input_processed", C.c_int), ("output_size", C.c_int),
+                    ("num_poly_points", C.c_int), ("poly_precalc_denomiator", C.POINTER(C.c_float)),
+                    ("coeffs_buf", C.POINTER(C.c_float)), ("filtered_buf", C.POINTER(C.c_float)),
+                    ("xifirst", C.c_int), ("xilast", C.c_int), ("rate", C.c_float),
+                    ("taps", C.POINTER(C.c_float)), ("taps_length", C.c_int)]
+
+    class _Agc(C.Structure):                # libcsdr.h:118-128
+        _fields_ = [("buffer_1", C.POINTER(C.c_float)), ("buffer_2", C.POINTER(C.c_float)),
+                    ("buffer_input", C.POINTER(C.c_float)), ("peak_1", C.c_float), ("peak_2", C.c_float),
+                    ("input_size", C.c_int), ("reference", C.c_float), ("last_gain", C.c_float)]
+
+    class _Plan(C.Structure):               # fft_fftw.h:14-20
+        _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
+
+    class _Ddc(C.Structure):                # fastddc.h:5-24
+        _fields_ = [(n, C.c_int) for n in ("pre_decimation", "post_decimation", "taps_length", "taps_min_length",
+                                           "overlap_length", "fft_size", "fft_inv_size", "input_size",
+                                           "post_input_size")] + \
+                   [("pre_shift", C.c_float), ("startbin", C.c_int), ("v", C.c_int), ("offsetbin", C.c_int),
+                    ("post_shift", C.c_float), ("output_scrape", C.c_int), ("scrap", C.c_int), ("dsadata", _Shift)]
+
+    def __init__(self, path: Path = REF_SO):
+        if not path.exists():
+            raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
+        L = self.L = C.CDLL(str(path))
+        L.firdes_filter_len.argtypes = [C.c_float]
+        L.firdes_lowpass_f.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int]
+        L.firdes_bandpass_c.argtypes = [C.POINTER(_CF), C.c_int, C.c_float, C.c_float, C.c_int]
+        L.shift_addition_init.argtypes = [C.c_float]; L.shift_addition_init.restype = _Shift
+        L.shift_addition_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, _Shift, C.c_float]
+        L.shift_addition_cc.restype = C.c_float
+        L.decimating_shift_addition_init.argtypes = [C.c_float, C.c_int]; L.decimating_shift_addition_init.restype = _Shift
+        L.decimating_shift_addition_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, _Shift, C.c_int, _DShiftStatus]
+        L.decimating_shift_addition_cc.restype = _DShiftStatus
+        L.fir_decimate_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.fmdemod_quadri_cf.argtypes = [C.POINTER(_CF), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), _CF]
+        L.fmdemod_quadri_cf.restype = _CF
+        L.fractional_decimator_ff_init.argtypes = [C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int]
+        L.fractional_decimator_ff_init.restype = self._FracDec
+        L.fractional_decimator_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(self._FracDec)]
+        L.fastagc_ff.argtypes = [C.POINTER(self._Agc), C.POINTER(C.c_float)]
+        L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
+        L.fft_execute.argtypes = [C.POINTER(self._Plan)]
+        L.fft_destroy.argtypes = [C.POINTER(self._Plan)]
+        L.apply_fir_fft_cc.argtypes = [C.POINTER(self._Plan), C.POINTER(self._Plan), C.POINTER(_CF), C.POINTER(_CF), C.c_int]
+        L.fastddc_init.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_float]
+        L.fft_swap_sides.argtypes = [C.POINTER(_CF), C.c_int]
+        L.fastddc_inv_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.POINTER(self._Ddc), C.POINTER(self._Plan), C.POINTER(_CF), _DShiftStatus]
+        L.fastddc_inv_cc.restype = _DShiftStatus
+        L.next_pow2.argtypes = [C.c_int]
+
+    def convert_u8_f(self, x):
+        x = np.ascontiguousarray(x, np.uint8); y = np.empty(x.size, np.float32)
+        self.L.convert_u8_f(_p(x, C.c_ubyte), _p(y, C.c_float), x.size); return y
+
+    def convert_s16_f(self, x):
+        x = np.ascontiguousarray(x, np.int16); y = np.empty(x.size, np.float32)
+        self.L.convert_s16_f(_p(x, C.c_short), _p(y, C.c_float), x.size); return y
+
+    def convert_f_s16(self, x):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty(x.size, np.int16)
+        self.L.convert_f_s16(_p(x, C.c_float), _p(y, C.c_short), x.size); return y
+
+    def firdes_filter_len(self, bw): return int(self.L.firdes_filter_len(bw))
+
+    def firdes_lowpass_f(self, length, cutoff, window="HAMMING"):
+        t = np.empty(length, np.float32)
+        self.L.firdes_lowpass_f(_p(t, C.c_float), length, cutoff, WINDOWS[window]); return t
+
+    def firdes_bandpass_c(self, length, lo, hi, window="HAMMING"):
+        t = np.empty(length, np.complex64)
+        self.L.firdes_bandpass_c(_p(t, _CF), length, lo, hi, WINDOWS[window]); return t
+
+    def shift_addition_init(self, rate):
+        d = self.L.shift_addition_init(rate); return (d.sindelta, d.cosdelta, d.rate)
+
+    def shift_addition_cc(self, x, rate, phase=0.0, chunk=None):
+        x = _c64(x); y = np.empty_like(x); d = self.L.shift_addition_init(rate)
+        chunk = chunk or max(x.size, 1)
+        for s in range(0, x.size, chunk):
+            n = min(chunk, x.size - s)
+            phase = self.L.shift_addition_cc(_p(x[s:], _CF), _p(y[s:], _CF), n, d, phase)
+        return y, float(np.float32(phase))
+
+    def decimating_shift_addition_cc(self, x, rate, decimation, remain=0, phase=0.0):
+        x = _c64(x); y = np.empty(x.size // decimation + 2, np.complex64)
+        d = self.L.decimating_shift_addition_init(rate, decimation)
+        st = self.L.decimating_shift_addition_cc(_p(x, _CF), _p(y, _CF), x.size, d, decimation, _DShiftStatus(remain, phase, 0))
+        return y[:st.output_size].copy(), (st.decimation_remain, st.starting_phase)
+
+    def fir_decimate_cc(self, x, decimation, taps):
+        x = _c64(x); taps = np.ascontiguousarray(taps, np.float32)
+        y = np.empty(max(x.size // decimation + 1, 1), np.complex64)
+        n = self.L.fir_decimate_cc(_p(x, _CF), _p(y, _CF), x.size, decimation, _p(taps, C.c_float), taps.size)
+        return y[:n].copy()
+
+    def fmdemod_quadri_cf(self, x, last=0j):
+        x = _c64(x); y = np.empty(x.size, np.float32); tmp = np.empty(2 * x.size + 4, np.float32)
+        r = self.L.fmdemod_quadri_cf(_p(x, _CF), _p(y, C.c_float), x.size, _p(tmp, C.c_float),
+                                     _CF(np.float32(last.real), np.float32(last.imag)))
+        return y, complex(r.i, r.q)
+
+    def fractional_decimator_ff(self, x, rate, num_poly_points=12, taps=None, block=None):
+        x = np.ascontiguousarray(x, np.float32)
+        tp = np.ascontiguousarray(taps, np.float32) if taps is not None else None
+        self._keep = tp
+        d = self.L.fractional_decimator_ff_init(rate, num_poly_points, _p(tp, C.c_float) if tp is not None else None,
+                                                tp.size if tp is not None else 0)
+        return _stream_fracdec(lambda buf, out, n: self.L.fractional_decimator_ff(_p(buf, C.c_float), _p(out, C.c_float), n, C.byref(d)),
+                               d, x, block)
+
+    def fastagc_ff(self, x, block=1024, reference=1.0):
+        x = np.ascontiguousarray(x, np.float32); nblk = x.size // block
+        bufs = [np.zeros(block, np.float32) for _ in range(3)]
+        byaddr = {b.ctypes.data: b for b in bufs}
+        st = self._Agc(_p(bufs[0], C.c_float), _p(bufs[1], C.c_float), _p(bufs[2], C.c_float), 0, 0, block, reference, 0)
+        y = np.empty(nblk * block, np.float32)
+        for b in range(nblk):
+            byaddr[C.cast(st.buffer_input, C.c_void_p).value][:] = x[b * block:(b + 1) * block]
+            self.L.fastagc_ff(C.byref(st), _p(y[b * block:], C.c_float))
+        return y
+
+    def dft(self, x, forward=True):
+        x = _c64(x).copy(); y = np.empty_like(x)
+        pl = self.L.make_fft_c2c(x.size, x.ctypes.data, y.ctypes.data, 1 if forward else 0, 0)
+        self.L.fft_execute(pl); self.L.fft_destroy(pl); return y
+
+    def bandpass_fir_fft_cc(self, x, lo, hi, bw, window="HAMMING"):
+        x = _c64(x)
+        T = self.firdes_filter_len(bw); N = int(self.L.next_pow2(T))
+        if N - T < 200: N <<= 1
+        isz = N - T + 1; ov = T - 1
+        taps = np.zeros(N, np.complex64); taps[:T] = self.firdes_bandpass_c(T, lo, hi, window)
+        taps_fft = self.dft(taps)
+        inp = np.zeros(N, np.complex64); spec = np.empty(N, np.complex64); ospec = np.empty(N, np.complex64)
+        o = [np.zeros(N, np.complex64), np.zeros(N, np.complex64)]
+        pf = self.L.make_fft_c2c(N, inp.ctypes.data, spec.ctypes.data, 1, 0)
+        pi = [self.L.make_fft_c2c(N, ospec.ctypes.data, o[k].ctypes.data, 0, 0) for k in range(2)]
+        out = []
+        for b in range(x.size // isz):
+            inp[:isz] = x[b * isz:(b + 1) * isz]
+            cur, prev = (1, 0) if b & 1 else (0, 1)
+            tail = o[prev][isz:]
+            self.L.apply_fir_fft_cc(pf, pi[cur], _p(taps_fft, _CF), C.cast(tail.ctypes.data, C.POINTER(_CF)), ov)
+            out.append(o[cur][:isz].copy())
+        self.L.fft_destroy(pf); [self.L.fft_destroy(p) for p in pi]
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+    def fastddc_init(self, bw, decimation, shift):
+        d = self._Ddc()
+        err = self.L.fastddc_init(C.byref(d), bw, decimation, shift)
+        return d, err
+
+    def fastddc_geometry(self, bw, decimation, shift):
+        d, _ = self.fastddc_init(bw, decimation, shift)
+        return {n: getattr(d, n) for n, _t in d._fields_ if n not in ("dsadata", "output_scrape")}
+
+    def fastddc_fwd(self, x, ddc):
+        x = _c64(x); buf = np.zeros(ddc.fft_size, np.complex64); out = []
+        for b in range(x.size // ddc.input_size):
+            buf[:ddc.overlap_length] = buf[ddc.input_size:ddc.input_size + ddc.overlap_length].copy()
+            buf[ddc.overlap_length:] = x[b * ddc.input_size:(b + 1) * ddc.input_size]
+            out.append(self.dft(buf))
+        return out
+
+    def fastddc_inv(self, spectra, bw, decimation, shift, window="HAMMING"):
+        ddc, _ = self.fastddc_init(bw, decimation, shift)
+        taps = np.zeros(ddc.fft_size, np.complex64)
+        hb = np.float32(0.5 / decimation); sh = np.float32(shift)
+        taps[:ddc.taps_length] = self.firdes_bandpass_c(ddc.taps_length, float(-sh - hb), float(-sh + hb), window)
+        tf = self.dft(taps); self.L.fft_swap_sides(_p(tf, _CF), ddc.fft_size)
+        ii = np.zeros(ddc.fft_inv_size, np.complex64); io = np.zeros(ddc.fft_inv_size, np.complex64)
+        pl = self.L.make_fft_c2c(ddc.fft_inv_size, ii.ctypes.data, io.ctypes.data, 0, 0)
+        st = _DShiftStatus(0, 0.0, 0); out = []
+        for sp in spectra:
+            sp = _c64(sp).copy(); y = np.empty(ddc.post_input_size, np.complex64)
+            st = self.L.fastddc_inv_cc(_p(sp, _CF), _p(y, _CF), C.byref(ddc), pl, _p(tf, _CF), st)
+            out.append(y[:st.output_size].copy())
+        self.L.fft_destroy(pl)
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+
+def have_ref() -> bool:
+    return REF_SO.exists()
+
+
+def rel_rms(y, ref) -> float:
+    """sqrt(sum|y-ref|^2 / sum|ref|^2) -- the parity metric of SURVEY.md section 8(d)."""
+    y = np.asarray(y); ref = np.asarray(ref)
+    den = float(np.sum(np.abs(ref.astype(np.complex128)) ** 2))
+    num = float(np.sum(np.abs(y.astype(np.complex128) - ref.astype(np.complex128)) ** 2))
+    return (num / den) ** 0.5 if den > 0 else (0.0 if num == 0 else float("inf"))

@@ -1,0 +1,167 @@
+"""CPU tests: the oracle restatement (oracle/oracle.c) against
+  (1) the committed golden vectors produced by the compiled reference (tests/golden/make_golden.py), and
+  (2) the compiled reference itself (oracle/_ref) on larger seeded inputs, when it is present.
+
+Tolerances: bit-exact where the reference build performs the same IEEE operations (conversions, NCO
+recursion, fmdemod, fractional decimator, fastagc, geometry); <= 1e-6 relative RMS where the
+reference's -ffast-math build may re-associate sums or swap libm calls (FIR sums, tap design, FFT).
+The north-star tolerance for float blocks is 1e-5 relative RMS.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle.pyoracle import rel_rms
+
+GOLD = np.load(Path(__file__).parent / "golden" / "hotpath_golden.npz")
+TIGHT = 1e-6
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_golden_conversions_bit_exact(oracle):
+    assert np.array_equal(oracle.convert_u8_f(GOLD["u8_in"]), GOLD["u8_out"])
+    assert np.array_equal(oracle.convert_s16_f(GOLD["s16_in"]), GOLD["s16_out"])
+    assert np.array_equal(oracle.convert_f_s16(GOLD["f_in"]), GOLD["f_s16_out"])
+    # the known answers SURVEY 8(a) quotes
+    t = oracle.convert_u8_f(np.array([0, 127, 128, 255], np.uint8))
+    assert t[0] == -1.0 and t[3] == 1.0 and t[1] == np.float32(-0.00392156886) and t[2] == np.float32(0.00392156886)
+    assert list(oracle.convert_f_s16(np.array([-1, 0.25, 1.5, 2.0], np.float32))) == [-32767, 8191, -16386, -2]
+
+
+def test_golden_filter_design(oracle):
+    lens = [oracle.firdes_filter_len(float(b)) for b in GOLD["filter_len_bw"]]
+    assert lens == list(GOLD["filter_len"])
+    assert lens[:5] == [79, 199, 201, 801, 1999]
+    assert rel_rms(oracle.firdes_lowpass_f(79, 0.05), GOLD["lowpass_79"]) < TIGHT
+    assert rel_rms(oracle.firdes_lowpass_f(199, 0.05), GOLD["lowpass_199"]) < TIGHT
+    assert rel_rms(oracle.firdes_lowpass_f(101, 0.1, "BLACKMAN"), GOLD["lowpass_101_blackman"]) < TIGHT
+    assert rel_rms(oracle.firdes_bandpass_c(79, 0.1, 0.3), GOLD["bandpass_79"]) < TIGHT
+    t = oracle.firdes_lowpass_f(199, 0.05)
+    assert np.array_equal(t, t[::-1]) and abs(float(t.sum()) - 1.0) < 1e-6
+
+
+def test_golden_shift(oracle):
+    y, ph = oracle.shift_addition_cc(GOLD["shift_in"], -0.085, 0.0, 1024)
+    assert rel_rms(y, GOLD["shift_out_chunk1024"]) < 1e-7 and np.float32(ph) == GOLD["shift_phase_chunk1024"]
+    y, ph = oracle.shift_addition_cc(GOLD["shift_in"], 0.2, 0.3, None)
+    assert rel_rms(y, GOLD["shift_out_whole"]) < 1e-7 and np.float32(ph) == GOLD["shift_phase_whole"]
+    y, st = oracle.decimating_shift_addition_cc(GOLD["shift_in"][:448], 0.01, 2, 1, 0.5)
+    assert rel_rms(y, GOLD["dshift_out"]) < 1e-7
+    assert st[0] == int(GOLD["dshift_state"][0]) and np.float32(st[1]) == np.float32(GOLD["dshift_state"][1])
+
+
+def test_golden_fir(oracle):
+    for key, d, taps in (("fir_out_79_d10", 10, "lowpass_79"), ("fir_out_199_d10", 10, "lowpass_199")):
+        y = oracle.fir_decimate_cc(GOLD["fir_in"], d, GOLD[taps])
+        assert y.size == GOLD[key].size and rel_rms(y, GOLD[key]) < TIGHT
+    y = oracle.fir_decimate_cc(GOLD["fir_in"][:1000], 7, GOLD["lowpass_79"])
+    assert y.size == GOLD["fir_out_79_d7"].size == (1000 - 79) // 7 + 1
+    assert rel_rms(y, GOLD["fir_out_79_d7"]) < TIGHT
+
+
+def test_golden_fmdemod(oracle):
+    y, last = oracle.fmdemod_quadri_cf(GOLD["fm_in"], 0.25 - 0.5j)
+    assert np.array_equal(y, GOLD["fm_out"]) and np.complex64(last) == GOLD["fm_last"]
+
+
+def test_golden_fractional_decimator(oracle):
+    y = oracle.fractional_decimator_ff(GOLD["fd_in"], 5.0, 12, None, 1024)
+    assert y.size == GOLD["fd_out_r5_blk1024"].size and rel_rms(y, GOLD["fd_out_r5_blk1024"]) < TIGHT
+    y = oracle.fractional_decimator_ff(GOLD["fd_in"], 2.7183, 12, None, None)
+    assert y.size == GOLD["fd_out_r2p7_whole"].size and rel_rms(y, GOLD["fd_out_r2p7_whole"]) < TIGHT
+    y = oracle.fractional_decimator_ff(GOLD["fd_in"][:3000], 3.0, 4, oracle.firdes_lowpass_f(31, 0.15), None)
+    assert y.size == GOLD["fd_out_r3_pts4_prefilter"].size and rel_rms(y, GOLD["fd_out_r3_pts4_prefilter"]) < TIGHT
+
+
+def test_golden_fastagc(oracle):
+    assert rel_rms(oracle.fastagc_ff(GOLD["agc_in"], 256, 1.0), GOLD["agc_out_b256"]) < 1e-7
+    assert rel_rms(oracle.fastagc_ff(GOLD["agc_in"], 512, 0.5), GOLD["agc_out_b512_ref0p5"]) < 1e-7
+    y = oracle.fastagc_ff(GOLD["agc_in"], 256, 1.0)
+    assert not y[:512].any()                     # two blocks of latency: calloc'ed history (csdr.c:1394-1395)
+
+
+def test_golden_bandpass_fir_fft(oracle):
+    y = oracle.bandpass_fir_fft_cc(GOLD["bp_in"], -0.1, 0.2, 0.05)
+    assert y.size == GOLD["bp_out"].size == (GOLD["bp_in"].size // 178) * 178 and   # 79 taps -> fft 256, 178 per block
+    rel_rms(y, GOLD["bp_out"]) < 2e-6
+
+
+def test_golden_fastddc(oracle):
+    keys = [str(k) for k in GOLD["ddc_keys"]]
+    for case, row in zip(GOLD["ddc_cases"], GOLD["ddc_geometry"]):
+        geo = oracle.fastddc_geometry(float(case[0]), int(case[1]), float(case[2]))
+        for k, v in zip(keys, row):
+            assert np.float32(geo[k]) == np.float32(v), (case, k, geo[k], v)
+    geo = oracle.fastddc_geometry(0.002, 64, 0.1)   # BASELINE config 3 geometry quoted in SURVEY 8(a) a11
+    assert (geo["fft_size"], geo["taps_length"], geo["input_size"], geo["pre_decimation"], geo["post_decimation"],
+            geo["fft_inv_size"], geo["scrap"], geo["post_input_size"], geo["v"]) == (16384, 2049, 14336, 32, 2, 512, 64, 448, 8)
+    ddc, err = oracle.fastddc_init(0.05, 8, 0.123)
+    assert not err
+    spectra = oracle.fastddc_fwd(GOLD["ddc_in"], ddc)
+    assert rel_rms(np.stack(spectra), GOLD["ddc_fwd_out"]) < TIGHT
+    y = oracle.fastddc_inv(list(GOLD["ddc_fwd_out"]), 0.05, 8, 0.123)
+    assert y.size == GOLD["ddc_inv_out"].size and rel_rms(y, GOLD["ddc_inv_out"]) < 2e-6
+
+
+# ------------------------------------------------------------------ the compiled reference, larger inputs
+def _cplx(rng, n):
+    return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+
+
+def test_ref_conversions_all_codes(oracle, ref):
+    u8 = np.arange(256, dtype=np.uint8)
+    s16 = np.arange(-32768, 32768).astype(np.int16)
+    f = np.random.default_rng(3).uniform(-1, 1, 1 << 18).astype(np.float32)
+    assert np.array_equal(oracle.convert_u8_f(u8), ref.convert_u8_f(u8))
+    assert np.array_equal(oracle.convert_s16_f(s16), ref.convert_s16_f(s16))
+    assert np.array_equal(oracle.convert_f_s16(f), ref.convert_f_s16(f))
+
+
+@pytest.mark.parametrize("T,D,bw", [(79, 10, 0.05), (199, 10, 0.0201), (801, 50, 0.005)])
+def test_ref_fir_decimate(oracle, ref, T, D, bw):
+    assert oracle.firdes_filter_len(bw) == ref.firdes_filter_len(bw) == T
+    taps = ref.firdes_lowpass_f(T, 0.5 / D)
+    assert rel_rms(oracle.firdes_lowpass_f(T, 0.5 / D), taps) < TIGHT
+    x = _cplx(np.random.default_rng(T), 262144)
+    ya, yb = oracle.fir_decimate_cc(x, D, taps), ref.fir_decimate_cc(x, D, taps)
+    assert ya.size == yb.size == (x.size - T) // D + 1
+    assert rel_rms(ya, yb) < TIGHT
+
+
+@pytest.mark.parametrize("rate,chunk", [(-0.085, 1024), (0.2, 1024), (0.4999, 1024), (0.01, 16384), (-0.3, None)])
+def test_ref_shift_addition(oracle, ref, rate, chunk):
+    x = _cplx(np.random.default_rng(7), 1 << 17)
+    ya, pa = oracle.shift_addition_cc(x, rate, 0.0, chunk)
+    yb, pb = ref.shift_addition_cc(x, rate, 0.0, chunk)
+    assert np.float32(pa) == np.float32(pb)
+    assert rel_rms(ya, yb) < 1e-7            # identical recursion; only the seed cos/sin may differ by an ulp
+
+
+def test_ref_fmdemod_fracdec_agc(oracle, ref):
+    rng = np.random.default_rng(11)
+    t = np.arange(1 << 16)
+    fm = np.exp(1j * np.cumsum(0.4 * np.sin(2 * np.pi * t / 300))).astype(np.complex64)
+    ya, la = oracle.fmdemod_quadri_cf(fm); yb, lb = ref.fmdemod_quadri_cf(fm)
+    assert np.array_equal(ya, yb) and la == lb
+    aud = rng.uniform(-1, 1, 1 << 16).astype(np.float32)
+    for rate, blk in ((5.0, 1024), (5.0, None), (1.5, 1024), (48.0 / 44.1, 4096)):
+        ya = oracle.fractional_decimator_ff(aud, rate, 12, None, blk); yb = ref.fractional_decimator_ff(aud, rate, 12, None, blk)
+        assert ya.size == yb.size and rel_rms(ya, yb) < TIGHT, (rate, blk)
+    for block, refl in ((1024, 1.0), (100, 0.3)):
+        ya = oracle.fastagc_ff(aud * 0.05, block, refl); yb = ref.fastagc_ff(aud * 0.05, block, refl)
+        assert rel_rms(ya, yb) < 1e-7
+
+
+def test_ref_fft_paths(oracle, ref):
+    rng = np.random.default_rng(13)
+    x = _cplx(rng, 2098 * 4)
+    ya = oracle.bandpass_fir_fft_cc(x, -0.05, 0.05, 0.002); yb = ref.bandpass_fir_fft_cc(x, -0.05, 0.05, 0.002)
+    assert ya.size == yb.size == 2098 * 4 and rel_rms(ya, yb) < 2e-6
+    ddc, _ = oracle.fastddc_init(0.002, 64, -0.2)
+    xs = _cplx(rng, ddc.input_size * 2)
+    rd, _ = ref.fastddc_init(0.002, 64, -0.2)
+    sa, sb = oracle.fastddc_fwd(xs, ddc), ref.fastddc_fwd(xs, rd)
+    assert rel_rms(np.stack(sa), np.stack(sb)) < TIGHT
+    ya = oracle.fastddc_inv(sa, 0.002, 64, -0.2); yb = ref.fastddc_inv(sb, 0.002, 64, -0.2)
+    assert ya.size == yb.size == 2 * 224 and rel_rms(ya, yb) < 2e-6
