@@ -83,8 +83,8 @@ def test_golden_fastagc(oracle):
 
 def test_golden_bandpass_fir_fft(oracle):
     y = oracle.bandpass_fir_fft_cc(GOLD["bp_in"], -0.1, 0.2, 0.05)
-    assert y.size == GOLD["bp_out"].size == (GOLD["bp_in"].size // 178) * 178 and   # 79 taps -> fft 256, 178 per block
-    rel_rms(y, GOLD["bp_out"]) < 2e-6
+    assert y.size == GOLD["bp_out"].size == (GOLD["bp_in"].size // 178) * 178     # 79 taps -> fft 256, 178 per block
+    assert rel_rms(y, GOLD["bp_out"]) < 2e-6
 
 
 def test_golden_fastddc(oracle):
