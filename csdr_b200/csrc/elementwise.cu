@@ -1,0 +1,191 @@
+// elementwise.cu -- K1 sample-format conversions and K4 fmdemod_quadri_cf.
+//
+// K1 replaces convert_u8_f / convert_s16_f / convert_f_s16 (libcsdr.c:2363-2366, 2373-2376, 2390-2398).
+// K4 replaces fmdemod_quadri_cf (libcsdr.c:1040-1071) for C channels per launch.
+// All are pure streaming kernels: 128-bit global accesses, grid-stride, nothing staged.
+#include "common.cuh"
+#include "kernels.h"
+#include <limits.h>
+
+namespace csdrb {
+
+// u8 -> f32.  The reference computes ((float)b)/(UCHAR_MAX/2.0) - 1.0 in double and rounds once;
+// there are only 256 inputs, so a table built with exactly that expression is bit-exact by construction.
+__constant__ float c_u8_lut[256];
+static bool g_lut_ready = false;
+
+static int ensure_u8_lut(cudaStream_t st)
+{
+    if (g_lut_ready) return 0;
+    float h[256];
+    for (int b = 0; b < 256; b++) h[b] = (float)(((double)(float)b) / (UCHAR_MAX / 2.0) - 1.0);
+    CSDRB_CUDA(cudaMemcpyToSymbolAsync(c_u8_lut, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
+    CSDRB_CUDA(cudaStreamSynchronize(st));
+    g_lut_ready = true;
+    return 0;
+}
+
+__device__ __forceinline__ float u8_to_f(unsigned b)
+{
+    // same value as the table; computed in double exactly like the reference expression
+    return (float)((double)b / 127.5 - 1.0);
+}
+
+__global__ void __launch_bounds__(256) convert_u8_f_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long n)
+{
+    __shared__ float lut[256];
+    lut[threadIdx.x] = c_u8_lut[threadIdx.x];
+    __syncthreads();
+    const long nvec = n / 16;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 q = reinterpret_cast<const uint4*>(in)[v];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        float4* o = reinterpret_cast<float4*>(out) + v * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            st_na_f4(o + k, make_float4(lut[w[k] & 255u], lut[(w[k] >> 8) & 255u], lut[(w[k] >> 16) & 255u], lut[w[k] >> 24]));
+    }
+    for (long i = nvec * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = lut[in[i]];
+}
+
+__global__ void __launch_bounds__(256) convert_s16_f_kernel(const short* __restrict__ in, float* __restrict__ out, long n)
+{
+    // reference build (-ffast-math) multiplies by the float-rounded reciprocal of SHRT_MAX; see oracle.c
+    const float recip = 1.0f / 32767.0f;
+    const long nvec = n / 8;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const uint4 q = reinterpret_cast<const uint4*>(in)[v];
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            f[2 * k] = __fmul_rn((float)(short)(w[k] & 0xffffu), recip);
+            f[2 * k + 1] = __fmul_rn((float)(short)(w[k] >> 16), recip);
+        }
+        float4* o = reinterpret_cast<float4*>(out) + v * 2;
+        st_na_f4(o, make_float4(f[0], f[1], f[2], f[3]));
+        st_na_f4(o + 1, make_float4(f[4], f[5], f[6], f[7]));
+    }
+    for (long i = nvec * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn((float)in[i], recip);
+}
+
+// f32 -> s16: float multiply by 32767, truncate toward zero, keep the low 16 bits of the int32
+// (what cvttss2si + a 16-bit store do on the reference's x86 build; out-of-range/NaN -> INT_MIN -> 0).
+__device__ __forceinline__ unsigned f_to_s16_bits(float x)
+{
+    const float s = __fmul_rn(x, 32767.0f);
+    int w = (s >= 2147483648.0f || s < -2147483648.0f || s != s) ? INT_MIN : __float2int_rz(s);
+    return (unsigned)w & 0xffffu;
+}
+
+__global__ void __launch_bounds__(256) convert_f_s16_kernel(const float* __restrict__ in, short* __restrict__ out, long n)
+{
+    const long nvec = n / 8;
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const float4 a = reinterpret_cast<const float4*>(in)[2 * v], b = reinterpret_cast<const float4*>(in)[2 * v + 1];
+        uint4 q;
+        q.x = f_to_s16_bits(a.x) | (f_to_s16_bits(a.y) << 16);
+        q.y = f_to_s16_bits(a.z) | (f_to_s16_bits(a.w) << 16);
+        q.z = f_to_s16_bits(b.x) | (f_to_s16_bits(b.y) << 16);
+        q.w = f_to_s16_bits(b.z) | (f_to_s16_bits(b.w) << 16);
+        reinterpret_cast<uint4*>(out)[v] = q;
+    }
+    for (long i = nvec * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (short)f_to_s16_bits(in[i]);
+}
+
+static int grid_for(long work_items, int block)
+{
+    long g = (work_items + block - 1) / block;
+    const long cap = 148L * 16;                               // 16 resident CTAs of 256 threads per SM is plenty
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int launch_convert_u8_f(const unsigned char* d_in, float* d_out, long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("convert_u8_f: device buffers must be 16-byte aligned"); return -1; }
+    if (int rc = ensure_u8_lut(st)) return rc;
+    convert_u8_f_kernel<<<grid_for(n / 16 + 1, 256), 256, 0, st>>>(d_in, d_out, n);
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_convert_s16_f(const short* d_in, float* d_out, long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("convert_s16_f: device buffers must be 16-byte aligned"); return -1; }
+    convert_s16_f_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, st>>>(d_in, d_out, n);
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_convert_f_s16(const float* d_in, short* d_out, long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("convert_f_s16: device buffers must be 16-byte aligned"); return -1; }
+    convert_f_s16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, st>>>(d_in, d_out, n);
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---- K4 fmdemod_quadri_cf -------------------------------------------------------------------------
+// out[i] = den ? K*(I*(Q-Qprev) - Q*(I-Iprev))/den : 0 with den = I*I+Q*Q; no FMA contraction so that
+// every intermediate rounds like the reference's SSE code; the K*num/den tail is evaluated in double
+// exactly as the C expression promotes it (libcsdr.c:1065).
+#define FMDEMOD_K 0.340447550238101026565118445432744920253753662109375
+
+__device__ __forceinline__ float quadri(float2 cur, float2 prev)
+{
+    const float dq = __fsub_rn(cur.y, prev.y), di = __fsub_rn(cur.x, prev.x);
+    const float num = __fsub_rn(__fmul_rn(cur.x, dq), __fmul_rn(cur.y, di));
+    const float den = __fadd_rn(__fmul_rn(cur.x, cur.x), __fmul_rn(cur.y, cur.y));
+    return den != 0.f ? (float)(FMDEMOD_K * (double)num / (double)den) : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+fmdemod_quadri_bank_kernel(const float2* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride, int n,
+                           const float2* __restrict__ last_in, float2* __restrict__ last_out)
+{
+    const int ch = blockIdx.y;
+    const float2* x = in + (long)ch * in_stride;
+    float* y = out + (long)ch * out_stride;
+    const float2 carry = last_in ? last_in[ch] : make_float2(0.f, 0.f);
+    const int stride = gridDim.x * blockDim.x;
+    // two samples per thread per step: one 128-bit load + the previous sample
+    const int npair = n / 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec_ok) {
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < npair; v += stride) {
+            const float4 q = reinterpret_cast<const float4*>(x)[v];
+            const float2 a = make_float2(q.x, q.y), b = make_float2(q.z, q.w);
+            const float2 p = v ? x[2 * v - 1] : carry;
+            reinterpret_cast<float2*>(y)[v] = make_float2(quadri(a, p), quadri(b, a));   // y is 8-byte aligned when out_stride is even
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) y[n - 1] = quadri(x[n - 1], n > 1 ? x[n - 2] : carry);
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = quadri(x[i], i ? x[i - 1] : carry);
+    }
+    if (last_out && blockIdx.x == 0 && threadIdx.x == 0 && n > 0) last_out[ch] = x[n - 1];
+}
+
+int launch_fmdemod_quadri_bank(const float2* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
+                               const float2* d_last_in, float2* d_last_out, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_out) & 7) || (out_stride & 1) ) {
+        set_error("fmdemod_quadri bank: output must be 8-byte aligned with an even channel stride"); return -1;
+    }
+    if (d_last_in && d_last_out == d_last_in) {
+        // in-place carry update is fine: each channel's carry is read before the single writer thread stores it?  No:
+        // other blocks of the same channel may read it later.  Require distinct buffers.
+        set_error("fmdemod_quadri bank: last_in and last_out must not alias"); return -1;
+    }
+    int gx = (n / 2 + 255) / 256; if (gx < 1) gx = 1; if (gx > 64) gx = 64;
+    if (in_stride & 1) gx = gx;   // unaligned rows take the scalar branch inside the kernel
+    fmdemod_quadri_bank_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, d_last_in, d_last_out);
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace csdrb

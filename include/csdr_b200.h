@@ -1,0 +1,147 @@
+/*
+ * csdr_b200.h -- public C ABI of libcsdr_b200.so (B200 / sm_100a implementation of the csdr block-DSP hot path).
+ *
+ * Two layers, both plain C (System V x86-64, no C++ or torch types in any signature):
+ *
+ *   Part A  "libcsdr drop-in": the SAME names, argument meaning and return values as the reference
+ *           library for the hot-path functions, taking HOST pointers and behaving synchronously, so
+ *           the reference's own callers (csdr.c, test200.c) link against this library unchanged.
+ *           Each prototype cites the reference declaration it replaces (file:line in ha7ilm/csdr @6ef2a742).
+ *
+ *   Part B  "bank API" (csdrb_*): the device-resident many-channel entry points the reference can only
+ *           express as one process chain per channel (ddcd_old.h:51-61).  Pointers named d_* are DEVICE
+ *           pointers, h_* are host pointers; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ *           default stream).  Calls are asynchronous on that stream unless stated otherwise.
+ *
+ * Error model: Part A keeps the reference's (no error codes); a CUDA failure prints to stderr and
+ * aborts the process, which is the closest equivalent of the reference's behaviour on a fatal fault.
+ * Part B returns >= 0 on success (usually an output count) and a negative value on failure;
+ * csdrb_last_error() returns the message of the calling thread's last failure.
+ * There is NO CPU fallback anywhere: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef CSDR_B200_H
+#define CSDR_B200_H
+#include <stdio.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* =====================================================================================================
+ * Part A -- libcsdr drop-in surface
+ * =================================================================================================== */
+
+typedef struct complexf_s { float i; float q; } complexf;                        /* libcsdr.h:46 */
+typedef enum window_s { WINDOW_BOXCAR, WINDOW_BLACKMAN, WINDOW_HAMMING } window_t; /* libcsdr.h:70-75 */
+#define WINDOW_DEFAULT WINDOW_HAMMING                                             /* libcsdr.h:77 */
+
+/* filter design -- stays on the host, in C (libcsdr.h:85-92; libcsdr.c:57-174) */
+void  firdes_lowpass_f(float *output, int length, float cutoff_rate, window_t window);
+void  firdes_bandpass_c(complexf *output, int length, float lowcut, float highcut, window_t window);
+float firdes_wkernel_blackman(float input);
+float firdes_wkernel_hamming(float input);
+float firdes_wkernel_boxcar(float input);
+window_t firdes_get_window_from_string(char *input);
+char *firdes_get_string_from_window(window_t window);
+int   firdes_filter_len(float transition_bw);
+int   log2n(int x);                                                               /* libcsdr.h:209 */
+int   next_pow2(int x);                                                           /* libcsdr.h:210 */
+
+/* sample-format conversion (libcsdr.h:220-227; libcsdr.c:2363-2401) */
+void convert_u8_f(unsigned char *input, float *output, int input_size);
+void convert_s16_f(short *input, float *output, int input_size);
+void convert_i16_f(short *input, float *output, int input_size);
+void convert_f_s16(float *input, short *output, int input_size);
+void convert_f_i16(float *input, short *output, int input_size);
+
+/* NCO shift by phasor recursion (libcsdr_gpl.h:26-46; libcsdr_gpl.c:27-52, 81-89, 126-160) */
+typedef struct shift_addition_data_s { float sindelta; float cosdelta; float rate; } shift_addition_data_t;
+shift_addition_data_t shift_addition_init(float rate);
+float shift_addition_cc(complexf *input, complexf *output, int input_size, shift_addition_data_t d, float starting_phase);
+typedef struct decimating_shift_addition_status_s { int decimation_remain; float starting_phase; int output_size; } decimating_shift_addition_status_t;
+shift_addition_data_t decimating_shift_addition_init(float rate, int decimation);
+decimating_shift_addition_status_t decimating_shift_addition_cc(complexf *input, complexf *output, int input_size,
+        shift_addition_data_t d, int decimation, decimating_shift_addition_status_t s);
+
+/* decimating FIR (libcsdr.h:104; libcsdr.c:528-549): returns the number of outputs written */
+int fir_decimate_cc(complexf *input, complexf *output, int input_size, int decimation, float *taps, int taps_length);
+
+/* FM demodulator (libcsdr.h:95; libcsdr.c:1040-1071): `temp` is accepted and ignored */
+complexf fmdemod_quadri_cf(complexf *input, float *output, int input_size, float *temp, complexf last_sample);
+
+/* fractional decimator (libcsdr.h:151-170; libcsdr.c:715-793) */
+typedef struct fractional_decimator_ff_s {
+    float where; int input_processed; int output_size; int num_poly_points;
+    float *poly_precalc_denomiator; float *coeffs_buf; float *filtered_buf;
+    int xifirst; int xilast; float rate; float *taps; int taps_length;
+} fractional_decimator_ff_t;
+fractional_decimator_ff_t fractional_decimator_ff_init(float rate, int num_poly_points, float *taps, int taps_length);
+void fractional_decimator_ff(float *input, float *output, int input_size, fractional_decimator_ff_t *d);
+
+/* block AGC (libcsdr.h:118-130; libcsdr.c:944-991) */
+typedef struct fastagc_ff_s {
+    float *buffer_1; float *buffer_2; float *buffer_input;
+    float peak_1; float peak_2; int input_size; float reference; float last_gain;
+} fastagc_ff_t;
+void fastagc_ff(fastagc_ff_t *input, float *output);
+
+/* FFT abstraction (fft_fftw.h:10-27; fft_fftw.c:6-46).  Callers read ->size/->input/->output directly
+ * (libcsdr.c:822-835, fastddc.c:112-116), so the first three members keep the reference layout. */
+struct fft_plan_s { int size; void *input; void *output; void *plan; };
+#define FFT_PLAN_T struct fft_plan_s
+FFT_PLAN_T *make_fft_c2c(int size, complexf *input, complexf *output, int forward, int benchmark);
+void  fft_execute(FFT_PLAN_T *plan);
+void  fft_destroy(FFT_PLAN_T *plan);
+void *csdrb_fft_malloc(size_t bytes);            /* stands in for the fft_malloc macro (fft_fftw.h:11) */
+void  csdrb_fft_free(void *p);
+#define fft_malloc csdrb_fft_malloc
+#define fft_free   csdrb_fft_free
+
+/* overlap-add FFT filter step (libcsdr.h:211; libcsdr.c:814-849) */
+void apply_fir_fft_cc(FFT_PLAN_T *plan, FFT_PLAN_T *plan_inverse, complexf *taps_fft, complexf *last_overlap, int overlap_size);
+
+/* fastddc (fastddc.h:5-29; fastddc.c:38-166) */
+typedef struct fastddc_s {
+    int pre_decimation; int post_decimation; int taps_length; int taps_min_length; int overlap_length;
+    int fft_size; int fft_inv_size; int input_size; int post_input_size;
+    float pre_shift; int startbin; int v; int offsetbin; float post_shift; int output_scrape; int scrap;
+    shift_addition_data_t dsadata;
+} fastddc_t;
+int  fastddc_init(fastddc_t *ddc, float transition_bw, int decimation, float shift_rate);
+decimating_shift_addition_status_t fastddc_inv_cc(complexf *input, complexf *output, fastddc_t *ddc,
+        FFT_PLAN_T *plan_inverse, complexf *taps_fft, decimating_shift_addition_status_t shift_stat);
+void fastddc_print(fastddc_t *ddc, char *source);
+void fft_swap_sides(complexf *io, int fft_size);
+
+/* =====================================================================================================
+ * Part B -- device-resident bank API
+ * =================================================================================================== */
+
+const char *csdrb_last_error(void);
+const char *csdrb_version(void);
+int  csdrb_device_count(void);                   /* < 0 when the CUDA runtime cannot be initialised */
+int  csdrb_set_device(int device);
+int  csdrb_stream_synchronize(void *stream);
+long csdrb_kernel_launches(void);                /* kernels this library has launched so far (per process) */
+
+/* K1 conversions on device buffers (16-byte aligned) */
+int csdrb_convert_u8_f(const unsigned char *d_in, float *d_out, long n, void *stream);
+int csdrb_convert_s16_f(const short *d_in, float *d_out, long n, void *stream);
+int csdrb_convert_f_s16(const float *d_in, short *d_out, long n, void *stream);
+
+/* K3 fir_decimate_cc bank: channel c reads d_in + c*in_stride (input_size samples) and writes
+ * d_out + c*out_stride; all channels share h_taps (HOST pointer, copied into the launch).
+ * Returns outputs per channel = input_size >= T ? (input_size - T)/D + 1 : 0  (reference libcsdr.c:537-547).
+ * `variant` < 0 lets the library choose the tiling; >= 0 forces one (bench/tuning only). */
+int csdrb_fir_decimate_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels,
+                               int input_size, int decimation, const float *h_taps, int taps_length, int variant, void *stream);
+int csdrb_fir_bank_variants(void);
+
+/* K4 fmdemod_quadri_cf bank: d_last_in[c] is the sample preceding channel c's block (NULL = zeros),
+ * d_last_out[c] receives its last sample (may be NULL; must not alias d_last_in). */
+int csdrb_fmdemod_quadri_bank_cf(const complexf *d_in, long in_stride, float *d_out, long out_stride, int channels,
+                                 int input_size, const complexf *d_last_in, complexf *d_last_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
