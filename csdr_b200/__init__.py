@@ -59,6 +59,9 @@ def lib() -> C.CDLL:
     L.csdrb_fir_decimate_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, it, vp]
     L.csdrb_fmdemod_quadri_bank_cf.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp]
     L.csdrb_stream_synchronize.argtypes = [vp]
+    L.csdrb_fir_decimate_bank_cc_host.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, it]
+    L.csdrb_host_alloc.argtypes = [C.c_size_t]; L.csdrb_host_alloc.restype = vp
+    L.csdrb_host_free.argtypes = [vp]
     # host-side design helpers (Part A)
     L.firdes_filter_len.argtypes = [C.c_float]
     L.firdes_lowpass_f.argtypes = [C.POINTER(C.c_float), it, C.c_float, it]
@@ -176,6 +179,45 @@ def fir_decimate_bank_cc(x, decimation: int, taps: np.ndarray, out=None, variant
     rc = _check(lib().csdrb_fir_decimate_bank_cc(ptr, stride, optr, ostride, ch, n, decimation, _fp(taps), taps.size, variant, _stream()),
                 "fir_decimate_bank_cc")
     assert rc == n_out, (rc, n_out)
+    return out[:, :n_out]
+
+
+class PinnedArray:
+    """A page-locked host buffer from csdrb_host_alloc exposed as a numpy array (freed on close/del)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape); self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().csdrb_host_alloc(nbytes)
+        if not self.ptr:
+            raise CsdrB200Error(f"csdrb_host_alloc({nbytes}): {lib().csdrb_last_error().decode()}")
+        buf = (C.c_char * nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib().csdrb_host_free(self.ptr); self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fir_decimate_bank_cc_host(x: np.ndarray, decimation: int, taps: np.ndarray, out: np.ndarray | None = None, chunk_channels: int = 0):
+    """End-to-end call on HOST arrays: x [C, N] complex64 -> out [C, n_out] complex64 (H2D, kernel, D2H inside)."""
+    assert x.dtype == np.complex64 and x.ndim == 2 and x.strides[1] == 8
+    taps = np.ascontiguousarray(taps, np.float32)
+    ch, n = x.shape
+    n_out = fir_out_len(n, decimation, taps.size)
+    if out is None:
+        out = np.empty((ch, n_out), np.complex64)
+    assert out.dtype == np.complex64 and out.shape[0] == ch and out.shape[1] >= n_out and out.strides[1] == 8
+    rc = _check(lib().csdrb_fir_decimate_bank_cc_host(x.ctypes.data, x.strides[0] // 8, out.ctypes.data, out.strides[0] // 8, ch, n,
+                                                      decimation, _fp(taps), taps.size, chunk_channels), "fir_decimate_bank_cc_host")
+    assert rc == n_out
     return out[:, :n_out]
 
 

@@ -126,6 +126,78 @@ int csdrb_fmdemod_quadri_bank_cf(const complexf* d_in, long in_stride, float* d_
                                               reinterpret_cast<const float2*>(d_last_in), reinterpret_cast<float2*>(d_last_out), S(stream)));
 }
 
+
+// ---- host-buffer bank call: the e2e path -------------------------------------------------------------
+// Streams a [channels][input_size] HOST bank through the device in channel chunks on three streams so
+// that the H2D copy of chunk i+1, the kernel of chunk i and the D2H copy of chunk i-1 overlap (PCIe is
+// full duplex).  Host buffers should be page-locked (csdrb_host_alloc) -- pageable memory works but is
+// staged by the driver.  Synchronous: returns when h_out is complete.
+} // extern C (reopened below)
+namespace csdrb {
+struct HostBank {
+    static constexpr int NS = 3;
+    cudaStream_t st[NS] = {nullptr, nullptr, nullptr};
+    void* din[NS] = {nullptr, nullptr, nullptr};
+    void* dout[NS] = {nullptr, nullptr, nullptr};
+    size_t cin = 0, cout = 0;
+    std::mutex mu;
+    int ensure(size_t bin, size_t bout)
+    {
+        for (int k = 0; k < NS; k++) if (!st[k]) CSDRB_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+        if (bin > cin) {
+            for (int k = 0; k < NS; k++) { if (din[k]) CSDRB_CUDA(cudaFree(din[k])); CSDRB_CUDA(cudaMalloc(&din[k], bin)); }
+            cin = bin;
+        }
+        if (bout > cout) {
+            for (int k = 0; k < NS; k++) { if (dout[k]) CSDRB_CUDA(cudaFree(dout[k])); CSDRB_CUDA(cudaMalloc(&dout[k], bout)); }
+            cout = bout;
+        }
+        return 0;
+    }
+};
+static HostBank g_hb;
+}  // namespace csdrb
+extern "C" {
+
+void* csdrb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__); return nullptr; }
+    return p;
+}
+void csdrb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int csdrb_fir_decimate_bank_cc_host(const complexf* h_in, long in_stride, complexf* h_out, long out_stride, int channels,
+                                    int input_size, int decimation, const float* h_taps, int taps_length, int chunk_channels)
+{
+    if (!h_in || !h_out || !h_taps || channels <= 0 || decimation <= 0 || taps_length <= 0) { set_error("fir_decimate host bank: bad argument"); return -1; }
+    const int n_out = input_size >= taps_length ? (input_size - taps_length) / decimation + 1 : 0;
+    if (n_out == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_hb.mu);
+    const long dstride_in = (input_size + 1) & ~1L, dstride_out = (n_out + 1) & ~1L;
+    if (chunk_channels <= 0) {                                 // ~192 MiB of input per chunk keeps all three stages busy
+        chunk_channels = (int)((192L << 20) / (dstride_in * 8));
+        if (chunk_channels < 1) chunk_channels = 1;
+    }
+    if (chunk_channels > channels) chunk_channels = channels;
+    if (int rc = g_hb.ensure((size_t)chunk_channels * dstride_in * 8, (size_t)chunk_channels * dstride_out * 8)) return rc;
+    int slot = 0;
+    for (int c0 = 0; c0 < channels; c0 += chunk_channels, slot = (slot + 1) % HostBank::NS) {
+        const int nc = channels - c0 < chunk_channels ? channels - c0 : chunk_channels;
+        cudaStream_t s = g_hb.st[slot];
+        CSDRB_CUDA(cudaMemcpy2DAsync(g_hb.din[slot], (size_t)dstride_in * 8, h_in + (long)c0 * in_stride, (size_t)in_stride * 8,
+                                     (size_t)input_size * 8, nc, cudaMemcpyHostToDevice, s));
+        int rc = csdrb_fir_decimate_bank_cc((const complexf*)g_hb.din[slot], dstride_in, (complexf*)g_hb.dout[slot], dstride_out, nc,
+                                            input_size, decimation, h_taps, taps_length, -1, s);
+        if (rc < 0) return rc;
+        CSDRB_CUDA(cudaMemcpy2DAsync(h_out + (long)c0 * out_stride, (size_t)out_stride * 8, g_hb.dout[slot], (size_t)dstride_out * 8,
+                                     (size_t)n_out * 8, nc, cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < HostBank::NS; k++) CSDRB_CUDA(cudaStreamSynchronize(g_hb.st[k]));
+    return n_out;
+}
+
 // =====================================================================================================
 // Part A -- host-pointer drop-ins
 // =====================================================================================================

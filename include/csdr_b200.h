@@ -136,6 +136,14 @@ int csdrb_fir_decimate_bank_cc(const complexf *d_in, long in_stride, complexf *d
                                int input_size, int decimation, const float *h_taps, int taps_length, int variant, void *stream);
 int csdrb_fir_bank_variants(void);
 
+/* Same operation on HOST buffers (the end-to-end path): streams the bank through the device in chunks of
+ * `chunk_channels` channels (<= 0: automatic) on three streams so H2D, kernel and D2H overlap; synchronous.
+ * Page-locked host memory (csdrb_host_alloc) is needed for full PCIe rate. */
+int csdrb_fir_decimate_bank_cc_host(const complexf *h_in, long in_stride, complexf *h_out, long out_stride, int channels,
+                                    int input_size, int decimation, const float *h_taps, int taps_length, int chunk_channels);
+void *csdrb_host_alloc(size_t bytes);
+void  csdrb_host_free(void *p);
+
 /* K4 fmdemod_quadri_cf bank: d_last_in[c] is the sample preceding channel c's block (NULL = zeros),
  * d_last_out[c] receives its last sample (may be NULL; must not alias d_last_in). */
 int csdrb_fmdemod_quadri_bank_cf(const complexf *d_in, long in_stride, float *d_out, long out_stride, int channels,
