@@ -33,6 +33,28 @@ class _DShiftStatus(C.Structure):
     _fields_ = [("decimation_remain", C.c_int), ("starting_phase", C.c_float), ("output_size", C.c_int)]
 
 
+class _FracDec(C.Structure):            # include/csdr_b200.h fractional_decimator_ff_t (= libcsdr.h:151-168)
+    _fields_ = [("where", C.c_float), ("input_processed", C.c_int), ("output_size", C.c_int), ("num_poly_points", C.c_int),
+                ("poly_precalc_denomiator", C.c_void_p), ("coeffs_buf", C.c_void_p), ("filtered_buf", C.c_void_p),
+                ("xifirst", C.c_int), ("xilast", C.c_int), ("rate", C.c_float), ("taps", C.c_void_p), ("taps_length", C.c_int)]
+
+
+class _FastAgc(C.Structure):            # fastagc_ff_t (= libcsdr.h:118-128)
+    _fields_ = [("buffer_1", C.c_void_p), ("buffer_2", C.c_void_p), ("buffer_input", C.c_void_p), ("peak_1", C.c_float),
+                ("peak_2", C.c_float), ("input_size", C.c_int), ("reference", C.c_float), ("last_gain", C.c_float)]
+
+
+class _Plan(C.Structure):               # struct fft_plan_s (= fft_fftw.h:14-20)
+    _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
+
+
+class FastDDC(C.Structure):             # fastddc_t (= fastddc.h:5-24)
+    _fields_ = [(n, C.c_int) for n in ("pre_decimation", "post_decimation", "taps_length", "taps_min_length", "overlap_length",
+                                       "fft_size", "fft_inv_size", "input_size", "post_input_size")] + \
+               [("pre_shift", C.c_float), ("startbin", C.c_int), ("v", C.c_int), ("offsetbin", C.c_int), ("post_shift", C.c_float),
+                ("output_scrape", C.c_int), ("scrap", C.c_int), ("dsadata", _Shift)]
+
+
 _lib = None
 
 
@@ -62,6 +84,31 @@ def lib() -> C.CDLL:
     L.csdrb_fir_decimate_bank_cc_host.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, it]
     L.csdrb_host_alloc.argtypes = [C.c_size_t]; L.csdrb_host_alloc.restype = vp
     L.csdrb_host_free.argtypes = [vp]
+    sz = C.c_size_t
+    L.csdrb_shift_addition_bank_scratch_bytes.argtypes = [it, it, it]; L.csdrb_shift_addition_bank_scratch_bytes.restype = sz
+    L.csdrb_shift_addition_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, it, vp, sz, vp]
+    L.csdrb_decimating_shift_addition_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, it, vp, vp, vp, vp]
+    L.csdrb_fractional_decimator_bank_scratch_bytes.argtypes = [it, it, C.c_float]; L.csdrb_fractional_decimator_bank_scratch_bytes.restype = sz
+    L.csdrb_fractional_decimator_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, it, vp, vp, sz, vp]
+    L.csdrb_fastagc_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp, vp, vp]
+    L.csdrb_fft_c2c_batch.argtypes = [vp, lg, vp, lg, it, it, it, vp]
+    L.csdrb_bandpass_fir_fft_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, it, vp, lg, vp, vp]
+    L.csdrb_fastddc_fwd_cc.argtypes = [vp, vp, vp, it, it, it, vp]
+    L.csdrb_fastddc_inv_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastddc_inv_bank_scratch_bytes.restype = sz
+    L.csdrb_fastddc_inv_bank_cc.argtypes = [vp, it, vp, vp, it, C.POINTER(FastDDC), vp, vp, vp, lg, vp, vp, sz, vp]
+    L.fastddc_init.argtypes = [C.POINTER(FastDDC), C.c_float, it, C.c_float]
+    L.decimating_shift_addition_init.argtypes = [C.c_float, it]; L.decimating_shift_addition_init.restype = _Shift
+    L.shift_addition_cc.argtypes = [vp, vp, it, _Shift, C.c_float]; L.shift_addition_cc.restype = C.c_float
+    L.decimating_shift_addition_cc.argtypes = [vp, vp, it, _Shift, it, _DShiftStatus]; L.decimating_shift_addition_cc.restype = _DShiftStatus
+    L.fractional_decimator_ff_init.argtypes = [C.c_float, it, vp, it]; L.fractional_decimator_ff_init.restype = _FracDec
+    L.fractional_decimator_ff.argtypes = [vp, vp, it, C.POINTER(_FracDec)]
+    L.fastagc_ff.argtypes = [C.POINTER(_FastAgc), vp]
+    L.make_fft_c2c.argtypes = [it, vp, vp, it, it]; L.make_fft_c2c.restype = C.POINTER(_Plan)
+    L.fft_execute.argtypes = [C.POINTER(_Plan)]
+    L.fft_destroy.argtypes = [C.POINTER(_Plan)]
+    L.apply_fir_fft_cc.argtypes = [C.POINTER(_Plan), C.POINTER(_Plan), vp, vp, it]
+    L.fastddc_inv_cc.argtypes = [vp, vp, C.POINTER(FastDDC), C.POINTER(_Plan), vp, _DShiftStatus]; L.fastddc_inv_cc.restype = _DShiftStatus
+    L.fft_swap_sides.argtypes = [vp, it]
     # host-side design helpers (Part A)
     L.firdes_filter_len.argtypes = [C.c_float]
     L.firdes_lowpass_f.argtypes = [C.POINTER(C.c_float), it, C.c_float, it]
@@ -266,7 +313,270 @@ class libcsdr:
         return y[:n].copy()
 
     @staticmethod
+    def shift_addition_cc(x, rate, phase=0.0, chunk=None):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x); d = lib().shift_addition_init(rate)
+        chunk = chunk or max(x.size, 1)
+        for s in range(0, x.size, chunk):
+            n = min(chunk, x.size - s)
+            phase = lib().shift_addition_cc(x[s:].ctypes.data, y[s:].ctypes.data, n, d, phase)
+        return y, float(np.float32(phase))
+
+    @staticmethod
+    def decimating_shift_addition_cc(x, rate, decimation, remain=0, phase=0.0):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty(x.size // decimation + 2, np.complex64)
+        d = lib().decimating_shift_addition_init(rate, decimation)
+        st = lib().decimating_shift_addition_cc(x.ctypes.data, y.ctypes.data, x.size, d, decimation, _DShiftStatus(remain, phase, 0))
+        return y[:st.output_size].copy(), (st.decimation_remain, st.starting_phase)
+
+    @staticmethod
+    def fractional_decimator_ff(x, rate, num_poly_points=12, taps=None, block=None):
+        """block=None: one call; else the CLI's block loop with tail re-feeding (csdr.c:1510-1522)."""
+        x = np.ascontiguousarray(x, np.float32)
+        tp = np.ascontiguousarray(taps, np.float32) if taps is not None else None
+        d = lib().fractional_decimator_ff_init(rate, num_poly_points, tp.ctypes.data if tp is not None else None, tp.size if tp is not None else 0)
+        if block is None:
+            out = np.empty(int(x.size / max(rate, 1.0)) + 16, np.float32)
+            lib().fractional_decimator_ff(x.ctypes.data, out.ctypes.data, x.size, C.byref(d))
+            return out[:d.output_size].copy()
+        buf = np.zeros(block, np.float32); out = np.empty(block, np.float32); outs = []; pos = 0
+        while True:
+            if d.input_processed == 0:
+                need, keep = block, 0
+            else:
+                need = d.input_processed; keep = block - need
+                buf[:keep] = buf[need:].copy()
+            if pos + need > x.size:
+                break
+            buf[keep:] = x[pos:pos + need]; pos += need
+            if d.input_processed == 0:
+                d.input_processed = block
+            lib().fractional_decimator_ff(buf.ctypes.data, out.ctypes.data, block, C.byref(d))
+            outs.append(out[:d.output_size].copy())
+        return np.concatenate(outs) if outs else np.zeros(0, np.float32)
+
+    @staticmethod
+    def fastagc_ff(x, block=1024, reference=1.0):
+        x = np.ascontiguousarray(x, np.float32); nblk = x.size // block
+        bufs = [np.zeros(block, np.float32) for _ in range(3)]
+        byaddr = {b.ctypes.data: b for b in bufs}
+        st = _FastAgc(bufs[0].ctypes.data, bufs[1].ctypes.data, bufs[2].ctypes.data, 0, 0, block, reference, 0)
+        y = np.empty(nblk * block, np.float32)
+        for b in range(nblk):
+            byaddr[st.buffer_input][:] = x[b * block:(b + 1) * block]
+            lib().fastagc_ff(C.byref(st), y[b * block:].ctypes.data)
+        return y
+
+    @staticmethod
+    def dft(x, forward=True):
+        x = np.ascontiguousarray(x, np.complex64).copy(); y = np.empty_like(x)
+        pl = lib().make_fft_c2c(x.size, x.ctypes.data, y.ctypes.data, 1 if forward else 0, 0)
+        lib().fft_execute(pl); lib().fft_destroy(pl); return y
+
+    @staticmethod
+    def bandpass_fir_fft_cc(x, lo, hi, bw, window="HAMMING"):
+        """The CLI block loop of csdr.c:1833-1883 over the libcsdr-named entry points (complete blocks only)."""
+        x = np.ascontiguousarray(x, np.complex64)
+        T, N, isz, ov = bandpass_geometry(bw)
+        taps = np.zeros(N, np.complex64); taps[:T] = firdes_bandpass_c(T, lo, hi, window)
+        taps_fft = libcsdr.dft(taps)
+        inp = np.zeros(N, np.complex64); spec = np.empty(N, np.complex64); ospec = np.empty(N, np.complex64)
+        o = [np.zeros(N, np.complex64), np.zeros(N, np.complex64)]
+        pf = lib().make_fft_c2c(N, inp.ctypes.data, spec.ctypes.data, 1, 0)
+        pi = [lib().make_fft_c2c(N, ospec.ctypes.data, o[k].ctypes.data, 0, 0) for k in range(2)]
+        out = []
+        for b in range(x.size // isz):
+            inp[:isz] = x[b * isz:(b + 1) * isz]
+            cur, prev = (1, 0) if b & 1 else (0, 1)
+            tail = o[prev][isz:]
+            lib().apply_fir_fft_cc(pf, pi[cur], taps_fft.ctypes.data, tail.ctypes.data, ov)
+            out.append(o[cur][:isz].copy())
+        lib().fft_destroy(pf); [lib().fft_destroy(p) for p in pi]
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+    @staticmethod
+    def fastddc_inv(spectra, bw, decimation, shift, window="HAMMING"):
+        """csdr.c:2335-2371 over the libcsdr-named entry points."""
+        ddc = fastddc_init(bw, decimation, shift)
+        hb = np.float32(0.5 / decimation); sh = np.float32(shift)
+        taps = np.zeros(ddc.fft_size, np.complex64)
+        taps[:ddc.taps_length] = firdes_bandpass_c(ddc.taps_length, float(-sh - hb), float(-sh + hb), window)
+        tf = libcsdr.dft(taps); lib().fft_swap_sides(tf.ctypes.data, ddc.fft_size)
+        st = _DShiftStatus(0, 0.0, 0); out = []
+        for sp in spectra:
+            sp = np.ascontiguousarray(sp, np.complex64).copy(); y = np.empty(ddc.post_input_size, np.complex64)
+            st = lib().fastddc_inv_cc(sp.ctypes.data, y.ctypes.data, C.byref(ddc), None, tf.ctypes.data, st)
+            out.append(y[:st.output_size].copy())
+        return np.concatenate(out) if out else np.zeros(0, np.complex64)
+
+    @staticmethod
     def fmdemod_quadri_cf(x, last=0j):
         x = np.ascontiguousarray(x, np.complex64); y = np.empty(x.size, np.float32)
         r = lib().fmdemod_quadri_cf(x.ctypes.data, y.ctypes.data, x.size, None, _CF(np.float32(last.real), np.float32(last.imag)))
         return y, complex(r.i, r.q)
+
+
+# --------------------------------------------------------------------------------------------------
+# K2 / K5 / K6 / K7 / K8 / K9 bank calls (torch CUDA tensors)
+# --------------------------------------------------------------------------------------------------
+def shift_addition_init(rate: float):
+    d = lib().shift_addition_init(rate)
+    return (d.sindelta, d.cosdelta, d.rate)
+
+
+def fastddc_init(transition_bw: float, decimation: int, shift_rate: float) -> FastDDC:
+    d = FastDDC()
+    if lib().fastddc_init(C.byref(d), transition_bw, decimation, shift_rate):
+        raise CsdrB200Error("fastddc_init: fft_size <= 2")
+    return d
+
+
+def _scratch(nbytes: int, device):
+    import torch
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def shift_addition_bank_cc(x, rates, phases=None, chunk: int = 1024, out=None):
+    """x: [N] (one shared wideband stream) or [C, N] complex64; rates: C floats.  Returns (y [C,N], new phases [C] tensor)."""
+    import torch
+    rates = np.atleast_1d(np.asarray(rates, np.float32))
+    ch = rates.size
+    shared = (x.dim() == 1) if x.dtype == torch.complex64 else (x.dim() == 2)
+    xr, ptr, stride, xc, n = _as_cf32_rows(x)
+    if shared:
+        stride = 0
+    else:
+        assert xc == ch
+    params = np.array([shift_addition_init(float(r)) for r in rates], np.float32)           # host: bit-exact deltas
+    d_params = torch.from_numpy(params).to(xr.device)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=xr.device) if phases is None else phases.clone()
+    if out is None:
+        out = torch.empty((ch, n), dtype=torch.complex64, device=xr.device)
+    sb = lib().csdrb_shift_addition_bank_scratch_bytes(ch, n, chunk)
+    scratch = _scratch(sb, xr.device)
+    _check(lib().csdrb_shift_addition_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_params.data_ptr(), d_phase.data_ptr(), chunk,
+                                              scratch.data_ptr(), scratch.numel(), _stream()), "shift_addition_bank_cc")
+    return out, d_phase
+
+
+def fractional_decimator_bank_ff(x, rate: float, num_poly_points: int = 12, taps=None, where=None):
+    """x [C, N] float32 -> (y [C, cap] float32, state tensor [C,3] int32-view (where bits, input_processed, output_size))."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    ch, n = x.shape
+    cap = int(n / max(rate, 1.0)) + 8
+    out = torch.empty((ch, cap), dtype=torch.float32, device=x.device)
+    state = torch.zeros((ch, 3), dtype=torch.int32, device=x.device)
+    w0 = np.float32(num_poly_points // 2 - 1 if where is None else 0)            # where = -xifirst at init (libcsdr.c:736)
+    if where is None:
+        state[:, 0] = int(np.array([w0], np.float32).view(np.int32)[0])
+    else:
+        state[:, 0] = torch.as_tensor(np.asarray(where, np.float32).view(np.int32), device=x.device)
+    d_taps = torch.from_numpy(np.ascontiguousarray(taps, np.float32)).to(x.device) if taps is not None else None
+    sb = lib().csdrb_fractional_decimator_bank_scratch_bytes(ch, n, rate)
+    scratch = _scratch(sb, x.device)
+    _check(lib().csdrb_fractional_decimator_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, rate, num_poly_points,
+                                                    d_taps.data_ptr() if d_taps is not None else None, d_taps.numel() if d_taps is not None else 0,
+                                                    state.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "fractional_decimator_bank_ff")
+    return out, state
+
+
+def fastagc_bank_ff(x, block: int = 1024, reference: float = 1.0, state=None, hist=None):
+    """x [C, nblocks*block] float32 -> y same shape (two blocks of latency); returns (y, state [C,3] f32, hist [C,2,block])."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    ch, n = x.shape
+    nblocks = n // block
+    out = torch.empty((ch, nblocks * block), dtype=torch.float32, device=x.device)
+    state = torch.zeros((ch, 3), dtype=torch.float32, device=x.device) if state is None else state
+    hist = torch.zeros((ch, 2, block), dtype=torch.float32, device=x.device) if hist is None else hist
+    _check(lib().csdrb_fastagc_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, block, nblocks, reference,
+                                       state.data_ptr(), hist.data_ptr(), _stream()), "fastagc_bank_ff")
+    return out, state, hist
+
+
+def fft_c2c(x, inverse: bool = False):
+    """Batched unnormalised DFT along the last axis of a [B, N] (or [N]) complex64 CUDA tensor."""
+    import torch
+    xr, ptr, stride, b, n = _as_cf32_rows(x)
+    out = torch.empty((b, n), dtype=torch.complex64, device=xr.device)
+    _check(lib().csdrb_fft_c2c_batch(ptr, stride, out.data_ptr(), out.stride(0), n, b, 1 if inverse else 0, _stream()), "fft_c2c")
+    return out if x.dim() > 1 or x.dtype != torch.complex64 else out[0]
+
+
+def bandpass_geometry(transition_bw: float):
+    """(taps_length, fft_size, input_size, overlap) exactly as csdr.c:1833-1838 sizes them."""
+    T = firdes_filter_len(transition_bw)
+    N = int(lib().next_pow2(T))
+    if N - T < 200:
+        N <<= 1
+    return T, N, N - T + 1, T - 1
+
+
+def bandpass_taps_fft(low_cut: float, high_cut: float, transition_bw: float, window: str = "HAMMING", device="cuda"):
+    import torch
+    T, N, _, _ = bandpass_geometry(transition_bw)
+    taps = np.zeros(N, np.complex64)
+    taps[:T] = firdes_bandpass_c(T, low_cut, high_cut, window)
+    return fft_c2c(torch.from_numpy(taps).to(device))
+
+
+def bandpass_fir_fft_bank_cc(x, taps_fft, input_size: int, tail=None):
+    """x [C, nblocks*input_size] complex64 -> y same shape; taps_fft [N] (shared) or [C, N]; tail [C, N] carried state."""
+    import torch
+    xr, ptr, stride, ch, n = _as_cf32_rows(x)
+    N = taps_fft.shape[-1]
+    nblocks = n // input_size
+    out = torch.empty((ch, nblocks * input_size), dtype=torch.complex64, device=xr.device)
+    tail = torch.zeros((ch, N), dtype=torch.complex64, device=xr.device) if tail is None else tail
+    tstride = 0 if taps_fft.dim() == 1 else taps_fft.stride(0)
+    _check(lib().csdrb_bandpass_fir_fft_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, N, input_size, nblocks, taps_fft.data_ptr(), tstride,
+                                                tail.data_ptr(), _stream()), "bandpass_fir_fft_bank_cc")
+    return out, tail
+
+
+def fastddc_fwd_cc(x, ddc: FastDDC, overlap=None):
+    """x [nblocks*input_size] complex64 -> spectra [nblocks, fft_size]; overlap [fft_size-input_size] carried state."""
+    import torch
+    assert x.dtype == torch.complex64 and x.is_cuda and x.dim() == 1
+    nblocks = x.numel() // ddc.input_size
+    spectra = torch.empty((nblocks, ddc.fft_size), dtype=torch.complex64, device=x.device)
+    overlap = torch.zeros(ddc.overlap_length, dtype=torch.complex64, device=x.device) if overlap is None else overlap
+    _check(lib().csdrb_fastddc_fwd_cc(x.data_ptr(), spectra.data_ptr(), overlap.data_ptr(), ddc.fft_size, ddc.input_size, nblocks, _stream()), "fastddc_fwd_cc")
+    return spectra, overlap
+
+
+def fastddc_make_taps_fft(ddc: FastDDC, shift_rate: float, decimation: int, window: str = "HAMMING", device="cuda"):
+    """csdr.c:2342-2351: bandpass taps at -shift -+ 0.5/decimation, zero pad, forward FFT, swap sides."""
+    import torch
+    hb = np.float32(0.5 / decimation); sh = np.float32(shift_rate)
+    taps = np.zeros(ddc.fft_size, np.complex64)
+    taps[:ddc.taps_length] = firdes_bandpass_c(ddc.taps_length, float(-sh - hb), float(-sh + hb), window)
+    tf = fft_c2c(torch.from_numpy(taps).to(device))
+    return torch.roll(tf, ddc.fft_size // 2)
+
+
+def fastddc_inv_bank_cc(spectra, shifts, decimation: int, transition_bw: float, window: str = "HAMMING", state=None):
+    """All channels (one per entry of ``shifts``) consume the same spectra [nblocks, fft_size].
+    Returns (out [C, nblocks*post_input_size/post_decimation + 1], counts [C] int32, state dict)."""
+    import torch
+    dev = spectra.device
+    nblocks = spectra.shape[0]
+    ddcs = [fastddc_init(transition_bw, decimation, float(s)) for s in shifts]
+    g = ddcs[0]
+    ch = len(ddcs)
+    if state is None:
+        taps_fft = torch.stack([fastddc_make_taps_fft(d, float(s), decimation, window, dev) for d, s in zip(ddcs, shifts)]).contiguous()
+        chan = np.zeros((ch, 4), np.float32)
+        chan.view(np.int32)[:, 0] = [d.offsetbin for d in ddcs]
+        chan[:, 1] = [d.dsadata.sindelta for d in ddcs]; chan[:, 2] = [d.dsadata.cosdelta for d in ddcs]; chan[:, 3] = [d.dsadata.rate for d in ddcs]
+        state = {"taps_fft": taps_fft, "chan": torch.from_numpy(chan).to(dev), "remain": torch.zeros(ch, dtype=torch.int32, device=dev),
+                 "phase": torch.zeros(ch, dtype=torch.float32, device=dev)}
+    per_block = g.post_input_size // g.post_decimation + 1
+    out = torch.empty((ch, nblocks * per_block + 2), dtype=torch.complex64, device=dev)
+    counts = torch.zeros(ch, dtype=torch.int32, device=dev)
+    sb = lib().csdrb_fastddc_inv_bank_scratch_bytes(ch, nblocks)
+    scratch = _scratch(sb, dev)
+    _check(lib().csdrb_fastddc_inv_bank_cc(spectra.data_ptr(), nblocks, state["taps_fft"].data_ptr(), state["chan"].data_ptr(), ch, C.byref(g),
+                                           state["remain"].data_ptr(), state["phase"].data_ptr(), out.data_ptr(), out.stride(0), counts.data_ptr(),
+                                           scratch.data_ptr(), scratch.numel(), _stream()), "fastddc_inv_bank_cc")
+    return out, counts, state

@@ -16,7 +16,7 @@ OBJ = PKG / "build"
 LIB = PKG / "libcsdr_b200.so"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true", "--expt-relaxed-constexpr", "-diag-suppress", "20281", f"-I{ROOT / 'include'}", f"-I{CSRC}"]
 GCC_FLAGS = ["-std=gnu99", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", f"-I{ROOT / 'include'}"]
 
 

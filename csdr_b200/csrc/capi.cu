@@ -278,3 +278,298 @@ complexf fmdemod_quadri_cf(complexf* input, float* output, int input_size, float
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Part B, continued: K2, K5-K9
+// =====================================================================================================
+extern "C" {
+
+size_t csdrb_shift_addition_bank_scratch_bytes(int channels, int input_size, int chunk) { return shift_bank_scratch_bytes(channels, input_size, chunk); }
+
+int csdrb_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                                 const shift_addition_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_in || !d_out || !d_params || !d_phase_io) { set_error("shift_addition bank: null pointer"); return -1; }
+    int rc = launch_shift_addition_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                        reinterpret_cast<const float*>(d_params), d_phase_io, chunk, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_decimating_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                                            const shift_addition_data_t* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size, void* stream)
+{
+    if (!d_in || !d_out || !d_params || !d_remain_io || !d_phase_io) { set_error("decimating_shift_addition bank: null pointer"); return -1; }
+    int rc = launch_decimating_shift_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                          reinterpret_cast<const float*>(d_params), decimation, d_remain_io, d_phase_io, d_out_size, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+size_t csdrb_fractional_decimator_bank_scratch_bytes(int channels, int input_size, float rate) { return fracdec_scratch_bytes(channels, input_size, rate); }
+
+int csdrb_fractional_decimator_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int input_size, float rate,
+                                       int num_poly_points, const float* d_taps, int taps_length, csdrb_fracdec_state_t* d_state,
+                                       void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_in || !d_out || !d_state) { set_error("fractional_decimator bank: null pointer"); return -1; }
+    int rc = launch_fractional_decimator_bank(d_in, in_stride, d_out, out_stride, channels, input_size, rate, num_poly_points, d_taps, taps_length, d_state,
+                                              d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_fastagc_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks, float reference,
+                          csdrb_fastagc_state_t* d_state, float* d_hist, void* stream)
+{
+    if (!d_in || !d_out || !d_state || !d_hist) { set_error("fastagc bank: null pointer"); return -1; }
+    int rc = launch_fastagc_bank(d_in, in_stride, d_out, out_stride, channels, block, nblocks, reference, d_state, d_hist, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_fft_c2c_batch(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int size, int batch, int inverse, void* stream)
+{
+    if (!d_in || !d_out) { set_error("fft: null pointer"); return -1; }
+    int rc = launch_fft_c2c_batch(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, size, batch, inverse, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_bandpass_fir_fft_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int fft_size, int input_size,
+                                   int nblocks, const complexf* d_taps_fft, long taps_stride, complexf* d_tail_io, void* stream)
+{
+    if (!d_in || !d_out || !d_taps_fft || !d_tail_io) { set_error("bandpass_fir_fft bank: null pointer"); return -1; }
+    int rc = launch_olafir_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, fft_size, input_size,
+                                nblocks, reinterpret_cast<const float2*>(d_taps_fft), taps_stride, reinterpret_cast<float2*>(d_tail_io), 0, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_fastddc_fwd_cc(const complexf* d_in, complexf* d_spectra, complexf* d_overlap_io, int fft_size, int input_size, int nblocks, void* stream)
+{
+    if (!d_in || !d_spectra || !d_overlap_io) { set_error("fastddc_fwd: null pointer"); return -1; }
+    int rc = launch_fastddc_fwd(reinterpret_cast<const float2*>(d_in), reinterpret_cast<float2*>(d_spectra), reinterpret_cast<float2*>(d_overlap_io),
+                                fft_size, input_size, nblocks, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+size_t csdrb_fastddc_inv_bank_scratch_bytes(int channels, int nblocks) { return fastddc_inv_scratch_bytes(channels, nblocks); }
+
+int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const complexf* d_taps_fft, const csdrb_fastddc_chan_t* d_chan, int channels,
+                              const fastddc_t* g, int* d_remain_io, float* d_phase_io, complexf* d_out, long out_stride, int* d_out_total,
+                              void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_spectra || !d_taps_fft || !d_chan || !g || !d_remain_io || !d_phase_io || !d_out || !d_out_total) { set_error("fastddc_inv bank: null pointer"); return -1; }
+    int rc = launch_fastddc_inv_bank(reinterpret_cast<const float2*>(d_spectra), nblocks, reinterpret_cast<const float2*>(d_taps_fft), d_chan, channels,
+                                     g->fft_size, g->fft_inv_size, g->pre_decimation, g->scrap, g->post_input_size, g->post_decimation,
+                                     d_remain_io, d_phase_io, reinterpret_cast<float2*>(d_out), out_stride, d_out_total, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+// =====================================================================================================
+// Part A, continued: host-pointer drop-ins for shift / fractional decimator / fastagc / FFT / fastddc
+// =====================================================================================================
+#define A_BEGIN(who) std::lock_guard<std::mutex> lk(g_ctx.mu); A_CHECK(g_ctx.init(), who)
+#define A_UP(slot, ptr, bytes, who) do { A_CHECK(g_ctx.reserve(slot, (bytes) + 16), who); \
+    A_CUDA(cudaMemcpyAsync(g_ctx.buf[slot], ptr, bytes, cudaMemcpyHostToDevice, g_ctx.stream), who); } while (0)
+#define A_DOWN(ptr, slot, bytes, who) A_CUDA(cudaMemcpyAsync(ptr, g_ctx.buf[slot], bytes, cudaMemcpyDeviceToHost, g_ctx.stream), who)
+#define A_SYNC(who) A_CUDA(cudaStreamSynchronize(g_ctx.stream), who)
+
+float shift_addition_cc(complexf* input, complexf* output, int input_size, shift_addition_data_t d, float starting_phase)
+{
+    const char* who = "shift_addition_cc";
+    if (input_size <= 0) return starting_phase;      // the reference still wraps the phase; with n = 0 nothing changes unless |phase| > pi
+    A_BEGIN(who);
+    // slot 0: input, 1: output, 2: params(12 B) + phase(4 B) at +64, 3: scratch
+    A_UP(0, input, (size_t)input_size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 8 + 16), who);
+    struct { shift_addition_data_t p; float pad; float phase; } blob = {d, 0.f, starting_phase};
+    A_UP(2, &blob, sizeof blob, who);
+    const size_t sb = csdrb_shift_addition_bank_scratch_bytes(1, input_size, input_size);
+    A_CHECK(g_ctx.reserve(3, sb + 16), who);
+    float* d_phase = reinterpret_cast<float*>(static_cast<char*>(g_ctx.buf[2]) + offsetof(decltype(blob), phase));
+    A_CHECK(csdrb_shift_addition_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
+                                         (const shift_addition_data_t*)g_ctx.buf[2], d_phase, input_size, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)input_size * 8, who);
+    float new_phase = 0.f;
+    A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return new_phase;
+}
+
+decimating_shift_addition_status_t decimating_shift_addition_cc(complexf* input, complexf* output, int input_size, shift_addition_data_t d,
+                                                                int decimation, decimating_shift_addition_status_t s)
+{
+    const char* who = "decimating_shift_addition_cc";
+    A_BEGIN(who);
+    if (input_size > 0) A_UP(0, input, (size_t)input_size * 8, who); else A_CHECK(g_ctx.reserve(0, 64), who);
+    const int cap = input_size / (decimation > 0 ? decimation : 1) + 2;
+    A_CHECK(g_ctx.reserve(1, (size_t)cap * 8 + 16), who);
+    struct { shift_addition_data_t p; int remain; float phase; int outsz; } blob = {d, s.decimation_remain, s.starting_phase, 0};
+    A_UP(2, &blob, sizeof blob, who);
+    char* b2 = static_cast<char*>(g_ctx.buf[2]);
+    A_CHECK(csdrb_decimating_shift_addition_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
+                                                    (const shift_addition_data_t*)b2, decimation, (int*)(b2 + offsetof(decltype(blob), remain)),
+                                                    (float*)(b2 + offsetof(decltype(blob), phase)), (int*)(b2 + offsetof(decltype(blob), outsz)), g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(&blob, b2, sizeof blob, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    if (blob.outsz > 0) { A_DOWN(output, 1, (size_t)blob.outsz * 8, who); A_SYNC(who); }
+    s.decimation_remain = blob.remain; s.starting_phase = blob.phase; s.output_size = blob.outsz;
+    return s;
+}
+
+fractional_decimator_ff_t fractional_decimator_ff_init(float rate, int num_poly_points, float* taps, int taps_length)
+{
+    // libcsdr.c:715-748 -- same field values; the three scratch arrays are kept so the struct stays layout- and
+    // ownership-compatible with callers that free them.
+    fractional_decimator_ff_t d;
+    d.num_poly_points = num_poly_points & ~1;
+    d.poly_precalc_denomiator = (float*)malloc(sizeof(float) * (size_t)(d.num_poly_points > 0 ? d.num_poly_points : 1));
+    d.xifirst = -(num_poly_points / 2) + 1;
+    d.xilast = num_poly_points / 2;
+    int slot = 0;
+    for (int xi = d.xifirst; xi <= d.xilast && slot < d.num_poly_points; xi++, slot++) {
+        float prod = 1;
+        for (int xj = d.xifirst; xj <= d.xilast; xj++) if (xi != xj) prod *= (float)(xi - xj);
+        d.poly_precalc_denomiator[slot] = prod;
+    }
+    d.where = (float)(-d.xifirst);
+    d.coeffs_buf = (float*)malloc(sizeof(float) * (size_t)(d.num_poly_points > 0 ? d.num_poly_points : 1));
+    d.filtered_buf = (float*)malloc(sizeof(float) * (size_t)(d.num_poly_points > 0 ? d.num_poly_points : 1));
+    d.rate = rate; d.taps = taps; d.taps_length = taps_length; d.input_processed = 0; d.output_size = 0;
+    return d;
+}
+
+void fractional_decimator_ff(float* input, float* output, int input_size, fractional_decimator_ff_t* d)
+{
+    const char* who = "fractional_decimator_ff";
+    if (input_size <= 0) { d->output_size = 0; return; }
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_size * 4, who);
+    const int cap = (int)((double)input_size / (d->rate > 1.f ? d->rate : 1.0)) + 8;
+    A_CHECK(g_ctx.reserve(1, (size_t)cap * 4 + 16), who);
+    const int tl = d->taps ? d->taps_length : 0;
+    struct Blob { csdrb_fracdec_state_t st; int pad; } blob = {{d->where, 0, 0}, 0};
+    // slot 2: [state | taps]
+    const size_t tap_off = 64;
+    A_CHECK(g_ctx.reserve(2, tap_off + (size_t)tl * 4 + 16), who);
+    A_CUDA(cudaMemcpyAsync(g_ctx.buf[2], &blob, sizeof blob, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    float* d_taps = nullptr;
+    if (tl > 0) {
+        d_taps = reinterpret_cast<float*>(static_cast<char*>(g_ctx.buf[2]) + tap_off);
+        A_CUDA(cudaMemcpyAsync(d_taps, d->taps, (size_t)tl * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    }
+    const size_t sb = csdrb_fractional_decimator_bank_scratch_bytes(1, input_size, d->rate);
+    A_CHECK(g_ctx.reserve(3, sb + 16), who);
+    A_CHECK(csdrb_fractional_decimator_bank_ff((const float*)g_ctx.buf[0], 0, (float*)g_ctx.buf[1], 0, 1, input_size, d->rate, d->num_poly_points,
+                                               d_taps, tl, (csdrb_fracdec_state_t*)g_ctx.buf[2], g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(&blob, g_ctx.buf[2], sizeof blob, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    if (blob.st.output_size > 0) { A_DOWN(output, 1, (size_t)blob.st.output_size * 4, who); A_SYNC(who); }
+    d->where = blob.st.where; d->input_processed = blob.st.input_processed; d->output_size = blob.st.output_size;
+}
+
+void fastagc_ff(fastagc_ff_t* a, float* output)
+{
+    const char* who = "fastagc_ff";
+    const int n = a->input_size;
+    if (n <= 0) return;
+    A_BEGIN(who);
+    A_UP(0, a->buffer_input, (size_t)n * 4, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)n * 4 + 16), who);
+    A_CHECK(g_ctx.reserve(2, (size_t)n * 8 + 64 + 16), who);            // [state 64 B | hist1 | hist2]
+    csdrb_fastagc_state_t st = {a->peak_1, a->peak_2, a->last_gain};
+    char* b2 = static_cast<char*>(g_ctx.buf[2]);
+    A_CUDA(cudaMemcpyAsync(b2, &st, sizeof st, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(b2 + 64, a->buffer_1, (size_t)n * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(b2 + 64 + (size_t)n * 4, a->buffer_2, (size_t)n * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CHECK(csdrb_fastagc_bank_ff((const float*)g_ctx.buf[0], 0, (float*)g_ctx.buf[1], 0, 1, n, 1, a->reference, (csdrb_fastagc_state_t*)b2,
+                                  (float*)(b2 + 64), g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)n * 4, who);
+    A_CUDA(cudaMemcpyAsync(&st, b2, sizeof st, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    // rotate the three caller-owned buffers exactly like libcsdr.c:981-989
+    float* recycled = a->buffer_1;
+    a->buffer_1 = a->buffer_2; a->buffer_2 = a->buffer_input; a->buffer_input = recycled;
+    a->peak_1 = st.peak_1; a->peak_2 = st.peak_2; a->last_gain = st.last_gain;
+}
+
+// ---- FFT abstraction ---------------------------------------------------------------------------------
+struct csdrb_plan_impl { int forward; };
+
+FFT_PLAN_T* make_fft_c2c(int size, complexf* input, complexf* output, int forward, int benchmark)
+{
+    (void)benchmark;
+    if (size < 2 || size > 16384 || (size & (size - 1))) {
+        fprintf(stderr, "libcsdr_b200: make_fft_c2c: size %d unsupported (power of two, 2..16384)\n", size);
+        return nullptr;
+    }
+    FFT_PLAN_T* p = (FFT_PLAN_T*)malloc(sizeof(FFT_PLAN_T));
+    csdrb_plan_impl* impl = (csdrb_plan_impl*)malloc(sizeof(csdrb_plan_impl));
+    impl->forward = forward ? 1 : 0;
+    p->size = size; p->input = input; p->output = output; p->plan = impl;
+    return p;
+}
+
+void fft_execute(FFT_PLAN_T* plan)
+{
+    const char* who = "fft_execute";
+    if (!plan) return;
+    A_BEGIN(who);
+    const size_t bytes = (size_t)plan->size * 8;
+    A_UP(0, plan->input, bytes, who);
+    A_CHECK(g_ctx.reserve(1, bytes + 16), who);
+    A_CHECK(csdrb_fft_c2c_batch((const complexf*)g_ctx.buf[0], plan->size, (complexf*)g_ctx.buf[1], plan->size, plan->size, 1,
+                                ((csdrb_plan_impl*)plan->plan)->forward ? 0 : 1, g_ctx.stream), who);
+    A_DOWN(plan->output, 1, bytes, who);
+    A_SYNC(who);
+}
+
+void fft_destroy(FFT_PLAN_T* plan) { if (plan) { free(plan->plan); free(plan); } }
+void* csdrb_fft_malloc(size_t bytes) { void* p = nullptr; return posix_memalign(&p, 64, bytes ? bytes : 64) ? nullptr : p; }
+void csdrb_fft_free(void* p) { free(p); }
+
+void apply_fir_fft_cc(FFT_PLAN_T* plan, FFT_PLAN_T* plan_inverse, complexf* taps_fft, complexf* last_overlap, int overlap_size)
+{
+    // libcsdr.c:814-849 in one fused kernel: the intermediate spectrum (plan->output) and product (plan_inverse->input)
+    // never leave the GPU, so those two caller buffers are NOT written (no caller in the reference reads them).
+    const char* who = "apply_fir_fft_cc";
+    A_BEGIN(who);
+    const int n = plan->size;
+    const size_t bytes = (size_t)n * 8;
+    A_UP(0, plan->input, bytes, who);
+    A_CHECK(g_ctx.reserve(1, bytes + 16), who);
+    A_UP(2, taps_fft, bytes, who);
+    if (overlap_size > 0) A_UP(3, last_overlap, (size_t)overlap_size * 8, who); else A_CHECK(g_ctx.reserve(3, 64), who);
+    int rc = launch_apply_fir_fft((const float2*)g_ctx.buf[0], (const float2*)g_ctx.buf[2], (const float2*)g_ctx.buf[3], overlap_size, (float2*)g_ctx.buf[1], n, g_ctx.stream);
+    A_CHECK(rc, who); counted(0, 1);
+    A_DOWN(plan_inverse->output, 1, bytes, who);
+    A_SYNC(who);
+}
+
+decimating_shift_addition_status_t fastddc_inv_cc(complexf* input, complexf* output, fastddc_t* ddc, FFT_PLAN_T* plan_inverse, complexf* taps_fft,
+                                                  decimating_shift_addition_status_t shift_stat)
+{
+    const char* who = "fastddc_inv_cc";
+    (void)plan_inverse;
+    {
+        A_BEGIN(who);
+        const size_t nb = (size_t)ddc->fft_size * 8;
+        A_UP(0, input, nb, who);
+        A_UP(2, taps_fft, nb, who);
+        A_CHECK(g_ctx.reserve(1, (size_t)ddc->post_input_size * 8 + 64), who);
+        struct { csdrb_fastddc_chan_t ch; int remain; float phase; int total; } blob =
+            {{ddc->offsetbin, ddc->dsadata.sindelta, ddc->dsadata.cosdelta, ddc->dsadata.rate}, shift_stat.decimation_remain, shift_stat.starting_phase, 0};
+        const size_t sb = csdrb_fastddc_inv_bank_scratch_bytes(1, 1);
+        A_CHECK(g_ctx.reserve(3, 256 + sb), who);
+        char* b3 = static_cast<char*>(g_ctx.buf[3]);
+        A_CUDA(cudaMemcpyAsync(b3, &blob, sizeof blob, cudaMemcpyHostToDevice, g_ctx.stream), who);
+        A_CHECK(csdrb_fastddc_inv_bank_cc((const complexf*)g_ctx.buf[0], 1, (const complexf*)g_ctx.buf[2], (const csdrb_fastddc_chan_t*)b3, 1, ddc,
+                                          (int*)(b3 + offsetof(decltype(blob), remain)), (float*)(b3 + offsetof(decltype(blob), phase)),
+                                          (complexf*)g_ctx.buf[1], ddc->post_input_size, (int*)(b3 + offsetof(decltype(blob), total)),
+                                          b3 + 256, sb, g_ctx.stream), who);
+        A_CUDA(cudaMemcpyAsync(&blob, b3, sizeof blob, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+        A_SYNC(who);
+        if (blob.total > 0) { A_DOWN(output, 1, (size_t)blob.total * 8, who); A_SYNC(who); }
+        shift_stat.decimation_remain = blob.remain; shift_stat.starting_phase = blob.phase; shift_stat.output_size = blob.total;
+    }
+    fft_swap_sides(input, ddc->fft_size);            // the reference leaves its input swapped in place (fastddc.c:123)
+    return shift_stat;
+}
+
+}  // extern "C"

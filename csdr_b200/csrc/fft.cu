@@ -1,0 +1,403 @@
+// fft.cu -- K7 batched c2c FFT, K9 overlap-add FFT filter bank, a12 fastddc forward step, K8 fastddc inverse bank.
+//
+//   fft_c2c_batch_kernel  : fft_execute() of a make_fft_c2c plan (fft_fftw.c:6-41), one CTA per transform.
+//   olafir_bank_kernel    : apply_fir_fft_cc (libcsdr.c:814-849) + the block loop of bandpass_fir_fft_cc
+//                           (csdr.c:1872-1883): FFT_N(zero-padded block) * taps_fft -> IFFT_N -> /N -> first
+//                           `overlap` outputs += previous block's tail.  A CTA walks a run of consecutive blocks
+//                           of one channel keeping the tail in shared memory; a run that does not start at block 0
+//                           first recomputes the tail of the block before it.
+//   fastddc_fwd_kernel    : csdr.c:2288-2299 -- overlap-save forward FFT (slide `overlap` samples, append
+//                           input_size new ones, no window), one CTA per block, all bins written.
+//   fastddc_inv_kernel    : fastddc_inv_cc (fastddc.c:106-166) -- fold N bins x taps into M aliasing bins
+//                           (same summation order as the reference: ascending bin index per destination),
+//                           /pre_decimation, swap, IFFT_M, /M, drop `scrap`, post shift + decimate.
+#include "fft.cuh"
+#include "kernels.h"
+
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace csdrb {
+
+// ---- twiddle tables ------------------------------------------------------------------------------
+static std::map<int, float2*> g_tw;
+static std::mutex g_tw_mu;
+
+int get_twiddles(int n, const float2** out, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw.find(n);
+    if (it != g_tw.end()) { *out = it->second; return 0; }
+    std::vector<float2> h((size_t)n);
+    for (int k = 0; k < n; k++) {
+        const double a = -2.0 * M_PI * (double)k / (double)n;
+        h[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2* d = nullptr;
+    CSDRB_CUDA(cudaMalloc(&d, sizeof(float2) * (size_t)n));
+    CSDRB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CSDRB_CUDA(cudaStreamSynchronize(st));
+    g_tw[n] = d;
+    *out = d;
+    return 0;
+}
+
+// ---- K7: batched c2c -------------------------------------------------------------------------------
+template <int N, bool INV>
+__global__ void __launch_bounds__(fft_threads(N))
+fft_c2c_batch_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x;
+    const float2* x = in + (long)blockIdx.x * in_stride;
+    float2* y = out + (long)blockIdx.x * out_stride;
+    for (int i = tid; i < N; i += NT) s[i] = x[i];
+    __syncthreads();
+    block_fft<N, NT, INV>(s, tw, tid);
+    for (int i = tid; i < N; i += NT) y[i] = s[i];
+}
+
+template <int N>
+static int launch_c2c_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * N;
+    if (inverse) {
+        auto k = fft_c2c_batch_kernel<N, true>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft_threads(N), smem, st>>>(in, is, out, os, tw);
+    } else {
+        auto k = fft_c2c_batch_kernel<N, false>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft_threads(N), smem, st>>>(in, is, out, os, tw);
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
+#define CSDRB_FFT_SIZES(X) X(2) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192) X(16384)
+
+int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long out_stride, int n, int batch, int inverse, cudaStream_t st)
+{
+    if (batch <= 0) return 0;
+    if (n < 2 || n > FFT_MAX_N || (n & (n - 1))) { set_error("fft: size %d unsupported (power of two, 2..%d)", n, FFT_MAX_N); return -1; }
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(n, &tw, st)) return rc;
+    switch (n) {
+#define X(N) case N: return launch_c2c_n<N>(d_in, in_stride, d_out, out_stride, batch, inverse != 0, tw, st);
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    return -1;
+}
+
+// ---- K9: overlap-add FIR bank -------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N))
+olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                   const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                   int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tail = s + N;
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const float inv_n = 1.0f / (float)N;                           // N is a power of two: exact, same as /N
+    // A block's result r[i] = ifft[i]/N + (i < overlap ? previous r[input_size + i] : 0)  (libcsdr.c:837-847 with the
+    // ping-pong output buffers of csdr.c:1852-1878).  When overlap > input_size the carried tail chains through
+    // ceil(overlap/input_size) earlier blocks, so a run that starts mid-stream recomputes that many lead-in blocks
+    // from a zero tail; everything that zero start gets wrong has been shifted out by the first emitted block.
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+    for (int b = b_start; b < b_last; b++) {
+        const bool emit = b >= b_first;
+        for (int i = tid; i < N; i += NT) s[i] = i < input_size ? x[(long)b * input_size + i] : make_float2(0.f, 0.f);
+        __syncthreads();
+        block_fft<N, NT, false>(s, tw, tid);
+        for (int i = tid; i < N; i += NT) {
+            const float2 a = s[i], h = H[i];
+            // same rounding sequence as libcsdr.c:827-828 (separate products, no FMA)
+            s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        }
+        __syncthreads();
+        block_fft<N, NT, true>(s, tw, tid);
+        for (int i = tid; i < N; i += NT) {
+            float2 v = make_float2(s[i].x * inv_n, s[i].y * inv_n);
+            if (i < overlap) v = make_float2(__fadd_rn(v.x, tail[i].x), __fadd_rn(v.y, tail[i].y));
+            s[i] = v;
+            if (emit && i < input_size) y[(long)b * input_size + i] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < overlap; i += NT) tail[i] = s[input_size + i];
+        __syncthreads();
+    }
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
+}
+
+int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int fft_size, int input_size,
+                       int nblocks, const float2* d_taps_fft, long taps_stride, float2* d_tail_io, int blocks_per_cta, cudaStream_t st)
+{
+    if (channels <= 0 || nblocks <= 0) return 0;
+    if (fft_size < 4 || fft_size > 8192 || (fft_size & (fft_size - 1))) { set_error("overlap-add FIR: fft_size %d unsupported (power of two, 4..8192)", fft_size); return -1; }
+    if (input_size <= 0 || input_size > fft_size) { set_error("overlap-add FIR: bad input_size %d for fft_size %d", input_size, fft_size); return -1; }
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
+    if (blocks_per_cta <= 0) {
+        // enough CTAs to fill the machine a few times over, but runs long enough that the recomputed lead-in block stays cheap
+        long want = (148L * 8 + channels - 1) / channels;
+        blocks_per_cta = (int)((nblocks + want - 1) / want);
+        if (blocks_per_cta < 16) blocks_per_cta = nblocks < 16 ? nblocks : 16;
+    }
+    const dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, channels);
+    const size_t smem = sizeof(float2) * 2 * (size_t)fft_size;
+    switch (fft_size) {
+#define X(N) case N: if constexpr (N >= 4 && N <= 8192) { auto k = olafir_bank_kernel<N>; \
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k<<<grid, fft_threads(N), smem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw); } break;
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ---- fastddc forward -------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N))
+fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, const float2* __restrict__ overlap_in,
+                   int input_size, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int overlap = N - input_size;
+    // block b transforms stream samples [b*input_size - overlap, (b+1)*input_size); negative positions come from the carried overlap
+    const long start = (long)b * input_size - overlap;
+    for (int i = tid; i < N; i += NT) {
+        const long p = start + i;
+        s[i] = p >= 0 ? in[p] : overlap_in[overlap + p];
+    }
+    __syncthreads();
+    block_fft<N, NT, false>(s, tw, tid);
+    float2* y = spectra + (long)b * N;
+    for (int i = tid; i < N; i += NT) y[i] = s[i];
+}
+
+__global__ void __launch_bounds__(1024)
+fastddc_carry_overlap_kernel(const float2* __restrict__ in, float2* __restrict__ overlap_io, int overlap, long total)
+{
+    // new carried overlap = last `overlap` samples of (old overlap ++ in[0..total)); one CTA, read everything, barrier, write
+    float2 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = threadIdx.x + k * 1024;
+        if (i < overlap) { const long p = total - overlap + i; v[k] = p >= 0 ? in[p] : overlap_io[overlap + p]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = threadIdx.x + k * 1024;
+        if (i < overlap) overlap_io[i] = v[k];
+    }
+}
+
+int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_io, int fft_size, int input_size, int nblocks, cudaStream_t st)
+{
+    if (nblocks <= 0) return 0;
+    if (fft_size < 4 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("fastddc_fwd: fft_size %d unsupported", fft_size); return -1; }
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
+    const size_t smem = sizeof(float2) * (size_t)fft_size;
+    switch (fft_size) {
+#define X(N) case N: if constexpr (N >= 4) { auto k = fastddc_fwd_kernel<N>; \
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k<<<nblocks, fft_threads(N), smem, st>>>(d_in, d_spectra, d_overlap_io, input_size, tw); } break;
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    const int overlap = fft_size - input_size;
+    if (overlap > 0) {
+        fastddc_carry_overlap_kernel<<<1, 1024, 0, st>>>(d_in, d_overlap_io, overlap, (long)nblocks * input_size);
+        CSDRB_CUDA(cudaGetLastError());
+        return 2;
+    }
+    return 1;
+}
+
+// ---- apply_fir_fft_cc drop-in (one block, explicit buffers) -------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N))
+apply_fir_fft_kernel(const float2* __restrict__ in, const float2* __restrict__ H, const float2* __restrict__ last_overlap, int overlap_size,
+                     float2* __restrict__ out, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < N; i += NT) s[i] = in[i];
+    __syncthreads();
+    block_fft<N, NT, false>(s, tw, tid);
+    for (int i = tid; i < N; i += NT) {
+        const float2 a = s[i], h = H[i];
+        s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+    }
+    __syncthreads();
+    block_fft<N, NT, true>(s, tw, tid);
+    const float inv_n = 1.0f / (float)N;
+    for (int i = tid; i < N; i += NT) {
+        float2 v = make_float2(s[i].x * inv_n, s[i].y * inv_n);
+        if (i < overlap_size) v = make_float2(__fadd_rn(v.x, last_overlap[i].x), __fadd_rn(v.y, last_overlap[i].y));
+        out[i] = v;
+    }
+}
+
+int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const float2* d_last_overlap, int overlap_size, float2* d_out,
+                         int fft_size, cudaStream_t st)
+{
+    if (fft_size < 2 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("apply_fir_fft: fft_size %d unsupported", fft_size); return -1; }
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
+    const size_t smem = sizeof(float2) * (size_t)fft_size;
+    switch (fft_size) {
+#define X(N) case N: { auto k = apply_fir_fft_kernel<N>; \
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k<<<1, fft_threads(N), smem, st>>>(d_in, d_taps_fft, d_last_overlap, overlap_size, d_out, tw); } break;
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// ---- fastddc inverse bank ----------------------------------------------------------------------------
+struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per channel: fastddc_t.offsetbin + dsadata
+
+#define PI_F 3.14159265358979323846f
+__device__ __forceinline__ float ddc_wrap(float ph)
+{
+    while (ph > PI_F) ph = __fsub_rn(ph, __fmul_rn(2.f, PI_F));
+    while (ph < -PI_F) ph = __fadd_rn(ph, __fmul_rn(2.f, PI_F));
+    return ph;
+}
+
+// per channel: walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
+__global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
+                                           int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
+                                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    int remain = remain_io[c], off = 0;
+    float ph = phase_io[c];
+    const float rate = chan[c].rate;
+    for (int b = 0; b < nblocks; b++) {
+        blk_remain[(long)c * nblocks + b] = remain;
+        blk_phase[(long)c * nblocks + b] = ph;
+        blk_offset[(long)c * nblocks + b] = off;
+        int k = 0, pos = remain;
+        if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
+        remain = pos - post_input_size;
+        ph = ddc_wrap(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate, PI_F), (float)k)));
+        off += k;
+    }
+    remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off;
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
+                   const int* __restrict__ blk_remain, const float* __restrict__ blk_phase, const int* __restrict__ blk_offset,
+                   float2* __restrict__ out, long out_stride, int N, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                   int nblocks, const float2* __restrict__ tw)
+{
+    __shared__ float2 s[M];
+    constexpr int NT = 256;
+    static_assert(M <= 16 * NT, "fft_inv_size too large for this kernel");
+    const int tid = threadIdx.x, b = blockIdx.x, c = blockIdx.y;
+    const float2* X = spectra + (long)b * N;
+    const float2* H = taps_fft + (long)c * N;
+    const DdcChan cp = chan[c];
+    const int half = N / 2;
+    // fold: inv_input[(N + i - offsetbin + M/2) % M] += Xs[i] * H[i], Xs = spectrum with halves swapped (fastddc.c:123-141)
+    // destination depends on i mod M only; each thread owns whole residue classes and adds in ascending i like the reference.
+    const float inv_pre = 1.0f / (float)pre_decimation;            // power of two: exact
+    for (int r = tid; r < M; r += NT) {
+        float ai = 0.f, aq = 0.f;
+        for (int i = r; i < N; i += M) {
+            const float2 x = X[i < half ? i + half : i - half];
+            const float2 h = H[i];
+            ai = __fadd_rn(ai, __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y)));
+            aq = __fadd_rn(aq, __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x)));
+        }
+        int dst = (N + r - cp.offsetbin + M / 2) % M;
+        if (dst < 0) dst += M;
+        // second swap (fastddc.c:150) folded into the store index
+        const int d2 = dst < M / 2 ? dst + M / 2 : dst - M / 2;
+        s[d2] = make_float2(ai * inv_pre, aq * inv_pre);
+    }
+    __syncthreads();
+    block_fft<M, NT, true>(s, tw, tid);
+    // normalise, drop the scrap, post shift + decimate (sequential phasor chain: one thread)
+    if (tid == 0) {
+        const float inv_m = 1.0f / (float)M;
+        const long bi = (long)c * nblocks + b;
+        const double ph = (double)blk_phase[bi];
+        float co = (float)cos(ph), si = (float)sin(ph);
+        float2* y = out + (long)c * out_stride + blk_offset[bi];
+        int k = 0;
+        for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
+            const float2 v = make_float2(s[scrap + pos].x * inv_m, s[scrap + pos].y * inv_m);
+            y[k++] = make_float2(__fsub_rn(__fmul_rn(co, v.x), __fmul_rn(si, v.y)), __fadd_rn(__fmul_rn(si, v.x), __fmul_rn(co, v.y)));
+            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            co = cn; si = sn;
+        }
+    }
+}
+
+size_t fastddc_inv_scratch_bytes(int channels, int nblocks) { return (size_t)channels * nblocks * 12 + 64; }
+
+int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* d_taps_fft, const void* d_chan, int channels,
+                            int fft_size, int fft_inv_size, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                            int* d_remain_io, float* d_phase_io, float2* d_out, long out_stride, int* d_out_total,
+                            void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || nblocks <= 0) return 0;
+    if (fft_inv_size < 2 || fft_inv_size > 4096 || (fft_inv_size & (fft_inv_size - 1)) || fft_size % fft_inv_size) {
+        set_error("fastddc_inv: fft_inv_size %d unsupported (power of two, 2..4096, dividing fft_size %d)", fft_inv_size, fft_size); return -1;
+    }
+    if (!d_scratch || scratch_bytes < fastddc_inv_scratch_bytes(channels, nblocks)) { set_error("fastddc_inv: scratch too small"); return -1; }
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(fft_inv_size, &tw, st)) return rc;
+    int* blk_remain = static_cast<int*>(d_scratch);
+    float* blk_phase = reinterpret_cast<float*>(blk_remain + (size_t)channels * nblocks);
+    int* blk_offset = reinterpret_cast<int*>(blk_phase + (size_t)channels * nblocks);
+    fastddc_state_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
+    CSDRB_CUDA(cudaGetLastError());
+    const dim3 grid(nblocks, channels);
+    switch (fft_inv_size) {
+#define X(M) case M: if constexpr (M <= 4096) { fastddc_inv_kernel<M><<<grid, 256, 0, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, \
+        blk_phase, blk_offset, d_out, out_stride, fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, tw); } break;
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+}  // namespace csdrb

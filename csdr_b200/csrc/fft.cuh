@@ -1,0 +1,129 @@
+// fft.cuh -- K7: block-level Stockham autosort FFT in shared memory (no cuFFT), power-of-two sizes.
+//
+// Stands behind the reference's FFT abstraction (fft_fftw.c:6-41: unnormalised DFT, exponent sign -1
+// forward / +1 backward).  One CTA transforms one N-point signal that already sits in shared memory.
+//
+// Pass structure (validated against numpy in the design notes): radices are
+// [2 or 4 (if log2 N is not a multiple of 3)] followed by radix-8 passes.  For a pass of radix R over
+// sub-transforms of size Ns (Ns = product of the previous radices), butterfly j in [0, N/R):
+//     k = j mod Ns;   v[r] = s[j + r*N/R] * W_N^(k*r*N/(Ns*R));   V = DFT_R(v);   s'[(j/Ns)*Ns*R + k + r*Ns] = V[r]
+// All threads read their butterflies into registers, synchronise, then write: one buffer is enough
+// (a thread holds at most 16 points per pass, so NT >= N/16 threads are required).
+// Twiddles come from a per-size table W_N^k = exp(-2*pi*i*k/N) computed in double on the host and
+// rounded once to float (error ~6e-8 per twiddle; the whole transform stays ~1e-7*log2 N from the exact DFT).
+#pragma once
+#include "common.cuh"
+
+namespace csdrb {
+
+template <bool INV>
+__device__ __forceinline__ float2 cmul_w(float2 a, float2 w)
+{
+    // a * w (forward) or a * conj(w) (inverse)
+    return INV ? make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y))
+               : make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.y, w.x, a.x * w.y));
+}
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a)       // a * (-i) forward, a * (+i) inverse
+{
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+template <bool INV>
+__device__ __forceinline__ void dft2(float2& a, float2& b) { float2 t = a; a = cadd(t, b); b = csub(t, b); }
+
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3)
+{
+    const float2 a0 = cadd(v0, v2), a1 = csub(v0, v2), a2 = cadd(v1, v3), a3 = mul_mi<INV>(csub(v1, v3));
+    v0 = cadd(a0, a2); v2 = csub(a0, a2); v1 = cadd(a1, a3); v3 = csub(a1, a3);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft8(float2 (&v)[8])
+{
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4<INV>(e0, e1, e2, e3);
+    dft4<INV>(o0, o1, o2, o3);
+    const float h = 0.70710678118654752440f;
+    // W8^1 = h*(1 -+ i), W8^2 = -+i, W8^3 = h*(-1 -+ i)
+    const float2 t1 = INV ? make_float2(h * (o1.x - o1.y), h * (o1.x + o1.y)) : make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));
+    const float2 t2 = mul_mi<INV>(o2);
+    const float2 t3 = INV ? make_float2(-h * (o3.x + o3.y), h * (o3.x - o3.y)) : make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
+    v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
+    v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft_small(float2 (&v)[R])
+{
+    if constexpr (R == 2) dft2<INV>(v[0], v[1]);
+    else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else dft8<INV>(v);
+}
+
+template <int N, int NT, int R, int NS, bool INV>
+__device__ __forceinline__ void fft_pass(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
+{
+    constexpr int NB = N / R;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    float2 v[PER][R];
+#pragma unroll
+    for (int b = 0; b < PER; b++) {
+        const int j = tid + b * NT;
+        if (NB % NT == 0 || j < NB) {
+#pragma unroll
+            for (int r = 0; r < R; r++) v[b][r] = s[j + r * NB];
+            if constexpr (NS > 1) {
+                const int k = j % NS;
+#pragma unroll
+                for (int r = 1; r < R; r++) v[b][r] = cmul_w<INV>(v[b][r], __ldg(tw + k * r * (N / (NS * R))));
+            }
+            dft_small<R, INV>(v[b]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < PER; b++) {
+        const int j = tid + b * NT;
+        if (NB % NT == 0 || j < NB) {
+            const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+            for (int r = 0; r < R; r++) s[j0 + r * NS] = v[b][r];
+        }
+    }
+    __syncthreads();
+}
+
+template <int N, int NT, int NS, bool INV>
+__device__ __forceinline__ void fft_r8_passes(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
+{
+    if constexpr (NS < N) {
+        fft_pass<N, NT, 8, NS, INV>(s, tw, tid);
+        fft_r8_passes<N, NT, NS * 8, INV>(s, tw, tid);
+    }
+}
+
+constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n / 2); }
+
+// In-place N-point transform of s[0..N) by a CTA of NT threads (all NT threads must call; s must be
+// visible to the CTA, i.e. a __syncthreads() separates the last write to s from this call).
+template <int N, int NT, bool INV>
+__device__ __forceinline__ void block_fft(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
+{
+    static_assert((N & (N - 1)) == 0 && N >= 2, "power of two sizes only");
+    constexpr int LG = ilog2_c(N);
+    if constexpr (LG % 3 == 1) { fft_pass<N, NT, 2, 1, INV>(s, tw, tid); fft_r8_passes<N, NT, 2, INV>(s, tw, tid); }
+    else if constexpr (LG % 3 == 2) { fft_pass<N, NT, 4, 1, INV>(s, tw, tid); fft_r8_passes<N, NT, 4, INV>(s, tw, tid); }
+    else fft_r8_passes<N, NT, 1, INV>(s, tw, tid);
+}
+
+constexpr int fft_threads(int n) { return n / 16 < 32 ? 32 : n / 16; }
+constexpr int FFT_MAX_N = 16384;
+
+}  // namespace csdrb

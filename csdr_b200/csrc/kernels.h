@@ -17,4 +17,32 @@ int launch_convert_f_s16(const float* d_in, short* d_out, long n, cudaStream_t s
 int launch_fmdemod_quadri_bank(const float2* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
                                const float2* d_last_in, float2* d_last_out, cudaStream_t st);
 
+// K2 shift.cu
+size_t shift_bank_scratch_bytes(int channels, int n, int chunk);
+int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                               const float* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+int launch_decimating_shift_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                                 const float* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size, cudaStream_t st);
+
+// K5/K6 audio.cu
+size_t fracdec_scratch_bytes(int channels, int n, float rate);
+int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
+                                     float rate, int num_poly_points, const float* d_taps, int taps_length, void* d_state,
+                                     void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+int launch_fastagc_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks,
+                        float reference, void* d_state, float* d_hist, cudaStream_t st);
+
+// K7/K8/K9 fft.cu
+int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long out_stride, int n, int batch, int inverse, cudaStream_t st);
+int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int fft_size, int input_size,
+                       int nblocks, const float2* d_taps_fft, long taps_stride, float2* d_tail_io, int blocks_per_cta, cudaStream_t st);
+int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const float2* d_last_overlap, int overlap_size, float2* d_out,
+                         int fft_size, cudaStream_t st);
+int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_io, int fft_size, int input_size, int nblocks, cudaStream_t st);
+size_t fastddc_inv_scratch_bytes(int channels, int nblocks);
+int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* d_taps_fft, const void* d_chan, int channels,
+                            int fft_size, int fft_inv_size, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                            int* d_remain_io, float* d_phase_io, float2* d_out, long out_stride, int* d_out_total,
+                            void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+
 }  // namespace csdrb

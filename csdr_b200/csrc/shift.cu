@@ -1,0 +1,171 @@
+// shift.cu -- K2: NCO frequency shift by phasor recursion, faithful to the reference's float arithmetic.
+//
+// Replaces shift_addition_cc (libcsdr_gpl.c:27-52) and decimating_shift_addition_cc (libcsdr_gpl.c:131-160).
+//
+// The reference's result IS its rounding sequence (hard part 2): inside one call the
+// phasor (cos phi, sin phi) is advanced by   c' = c*cosd - s*sind ;  s' = s*cosd + c*sind   in fp32 with
+// separately rounded products (x86 SSE, no FMA); between calls the float phase is advanced by
+// rate*PI*n and wrapped with while loops, and every call re-seeds the phasor from cos/sin of that float
+// phase evaluated in double.  How a stream is cut into calls ("chunks", <= 1024 samples in the CLI,
+// csdr.c:911-918) is therefore a parameter of the bank.
+//
+// Kernels:
+//   shift_phase_chain_kernel : one thread per channel walks the chunk-to-chunk float phase chain
+//                              (sequential by definition, a few thousand steps) and stores each chunk's seed phase.
+//   shift_bank_kernel        : one lane per (channel, chunk) runs the <=chunk-step recursion; a warp owns 32
+//                              consecutive chunks and moves data through a padded shared tile so that every
+//                              global access is a coalesced 256-byte row while each lane walks its own row.
+//   dshift_kernel            : decimating variant, one thread per channel (chains of a few hundred outputs).
+// All products/sums use __fmul_rn/__fadd_rn/__fsub_rn so nvcc cannot contract them into FMAs.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace csdrb {
+
+#define PI_F 3.14159265358979323846f            // (float)3.14159265358979323846, libcsdr.h:65
+
+__device__ __forceinline__ float wrap_pm_pi(float ph)
+{
+    while (ph > PI_F) ph = __fsub_rn(ph, __fmul_rn(2.f, PI_F));
+    while (ph < -PI_F) ph = __fadd_rn(ph, __fmul_rn(2.f, PI_F));
+    return ph;
+}
+__device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
+{
+    // starting_phase += d.rate*PI*input_size  (float*float -> float, * (float)int -> float, += float)
+    return wrap_pm_pi(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate2, PI_F), (float)n)));
+}
+
+__global__ void shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                                         int channels, int n, int chunk, int nchunks)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const float rate2 = params[c].z;
+    float ph = phase_io[c];
+    for (int k = 0; k < nchunks; k++) {
+        chunk_phase[(long)c * nchunks + k] = ph;
+        const int len = min(chunk, n - k * chunk);
+        ph = advance_phase(ph, rate2, len);
+    }
+    phase_io[c] = ph;
+}
+
+constexpr int SH_TILE = 32;                       // samples per lane per sub-step
+constexpr int SH_PITCH = SH_TILE + 1;             // odd pitch in 8-byte units: row-wise walks are conflict-free
+
+__global__ void __launch_bounds__(128)
+shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                  const float3* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks)
+{
+    __shared__ float2 tile_all[4][32 * SH_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = tile_all[warp];
+    const int ch = blockIdx.y;
+    const int k0 = (blockIdx.x * 4 + warp) * 32;              // first chunk of this warp
+    if (k0 >= nchunks) return;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float3 p = params[ch];
+    const float sind = p.x, cosd = p.y;
+    const int k = k0 + lane;
+    const bool live = k < nchunks;
+    const int my_len = live ? min(chunk, n - k * chunk) : 0;
+    float c = 0.f, s = 0.f;
+    if (live) {
+        const double ph = (double)chunk_phase[(long)ch * nchunks + k];
+        c = (float)cos(ph); s = (float)sin(ph);
+    }
+    const int rows = min(32, nchunks - k0);
+    const int max_len = min(chunk, n - k0 * chunk);          // the first chunk of the warp is never the short one
+    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
+        // coalesced load: row r = chunk k0+r, 32 consecutive samples starting at t0
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * chunk + t0 + lane;
+            const int len_r = min(chunk, n - (k0 + r) * chunk);
+            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+        if (live) {
+            float2* row = tile + lane * SH_PITCH;
+            const int steps = min(SH_TILE, my_len - t0);
+            for (int j = 0; j < steps; j++) {
+                const float2 v = row[j];
+                row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
+                const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
+                c = cn; s = sn;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * chunk + t0 + lane;
+            const int len_r = min(chunk, n - (k0 + r) * chunk);
+            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
+        }
+        __syncwarp();
+    }
+}
+
+// decimating variant: status per channel {decimation_remain, starting_phase, output_size} (libcsdr_gpl.h:39-44)
+__global__ void dshift_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                              const float3* __restrict__ params, int n, int decimation, int* __restrict__ remain_io,
+                              float* __restrict__ phase_io, int* __restrict__ out_size, int channels)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= channels) return;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float3 p = params[ch];
+    const float ph0 = phase_io[ch];
+    float c = (float)cos((double)ph0), s = (float)sin((double)ph0);
+    int produced = 0, pos;
+    for (pos = remain_io[ch]; pos < n; pos += decimation) {
+        const float2 v = x[pos];
+        y[produced++] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+        const float cn = __fsub_rn(__fmul_rn(c, p.y), __fmul_rn(s, p.x));
+        const float sn = __fadd_rn(__fmul_rn(s, p.y), __fmul_rn(c, p.x));
+        c = cn; s = sn;
+    }
+    remain_io[ch] = pos - n;
+    phase_io[ch] = advance_phase(ph0, p.z, produced);
+    if (out_size) out_size[ch] = produced;
+}
+
+size_t shift_bank_scratch_bytes(int channels, int n, int chunk)
+{
+    if (chunk <= 0 || chunk > n) chunk = n > 0 ? n : 1;
+    const int nchunks = (n + chunk - 1) / chunk;
+    return (size_t)channels * (size_t)(nchunks > 0 ? nchunks : 1) * sizeof(float);
+}
+
+int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                               const float* d_params /*[C][3] sindelta,cosdelta,rate*/, float* d_phase_io, int chunk,
+                               void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if (chunk <= 0 || chunk > n) chunk = n;
+    const int nchunks = (n + chunk - 1) / chunk;
+    if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addition bank: scratch too small"); return -1; }
+    float* chunk_phase = static_cast<float*>(d_scratch);
+    shift_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    dim3 grid((nchunks + 127) / 128, channels);
+    shift_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, reinterpret_cast<const float3*>(d_params), chunk_phase, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+int launch_decimating_shift_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                                 const float* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size,
+                                 cudaStream_t st)
+{
+    if (channels <= 0) return 0;
+    if (decimation <= 0) { set_error("decimating_shift_addition bank: decimation must be positive"); return -1; }
+    dshift_kernel<<<(channels + 63) / 64, 64, 0, st>>>(d_in, in_stride, d_out, out_stride, reinterpret_cast<const float3*>(d_params), n, decimation,
+                                                       d_remain_io, d_phase_io, d_out_size, channels);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace csdrb

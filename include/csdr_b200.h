@@ -149,6 +149,55 @@ void  csdrb_host_free(void *p);
 int csdrb_fmdemod_quadri_bank_cf(const complexf *d_in, long in_stride, float *d_out, long out_stride, int channels,
                                  int input_size, const complexf *d_last_in, complexf *d_last_out, void *stream);
 
+/* K2 shift_addition_cc bank.  in_stride == 0: every channel shifts the SAME wideband input (ddcd use case).
+ * d_params[c] = shift_addition_init(rate_c) computed on the host (bit-exact sin/cos deltas); d_phase_io[c] is the
+ * starting phase on entry and the phase to continue from on return.  `chunk` is how the reference caller cuts
+ * the stream into shift_addition_cc() calls (the CLI uses 1024, csdr.c:911-918; <= 0 means one call).
+ * Scratch: csdrb_shift_addition_bank_scratch_bytes() bytes of device memory. */
+size_t csdrb_shift_addition_bank_scratch_bytes(int channels, int input_size, int chunk);
+int csdrb_shift_addition_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
+                                 const shift_addition_data_t *d_params, float *d_phase_io, int chunk,
+                                 void *d_scratch, size_t scratch_bytes, void *stream);
+int csdrb_decimating_shift_addition_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels,
+                                            int input_size, const shift_addition_data_t *d_params, int decimation,
+                                            int *d_remain_io, float *d_phase_io, int *d_out_size, void *stream);
+
+/* K5 fractional_decimator_ff bank: d_state[c].where carries the reference's `where`; on return input_processed
+ * and output_size are filled like fractional_decimator_ff() fills them (libcsdr.c:789-792). */
+typedef struct csdrb_fracdec_state_s { float where; int input_processed; int output_size; } csdrb_fracdec_state_t;
+size_t csdrb_fractional_decimator_bank_scratch_bytes(int channels, int input_size, float rate);
+int csdrb_fractional_decimator_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
+                                       float rate, int num_poly_points, const float *d_taps, int taps_length,
+                                       csdrb_fracdec_state_t *d_state, void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* K6 fastagc_ff bank: nblocks consecutive blocks of `block` samples per channel; d_hist is [channels][2][block]
+ * (the reference's buffer_1, buffer_2; zero it at stream start), d_state[c] = {peak_1, peak_2, last_gain}. */
+typedef struct csdrb_fastagc_state_s { float peak_1, peak_2, last_gain; } csdrb_fastagc_state_t;
+int csdrb_fastagc_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int block, int nblocks,
+                          float reference, csdrb_fastagc_state_t *d_state, float *d_hist, void *stream);
+
+/* K7 batched unnormalised c2c DFT (power-of-two size 2..16384), sign -1 forward / +1 inverse */
+int csdrb_fft_c2c_batch(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int size, int batch, int inverse, void *stream);
+
+/* K9 overlap-add FFT filter bank = bandpass_fir_fft_cc block loop (csdr.c:1872-1883) for many channels.
+ * d_taps_fft: FFT of the zero-padded taps (taps_stride 0 = shared); d_tail_io [channels][fft_size] carries the
+ * previous block's tail between calls (zero at stream start). nblocks blocks of input_size samples per channel. */
+int csdrb_bandpass_fir_fft_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int fft_size,
+                                   int input_size, int nblocks, const complexf *d_taps_fft, long taps_stride, complexf *d_tail_io, void *stream);
+
+/* fastddc forward step (csdr.c:2288-2299): nblocks x input_size new samples -> nblocks x fft_size bins;
+ * d_overlap_io [fft_size - input_size] carries the overlap between calls (zero at stream start). */
+int csdrb_fastddc_fwd_cc(const complexf *d_in, complexf *d_spectra, complexf *d_overlap_io, int fft_size, int input_size, int nblocks, void *stream);
+
+/* K8 fastddc_inv_cc bank: every channel c (its own d_taps_fft + c*fft_size, offsetbin and post-shift NCO) consumes the
+ * same nblocks spectra.  d_remain_io/d_phase_io carry decimating_shift_addition_status_t between calls;
+ * d_out_total[c] receives the samples written for channel c.  `geometry` is a HOST fastddc_t (fastddc_init). */
+typedef struct csdrb_fastddc_chan_s { int offsetbin; float sindelta, cosdelta, rate; } csdrb_fastddc_chan_t;
+size_t csdrb_fastddc_inv_bank_scratch_bytes(int channels, int nblocks);
+int csdrb_fastddc_inv_bank_cc(const complexf *d_spectra, int nblocks, const complexf *d_taps_fft, const csdrb_fastddc_chan_t *d_chan,
+                              int channels, const fastddc_t *geometry, int *d_remain_io, float *d_phase_io, complexf *d_out,
+                              long out_stride, int *d_out_total, void *d_scratch, size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
