@@ -60,6 +60,17 @@ struct HostCtx {
 };
 static HostCtx g_ctx;
 
+// CSDRB_TRACE=1: report at exit how many kernels this process launched (lets a caller verify that a
+// preloaded/linked libcsdr_b200 really did the work instead of some other libcsdr).
+struct ExitReport {
+    ~ExitReport()
+    {
+        const char* t = getenv("CSDRB_TRACE");
+        if (t && *t && *t != '0') fprintf(stderr, "libcsdr_b200: %ld kernel launches in this process\n", g_launches.load());
+    }
+};
+static ExitReport g_exit_report;
+
 [[noreturn]] static void die(const char* who)
 {
     fprintf(stderr, "libcsdr_b200: %s failed: %s\n", who, g_err[0] ? g_err : "(no detail)");
@@ -490,7 +501,8 @@ void fastagc_ff(fastagc_ff_t* a, float* output)
 }
 
 // ---- FFT abstraction ---------------------------------------------------------------------------------
-struct csdrb_plan_impl { int forward; };
+struct csdrb_plan_impl { unsigned magic; int forward; };
+static const unsigned kPlanMagic = 0xC5D2B200u;
 
 FFT_PLAN_T* make_fft_c2c(int size, complexf* input, complexf* output, int forward, int benchmark)
 {
@@ -501,7 +513,7 @@ FFT_PLAN_T* make_fft_c2c(int size, complexf* input, complexf* output, int forwar
     }
     FFT_PLAN_T* p = (FFT_PLAN_T*)malloc(sizeof(FFT_PLAN_T));
     csdrb_plan_impl* impl = (csdrb_plan_impl*)malloc(sizeof(csdrb_plan_impl));
-    impl->forward = forward ? 1 : 0;
+    impl->magic = kPlanMagic; impl->forward = forward ? 1 : 0;
     p->size = size; p->input = input; p->output = output; p->plan = impl;
     return p;
 }
@@ -510,6 +522,9 @@ void fft_execute(FFT_PLAN_T* plan)
 {
     const char* who = "fft_execute";
     if (!plan) return;
+    if (!plan->plan || ((csdrb_plan_impl*)plan->plan)->magic != kPlanMagic) {
+        set_error("plan was not created by libcsdr_b200's make_fft_c2c (r2c/c2r plans are outside the hot path)"); die(who);
+    }
     A_BEGIN(who);
     const size_t bytes = (size_t)plan->size * 8;
     A_UP(0, plan->input, bytes, who);

@@ -1,0 +1,139 @@
+"""GPU tests (-m gpu) of the stdin/stdout command surface: our C host CLI (csdr_b200/csdr, computing on the GPU through
+libcsdr_b200.so) against the UNMODIFIED reference CLI (oracle/_ref/csdr_ref, built from /root/reference/csdr.c) on the same
+pipe graphs, plus the LD_PRELOAD drop-in: the reference's own binary running on top of our library."""
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = Path(__file__).resolve().parent.parent
+OURS = ROOT / "csdr_b200" / "csdr"
+LIB = ROOT / "csdr_b200" / "libcsdr_b200.so"
+REF = ROOT / "oracle" / "_ref" / "csdr_ref"
+
+
+@pytest.fixture(scope="module")
+def clis():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    if not REF.exists():
+        pytest.skip("oracle/_ref/csdr_ref not built")
+    from csdr_b200.build import build
+    build()
+    assert OURS.exists() and LIB.exists()
+    return str(OURS), str(REF)
+
+
+def run_graph(cli, stages, data: bytes, env=None, timeout=120) -> bytes:
+    cmd = " | ".join(f"{cli} {s}" for s in stages)
+    e = dict(os.environ); e.update(env or {})
+    r = subprocess.run(["bash", "-c", cmd], input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=timeout)
+    assert r.returncode == 0, (cmd, r.stderr[-2000:])
+    return r.stdout
+
+
+def rel(a, b):
+    from oracle.pyoracle import rel_rms
+    return rel_rms(a, b)
+
+
+def fm_u8(n, seed=0):
+    """u8 IQ of an FM-modulated carrier + a little noise (so the discriminator has a defined output)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    ph = np.cumsum(0.05 * np.sin(2 * np.pi * t / 4000.0)) + 2 * np.pi * 0.01 * t
+    z = 0.7 * np.exp(1j * ph) + 0.01 * (rng.normal(size=n) + 1j * rng.normal(size=n))
+    iq = np.empty(2 * n, np.float64); iq[0::2] = z.real; iq[1::2] = z.imag
+    return np.clip(np.floor(iq * 127.5 + 128), 0, 255).astype(np.uint8).tobytes()
+
+
+def test_config1_graph_matches_reference_cli(clis):
+    """BASELINE configs[0]: convert_u8_f | fir_decimate_cc 10 0.05 HAMMING | fmdemod_quadri_cf on 1 M u8 IQ samples."""
+    ours, ref = clis
+    data = fm_u8(1_000_000)
+    stages = ["convert_u8_f", "fir_decimate_cc 10 0.05 HAMMING", "fmdemod_quadri_cf"]
+    a = np.frombuffer(run_graph(ours, stages, data), np.float32)
+    b = np.frombuffer(run_graph(ref, stages, data), np.float32)
+    assert a.size == b.size and a.size > 90_000                     # identical framing, including the stale tail blocks at EOF
+    assert rel(a, b) < 1e-5
+    # stage by stage: the byte conversion is bit-exact, framing identical
+    a1 = run_graph(ours, stages[:1], data); b1 = run_graph(ref, stages[:1], data)
+    assert a1 == b1
+    a2 = np.frombuffer(run_graph(ours, stages[:2], data), np.complex64); b2 = np.frombuffer(run_graph(ref, stages[:2], data), np.complex64)
+    assert a2.size == b2.size and rel(a2, b2) < 1e-5
+
+
+def test_eof_framing_quirks(clis):
+    ours, ref = clis
+    for nbytes in (2048, 2000, 1, 1024, 5000):
+        data = bytes(np.random.default_rng(nbytes).integers(0, 256, nbytes, dtype=np.uint8))
+        a = run_graph(ours, ["convert_u8_f"], data); b = run_graph(ref, ["convert_u8_f"], data)
+        assert len(a) == len(b), nbytes                              # e.g. 2048 B in -> 3 blocks (12288 B) out, 2000 B -> 2 blocks
+        n = (nbytes // 1024) * 1024 * 4
+        assert a[:n] == b[:n]
+    x = np.random.default_rng(1).uniform(-1, 1, 40_000).astype(np.float32).tobytes()
+    assert run_graph(ours, ["convert_f_s16"], x) == run_graph(ref, ["convert_f_s16"], x)
+    s = np.random.default_rng(2).integers(-32768, 32767, 30_000).astype(np.int16).tobytes()
+    assert run_graph(ours, ["convert_s16_f"], s) == run_graph(ref, ["convert_s16_f"], s)
+
+
+def test_nfm_style_chain(clis):
+    """shift | fir_decimate | fmdemod | fractional_decimator | fastagc | convert_f_s16 (the README.md:87 NFM graph minus limit/deemphasis)."""
+    ours, ref = clis
+    n = 600_000
+    rng = np.random.default_rng(5)
+    t = np.arange(n)
+    z = (0.5 * np.exp(1j * (2 * np.pi * 0.2 * t + np.cumsum(0.02 * np.sin(2 * np.pi * t / 3000.0)))) +
+         0.01 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
+    stages = ["shift_addition_cc -0.2", "fir_decimate_cc 10 0.05 HAMMING", "fmdemod_quadri_cf", "fractional_decimator_ff 1.25", "fastagc_ff 1024 0.5"]
+    a = np.frombuffer(run_graph(ours, stages, z.tobytes()), np.float32)
+    b = np.frombuffer(run_graph(ref, stages, z.tobytes()), np.float32)
+    assert a.size == b.size and a.size > 40_000
+    assert rel(a, b) < 1e-5
+    a16 = np.frombuffer(run_graph(ours, stages + ["convert_f_s16"], z.tobytes()), np.int16)
+    b16 = np.frombuffer(run_graph(ref, stages + ["convert_f_s16"], z.tobytes()), np.int16)
+    assert a16.size == b16.size and np.abs(a16.astype(np.int32) - b16.astype(np.int32)).max() <= 1     # float->short of values equal to 1e-5
+
+
+def test_fft_commands(clis):
+    ours, ref = clis
+    rng = np.random.default_rng(7)
+    z = (rng.uniform(-1, 1, 120_000) + 1j * rng.uniform(-1, 1, 120_000)).astype(np.complex64)
+    for stages in (["bandpass_fir_fft_cc -0.05 0.05 0.002 HAMMING"], ["bandpass_fir_fft_cc 0.1 0.3 0.05"],
+                   ["fastddc_fwd_cc 64 0.002", "fastddc_inv_cc 0.1 64 0.002"], ["fastddc_fwd_cc 8", "fastddc_inv_cc -0.21 8"]):
+        a = np.frombuffer(run_graph(ours, stages, z.tobytes()), np.complex64)
+        b = np.frombuffer(run_graph(ref, stages, z.tobytes()), np.complex64)
+        assert a.size == b.size and a.size > 0, stages
+        assert rel(a, b) < 1e-5, stages
+
+
+def test_dynamic_bufsize_preamble(clis):
+    ours, ref = clis
+    z = np.random.default_rng(9).uniform(-1, 1, 2 * 70_000).astype(np.float32)
+    head = b"csdr" + np.array([2048], np.int32).tobytes()
+    env = {"CSDR_DYNAMIC_BUFSIZE_ON": "1"}
+    stages = ["fir_decimate_cc 10 0.05 HAMMING", "fmdemod_quadri_cf"]
+    a = run_graph(ours, stages, head + z.tobytes(), env); b = run_graph(ref, stages, head + z.tobytes(), env)
+    assert a[:8] == b[:8] and len(a) == len(b)                       # the next-stage preamble is forwarded identically
+    assert rel(np.frombuffer(a[8:], np.float32), np.frombuffer(b[8:], np.float32)) < 1e-5
+
+
+def test_reference_binary_runs_on_our_library(clis):
+    """Drop-in at the dynamic-link boundary: the reference's own csdr binary with libcsdr_b200.so preloaded computes its
+    hot-path functions on the GPU (every other symbol still resolves to the reference library)."""
+    ours, ref = clis
+    data = fm_u8(300_000, seed=3)
+    stages = ["convert_u8_f", "fir_decimate_cc 10 0.05 HAMMING", "fmdemod_quadri_cf"]
+    plain = np.frombuffer(run_graph(ref, stages, data), np.float32)
+    pre = np.frombuffer(run_graph(ref, stages, data, env={"LD_PRELOAD": str(LIB), "CSDRB_TRACE": "1"}), np.float32)
+    assert pre.size == plain.size and rel(pre, plain) < 1e-5
+    assert not np.array_equal(pre, plain) or True                    # (sums are ordered differently on the GPU; equality is not required)
+    # prove the preloaded library actually did the work: it counts its kernel launches and reports them at exit
+    e = dict(os.environ); e.update({"LD_PRELOAD": str(LIB), "CSDRB_TRACE": "1"})
+    r = subprocess.run(["bash", "-c", f"{ref} fir_decimate_cc 10 0.05 HAMMING"], input=np.zeros(2 * 40000, np.float32).tobytes(),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=60)
+    assert b"libcsdr_b200: " in r.stderr and b"kernel launches" in r.stderr, r.stderr[-500:]
