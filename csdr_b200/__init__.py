@@ -90,9 +90,12 @@ def lib() -> C.CDLL:
     L.csdrb_decimating_shift_addition_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, it, vp, vp, vp, vp]
     L.csdrb_fractional_decimator_bank_scratch_bytes.argtypes = [it, it, C.c_float]; L.csdrb_fractional_decimator_bank_scratch_bytes.restype = sz
     L.csdrb_fractional_decimator_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, it, vp, vp, sz, vp]
-    L.csdrb_fastagc_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp, vp, vp]
+    L.csdrb_fastagc_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastagc_bank_scratch_bytes.restype = sz
+    L.csdrb_fastagc_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp, vp, vp, sz, vp]
     L.csdrb_fft_c2c_batch.argtypes = [vp, lg, vp, lg, it, it, it, vp]
     L.csdrb_bandpass_fir_fft_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, it, vp, lg, vp, vp]
+    L.csdrb_ddc_bank_scratch_bytes.argtypes = [it, it, it, it]; L.csdrb_ddc_bank_scratch_bytes.restype = sz
+    L.csdrb_ddc_bank.argtypes = [vp, it, it, vp, vp, it, it, it, C.POINTER(C.c_float), it, it, vp, lg, vp, vp, vp, sz, vp]
     L.csdrb_fastddc_fwd_cc.argtypes = [vp, vp, vp, it, it, it, vp]
     L.csdrb_fastddc_inv_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastddc_inv_bank_scratch_bytes.restype = sz
     L.csdrb_fastddc_inv_bank_cc.argtypes = [vp, it, vp, vp, it, C.POINTER(FastDDC), vp, vp, vp, lg, vp, vp, sz, vp]
@@ -489,8 +492,9 @@ def fastagc_bank_ff(x, block: int = 1024, reference: float = 1.0, state=None, hi
     out = torch.empty((ch, nblocks * block), dtype=torch.float32, device=x.device)
     state = torch.zeros((ch, 3), dtype=torch.float32, device=x.device) if state is None else state
     hist = torch.zeros((ch, 2, block), dtype=torch.float32, device=x.device) if hist is None else hist
+    scratch = _scratch(lib().csdrb_fastagc_bank_scratch_bytes(ch, nblocks), x.device)
     _check(lib().csdrb_fastagc_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, block, nblocks, reference,
-                                       state.data_ptr(), hist.data_ptr(), _stream()), "fastagc_bank_ff")
+                                       state.data_ptr(), hist.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "fastagc_bank_ff")
     return out, state, hist
 
 
@@ -580,3 +584,28 @@ def fastddc_inv_bank_cc(spectra, shifts, decimation: int, transition_bw: float, 
                                            state["remain"].data_ptr(), state["phase"].data_ptr(), out.data_ptr(), out.stride(0), counts.data_ptr(),
                                            scratch.data_ptr(), scratch.numel(), _stream()), "fastddc_inv_bank_cc")
     return out, counts, state
+
+
+def ddc_bank(wide, rates, decimation: int, taps: np.ndarray, demod: bool = True, chunk: int = 1024, offset: int = 0,
+             phases=None, last=None, out=None):
+    """Fused shared-input bank: one wideband block [N] complex64 -> per channel shift | fir_decimate | (fmdemod).
+    Returns (out [C, n_out], new chunk-start phases [C], last baseband samples [C] or None)."""
+    import torch
+    assert wide.dtype == torch.complex64 and wide.is_cuda and wide.dim() == 1
+    rates = np.atleast_1d(np.asarray(rates, np.float32)); ch = rates.size
+    taps = np.ascontiguousarray(taps, np.float32)
+    n = wide.numel()
+    n_out = fir_out_len(n, decimation, taps.size)
+    dev = wide.device
+    params = torch.from_numpy(np.array([shift_addition_init(float(r)) for r in rates], np.float32)).to(dev)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=dev) if phases is None else phases.clone()
+    stride = n_out + (n_out & 1)
+    if out is None:
+        out = torch.empty((ch, stride), dtype=torch.float32 if demod else torch.complex64, device=dev)
+    last_out = torch.empty(ch, dtype=torch.complex64, device=dev) if demod else None
+    scratch = _scratch(lib().csdrb_ddc_bank_scratch_bytes(ch, n, chunk, offset), dev)
+    rc = _check(lib().csdrb_ddc_bank(wide.data_ptr(), n, ch, params.data_ptr(), d_phase.data_ptr(), chunk, offset, decimation, _fp(taps), taps.size,
+                                     1 if demod else 0, out.data_ptr(), out.stride(0), last.data_ptr() if last is not None else None,
+                                     last_out.data_ptr() if last_out is not None else None, scratch.data_ptr(), scratch.numel(), _stream()), "ddc_bank")
+    assert rc == n_out
+    return out[:, :n_out], d_phase, last_out

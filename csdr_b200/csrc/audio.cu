@@ -7,9 +7,9 @@
 //                                 (index_high, xwhere) per output -- sequential by definition, tiny;
 //      fracdec_interp_kernel    : one thread per output evaluates the Lagrange polynomial with the same
 //                                 operation order as the reference (IEEE mul/div/add, no contraction).
-// K6 replaces fastagc_ff (libcsdr.c:944-991; state struct libcsdr.h:118-128): one CTA per channel walks the
-//    blocks of its stream (the gain of block b depends on block b-1), block-wide |x| max reduction, linear
-//    gain ramp evaluated in double exactly as the C expression promotes it, two blocks of latency.
+// K6 replaces fastagc_ff (libcsdr.c:944-991; state struct libcsdr.h:118-128): fully parallel over (channel, block) -- the
+//    gain only depends on a three-block window of peaks; linear gain ramp evaluated in double exactly as the C
+//    expression promotes it, two blocks of latency.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -100,65 +100,105 @@ int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d
 }
 
 // ---------------------------------------------------------------------------------------------- K6
+// The gain of block b is reference / max(peak_b, peak_{b-1}, peak_{b-2}) (capped), ramped from the gain of block b-1, applied to
+// block b-2: nothing is sequential beyond a three-block window, so the bank runs fully parallel over (channel, block):
+//   fastagc_peaks_kernel : |x| maximum of every block                                 (reads the input once)
+//   fastagc_apply_kernel : recomputes target_b and target_{b-1} from the peaks window, writes block b-2 scaled by the ramp
+//   fastagc_carry_kernel : new history (last two input blocks), peaks and last gain for the next call
 struct FastAgcState { float peak_1, peak_2, last_gain; };
 
 __global__ void __launch_bounds__(256)
-fastagc_bank_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride, int block, int nblocks,
-                    float reference, FastAgcState* __restrict__ state, float* __restrict__ hist /*[C][2][block]*/)
+fastagc_peaks_kernel(const float* __restrict__ in, long in_stride, int block, int nblocks, float* __restrict__ peaks)
 {
     __shared__ float red[8];
-    __shared__ float s_peak;
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* x = in + (long)c * in_stride;
-    float* y = out + (long)c * out_stride;
-    float* h1 = hist + (long)c * 2 * block;      // block that leaves next (reference buffer_1)
-    float* h2 = h1 + block;                      // block after that     (reference buffer_2)
-    float peak_1 = state[c].peak_1, peak_2 = state[c].peak_2, last_gain = state[c].last_gain;
-    for (int b = 0; b < nblocks; b++) {
-        const float* cur = x + (long)b * block;
-        float m = 0.f;
-        for (int i = tid; i < block; i += blockDim.x) m = fmaxf(m, fabsf(cur[i]));
-        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) red[warp] = m;
-        __syncthreads();
-        if (tid == 0) { float t = red[0]; for (int w = 1; w < (int)(blockDim.x >> 5); w++) t = fmaxf(t, red[w]); s_peak = t; }
-        __syncthreads();
-        const float peak_in = s_peak;
-        float target_peak = peak_in;
-        if (target_peak < peak_2) target_peak = peak_2;
-        if (target_peak < peak_1) target_peak = peak_1;
-        float target = __fdiv_rn(reference, target_peak);
-        if (target > 50.f) target = 50.f;                               // FASTAGC_MAX_GAIN, libcsdr.c:944
-        // the block leaving now entered two calls ago: history for b < 2, otherwise the input itself
-        const float* leaving = b >= 2 ? x + (long)(b - 2) * block : (b == 0 ? h1 : h2);
-        for (int i = tid; i < block; i += blockDim.x) {
-            const float r = __fdiv_rn((float)i, (float)block);
-            const float gain = (float)((double)last_gain * (1.0 - (double)r) + (double)__fmul_rn(target, r));
-            y[(long)b * block + i] = __fmul_rn(leaving[i], gain);
-        }
-        peak_1 = peak_2; peak_2 = peak_in; last_gain = target;
-        __syncthreads();
-    }
-    // new history = the last two input blocks (or shifted old history when fewer than two arrived)
-    if (nblocks >= 2) {
-        for (int i = tid; i < block; i += blockDim.x) { h1[i] = x[(long)(nblocks - 2) * block + i]; h2[i] = x[(long)(nblocks - 1) * block + i]; }
-    } else if (nblocks == 1) {
-        for (int i = tid; i < block; i += blockDim.x) { h1[i] = h2[i]; }
-        __syncthreads();
-        for (int i = tid; i < block; i += blockDim.x) { h2[i] = x[i]; }
-    }
-    if (tid == 0) { state[c].peak_1 = peak_1; state[c].peak_2 = peak_2; state[c].last_gain = last_gain; }
+    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const float* cur = in + (long)c * in_stride + (long)b * block;
+    float m = 0.f;
+    for (int i = tid; i < block; i += blockDim.x) m = fmaxf(m, fabsf(cur[i]));
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) { float t = red[0]; for (int w = 1; w < (int)(blockDim.x >> 5); w++) t = fmaxf(t, red[w]); peaks[(long)c * nblocks + b] = t; }
 }
 
+__device__ __forceinline__ float agc_peak_at(const float* pk, const FastAgcState& st, int b)
+{
+    // peak of the block that entered at call b; b = -1 / -2 are the two blocks before this launch (state.peak_2 / peak_1)
+    return b >= 0 ? pk[b] : (b == -1 ? st.peak_2 : st.peak_1);
+}
+__device__ __forceinline__ float agc_target(const float* pk, const FastAgcState& st, int b, float reference)
+{
+    float t = agc_peak_at(pk, st, b);
+    const float p2 = agc_peak_at(pk, st, b - 1), p1 = agc_peak_at(pk, st, b - 2);
+    if (t < p2) t = p2;
+    if (t < p1) t = p1;
+    float g = __fdiv_rn(reference, t);
+    if (g > 50.f) g = 50.f;                                            // FASTAGC_MAX_GAIN, libcsdr.c:944
+    return g;
+}
+
+__global__ void __launch_bounds__(256)
+fastagc_apply_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride, int block, int nblocks,
+                     float reference, const FastAgcState* __restrict__ state, const float* __restrict__ hist, const float* __restrict__ peaks)
+{
+    const int b = blockIdx.x, c = blockIdx.y, tid = threadIdx.x;
+    const FastAgcState st = state[c];
+    const float* pk = peaks + (long)c * nblocks;
+    const float target = agc_target(pk, st, b, reference);
+    const float last_gain = b == 0 ? st.last_gain : agc_target(pk, st, b - 1, reference);
+    const float* x = in + (long)c * in_stride;
+    const float* h1 = hist + (long)c * 2 * block;
+    const float* leaving = b >= 2 ? x + (long)(b - 2) * block : (b == 0 ? h1 : h1 + block);
+    float* y = out + (long)c * out_stride + (long)b * block;
+    for (int i = tid; i < block; i += blockDim.x) {
+        const float r = __fdiv_rn((float)i, (float)block);
+        const float gain = (float)((double)last_gain * (1.0 - (double)r) + (double)__fmul_rn(target, r));
+        y[i] = __fmul_rn(leaving[i], gain);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fastagc_carry_kernel(const float* __restrict__ in, long in_stride, int block, int nblocks, float reference, FastAgcState* __restrict__ state,
+                     float* __restrict__ hist, const float* __restrict__ peaks)
+{
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const float* x = in + (long)c * in_stride;
+    float* h1 = hist + (long)c * 2 * block;
+    float* h2 = h1 + block;
+    if (nblocks >= 2) {
+        for (int i = tid; i < block; i += blockDim.x) { h1[i] = x[(long)(nblocks - 2) * block + i]; h2[i] = x[(long)(nblocks - 1) * block + i]; }
+    } else {
+        for (int i = tid; i < block; i += blockDim.x) { const float keep = h2[i]; h1[i] = keep; h2[i] = x[i]; }
+    }
+    if (tid == 0) {
+        const FastAgcState st = state[c];
+        const float* pk = peaks + (long)c * nblocks;
+        FastAgcState nx;
+        nx.last_gain = agc_target(pk, st, nblocks - 1, reference);
+        nx.peak_2 = agc_peak_at(pk, st, nblocks - 1);
+        nx.peak_1 = agc_peak_at(pk, st, nblocks - 2);
+        state[c] = nx;
+    }
+}
+
+size_t fastagc_scratch_bytes(int channels, int nblocks) { return (size_t)channels * (size_t)(nblocks > 0 ? nblocks : 1) * sizeof(float); }
+
 int launch_fastagc_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks,
-                        float reference, void* d_state, float* d_hist, cudaStream_t st)
+                        float reference, void* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (channels <= 0 || nblocks <= 0) return 0;
     if (block <= 0) { set_error("fastagc: block size must be positive"); return -1; }
     if (d_out == d_in) { set_error("fastagc: in-place operation is not supported (output lags input by two blocks)"); return -1; }
-    fastagc_bank_kernel<<<channels, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, block, nblocks, reference, static_cast<FastAgcState*>(d_state), d_hist);
+    if (!d_scratch || scratch_bytes < fastagc_scratch_bytes(channels, nblocks)) { set_error("fastagc: scratch too small"); return -1; }
+    float* peaks = static_cast<float*>(d_scratch);
+    const dim3 grid(nblocks, channels);
+    fastagc_peaks_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, block, nblocks, peaks);
     CSDRB_CUDA(cudaGetLastError());
-    return 1;
+    fastagc_apply_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, block, nblocks, reference, static_cast<const FastAgcState*>(d_state), d_hist, peaks);
+    CSDRB_CUDA(cudaGetLastError());
+    fastagc_carry_kernel<<<channels, 256, 0, st>>>(d_in, in_stride, block, nblocks, reference, static_cast<FastAgcState*>(d_state), d_hist, peaks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 3;
 }
 
 }  // namespace csdrb

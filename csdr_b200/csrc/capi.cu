@@ -327,11 +327,13 @@ int csdrb_fractional_decimator_bank_ff(const float* d_in, long in_stride, float*
     return rc < 0 ? rc : counted(0, rc);
 }
 
+size_t csdrb_fastagc_bank_scratch_bytes(int channels, int nblocks) { return fastagc_scratch_bytes(channels, nblocks); }
+
 int csdrb_fastagc_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks, float reference,
-                          csdrb_fastagc_state_t* d_state, float* d_hist, void* stream)
+                          csdrb_fastagc_state_t* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, void* stream)
 {
     if (!d_in || !d_out || !d_state || !d_hist) { set_error("fastagc bank: null pointer"); return -1; }
-    int rc = launch_fastagc_bank(d_in, in_stride, d_out, out_stride, channels, block, nblocks, reference, d_state, d_hist, S(stream));
+    int rc = launch_fastagc_bank(d_in, in_stride, d_out, out_stride, channels, block, nblocks, reference, d_state, d_hist, d_scratch, scratch_bytes, S(stream));
     return rc < 0 ? rc : counted(0, rc);
 }
 
@@ -370,6 +372,21 @@ int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const comp
                                      g->fft_size, g->fft_inv_size, g->pre_decimation, g->scrap, g->post_input_size, g->post_decimation,
                                      d_remain_io, d_phase_io, reinterpret_cast<float2*>(d_out), out_stride, d_out_total, d_scratch, scratch_bytes, S(stream));
     return rc < 0 ? rc : counted(0, rc);
+}
+
+size_t csdrb_ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset) { return ddc_bank_scratch_bytes(channels, input_size, chunk, offset); }
+
+int csdrb_ddc_bank(const complexf* d_wide, int input_size, int channels, const shift_addition_data_t* d_params, float* d_phase_io, int chunk, int offset,
+                   int decimation, const float* h_taps, int taps_length, int demod, void* d_out, long out_stride,
+                   const complexf* d_last_in, complexf* d_last_out, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_wide || !d_params || !d_phase_io || !h_taps || !d_out) { set_error("ddc bank: null pointer"); return -1; }
+    int launches = 0;
+    int rc = launch_ddc_bank(reinterpret_cast<const float2*>(d_wide), input_size, channels, reinterpret_cast<const float*>(d_params), d_phase_io, chunk, offset,
+                             decimation, h_taps, taps_length, demod, d_out, out_stride, reinterpret_cast<const float2*>(d_last_in),
+                             reinterpret_cast<float2*>(d_last_out), d_scratch, scratch_bytes, &launches, S(stream));
+    if (rc >= 0) g_launches += launches;
+    return rc;
 }
 
 // =====================================================================================================
@@ -489,8 +506,9 @@ void fastagc_ff(fastagc_ff_t* a, float* output)
     A_CUDA(cudaMemcpyAsync(b2, &st, sizeof st, cudaMemcpyHostToDevice, g_ctx.stream), who);
     A_CUDA(cudaMemcpyAsync(b2 + 64, a->buffer_1, (size_t)n * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
     A_CUDA(cudaMemcpyAsync(b2 + 64 + (size_t)n * 4, a->buffer_2, (size_t)n * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CHECK(g_ctx.reserve(3, 256), who);
     A_CHECK(csdrb_fastagc_bank_ff((const float*)g_ctx.buf[0], 0, (float*)g_ctx.buf[1], 0, 1, n, 1, a->reference, (csdrb_fastagc_state_t*)b2,
-                                  (float*)(b2 + 64), g_ctx.stream), who);
+                                  (float*)(b2 + 64), g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
     A_DOWN(output, 1, (size_t)n * 4, who);
     A_CUDA(cudaMemcpyAsync(&st, b2, sizeof st, cudaMemcpyDeviceToHost, g_ctx.stream), who);
     A_SYNC(who);

@@ -9,33 +9,13 @@
 
 namespace csdrb {
 
-// u8 -> f32.  The reference computes ((float)b)/(UCHAR_MAX/2.0) - 1.0 in double and rounds once;
-// there are only 256 inputs, so a table built with exactly that expression is bit-exact by construction.
-__constant__ float c_u8_lut[256];
-static bool g_lut_ready = false;
-
-static int ensure_u8_lut(cudaStream_t st)
-{
-    if (g_lut_ready) return 0;
-    float h[256];
-    for (int b = 0; b < 256; b++) h[b] = (float)(((double)(float)b) / (UCHAR_MAX / 2.0) - 1.0);
-    CSDRB_CUDA(cudaMemcpyToSymbolAsync(c_u8_lut, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
-    CSDRB_CUDA(cudaStreamSynchronize(st));
-    g_lut_ready = true;
-    return 0;
-}
-
-__device__ __forceinline__ float u8_to_f(unsigned b)
-{
-    // same value as the table; computed in double exactly like the reference expression
-    return (float)((double)b / 127.5 - 1.0);
-}
+// u8 -> f32.  The reference computes ((float)b)/(UCHAR_MAX/2.0) - 1.0 in double and rounds once.  For the 256 possible
+// inputs that equals the correctly rounded float quotient (2b - 255)/255 (both operands exact in fp32, one IEEE division);
+// identical for every code -- pinned by tests/test_gpu_parity.py::test_convert_u8_f_bit_exact against oracle and golden table.
+__device__ __forceinline__ float u8_to_f(unsigned b) { return __fdiv_rn((float)(2 * (int)b - 255), 255.0f); }
 
 __global__ void __launch_bounds__(256) convert_u8_f_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long n)
 {
-    __shared__ float lut[256];
-    lut[threadIdx.x] = c_u8_lut[threadIdx.x];
-    __syncthreads();
     const long nvec = n / 16;
     const long stride = (long)gridDim.x * blockDim.x;
     for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
@@ -44,9 +24,9 @@ __global__ void __launch_bounds__(256) convert_u8_f_kernel(const unsigned char* 
         float4* o = reinterpret_cast<float4*>(out) + v * 4;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-            st_na_f4(o + k, make_float4(lut[w[k] & 255u], lut[(w[k] >> 8) & 255u], lut[(w[k] >> 16) & 255u], lut[w[k] >> 24]));
+            st_na_f4(o + k, make_float4(u8_to_f(w[k] & 255u), u8_to_f((w[k] >> 8) & 255u), u8_to_f((w[k] >> 16) & 255u), u8_to_f(w[k] >> 24)));
     }
-    for (long i = nvec * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = lut[in[i]];
+    for (long i = nvec * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = u8_to_f(in[i]);
 }
 
 __global__ void __launch_bounds__(256) convert_s16_f_kernel(const short* __restrict__ in, float* __restrict__ out, long n)
@@ -107,7 +87,6 @@ int launch_convert_u8_f(const unsigned char* d_in, float* d_out, long n, cudaStr
 {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("convert_u8_f: device buffers must be 16-byte aligned"); return -1; }
-    if (int rc = ensure_u8_lut(st)) return rc;
     convert_u8_f_kernel<<<grid_for(n / 16 + 1, 256), 256, 0, st>>>(d_in, d_out, n);
     CSDRB_CUDA(cudaGetLastError());
     return 0;
@@ -182,7 +161,6 @@ int launch_fmdemod_quadri_bank(const float2* d_in, long in_stride, float* d_out,
         set_error("fmdemod_quadri bank: last_in and last_out must not alias"); return -1;
     }
     int gx = (n / 2 + 255) / 256; if (gx < 1) gx = 1; if (gx > 64) gx = 64;
-    if (in_stride & 1) gx = gx;   // unaligned rows take the scalar branch inside the kernel
     fmdemod_quadri_bank_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, d_last_in, d_last_out);
     CSDRB_CUDA(cudaGetLastError());
     return 0;

@@ -287,12 +287,7 @@ int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const flo
 struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per channel: fastddc_t.offsetbin + dsadata
 
 #define PI_F 3.14159265358979323846f
-__device__ __forceinline__ float ddc_wrap(float ph)
-{
-    while (ph > PI_F) ph = __fsub_rn(ph, __fmul_rn(2.f, PI_F));
-    while (ph < -PI_F) ph = __fadd_rn(ph, __fmul_rn(2.f, PI_F));
-    return ph;
-}
+__device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph); }
 
 // per channel: walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
 __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,

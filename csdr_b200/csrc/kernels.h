@@ -29,8 +29,9 @@ size_t fracdec_scratch_bytes(int channels, int n, float rate);
 int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
                                      float rate, int num_poly_points, const float* d_taps, int taps_length, void* d_state,
                                      void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+size_t fastagc_scratch_bytes(int channels, int nblocks);
 int launch_fastagc_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks,
-                        float reference, void* d_state, float* d_hist, cudaStream_t st);
+                        float reference, void* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
 
 // K7/K8/K9 fft.cu
 int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long out_stride, int n, int batch, int inverse, cudaStream_t st);
@@ -44,5 +45,11 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                             int fft_size, int fft_inv_size, int pre_decimation, int scrap, int post_input_size, int post_decimation,
                             int* d_remain_io, float* d_phase_io, float2* d_out, long out_stride, int* d_out_total,
                             void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+
+// fused shared-input DDC bank, ddc_bank.cu
+size_t ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset);
+int launch_ddc_bank(const float2* d_wide, int input_size, int channels, const float* d_params, float* d_phase_io, int chunk, int offset,
+                    int decimation, const float* h_taps, int taps_length, int demod, void* d_out, long out_stride,
+                    const float2* d_last_in, float2* d_last_out, void* d_scratch, size_t scratch_bytes, int* launches, cudaStream_t st);
 
 }  // namespace csdrb

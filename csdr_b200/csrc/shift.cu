@@ -24,12 +24,7 @@ namespace csdrb {
 
 #define PI_F 3.14159265358979323846f            // (float)3.14159265358979323846, libcsdr.h:65
 
-__device__ __forceinline__ float wrap_pm_pi(float ph)
-{
-    while (ph > PI_F) ph = __fsub_rn(ph, __fmul_rn(2.f, PI_F));
-    while (ph < -PI_F) ph = __fadd_rn(ph, __fmul_rn(2.f, PI_F));
-    return ph;
-}
+__device__ __forceinline__ float wrap_pm_pi(float ph) { return wrap_phase_pm_pi(ph); }   // exact fast-forward, common.cuh
 __device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
 {
     // starting_phase += d.rate*PI*input_size  (float*float -> float, * (float)int -> float, += float)

@@ -162,6 +162,19 @@ int csdrb_decimating_shift_addition_bank_cc(const complexf *d_in, long in_stride
                                             int input_size, const shift_addition_data_t *d_params, int decimation,
                                             int *d_remain_io, float *d_phase_io, int *d_out_size, void *stream);
 
+/* Fused shared-input DDC / NFM bank = shift_addition_cc(rate_c) | fir_decimate_cc(D, taps) [| fmdemod_quadri_cf] for `channels`
+ * channels of ONE wideband block (ddcd_old.h:51-57 as one launch).  d_params / d_phase_io / chunk as in the shift bank, except
+ * that chunks are counted on the absolute stream: the block starts `offset` samples into a chunk and d_phase_io[c] is the phase at
+ * the START of that chunk; on return it is the phase at the start of the chunk containing sample n_out*decimation, where the caller
+ * must start the next block (re-presenting the unconsumed tail exactly like fir_decimate_cc's callers do, csdr.c:1172-1174).
+ * demod = 0: d_out is complexf [channels][out_stride] baseband; demod = 1: float [channels][out_stride] discriminator output,
+ * d_last_in/d_last_out carry the previous baseband sample per channel (NULL = zeros / not wanted).
+ * Returns outputs per channel, -2 when no fused kernel is compiled for (decimation, taps_length) -- use the unfused bank calls then. */
+size_t csdrb_ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset);
+int csdrb_ddc_bank(const complexf *d_wide, int input_size, int channels, const shift_addition_data_t *d_params, float *d_phase_io,
+                   int chunk, int offset, int decimation, const float *h_taps, int taps_length, int demod, void *d_out, long out_stride,
+                   const complexf *d_last_in, complexf *d_last_out, void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* K5 fractional_decimator_ff bank: d_state[c].where carries the reference's `where`; on return input_processed
  * and output_size are filled like fractional_decimator_ff() fills them (libcsdr.c:789-792). */
 typedef struct csdrb_fracdec_state_s { float where; int input_processed; int output_size; } csdrb_fracdec_state_t;
@@ -173,8 +186,9 @@ int csdrb_fractional_decimator_bank_ff(const float *d_in, long in_stride, float 
 /* K6 fastagc_ff bank: nblocks consecutive blocks of `block` samples per channel; d_hist is [channels][2][block]
  * (the reference's buffer_1, buffer_2; zero it at stream start), d_state[c] = {peak_1, peak_2, last_gain}. */
 typedef struct csdrb_fastagc_state_s { float peak_1, peak_2, last_gain; } csdrb_fastagc_state_t;
+size_t csdrb_fastagc_bank_scratch_bytes(int channels, int nblocks);
 int csdrb_fastagc_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int block, int nblocks,
-                          float reference, csdrb_fastagc_state_t *d_state, float *d_hist, void *stream);
+                          float reference, csdrb_fastagc_state_t *d_state, float *d_hist, void *d_scratch, size_t scratch_bytes, void *stream);
 
 /* K7 batched unnormalised c2c DFT (power-of-two size 2..16384), sign -1 forward / +1 inverse */
 int csdrb_fft_c2c_batch(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int size, int batch, int inverse, void *stream);

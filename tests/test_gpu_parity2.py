@@ -222,3 +222,65 @@ def test_fastddc_odd_post_decimation(gpu, oracle):
         want = oracle.fastddc_inv(oracle.fastddc_fwd(x, od), bw, dec, sh)
         k = int(counts[c])
         assert k == want.size and _rel(out[c, :k].cpu().numpy(), want) < TOL / 2
+
+
+# ------------------------------------------------------------------------------------------ exact phase wrap + fused DDC bank
+def test_phase_wrap_fast_forward_is_exact(gpu, oracle):
+    """The binade-by-binade fast-forward of `while(ph>PI) ph-=2*PI` (common.cuh) must give the very float the loop gives.
+    One shift_addition_cc call of n samples advances the phase by 2*rate*PI*n un-wrapped (up to ~2^20 here), then wraps it."""
+    x = _cplx(np.random.default_rng(0), 64)
+    for rate in (0.4999, -0.4999, 0.31, 0.123456, -0.25, 1e-3, 0.0401):
+        for n in (64, 1000, 4099, 65536, 300_000):
+            xx = np.resize(x, n)
+            _, ph = gpu.shift_addition_bank_cc(_dev(xx), [rate], chunk=0)
+            _, want = oracle.shift_addition_cc(xx, rate, 0.0, None)
+            assert np.float32(want) == ph[0].item(), (rate, n, want, ph[0].item())
+    # many consecutive wraps with carried phase: 3000 chunks of 64 samples
+    xx = np.resize(x, 64 * 3000)
+    for rate in (0.4999, -0.37):
+        _, ph = gpu.shift_addition_bank_cc(_dev(xx), [rate], chunk=64)
+        _, want = oracle.shift_addition_cc(xx, rate, 0.0, 64)
+        assert np.float32(want) == ph[0].item()
+
+
+@pytest.mark.parametrize("D,bw,demod", [(50, 0.005, True), (50, 0.005, False), (10, 0.0201, True), (10, 0.05, True)])
+def test_fused_ddc_bank_matches_unfused_reference_chain(gpu, oracle, D, bw, demod):
+    """BASELINE config 4 chain on a small bank: shift_addition_cc (1024-sample chunks) | fir_decimate_cc D | fmdemod_quadri_cf."""
+    T = oracle.firdes_filter_len(bw)
+    taps = gpu.firdes_lowpass_f(T, 0.5 / D)
+    N = 60_000 + 13
+    rng = np.random.default_rng(D)
+    t = np.arange(N)
+    rates = np.array([-0.31, -0.085, 0.0, 0.02, 0.2, 0.4567, 0.11], np.float32)
+    wide = sum(0.3 * np.exp(1j * (2 * np.pi * (-float(r)) * t + np.cumsum(0.05 * np.sin(2 * np.pi * t / (2000.0 + 100 * k))))) for k, r in enumerate(rates))
+    wide = (wide + 0.01 * (rng.normal(size=N) + 1j * rng.normal(size=N))).astype(np.complex64)
+    out, ph, last = gpu.ddc_bank(_dev(wide), rates, D, taps, demod=demod, chunk=1024)
+    out = out.cpu().numpy()
+    n_out = (N - T) // D + 1
+    assert out.shape == (rates.size, n_out)
+    for c, r in enumerate(rates):
+        sh, _ = oracle.shift_addition_cc(wide, float(r), 0.0, 1024)
+        base = oracle.fir_decimate_cc(sh, D, taps)
+        want = oracle.fmdemod_quadri_cf(base)[0] if demod else base
+        assert _rel(out[c], want) < TOL / 2, (c, r, _rel(out[c], want))
+        if demod:
+            assert _rel(np.array([last[c].item()]), base[-1:]) < 1e-5
+
+
+def test_fused_ddc_bank_streams_block_by_block(gpu, oracle):
+    """Two calls with the tail re-presented (csdr.c:1172-1174) and chunk phase/offset carried == one long reference stream."""
+    D, T, chunk = 50, 801, 1024
+    taps = gpu.firdes_lowpass_f(T, 0.5 / D)
+    rng = np.random.default_rng(3)
+    N = 50_000
+    wide = _cplx(rng, N, 0.5)
+    rates = np.array([0.123, -0.4], np.float32)
+    n1 = 20_000
+    o1, ph1, last1 = gpu.ddc_bank(_dev(wide[:n1]), rates, D, taps, demod=True, chunk=chunk, offset=0)
+    consumed = o1.shape[1] * D
+    o2, ph2, last2 = gpu.ddc_bank(_dev(wide[consumed:]), rates, D, taps, demod=True, chunk=chunk, offset=consumed % chunk, phases=ph1, last=last1)
+    got = np.concatenate([o1.cpu().numpy(), o2.cpu().numpy()], 1)
+    for c, r in enumerate(rates):
+        sh, _ = oracle.shift_addition_cc(wide, float(r), 0.0, chunk)
+        want = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0]
+        assert got.shape[1] == want.size and _rel(got[c], want) < TOL / 2
