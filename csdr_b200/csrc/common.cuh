@@ -98,33 +98,41 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 // as long as the exact difference stays in the binade, i.e. M >= 2^23 + ceil(c/u).  So whole runs of iterations
 // collapse into one integer multiply; the binade-crossing steps are done with a real float subtraction.
 // Bit-exact with the loop (tests/test_gpu_parity2.py::test_phase_wrap_fast_forward_is_exact), ~25 steps instead of ~400.
+template <int E>
+__device__ __forceinline__ float wrap_binade_step(float a)
+{
+    // a in [2^E, 2^(E+1)): collapse every subtraction that provably stays in this binade, then cross with real subtractions
+    constexpr unsigned MC = 0xC90FDBu;
+    constexpr int sh = E - 2;
+    constexpr unsigned q = (MC + (1u << (sh - 1))) >> sh;                                         // round(c/u)
+    constexpr unsigned mmin = (1u << 23) + ((MC + (1u << sh) - 1u) >> sh);                        // 2^23 + ceil(c/u)
+    const float lo = __uint_as_float((unsigned)(E + 127) << 23);                                  // 2^E
+    if (a >= lo) {
+        const unsigned M = (__float_as_uint(a) & 0x7fffffu) | 0x800000u;
+        if (M >= mmin) {
+            const unsigned k = (M - mmin) / q + 1u;                                               // division by a compile-time constant
+            a = __uint_as_float(((unsigned)(E + 127) << 23) | ((M - k * q) & 0x7fffffu));
+        }
+        while (a >= lo) a = __fsub_rn(a, 6.28318530717958647692f);                                // 1-2 real, rounded steps across the boundary
+    }
+    return a;
+}
+
 __device__ __forceinline__ float wrap_phase_pm_pi(float ph)
 {
     const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;   // float(2)*PI rounds to the same float
-    const unsigned MC = 0xC90FDBu;                                                           // 2*pi = MC * 2^-21
     const bool neg = ph < 0.f;
     float a = fabsf(ph);
-    if (!(a <= 3.0e38f)) return ph;                                                          // inf/nan: leave (the reference would spin)
-    while (a > PI_F32) {
-        const unsigned bits = __float_as_uint(a);
-        const int E = (int)(bits >> 23) - 127;
-        if (E >= 4 && E <= 40) {
-            const int sh = E - 2;
-            const unsigned long long M = (bits & 0x7fffffu) | 0x800000u;
-            const unsigned long long q = sh < 32 ? (((unsigned long long)MC + (1ull << (sh - 1))) >> sh) : 0ull;
-            const unsigned long long cq = sh < 32 ? (((unsigned long long)MC + (1ull << sh) - 1ull) >> sh) : 1ull;
-            const unsigned long long mmin = (1ull << 23) + cq;
-            if (q > 0 && M >= mmin) {
-                const unsigned long long k = (M - mmin) / q + 1ull;
-                const unsigned m2 = (unsigned)(M - k * q);                                   // still in [2^23, 2^24)
-                a = __uint_as_float(((unsigned)(E + 127) << 23) | (m2 & 0x7fffffu));
-                continue;
-            }
-        }
-        const float b = __fsub_rn(a, TWO_PI_F32);
-        if (b == a) break;                                                                   // |ph| > 2^26: the reference loop never terminates
-        a = b;
+    if (!(a < 67108864.f)) return ph;                // |ph| >= 2^26 (or nan): subtracting 2*pi no longer changes it; the reference would spin
+    if (a >= 16.f) {
+        a = wrap_binade_step<25>(a); a = wrap_binade_step<24>(a); a = wrap_binade_step<23>(a); a = wrap_binade_step<22>(a);
+        a = wrap_binade_step<21>(a); a = wrap_binade_step<20>(a); a = wrap_binade_step<19>(a); a = wrap_binade_step<18>(a);
+        a = wrap_binade_step<17>(a); a = wrap_binade_step<16>(a); a = wrap_binade_step<15>(a); a = wrap_binade_step<14>(a);
+        a = wrap_binade_step<13>(a); a = wrap_binade_step<12>(a); a = wrap_binade_step<11>(a); a = wrap_binade_step<10>(a);
+        a = wrap_binade_step<9>(a);  a = wrap_binade_step<8>(a);  a = wrap_binade_step<7>(a);  a = wrap_binade_step<6>(a);
+        a = wrap_binade_step<5>(a);  a = wrap_binade_step<4>(a);
     }
+    while (a > PI_F32) a = __fsub_rn(a, TWO_PI_F32);                                       // below 16: at most three plain steps
     return neg ? -a : a;
 }
 

@@ -20,7 +20,7 @@
 namespace csdrb {
 
 template <int TPAD>
-struct DdcTaps { float2 hh[TPAD]; };
+struct alignas(16) DdcTaps { float4 hh2[TPAD / 2]; };               // rows of MP = M rounded up to even; one float4 = taps (j, j+1), each duplicated (h,h)
 
 #define FMDEMOD_K_D 0.340447550238101026565118445432744920253753662109375
 
@@ -62,18 +62,21 @@ __global__ void ddc_phase_chain_kernel(const float3* __restrict__ params, float*
     phase_io[c] = keep;
 }
 
-template <int D, int M, bool DEMOD>
+// CPL = channels per lane.  A tap pair is loaded once per warp and sample phase (LDCU.128 fetches two of them: taps are stored
+// [p][j] so the M taps that one sample meets are contiguous); with CPL = 2 every loaded tap feeds two FFMA2 and every wideband
+// sample load feeds two channels, which halves the non-FMA issue slots per channel-sample (ncu r01: 868 LDCU per 850 FFMA2 at CPL = 1).
+template <int D, int M, int CPL, bool DEMOD>
 __global__ void __launch_bounds__(128)
 ddc_bank_fused_kernel(const float2* __restrict__ wide, int n_in, int offset, int chunk, int nchunks,
                       const float3* __restrict__ params, const float2* __restrict__ seeds, int channels,
                       void* __restrict__ out_v, long out_stride, int n_out, int seg_outputs,
                       const float2* __restrict__ last_in, float2* __restrict__ last_out,
-                      const __grid_constant__ DdcTaps<D * M> taps)
+                      const __grid_constant__ DdcTaps<D * ((M + 1) & ~1)> taps)
 {
+    constexpr int MP = (M + 1) & ~1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ch = (blockIdx.y * 4 + warp) * 32 + lane;
-    const bool live = ch < channels;
-    const int chs = live ? ch : channels - 1;                           // dead lanes shadow a real channel (no divergence), never store
+    const int ch0 = (blockIdx.y * 4 + warp) * (32 * CPL) + lane;        // this lane's channels: ch0 + 32*u
+    if (ch0 - lane >= channels) return;                                 // whole warp beyond the bank
     const int o_first = blockIdx.x * seg_outputs;                       // first output this warp emits
     if (o_first >= n_out) return;
     const int o_end = min(n_out, o_first + seg_outputs);
@@ -81,65 +84,94 @@ ddc_bank_fused_kernel(const float2* __restrict__ wide, int n_in, int offset, int
     // partial ones and are simply not emitted); the demodulator needs the previous baseband sample: start one output early.
     int o_start = o_first - (DEMOD ? 1 : 0);
     if (o_start < 0) o_start = 0;
-    const float3 p = params[chs];
-    const float sind = p.x, cosd = p.y;
-    float2 acc[M];
-#pragma unroll
-    for (int j = 0; j < M; j++) acc[j] = make_float2(0.f, 0.f);
-    float2 prev = (DEMOD && last_in) ? last_in[chs] : make_float2(0.f, 0.f);
-    // sample index n runs from o_start*D; absolute chunk position = offset + n
-    long n = (long)o_start * D;
+    int chs[CPL]; bool live[CPL];
+    float sind[CPL], cosd[CPL], c[CPL], s[CPL];
+    float2 acc[CPL][M], prev[CPL];
+    long n = (long)o_start * D;                                         // absolute chunk position = offset + n
     int kchunk = (int)((offset + n) / chunk);
-    int into = (int)((offset + n) % chunk);                            // samples already consumed in this chunk
-    float2 cs = seeds[(long)chs * nchunks + kchunk];
-    float c = cs.x, s = cs.y;
+    const int into = (int)((offset + n) % chunk);                       // samples already consumed in this chunk
+#pragma unroll
+    for (int u = 0; u < CPL; u++) {
+        live[u] = ch0 + 32 * u < channels;
+        chs[u] = live[u] ? ch0 + 32 * u : channels - 1;                 // dead lanes shadow a real channel (no divergence), never store
+        const float3 p = params[chs[u]];
+        sind[u] = p.x; cosd[u] = p.y;
+#pragma unroll
+        for (int j = 0; j < M; j++) acc[u][j] = make_float2(0.f, 0.f);
+        prev[u] = (DEMOD && last_in) ? last_in[chs[u]] : make_float2(0.f, 0.f);
+        const float2 cs = seeds[(long)chs[u] * nchunks + kchunk];
+        c[u] = cs.x; s[u] = cs.y;
+    }
     for (int t = 0; t < into; t++) {                                    // replay the recursion up to the segment start (< chunk steps, no data)
-        const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
-        const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
-        c = cn; s = sn;
+#pragma unroll
+        for (int u = 0; u < CPL; u++) {
+            const float cn = __fsub_rn(__fmul_rn(c[u], cosd[u]), __fmul_rn(s[u], sind[u]));
+            const float sn = __fadd_rn(__fmul_rn(s[u], cosd[u]), __fmul_rn(c[u], sind[u]));
+            c[u] = cn; s[u] = sn;
+        }
     }
     int left = chunk - into;
-    // acc[j] collects output (o_cur + j) where o_cur is the output whose window STARTS at the current period:
-    // at period q (samples qD .. qD+D-1) sample qD+p contributes to output q-j with tap p + jD, j = 0..M-1.
+    // acc[.][j] collects output q-j while the walk is in period q (samples qD .. qD+D-1): sample qD+p meets tap p + jD.
     for (int q = o_start; q < o_end + M - 1; q++) {
-        const long base = (long)q * D;                                  // samples past n_in only ever meet zero-padded taps: read as zeros
+        const long base = (long)q * D;
+        const bool inside = base + D <= n_in;                           // whole period inside the block: no per-load checks
+        const float4* src = reinterpret_cast<const float4*>(wide + base);   // D even, base even: 16-byte aligned
 #pragma unroll
         for (int pp = 0; pp < D; pp += 2) {
-            // two wideband samples per 128-bit broadcast load (D is even, base is even -> 16-byte aligned)
-            float4 xx;
-            if (base + pp + 1 < n_in) xx = __ldg(reinterpret_cast<const float4*>(wide + base + pp));
-            else { const float2 a = base + pp < n_in ? wide[base + pp] : make_float2(0.f, 0.f); xx = make_float4(a.x, a.y, 0.f, 0.f); }
+            float4 xx;                                                  // two wideband samples per 128-bit broadcast load
+            if (inside) xx = __ldg(src + pp / 2);
+            else {                                                      // samples past n_in only ever meet zero-padded taps: read as zeros
+                const float2 a = base + pp < n_in ? wide[base + pp] : make_float2(0.f, 0.f);
+                const float2 b = base + pp + 1 < n_in ? wide[base + pp + 1] : make_float2(0.f, 0.f);
+                xx = make_float4(a.x, a.y, b.x, b.y);
+            }
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int pidx = pp + e;
                 const float xi = e ? xx.z : xx.x, xq = e ? xx.w : xx.y;
-                if (left == 0) {                                        // chunk boundary: re-seed the phasor (warp-uniform branch)
+                if (left == 0) {                                        // chunk boundary: re-seed the phasors (warp-uniform branch)
                     if (kchunk < nchunks - 1) kchunk++;                 // (beyond the block the data are zeros; any phasor will do)
-                    cs = seeds[(long)chs * nchunks + kchunk];
-                    c = cs.x; s = cs.y; left = chunk;
-                }
-                const float2 sh = make_float2(fmaf(c, xi, -s * xq), fmaf(s, xi, c * xq));
-                const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
-                const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
-                c = cn; s = sn; left--;
 #pragma unroll
-                for (int j = 0; j < M; j++) acc[j] = ffma2(sh, taps.hh[pidx + j * D], acc[j]);
+                    for (int u = 0; u < CPL; u++) { const float2 cs = seeds[(long)chs[u] * nchunks + kchunk]; c[u] = cs.x; s[u] = cs.y; }
+                    left = chunk;
+                }
+                left--;
+                float2 sh[CPL];
+#pragma unroll
+                for (int u = 0; u < CPL; u++) {
+                    sh[u] = make_float2(fmaf(c[u], xi, -s[u] * xq), fmaf(s[u], xi, c[u] * xq));
+                    const float cn = __fsub_rn(__fmul_rn(c[u], cosd[u]), __fmul_rn(s[u], sind[u]));
+                    const float sn = __fadd_rn(__fmul_rn(s[u], cosd[u]), __fmul_rn(c[u], sind[u]));
+                    c[u] = cn; s[u] = sn;
+                }
+#pragma unroll
+                for (int j = 0; j < M; j += 2) {
+                    const float4 h2 = taps.hh2[(pidx * MP + j) / 2];    // [p][j] layout, one 128-bit uniform load = two taps
+#pragma unroll
+                    for (int u = 0; u < CPL; u++) {
+                        acc[u][j] = ffma2(sh[u], make_float2(h2.x, h2.y), acc[u][j]);
+                        if (j + 1 < M) acc[u][j + 1] = ffma2(sh[u], make_float2(h2.z, h2.w), acc[u][j + 1]);
+                    }
+                }
             }
         }
         // period q done: output q-(M-1) is complete (its last tap block was j = M-1)
         const int o = q - (M - 1);
-        const float2 y = acc[M - 1];
 #pragma unroll
-        for (int j = M - 1; j > 0; j--) acc[j] = acc[j - 1];
-        acc[0] = make_float2(0.f, 0.f);
-        if (o >= o_start) {
-            if (DEMOD) {
-                if (o >= o_first && live) static_cast<float*>(out_v)[(long)ch * out_stride + o] = quadri_d(y, prev);
-                prev = y;
-            } else if (o >= o_first && live) {
-                static_cast<float2*>(out_v)[(long)ch * out_stride + o] = y;
+        for (int u = 0; u < CPL; u++) {
+            const float2 y = acc[u][M - 1];
+#pragma unroll
+            for (int j = M - 1; j > 0; j--) acc[u][j] = acc[u][j - 1];
+            acc[u][0] = make_float2(0.f, 0.f);
+            if (o >= o_start) {
+                if (DEMOD) {
+                    if (o >= o_first && live[u]) static_cast<float*>(out_v)[(long)chs[u] * out_stride + o] = quadri_d(y, prev[u]);
+                    prev[u] = y;
+                    if (last_out && live[u] && o == n_out - 1) last_out[chs[u]] = y;
+                } else if (o >= o_first && live[u]) {
+                    static_cast<float2*>(out_v)[(long)chs[u] * out_stride + o] = y;
+                }
             }
-            if (DEMOD && last_out && live && o == n_out - 1) last_out[ch] = y;
         }
     }
 }
@@ -155,16 +187,24 @@ template <int D, int M>
 static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int nchunks, const float3* params, const float2* seeds, int channels,
                         int demod, void* out, long out_stride, int n_out, const float2* last_in, float2* last_out, const float* h_taps, int T, cudaStream_t st)
 {
-    DdcTaps<D * M> tp;
-    for (int k = 0; k < D * M; k++) { const float h = k < T ? h_taps[k] : 0.f; tp.hh[k] = make_float2(h, h); }
-    const int groups = (channels + 127) / 128;
-    // enough warps to fill the machine (~12 per SM) without making the warm-up (M+1 outputs) dominate
-    long want_segments = (148L * 12 + groups * 4 - 1) / (groups * 4);
+    constexpr int MP = (M + 1) & ~1;
+    DdcTaps<D * MP> tp;                                                 // tap k = jD + p stored at [p][j], duplicated for FFMA2
+    for (int p = 0; p < D; p++)
+        for (int j = 0; j < MP; j++) {
+            const int k = j * D + p; const float h = (j < M && k < T) ? h_taps[k] : 0.f;
+            float4& slot = tp.hh2[(p * MP + j) / 2];
+            if (j & 1) { slot.z = h; slot.w = h; } else { slot.x = h; slot.y = h; }
+        }
+    constexpr int CPL = 2;
+    const int warps_per_seg = (channels + 32 * CPL - 1) / (32 * CPL);
+    const int groups = (warps_per_seg + 3) / 4;
+    // enough warps to fill the machine (~10 per SM) while keeping the M-1 trailing periods of every segment a small fraction
+    long want_segments = (148L * 10 + warps_per_seg - 1) / warps_per_seg;
     int seg = (int)((n_out + want_segments - 1) / want_segments);
     if (seg < 4 * M) seg = 4 * M;
     dim3 grid((n_out + seg - 1) / seg, groups);
-    if (demod) ddc_bank_fused_kernel<D, M, true><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
-    else ddc_bank_fused_kernel<D, M, false><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
+    if (demod) ddc_bank_fused_kernel<D, M, CPL, true><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
+    else ddc_bank_fused_kernel<D, M, CPL, false><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
     CSDRB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -14,41 +14,54 @@ namespace csdrb {
 // identical for every code -- pinned by tests/test_gpu_parity.py::test_convert_u8_f_bit_exact against oracle and golden table.
 __device__ __forceinline__ float u8_to_f(unsigned b) { return __fdiv_rn((float)(2 * (int)b - 255), 255.0f); }
 
+// Access pattern of the widening conversions: a lane takes ONE 32-bit input word per step and writes ONE 128-bit output, so a
+// warp reads 128 contiguous bytes and writes 512 contiguous bytes per instruction (fully coalesced on both sides); four steps
+// are in flight per thread for memory-level parallelism.
 __global__ void __launch_bounds__(256) convert_u8_f_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, long n)
 {
-    const long nvec = n / 16;
+    const long nw = n / 4;                                             // whole 4-byte words
     const long stride = (long)gridDim.x * blockDim.x;
-    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const uint4 q = reinterpret_cast<const uint4*>(in)[v];
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
-        float4* o = reinterpret_cast<float4*>(out) + v * 4;
+    long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < nw; v += 4 * stride) {
+        unsigned w[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            st_na_f4(o + k, make_float4(u8_to_f(w[k] & 255u), u8_to_f((w[k] >> 8) & 255u), u8_to_f((w[k] >> 16) & 255u), u8_to_f(w[k] >> 24)));
+        for (int u = 0; u < 4; u++) w[u] = __ldg(reinterpret_cast<const unsigned*>(in) + v + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            st_na_f4(reinterpret_cast<float4*>(out) + v + u * stride,
+                     make_float4(u8_to_f(w[u] & 255u), u8_to_f((w[u] >> 8) & 255u), u8_to_f((w[u] >> 16) & 255u), u8_to_f(w[u] >> 24)));
     }
-    for (long i = nvec * 16 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = u8_to_f(in[i]);
+    for (; v < nw; v += stride) {
+        const unsigned w = __ldg(reinterpret_cast<const unsigned*>(in) + v);
+        st_na_f4(reinterpret_cast<float4*>(out) + v, make_float4(u8_to_f(w & 255u), u8_to_f((w >> 8) & 255u), u8_to_f((w >> 16) & 255u), u8_to_f(w >> 24)));
+    }
+    for (long i = nw * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = u8_to_f(in[i]);
 }
 
 __global__ void __launch_bounds__(256) convert_s16_f_kernel(const short* __restrict__ in, float* __restrict__ out, long n)
 {
     // reference build (-ffast-math) multiplies by the float-rounded reciprocal of SHRT_MAX; see oracle.c
     const float recip = 1.0f / 32767.0f;
-    const long nvec = n / 8;
+    const long nw = n / 4;                                             // 8-byte words of four shorts
     const long stride = (long)gridDim.x * blockDim.x;
-    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        const uint4 q = reinterpret_cast<const uint4*>(in)[v];
-        const unsigned w[4] = {q.x, q.y, q.z, q.w};
-        float f[8];
+    long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < nw; v += 4 * stride) {
+        uint2 w[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            f[2 * k] = __fmul_rn((float)(short)(w[k] & 0xffffu), recip);
-            f[2 * k + 1] = __fmul_rn((float)(short)(w[k] >> 16), recip);
-        }
-        float4* o = reinterpret_cast<float4*>(out) + v * 2;
-        st_na_f4(o, make_float4(f[0], f[1], f[2], f[3]));
-        st_na_f4(o + 1, make_float4(f[4], f[5], f[6], f[7]));
+        for (int u = 0; u < 4; u++) w[u] = __ldg(reinterpret_cast<const uint2*>(in) + v + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            st_na_f4(reinterpret_cast<float4*>(out) + v + u * stride,
+                     make_float4(__fmul_rn((float)(short)(w[u].x & 0xffffu), recip), __fmul_rn((float)(short)(w[u].x >> 16), recip),
+                                 __fmul_rn((float)(short)(w[u].y & 0xffffu), recip), __fmul_rn((float)(short)(w[u].y >> 16), recip)));
     }
-    for (long i = nvec * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn((float)in[i], recip);
+    for (; v < nw; v += stride) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(in) + v);
+        st_na_f4(reinterpret_cast<float4*>(out) + v,
+                 make_float4(__fmul_rn((float)(short)(w.x & 0xffffu), recip), __fmul_rn((float)(short)(w.x >> 16), recip),
+                             __fmul_rn((float)(short)(w.y & 0xffffu), recip), __fmul_rn((float)(short)(w.y >> 16), recip)));
+    }
+    for (long i = nw * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn((float)in[i], recip);
 }
 
 // f32 -> s16: float multiply by 32767, truncate toward zero, keep the low 16 bits of the int32

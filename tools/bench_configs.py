@@ -95,7 +95,10 @@ if "c4" in which:
     report(f"cfg4 shift (shared in) 128 ch x {N}", t1, N, N * 8 + C * N * 8)
     report(f"cfg4 fir_decimate d=50 T={T} 128 ch (generic kernel)", t2, N, C * N * 8.16, f"{C * n_out * T * 4 / t2 / 1e9:.1f} TFLOP/s")
     report("cfg4 fmdemod 128 ch", t3, N, C * n_out * 12)
-    report("cfg4 chain, wideband Msps per GPU (18.24 B/sample algorithmic)", timed(chain, reps=3), N, N * 18.24)
+    report("cfg4 unfused chain, wideband Msps per GPU (18.24 B/sample algorithmic)", timed(chain, reps=3), N, N * 18.24)
+    fo = torch.empty((C, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
+    tfu = timed(lambda: cb.ddc_bank(x, rates, D, taps, demod=True, chunk=1024, out=fo), reps=5)
+    report("cfg4 FUSED ddc_bank (shift|fir d=50 T=801|fmdemod) 128 ch", tfu, N, N * 18.24, f"{C * N * (10 + 4 * 17 * 1.0) / tfu / 1e9:.1f} TFLOP/s fp32 (10+4M flop per sample-channel)")
     del shifted, base, audio
     torch.cuda.empty_cache()
 
