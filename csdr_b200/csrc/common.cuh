@@ -101,20 +101,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 template <int E>
 __device__ __forceinline__ float wrap_binade_step(float a)
 {
-    // a in [2^E, 2^(E+1)): collapse every subtraction that provably stays in this binade, then cross with real subtractions
+    // Branch-free (lanes = channels sit in different binades; predication keeps the warp converged).
+    // a in [2^E, 2^(E+1)): collapse every subtraction that provably stays in this binade, then cross with real subtractions.
     constexpr unsigned MC = 0xC90FDBu;
     constexpr int sh = E - 2;
     constexpr unsigned q = (MC + (1u << (sh - 1))) >> sh;                                         // round(c/u)
     constexpr unsigned mmin = (1u << 23) + ((MC + (1u << sh) - 1u) >> sh);                        // 2^23 + ceil(c/u)
     const float lo = __uint_as_float((unsigned)(E + 127) << 23);                                  // 2^E
-    if (a >= lo) {
-        const unsigned M = (__float_as_uint(a) & 0x7fffffu) | 0x800000u;
-        if (M >= mmin) {
-            const unsigned k = (M - mmin) / q + 1u;                                               // division by a compile-time constant
-            a = __uint_as_float(((unsigned)(E + 127) << 23) | ((M - k * q) & 0x7fffffu));
-        }
-        while (a >= lo) a = __fsub_rn(a, 6.28318530717958647692f);                                // 1-2 real, rounded steps across the boundary
-    }
+    const unsigned M = (__float_as_uint(a) & 0x7fffffu) | 0x800000u;
+    const int span = (int)M - (int)mmin;
+    const unsigned k = span >= 0 ? (unsigned)span / q + 1u : 0u;                                  // division by a compile-time constant
+    const float bulk = __uint_as_float(((unsigned)(E + 127) << 23) | ((M - k * q) & 0x7fffffu));
+    a = a >= lo ? bulk : a;
+    // after the bulk step a < 2^E + c + u, so at most two real (rounded) subtractions cross the boundary
+    a = a >= lo ? __fsub_rn(a, 6.28318530717958647692f) : a;
+    a = a >= lo ? __fsub_rn(a, 6.28318530717958647692f) : a;
     return a;
 }
 
@@ -124,13 +125,18 @@ __device__ __forceinline__ float wrap_phase_pm_pi(float ph)
     const bool neg = ph < 0.f;
     float a = fabsf(ph);
     if (!(a < 67108864.f)) return ph;                // |ph| >= 2^26 (or nan): subtracting 2*pi no longer changes it; the reference would spin
-    if (a >= 16.f) {
-        a = wrap_binade_step<25>(a); a = wrap_binade_step<24>(a); a = wrap_binade_step<23>(a); a = wrap_binade_step<22>(a);
-        a = wrap_binade_step<21>(a); a = wrap_binade_step<20>(a); a = wrap_binade_step<19>(a); a = wrap_binade_step<18>(a);
-        a = wrap_binade_step<17>(a); a = wrap_binade_step<16>(a); a = wrap_binade_step<15>(a); a = wrap_binade_step<14>(a);
-        a = wrap_binade_step<13>(a); a = wrap_binade_step<12>(a); a = wrap_binade_step<11>(a); a = wrap_binade_step<10>(a);
-        a = wrap_binade_step<9>(a);  a = wrap_binade_step<8>(a);  a = wrap_binade_step<7>(a);  a = wrap_binade_step<6>(a);
-        a = wrap_binade_step<5>(a);  a = wrap_binade_step<4>(a);
+    if (a >= 1048576.f) {                            // 2^20 and up: rare
+        a = wrap_binade_step<25>(a); a = wrap_binade_step<24>(a); a = wrap_binade_step<23>(a);
+        a = wrap_binade_step<22>(a); a = wrap_binade_step<21>(a); a = wrap_binade_step<20>(a);
+    }
+    if (a >= 8192.f) {                               // 2^13 .. 2^20
+        a = wrap_binade_step<19>(a); a = wrap_binade_step<18>(a); a = wrap_binade_step<17>(a); a = wrap_binade_step<16>(a);
+        a = wrap_binade_step<15>(a); a = wrap_binade_step<14>(a); a = wrap_binade_step<13>(a);
+    }
+    if (a >= 16.f) {                                 // the common range: one 1024-sample chunk advances the phase by < 2^12 rad
+        a = wrap_binade_step<12>(a); a = wrap_binade_step<11>(a); a = wrap_binade_step<10>(a);
+        a = wrap_binade_step<9>(a);  a = wrap_binade_step<8>(a);  a = wrap_binade_step<7>(a);
+        a = wrap_binade_step<6>(a);  a = wrap_binade_step<5>(a);  a = wrap_binade_step<4>(a);
     }
     while (a > PI_F32) a = __fsub_rn(a, TWO_PI_F32);                                       // below 16: at most three plain steps
     return neg ? -a : a;

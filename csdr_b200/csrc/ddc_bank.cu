@@ -16,6 +16,7 @@
 // Bound: FP32 issue: ~ (10 + 4*M) FMA-lane slots per (sample, channel).
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace csdrb {
 
@@ -195,16 +196,21 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
             float4& slot = tp.hh2[(p * MP + j) / 2];
             if (j & 1) { slot.z = h; slot.w = h; } else { slot.x = h; slot.y = h; }
         }
-    constexpr int CPL = 2;
-    const int warps_per_seg = (channels + 32 * CPL - 1) / (32 * CPL);
+    // tuning knobs (defaults from the r01 sweep in profiles/): channels per lane and resident-warp target per SM
+    static const int cpl_env = getenv("CSDRB_DDC_CPL") ? atoi(getenv("CSDRB_DDC_CPL")) : 1;
+    static const int wps_env = getenv("CSDRB_DDC_WPS") ? atoi(getenv("CSDRB_DDC_WPS")) : 24;
+    const int cpl = cpl_env == 2 ? 2 : 1;
+    const int warps_per_seg = (channels + 32 * cpl - 1) / (32 * cpl);
     const int groups = (warps_per_seg + 3) / 4;
-    // enough warps to fill the machine (~10 per SM) while keeping the M-1 trailing periods of every segment a small fraction
-    long want_segments = (148L * 10 + warps_per_seg - 1) / warps_per_seg;
+    // enough warps to fill the machine while keeping the M-1 trailing periods of every segment a small fraction
+    long want_segments = (148L * wps_env + warps_per_seg - 1) / warps_per_seg;
     int seg = (int)((n_out + want_segments - 1) / want_segments);
-    if (seg < 4 * M) seg = 4 * M;
+    if (seg < 2 * M) seg = 2 * M;
     dim3 grid((n_out + seg - 1) / seg, groups);
-    if (demod) ddc_bank_fused_kernel<D, M, CPL, true><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
-    else ddc_bank_fused_kernel<D, M, CPL, false><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp);
+#define CSDRB_DDC_LAUNCH(CPLV, DM) ddc_bank_fused_kernel<D, M, CPLV, DM><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp)
+    if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH(2, true); else CSDRB_DDC_LAUNCH(2, false); }
+    else { if (demod) CSDRB_DDC_LAUNCH(1, true); else CSDRB_DDC_LAUNCH(1, false); }
+#undef CSDRB_DDC_LAUNCH
     CSDRB_CUDA(cudaGetLastError());
     return 0;
 }

@@ -55,16 +55,16 @@ fft_c2c_batch_kernel(const float2* __restrict__ in, long in_stride, float2* __re
     const int tid = threadIdx.x;
     const float2* x = in + (long)blockIdx.x * in_stride;
     float2* y = out + (long)blockIdx.x * out_stride;
-    for (int i = tid; i < N; i += NT) s[i] = x[i];
+    for (int i = tid; i < N; i += NT) s[fft_pad(i)] = x[i];
     __syncthreads();
     block_fft<N, NT, INV>(s, tw, tid);
-    for (int i = tid; i < N; i += NT) y[i] = s[i];
+    for (int i = tid; i < N; i += NT) y[i] = s[fft_pad(i)];
 }
 
 template <int N>
 static int launch_c2c_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw, cudaStream_t st)
 {
-    const size_t smem = sizeof(float2) * N;
+    const size_t smem = sizeof(float2) * fft_smem_elems(N);
     if (inverse) {
         auto k = fft_c2c_batch_kernel<N, true>;
         if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -103,7 +103,7 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    float2* tail = s + N;
+    float2* tail = s + fft_smem_elems(N);
     constexpr int NT = fft_threads(N);
     const int tid = threadIdx.x, ch = blockIdx.y;
     const int overlap = N - input_size;
@@ -123,24 +123,25 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
     for (int i = tid; i < overlap; i += NT) tail[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
     for (int b = b_start; b < b_last; b++) {
         const bool emit = b >= b_first;
-        for (int i = tid; i < N; i += NT) s[i] = i < input_size ? x[(long)b * input_size + i] : make_float2(0.f, 0.f);
+        for (int i = tid; i < N; i += NT) s[fft_pad(i)] = i < input_size ? x[(long)b * input_size + i] : make_float2(0.f, 0.f);
         __syncthreads();
         block_fft<N, NT, false>(s, tw, tid);
         for (int i = tid; i < N; i += NT) {
-            const float2 a = s[i], h = H[i];
+            const float2 a = s[fft_pad(i)], h = H[i];
             // same rounding sequence as libcsdr.c:827-828 (separate products, no FMA)
-            s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+            s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
         }
         __syncthreads();
         block_fft<N, NT, true>(s, tw, tid);
         for (int i = tid; i < N; i += NT) {
-            float2 v = make_float2(s[i].x * inv_n, s[i].y * inv_n);
+            const float2 raw = s[fft_pad(i)];
+            float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
             if (i < overlap) v = make_float2(__fadd_rn(v.x, tail[i].x), __fadd_rn(v.y, tail[i].y));
-            s[i] = v;
+            s[fft_pad(i)] = v;
             if (emit && i < input_size) y[(long)b * input_size + i] = v;
         }
         __syncthreads();
-        for (int i = tid; i < overlap; i += NT) tail[i] = s[input_size + i];
+        for (int i = tid; i < overlap; i += NT) tail[i] = s[fft_pad(input_size + i)];
         __syncthreads();
     }
     if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
@@ -161,7 +162,7 @@ int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long o
         if (blocks_per_cta < 16) blocks_per_cta = nblocks < 16 ? nblocks : 16;
     }
     const dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, channels);
-    const size_t smem = sizeof(float2) * 2 * (size_t)fft_size;
+    const size_t smem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + (size_t)fft_size);
     switch (fft_size) {
 #define X(N) case N: if constexpr (N >= 4 && N <= 8192) { auto k = olafir_bank_kernel<N>; \
         if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -188,12 +189,12 @@ fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, 
     const long start = (long)b * input_size - overlap;
     for (int i = tid; i < N; i += NT) {
         const long p = start + i;
-        s[i] = p >= 0 ? in[p] : overlap_in[overlap + p];
+        s[fft_pad(i)] = p >= 0 ? in[p] : overlap_in[overlap + p];
     }
     __syncthreads();
     block_fft<N, NT, false>(s, tw, tid);
     float2* y = spectra + (long)b * N;
-    for (int i = tid; i < N; i += NT) y[i] = s[i];
+    for (int i = tid; i < N; i += NT) y[i] = s[fft_pad(i)];
 }
 
 __global__ void __launch_bounds__(1024)
@@ -220,7 +221,7 @@ int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_
     if (fft_size < 4 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("fastddc_fwd: fft_size %d unsupported", fft_size); return -1; }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
-    const size_t smem = sizeof(float2) * (size_t)fft_size;
+    const size_t smem = sizeof(float2) * (size_t)fft_smem_elems(fft_size);
     switch (fft_size) {
 #define X(N) case N: if constexpr (N >= 4) { auto k = fastddc_fwd_kernel<N>; \
         if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -248,18 +249,18 @@ apply_fir_fft_kernel(const float2* __restrict__ in, const float2* __restrict__ H
     float2* s = reinterpret_cast<float2*>(smem_raw);
     constexpr int NT = fft_threads(N);
     const int tid = threadIdx.x;
-    for (int i = tid; i < N; i += NT) s[i] = in[i];
+    for (int i = tid; i < N; i += NT) s[fft_pad(i)] = in[i];
     __syncthreads();
     block_fft<N, NT, false>(s, tw, tid);
     for (int i = tid; i < N; i += NT) {
-        const float2 a = s[i], h = H[i];
-        s[i] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        const float2 a = s[fft_pad(i)], h = H[i];
+        s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
     }
     __syncthreads();
     block_fft<N, NT, true>(s, tw, tid);
     const float inv_n = 1.0f / (float)N;
     for (int i = tid; i < N; i += NT) {
-        float2 v = make_float2(s[i].x * inv_n, s[i].y * inv_n);
+        float2 v = make_float2(s[fft_pad(i)].x * inv_n, s[fft_pad(i)].y * inv_n);
         if (i < overlap_size) v = make_float2(__fadd_rn(v.x, last_overlap[i].x), __fadd_rn(v.y, last_overlap[i].y));
         out[i] = v;
     }
@@ -271,7 +272,7 @@ int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const flo
     if (fft_size < 2 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("apply_fir_fft: fft_size %d unsupported", fft_size); return -1; }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
-    const size_t smem = sizeof(float2) * (size_t)fft_size;
+    const size_t smem = sizeof(float2) * (size_t)fft_smem_elems(fft_size);
     switch (fft_size) {
 #define X(N) case N: { auto k = apply_fir_fft_kernel<N>; \
         if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -319,7 +320,7 @@ fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const fl
                    float2* __restrict__ out, long out_stride, int N, int pre_decimation, int scrap, int post_input_size, int post_decimation,
                    int nblocks, const float2* __restrict__ tw)
 {
-    __shared__ float2 s[M];
+    __shared__ float2 s[fft_smem_elems(M)];
     constexpr int NT = 256;
     static_assert(M <= 16 * NT, "fft_inv_size too large for this kernel");
     const int tid = threadIdx.x, b = blockIdx.x, c = blockIdx.y;
@@ -342,7 +343,7 @@ fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const fl
         if (dst < 0) dst += M;
         // second swap (fastddc.c:150) folded into the store index
         const int d2 = dst < M / 2 ? dst + M / 2 : dst - M / 2;
-        s[d2] = make_float2(ai * inv_pre, aq * inv_pre);
+        s[fft_pad(d2)] = make_float2(ai * inv_pre, aq * inv_pre);
     }
     __syncthreads();
     block_fft<M, NT, true>(s, tw, tid);
@@ -355,11 +356,96 @@ fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const fl
         float2* y = out + (long)c * out_stride + blk_offset[bi];
         int k = 0;
         for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
-            const float2 v = make_float2(s[scrap + pos].x * inv_m, s[scrap + pos].y * inv_m);
+            const float2 raw = s[fft_pad(scrap + pos)];
+            const float2 v = make_float2(raw.x * inv_m, raw.y * inv_m);
             y[k++] = make_float2(__fsub_rn(__fmul_rn(co, v.x), __fmul_rn(si, v.y)), __fadd_rn(__fmul_rn(si, v.x), __fmul_rn(co, v.y)));
             const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
             const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
             co = cn; si = sn;
+        }
+    }
+}
+
+// Tiled variant for M <= 1024: one CTA folds CT channels x BT blocks at once, so every spectrum bin is fetched once per CT
+// channels and every tap once per BT blocks (r01: the untiled kernel moved 256 KB of L2 traffic per (channel, block) and ran
+// at the L2 bandwidth limit).  The CT*BT inverse FFTs run four at a time (64 threads each); the CT*BT sequential post-shift
+// chains run on CT*BT different lanes in parallel.  Summation order per destination bin is still ascending, as in the reference.
+template <int M, int CT, int BT>
+__global__ void __launch_bounds__(256)
+fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __restrict__ taps_fft, const DdcChan* __restrict__ chan,
+                         const int* __restrict__ blk_remain, const float* __restrict__ blk_phase, const int* __restrict__ blk_offset,
+                         float2* __restrict__ out, long out_stride, int N, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                         int nblocks, int channels, const float2* __restrict__ tw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* s = reinterpret_cast<float2*>(smem_raw);                    // CT*BT padded arrays of M
+    constexpr int NT = 256, NTG = 64, GROUPS = NT / NTG, ELEMS = fft_smem_elems(M), PERT = (M + NT - 1) / NT;
+    static_assert(M <= 16 * NTG, "tiled fastddc_inv needs M <= 1024");
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * BT, c0 = blockIdx.y * CT;
+    const int half = N / 2;
+    const float inv_pre = 1.0f / (float)pre_decimation;                 // power of two: exact
+    int cidx[CT], bidx[BT];
+#pragma unroll
+    for (int u = 0; u < CT; u++) cidx[u] = min(c0 + u, channels - 1);   // ragged edges shadow the last valid channel / block
+#pragma unroll
+    for (int v = 0; v < BT; v++) bidx[v] = min(b0 + v, nblocks - 1);
+#pragma unroll 1
+    for (int rr = 0; rr < PERT; rr++) {
+        const int r = tid + rr * NT;
+        if (r >= M) break;
+        float2 acc[CT][BT];
+#pragma unroll
+        for (int u = 0; u < CT; u++)
+#pragma unroll
+            for (int v = 0; v < BT; v++) acc[u][v] = make_float2(0.f, 0.f);
+        for (int i = r; i < N; i += M) {
+            const int xi = i < half ? i + half : i - half;
+            float2 x[BT], h[CT];
+#pragma unroll
+            for (int v = 0; v < BT; v++) x[v] = __ldg(spectra + (long)bidx[v] * N + xi);
+#pragma unroll
+            for (int u = 0; u < CT; u++) h[u] = __ldg(taps_fft + (long)cidx[u] * N + i);
+#pragma unroll
+            for (int u = 0; u < CT; u++)
+#pragma unroll
+                for (int v = 0; v < BT; v++) {
+                    acc[u][v].x = __fadd_rn(acc[u][v].x, __fsub_rn(__fmul_rn(x[v].x, h[u].x), __fmul_rn(x[v].y, h[u].y)));
+                    acc[u][v].y = __fadd_rn(acc[u][v].y, __fadd_rn(__fmul_rn(x[v].x, h[u].y), __fmul_rn(x[v].y, h[u].x)));
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < CT; u++) {
+            int dst = (N + r - chan[cidx[u]].offsetbin + M / 2) % M;
+            if (dst < 0) dst += M;
+            const int d2 = dst < M / 2 ? dst + M / 2 : dst - M / 2;   // second swap folded into the store index
+#pragma unroll
+            for (int v = 0; v < BT; v++) s[(u * BT + v) * ELEMS + fft_pad(d2)] = make_float2(acc[u][v].x * inv_pre, acc[u][v].y * inv_pre);
+        }
+    }
+    __syncthreads();
+    const int g = tid / NTG, tg = tid % NTG;
+#pragma unroll 1
+    for (int a = 0; a < CT * BT; a += GROUPS) block_fft<M, NTG, true>(s + (a + g) * ELEMS, tw, tg);   // CT*BT is a multiple of GROUPS
+    if (tid < CT * BT) {
+        const int u = tid / BT, v = tid % BT;
+        if (c0 + u < channels && b0 + v < nblocks) {
+            const DdcChan cp = chan[c0 + u];
+            const float2* src = s + tid * ELEMS;
+            const float inv_m = 1.0f / (float)M;
+            const long bi = (long)(c0 + u) * nblocks + (b0 + v);
+            const double ph = (double)blk_phase[bi];
+            float co = (float)cos(ph), si = (float)sin(ph);
+            float2* y = out + (long)(c0 + u) * out_stride + blk_offset[bi];
+            int k = 0;
+            for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
+                const float2 raw = src[fft_pad(scrap + pos)];
+                const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
+                y[k++] = make_float2(__fsub_rn(__fmul_rn(co, w.x), __fmul_rn(si, w.y)), __fadd_rn(__fmul_rn(si, w.x), __fmul_rn(co, w.y)));
+                const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+                const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+                co = cn; si = sn;
+            }
         }
     }
 }
@@ -384,6 +470,21 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     fastddc_state_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
     CSDRB_CUDA(cudaGetLastError());
+    if (fft_inv_size <= 1024 && fft_inv_size >= 8) {
+        constexpr int CT = 4, BT = 4;
+        const dim3 tgrid((nblocks + BT - 1) / BT, (channels + CT - 1) / CT);
+        const size_t smem = sizeof(float2) * (size_t)CT * BT * fft_smem_elems(fft_inv_size);
+        switch (fft_inv_size) {
+#define X(M) case M: if constexpr (M >= 8 && M <= 1024) { auto k = fastddc_inv_tiled_kernel<M, CT, BT>; \
+            if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                       fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        return 2;
+    }
     const dim3 grid(nblocks, channels);
     switch (fft_inv_size) {
 #define X(M) case M: if constexpr (M <= 4096) { fastddc_inv_kernel<M><<<grid, 256, 0, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, \

@@ -16,6 +16,12 @@
 
 namespace csdrb {
 
+// Shared-memory layout: element i lives at i + (i >> 3) (one pad slot per eight complex values, 12.5 % extra).
+// The first radix-8 pass writes 8 consecutive elements per thread (lane stride 8): unpadded that is a 16-way bank conflict on
+// 64-bit stores; with the skew the lane stride becomes 9 (odd) and the pass is conflict-free, as are the stride-64/512 passes.
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int fft_smem_elems(int n) { return n + (n >> 3) + 1; }
+
 template <bool INV>
 __device__ __forceinline__ float2 cmul_w(float2 a, float2 w)
 {
@@ -78,7 +84,7 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ s, const float2* _
         const int j = tid + b * NT;
         if (NB % NT == 0 || j < NB) {
 #pragma unroll
-            for (int r = 0; r < R; r++) v[b][r] = s[j + r * NB];
+            for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
             if constexpr (NS > 1) {
                 const int k = j % NS;
 #pragma unroll
@@ -94,7 +100,7 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ s, const float2* _
         if (NB % NT == 0 || j < NB) {
             const int j0 = (j / NS) * NS * R + (j % NS);
 #pragma unroll
-            for (int r = 0; r < R; r++) s[j0 + r * NS] = v[b][r];
+            for (int r = 0; r < R; r++) s[fft_pad(j0 + r * NS)] = v[b][r];
         }
     }
     __syncthreads();
@@ -111,8 +117,8 @@ __device__ __forceinline__ void fft_r8_passes(float2* __restrict__ s, const floa
 
 constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n / 2); }
 
-// In-place N-point transform of s[0..N) by a CTA of NT threads (all NT threads must call; s must be
-// visible to the CTA, i.e. a __syncthreads() separates the last write to s from this call).
+// In-place N-point transform of the PADDED array s (element i at s[fft_pad(i)], fft_smem_elems(N) slots) by a CTA of NT threads
+// (all NT threads must call; a __syncthreads() must separate the last write to s from this call).
 template <int N, int NT, bool INV>
 __device__ __forceinline__ void block_fft(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
 {
