@@ -30,14 +30,20 @@ int get_twiddles(int n, const float2** out, cudaStream_t st)
     std::lock_guard<std::mutex> lk(g_tw_mu);
     auto it = g_tw.find(n);
     if (it != g_tw.end()) { *out = it->second; return 0; }
-    std::vector<float2> h((size_t)n);
-    for (int k = 0; k < n; k++) {
-        const double a = -2.0 * M_PI * (double)k / (double)n;
-        h[k] = make_float2((float)cos(a), (float)sin(a));
-    }
+    // three planes (w^1, w^2, w^4) of n entries; a radix-8 pass over sub-size NS reads index NS + k, k < NS (see fft.cuh)
+    std::vector<float2> h((size_t)3 * n, make_float2(1.f, 0.f));
+    int lg = 0; while ((1 << lg) < n) lg++;
+    int ns = lg % 3 == 1 ? 2 : (lg % 3 == 2 ? 4 : 1);
+    if (ns == 1) ns = 8;                                                // first pass (NS = 1) needs no twiddles
+    for (; ns < n; ns *= 8)
+        for (int k = 0; k < ns; k++)
+            for (int c = 0; c < 3; c++) {
+                const double a = -2.0 * M_PI * (double)((1 << c) * k) / (double)(ns * 8);
+                h[(size_t)c * n + ns + k] = make_float2((float)cos(a), (float)sin(a));
+            }
     float2* d = nullptr;
-    CSDRB_CUDA(cudaMalloc(&d, sizeof(float2) * (size_t)n));
-    CSDRB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CSDRB_CUDA(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CSDRB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, st));
     CSDRB_CUDA(cudaStreamSynchronize(st));
     g_tw[n] = d;
     *out = d;
@@ -96,7 +102,7 @@ int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long
 
 // ---- K9: overlap-add FIR bank -------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(fft_threads(N))
+__global__ void __launch_bounds__(fft_threads(N), (N <= 4096 ? 2 : 1))
 olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                    const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
                    int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw)

@@ -9,8 +9,11 @@
 //     k = j mod Ns;   v[r] = s[j + r*N/R] * W_N^(k*r*N/(Ns*R));   V = DFT_R(v);   s'[(j/Ns)*Ns*R + k + r*Ns] = V[r]
 // All threads read their butterflies into registers, synchronise, then write: one buffer is enough
 // (a thread holds at most 16 points per pass, so NT >= N/16 threads are required).
-// Twiddles come from a per-size table W_N^k = exp(-2*pi*i*k/N) computed in double on the host and
-// rounded once to float (error ~6e-8 per twiddle; the whole transform stays ~1e-7*log2 N from the exact DFT).
+// Twiddles: for a radix-8 pass over sub-transforms of size NS the butterfly with k = j mod NS needs w^r, w = exp(-2*pi*i*k/(8*NS)).
+// Three planes of a per-size table hold w^1, w^2, w^4 at index NS + k (the ranges [NS, 2NS) of the different passes do not
+// overlap), computed in double on the host and rounded once to float; lanes with consecutive k read consecutive entries (the r01
+// profile showed seven scattered LDGs per butterfly saturating L1TEX).  w^3, w^5, w^6, w^7 are one float product each, so every
+// twiddle is within ~2 ulp and the whole transform stays ~1e-7*log2 N from the exact DFT.
 #pragma once
 #include "common.cuh"
 
@@ -86,9 +89,16 @@ __device__ __forceinline__ void fft_pass(float2* __restrict__ s, const float2* _
 #pragma unroll
             for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
             if constexpr (NS > 1) {
+                static_assert(R == 8, "only the first pass may have a radix below 8");
                 const int k = j % NS;
-#pragma unroll
-                for (int r = 1; r < R; r++) v[b][r] = cmul_w<INV>(v[b][r], __ldg(tw + k * r * (N / (NS * R))));
+                const float2 w1 = __ldg(tw + NS + k), w2 = __ldg(tw + N + NS + k), w4 = __ldg(tw + 2 * N + NS + k);
+                const float2 w3 = make_float2(fmaf(w1.x, w2.x, -w1.y * w2.y), fmaf(w1.x, w2.y, w1.y * w2.x));
+                const float2 w5 = make_float2(fmaf(w1.x, w4.x, -w1.y * w4.y), fmaf(w1.x, w4.y, w1.y * w4.x));
+                const float2 w6 = make_float2(fmaf(w2.x, w4.x, -w2.y * w4.y), fmaf(w2.x, w4.y, w2.y * w4.x));
+                const float2 w7 = make_float2(fmaf(w3.x, w4.x, -w3.y * w4.y), fmaf(w3.x, w4.y, w3.y * w4.x));
+                v[b][1] = cmul_w<INV>(v[b][1], w1); v[b][2] = cmul_w<INV>(v[b][2], w2); v[b][3] = cmul_w<INV>(v[b][3], w3);
+                v[b][4] = cmul_w<INV>(v[b][4], w4); v[b][5] = cmul_w<INV>(v[b][5], w5); v[b][6] = cmul_w<INV>(v[b][6], w6);
+                v[b][7] = cmul_w<INV>(v[b][7], w7);
             }
             dft_small<R, INV>(v[b]);
         }
