@@ -96,6 +96,10 @@ def lib() -> C.CDLL:
     L.csdrb_bandpass_fir_fft_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, it, vp, lg, vp, vp]
     L.csdrb_ddc_bank_scratch_bytes.argtypes = [it, it, it, it]; L.csdrb_ddc_bank_scratch_bytes.restype = sz
     L.csdrb_ddc_bank.argtypes = [vp, it, it, vp, vp, it, it, it, C.POINTER(C.c_float), it, it, vp, lg, vp, vp, vp, sz, vp]
+    L.csdrb_limit_ff.argtypes = [vp, vp, lg, C.c_float, vp]
+    L.csdrb_deemphasis_wfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, vp]
+    L.limit_ff.argtypes = [vp, vp, it, C.c_float]
+    L.deemphasis_wfm_ff.argtypes = [vp, vp, it, C.c_float, it, C.c_float]; L.deemphasis_wfm_ff.restype = C.c_float
     L.csdrb_fastddc_fwd_cc.argtypes = [vp, vp, vp, it, it, it, vp]
     L.csdrb_fastddc_inv_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastddc_inv_bank_scratch_bytes.restype = sz
     L.csdrb_fastddc_inv_bank_cc.argtypes = [vp, it, vp, vp, it, C.POINTER(FastDDC), vp, vp, vp, lg, vp, vp, sz, vp]
@@ -370,6 +374,19 @@ class libcsdr:
         return y
 
     @staticmethod
+    def deemphasis_wfm_ff(x, tau, sample_rate, last=0.0, block=None):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x); block = block or max(x.size, 1)
+        for s0 in range(0, x.size, block):
+            n = min(block, x.size - s0)
+            last = lib().deemphasis_wfm_ff(x[s0:].ctypes.data, y[s0:].ctypes.data, n, tau, sample_rate, last)
+        return y, float(np.float32(last))
+
+    @staticmethod
+    def limit_ff(x, max_amplitude=1.0):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
+        lib().limit_ff(x.ctypes.data, y.ctypes.data, x.size, max_amplitude); return y
+
+    @staticmethod
     def dft(x, forward=True):
         x = np.ascontiguousarray(x, np.complex64).copy(); y = np.empty_like(x)
         pl = lib().make_fft_c2c(x.size, x.ctypes.data, y.ctypes.data, 1 if forward else 0, 0)
@@ -609,3 +626,23 @@ def ddc_bank(wide, rates, decimation: int, taps: np.ndarray, demod: bool = True,
                                      last_out.data_ptr() if last_out is not None else None, scratch.data_ptr(), scratch.numel(), _stream()), "ddc_bank")
     assert rc == n_out
     return out[:, :n_out], d_phase, last_out
+
+
+def limit_ff(x, max_amplitude: float = 1.0, out=None):
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    _check(lib().csdrb_limit_ff(x.data_ptr(), out.data_ptr(), x.numel(), max_amplitude, _stream()), "limit_ff")
+    return out
+
+
+def deemphasis_wfm_bank_ff(x, tau: float, sample_rate: int, last=None, out=None):
+    """x [C, N] float32 -> (y [C, N], carried last outputs [C])."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    ch, n = x.shape
+    out = torch.empty((ch, n), dtype=torch.float32, device=x.device) if out is None else out
+    last = torch.zeros(ch, dtype=torch.float32, device=x.device) if last is None else last.clone()
+    _check(lib().csdrb_deemphasis_wfm_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, tau, sample_rate, last.data_ptr(), _stream()),
+           "deemphasis_wfm_bank_ff")
+    return out, last

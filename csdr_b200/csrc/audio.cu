@@ -99,6 +99,51 @@ int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d
     return 2;
 }
 
+// ---------------------------------------------------------------------------------------------- de-emphasis
+// deemphasis_wfm_ff (libcsdr.c:1081-1097): y[i] = alpha*x[i] + (1-alpha)*y[i-1] -- a float recursion whose rounding sequence is
+// the result, so it stays sequential per channel: lane = channel, a warp moves 32 channels through a padded shared tile so that
+// global accesses are coalesced rows while each lane walks its own row (same scheme as the NCO kernel).
+__global__ void __launch_bounds__(128)
+deemphasis_wfm_bank_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride, int channels, int n,
+                           float alpha, float keep, float* __restrict__ last_io)
+{
+    __shared__ float tile_all[4][32 * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = tile_all[warp];
+    const int c0 = (blockIdx.x * 4 + warp) * 32;
+    if (c0 >= channels) return;
+    const int rows = min(32, channels - c0);
+    const bool live = lane < rows;
+    float y = live ? last_io[c0 + lane] : 0.f;
+    if (y != y) y = 0.f;                                               // NaN carry restarts from 0 (libcsdr.c:1092)
+    for (int t0 = 0; t0 < n; t0 += 32) {
+        const int len = min(32, n - t0);
+        for (int r = 0; r < rows; r++) tile[r * 33 + lane] = lane < len ? in[(long)(c0 + r) * in_stride + t0 + lane] : 0.f;
+        __syncwarp();
+        if (live) {
+            float* row = tile + lane * 33;
+            for (int j = 0; j < len; j++) { y = __fadd_rn(__fmul_rn(alpha, row[j]), __fmul_rn(keep, y)); row[j] = y; }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) if (lane < len) out[(long)(c0 + r) * out_stride + t0 + lane] = tile[r * 33 + lane];
+        __syncwarp();
+    }
+    if (live) last_io[c0 + lane] = y;
+}
+
+int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, float tau, int sample_rate,
+                               float* d_last_io, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if (sample_rate <= 0) { set_error("deemphasis_wfm: sample_rate must be positive"); return -1; }
+    const float dt = (float)(1.0 / sample_rate);                        // same promotions as libcsdr.c:1090-1091
+    const float alpha = dt / (tau + dt);
+    const float keep = 1 - alpha;
+    deemphasis_wfm_bank_kernel<<<(channels + 127) / 128, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, channels, n, alpha, keep, d_last_io);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ---------------------------------------------------------------------------------------------- K6
 // The gain of block b is reference / max(peak_b, peak_{b-1}, peak_{b-2}) (capped), ramped from the gain of block b-1, applied to
 // block b-2: nothing is sequential beyond a three-block window, so the bank runs fully parallel over (channel, block):

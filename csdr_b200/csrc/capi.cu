@@ -374,6 +374,21 @@ int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const comp
     return rc < 0 ? rc : counted(0, rc);
 }
 
+int csdrb_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, void* stream)
+{
+    if (!d_in || !d_out) { set_error("limit_ff: null pointer"); return -1; }
+    int rc = launch_limit_ff(d_in, d_out, n, max_amplitude, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_deemphasis_wfm_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int input_size, float tau,
+                                 int sample_rate, float* d_last_io, void* stream)
+{
+    if (!d_in || !d_out || !d_last_io) { set_error("deemphasis_wfm bank: null pointer"); return -1; }
+    int rc = launch_deemphasis_wfm_bank(d_in, in_stride, d_out, out_stride, channels, input_size, tau, sample_rate, d_last_io, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 size_t csdrb_ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset) { return ddc_bank_scratch_bytes(channels, input_size, chunk, offset); }
 
 int csdrb_ddc_bank(const complexf* d_wide, int input_size, int channels, const shift_addition_data_t* d_params, float* d_phase_io, int chunk, int offset,
@@ -516,6 +531,33 @@ void fastagc_ff(fastagc_ff_t* a, float* output)
     float* recycled = a->buffer_1;
     a->buffer_1 = a->buffer_2; a->buffer_2 = a->buffer_input; a->buffer_input = recycled;
     a->peak_1 = st.peak_1; a->peak_2 = st.peak_2; a->last_gain = st.last_gain;
+}
+
+void limit_ff(float* input, float* output, int input_size, float max_amplitude)
+{
+    const char* who = "limit_ff";
+    if (input_size <= 0) return;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_size * 4, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 4 + 16), who);
+    A_CHECK(csdrb_limit_ff((const float*)g_ctx.buf[0], (float*)g_ctx.buf[1], input_size, max_amplitude, g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)input_size * 4, who);
+    A_SYNC(who);
+}
+
+float deemphasis_wfm_ff(float* input, float* output, int input_size, float tau, int sample_rate, float last_output)
+{
+    const char* who = "deemphasis_wfm_ff";
+    if (input_size <= 0) return last_output;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_size * 4, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 4 + 16), who);
+    A_UP(2, &last_output, 4, who);
+    A_CHECK(csdrb_deemphasis_wfm_bank_ff((const float*)g_ctx.buf[0], input_size, (float*)g_ctx.buf[1], input_size, 1, input_size, tau, sample_rate,
+                                         (float*)g_ctx.buf[2], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)input_size * 4, who);
+    A_SYNC(who);
+    return output[input_size - 1];
 }
 
 // ---- FFT abstraction ---------------------------------------------------------------------------------

@@ -121,6 +121,29 @@ int launch_convert_f_s16(const float* d_in, short* d_out, long n, cudaStream_t s
     return 0;
 }
 
+// ---- limit_ff (libcsdr.c:1130-1137): clamp to +-max; NaN -> +max like the reference build's minss/maxss (see oracle.c) ----
+__global__ void __launch_bounds__(256) limit_ff_kernel(const float* __restrict__ in, float* __restrict__ out, long n, float max_amplitude)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long nvec = n / 4;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + v);
+        st_na_f4(reinterpret_cast<float4*>(out) + v,
+                 make_float4(fmaxf(-max_amplitude, fminf(max_amplitude, a.x)), fmaxf(-max_amplitude, fminf(max_amplitude, a.y)),
+                             fmaxf(-max_amplitude, fminf(max_amplitude, a.z)), fmaxf(-max_amplitude, fminf(max_amplitude, a.w))));
+    }
+    for (long i = nvec * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = fmaxf(-max_amplitude, fminf(max_amplitude, in[i]));
+}
+
+int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15)) { set_error("limit_ff: device buffers must be 16-byte aligned"); return -1; }
+    limit_ff_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, st>>>(d_in, d_out, n, max_amplitude);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ---- K4 fmdemod_quadri_cf -------------------------------------------------------------------------
 // out[i] = den ? K*(I*(Q-Qprev) - Q*(I-Iprev))/den : 0 with den = I*I+Q*Q; no FMA contraction so that
 // every intermediate rounds like the reference's SSE code; the K*num/den tail is evaluated in double

@@ -17,6 +17,10 @@ int launch_convert_f_s16(const float* d_in, short* d_out, long n, cudaStream_t s
 int launch_fmdemod_quadri_bank(const float2* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
                                const float2* d_last_in, float2* d_last_out, cudaStream_t st);
 
+int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, cudaStream_t st);
+int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, float tau, int sample_rate,
+                               float* d_last_io, cudaStream_t st);
+
 // K2 shift.cu
 size_t shift_bank_scratch_bytes(int channels, int n, int chunk);
 int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,

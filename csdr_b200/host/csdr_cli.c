@@ -237,6 +237,38 @@ static int cmd_fmdemod_quadri_cf(int argc, char **argv)
     }
 }
 
+static int cmd_limit_ff(int argc, char **argv)                              /* csdr.c:673-686 */
+{
+    float max_amplitude = 1.0f; if (argc >= 3) sscanf(argv[2], "%g", &max_amplitude);
+    if (!announce_block(open_block())) return -2;
+    float *in = must_alloc(sizeof(float) * (size_t)block), *out = must_alloc(sizeof(float) * (size_t)block);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in, sizeof(float), (size_t)block, stdin);
+        limit_ff(in, out, block, max_amplitude);
+        fwrite(out, sizeof(float), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_deemphasis_wfm_ff(int argc, char **argv)                     /* csdr.c:1014-1032 */
+{
+    if (argc <= 3) return complain("need required parameters (sample rate, tau)");
+    if (!announce_block(open_block())) return -2;
+    int sample_rate = 0; sscanf(argv[2], "%d", &sample_rate);
+    float tau = 0; sscanf(argv[3], "%g", &tau);
+    who(); fprintf(stderr, "tau = %g, sample_rate = %d\n", tau, sample_rate);
+    float *in = must_alloc(sizeof(float) * (size_t)block), *out = must_alloc(sizeof(float) * (size_t)block);
+    float last = 0;
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in, sizeof(float), (size_t)block, stdin);
+        last = deemphasis_wfm_ff(in, out, block, tau, sample_rate, last);
+        fwrite(out, sizeof(float), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_fractional_decimator_ff(int argc, char **argv)
 {
     if (argc <= 2) return complain("need required parameters (rate)");
@@ -430,6 +462,8 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fmdemod_quadri_cf", cmd_fmdemod_quadri_cf, "fmdemod_quadri_cf"},
     {"fractional_decimator_ff", cmd_fractional_decimator_ff, "fractional_decimator_ff <decimation_rate> [num_poly_points ( [transition_bw [window]] | --prefilter )]"},
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
+    {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
+    {"deemphasis_wfm_ff", cmd_deemphasis_wfm_ff, "deemphasis_wfm_ff <sample_rate> <tau>"},
     {"bandpass_fir_fft_cc", cmd_bandpass_fir_fft_cc, "bandpass_fir_fft_cc <low_cut> <high_cut> <transition_bw> [window] | --fifo <fifo_path> <transition_bw> [window]"},
     {"fastddc_fwd_cc", cmd_fastddc_fwd_cc, "fastddc_fwd_cc <decimation> [transition_bw [window]]"},
     {"fastddc_inv_cc", cmd_fastddc_inv_cc, "fastddc_inv_cc <shift_rate> <decimation> [transition_bw [window]] | --fifo <fifo_path> ... | --fd <fd> ..."},

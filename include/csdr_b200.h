@@ -84,6 +84,10 @@ typedef struct fastagc_ff_s {
 } fastagc_ff_t;
 void fastagc_ff(fastagc_ff_t *input, float *output);
 
+/* audio tail of the WFM graph, SURVEY 8(f) rank 1 (libcsdr.h:100-105; libcsdr.c:1081-1097, 1130-1137) */
+float deemphasis_wfm_ff(float *input, float *output, int input_size, float tau, int sample_rate, float last_output);
+void  limit_ff(float *input, float *output, int input_size, float max_amplitude);
+
 /* FFT abstraction (fft_fftw.h:10-27; fft_fftw.c:6-46).  Callers read ->size/->input/->output directly
  * (libcsdr.c:822-835, fastddc.c:112-116), so the first three members keep the reference layout. */
 struct fft_plan_s { int size; void *input; void *output; void *plan; };
@@ -174,6 +178,11 @@ size_t csdrb_ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int
 int csdrb_ddc_bank(const complexf *d_wide, int input_size, int channels, const shift_addition_data_t *d_params, float *d_phase_io,
                    int chunk, int offset, int decimation, const float *h_taps, int taps_length, int demod, void *d_out, long out_stride,
                    const complexf *d_last_in, complexf *d_last_out, void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* audio tail banks: hard limiter (elementwise) and the 1-pole de-emphasis IIR (d_last_io[c] = previous output of channel c) */
+int csdrb_limit_ff(const float *d_in, float *d_out, long n, float max_amplitude, void *stream);
+int csdrb_deemphasis_wfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
+                                 float tau, int sample_rate, float *d_last_io, void *stream);
 
 /* K5 fractional_decimator_ff bank: d_state[c].where carries the reference's `where`; on return input_processed
  * and output_size are filled like fractional_decimator_ff() fills them (libcsdr.c:789-792). */

@@ -307,6 +307,34 @@ void oracle_fastagc_ff(oracle_fastagc_t *st, float *hist1, float *hist2, const f
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * audio tail
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:1081-1097] y[i] = alpha*x[i] + (1-alpha)*y[i-1], alpha = dt/(tau+dt), dt = 1/sample_rate; everything in float
+ * except the 1.0/sample_rate division; a NaN carry restarts from 0. */
+float oracle_deemphasis_wfm_ff(const float *in, float *out, int n, float tau, int sample_rate, float last_output)
+{
+    float dt = (float)(1.0 / sample_rate);
+    float alpha = dt / (tau + dt);
+    float keep = 1 - alpha;
+    if (last_output != last_output) last_output = 0.0f;
+    float y = last_output;
+    for (int k = 0; k < n; k++) { y = alpha * in[k] + keep * y; out[k] = y; }
+    return n > 0 ? out[n - 1] : last_output;
+}
+
+/* [ref libcsdr.c:1130-1137] clamp to +-max_amplitude.  The reference's own build flags (-ffast-math) compile the two selects to
+ * minss/maxss, which return the non-NaN operand: a NaN sample leaves as +max_amplitude in every shipped libcsdr (verified against
+ * oracle/_ref), so that is what we pin (the strict C expression would pass the NaN through). */
+void oracle_limit_ff(const float *in, float *out, int n, float max_amplitude)
+{
+    for (int k = 0; k < n; k++) {
+        float v = (in[k] != in[k]) ? max_amplitude : ((max_amplitude < in[k]) ? max_amplitude : in[k]);
+        out[k] = (-max_amplitude > v) ? -max_amplitude : v;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * DFT (stands in for FFTW3f)
  * ---------------------------------------------------------------------------------------------- */
 

@@ -70,6 +70,10 @@ void oracle_fractional_decimator_ff(const float *in, float *out, int n, oracle_f
 typedef struct { float peak_1, peak_2, reference, last_gain; int block; } oracle_fastagc_t;
 void oracle_fastagc_ff(oracle_fastagc_t *st, float *hist1, float *hist2, const float *in, float *out);
 
+/* audio tail of the WFM/NFM graphs: libcsdr.c:1081-1097 (1-pole de-emphasis IIR), 1130-1137 (hard limiter) */
+float oracle_deemphasis_wfm_ff(const float *in, float *out, int n, float tau, int sample_rate, float last_output);
+void  oracle_limit_ff(const float *in, float *out, int n, float max_amplitude);
+
 /* mathematical DFT in float64, rounded once to float (stands in for FFTW3f; fft_fftw.c:6-41) */
 void oracle_dft_c2c(const ocf32 *in, ocf32 *out, int n, int forward);
 

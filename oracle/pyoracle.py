@@ -98,6 +98,9 @@ class Oracle:
         L.oracle_fractional_decimator_ff_init.argtypes = [C.POINTER(self._FracDec), C.c_float, C.c_int, C.POINTER(C.c_float), C.c_int]
         L.oracle_fractional_decimator_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(self._FracDec)]
         L.oracle_fastagc_ff.argtypes = [C.POINTER(self._Agc)] + [C.POINTER(C.c_float)] * 4
+        L.oracle_deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
+        L.oracle_deemphasis_wfm_ff.restype = C.c_float
+        L.oracle_limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
         L.oracle_dft_c2c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int]
         L.oracle_apply_fir_fft_cc.argtypes = [C.POINTER(_CF)] * 3 + [C.c_int, C.POINTER(_CF), C.c_int]
         L.oracle_fastddc_init.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_float]
@@ -182,6 +185,18 @@ class Oracle:
             self.L.oracle_fastagc_ff(C.byref(st), _p(h1, C.c_float), _p(h2, C.c_float),
                                      _p(x[b * block:], C.c_float), _p(y[b * block:], C.c_float))
         return y
+
+    # ---- audio tail
+    def deemphasis_wfm_ff(self, x, tau, sample_rate, last=0.0, block=None):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x); block = block or max(x.size, 1)
+        for s0 in range(0, x.size, block):
+            n = min(block, x.size - s0)
+            last = self.L.oracle_deemphasis_wfm_ff(_p(x[s0:], C.c_float), _p(y[s0:], C.c_float), n, tau, sample_rate, last)
+        return y, float(np.float32(last))
+
+    def limit_ff(self, x, max_amplitude=1.0):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
+        self.L.oracle_limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
 
     # ---- FFT family
     def dft(self, x, forward=True):
@@ -314,6 +329,9 @@ class Ref:
         L.fractional_decimator_ff_init.restype = self._FracDec
         L.fractional_decimator_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(self._FracDec)]
         L.fastagc_ff.argtypes = [C.POINTER(self._Agc), C.POINTER(C.c_float)]
+        L.deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
+        L.deemphasis_wfm_ff.restype = C.c_float
+        L.limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
         L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
         L.fft_execute.argtypes = [C.POINTER(self._Plan)]
         L.fft_destroy.argtypes = [C.POINTER(self._Plan)]
@@ -394,6 +412,17 @@ class Ref:
             byaddr[C.cast(st.buffer_input, C.c_void_p).value][:] = x[b * block:(b + 1) * block]
             self.L.fastagc_ff(C.byref(st), _p(y[b * block:], C.c_float))
         return y
+
+    def deemphasis_wfm_ff(self, x, tau, sample_rate, last=0.0, block=None):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x); block = block or max(x.size, 1)
+        for s0 in range(0, x.size, block):
+            n = min(block, x.size - s0)
+            last = self.L.deemphasis_wfm_ff(_p(x[s0:], C.c_float), _p(y[s0:], C.c_float), n, tau, sample_rate, last)
+        return y, float(np.float32(last))
+
+    def limit_ff(self, x, max_amplitude=1.0):
+        x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
+        self.L.limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
 
     def dft(self, x, forward=True):
         x = _c64(x).copy(); y = np.empty_like(x)

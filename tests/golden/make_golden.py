@@ -73,6 +73,11 @@ def main():
     g["agc_in"] = (rng.uniform(-1, 1, env.size).astype(np.float32) * env)
     g["agc_out_b256"] = r.fastagc_ff(g["agc_in"], 256, 1.0)
     g["agc_out_b512_ref0p5"] = r.fastagc_ff(g["agc_in"], 512, 0.5)
+    # --- audio tail (8f rank 1): 1-pole de-emphasis and limiter
+    g["deemph_in"] = rng.uniform(-1.5, 1.5, 4096).astype(np.float32)
+    y, last = r.deemphasis_wfm_ff(g["deemph_in"], 50e-6, 48000, 0.0, 1024)
+    g["deemph_out_50us_48k"], g["deemph_last"] = y, np.float32(last)
+    g["limit_out"] = r.limit_ff(g["deemph_in"], 1.0)
     # --- overlap-add FFT FIR (a10) : bw 0.05 -> 79 taps, fft 256, 178 samples/block (csdr.c:1833-1838)
     g["bp_in"] = cplx(rng, 434 * 5)
     g["bp_out"] = r.bandpass_fir_fft_cc(g["bp_in"], -0.1, 0.2, 0.05, "HAMMING")

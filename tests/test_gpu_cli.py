@@ -99,6 +99,18 @@ def test_nfm_style_chain(clis):
     assert a16.size == b16.size and np.abs(a16.astype(np.int32) - b16.astype(np.int32)).max() <= 1     # float->short of values equal to 1e-5
 
 
+def test_wfm_graph_of_csdr_fm(clis):
+    """The reference's canonical WFM receiver (csdr-fm:41, README.md:66) end to end:
+    convert_u8_f | fmdemod_quadri_cf | fractional_decimator_ff 5 | deemphasis_wfm_ff 48000 50e-6 | convert_f_s16, plus limit_ff."""
+    ours, ref = clis
+    data = fm_u8(480_000, seed=11)
+    stages = ["convert_u8_f", "fmdemod_quadri_cf", "fractional_decimator_ff 5", "deemphasis_wfm_ff 48000 50e-6", "limit_ff 0.5"]
+    a = np.frombuffer(run_graph(ours, stages, data), np.float32); b = np.frombuffer(run_graph(ref, stages, data), np.float32)
+    assert a.size == b.size and a.size > 90_000 and rel(a, b) < 1e-5
+    a16 = np.frombuffer(run_graph(ours, stages + ["convert_f_s16"], data), np.int16); b16 = np.frombuffer(run_graph(ref, stages + ["convert_f_s16"], data), np.int16)
+    assert a16.size == b16.size and np.abs(a16.astype(np.int32) - b16.astype(np.int32)).max() <= 1
+
+
 def test_fft_commands(clis):
     ours, ref = clis
     rng = np.random.default_rng(7)

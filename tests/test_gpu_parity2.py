@@ -288,3 +288,19 @@ def test_fused_ddc_bank_streams_block_by_block(gpu, oracle):
         sh, _ = oracle.shift_addition_cc(wide, float(r), 0.0, chunk)
         want = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0]
         assert got.shape[1] == want.size and _rel(got[c], want) < TOL
+
+
+# ------------------------------------------------------------------------------------------ audio tail (8f rank 1)
+def test_audio_tail_limit_and_deemphasis(gpu, oracle):
+    x = np.random.default_rng(31).uniform(-2, 2, 200_003).astype(np.float32)
+    x[7] = np.nan; x[9] = np.inf; x[11] = -np.inf
+    assert np.array_equal(gpu.limit_ff(_dev(x), 0.7).cpu().numpy(), oracle.limit_ff(x, 0.7))
+    assert np.array_equal(gpu.libcsdr.limit_ff(GOLD["deemph_in"], 1.0), GOLD["limit_out"])
+    y, last = gpu.libcsdr.deemphasis_wfm_ff(GOLD["deemph_in"], 50e-6, 48000, 0.0, 1024)
+    assert np.array_equal(y, GOLD["deemph_out_50us_48k"]) and np.float32(last) == GOLD["deemph_last"]     # same rounding sequence: bit exact
+    xb = np.stack([np.random.default_rng(c).uniform(-1, 1, 50_001).astype(np.float32) for c in range(37)])
+    lasts = np.linspace(-0.5, 0.5, 37).astype(np.float32); lasts[3] = np.nan
+    yb, lb = gpu.deemphasis_wfm_bank_ff(_dev(xb), 75e-6, 240000, last=_dev(lasts))
+    for c in range(37):
+        want, wl = oracle.deemphasis_wfm_ff(xb[c], 75e-6, 240000, float(lasts[c]))
+        assert np.array_equal(yb[c].cpu().numpy(), want) and np.float32(wl) == lb[c].item()

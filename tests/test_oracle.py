@@ -81,6 +81,22 @@ def test_golden_fastagc(oracle):
     assert not y[:512].any()                     # two blocks of latency: calloc'ed history (csdr.c:1394-1395)
 
 
+def test_golden_audio_tail(oracle):
+    y, last = oracle.deemphasis_wfm_ff(GOLD["deemph_in"], 50e-6, 48000, 0.0, 1024)
+    assert np.array_equal(y, GOLD["deemph_out_50us_48k"]) and np.float32(last) == GOLD["deemph_last"]
+    assert np.array_equal(oracle.limit_ff(GOLD["deemph_in"], 1.0), GOLD["limit_out"])
+
+
+def test_ref_audio_tail(oracle, ref):
+    x = np.random.default_rng(21).uniform(-2, 2, 1 << 16).astype(np.float32)
+    x[7] = np.nan; x[9] = np.inf; x[11] = -np.inf
+    assert np.array_equal(oracle.limit_ff(x, 0.7), ref.limit_ff(x, 0.7))            # NaN -> +max like the reference build (minss/maxss)
+    x = np.nan_to_num(x, nan=0.0, posinf=1.0, neginf=-1.0)
+    for tau, fs, last, blk in ((50e-6, 48000, 0.0, 1024), (75e-6, 240000, float("nan"), None), (50e-6, 44100, 0.3, 4096)):
+        ya, la = oracle.deemphasis_wfm_ff(x, tau, fs, last, blk); yb, lb = ref.deemphasis_wfm_ff(x, tau, fs, last, blk)
+        assert np.array_equal(ya, yb) and np.float32(la) == np.float32(lb)
+
+
 def test_golden_bandpass_fir_fft(oracle):
     y = oracle.bandpass_fir_fft_cc(GOLD["bp_in"], -0.1, 0.2, 0.05)
     assert y.size == GOLD["bp_out"].size == (GOLD["bp_in"].size // 178) * 178     # 79 taps -> fft 256, 178 per block

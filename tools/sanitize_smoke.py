@@ -1,0 +1,28 @@
+"""Every kernel once on small, awkward sizes -- meant to run under `compute-sanitizer --tool memcheck` (and racecheck)."""
+import sys, numpy as np, torch
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import csdr_b200 as cb
+dev = "cuda"; rng = np.random.default_rng(0)
+def cplx(*shape): return torch.view_as_complex(torch.rand(shape + (2,), device=dev) * 2 - 1)
+cb.convert_u8_f(torch.randint(0, 256, (4099,), dtype=torch.uint8, device=dev)); cb.convert_s16_f(torch.randint(-30000, 30000, (4099,), dtype=torch.int16, device=dev))
+f = torch.rand(4099, device=dev); cb.convert_f_s16(f); cb.limit_ff(f, 0.5)
+taps = cb.firdes_lowpass_f(199, 0.05)
+for n in (199, 208, 9999, 30011):
+    for v in (-1, 0, 1, 2, 3): cb.fir_decimate_bank_cc(cplx(3, n + (n & 1))[:, :n] if False else cplx(3, n + (n & 1)), 10, taps, variant=v)
+cb.fir_decimate_bank_cc(cplx(2, 5001), 7, cb.firdes_lowpass_f(79, 0.07))            # generic kernel, odd stride
+cb.fir_decimate_bank_cc(cplx(2, 70000), 50, cb.firdes_lowpass_f(801, 0.01))
+y = cb.fmdemod_quadri_bank_cf(cplx(3, 10001))
+cb.shift_addition_bank_cc(cplx(16384 + 777), [0.1, -0.3, 0.45], chunk=1024); cb.shift_addition_bank_cc(cplx(3, 1000), [0.1, -0.3, 0.45], chunk=37)
+a = torch.rand((3, 20000), device=dev); cb.fractional_decimator_bank_ff(a, 5.0, 12); cb.fractional_decimator_bank_ff(a, 2.5, 4, taps=cb.firdes_lowpass_f(31, 0.15))
+cb.fastagc_bank_ff(a[:, :19 * 1024], 1024, 1.0); cb.fastagc_bank_ff(a[:, :1000], 1000, 1.0); cb.deemphasis_wfm_bank_ff(a[:37 if False else 3, :10001].contiguous(), 50e-6, 48000)
+for n in (2, 4, 8, 16, 64, 512, 4096, 16384): cb.fft_c2c(cplx(2, n)); cb.fft_c2c(cplx(2, n), inverse=True)
+for bw in (0.002, 0.05, 0.005):
+    T, N, isz, ov = cb.bandpass_geometry(bw); cb.bandpass_fir_fft_bank_cc(cplx(3, 9 * isz), cb.bandpass_taps_fft(-0.1, 0.1, bw), isz)
+for bw, dec, sh in ((0.002, 64, [0.1, -0.3, 0.0, 0.2, 0.44]), (0.01, 6, [0.25]), (0.05, 8, [0.123, -0.2])):
+    d = cb.fastddc_init(bw, dec, 0.0); sp, ov = cb.fastddc_fwd_cc(cplx(3 * d.input_size), d); cb.fastddc_inv_bank_cc(sp, sh, dec, bw)
+for D, bw in ((50, 0.005), (10, 0.0201), (10, 0.05)):
+    T = cb.firdes_filter_len(bw)
+    for demod in (True, False): cb.ddc_bank(cplx(40000 + 14), np.linspace(-0.4, 0.4, 37), D, cb.firdes_lowpass_f(T, 0.5 / D), demod=demod, chunk=1024, offset=100)
+x = rng.integers(0, 256, 5000).astype(np.uint8); cb.libcsdr.convert_u8_f(x); cb.libcsdr.fir_decimate_cc(rng.normal(size=4000).astype(np.complex64), 10, taps)
+torch.cuda.synchronize(); print("sanitize_smoke: all kernels ran")
