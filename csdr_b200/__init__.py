@@ -582,21 +582,25 @@ def fastddc_inv_bank_cc(spectra, shifts, decimation: int, transition_bw: float, 
     import torch
     dev = spectra.device
     nblocks = spectra.shape[0]
-    ddcs = [fastddc_init(transition_bw, decimation, float(s)) for s in shifts]
-    g = ddcs[0]
-    ch = len(ddcs)
+    ch = len(shifts)
+    if state is not None:
+        g = state["geometry"]                                         # per-channel host work happens once, at bank creation
+    else:
+        ddcs = [fastddc_init(transition_bw, decimation, float(s)) for s in shifts]
+        g = ddcs[0]
     if state is None:
         taps_fft = torch.stack([fastddc_make_taps_fft(d, float(s), decimation, window, dev) for d, s in zip(ddcs, shifts)]).contiguous()
         chan = np.zeros((ch, 4), np.float32)
         chan.view(np.int32)[:, 0] = [d.offsetbin for d in ddcs]
         chan[:, 1] = [d.dsadata.sindelta for d in ddcs]; chan[:, 2] = [d.dsadata.cosdelta for d in ddcs]; chan[:, 3] = [d.dsadata.rate for d in ddcs]
         state = {"taps_fft": taps_fft, "chan": torch.from_numpy(chan).to(dev), "remain": torch.zeros(ch, dtype=torch.int32, device=dev),
-                 "phase": torch.zeros(ch, dtype=torch.float32, device=dev)}
+                 "phase": torch.zeros(ch, dtype=torch.float32, device=dev), "geometry": g}
     per_block = g.post_input_size // g.post_decimation + 1
-    out = torch.empty((ch, nblocks * per_block + 2), dtype=torch.complex64, device=dev)
-    counts = torch.zeros(ch, dtype=torch.int32, device=dev)
-    sb = lib().csdrb_fastddc_inv_bank_scratch_bytes(ch, nblocks)
-    scratch = _scratch(sb, dev)
+    key = ("buffers", nblocks)
+    if key not in state:
+        state[key] = (torch.empty((ch, nblocks * per_block + 2), dtype=torch.complex64, device=dev), torch.zeros(ch, dtype=torch.int32, device=dev),
+                      _scratch(lib().csdrb_fastddc_inv_bank_scratch_bytes(ch, nblocks), dev))
+    out, counts, scratch = state[key]
     _check(lib().csdrb_fastddc_inv_bank_cc(spectra.data_ptr(), nblocks, state["taps_fft"].data_ptr(), state["chan"].data_ptr(), ch, C.byref(g),
                                            state["remain"].data_ptr(), state["phase"].data_ptr(), out.data_ptr(), out.stride(0), counts.data_ptr(),
                                            scratch.data_ptr(), scratch.numel(), _stream()), "fastddc_inv_bank_cc")

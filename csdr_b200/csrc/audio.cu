@@ -39,12 +39,115 @@ __global__ void fracdec_positions_kernel(FracDecState* __restrict__ state, int* 
 }
 
 constexpr int FD_MAX_POINTS = 64;
+constexpr int FD_MAX_SEGS = 96;
+
+// Closed form of the position chain.  While `where` stays inside one binade [2^E, 2^(E+1)) it is M*u (u = 2^(E-23)) and
+// fl(where + rate) = (M + q)*u with a constant q = round(rate/u) (ties-to-even resolves to a constant step once M is even), as long
+// as the exact sum stays inside the binade.  So the chain is a handful of arithmetic progressions ("segments") joined by single
+// real float additions at the binade crossings; one thread per channel emits the segments (<= ~60 iterations instead of one
+// per output), and every output then recomputes its own `where` exactly from its segment.  Bit-exact with the sequential loop
+// (the K5 tests compare outputs with array_equal against the strict oracle).
+struct FdSeg { int k0; unsigned M; unsigned q; int E; int cnt; };
+
+__global__ void fracdec_segments_kernel(FracDecState* __restrict__ state, FdSeg* __restrict__ segs, int* __restrict__ nsegs, int channels, int n,
+                                        float rate, int num_poly_points, int xifirst, int taps_length, int cap)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const long L = (long)n - num_poly_points - taps_length - 1;          // loop runs while ceil(where) <= L
+    const unsigned rbits = __float_as_uint(rate);
+    const int er = (int)((rbits >> 23) & 0xff) - 127;
+    const unsigned R = (rbits & 0x7fffffu) | 0x800000u;                  // rate = R * 2^(er-23)
+    float where = state[c].where;
+    int k = 0, ns = 0;
+    FdSeg* out = segs + (long)c * FD_MAX_SEGS;
+    while ((long)ceilf(where) <= L && k < cap) {
+        int cnt = 1;
+        const unsigned wb = __float_as_uint(where);
+        const int E = (int)((wb >> 23) & 0xff) - 127;
+        const unsigned M = (wb & 0x7fffffu) | 0x800000u;
+        unsigned q = 0;
+        if (where > 0.f && E >= 0 && E <= 22 && ns < FD_MAX_SEGS - 2) {
+            const int d = E - er;                                        // ulp(where) = 2^d * ulp(rate)
+            unsigned cq = 0; bool regular = false;
+            if (d <= 0) { if (d >= -6) { q = R << (-d); cq = q; regular = true; } }
+            else if (d < 24) {
+                const unsigned frac = R & ((1u << d) - 1u), I = R >> d, half = 1u << (d - 1);
+                cq = I + (frac ? 1u : 0u);
+                if (frac != half) { q = I + (frac > half ? 1u : 0u); regular = true; }
+                else if ((M & 1u) == 0u) { q = I + (I & 1u); regular = true; }   // tie, M even: the sum always rounds to the even neighbour
+            }
+            if (regular && q > 0) {
+                const long room = (long)(1u << 24) - 1 - (long)cq - (long)M;      // transitions that provably stay in the binade
+                long jreg = room >= 0 ? room / (long)q : -1;
+                const long lim = (L << (23 - E)) - (long)M;                        // where_j <= L  <=>  M + j*q <= L / u
+                long jlim = lim >= 0 ? lim / (long)q : 0;
+                long j = jreg < jlim ? jreg : jlim;
+                if (j < 0) j = 0;
+                if (j + 1 > (long)(cap - k)) j = cap - k - 1;
+                cnt = (int)j + 1;
+            }
+        }
+        FdSeg sg; sg.k0 = k; sg.M = M; sg.q = cnt > 1 ? q : 0u; sg.E = E; sg.cnt = cnt;
+        if (cnt == 1) { sg.M = wb; sg.E = -1000; }                       // single output: keep the float itself
+        if (ns < FD_MAX_SEGS) out[ns++] = sg;
+        k += cnt;
+        const float last = cnt > 1 ? __uint_as_float(((unsigned)(E + 127) << 23) | ((M + (unsigned)(cnt - 1) * q) & 0x7fffffu)) : where;
+        where = __fadd_rn(last, rate);                                   // the crossing step (or a plain step) is a real float addition
+    }
+    const int index_high = (int)ceilf(where);
+    const int processed = (index_high - 1) + xifirst;
+    state[c].input_processed = processed;
+    state[c].where = __fsub_rn(where, (float)processed);
+    state[c].output_size = k;
+    nsegs[c] = ns;
+}
+
+__global__ void __launch_bounds__(128)
+fracdec_interp_seg_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride,
+                          const FracDecState* __restrict__ state, const FdSeg* __restrict__ segs, const int* __restrict__ nsegs,
+                          int num_poly_points, int xifirst, int xilast, const float* __restrict__ taps, int taps_length)
+{
+    __shared__ FdSeg sseg[FD_MAX_SEGS];
+    const int c = blockIdx.y;
+    const int ns = nsegs[c];
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) sseg[i] = segs[(long)c * FD_MAX_SEGS + i];
+    __syncthreads();
+    const int produced = state[c].output_size;
+    const float* x = in + (long)c * in_stride;
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < produced; o += gridDim.x * blockDim.x) {
+        int si = 0;
+        while (si + 1 < ns && sseg[si + 1].k0 <= o) si++;
+        const FdSeg sg = sseg[si];
+        float where;
+        if (sg.E == -1000) where = __uint_as_float(sg.M);
+        else where = __uint_as_float(((unsigned)(sg.E + 127) << 23) | ((sg.M + (unsigned)(o - sg.k0) * sg.q) & 0x7fffffu));
+        const int low = (int)ceilf(where) - 1;
+        const float xw = __fsub_rn(where, (float)low);
+        float acc = 0.f;
+        int slot = 0;
+        for (int xi = xifirst; xi <= xilast; xi++, slot++) {
+            float coef = 1.f, den = 1.f;
+            for (int xj = xifirst; xj <= xilast; xj++)
+                if (xi != xj) { coef = __fmul_rn(coef, __fsub_rn(xw, (float)xj)); den = __fmul_rn(den, (float)(xi - xj)); }
+            float pt;
+            if (taps) {
+                pt = 0.f;
+                const float* seg = x + low + slot;
+                for (int t = 0; t < taps_length; t++) pt = __fadd_rn(pt, __fmul_rn(seg[t], taps[t]));
+            } else pt = x[low + slot];
+            acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(coef, den), pt));
+        }
+        out[(long)c * out_stride + o] = acc;
+    }
+}
 
 __global__ void __launch_bounds__(128)
 fracdec_interp_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride,
                       const FracDecState* __restrict__ state, const int* __restrict__ idx_high, const float* __restrict__ xwhere,
                       int cap, int num_poly_points, int xifirst, int xilast, const float* __restrict__ taps, int taps_length)
 {
+    // fallback for blocks of 2^22 samples and more: positions were replayed sequentially by fracdec_positions_kernel
     const int c = blockIdx.y;
     const int produced = state[c].output_size;
     const float* x = in + (long)c * in_stride;
@@ -72,7 +175,9 @@ fracdec_interp_kernel(const float* __restrict__ in, long in_stride, float* __res
 size_t fracdec_scratch_bytes(int channels, int n, float rate)
 {
     const int cap = (int)((double)n / (rate > 1.f ? rate : 1.0)) + 8;
-    return (size_t)channels * cap * (sizeof(int) + sizeof(float));
+    const size_t seq = (size_t)channels * cap * (sizeof(int) + sizeof(float));             // sequential fallback (n >= 2^22)
+    const size_t par = (size_t)channels * (FD_MAX_SEGS * sizeof(FdSeg) + sizeof(int)) + 64;
+    return seq > par ? seq : par;
 }
 
 int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
@@ -89,6 +194,18 @@ int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d
     int* idx = static_cast<int*>(d_scratch);
     float* xw = reinterpret_cast<float*>(idx + (size_t)channels * cap);
     if (!d_taps) taps_length = 0;
+    if (n < (1 << 22)) {                                                 // closed-form positions: fully parallel
+        FdSeg* segs = static_cast<FdSeg*>(d_scratch);
+        int* nsegs = reinterpret_cast<int*>(segs + (size_t)channels * FD_MAX_SEGS);
+        fracdec_segments_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<FracDecState*>(d_state), segs, nsegs, channels, n, rate, num_poly_points,
+                                                                     xifirst, taps_length, cap);
+        CSDRB_CUDA(cudaGetLastError());
+        int gx2 = (cap + 127) / 128; if (gx2 > 2048) gx2 = 2048;
+        fracdec_interp_seg_kernel<<<dim3(gx2, channels), 128, 0, st>>>(d_in, in_stride, d_out, out_stride, static_cast<const FracDecState*>(d_state), segs, nsegs,
+                                                                       num_poly_points, xifirst, xilast, d_taps, taps_length);
+        CSDRB_CUDA(cudaGetLastError());
+        return 2;
+    }
     fracdec_positions_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<FracDecState*>(d_state), idx, xw, channels, n, rate, num_poly_points,
                                                                   xifirst, taps_length, cap);
     CSDRB_CUDA(cudaGetLastError());

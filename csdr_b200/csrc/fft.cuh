@@ -19,11 +19,12 @@
 
 namespace csdrb {
 
-// Shared-memory layout: element i lives at i + (i >> 3) (one pad slot per eight complex values, 12.5 % extra).
-// The first radix-8 pass writes 8 consecutive elements per thread (lane stride 8): unpadded that is a 16-way bank conflict on
-// 64-bit stores; with the skew the lane stride becomes 9 (odd) and the pass is conflict-free, as are the stride-64/512 passes.
-__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
-__host__ __device__ constexpr int fft_smem_elems(int n) { return n + (n >> 3) + 1; }
+// Shared-memory layout: element i lives at i + 2*(i >> 4) (two pad slots per sixteen complex values, 12.5 % extra; even indices stay
+// even so element pairs are 16-byte aligned).  A thread owns PAIRS of adjacent butterflies and moves them with 128-bit LDS/STS:
+// in the first pass it writes 16 consecutive elements (lane stride 18 elements = 9 x 16 B, odd: conflict-free), in the later passes
+// the pair lands at adjacent positions again (sub-transform sizes are even).
+__host__ __device__ constexpr int fft_pad(int i) { return i + 2 * (i >> 4); }
+__host__ __device__ constexpr int fft_smem_elems(int n) { return n + 2 * (n >> 4) + 2; }
 
 template <bool INV>
 __device__ __forceinline__ float2 cmul_w(float2 a, float2 w)
@@ -75,45 +76,85 @@ __device__ __forceinline__ void dft_small(float2 (&v)[R])
     else dft8<INV>(v);
 }
 
+template <int N, int R, int NS, bool INV>
+__device__ __forceinline__ void fft_butterfly(float2 (&v)[R], int j, const float2* __restrict__ tw)
+{
+    if constexpr (NS > 1) {
+        static_assert(R == 8, "only the first pass may have a radix below 8");
+        const int k = j % NS;
+        const float2 w1 = __ldg(tw + NS + k), w2 = __ldg(tw + N + NS + k), w4 = __ldg(tw + 2 * N + NS + k);
+        const float2 w3 = make_float2(fmaf(w1.x, w2.x, -w1.y * w2.y), fmaf(w1.x, w2.y, w1.y * w2.x));
+        const float2 w5 = make_float2(fmaf(w1.x, w4.x, -w1.y * w4.y), fmaf(w1.x, w4.y, w1.y * w4.x));
+        const float2 w6 = make_float2(fmaf(w2.x, w4.x, -w2.y * w4.y), fmaf(w2.x, w4.y, w2.y * w4.x));
+        const float2 w7 = make_float2(fmaf(w3.x, w4.x, -w3.y * w4.y), fmaf(w3.x, w4.y, w3.y * w4.x));
+        v[1] = cmul_w<INV>(v[1], w1); v[2] = cmul_w<INV>(v[2], w2); v[3] = cmul_w<INV>(v[3], w3);
+        v[4] = cmul_w<INV>(v[4], w4); v[5] = cmul_w<INV>(v[5], w5); v[6] = cmul_w<INV>(v[6], w6);
+        v[7] = cmul_w<INV>(v[7], w7);
+    }
+    dft_small<R, INV>(v);
+}
+
 template <int N, int NT, int R, int NS, bool INV>
 __device__ __forceinline__ void fft_pass(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
 {
     constexpr int NB = N / R;
     constexpr int PER = (NB + NT - 1) / NT;
     static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    constexpr bool PAIRED = (PER % 2 == 0) && (NB % (NT * PER) == 0);   // every thread owns whole pairs of adjacent butterflies
     float2 v[PER][R];
+    if constexpr (PAIRED) {
 #pragma unroll
-    for (int b = 0; b < PER; b++) {
-        const int j = tid + b * NT;
-        if (NB % NT == 0 || j < NB) {
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;                                // j even: (j, j+1) adjacent and 16-byte aligned in the padded array
 #pragma unroll
-            for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
-            if constexpr (NS > 1) {
-                static_assert(R == 8, "only the first pass may have a radix below 8");
-                const int k = j % NS;
-                const float2 w1 = __ldg(tw + NS + k), w2 = __ldg(tw + N + NS + k), w4 = __ldg(tw + 2 * N + NS + k);
-                const float2 w3 = make_float2(fmaf(w1.x, w2.x, -w1.y * w2.y), fmaf(w1.x, w2.y, w1.y * w2.x));
-                const float2 w5 = make_float2(fmaf(w1.x, w4.x, -w1.y * w4.y), fmaf(w1.x, w4.y, w1.y * w4.x));
-                const float2 w6 = make_float2(fmaf(w2.x, w4.x, -w2.y * w4.y), fmaf(w2.x, w4.y, w2.y * w4.x));
-                const float2 w7 = make_float2(fmaf(w3.x, w4.x, -w3.y * w4.y), fmaf(w3.x, w4.y, w3.y * w4.x));
-                v[b][1] = cmul_w<INV>(v[b][1], w1); v[b][2] = cmul_w<INV>(v[b][2], w2); v[b][3] = cmul_w<INV>(v[b][3], w3);
-                v[b][4] = cmul_w<INV>(v[b][4], w4); v[b][5] = cmul_w<INV>(v[b][5], w5); v[b][6] = cmul_w<INV>(v[b][6], w6);
-                v[b][7] = cmul_w<INV>(v[b][7], w7);
+            for (int r = 0; r < R; r++) {
+                const float4 two = *reinterpret_cast<const float4*>(s + fft_pad(j + r * NB));
+                v[b][r] = make_float2(two.x, two.y); v[b + 1][r] = make_float2(two.z, two.w);
             }
-            dft_small<R, INV>(v[b]);
+            fft_butterfly<N, R, NS, INV>(v[b], j, tw);
+            fft_butterfly<N, R, NS, INV>(v[b + 1], j + 1, tw);
         }
-    }
-    __syncthreads();
+        __syncthreads();
 #pragma unroll
-    for (int b = 0; b < PER; b++) {
-        const int j = tid + b * NT;
-        if (NB % NT == 0 || j < NB) {
-            const int j0 = (j / NS) * NS * R + (j % NS);
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+            if constexpr (NS == 1) {
+                // first pass: the two butterflies write 2R consecutive elements
 #pragma unroll
-            for (int r = 0; r < R; r++) s[fft_pad(j0 + r * NS)] = v[b][r];
+                for (int r = 0; r < R; r += 2) {
+                    *reinterpret_cast<float4*>(s + fft_pad(j * R + r)) = make_float4(v[b][r].x, v[b][r].y, v[b][r + 1].x, v[b][r + 1].y);
+                    *reinterpret_cast<float4*>(s + fft_pad((j + 1) * R + r)) = make_float4(v[b + 1][r].x, v[b + 1][r].y, v[b + 1][r + 1].x, v[b + 1][r + 1].y);
+                }
+            } else {
+                const int j0 = (j / NS) * NS * R + (j % NS);            // NS even: j and j+1 share the group, their outputs are adjacent
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    *reinterpret_cast<float4*>(s + fft_pad(j0 + r * NS)) = make_float4(v[b][r].x, v[b][r].y, v[b + 1][r].x, v[b + 1][r].y);
+            }
         }
+        __syncthreads();
+    } else {
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
+                fft_butterfly<N, R, NS, INV>(v[b], j, tw);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+                const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+                for (int r = 0; r < R; r++) s[fft_pad(j0 + r * NS)] = v[b][r];
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 template <int N, int NT, int NS, bool INV>
