@@ -306,15 +306,25 @@ __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int
     int remain = remain_io[c], off = 0;
     float ph = phase_io[c];
     const float rate = chan[c].rate;
+    // when post_decimation divides post_input_size (every fastddc geometry with an even scrap, e.g. 448/2) and the carried
+    // remainder is in range, both the per-block output count and the remainder are constants: no integer division in the loop
+    const bool steady = (post_input_size % post_decimation == 0) && remain >= 0 && remain < post_decimation;
+    const int k_const = post_input_size / post_decimation;
+    const float adv_const = __fmul_rn(__fmul_rn(rate, PI_F), (float)k_const);
     for (int b = 0; b < nblocks; b++) {
-        blk_remain[(long)c * nblocks + b] = remain;
-        blk_phase[(long)c * nblocks + b] = ph;
-        blk_offset[(long)c * nblocks + b] = off;
-        int k = 0, pos = remain;
-        if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
-        remain = pos - post_input_size;
-        ph = ddc_wrap(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate, PI_F), (float)k)));
-        off += k;
+        blk_remain[(long)b * channels + c] = remain;                    // [block][channel]: consecutive lanes store consecutive words
+        blk_phase[(long)b * channels + c] = ph;
+        blk_offset[(long)b * channels + c] = off;
+        if (steady) {
+            ph = ddc_wrap(__fadd_rn(ph, adv_const));
+            off += k_const;
+        } else {
+            int k = 0, pos = remain;
+            if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
+            remain = pos - post_input_size;
+            ph = ddc_wrap(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate, PI_F), (float)k)));
+            off += k;
+        }
     }
     remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off;
 }
@@ -356,7 +366,7 @@ fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const fl
     // normalise, drop the scrap, post shift + decimate (sequential phasor chain: one thread)
     if (tid == 0) {
         const float inv_m = 1.0f / (float)M;
-        const long bi = (long)c * nblocks + b;
+        const long bi = (long)b * gridDim.y + c;
         const double ph = (double)blk_phase[bi];
         float co = (float)cos(ph), si = (float)sin(ph);
         float2* y = out + (long)c * out_stride + blk_offset[bi];
@@ -405,7 +415,8 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
         for (int u = 0; u < CT; u++)
 #pragma unroll
             for (int v = 0; v < BT; v++) acc[u][v] = make_float2(0.f, 0.f);
-        for (int i = r; i < N; i += M) {
+#pragma unroll 4
+        for (int i = r; i < N; i += M) {                                // unrolled so the loads of later bins overlap the arithmetic of earlier ones
             const int xi = i < half ? i + half : i - half;
             float2 x[BT], h[CT];
 #pragma unroll
@@ -439,7 +450,7 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
             const DdcChan cp = chan[c0 + u];
             const float2* src = s + tid * ELEMS;
             const float inv_m = 1.0f / (float)M;
-            const long bi = (long)(c0 + u) * nblocks + (b0 + v);
+            const long bi = (long)(b0 + v) * channels + (c0 + u);
             const double ph = (double)blk_phase[bi];
             float co = (float)cos(ph), si = (float)sin(ph);
             float2* y = out + (long)(c0 + u) * out_stride + blk_offset[bi];
