@@ -13,6 +13,11 @@
 // A warp owns a time segment of SEG outputs (plus M-1 trailing periods to finish its last outputs); segments are independent
 // because the phasor of any sample depends only on its chunk's seed and its position inside the chunk.
 //
+// The float phase chain is a separate one-thread-per-channel pre-pass.  Folding it into this kernel as a ticketed producer CTA was
+// tried and measured SLOWER (2.27 ms vs 2.06 ms at 2 M samples x 128 ch): the whole grid is resident at once, so every segment needs
+// its chunk phase at t = 0 and nothing overlaps, while the producer runs ~3x slower on a shared SM.  The remaining lever is to run the
+// pre-pass of block k+1 on a side stream during the main kernel of block k (it only depends on the previous pre-pass).
+//
 // Bound: FP32 issue: ~ (10 + 4*M) FMA-lane slots per (sample, channel).
 #include "common.cuh"
 #include "kernels.h"
@@ -33,79 +38,52 @@ __device__ __forceinline__ float quadri_d(float2 cur, float2 prev)
     return den != 0.f ? (float)(FMDEMOD_K_D * (double)num / (double)den) : 0.f;
 }
 
+// seeds: (cos, sin) of every chunk's starting phase, evaluated in double like the reference does at each call
+__global__ void ddc_seed_kernel(const float* __restrict__ chunk_phase, float2* __restrict__ seeds, long total)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double ph = (double)chunk_phase[i];
+    seeds[i] = make_float2((float)cos(ph), (float)sin(ph));
+}
+
+// phase chain over ABSOLUTE chunks: the block starts `offset` samples into chunk 0; phase_io holds the phase at the start of
+// chunk 0 on entry and, on return, the phase at the start of the chunk that contains sample `advance` (the next block's start).
+__global__ void ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                                       int channels, int nchunks, int chunk, int next_chunk)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const float rate2 = params[c].z;
+    float ph = phase_io[c], keep = ph;
+    for (int k = 0; k < nchunks; k++) {
+        chunk_phase[(long)c * nchunks + k] = ph;
+        if (k == next_chunk) keep = ph;
+        ph = wrap_phase_pm_pi(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate2, 3.14159265358979323846f), (float)chunk)));
+    }
+    if (next_chunk >= nchunks) {                       // the next block starts beyond the chunks this block touched
+        for (int k = nchunks; k < next_chunk; k++) ph = wrap_phase_pm_pi(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate2, 3.14159265358979323846f), (float)chunk)));
+        keep = ph;
+    }
+    phase_io[c] = keep;
+}
+
 // CPL = channels per lane.  A tap pair is loaded once per warp and sample phase (LDCU.128 fetches two of them: taps are stored
 // [p][j] so the M taps that one sample meets are contiguous); with CPL = 2 every loaded tap feeds two FFMA2 and every wideband
 // sample load feeds two channels, which halves the non-FMA issue slots per channel-sample (ncu r01: 868 LDCU per 850 FFMA2 at CPL = 1).
-// Pipelined roles inside ONE launch (r01: the serial phase-chain pre-pass cost as much as the main kernel at multi-M-sample blocks):
-// every CTA draws a ticket; the first `groups` tickets become PRODUCERS (one per 128-channel group: a thread per channel walks the
-// float phase chain chunk by chunk and publishes chunk_phase[c][k] + a per-chunk flag), every later ticket is a CONSUMER that maps
-// to (segment, group) in time order and only waits when it reaches a chunk whose phase is not published yet.  Tickets are handed
-// out in the order CTAs start running, so a producer is always resident before any consumer of its group can wait on it.
-struct DdcSync { unsigned ticket; unsigned pad[3]; };
-
-__device__ __forceinline__ void ddc_wait_flag(const volatile unsigned* flag)
-{
-    while (*flag == 0u) __nanosleep(64);
-    __threadfence();
-}
-
 template <int D, int M, int CPL, bool DEMOD>
 __global__ void __launch_bounds__(128)
 ddc_bank_fused_kernel(const float2* __restrict__ wide, int n_in, int offset, int chunk, int nchunks,
-                      const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                      unsigned* __restrict__ flags, DdcSync* __restrict__ sync, int next_chunk, int groups, int channels,
+                      const float3* __restrict__ params, const float2* __restrict__ seeds, int channels,
                       void* __restrict__ out_v, long out_stride, int n_out, int seg_outputs,
                       const float2* __restrict__ last_in, float2* __restrict__ last_out,
                       const __grid_constant__ DdcTaps<D * ((M + 1) & ~1)> taps)
 {
     constexpr int MP = (M + 1) & ~1;
-    constexpr int CH_PER_GROUP = 128 * CPL;
-    __shared__ unsigned s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&sync->ticket, 1u);
-    __syncthreads();
-    const unsigned ticket = s_ticket;
-    if (ticket < (unsigned)groups) {
-        // ---------------- producer: the float phase chain of this group's channels, published chunk by chunk ----------------
-        const int g = (int)ticket;
-        float ph[CPL], keep[CPL], rate2[CPL]; int chn[CPL];
-#pragma unroll
-        for (int u = 0; u < CPL; u++) {
-            chn[u] = g * CH_PER_GROUP + u * 128 + threadIdx.x;
-            const bool ok = chn[u] < channels;
-            ph[u] = ok ? phase_io[chn[u]] : 0.f; keep[u] = ph[u]; rate2[u] = ok ? params[chn[u]].z : 0.f;
-        }
-        for (int k = 0; k < nchunks; k++) {
-#pragma unroll
-            for (int u = 0; u < CPL; u++) {
-                if (chn[u] < channels) chunk_phase[(long)chn[u] * nchunks + k] = ph[u];
-                if (k == next_chunk) keep[u] = ph[u];
-                ph[u] = wrap_phase_pm_pi(__fadd_rn(ph[u], __fmul_rn(__fmul_rn(rate2[u], 3.14159265358979323846f), (float)chunk)));
-            }
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned*>(flags + (long)g * nchunks + k) = 1u; }
-        }
-        if (next_chunk >= nchunks) {
-            for (int k = nchunks; k <= next_chunk; k++) {
-#pragma unroll
-                for (int u = 0; u < CPL; u++) {
-                    if (k == next_chunk) keep[u] = ph[u];
-                    ph[u] = wrap_phase_pm_pi(__fadd_rn(ph[u], __fmul_rn(__fmul_rn(rate2[u], 3.14159265358979323846f), (float)chunk)));
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < CPL; u++) if (chn[u] < channels) phase_io[chn[u]] = keep[u];
-        return;
-    }
-    // ---------------- consumer ----------------
-    const unsigned work = ticket - (unsigned)groups;
-    const int seg_idx = (int)(work / (unsigned)groups), grp = (int)(work % (unsigned)groups);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ch0 = grp * CH_PER_GROUP + warp * (32 * CPL) + lane;      // this lane's channels: ch0 + 32*u
+    const int ch0 = (blockIdx.y * 4 + warp) * (32 * CPL) + lane;        // this lane's channels: ch0 + 32*u
     if (ch0 - lane >= channels) return;                                 // whole warp beyond the bank
-    const volatile unsigned* gflags = flags + (long)grp * nchunks;
-    const int o_first = seg_idx * seg_outputs;                          // first output this warp emits
+    const int o_first = blockIdx.x * seg_outputs;                       // first output this warp emits
     if (o_first >= n_out) return;
     const int o_end = min(n_out, o_first + seg_outputs);
     // an output's window starts at its own first sample, so the walk can begin right at o_first (outputs before it are the
@@ -127,12 +105,8 @@ ddc_bank_fused_kernel(const float2* __restrict__ wide, int n_in, int offset, int
 #pragma unroll
         for (int j = 0; j < M; j++) acc[u][j] = make_float2(0.f, 0.f);
         prev[u] = (DEMOD && last_in) ? last_in[chs[u]] : make_float2(0.f, 0.f);
-    }
-    ddc_wait_flag(gflags + kchunk);
-#pragma unroll
-    for (int u = 0; u < CPL; u++) {                                     // seed = cos/sin of the float phase, evaluated in double like the reference
-        const double ph = (double)__ldcg(chunk_phase + (long)chs[u] * nchunks + kchunk);
-        c[u] = (float)cos(ph); s[u] = (float)sin(ph);
+        const float2 cs = seeds[(long)chs[u] * nchunks + kchunk];
+        c[u] = cs.x; s[u] = cs.y;
     }
     for (int t = 0; t < into; t++) {                                    // replay the recursion up to the segment start (< chunk steps, no data)
 #pragma unroll
@@ -163,12 +137,8 @@ ddc_bank_fused_kernel(const float2* __restrict__ wide, int n_in, int offset, int
                 const float xi = e ? xx.z : xx.x, xq = e ? xx.w : xx.y;
                 if (left == 0) {                                        // chunk boundary: re-seed the phasors (warp-uniform branch)
                     if (kchunk < nchunks - 1) kchunk++;                 // (beyond the block the data are zeros; any phasor will do)
-                    ddc_wait_flag(gflags + kchunk);
 #pragma unroll
-                    for (int u = 0; u < CPL; u++) {
-                        const double ph = (double)__ldcg(chunk_phase + (long)chs[u] * nchunks + kchunk);
-                        c[u] = (float)cos(ph); s[u] = (float)sin(ph);
-                    }
+                    for (int u = 0; u < CPL; u++) { const float2 cs = seeds[(long)chs[u] * nchunks + kchunk]; c[u] = cs.x; s[u] = cs.y; }
                     left = chunk;
                 }
                 left--;
@@ -216,14 +186,12 @@ size_t ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offse
 {
     if (chunk <= 0) chunk = input_size > 0 ? input_size : 1;
     const long nchunks = ((long)offset + input_size + chunk - 1) / chunk + 1;
-    const long groups = (channels + 127) / 128;
-    return 64 + (size_t)groups * (size_t)nchunks * sizeof(unsigned) + (size_t)channels * (size_t)nchunks * sizeof(float) + 64;
+    return (size_t)channels * (size_t)nchunks * (sizeof(float) + sizeof(float2)) + 64;
 }
 
 template <int D, int M>
-static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int nchunks, const float3* params, float* phase_io, void* scratch,
-                        int next_chunk, int channels, int demod, void* out, long out_stride, int n_out, const float2* last_in, float2* last_out,
-                        const float* h_taps, int T, cudaStream_t st)
+static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int nchunks, const float3* params, const float2* seeds, int channels,
+                        int demod, void* out, long out_stride, int n_out, const float2* last_in, float2* last_out, const float* h_taps, int T, cudaStream_t st)
 {
     constexpr int MP = (M + 1) & ~1;
     DdcTaps<D * MP> tp;                                                 // tap k = jD + p stored at [p][j], duplicated for FFMA2
@@ -237,21 +205,14 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
     static const int cpl_env = getenv("CSDRB_DDC_CPL") ? atoi(getenv("CSDRB_DDC_CPL")) : 1;
     static const int wps_env = getenv("CSDRB_DDC_WPS") ? atoi(getenv("CSDRB_DDC_WPS")) : 24;
     const int cpl = cpl_env == 2 ? 2 : 1;
-    const int groups = (channels + 128 * cpl - 1) / (128 * cpl);
     const int warps_per_seg = (channels + 32 * cpl - 1) / (32 * cpl);
+    const int groups = (warps_per_seg + 3) / 4;
     // enough warps to fill the machine while keeping the M-1 trailing periods of every segment a small fraction
     long want_segments = (148L * wps_env + warps_per_seg - 1) / warps_per_seg;
     int seg = (int)((n_out + want_segments - 1) / want_segments);
     if (seg < 2 * M) seg = 2 * M;
-    const int nseg = (n_out + seg - 1) / seg;
-    // scratch: [sync 64 B][flags groups*nchunks][chunk_phase channels*nchunks]; sync + flags are zeroed every call
-    DdcSync* sync = static_cast<DdcSync*>(scratch);
-    unsigned* flags = reinterpret_cast<unsigned*>(static_cast<char*>(scratch) + 64);
-    float* chunk_phase = reinterpret_cast<float*>(flags + (size_t)groups * nchunks);
-    CSDRB_CUDA(cudaMemsetAsync(scratch, 0, 64 + (size_t)groups * nchunks * sizeof(unsigned), st));
-    const dim3 grid((unsigned)(nseg * groups + groups));
-#define CSDRB_DDC_LAUNCH(CPLV, DM) ddc_bank_fused_kernel<D, M, CPLV, DM><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, phase_io, chunk_phase, \
-        flags, sync, next_chunk, groups, channels, out, out_stride, n_out, seg, last_in, last_out, tp)
+    dim3 grid((n_out + seg - 1) / seg, groups);
+#define CSDRB_DDC_LAUNCH(CPLV, DM) ddc_bank_fused_kernel<D, M, CPLV, DM><<<grid, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, out, out_stride, n_out, seg, last_in, last_out, tp)
     if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH(2, true); else CSDRB_DDC_LAUNCH(2, false); }
     else { if (demod) CSDRB_DDC_LAUNCH(1, true); else CSDRB_DDC_LAUNCH(1, false); }
 #undef CSDRB_DDC_LAUNCH
@@ -272,18 +233,24 @@ int launch_ddc_bank(const float2* d_wide, int input_size, int channels, const fl
     if (offset < 0 || offset >= chunk) { set_error("ddc bank: offset must be in [0, chunk)"); return -1; }
     if (reinterpret_cast<uintptr_t>(d_wide) & 15) { set_error("ddc bank: wideband input must be 16-byte aligned"); return -1; }
     if (scratch_bytes < ddc_bank_scratch_bytes(channels, input_size, chunk, offset) || !d_scratch) { set_error("ddc bank: scratch too small"); return -1; }
-    if (reinterpret_cast<uintptr_t>(d_scratch) & 15) { set_error("ddc bank: scratch must be 16-byte aligned"); return -1; }
     const int nchunks = (int)(((long)offset + input_size + chunk - 1) / chunk) + 1;
+    float* chunk_phase = static_cast<float*>(d_scratch);
+    float2* seeds = reinterpret_cast<float2*>(static_cast<char*>(d_scratch) + (((size_t)channels * nchunks * sizeof(float) + 15) & ~(size_t)15));
     const long advance = (long)n_out * decimation;                      // the next block starts here (the caller re-presents the tail)
     const int next_chunk = (int)((offset + advance) / chunk);
+    ddc_phase_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk);
+    CSDRB_CUDA(cudaGetLastError());
+    const long total = (long)channels * nchunks;
+    ddc_seed_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(chunk_phase, seeds, total);
+    CSDRB_CUDA(cudaGetLastError());
     int rc = -1;
     const float3* P = reinterpret_cast<const float3*>(d_params);
-    if (decimation == 50 && taps_length <= 50 * 17) rc = launch_fused<50, 17>(d_wide, input_size, offset, chunk, nchunks, P, d_phase_io, d_scratch, next_chunk, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
-    else if (decimation == 10 && taps_length <= 10 * 8) rc = launch_fused<10, 8>(d_wide, input_size, offset, chunk, nchunks, P, d_phase_io, d_scratch, next_chunk, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
-    else if (decimation == 10 && taps_length <= 10 * 20) rc = launch_fused<10, 20>(d_wide, input_size, offset, chunk, nchunks, P, d_phase_io, d_scratch, next_chunk, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
+    if (decimation == 50 && taps_length <= 50 * 17) rc = launch_fused<50, 17>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
+    else if (decimation == 10 && taps_length <= 10 * 8) rc = launch_fused<10, 8>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
+    else if (decimation == 10 && taps_length <= 10 * 20) rc = launch_fused<10, 20>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
     else { set_error("ddc bank: no fused kernel for decimation %d / %d taps (compiled: d=50 T<=850, d=10 T<=200); run the unfused bank calls", decimation, taps_length); return -2; }
     if (rc < 0) return rc;
-    *launches = 1;
+    *launches = 3;
     return n_out;
 }
 
