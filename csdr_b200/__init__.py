@@ -96,6 +96,11 @@ def lib() -> C.CDLL:
     L.csdrb_bandpass_fir_fft_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, it, vp, lg, vp, vp]
     L.csdrb_ddc_bank_scratch_bytes.argtypes = [it, it, it, it]; L.csdrb_ddc_bank_scratch_bytes.restype = sz
     L.csdrb_ddc_bank.argtypes = [vp, it, it, vp, vp, it, it, it, C.POINTER(C.c_float), it, it, vp, lg, vp, vp, vp, sz, vp]
+    L.csdrb_ddc_bank_create.argtypes = [it, C.POINTER(C.c_float), it, C.POINTER(C.c_float), it, it, it]; L.csdrb_ddc_bank_create.restype = vp
+    L.csdrb_ddc_bank_destroy.argtypes = [vp]
+    L.csdrb_ddc_bank_set_rate.argtypes = [vp, it, C.c_float]
+    L.csdrb_ddc_bank_offset.argtypes = [vp]
+    L.csdrb_ddc_bank_process.argtypes = [vp, vp, it, vp, lg, vp]
     L.csdrb_limit_ff.argtypes = [vp, vp, lg, C.c_float, vp]
     L.csdrb_deemphasis_wfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, vp]
     L.limit_ff.argtypes = [vp, vp, it, C.c_float]
@@ -650,3 +655,43 @@ def deemphasis_wfm_bank_ff(x, tau: float, sample_rate: int, last=None, out=None)
     _check(lib().csdrb_deemphasis_wfm_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, tau, sample_rate, last.data_ptr(), _stream()),
            "deemphasis_wfm_bank_ff")
     return out, last
+
+
+class DdcBank:
+    """Streaming shared-input DDC/NFM bank (csdrb_ddc_bank_*): shift | fir_decimate | [fmdemod] for C channels of one wideband stream,
+    one call per block, all per-channel state inside; the phase-chain pre-pass of the next block overlaps the current block."""
+
+    def __init__(self, rates, decimation: int, taps: np.ndarray, demod: bool = True, chunk: int = 1024):
+        self.rates = np.ascontiguousarray(np.atleast_1d(rates), np.float32)
+        self.taps = np.ascontiguousarray(taps, np.float32)
+        self.decimation, self.demod, self.channels = decimation, demod, self.rates.size
+        self.h = lib().csdrb_ddc_bank_create(self.channels, _fp(self.rates), decimation, _fp(self.taps), self.taps.size, 1 if demod else 0, chunk)
+        if not self.h:
+            raise CsdrB200Error(f"csdrb_ddc_bank_create: {lib().csdrb_last_error().decode()}")
+
+    def process(self, wide, out=None):
+        """wide: [N] complex64 CUDA tensor starting where the previous call stopped consuming (n_out*decimation samples in)."""
+        import torch
+        assert wide.dtype == torch.complex64 and wide.is_cuda and wide.dim() == 1
+        n_out = fir_out_len(wide.numel(), self.decimation, self.taps.size)
+        if out is None:
+            out = torch.empty((self.channels, n_out + (n_out & 1)), dtype=torch.float32 if self.demod else torch.complex64, device=wide.device)
+        rc = _check(lib().csdrb_ddc_bank_process(self.h, wide.data_ptr(), wide.numel(), out.data_ptr(), out.stride(0), _stream()), "ddc_bank_process")
+        return out[:, :rc]
+
+    def set_rate(self, channel: int, rate: float):
+        _check(lib().csdrb_ddc_bank_set_rate(self.h, channel, rate), "ddc_bank_set_rate")
+
+    @property
+    def offset(self) -> int:
+        return int(lib().csdrb_ddc_bank_offset(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().csdrb_ddc_bank_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

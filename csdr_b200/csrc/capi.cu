@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace csdrb {
 
@@ -402,6 +403,144 @@ int csdrb_ddc_bank(const complexf* d_wide, int input_size, int channels, const s
                              reinterpret_cast<float2*>(d_last_out), d_scratch, scratch_bytes, &launches, S(stream));
     if (rc >= 0) g_launches += launches;
     return rc;
+}
+
+// ---- streaming DDC/NFM bank object ---------------------------------------------------------------------
+// Owns every piece of per-channel state (NCO parameters, chunk-start phases, discriminator history, position inside the current
+// chunk) so that a stream is processed block by block with one call per block, and hides the serial float phase chain: while the
+// caller's stream runs the main kernel of block k, a private side stream already runs the pre-pass of block k+1 (it depends only on
+// the previous pre-pass).  Two scratch/phase buffers alternate; a retune or a block of a different size simply drops the look-ahead.
+struct csdrb_ddc_bank_s {
+    int channels = 0, decimation = 0, taps_length = 0, demod = 0, chunk = 0;
+    std::vector<float> taps;
+    std::vector<shift_addition_data_t> h_params;
+    float* d_params = nullptr;
+    float* d_phase[2] = {nullptr, nullptr};          // phase at the start of the chunk holding the next block's first sample (ping-pong)
+    float2* d_last[2] = {nullptr, nullptr};          // previous baseband sample per channel (ping-pong across blocks)
+    void* d_scratch[2] = {nullptr, nullptr};
+    size_t scratch_cap = 0;
+    int cur = 0;                                      // which phase/scratch buffer holds the state for the NEXT process() call
+    int last_sel = 0;
+    int offset = 0;                                   // position of the next block's first sample inside its chunk
+    bool ahead_valid = false; int ahead_input_size = 0; // a pre-pass for the next block (of this size) is already in flight/done
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_prepass = nullptr, ev_pre_inline = nullptr, ev_main[2] = {nullptr, nullptr};
+    long blocks = 0;
+    bool params_dirty = false;
+};
+
+csdrb_ddc_bank_t* csdrb_ddc_bank_create(int channels, const float* h_rates, int decimation, const float* h_taps, int taps_length, int demod, int chunk)
+{
+    if (channels <= 0 || !h_rates || !h_taps || decimation <= 0 || taps_length <= 0) { set_error("ddc bank create: bad argument"); return nullptr; }
+    auto* b = new csdrb_ddc_bank_s();
+    b->channels = channels; b->decimation = decimation; b->taps_length = taps_length; b->demod = demod ? 1 : 0; b->chunk = chunk > 0 ? chunk : 1024;
+    b->taps.assign(h_taps, h_taps + taps_length);
+    b->h_params.resize((size_t)channels);
+    for (int c = 0; c < channels; c++) b->h_params[(size_t)c] = shift_addition_init(h_rates[c]);
+    bool ok = cudaMalloc(&b->d_params, sizeof(shift_addition_data_t) * (size_t)channels) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; k++) {
+        ok = ok && cudaMalloc(&b->d_phase[k], sizeof(float) * (size_t)channels) == cudaSuccess;
+        ok = ok && cudaMalloc(&b->d_last[k], sizeof(float2) * (size_t)channels) == cudaSuccess;
+        if (ok) { cudaMemset(b->d_phase[k], 0, sizeof(float) * (size_t)channels); cudaMemset(b->d_last[k], 0, sizeof(float2) * (size_t)channels); }
+    }
+    ok = ok && cudaMemcpy(b->d_params, b->h_params.data(), sizeof(shift_addition_data_t) * (size_t)channels, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&b->ev_prepass, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&b->ev_pre_inline, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&b->ev_main[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { set_error("ddc bank create: CUDA allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); csdrb_ddc_bank_destroy(b); return nullptr; }
+    return b;
+}
+
+void csdrb_ddc_bank_destroy(csdrb_ddc_bank_t* b)
+{
+    if (!b) return;
+    if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
+    if (b->ev_prepass) cudaEventDestroy(b->ev_prepass);
+    if (b->ev_pre_inline) cudaEventDestroy(b->ev_pre_inline);
+    for (int k = 0; k < 2; k++) if (b->ev_main[k]) cudaEventDestroy(b->ev_main[k]);
+    cudaFree(b->d_params);
+    for (int k = 0; k < 2; k++) { cudaFree(b->d_phase[k]); cudaFree(b->d_last[k]); cudaFree(b->d_scratch[k]); }
+    delete b;
+}
+
+int csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t* b, int channel, float rate)
+{
+    if (!b || channel < 0 || channel >= b->channels) { set_error("ddc bank set_rate: bad channel"); return -1; }
+    b->h_params[(size_t)channel] = shift_addition_init(rate);
+    b->params_dirty = true;                           // uploaded, and the look-ahead dropped, at the next process()
+    return 0;
+}
+
+int csdrb_ddc_bank_offset(const csdrb_ddc_bank_t* b) { return b ? b->offset : -1; }
+
+int csdrb_ddc_bank_process(csdrb_ddc_bank_t* b, const complexf* d_wide, int input_size, void* d_out, long out_stride, void* stream)
+{
+    if (!b || !d_wide || !d_out) { set_error("ddc bank process: null pointer"); return -1; }
+    cudaStream_t st = S(stream);
+    const int n_out = input_size >= b->taps_length ? (input_size - b->taps_length) / b->decimation + 1 : 0;
+    if (n_out == 0) return 0;
+    const size_t need = csdrb_ddc_bank_scratch_bytes(b->channels, input_size, b->chunk, b->chunk - 1) + 64;
+    if (need > b->scratch_cap) {                      // grow both scratch buffers (drops any look-ahead)
+        CSDRB_CUDA(cudaStreamSynchronize(b->side));
+        CSDRB_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 2; k++) { if (b->d_scratch[k]) CSDRB_CUDA(cudaFree(b->d_scratch[k])); CSDRB_CUDA(cudaMalloc(&b->d_scratch[k], need)); }
+        b->scratch_cap = need; b->ahead_valid = false;
+    }
+    if (b->params_dirty) {                            // retune: the phases stay, the deltas change, a pre-pass made with the old ones is void
+        CSDRB_CUDA(cudaStreamSynchronize(b->side));
+        if (b->ahead_valid) {
+            // the look-ahead already advanced phase[cur^1] from phase[cur]; phase[cur] is still the state before it: just forget it
+            b->ahead_valid = false;
+        }
+        CSDRB_CUDA(cudaMemcpyAsync(b->d_params, b->h_params.data(), sizeof(shift_addition_data_t) * (size_t)b->channels, cudaMemcpyHostToDevice, st));
+        b->params_dirty = false;
+    }
+    int launches = 0;
+    int sel;                                          // scratch buffer holding this block's seeds
+    if (b->ahead_valid && b->ahead_input_size == input_size) {
+        sel = b->cur ^ 1;                             // the side stream produced seeds[sel] and advanced phase[sel] from phase[cur]
+        CSDRB_CUDA(cudaStreamWaitEvent(st, b->ev_prepass, 0));
+    } else {
+        if (b->ahead_valid) CSDRB_CUDA(cudaStreamSynchronize(b->side));   // a mismatching look-ahead: let it finish, then ignore it
+        sel = b->cur ^ 1;
+        // phase[sel] <- phase[cur], then run the pre-pass on the caller's stream (it advances phase[sel])
+        CSDRB_CUDA(cudaMemcpyAsync(b->d_phase[sel], b->d_phase[b->cur], sizeof(float) * (size_t)b->channels, cudaMemcpyDeviceToDevice, st));
+        int rc = launch_ddc_prepass(input_size, b->channels, b->d_params, b->d_phase[sel], b->chunk, b->offset, b->decimation, b->taps_length,
+                                    b->d_scratch[sel], b->scratch_cap, st);
+        if (rc < 0) return rc;
+        launches += rc;
+        CSDRB_CUDA(cudaEventRecord(b->ev_pre_inline, st));             // the look-ahead below starts from the phases this pre-pass produced
+        CSDRB_CUDA(cudaStreamWaitEvent(b->side, b->ev_pre_inline, 0));
+    }
+    b->ahead_valid = false;
+    // main kernel of this block: discriminator history ping-pongs last[last_sel] -> last[last_sel^1]
+    int rc = launch_ddc_main(reinterpret_cast<const float2*>(d_wide), input_size, b->channels, b->d_params, b->chunk, b->offset, b->decimation, b->taps.data(),
+                             b->taps_length, b->demod, d_out, out_stride, b->d_last[b->last_sel], b->d_last[b->last_sel ^ 1], b->d_scratch[sel], st);
+    if (rc < 0) return rc;
+    launches += 1;
+    b->last_sel ^= 1;
+    CSDRB_CUDA(cudaEventRecord(b->ev_main[b->blocks & 1], st));
+    // state for the next block now lives in phase[sel]; its first sample sits `offset` samples into that chunk
+    b->cur = sel;
+    b->offset = (int)(((long)b->offset + (long)n_out * b->decimation) % b->chunk);
+    // look-ahead: pre-pass of the next block (assumed to have the same size) on the side stream into the other buffer, CONCURRENT
+    // with the main kernel just launched.  It only has to wait for (a) this block's pre-pass (ordered above / same stream) and
+    // (b) the main kernel of the PREVIOUS block, the last reader of the scratch buffer it is about to overwrite.
+    {
+        const int nxt = b->cur ^ 1;
+        if (b->blocks > 0) CSDRB_CUDA(cudaStreamWaitEvent(b->side, b->ev_main[(b->blocks - 1) & 1], 0));
+        CSDRB_CUDA(cudaMemcpyAsync(b->d_phase[nxt], b->d_phase[b->cur], sizeof(float) * (size_t)b->channels, cudaMemcpyDeviceToDevice, b->side));
+        int rp = launch_ddc_prepass(input_size, b->channels, b->d_params, b->d_phase[nxt], b->chunk, b->offset, b->decimation, b->taps_length,
+                                    b->d_scratch[nxt], b->scratch_cap, b->side);
+        if (rp < 0) return rp;
+        launches += rp;
+        CSDRB_CUDA(cudaEventRecord(b->ev_prepass, b->side));
+        b->ahead_valid = true; b->ahead_input_size = input_size;
+    }
+    b->blocks++;
+    g_launches += launches;
+    return n_out;
 }
 
 // =====================================================================================================

@@ -220,18 +220,16 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
     return 0;
 }
 
-// returns outputs per channel; *launches receives the number of kernels launched
-int launch_ddc_bank(const float2* d_wide, int input_size, int channels, const float* d_params, float* d_phase_io, int chunk, int offset,
-                    int decimation, const float* h_taps, int taps_length, int demod, void* d_out, long out_stride,
-                    const float2* d_last_in, float2* d_last_out, void* d_scratch, size_t scratch_bytes, int* launches, cudaStream_t st)
+// ---- the two halves of a block, exposed separately so a bank object can run the pre-pass of the NEXT block on a side stream ----
+// pre-pass: float phase chain over the absolute chunks the block touches + the (cos, sin) seeds; advances d_phase_io to the chunk
+// that contains the next block's first sample.
+int launch_ddc_prepass(int input_size, int channels, const float* d_params, float* d_phase_io, int chunk, int offset, int decimation,
+                       int taps_length, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
 {
-    *launches = 0;
-    if (channels <= 0 || decimation <= 0 || taps_length <= 0) { set_error("ddc bank: bad geometry"); return -1; }
     const int n_out = input_size >= taps_length ? (input_size - taps_length) / decimation + 1 : 0;
     if (n_out == 0) return 0;
     if (chunk <= 0) chunk = input_size;
     if (offset < 0 || offset >= chunk) { set_error("ddc bank: offset must be in [0, chunk)"); return -1; }
-    if (reinterpret_cast<uintptr_t>(d_wide) & 15) { set_error("ddc bank: wideband input must be 16-byte aligned"); return -1; }
     if (scratch_bytes < ddc_bank_scratch_bytes(channels, input_size, chunk, offset) || !d_scratch) { set_error("ddc bank: scratch too small"); return -1; }
     const int nchunks = (int)(((long)offset + input_size + chunk - 1) / chunk) + 1;
     float* chunk_phase = static_cast<float*>(d_scratch);
@@ -243,15 +241,44 @@ int launch_ddc_bank(const float2* d_wide, int input_size, int channels, const fl
     const long total = (long)channels * nchunks;
     ddc_seed_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(chunk_phase, seeds, total);
     CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+// main kernel: needs the seeds a matching launch_ddc_prepass() left in d_scratch
+int launch_ddc_main(const float2* d_wide, int input_size, int channels, const float* d_params, int chunk, int offset, int decimation,
+                    const float* h_taps, int taps_length, int demod, void* d_out, long out_stride, const float2* d_last_in, float2* d_last_out,
+                    const void* d_scratch, cudaStream_t st)
+{
+    if (channels <= 0 || decimation <= 0 || taps_length <= 0) { set_error("ddc bank: bad geometry"); return -1; }
+    const int n_out = input_size >= taps_length ? (input_size - taps_length) / decimation + 1 : 0;
+    if (n_out == 0) return 0;
+    if (chunk <= 0) chunk = input_size;
+    if (reinterpret_cast<uintptr_t>(d_wide) & 15) { set_error("ddc bank: wideband input must be 16-byte aligned"); return -1; }
+    const int nchunks = (int)(((long)offset + input_size + chunk - 1) / chunk) + 1;
+    const float2* seeds = reinterpret_cast<const float2*>(static_cast<const char*>(d_scratch) + (((size_t)channels * nchunks * sizeof(float) + 15) & ~(size_t)15));
     int rc = -1;
     const float3* P = reinterpret_cast<const float3*>(d_params);
     if (decimation == 50 && taps_length <= 50 * 17) rc = launch_fused<50, 17>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
     else if (decimation == 10 && taps_length <= 10 * 8) rc = launch_fused<10, 8>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
     else if (decimation == 10 && taps_length <= 10 * 20) rc = launch_fused<10, 20>(d_wide, input_size, offset, chunk, nchunks, P, seeds, channels, demod, d_out, out_stride, n_out, d_last_in, d_last_out, h_taps, taps_length, st);
     else { set_error("ddc bank: no fused kernel for decimation %d / %d taps (compiled: d=50 T<=850, d=10 T<=200); run the unfused bank calls", decimation, taps_length); return -2; }
+    return rc < 0 ? rc : n_out;
+}
+
+// one-shot: pre-pass and main kernel back to back on the caller's stream
+int launch_ddc_bank(const float2* d_wide, int input_size, int channels, const float* d_params, float* d_phase_io, int chunk, int offset,
+                    int decimation, const float* h_taps, int taps_length, int demod, void* d_out, long out_stride,
+                    const float2* d_last_in, float2* d_last_out, void* d_scratch, size_t scratch_bytes, int* launches, cudaStream_t st)
+{
+    *launches = 0;
+    if (channels <= 0 || decimation <= 0 || taps_length <= 0) { set_error("ddc bank: bad geometry"); return -1; }
+    if (reinterpret_cast<uintptr_t>(d_wide) & 15) { set_error("ddc bank: wideband input must be 16-byte aligned"); return -1; }
+    int rc = launch_ddc_prepass(input_size, channels, d_params, d_phase_io, chunk, offset, decimation, taps_length, d_scratch, scratch_bytes, st);
+    if (rc <= 0) return rc;
+    rc = launch_ddc_main(d_wide, input_size, channels, d_params, chunk, offset, decimation, h_taps, taps_length, demod, d_out, out_stride, d_last_in, d_last_out, d_scratch, st);
     if (rc < 0) return rc;
     *launches = 3;
-    return n_out;
+    return rc;
 }
 
 }  // namespace csdrb

@@ -179,6 +179,18 @@ int csdrb_ddc_bank(const complexf *d_wide, int input_size, int channels, const s
                    int chunk, int offset, int decimation, const float *h_taps, int taps_length, int demod, void *d_out, long out_stride,
                    const complexf *d_last_in, complexf *d_last_out, void *d_scratch, size_t scratch_bytes, void *stream);
 
+/* Streaming bank object over the fused kernel: owns rates, chunk phases, discriminator history and the position inside the current
+ * NCO chunk, so a wideband stream is processed with one call per block; internally the serial phase-chain pre-pass of block k+1 runs on
+ * a private stream while the caller's stream executes block k.  Contract of process(): it consumes n_out*decimation samples (the return
+ * value is n_out); the next block must start there, i.e. the caller re-presents the unconsumed tail exactly like fir_decimate_cc's
+ * callers do (csdr.c:1172-1174).  d_out is float [channels][out_stride] when the bank was created with demod = 1, else complexf. */
+typedef struct csdrb_ddc_bank_s csdrb_ddc_bank_t;
+csdrb_ddc_bank_t *csdrb_ddc_bank_create(int channels, const float *h_rates, int decimation, const float *h_taps, int taps_length, int demod, int chunk);
+void csdrb_ddc_bank_destroy(csdrb_ddc_bank_t *bank);
+int  csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t *bank, int channel, float rate);     /* retune one channel; effective from the next block */
+int  csdrb_ddc_bank_offset(const csdrb_ddc_bank_t *bank);                          /* samples of the current NCO chunk already consumed */
+int  csdrb_ddc_bank_process(csdrb_ddc_bank_t *bank, const complexf *d_wide, int input_size, void *d_out, long out_stride, void *stream);
+
 /* audio tail banks: hard limiter (elementwise) and the 1-pole de-emphasis IIR (d_last_io[c] = previous output of channel c) */
 int csdrb_limit_ff(const float *d_in, float *d_out, long n, float max_amplitude, void *stream);
 int csdrb_deemphasis_wfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,

@@ -304,3 +304,30 @@ def test_audio_tail_limit_and_deemphasis(gpu, oracle):
     for c in range(37):
         want, wl = oracle.deemphasis_wfm_ff(xb[c], 75e-6, 240000, float(lasts[c]))
         assert np.array_equal(yb[c].cpu().numpy(), want) and np.float32(wl) == lb[c].item()
+
+
+def test_ddc_bank_object_streams_with_lookahead(gpu, oracle):
+    """csdrb_ddc_bank_*: many blocks with the tail re-presented, look-ahead pre-pass on the side stream, a block of a different size
+    in the middle (look-ahead dropped) -- always equal to one long reference stream per channel."""
+    D, T, chunk = 50, 801, 1024
+    taps = gpu.firdes_lowpass_f(T, 0.5 / D)
+    rng = np.random.default_rng(17)
+    N = 200_000
+    t = np.arange(N)
+    rates = np.array([0.123, -0.4, 0.31], np.float32)
+    wide = sum(0.3 * np.exp(1j * (2 * np.pi * (-float(r)) * t + np.cumsum(0.004 * np.sin(2 * np.pi * t / 5000.0)))) for r in rates)
+    wide = (wide + 0.005 * (rng.normal(size=N) + 1j * rng.normal(size=N))).astype(np.complex64)
+    dwide = _dev(wide)
+    bank = gpu.DdcBank(rates, D, taps, demod=True, chunk=chunk)
+    pos, outs, sizes = 0, [], [30_000, 30_000, 30_000, 17_001, 30_000, 30_000]
+    for sz in sizes:
+        assert bank.offset == pos % chunk
+        o = bank.process(dwide[pos:pos + sz])
+        outs.append(o.cpu().numpy().copy())
+        pos += o.shape[1] * D
+    got = np.concatenate(outs, 1)
+    for c, r in enumerate(rates):
+        sh, _ = oracle.shift_addition_cc(wide[:pos + T], float(r), 0.0, chunk)
+        want = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0]
+        assert _rel(got[c], want[:got.shape[1]]) < TOL, c
+    bank.close()

@@ -99,6 +99,10 @@ if "c4" in which:
     fo = torch.empty((C, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
     tfu = timed(lambda: cb.ddc_bank(x, rates, D, taps, demod=True, chunk=1024, out=fo), reps=5)
     report("cfg4 FUSED ddc_bank (shift|fir d=50 T=801|fmdemod) 128 ch", tfu, N, N * 18.24, f"{C * N * (10 + 4 * 17 * 1.0) / tfu / 1e9:.1f} TFLOP/s fp32 (10+4M flop per sample-channel)")
+    bank = cb.DdcBank(rates, D, taps, demod=True, chunk=1024)
+    tbk = timed(lambda: bank.process(x, out=fo), reps=8, warm=3)
+    report("cfg4 FUSED via bank object (pre-pass of block k+1 overlaps block k)", tbk, N, N * 18.24, f"{C * N * (10 + 4 * 17 * 1.0) / tbk / 1e9:.1f} TFLOP/s fp32")
+    bank.close()
     del shifted, base, audio
     torch.cuda.empty_cache()
 

@@ -18,14 +18,12 @@ T = cb.firdes_filter_len(BW); taps = cb.firdes_lowpass_f(T, 0.5 / D)
 shard = BankShard(C, world, rank)
 rates = np.linspace(-0.45, 0.45, C).astype(np.float32)[shard.start:shard.start + shard.count]
 n_out = cb.fir_out_len(N, D, T)
-state = {"phase": None, "last": None, "offset": 0}
 out = torch.empty((shard.count, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
+ddc = cb.DdcBank(rates, D, taps, demod=True, chunk=CHUNK)          # owns phases/history; pre-pass of block k+1 overlaps block k
 
 def compute(buf, sh):
-    o, ph, last = cb.ddc_bank(buf, rates, D, taps, demod=True, chunk=CHUNK, offset=state["offset"], phases=state["phase"], last=state["last"], out=out)
     # (a streaming caller would re-present the unconsumed tail; for the throughput measurement every block is processed whole)
-    state["phase"], state["last"] = ph, last
-    return o
+    return ddc.process(buf, out=out)
 
 bank = SharedInputBank(shard, lambda: torch.zeros(N, dtype=torch.complex64, device=dev), compute, src=0)
 g = torch.Generator(device=dev).manual_seed(1)
