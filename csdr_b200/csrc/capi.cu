@@ -115,7 +115,8 @@ int csdrb_fir_decimate_bank_cc(const complexf* d_in, long in_stride, complexf* d
     // the generic kernel reads taps from device memory: keep a small per-process copy
     static float* d_taps = nullptr; static int d_taps_cap = 0; static std::mutex mu;
     const float* dt = nullptr;
-    const bool fast = (decimation == 10 && taps_length <= 200 && (in_stride % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0));
+    const bool fast = ((decimation == 10 && taps_length <= 200) || (decimation == 50 && taps_length <= 900)) && (in_stride % 2 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
     if (!fast) {
         std::lock_guard<std::mutex> lk(mu);
         if (taps_length > d_taps_cap) {

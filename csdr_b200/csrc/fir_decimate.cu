@@ -163,12 +163,9 @@ static int launch_fast(const float2* in, long in_stride, float2* out, long out_s
                        int n_out, const float* h_taps, int T, cudaStream_t st)
 {
     using C = FirCfg<D, M, R, NPAIR>;
-    static bool configured = false;
     auto kern = fir_bank_fast_kernel<D, M, R, NPAIR, MINB>;
-    if (!configured) {
-        CSDRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        configured = true;
-    }
+    // per call, not cached: the attribute is per device and a process may switch devices (it costs ~1 us)
+    CSDRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     FirTaps<D * M> tp;
     for (int k = 0; k < D * M; k++) { float h = k < T ? h_taps[k] : 0.f; tp.hh[k] = make_float2(h, h); }
     dim3 grid((n_out + C::OUT_TILE - 1) / C::OUT_TILE, channels);
@@ -189,6 +186,11 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
     if (n_out == 0) return 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (in_stride % 2 == 0);
     const bool shared_taps = (taps_stride == 0) && h_taps != nullptr;
+    if (aligned && shared_taps && D == 10 && T <= 80 && variant < 0) {
+        // the CLI default (fir_decimate_cc 10 0.05 -> 79 taps): 8 sub-taps per phase instead of 20 zero-padded ones
+        const int rc = launch_fast<10, 8, 15, 2, 3>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st);
+        return rc < 0 ? rc : n_out;
+    }
     if (aligned && shared_taps && D == 10 && T <= 200) {
         int rc;
         switch (variant) {
@@ -199,6 +201,11 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
         }
         return rc < 0 ? rc : n_out;
     }
+    if (aligned && shared_taps && D == 50 && T <= 900) {
+        // fir_decimate_cc 50 0.005 (801 taps), independent inputs: 3 outputs per thread keep the tile (150 samples per thread) in shared memory
+        const int rc = launch_fast<50, 18, 3, 2, 2>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st);
+        return rc < 0 ? rc : n_out;
+    }
     // generic
     if (!d_taps) { set_error("fir_decimate bank: generic path needs device taps"); return -1; }
     size_t tap_bytes = ((size_t)T * 4 + 15) & ~(size_t)15;
@@ -206,11 +213,7 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
     if (out_tile < 1) { set_error("fir_decimate bank: taps_length %d too long for the generic kernel", T); return -1; }
     if (out_tile > 2048) out_tile = 2048;
     size_t smem = tap_bytes + ((size_t)(out_tile - 1) * D + T) * 8;
-    static bool configured = false;
-    if (!configured) {
-        CSDRB_CUDA(cudaFuncSetAttribute(fir_bank_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
-    }
+    CSDRB_CUDA(cudaFuncSetAttribute(fir_bank_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     dim3 grid((n_out + out_tile - 1) / out_tile, channels);
     fir_bank_generic_kernel<<<grid, 256, smem, st>>>(d_in, in_stride, d_out, out_stride, n_in, n_out, D, d_taps, taps_stride, T, out_tile);
     CSDRB_CUDA(cudaGetLastError());

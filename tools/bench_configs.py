@@ -93,7 +93,7 @@ if "c4" in which:
     t2 = timed(lambda: cb.fir_decimate_bank_cc(shifted, D, taps, out=base), reps=3)
     t3 = timed(lambda: cb.fmdemod_quadri_bank_cf(base[:, :n_out], out=audio), reps=3)
     report(f"cfg4 shift (shared in) 128 ch x {N}", t1, N, N * 8 + C * N * 8)
-    report(f"cfg4 fir_decimate d=50 T={T} 128 ch (generic kernel)", t2, N, C * N * 8.16, f"{C * n_out * T * 4 / t2 / 1e9:.1f} TFLOP/s")
+    report(f"cfg4 fir_decimate d=50 T={T} 128 ch (independent-input bank kernel)", t2, N, C * N * 8.16, f"{C * n_out * T * 4 / t2 / 1e9:.1f} TFLOP/s")
     report("cfg4 fmdemod 128 ch", t3, N, C * n_out * 12)
     report("cfg4 unfused chain, wideband Msps per GPU (18.24 B/sample algorithmic)", timed(chain, reps=3), N, N * 18.24)
     fo = torch.empty((C, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
@@ -120,4 +120,6 @@ if "c5" in which:
         torch.cuda.empty_cache()
 
 Path("gpurun_out").mkdir(exist_ok=True)
-Path("gpurun_out/configs.json").write_text(json.dumps(res, indent=1))
+prev = json.loads(Path("gpurun_out/configs.json").read_text()) if Path("gpurun_out/configs.json").exists() else {}
+prev.update(res)
+Path("gpurun_out/configs.json").write_text(json.dumps(prev, indent=1))
