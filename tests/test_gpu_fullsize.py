@@ -35,8 +35,8 @@ def test_config3_fastddc_64_channels(gpu, oracle):
     rng = np.random.default_rng(33)
     t = np.arange(n)
     x = np.zeros(n, np.complex128)
-    for k in (0, 17, 40, 63):                                          # tones inside four of the channels
-        x += 0.2 * np.exp(2j * np.pi * (shifts[k] + 0.002) * t)
+    for k in (0, 17, 40, 63):                                          # tones inside four of the channels (channel k passes the band around -shift_k)
+        x += 0.2 * np.exp(2j * np.pi * (-shifts[k] + 0.002) * t)
     x = (x + 0.05 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
     sp, _ = gpu.fastddc_fwd_cc(torch.from_numpy(x).cuda(), ddc)
     out, counts, _ = gpu.fastddc_inv_bank_cc(sp, shifts, dec, bw)
