@@ -44,6 +44,10 @@ class _FastAgc(C.Structure):            # fastagc_ff_t (= libcsdr.h:118-128)
                 ("peak_2", C.c_float), ("input_size", C.c_int), ("reference", C.c_float), ("last_gain", C.c_float)]
 
 
+class _Unroll(C.Structure):             # shift_unroll_data_t (= libcsdr.h:199-205)
+    _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
+
+
 class _Plan(C.Structure):               # struct fft_plan_s (= fft_fftw.h:14-20)
     _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
 
@@ -101,6 +105,19 @@ def lib() -> C.CDLL:
     L.csdrb_ddc_bank_set_rate.argtypes = [vp, it, C.c_float]
     L.csdrb_ddc_bank_offset.argtypes = [vp]
     L.csdrb_ddc_bank_process.argtypes = [vp, vp, it, vp, lg, vp]
+    L.csdrb_apply_window_rows_c.argtypes = [vp, vp, vp, it, lg, vp]
+    L.csdrb_logpower_cf.argtypes = [vp, vp, lg, C.c_float, vp]
+    L.csdrb_accumulate_power_cf.argtypes = [vp, vp, lg, vp]
+    L.csdrb_log_ff.argtypes = [vp, vp, lg, C.c_float, vp]
+    L.csdrb_shift_unroll_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp, lg, it, vp, vp, sz, vp]
+    L.precalculate_window.argtypes = [it, it]; L.precalculate_window.restype = C.POINTER(C.c_float)
+    L.apply_precalculated_window_c.argtypes = [vp, vp, it, vp]
+    L.apply_window_c.argtypes = [vp, vp, it, it]
+    L.logpower_cf.argtypes = [vp, vp, it, C.c_float]
+    L.accumulate_power_cf.argtypes = [vp, vp, it]
+    L.log_ff.argtypes = [vp, vp, it, C.c_float]
+    L.shift_unroll_init.argtypes = [C.c_float, it]; L.shift_unroll_init.restype = _Unroll
+    L.shift_unroll_cc.argtypes = [vp, vp, it, C.POINTER(_Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
     L.csdrb_limit_ff.argtypes = [vp, vp, lg, C.c_float, vp]
     L.csdrb_deemphasis_wfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, vp]
     L.limit_ff.argtypes = [vp, vp, it, C.c_float]
@@ -390,6 +407,41 @@ class libcsdr:
     def limit_ff(x, max_amplitude=1.0):
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
         lib().limit_ff(x.ctypes.data, y.ctypes.data, x.size, max_amplitude); return y
+
+    @staticmethod
+    def precalculate_window(size, window="HAMMING"):
+        p = lib().precalculate_window(size, WINDOWS[window]); return np.ctypeslib.as_array(p, shape=(size,)).copy()
+
+    @staticmethod
+    def apply_window_c(x, window="HAMMING"):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x)
+        lib().apply_window_c(x.ctypes.data, y.ctypes.data, x.size, WINDOWS[window]); return y
+
+    @staticmethod
+    def logpower_cf(x, add_db=0.0):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty(x.size, np.float32)
+        lib().logpower_cf(x.ctypes.data, y.ctypes.data, x.size, add_db); return y
+
+    @staticmethod
+    def logaveragepower_cf(x, add_db, fft_size, avgnumber):
+        x = np.ascontiguousarray(x, np.complex64); out = []
+        adj = np.float32(np.float32(add_db) - np.float32(10.0 * np.log10(avgnumber)))
+        for b in range(x.size // (fft_size * avgnumber)):
+            acc = np.zeros(fft_size, np.float32)
+            for n in range(avgnumber):
+                seg = x[(b * avgnumber + n) * fft_size:(b * avgnumber + n + 1) * fft_size]
+                lib().accumulate_power_cf(seg.ctypes.data, acc.ctypes.data, fft_size)
+            y = np.empty(fft_size, np.float32); lib().log_ff(acc.ctypes.data, y.ctypes.data, fft_size, float(adj)); out.append(y)
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    @staticmethod
+    def shift_unroll_cc(x, rate, phase=0.0, size=1024):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x)
+        d = lib().shift_unroll_init(rate, size)
+        for s0 in range(0, x.size, size):
+            n = min(size, x.size - s0)
+            phase = lib().shift_unroll_cc(x[s0:].ctypes.data, y[s0:].ctypes.data, n, C.byref(d), phase)
+        return y, float(np.float32(phase))
 
     @staticmethod
     def dft(x, forward=True):
@@ -695,3 +747,41 @@ class DdcBank:
             self.close()
         except Exception:
             pass
+
+
+def shift_unroll_bank_cc(x, rates, phases=None, table_size: int = 1024, out=None):
+    """shift_unroll_cc for C channels; x [N] (shared wideband input) or [C, N].  Returns (y [C, N], carried phases [C])."""
+    import torch
+    rates = np.atleast_1d(np.asarray(rates, np.float32)); ch = rates.size
+    shared = (x.dim() == 1) if x.dtype == torch.complex64 else (x.dim() == 2)
+    xr, ptr, stride, xc, n = _as_cf32_rows(x)
+    if shared:
+        stride = 0
+    dev = xr.device
+    params = torch.from_numpy(np.array([shift_addition_init(float(r)) for r in rates], np.float32)).to(dev)
+    ds = np.empty((ch, table_size), np.float32); dc = np.empty((ch, table_size), np.float32)
+    for c, r in enumerate(rates):
+        d = lib().shift_unroll_init(float(r), table_size)
+        ds[c] = np.ctypeslib.as_array(d.dsin, shape=(table_size,)); dc[c] = np.ctypeslib.as_array(d.dcos, shape=(table_size,))
+    d_ds, d_dc = torch.from_numpy(ds).to(dev), torch.from_numpy(dc).to(dev)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=dev) if phases is None else phases.clone()
+    out = torch.empty((ch, n), dtype=torch.complex64, device=dev) if out is None else out
+    scratch = _scratch(ch * ((n + table_size - 1) // table_size + 1) * 4, dev)
+    _check(lib().csdrb_shift_unroll_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, params.data_ptr(), d_ds.data_ptr(), d_dc.data_ptr(), table_size,
+                                            table_size, d_phase.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "shift_unroll_bank_cc")
+    return out, d_phase
+
+
+def spectrum_logpower(x, fft_size: int, window: str = "HAMMING", add_db: float = 0.0):
+    """fft_cc | logpower_cf for a whole stream on the device: frames of fft_size samples -> [frames, fft_size] dB values."""
+    import torch
+    assert x.dtype == torch.complex64 and x.is_cuda and x.dim() == 1
+    frames = x.numel() // fft_size
+    xs = x[:frames * fft_size].contiguous().view(frames, fft_size)
+    w = torch.from_numpy(libcsdr.precalculate_window(fft_size, window)).to(x.device)
+    xw = torch.empty_like(xs)
+    _check(lib().csdrb_apply_window_rows_c(xs.data_ptr(), xw.data_ptr(), w.data_ptr(), fft_size, frames, _stream()), "apply_window_rows_c")
+    spec = fft_c2c(xw)
+    out = torch.empty((frames, fft_size), dtype=torch.float32, device=x.device)
+    _check(lib().csdrb_logpower_cf(spec.data_ptr(), out.data_ptr(), frames * fft_size, add_db, _stream()), "logpower_cf")
+    return out

@@ -376,6 +376,40 @@ int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const comp
     return rc < 0 ? rc : counted(0, rc);
 }
 
+int csdrb_apply_window_rows_c(const complexf* d_in, complexf* d_out, const float* d_window, int size, long rows, void* stream)
+{
+    if (!d_in || !d_out || !d_window) { set_error("apply_window: null pointer"); return -1; }
+    int rc = launch_apply_window_rows(reinterpret_cast<const float2*>(d_in), reinterpret_cast<float2*>(d_out), d_window, size, rows, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+int csdrb_logpower_cf(const complexf* d_in, float* d_out, long n, float add_db, void* stream)
+{
+    if (!d_in || !d_out) { set_error("logpower_cf: null pointer"); return -1; }
+    int rc = launch_power(reinterpret_cast<const float2*>(d_in), nullptr, d_out, n, add_db, 0, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+int csdrb_accumulate_power_cf(const complexf* d_in, float* d_acc, long n, void* stream)
+{
+    if (!d_in || !d_acc) { set_error("accumulate_power_cf: null pointer"); return -1; }
+    int rc = launch_power(reinterpret_cast<const float2*>(d_in), nullptr, d_acc, n, 0.f, 1, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+int csdrb_log_ff(const float* d_in, float* d_out, long n, float add_db, void* stream)
+{
+    if (!d_in || !d_out) { set_error("log_ff: null pointer"); return -1; }
+    int rc = launch_power(nullptr, d_in, d_out, n, add_db, 2, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+int csdrb_shift_unroll_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                               const shift_addition_data_t* d_params, const float* d_dsin, const float* d_dcos, long table_stride, int table_size,
+                               float* d_phase_io, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_in || !d_out || !d_params || !d_dsin || !d_dcos || !d_phase_io) { set_error("shift_unroll bank: null pointer"); return -1; }
+    int rc = launch_shift_unroll_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                      reinterpret_cast<const float*>(d_params), d_dsin, d_dcos, table_stride, table_size, d_phase_io, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, void* stream)
 {
     if (!d_in || !d_out) { set_error("limit_ff: null pointer"); return -1; }
@@ -671,6 +705,69 @@ void fastagc_ff(fastagc_ff_t* a, float* output)
     float* recycled = a->buffer_1;
     a->buffer_1 = a->buffer_2; a->buffer_2 = a->buffer_input; a->buffer_input = recycled;
     a->peak_1 = st.peak_1; a->peak_2 = st.peak_2; a->last_gain = st.last_gain;
+}
+
+void apply_precalculated_window_c(complexf* input, complexf* output, int size, float* windowt)
+{
+    const char* who = "apply_precalculated_window_c";
+    if (size <= 0) return;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)size * 8 + 16), who);
+    A_UP(2, windowt, (size_t)size * 4, who);
+    A_CHECK(csdrb_apply_window_rows_c((const complexf*)g_ctx.buf[0], (complexf*)g_ctx.buf[1], (const float*)g_ctx.buf[2], size, 1, g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)size * 8, who);
+    A_SYNC(who);
+}
+
+void apply_window_c(complexf* input, complexf* output, int size, window_t window)
+{
+    float* table = precalculate_window(size, window);                    // the table itself is one-off host work, like every filter design step
+    apply_precalculated_window_c(input, output, size, table);
+    free(table);
+}
+
+static void power_dropin(const char* who, const void* in, size_t in_bytes, float* out, int n, float add_db, int mode)
+{
+    if (n <= 0) return;
+    A_BEGIN(who);
+    A_UP(0, in, in_bytes, who);
+    if (mode == 1) A_UP(1, out, (size_t)n * 4, who); else A_CHECK(g_ctx.reserve(1, (size_t)n * 4 + 16), who);
+    int rc = launch_power(mode == 2 ? nullptr : (const float2*)g_ctx.buf[0], mode == 2 ? (const float*)g_ctx.buf[0] : nullptr, (float*)g_ctx.buf[1], n, add_db, mode, g_ctx.stream);
+    A_CHECK(rc, who); counted(0, 1);
+    A_DOWN(out, 1, (size_t)n * 4, who);
+    A_SYNC(who);
+}
+void logpower_cf(complexf* input, float* output, int size, float add_db) { power_dropin("logpower_cf", input, (size_t)(size > 0 ? size : 0) * 8, output, size, add_db, 0); }
+void accumulate_power_cf(complexf* input, float* output, int size) { power_dropin("accumulate_power_cf", input, (size_t)(size > 0 ? size : 0) * 8, output, size, 0.f, 1); }
+void log_ff(float* input, float* output, int size, float add_db) { power_dropin("log_ff", input, (size_t)(size > 0 ? size : 0) * 4, output, size, add_db, 2); }
+
+float shift_unroll_cc(complexf* input, complexf* output, int input_size, shift_unroll_data_t* d, float starting_phase)
+{
+    const char* who = "shift_unroll_cc";
+    if (input_size <= 0) return starting_phase;
+    if (!d || input_size > d->size) { set_error("input_size %d exceeds the table size %d", input_size, d ? d->size : 0); die(who); }
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 8 + 16), who);
+    // slot 2: [starting phase at +16 | dsin at +64 | dcos after it]
+    const size_t tb = (size_t)d->size * 4;
+    A_CHECK(g_ctx.reserve(2, 64 + 2 * tb + 16), who);
+    char* b2 = static_cast<char*>(g_ctx.buf[2]);
+    // one call = one chunk: the phase carried to the next call is one float multiply-add and a wrap -- done right here on the host
+    float new_phase = starting_phase + input_size * d->phase_increment;
+    while (new_phase > 3.14159265358979323846f) new_phase -= 2 * 3.14159265358979323846f;
+    while (new_phase < -3.14159265358979323846f) new_phase += 2 * 3.14159265358979323846f;
+    A_CUDA(cudaMemcpyAsync(b2 + 16, &starting_phase, 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(b2 + 64, d->dsin, tb, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    A_CUDA(cudaMemcpyAsync(b2 + 64 + tb, d->dcos, tb, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    // single call = single chunk: chunk_phase[0] is the starting phase itself
+    shift_unroll_bank_single(reinterpret_cast<const float2*>(g_ctx.buf[0]), reinterpret_cast<float2*>(g_ctx.buf[1]), input_size,
+                             reinterpret_cast<const float*>(b2 + 64), reinterpret_cast<const float*>(b2 + 64 + tb), reinterpret_cast<const float*>(b2 + 16), g_ctx.stream);
+    counted(0, 1);
+    A_DOWN(output, 1, (size_t)input_size * 8, who);
+    A_SYNC(who);
+    return new_phase;
 }
 
 void limit_ff(float* input, float* output, int input_size, float max_amplitude)

@@ -144,6 +144,44 @@ int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude
     return 1;
 }
 
+// ---- spectrum side path (8f rank 4): window multiply, log power (libcsdr.c:1269-1276, 1296-1314) ----------------------------
+// rows of `size` complex values; the window table repeats per row (fft_cc applies one window per FFT frame)
+__global__ void __launch_bounds__(256) apply_window_rows_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ w, int size, long total)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float2 v = in[i]; const float g = __ldg(w + (int)(i % size));
+        out[i] = make_float2(__fmul_rn(v.x, g), __fmul_rn(v.y, g));
+    }
+}
+// mode 0: out = 10*log10(I^2+Q^2)+add_db   mode 1: acc += I^2+Q^2   mode 2: out = 10*log10(in_f)+add_db (log_ff)
+__global__ void __launch_bounds__(256) power_kernel(const float2* __restrict__ in_c, const float* __restrict__ in_f, float* __restrict__ out, long n, float add_db, int mode)
+{
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float p;
+        if (mode == 2) p = in_f[i];
+        else { const float2 v = in_c[i]; p = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)); }
+        if (mode == 1) out[i] = __fadd_rn(out[i], p);
+        else out[i] = __fadd_rn(__fmul_rn(10.f, (float)log10((double)p)), add_db);      // log10 in double on the float value, like the C promotion
+    }
+}
+
+int launch_apply_window_rows(const float2* d_in, float2* d_out, const float* d_window, int size, long rows, cudaStream_t st)
+{
+    if (size <= 0 || rows <= 0) return 0;
+    apply_window_rows_kernel<<<grid_for((long)size * rows, 256), 256, 0, st>>>(d_in, d_out, d_window, size, (long)size * rows);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+int launch_power(const float2* d_in_c, const float* d_in_f, float* d_out, long n, float add_db, int mode, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    power_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_in_c, d_in_f, d_out, n, add_db, mode);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ---- K4 fmdemod_quadri_cf -------------------------------------------------------------------------
 // out[i] = den ? K*(I*(Q-Qprev) - Q*(I-Iprev))/den : 0 with den = I*I+Q*Q; no FMA contraction so that
 // every intermediate rounds like the reference's SSE code; the K*num/den tail is evaluated in double

@@ -21,6 +21,14 @@ int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude
 int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, float tau, int sample_rate,
                                float* d_last_io, cudaStream_t st);
 
+int launch_apply_window_rows(const float2* d_in, float2* d_out, const float* d_window, int size, long rows, cudaStream_t st);
+int launch_power(const float2* d_in_c, const float* d_in_f, float* d_out, long n, float add_db, int mode, cudaStream_t st);
+int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                             const float* d_params, const float* d_dsin, const float* d_dcos, long table_stride, int table_size,
+                             float* d_phase_io, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+
+void shift_unroll_bank_single(const float2* d_in, float2* d_out, int n, const float* d_dsin, const float* d_dcos, const float* d_phase, cudaStream_t st);
+
 // K2 shift.cu
 size_t shift_bank_scratch_bytes(int channels, int n, int chunk);
 int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,

@@ -127,6 +127,56 @@ __global__ void dshift_kernel(const float2* __restrict__ in, long in_stride, flo
     if (out_size) out_size[ch] = produced;
 }
 
+// shift_unroll_cc (libcsdr.c:301-320): every sample of a call is rotated by (phasor at the call's start) x (table entry i), no
+// recursion -- fully parallel once the per-call start phases are known.  The phase chain between calls is the same float chain as
+// shift_addition_cc's (n * phase_increment with phase_increment = 2*rate*PI), so the same pre-pass kernel serves both.
+__global__ void __launch_bounds__(256)
+shift_unroll_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                         const float* __restrict__ dsin, const float* __restrict__ dcos, long table_stride,
+                         const float* __restrict__ chunk_phase, int n, int chunk, int nchunks)
+{
+    const int ch = blockIdx.y;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float* ts = dsin + (long)ch * table_stride;
+    const float* tc = dcos + (long)ch * table_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = i / chunk, j = i - k * chunk;
+        const double ph = (double)chunk_phase[(long)ch * nchunks + k];
+        const float c0 = (float)cos(ph), s0 = (float)sin(ph);
+        const float dc = __ldg(tc + j), ds = __ldg(ts + j);
+        const float c = __fsub_rn(__fmul_rn(c0, dc), __fmul_rn(s0, ds));
+        const float s = __fadd_rn(__fmul_rn(s0, dc), __fmul_rn(c0, ds));
+        const float2 v = x[i];
+        y[i] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+    }
+}
+
+int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                             const float* d_params, const float* d_dsin, const float* d_dcos, long table_stride, int table_size,
+                             float* d_phase_io, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if (table_size <= 0) { set_error("shift_unroll bank: table size must be positive"); return -1; }
+    const int chunk = table_size < n ? table_size : n;                  // one reference call per `table_size` samples (csdr.c:834-841)
+    const int nchunks = (n + chunk - 1) / chunk;
+    if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
+    float* chunk_phase = static_cast<float*>(d_scratch);
+    shift_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
+    shift_unroll_bank_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, d_dsin, d_dcos, table_stride, chunk_phase, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+// one reference call (n <= table size) from a known starting phase: the drop-in path of shift_unroll_cc
+void shift_unroll_bank_single(const float2* d_in, float2* d_out, int n, const float* d_dsin, const float* d_dcos, const float* d_phase, cudaStream_t st)
+{
+    int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
+    shift_unroll_bank_kernel<<<dim3(gx, 1), 256, 0, st>>>(d_in, 0, d_out, 0, d_dsin, d_dcos, 0, d_phase, n, n, 1);
+}
+
 size_t shift_bank_scratch_bytes(int channels, int n, int chunk)
 {
     if (chunk <= 0 || chunk > n) chunk = n > 0 ? n : 1;

@@ -237,6 +237,100 @@ static int cmd_fmdemod_quadri_cf(int argc, char **argv)
     }
 }
 
+static int cmd_shift_unroll_cc(int argc, char **argv)                      /* csdr.c:800-849 */
+{
+    G.wideband = 1;
+    float phase = 0, rate = 0;
+    int ctl = open_control(argc, argv);
+    if (ctl) { while (!poll_control(ctl, "%g\n", &rate)) usleep(10000); }
+    else { if (argc <= 2) return complain("need required parameter (rate)"); sscanf(argv[2], "%g", &rate); }
+    if (!announce_block(open_block())) return -2;
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block), *out = must_alloc(sizeof(complexf) * (size_t)block);
+    for (;;) {
+        shift_unroll_data_t table = shift_unroll_init(rate, 1024);
+        who(); fprintf(stderr, "reinitialized to %g\n", rate);
+        for (;;) {
+            if (feof(stdin)) return 0;
+            if (!fread(in, sizeof(complexf), (size_t)block, stdin)) break;
+            for (int done = 0; done < block;) {
+                int n = block - done > 1024 ? 1024 : block - done;
+                phase = shift_unroll_cc(in + done, out + done, n, &table, phase);
+                done += n;
+            }
+            fwrite(out, sizeof(complexf), (size_t)block, stdout);
+            if (poll_control(ctl, "%g\n", &rate)) break;
+            end_of_block();
+        }
+        free(table.dsin); free(table.dcos);
+    }
+}
+
+static int cmd_fft_cc(int argc, char **argv)                               /* csdr.c:1569-1643 (binary output; --octave is not part of this build) */
+{
+    if (argc <= 3) return complain("need required parameters (fft_size, out_of_every_n_samples)");
+    int fft_size = 0; sscanf(argv[2], "%d", &fft_size);
+    if (log2n(fft_size) == -1) return complain("fft_size should be power of 2");
+    int every = 0; sscanf(argv[3], "%d", &every);
+    window_t window = WINDOW_DEFAULT;
+    if (argc >= 5) window = firdes_get_window_from_string(argv[4]);
+    if (!open_block()) return -2;
+    announce_block(fft_size);
+    complexf *in = fft_malloc(sizeof(complexf) * (size_t)fft_size), *win = fft_malloc(sizeof(complexf) * (size_t)fft_size);
+    complexf *out = fft_malloc(sizeof(complexf) * (size_t)fft_size), *skip = must_alloc(sizeof(complexf) * (size_t)block);
+    FFT_PLAN_T *plan = make_fft_c2c(fft_size, win, out, 1, 0);
+    if (!plan) return complain("FFT size error.");
+    float *table = precalculate_window(fft_size, window);
+    memset(in, 0, sizeof(complexf) * (size_t)fft_size);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        if (every > fft_size) {
+            fread(in, sizeof(complexf), (size_t)fft_size, stdin);
+            for (int remain = every - fft_size; remain > 0; remain -= block) fread(skip, sizeof(complexf), (size_t)(remain < block ? remain : block), stdin);
+        } else {
+            memmove(in, in + every, sizeof(complexf) * (size_t)(fft_size - every));
+            fread(in + fft_size - every, sizeof(complexf), (size_t)every, stdin);
+        }
+        apply_precalculated_window_c(in, win, fft_size, table);
+        fft_execute(plan);
+        fwrite(out, sizeof(complexf), (size_t)fft_size, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_logpower_cf(int argc, char **argv)                          /* csdr.c:1645-1661 */
+{
+    float add_db = 0; if (argc >= 3) sscanf(argv[2], "%g", &add_db);
+    if (!announce_block(open_block())) return -2;
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block);
+    float *out = must_alloc(sizeof(float) * (size_t)block);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in, sizeof(complexf), (size_t)block, stdin);
+        logpower_cf(in, out, block, add_db);
+        fwrite(out, sizeof(float), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_logaveragepower_cf(int argc, char **argv)                   /* csdr.c:1663-1695 */
+{
+    G.wideband = 1;
+    if (argc <= 4) return complain("need required parameters (add_db, fft_size, avgnumber)");
+    float add_db = 0; int fft_size = 0, avgnumber = 0;
+    sscanf(argv[2], "%g", &add_db); sscanf(argv[3], "%d", &fft_size); sscanf(argv[4], "%d", &avgnumber);
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)fft_size);
+    float *acc = must_alloc(sizeof(float) * (size_t)fft_size);
+    add_db -= 10.0 * log10(avgnumber);
+    for (;;) {
+        memset(acc, 0, sizeof(float) * (size_t)fft_size);
+        if (feof(stdin)) return 0;
+        for (int n = 0; n < avgnumber; n++) { fread(in, sizeof(complexf), (size_t)fft_size, stdin); accumulate_power_cf(in, acc, fft_size); }
+        log_ff(acc, acc, fft_size, add_db);
+        fwrite(acc, sizeof(float), (size_t)fft_size, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_limit_ff(int argc, char **argv)                              /* csdr.c:673-686 */
 {
     float max_amplitude = 1.0f; if (argc >= 3) sscanf(argv[2], "%g", &max_amplitude);
@@ -463,6 +557,10 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fractional_decimator_ff", cmd_fractional_decimator_ff, "fractional_decimator_ff <decimation_rate> [num_poly_points ( [transition_bw [window]] | --prefilter )]"},
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
     {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
+    {"shift_unroll_cc", cmd_shift_unroll_cc, "shift_unroll_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
+    {"fft_cc", cmd_fft_cc, "fft_cc <fft_size> <out_of_every_n_samples> [window]"},
+    {"logpower_cf", cmd_logpower_cf, "logpower_cf [add_db]"},
+    {"logaveragepower_cf", cmd_logaveragepower_cf, "logaveragepower_cf <add_db> <fft_size> <avgnumber>"},
     {"deemphasis_wfm_ff", cmd_deemphasis_wfm_ff, "deemphasis_wfm_ff <sample_rate> <tau>"},
     {"bandpass_fir_fft_cc", cmd_bandpass_fir_fft_cc, "bandpass_fir_fft_cc <low_cut> <high_cut> <transition_bw> [window] | --fifo <fifo_path> <transition_bw> [window]"},
     {"fastddc_fwd_cc", cmd_fastddc_fwd_cc, "fastddc_fwd_cc <decimation> [transition_bw [window]]"},

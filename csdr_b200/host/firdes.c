@@ -128,6 +128,35 @@ shift_addition_data_t decimating_shift_addition_init(float rate, int decimation)
     return shift_addition_init(rate * decimation);
 }
 
+/* ---- window table and shift_unroll table (libcsdr.c:1256-1267, 283-299): one-off host work ------------ */
+float *precalculate_window(int size, window_t window)
+{
+    float *table = (float *)malloc(sizeof(float) * (size_t)(size > 0 ? size : 1));
+    for (int k = 0; k < size; k++) {
+        const float rate = (float)k / (size - 1);
+        table[k] = window_value(window, (float)(2.0 * (double)rate + 1.0));
+    }
+    return table;
+}
+
+shift_unroll_data_t shift_unroll_init(float rate, int size)
+{
+    shift_unroll_data_t d;
+    d.phase_increment = 2 * rate * PI_F;
+    d.size = size;
+    d.dsin = (float *)malloc(sizeof(float) * (size_t)(size > 0 ? size : 1));
+    d.dcos = (float *)malloc(sizeof(float) * (size_t)(size > 0 ? size : 1));
+    float phase = 0;
+    for (int k = 0; k < size; k++) {
+        phase += d.phase_increment;
+        while (phase > PI_F) phase -= 2 * PI_F;
+        while (phase < -PI_F) phase += 2 * PI_F;
+        d.dsin[k] = (float)sin((double)phase);
+        d.dcos[k] = (float)cos((double)phase);
+    }
+    return d;
+}
+
 /* ---- fastddc geometry (fastddc.c:38-104) ------------------------------------------------------- */
 int fastddc_init(fastddc_t *ddc, float transition_bw, int decimation, float shift_rate)
 {

@@ -88,6 +88,17 @@ void fastagc_ff(fastagc_ff_t *input, float *output);
 float deemphasis_wfm_ff(float *input, float *output, int input_size, float tau, int sample_rate, float last_output);
 void  limit_ff(float *input, float *output, int input_size, float max_amplitude);
 
+/* spectrum side path and shift_unroll, SURVEY 8(f) ranks 3-4 (libcsdr.h:142-149, 199-207; libcsdr.c:1245-1276, 1296-1314, 283-320) */
+float *precalculate_window(int size, window_t window);                                   /* host table, malloc'ed like the reference's */
+void  apply_window_c(complexf *input, complexf *output, int size, window_t window);
+void  apply_precalculated_window_c(complexf *input, complexf *output, int size, float *windowt);
+void  logpower_cf(complexf *input, float *output, int size, float add_db);
+void  accumulate_power_cf(complexf *input, float *output, int size);
+void  log_ff(float *input, float *output, int size, float add_db);
+typedef struct shift_unroll_data_s { float *dsin; float *dcos; float phase_increment; int size; } shift_unroll_data_t;
+shift_unroll_data_t shift_unroll_init(float rate, int size);
+float shift_unroll_cc(complexf *input, complexf *output, int input_size, shift_unroll_data_t *d, float starting_phase);
+
 /* FFT abstraction (fft_fftw.h:10-27; fft_fftw.c:6-46).  Callers read ->size/->input/->output directly
  * (libcsdr.c:822-835, fastddc.c:112-116), so the first three members keep the reference layout. */
 struct fft_plan_s { int size; void *input; void *output; void *plan; };
@@ -195,6 +206,18 @@ int  csdrb_ddc_bank_process(csdrb_ddc_bank_t *bank, const complexf *d_wide, int 
 int csdrb_limit_ff(const float *d_in, float *d_out, long n, float max_amplitude, void *stream);
 int csdrb_deemphasis_wfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
                                  float tau, int sample_rate, float *d_last_io, void *stream);
+
+/* spectrum side path on device buffers: `rows` frames of `size` values share one window table; power modes as the reference's
+ * logpower_cf / accumulate_power_cf (d_out is read-modify-write) / log_ff */
+int csdrb_apply_window_rows_c(const complexf *d_in, complexf *d_out, const float *d_window, int size, long rows, void *stream);
+int csdrb_logpower_cf(const complexf *d_in, float *d_out, long n, float add_db, void *stream);
+int csdrb_accumulate_power_cf(const complexf *d_in, float *d_acc, long n, void *stream);
+int csdrb_log_ff(const float *d_in, float *d_out, long n, float add_db, void *stream);
+/* shift_unroll_cc bank: d_params as for the shift_addition bank (shift_addition_init(rate_c): its .rate is the same 2*rate), tables
+ * d_dsin/d_dcos [channels][table_stride] from shift_unroll_init(rate_c, table_size); one reference call per table_size samples */
+int csdrb_shift_unroll_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
+                               const shift_addition_data_t *d_params, const float *d_dsin, const float *d_dcos, long table_stride,
+                               int table_size, float *d_phase_io, void *d_scratch, size_t scratch_bytes, void *stream);
 
 /* K5 fractional_decimator_ff bank: d_state[c].where carries the reference's `where`; on return input_processed
  * and output_size are filled like fractional_decimator_ff() fills them (libcsdr.c:789-792). */

@@ -335,6 +335,75 @@ void oracle_limit_ff(const float *in, float *out, int n, float max_amplitude)
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * spectrum side path, shift_unroll
+ * ---------------------------------------------------------------------------------------------- */
+
+/* [ref libcsdr.c:1256-1267] window table over [-1, 1] mapped as 2*rate+1 with rate = i/(size-1) (the kernels then fold that back). */
+void oracle_precalculate_window(float *windowt, int size, int window)
+{
+    for (int k = 0; k < size; k++) {
+        float rate = (float)k / (size - 1);
+        windowt[k] = oracle_window(window, (float)(2.0 * (double)rate + 1.0));
+    }
+}
+
+/* [ref libcsdr.c:1269-1276] */
+void oracle_apply_precalculated_window_c(const ocf32 *in, ocf32 *out, int size, const float *windowt)
+{
+    for (int k = 0; k < size; k++) { out[k].i = in[k].i * windowt[k]; out[k].q = in[k].q * windowt[k]; }
+}
+
+/* [ref libcsdr.c:1296-1303] 10*log10(I^2+Q^2) + add_db; the logarithm is the double libm one applied to a float. */
+void oracle_logpower_cf(const ocf32 *in, float *out, int size, float add_db)
+{
+    for (int k = 0; k < size; k++) {
+        float p = in[k].i * in[k].i + in[k].q * in[k].q;
+        float l = (float)log10((double)p);
+        out[k] = 10 * l + add_db;
+    }
+}
+
+/* [ref libcsdr.c:1305-1308] */
+void oracle_accumulate_power_cf(const ocf32 *in, float *acc, int size)
+{
+    for (int k = 0; k < size; k++) acc[k] += in[k].i * in[k].i + in[k].q * in[k].q;
+}
+
+/* [ref libcsdr.c:1310-1314] */
+void oracle_log_ff(const float *in, float *out, int size, float add_db)
+{
+    for (int k = 0; k < size; k++) { float l = (float)log10((double)in[k]); out[k] = 10 * l + add_db; }
+}
+
+/* [ref libcsdr.c:283-299] table of the phasor after 1..size steps, built with a float phase accumulator wrapped to (-pi, pi]. */
+float oracle_shift_unroll_init(float rate, int size, float *dsin, float *dcos)
+{
+    float inc = 2 * rate * kPi;
+    float ph = 0;
+    for (int k = 0; k < size; k++) {
+        ph += inc;
+        while (ph > kPi) ph -= 2 * kPi;
+        while (ph < -kPi) ph += 2 * kPi;
+        dsin[k] = (float)sin((double)ph);
+        dcos[k] = (float)cos((double)ph);
+    }
+    return inc;
+}
+
+/* [ref libcsdr.c:301-320] every sample is rotated by (start phasor) x (table entry): no recursion, so no error growth inside a call. */
+float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *dsin, const float *dcos, float phase_increment, float starting_phase)
+{
+    float c0 = (float)cos((double)starting_phase), s0 = (float)sin((double)starting_phase);
+    for (int k = 0; k < n; k++) {
+        float c = c0 * dcos[k] - s0 * dsin[k];
+        float s = s0 * dcos[k] + c0 * dsin[k];
+        out[k].i = c * in[k].i - s * in[k].q;
+        out[k].q = s * in[k].i + c * in[k].q;
+    }
+    return wrap_pm_pi(starting_phase + n * phase_increment);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * DFT (stands in for FFTW3f)
  * ---------------------------------------------------------------------------------------------- */
 

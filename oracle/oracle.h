@@ -74,6 +74,16 @@ void oracle_fastagc_ff(oracle_fastagc_t *st, float *hist1, float *hist2, const f
 float oracle_deemphasis_wfm_ff(const float *in, float *out, int n, float tau, int sample_rate, float last_output);
 void  oracle_limit_ff(const float *in, float *out, int n, float max_amplitude);
 
+/* spectrum side path + shift_unroll: libcsdr.c:1245-1276 (windows), 1296-1314 (log power),
+ * 283-315 (shift_unroll_init / shift_unroll_cc) */
+void  oracle_precalculate_window(float *windowt, int size, int window);
+void  oracle_apply_precalculated_window_c(const ocf32 *in, ocf32 *out, int size, const float *windowt);
+void  oracle_logpower_cf(const ocf32 *in, float *out, int size, float add_db);
+void  oracle_accumulate_power_cf(const ocf32 *in, float *acc, int size);
+void  oracle_log_ff(const float *in, float *out, int size, float add_db);
+float oracle_shift_unroll_init(float rate, int size, float *dsin, float *dcos);            /* returns phase_increment */
+float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *dsin, const float *dcos, float phase_increment, float starting_phase);
+
 /* mathematical DFT in float64, rounded once to float (stands in for FFTW3f; fft_fftw.c:6-41) */
 void oracle_dft_c2c(const ocf32 *in, ocf32 *out, int n, int forward);
 

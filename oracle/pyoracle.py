@@ -101,6 +101,15 @@ class Oracle:
         L.oracle_deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
         L.oracle_deemphasis_wfm_ff.restype = C.c_float
         L.oracle_limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
+        fp = C.POINTER(C.c_float)
+        L.oracle_precalculate_window.argtypes = [fp, C.c_int, C.c_int]
+        L.oracle_apply_precalculated_window_c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp]
+        L.oracle_logpower_cf.argtypes = [C.POINTER(_CF), fp, C.c_int, C.c_float]
+        L.oracle_accumulate_power_cf.argtypes = [C.POINTER(_CF), fp, C.c_int]
+        L.oracle_log_ff.argtypes = [fp, fp, C.c_int, C.c_float]
+        L.oracle_shift_unroll_init.argtypes = [C.c_float, C.c_int, fp, fp]; L.oracle_shift_unroll_init.restype = C.c_float
+        L.oracle_shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, fp, C.c_float, C.c_float]
+        L.oracle_shift_unroll_cc.restype = C.c_float
         L.oracle_dft_c2c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int]
         L.oracle_apply_fir_fft_cc.argtypes = [C.POINTER(_CF)] * 3 + [C.c_int, C.POINTER(_CF), C.c_int]
         L.oracle_fastddc_init.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_float]
@@ -197,6 +206,38 @@ class Oracle:
     def limit_ff(self, x, max_amplitude=1.0):
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
         self.L.oracle_limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
+
+    # ---- spectrum side path, shift_unroll
+    def precalculate_window(self, size, window="HAMMING"):
+        w = np.empty(size, np.float32); self.L.oracle_precalculate_window(_p(w, C.c_float), size, WINDOWS[window]); return w
+
+    def apply_precalculated_window_c(self, x, w):
+        x = _c64(x); w = np.ascontiguousarray(w, np.float32); y = np.empty_like(x)
+        self.L.oracle_apply_precalculated_window_c(_p(x, _CF), _p(y, _CF), x.size, _p(w, C.c_float)); return y
+
+    def logpower_cf(self, x, add_db=0.0):
+        x = _c64(x); y = np.empty(x.size, np.float32)
+        self.L.oracle_logpower_cf(_p(x, _CF), _p(y, C.c_float), x.size, add_db); return y
+
+    def logaveragepower_cf(self, x, add_db, fft_size, avgnumber):
+        """csdr.c:1663-1695: accumulate avgnumber spectra, then 10*log10 + (add_db - 10*log10(avgnumber))."""
+        x = _c64(x); out = []
+        adj = np.float32(np.float32(add_db) - np.float32(10.0 * np.log10(avgnumber)))
+        for b in range(x.size // (fft_size * avgnumber)):
+            acc = np.zeros(fft_size, np.float32)
+            for n in range(avgnumber):
+                seg = x[(b * avgnumber + n) * fft_size:(b * avgnumber + n + 1) * fft_size]
+                self.L.oracle_accumulate_power_cf(_p(seg, _CF), _p(acc, C.c_float), fft_size)
+            y = np.empty(fft_size, np.float32); self.L.oracle_log_ff(_p(acc, C.c_float), _p(y, C.c_float), fft_size, float(adj)); out.append(y)
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    def shift_unroll_cc(self, x, rate, phase=0.0, size=1024):
+        x = _c64(x); y = np.empty_like(x); ds = np.empty(size, np.float32); dc = np.empty(size, np.float32)
+        inc = self.L.oracle_shift_unroll_init(rate, size, _p(ds, C.c_float), _p(dc, C.c_float))
+        for s0 in range(0, x.size, size):
+            n = min(size, x.size - s0)
+            phase = self.L.oracle_shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, _p(ds, C.c_float), _p(dc, C.c_float), inc, phase)
+        return y, float(np.float32(phase))
 
     # ---- FFT family
     def dft(self, x, forward=True):
@@ -299,6 +340,9 @@ class Ref:
                     ("buffer_input", C.POINTER(C.c_float)), ("peak_1", C.c_float), ("peak_2", C.c_float),
                     ("input_size", C.c_int), ("reference", C.c_float), ("last_gain", C.c_float)]
 
+    class _Unroll(C.Structure):             # libcsdr.h:199-205
+        _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
+
     class _Plan(C.Structure):               # fft_fftw.h:14-20
         _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
 
@@ -332,6 +376,14 @@ class Ref:
         L.deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
         L.deemphasis_wfm_ff.restype = C.c_float
         L.limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
+        fp = C.POINTER(C.c_float)
+        L.precalculate_window.argtypes = [C.c_int, C.c_int]; L.precalculate_window.restype = fp
+        L.apply_precalculated_window_c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp]
+        L.logpower_cf.argtypes = [C.POINTER(_CF), fp, C.c_int, C.c_float]
+        L.accumulate_power_cf.argtypes = [C.POINTER(_CF), fp, C.c_int]
+        L.log_ff.argtypes = [fp, fp, C.c_int, C.c_float]
+        L.shift_unroll_init.argtypes = [C.c_float, C.c_int]; L.shift_unroll_init.restype = self._Unroll
+        L.shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
         L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
         L.fft_execute.argtypes = [C.POINTER(self._Plan)]
         L.fft_destroy.argtypes = [C.POINTER(self._Plan)]
@@ -423,6 +475,36 @@ class Ref:
     def limit_ff(self, x, max_amplitude=1.0):
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
         self.L.limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
+
+    def precalculate_window(self, size, window="HAMMING"):
+        p = self.L.precalculate_window(size, WINDOWS[window]); return np.ctypeslib.as_array(p, shape=(size,)).copy()
+
+    def apply_precalculated_window_c(self, x, w):
+        x = _c64(x); w = np.ascontiguousarray(w, np.float32); y = np.empty_like(x)
+        self.L.apply_precalculated_window_c(_p(x, _CF), _p(y, _CF), x.size, _p(w, C.c_float)); return y
+
+    def logpower_cf(self, x, add_db=0.0):
+        x = _c64(x); y = np.empty(x.size, np.float32)
+        self.L.logpower_cf(_p(x, _CF), _p(y, C.c_float), x.size, add_db); return y
+
+    def logaveragepower_cf(self, x, add_db, fft_size, avgnumber):
+        x = _c64(x); out = []
+        adj = np.float32(np.float32(add_db) - np.float32(10.0 * np.log10(avgnumber)))
+        for b in range(x.size // (fft_size * avgnumber)):
+            acc = np.zeros(fft_size, np.float32)
+            for n in range(avgnumber):
+                seg = x[(b * avgnumber + n) * fft_size:(b * avgnumber + n + 1) * fft_size]
+                self.L.accumulate_power_cf(_p(seg, _CF), _p(acc, C.c_float), fft_size)
+            y = np.empty(fft_size, np.float32); self.L.log_ff(_p(acc, C.c_float), _p(y, C.c_float), fft_size, float(adj)); out.append(y)
+        return np.concatenate(out) if out else np.zeros(0, np.float32)
+
+    def shift_unroll_cc(self, x, rate, phase=0.0, size=1024):
+        x = _c64(x); y = np.empty_like(x)
+        d = self.L.shift_unroll_init(rate, size)
+        for s0 in range(0, x.size, size):
+            n = min(size, x.size - s0)
+            phase = self.L.shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
+        return y, float(np.float32(phase))
 
     def dft(self, x, forward=True):
         x = _c64(x).copy(); y = np.empty_like(x)

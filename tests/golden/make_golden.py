@@ -78,6 +78,13 @@ def main():
     y, last = r.deemphasis_wfm_ff(g["deemph_in"], 50e-6, 48000, 0.0, 1024)
     g["deemph_out_50us_48k"], g["deemph_last"] = y, np.float32(last)
     g["limit_out"] = r.limit_ff(g["deemph_in"], 1.0)
+    # --- spectrum side path + shift_unroll (8f ranks 3, 4)
+    g["win_hamming_1024"] = r.precalculate_window(1024, "HAMMING")
+    g["spec_in"] = cplx(rng, 4096, 0.5)
+    g["logpower_out"] = r.logpower_cf(g["spec_in"], -70.0)
+    g["logavg_out"] = r.logaveragepower_cf(g["spec_in"], -70.0, 512, 4)
+    y, ph = r.shift_unroll_cc(g["shift_in"], -0.085, 0.0, 1024)
+    g["unroll_out"], g["unroll_phase"] = y, np.float32(ph)
     # --- overlap-add FFT FIR (a10) : bw 0.05 -> 79 taps, fft 256, 178 samples/block (csdr.c:1833-1838)
     g["bp_in"] = cplx(rng, 434 * 5)
     g["bp_out"] = r.bandpass_fir_fft_cc(g["bp_in"], -0.1, 0.2, 0.05, "HAMMING")

@@ -123,6 +123,22 @@ def test_fft_commands(clis):
         assert rel(a, b) < 1e-5, stages
 
 
+def test_spectrum_and_unroll_commands(clis):
+    ours, ref = clis
+    rng = np.random.default_rng(12)
+    z = (rng.uniform(-1, 1, 150_000) + 1j * rng.uniform(-1, 1, 150_000)).astype(np.complex64)
+    a = np.frombuffer(run_graph(ours, ["shift_unroll_cc 0.123"], z.tobytes()), np.complex64); b = np.frombuffer(run_graph(ref, ["shift_unroll_cc 0.123"], z.tobytes()), np.complex64)
+    assert a.size == b.size and rel(a, b) < 1e-6
+    for stages in (["fft_cc 1024 1024 HAMMING", "logpower_cf -70"], ["fft_cc 2048 500", "logaveragepower_cf -70 2048 4"], ["fft_cc 512 3000 BLACKMAN"]):
+        ra = run_graph(ours, stages, z.tobytes()); rb = run_graph(ref, stages, z.tobytes())
+        assert len(ra) == len(rb) and len(ra) > 0, stages
+        if stages[-1].startswith("fft_cc"):
+            assert rel(np.frombuffer(ra, np.complex64), np.frombuffer(rb, np.complex64)) < 1e-5
+        else:
+            da, db = np.frombuffer(ra, np.float32), np.frombuffer(rb, np.float32)
+            assert np.abs(da - db).max() < 5e-3, stages                              # dB values; FFT rounding differences on weak bins
+
+
 def test_dynamic_bufsize_preamble(clis):
     ours, ref = clis
     z = np.random.default_rng(9).uniform(-1, 1, 2 * 70_000).astype(np.float32)

@@ -331,3 +331,27 @@ def test_ddc_bank_object_streams_with_lookahead(gpu, oracle):
         want = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0]
         assert _rel(got[c], want[:got.shape[1]]) < TOL, c
     bank.close()
+
+
+# ------------------------------------------------------------------------------------------ spectrum path + shift_unroll (8f ranks 3, 4)
+def test_spectrum_path_and_shift_unroll(gpu, oracle):
+    assert np.array_equal(gpu.libcsdr.precalculate_window(1024, "HAMMING"), oracle.precalculate_window(1024, "HAMMING"))
+    x = GOLD["spec_in"]
+    assert np.abs(gpu.libcsdr.logpower_cf(x, -70.0) - GOLD["logpower_out"]).max() < 2e-5
+    assert np.abs(gpu.libcsdr.logaveragepower_cf(x, -70.0, 512, 4) - GOLD["logavg_out"]).max() < 2e-5
+    assert np.array_equal(gpu.libcsdr.apply_window_c(x[:1024], "BLACKMAN"), oracle.apply_precalculated_window_c(x[:1024], oracle.precalculate_window(1024, "BLACKMAN")))
+    # whole-stream spectrum on the device vs window -> float64 DFT -> logpower on the CPU
+    big = _cplx(np.random.default_rng(41), 64 * 2048, 0.5)
+    db = gpu.spectrum_logpower(_dev(big), 2048, "HAMMING", -30.0).cpu().numpy()
+    w = oracle.precalculate_window(2048, "HAMMING")
+    for f in (0, 31, 63):
+        want = oracle.logpower_cf(oracle.dft(oracle.apply_precalculated_window_c(big[f * 2048:(f + 1) * 2048], w)), -30.0)
+        assert np.abs(db[f] - want).max() < 1e-3                                      # dB: FFT rounding (1e-7 relative) on bins far below the peak
+    y, ph = gpu.libcsdr.shift_unroll_cc(GOLD["shift_in"], -0.085, 0.0, 1024)
+    assert _rel(y, GOLD["unroll_out"]) < 1e-7 and np.float32(ph) == GOLD["unroll_phase"]
+    xs = _cplx(np.random.default_rng(42), 20_000)
+    rates = [0.2, -0.4999, 0.0123]
+    yb, pb = gpu.shift_unroll_bank_cc(_dev(xs), rates)
+    for c, r in enumerate(rates):
+        want, wp = oracle.shift_unroll_cc(xs, r, 0.0, 1024)
+        assert _rel(yb[c].cpu().numpy(), want) < 1e-7 and np.float32(wp) == pb[c].item()

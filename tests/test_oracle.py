@@ -97,6 +97,14 @@ def test_ref_audio_tail(oracle, ref):
         assert np.array_equal(ya, yb) and np.float32(la) == np.float32(lb)
 
 
+def test_golden_spectrum_and_unroll(oracle, ref=None):
+    assert rel_rms(oracle.precalculate_window(1024, "HAMMING"), GOLD["win_hamming_1024"]) < TIGHT
+    assert np.abs(oracle.logpower_cf(GOLD["spec_in"], -70.0) - GOLD["logpower_out"]).max() < 2e-5          # dB; an ulp at |x| ~ 100
+    assert np.abs(oracle.logaveragepower_cf(GOLD["spec_in"], -70.0, 512, 4) - GOLD["logavg_out"]).max() < 2e-5
+    y, ph = oracle.shift_unroll_cc(GOLD["shift_in"], -0.085, 0.0, 1024)
+    assert rel_rms(y, GOLD["unroll_out"]) < 1e-7 and np.float32(ph) == GOLD["unroll_phase"]
+
+
 def test_golden_bandpass_fir_fft(oracle):
     y = oracle.bandpass_fir_fft_cc(GOLD["bp_in"], -0.1, 0.2, 0.05)
     assert y.size == GOLD["bp_out"].size == (GOLD["bp_in"].size // 178) * 178     # 79 taps -> fft 256, 178 per block
