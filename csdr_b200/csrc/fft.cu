@@ -61,7 +61,10 @@ fft_c2c_batch_kernel(const float2* __restrict__ in, long in_stride, float2* __re
     const int tid = threadIdx.x;
     const float2* x = in + (long)blockIdx.x * in_stride;
     float2* y = out + (long)blockIdx.x * out_stride;
-    for (int i = tid; i < N; i += NT) s[fft_pad(i)] = x[i];
+    if constexpr (N >= 2 * NT) {
+        if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) fft_stage_in_vec<N, NT>(s, tid, x);
+        else fft_stage_in<N, NT>(s, tid, [&](int i) { return x[i]; });
+    } else fft_stage_in<N, NT>(s, tid, [&](int i) { return x[i]; });
     __syncthreads();
     block_fft<N, NT, INV>(s, tw, tid);
     for (int i = tid; i < N; i += NT) y[i] = s[fft_pad(i)];
@@ -129,13 +132,24 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
     for (int i = tid; i < overlap; i += NT) tail[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
     for (int b = b_start; b < b_last; b++) {
         const bool emit = b >= b_first;
-        for (int i = tid; i < N; i += NT) s[fft_pad(i)] = i < input_size ? x[(long)b * input_size + i] : make_float2(0.f, 0.f);
+        { const float2* xb = x + (long)b * input_size;
+          fft_stage_in<N, NT>(s, tid, [&](int i) { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }); }
         __syncthreads();
         block_fft<N, NT, false>(s, tw, tid);
-        for (int i = tid; i < N; i += NT) {
-            const float2 a = s[fft_pad(i)], h = H[i];
-            // same rounding sequence as libcsdr.c:827-828 (separate products, no FMA)
-            s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        {
+            constexpr int PERH = (N + NT - 1) / NT;
+            float2 hh[PERH];                                            // all taps_fft loads first (L2 latency once, not PERH times)
+#pragma unroll
+            for (int k = 0; k < PERH; k++) { const int i = tid + k * NT; hh[k] = (N % NT == 0 || i < N) ? __ldg(H + i) : make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int k = 0; k < PERH; k++) {
+                const int i = tid + k * NT;
+                if (N % NT == 0 || i < N) {
+                    const float2 a = s[fft_pad(i)], h = hh[k];
+                    // same rounding sequence as libcsdr.c:827-828 (separate products, no FMA)
+                    s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+                }
+            }
         }
         __syncthreads();
         block_fft<N, NT, true>(s, tw, tid);
@@ -193,10 +207,7 @@ fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, 
     const int overlap = N - input_size;
     // block b transforms stream samples [b*input_size - overlap, (b+1)*input_size); negative positions come from the carried overlap
     const long start = (long)b * input_size - overlap;
-    for (int i = tid; i < N; i += NT) {
-        const long p = start + i;
-        s[fft_pad(i)] = p >= 0 ? in[p] : overlap_in[overlap + p];
-    }
+    fft_stage_in<N, NT>(s, tid, [&](int i) { const long p = start + i; return p >= 0 ? __ldg(in + p) : overlap_in[overlap + p]; });
     __syncthreads();
     block_fft<N, NT, false>(s, tw, tid);
     float2* y = spectra + (long)b * N;
@@ -255,7 +266,7 @@ apply_fir_fft_kernel(const float2* __restrict__ in, const float2* __restrict__ H
     float2* s = reinterpret_cast<float2*>(smem_raw);
     constexpr int NT = fft_threads(N);
     const int tid = threadIdx.x;
-    for (int i = tid; i < N; i += NT) s[fft_pad(i)] = in[i];
+    fft_stage_in<N, NT>(s, tid, [&](int i) { return in[i]; });
     __syncthreads();
     block_fft<N, NT, false>(s, tw, tid);
     for (int i = tid; i < N; i += NT) {
