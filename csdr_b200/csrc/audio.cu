@@ -125,18 +125,36 @@ fracdec_interp_seg_kernel(const float* __restrict__ in, long in_stride, float* _
         const int low = (int)ceilf(where) - 1;
         const float xw = __fsub_rn(where, (float)low);
         float acc = 0.f;
-        int slot = 0;
-        for (int xi = xifirst; xi <= xilast; xi++, slot++) {
-            float coef = 1.f, den = 1.f;
-            for (int xj = xifirst; xj <= xilast; xj++)
-                if (xi != xj) { coef = __fmul_rn(coef, __fsub_rn(xw, (float)xj)); den = __fmul_rn(den, (float)(xi - xj)); }
-            float pt;
-            if (taps) {
-                pt = 0.f;
-                const float* seg = x + low + slot;
-                for (int t = 0; t < taps_length; t++) pt = __fadd_rn(pt, __fmul_rn(seg[t], taps[t]));
-            } else pt = x[low + slot];
-            acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(coef, den), pt));
+        if (!taps && num_poly_points <= 16) {
+            // common case (12 points, no prefilter): fetch all points and form all (xw - xj) first, then the products -- the loads are
+            // independent of the accumulation chain, issuing them up front hides their latency once instead of once per point
+            float pts[16], dxj[16];
+#pragma unroll
+            for (int w = 0; w < 16; w++) { pts[w] = w < num_poly_points ? x[low + w] : 0.f; dxj[w] = __fsub_rn(xw, (float)(xifirst + w)); }
+#pragma unroll
+            for (int wi = 0; wi < 16; wi++) {
+                if (wi < num_poly_points) {
+                    float coef = 1.f, den = 1.f;
+#pragma unroll
+                    for (int wj = 0; wj < 16; wj++)
+                        if (wj < num_poly_points && wj != wi) { coef = __fmul_rn(coef, dxj[wj]); den = __fmul_rn(den, (float)(wi - wj)); }
+                    acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(coef, den), pts[wi]));
+                }
+            }
+        } else {
+            int slot = 0;
+            for (int xi = xifirst; xi <= xilast; xi++, slot++) {
+                float coef = 1.f, den = 1.f;
+                for (int xj = xifirst; xj <= xilast; xj++)
+                    if (xi != xj) { coef = __fmul_rn(coef, __fsub_rn(xw, (float)xj)); den = __fmul_rn(den, (float)(xi - xj)); }
+                float pt;
+                if (taps) {
+                    pt = 0.f;
+                    const float* seg = x + low + slot;
+                    for (int t = 0; t < taps_length; t++) pt = __fadd_rn(pt, __fmul_rn(seg[t], taps[t]));
+                } else pt = x[low + slot];
+                acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(coef, den), pt));
+            }
         }
         out[(long)c * out_stride + o] = acc;
     }

@@ -426,20 +426,28 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
         for (int u = 0; u < CT; u++)
 #pragma unroll
             for (int v = 0; v < BT; v++) acc[u][v] = make_float2(0.f, 0.f);
-#pragma unroll 4
-        for (int i = r; i < N; i += M) {                                // unrolled so the loads of later bins overlap the arithmetic of earlier ones
-            const int xi = i < half ? i + half : i - half;
-            float2 x[BT], h[CT];
+        // two bins per step, all eight loads of both bins issued before the arithmetic of the first (r01: long_scoreboard dominated)
+        for (int i = r; i < N; i += 2 * M) {
+            const int i2 = i + M;                                       // N / M is even for every fastddc geometry (pre_decimation >= 2)
+            const int xi = i < half ? i + half : i - half, xi2 = i2 < half ? i2 + half : i2 - half;
+            float2 x[BT], h[CT], x2[BT], h2[CT];
 #pragma unroll
-            for (int v = 0; v < BT; v++) x[v] = __ldg(spectra + (long)bidx[v] * N + xi);
+            for (int v = 0; v < BT; v++) { x[v] = __ldg(spectra + (long)bidx[v] * N + xi); x2[v] = __ldg(spectra + (long)bidx[v] * N + xi2); }
 #pragma unroll
-            for (int u = 0; u < CT; u++) h[u] = __ldg(taps_fft + (long)cidx[u] * N + i);
+            for (int u = 0; u < CT; u++) { h[u] = __ldg(taps_fft + (long)cidx[u] * N + i); h2[u] = __ldg(taps_fft + (long)cidx[u] * N + i2); }
 #pragma unroll
             for (int u = 0; u < CT; u++)
 #pragma unroll
                 for (int v = 0; v < BT; v++) {
                     acc[u][v].x = __fadd_rn(acc[u][v].x, __fsub_rn(__fmul_rn(x[v].x, h[u].x), __fmul_rn(x[v].y, h[u].y)));
                     acc[u][v].y = __fadd_rn(acc[u][v].y, __fadd_rn(__fmul_rn(x[v].x, h[u].y), __fmul_rn(x[v].y, h[u].x)));
+                }
+#pragma unroll
+            for (int u = 0; u < CT; u++)
+#pragma unroll
+                for (int v = 0; v < BT; v++) {
+                    acc[u][v].x = __fadd_rn(acc[u][v].x, __fsub_rn(__fmul_rn(x2[v].x, h2[u].x), __fmul_rn(x2[v].y, h2[u].y)));
+                    acc[u][v].y = __fadd_rn(acc[u][v].y, __fadd_rn(__fmul_rn(x2[v].x, h2[u].y), __fmul_rn(x2[v].y, h2[u].x)));
                 }
         }
 #pragma unroll
@@ -498,7 +506,7 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     fastddc_state_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
     CSDRB_CUDA(cudaGetLastError());
-    if (fft_inv_size <= 1024 && fft_inv_size >= 8) {
+    if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {
         constexpr int CT = 4, BT = 4;
         const dim3 tgrid((nblocks + BT - 1) / BT, (channels + CT - 1) / CT);
         const size_t smem = sizeof(float2) * (size_t)CT * BT * fft_smem_elems(fft_inv_size);
