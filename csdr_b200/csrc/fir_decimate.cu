@@ -174,7 +174,7 @@ static int launch_fast(const float2* in, long in_stride, float2* out, long out_s
     return 0;
 }
 
-int fir_bank_variant_count() { return 4; }
+int fir_bank_variant_count() { return 8; }
 
 // variant: -1 = automatic choice; >= 0 selects one of the compiled tilings (tuning / benchmarking hook)
 int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n_in,
@@ -197,6 +197,10 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
             case 1:  rc = launch_fast<10, 20, 15, 2, 2>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
             case 2:  rc = launch_fast<10, 20, 15, 4, 1>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
             case 3:  rc = launch_fast<10, 20, 9, 4, 2>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
+            case 4:  rc = launch_fast<10, 20, 13, 1, 5>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
+            case 5:  rc = launch_fast<10, 20, 9, 2, 4>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
+            case 6:  rc = launch_fast<10, 20, 11, 2, 3>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
+            case 7:  rc = launch_fast<10, 20, 17, 2, 2>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
             default: rc = launch_fast<10, 20, 13, 2, 3>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st); break;
         }
         return rc < 0 ? rc : n_out;

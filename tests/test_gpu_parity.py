@@ -62,7 +62,7 @@ def test_convert_s16_both_ways_bit_exact(gpu, oracle):
 
 
 # ------------------------------------------------------------------------------------------ K3
-@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3, 4, 5, 6, 7])
 def test_fir_bank_headline_shape_vs_oracle(gpu, oracle, variant):
     """256-channel geometry of BASELINE config 2 (T=199, D=10) at an oracle-sized N, every tiling variant."""
     T, D, C, N = 199, 10, 8, 40_000 + 7
