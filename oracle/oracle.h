@@ -8,7 +8,7 @@
  * Every function restates, in strict IEEE-754 arithmetic (-fno-fast-math, no FMA contraction),
  * the algorithm of the reference function named in its comment (file:line into ha7ilm/csdr @6ef2a742).
  * It is pinned against the compiled, unmodified reference (oracle/_ref/libcsdr_ref.so, built by
- * `make -C oracle ref`) in tests/test_oracle_vs_ref.py and against the committed golden vectors in
+ * `make -C oracle ref`) in tests/test_oracle.py and against the committed golden vectors in
  * tests/golden/ (generated from that same compiled reference by tests/golden/make_golden.py).
  *
  * FFT boundary: the reference calls FFTW3f (third-party, absent here; only pinned version anywhere
