@@ -48,6 +48,10 @@ class _Unroll(C.Structure):             # shift_unroll_data_t (= libcsdr.h:199-2
     _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
 
+class _AddFast(C.Structure):            # shift_addfast_data_t (= libcsdr.h:189-194)
+    _fields_ = [("dsin", C.c_float * 4), ("dcos", C.c_float * 4), ("phase_increment", C.c_float)]
+
+
 class _Plan(C.Structure):               # struct fft_plan_s (= fft_fftw.h:14-20)
     _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
 
@@ -118,9 +122,15 @@ def lib() -> C.CDLL:
     L.log_ff.argtypes = [vp, vp, it, C.c_float]
     L.shift_unroll_init.argtypes = [C.c_float, it]; L.shift_unroll_init.restype = _Unroll
     L.shift_unroll_cc.argtypes = [vp, vp, it, C.POINTER(_Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
+    L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = _AddFast
+    L.shift_addfast_cc.argtypes = [vp, vp, it, C.POINTER(_AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
+    L.csdrb_shift_addfast_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, it, vp, sz, vp]
     L.csdrb_limit_ff.argtypes = [vp, vp, lg, C.c_float, vp]
     L.csdrb_deemphasis_wfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, vp]
     L.limit_ff.argtypes = [vp, vp, it, C.c_float]
+    L.deemphasis_nfm_ff.argtypes = [vp, vp, it, it]
+    L.csdrb_deemphasis_nfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp]
+    L.csdrb_deemphasis_nfm_taps.argtypes = [it, C.POINTER(it)]; L.csdrb_deemphasis_nfm_taps.restype = C.POINTER(C.c_float)
     L.deemphasis_wfm_ff.argtypes = [vp, vp, it, C.c_float, it, C.c_float]; L.deemphasis_wfm_ff.restype = C.c_float
     L.csdrb_fastddc_fwd_cc.argtypes = [vp, vp, vp, it, it, it, vp]
     L.csdrb_fastddc_inv_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastddc_inv_bank_scratch_bytes.restype = sz
@@ -409,6 +419,12 @@ class libcsdr:
         lib().limit_ff(x.ctypes.data, y.ctypes.data, x.size, max_amplitude); return y
 
     @staticmethod
+    def deemphasis_nfm_ff(x, sample_rate):
+        x = np.ascontiguousarray(x, np.float32); y = np.zeros_like(x)
+        n = lib().deemphasis_nfm_ff(x.ctypes.data, y.ctypes.data, x.size, sample_rate)
+        return y[:n].copy()
+
+    @staticmethod
     def precalculate_window(size, window="HAMMING"):
         p = lib().precalculate_window(size, WINDOWS[window]); return np.ctypeslib.as_array(p, shape=(size,)).copy()
 
@@ -441,6 +457,17 @@ class libcsdr:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = lib().shift_unroll_cc(x[s0:].ctypes.data, y[s0:].ctypes.data, n, C.byref(d), phase)
+        return y, float(np.float32(phase))
+
+    @staticmethod
+    def shift_addfast_cc(x, rate=None, phase=0.0, chunk=1024, steps=None):
+        """calls of <= chunk samples like csdr.c:781-791; `steps` (9 floats: dsin[4], dcos[4], increment) overrides shift_addfast_init(rate);
+        samples a call leaves untouched (n % 4) come back as 0"""
+        x = np.ascontiguousarray(x, np.complex64); y = np.zeros_like(x); chunk = chunk or max(x.size, 1)
+        d = lib().shift_addfast_init(rate) if steps is None else _AddFast((C.c_float * 4)(*steps[0:4]), (C.c_float * 4)(*steps[4:8]), float(steps[8]))
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = lib().shift_addfast_cc(x[s0:].ctypes.data, y[s0:].ctypes.data, n, C.byref(d), phase)
         return y, float(np.float32(phase))
 
     @staticmethod
@@ -532,6 +559,35 @@ def shift_addition_bank_cc(x, rates, phases=None, chunk: int = 1024, out=None):
     scratch = _scratch(sb, xr.device)
     _check(lib().csdrb_shift_addition_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_params.data_ptr(), d_phase.data_ptr(), chunk,
                                               scratch.data_ptr(), scratch.numel(), _stream()), "shift_addition_bank_cc")
+    return out, d_phase
+
+
+def shift_addfast_init(rate: float) -> np.ndarray:
+    """9 floats: dsin[4], dcos[4], phase_increment (host; shift_addfast_data_t member order)"""
+    d = lib().shift_addfast_init(rate)
+    return np.array(list(d.dsin) + list(d.dcos) + [d.phase_increment], np.float32)
+
+
+def shift_addfast_bank_cc(x, rates=None, phases=None, chunk: int = 1024, out=None, steps=None):
+    """x: [N] (one shared wideband stream) or [C, N] complex64; one reference call per `chunk` samples.  `steps` [C, 9] overrides the
+    per-channel shift_addfast_init(rate).  Samples a call does not touch (its n % 4 tail) are 0.  Returns (y [C, N], new phases [C])."""
+    import torch
+    params = np.stack([shift_addfast_init(float(r)) for r in np.atleast_1d(np.asarray(rates, np.float32))]) if steps is None \
+        else np.ascontiguousarray(steps, np.float32).reshape(-1, 9)
+    ch = params.shape[0]
+    shared = (x.dim() == 1) if x.dtype == torch.complex64 else (x.dim() == 2)
+    xr, ptr, stride, xc, n = _as_cf32_rows(x)
+    if shared:
+        stride = 0
+    else:
+        assert xc == ch
+    d_params = torch.from_numpy(params).to(xr.device)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=xr.device) if phases is None else phases.clone()
+    if out is None:
+        out = torch.zeros((ch, n), dtype=torch.complex64, device=xr.device)
+    scratch = _scratch(lib().csdrb_shift_addition_bank_scratch_bytes(ch, n, chunk), xr.device)
+    _check(lib().csdrb_shift_addfast_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_params.data_ptr(), d_phase.data_ptr(), chunk,
+                                             scratch.data_ptr(), scratch.numel(), _stream()), "shift_addfast_bank_cc")
     return out, d_phase
 
 
@@ -707,6 +763,24 @@ def deemphasis_wfm_bank_ff(x, tau: float, sample_rate: int, last=None, out=None)
     _check(lib().csdrb_deemphasis_wfm_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, tau, sample_rate, last.data_ptr(), _stream()),
            "deemphasis_wfm_bank_ff")
     return out, last
+
+
+def deemphasis_nfm_taps(sample_rate: int):
+    """the fixed FIR deemphasis_nfm_ff uses at this rate (host table of the library), or None"""
+    n = C.c_int(0)
+    p = lib().csdrb_deemphasis_nfm_taps(sample_rate, C.byref(n))
+    return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else None
+
+
+def deemphasis_nfm_bank_ff(x, sample_rate: int, limit_max: float = 0.0, out=None):
+    """x [C, N] float32 -> y [C, N - taps] (empty when the rate has no table); limit_max > 0 clamps the input first (fused limit_ff)."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    ch, n = x.shape
+    out = torch.empty((ch, n), dtype=torch.float32, device=x.device) if out is None else out
+    rc = _check(lib().csdrb_deemphasis_nfm_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, sample_rate, limit_max, _stream()),
+                "deemphasis_nfm_bank_ff")
+    return out[:, :rc]
 
 
 class DdcBank:

@@ -279,6 +279,68 @@ int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, 
     return 1;
 }
 
+// deemphasis_nfm_ff (libcsdr.c:1101-1128): a plain "valid" FIR over a real row, out[i] = sum_t taps[t] * in[i+t] for i < n - T
+// (n - T outputs -- one fewer than a valid convolution has, exactly like the reference loop), taps picked by sample rate from the
+// four fixed tables (host/nfm_deemph_taps.h).  One CTA = 1024 outputs of one channel: the 1024+T input window is staged in shared
+// memory once (optionally clamped on the way in = the limit_ff that precedes this block in the NFM graph, README.md:87), the taps
+// ride in as a __grid_constant__ parameter (uniform-index constant loads, no device-side table), and each thread owns four outputs
+// 256 apart so that every shared read of a warp is 32 consecutive words.  Taps are accumulated in the reference's order (t ascending,
+// one accumulator per output).
+struct NfmTaps { float v[kNfmMaxTaps]; };
+
+template <bool LIMIT>
+__global__ void __launch_bounds__(256)
+nfm_deemph_bank_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride, int n, int T,
+                       const __grid_constant__ NfmTaps taps, float limit_max)
+{
+    constexpr int kTile = 1024;
+    __shared__ float win[kTile + kNfmMaxTaps];
+    const int n_out = n - T;
+    const int o0 = blockIdx.x * kTile;
+    const float* row = in + (long)blockIdx.y * in_stride;
+    for (int j = threadIdx.x; j < kTile + T; j += 256) {
+        float v = o0 + j < n ? __ldg(row + o0 + j) : 0.f;
+        if (LIMIT) v = fmaxf(-limit_max, fminf(limit_max, v));         // same expression as limit_ff_kernel (NaN -> +max)
+        win[j] = v;
+    }
+    __syncthreads();
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const float* w = win + threadIdx.x;
+#pragma unroll 4
+    for (int t = 0; t < T; t++) {
+        const float h = taps.v[t];
+        acc0 = fmaf(h, w[t], acc0);
+        acc1 = fmaf(h, w[t + 256], acc1);
+        acc2 = fmaf(h, w[t + 512], acc2);
+        acc3 = fmaf(h, w[t + 768], acc3);
+    }
+    float* orow = out + (long)blockIdx.y * out_stride;
+    const int o = o0 + threadIdx.x;
+    if (o < n_out) orow[o] = acc0;
+    if (o + 256 < n_out) orow[o + 256] = acc1;
+    if (o + 512 < n_out) orow[o + 512] = acc2;
+    if (o + 768 < n_out) orow[o + 768] = acc3;
+}
+
+// returns the number of outputs per channel (n - T), 0 when the rate has no table or the block is too short, < 0 on error
+int launch_deemphasis_nfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, int sample_rate,
+                               float limit_max, cudaStream_t st)
+{
+    int T = 0;
+    const float* h = csdrb_deemphasis_nfm_taps(sample_rate, &T);
+    if (!h || T <= 0) return 0;                                         // libcsdr.c:1119: unknown rate -> 0 samples processed
+    if (T > kNfmMaxTaps) { set_error("deemphasis_nfm: tap table longer than the kernel's window"); return -1; }
+    if (channels <= 0 || n - T <= 0) return 0;
+    if (channels > 65535) { set_error("deemphasis_nfm: more than 65535 channels in one call"); return -1; }
+    NfmTaps taps;
+    for (int t = 0; t < kNfmMaxTaps; t++) taps.v[t] = t < T ? h[t] : 0.f;
+    const dim3 grid((unsigned)((n - T + 1023) / 1024), (unsigned)channels);
+    if (limit_max > 0.f) nfm_deemph_bank_kernel<true><<<grid, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, taps, limit_max);
+    else nfm_deemph_bank_kernel<false><<<grid, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, taps, 0.f);
+    CSDRB_CUDA(cudaGetLastError());
+    return n - T;
+}
+
 // ---------------------------------------------------------------------------------------------- K6
 // The gain of block b is reference / max(peak_b, peak_{b-1}, peak_{b-2}) (capped), ramped from the gain of block b-1, applied to
 // block b-2: nothing is sequential beyond a three-block window, so the bank runs fully parallel over (channel, block):

@@ -308,6 +308,15 @@ int csdrb_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf*
     return rc < 0 ? rc : counted(0, rc);
 }
 
+int csdrb_shift_addfast_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                                const shift_addfast_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_in || !d_out || !d_params || !d_phase_io) { set_error("shift_addfast bank: null pointer"); return -1; }
+    int rc = launch_shift_addfast_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                       reinterpret_cast<const float*>(d_params), d_phase_io, chunk, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_decimating_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                                             const shift_addition_data_t* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size, void* stream)
 {
@@ -423,6 +432,15 @@ int csdrb_deemphasis_wfm_bank_ff(const float* d_in, long in_stride, float* d_out
     if (!d_in || !d_out || !d_last_io) { set_error("deemphasis_wfm bank: null pointer"); return -1; }
     int rc = launch_deemphasis_wfm_bank(d_in, in_stride, d_out, out_stride, channels, input_size, tau, sample_rate, d_last_io, S(stream));
     return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_deemphasis_nfm_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int input_size, int sample_rate,
+                                 float limit_max, void* stream)
+{
+    if (!d_in || !d_out) { set_error("deemphasis_nfm bank: null pointer"); return -1; }
+    int rc = launch_deemphasis_nfm_bank(d_in, in_stride, d_out, out_stride, channels, input_size, sample_rate, limit_max, S(stream));
+    if (rc > 0) counted(0, 1);
+    return rc;
 }
 
 size_t csdrb_ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset) { return ddc_bank_scratch_bytes(channels, input_size, chunk, offset); }
@@ -603,6 +621,31 @@ float shift_addition_cc(complexf* input, complexf* output, int input_size, shift
     A_CHECK(csdrb_shift_addition_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
                                          (const shift_addition_data_t*)g_ctx.buf[2], d_phase, input_size, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
     A_DOWN(output, 1, (size_t)input_size * 8, who);
+    float new_phase = 0.f;
+    A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return new_phase;
+}
+
+float shift_addfast_cc(complexf* input, complexf* output, int input_size, shift_addfast_data_t* d, float starting_phase)
+{
+    const char* who = "shift_addfast_cc";
+    if (input_size <= 0 || !d) return starting_phase;
+    A_BEGIN(who);
+    // slot 0: input, 1: output, 2: params (36 B) + phase at +64, 3: scratch
+    A_UP(0, input, (size_t)input_size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 8 + 16), who);
+    struct { shift_addfast_data_t p; float pad[7]; float phase; } blob;
+    blob.p = *d; blob.phase = starting_phase;
+    static_assert(offsetof(decltype(blob), phase) == 64, "phase sits at +64");
+    A_UP(2, &blob, sizeof blob, who);
+    const size_t sb = csdrb_shift_addition_bank_scratch_bytes(1, input_size, input_size);
+    A_CHECK(g_ctx.reserve(3, sb + 16), who);
+    float* d_phase = reinterpret_cast<float*>(static_cast<char*>(g_ctx.buf[2]) + 64);
+    A_CHECK(csdrb_shift_addfast_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
+                                        (const shift_addfast_data_t*)g_ctx.buf[2], d_phase, input_size, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
+    const int whole = input_size & ~3;                                  // the n%4 tail of `output` is left alone, like the reference
+    if (whole > 0) A_DOWN(output, 1, (size_t)whole * 8, who);
     float new_phase = 0.f;
     A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);
     A_SYNC(who);
@@ -795,6 +838,22 @@ float deemphasis_wfm_ff(float* input, float* output, int input_size, float tau, 
     A_DOWN(output, 1, (size_t)input_size * 4, who);
     A_SYNC(who);
     return output[input_size - 1];
+}
+
+int deemphasis_nfm_ff(float* input, float* output, int input_size, int sample_rate)
+{
+    const char* who = "deemphasis_nfm_ff";
+    int taps_length = 0;
+    if (!csdrb_deemphasis_nfm_taps(sample_rate, &taps_length)) return 0;          // libcsdr.c:1119: no table for this rate
+    if (input_size - taps_length <= 0) return 0;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_size * 4, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 4 + 16), who);
+    int produced = csdrb_deemphasis_nfm_bank_ff((const float*)g_ctx.buf[0], input_size, (float*)g_ctx.buf[1], input_size, 1, input_size, sample_rate, 0.f, g_ctx.stream);
+    A_CHECK(produced, who);
+    A_DOWN(output, 1, (size_t)produced * 4, who);
+    A_SYNC(who);
+    return produced;
 }
 
 // ---- FFT abstraction ---------------------------------------------------------------------------------

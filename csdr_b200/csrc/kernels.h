@@ -21,6 +21,12 @@ int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude
 int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, float tau, int sample_rate,
                                float* d_last_io, cudaStream_t st);
 
+// deemphasis_nfm_ff: the tap tables live in host/firdes.c (public accessor, see include/csdr_b200.h)
+constexpr int kNfmMaxTaps = 208;
+extern "C" const float* csdrb_deemphasis_nfm_taps(int sample_rate, int* taps_length);
+int launch_deemphasis_nfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, int sample_rate,
+                               float limit_max, cudaStream_t st);
+
 int launch_apply_window_rows(const float2* d_in, float2* d_out, const float* d_window, int size, long rows, cudaStream_t st);
 int launch_power(const float2* d_in_c, const float* d_in_f, float* d_out, long n, float add_db, int mode, cudaStream_t st);
 int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
@@ -33,6 +39,8 @@ void shift_unroll_bank_single(const float2* d_in, float2* d_out, int n, const fl
 size_t shift_bank_scratch_bytes(int channels, int n, int chunk);
 int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
                                const float* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                              const float* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
 int launch_decimating_shift_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
                                  const float* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size, cudaStream_t st);
 

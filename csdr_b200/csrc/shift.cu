@@ -102,6 +102,87 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
     }
 }
 
+// shift_addfast_cc (libcsdr.c:396-433, the plain-C branch): the same recursion advanced once per FOUR samples -- each group's phasors
+// are the previous group's last phasor times four fixed steps (dsin/dcos[0..3] = 1..4 increments, shift_addfast_init :307-317).
+// Same decomposition as above: a float phase chain between calls (n * phase_increment, wrapped to +-pi) and one lane per
+// (channel, call) walking its own shared-memory row.  A call only touches input_size/4 groups: the n%4 tail is not written.
+struct AddFastParams { float dsin[4], dcos[4], inc; };                 // = shift_addfast_data_t (libcsdr.h:189-194)
+
+__global__ void addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                                           int channels, int n, int chunk, int nchunks)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const float inc = params[c].inc;
+    float ph = phase_io[c];
+    for (int k = 0; k < nchunks; k++) {
+        chunk_phase[(long)c * nchunks + k] = ph;
+        const int len = min(chunk, n - k * chunk);
+        ph = wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc)));      // starting_phase += input_size * d->phase_increment  (:428)
+    }
+    phase_io[c] = ph;
+}
+
+__global__ void __launch_bounds__(128)
+shift_addfast_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                          const AddFastParams* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks)
+{
+    __shared__ float2 tile_all[4][32 * SH_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = tile_all[warp];
+    const int ch = blockIdx.y;
+    const int k0 = (blockIdx.x * 4 + warp) * 32;              // first call ("chunk") of this warp
+    if (k0 >= nchunks) return;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    float ds[4], dc[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ds[q] = params[ch].dsin[q]; dc[q] = params[ch].dcos[q]; }
+    const int k = k0 + lane;
+    const bool live = k < nchunks;
+    const int my_len = live ? (min(chunk, n - k * chunk) & ~3) : 0;   // whole groups of four only
+    float c = 0.f, s = 0.f;
+    if (live) {
+        const double ph = (double)chunk_phase[(long)ch * nchunks + k];
+        c = (float)cos(ph); s = (float)sin(ph);
+    }
+    const int rows = min(32, nchunks - k0);
+    const int max_len = min(chunk, n - k0 * chunk);          // the first call of the warp is never the short one
+    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * chunk + t0 + lane;
+            const int len_r = min(chunk, n - (k0 + r) * chunk);
+            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+        if (live) {
+            float2* row = tile + lane * SH_PITCH;
+            const int steps = min(SH_TILE, my_len - t0);     // a multiple of 4 (SH_TILE is), <= 0 past the end of a short call
+            for (int j = 0; j < steps; j += 4) {
+                float cg[4], sg[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    cg[q] = __fsub_rn(__fmul_rn(c, dc[q]), __fmul_rn(s, ds[q]));
+                    sg[q] = __fadd_rn(__fmul_rn(s, dc[q]), __fmul_rn(c, ds[q]));
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float2 v = row[j + q];
+                    row[j + q] = make_float2(__fsub_rn(__fmul_rn(cg[q], v.x), __fmul_rn(sg[q], v.y)), __fadd_rn(__fmul_rn(sg[q], v.x), __fmul_rn(cg[q], v.y)));
+                }
+                c = cg[3]; s = sg[3];
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * chunk + t0 + lane;
+            const int len_r = min(chunk, n - (k0 + r) * chunk) & ~3;
+            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
+        }
+        __syncwarp();
+    }
+}
+
 // decimating variant: status per channel {decimation_remain, starting_phase, output_size} (libcsdr_gpl.h:39-44)
 __global__ void dshift_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                               const float3* __restrict__ params, int n, int decimation, int* __restrict__ remain_io,
@@ -197,6 +278,24 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, reinterpret_cast<const float3*>(d_params), chunk_phase, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
+                              const float* d_params /*[C][9] dsin[4],dcos[4],phase_increment*/, float* d_phase_io, int chunk,
+                              void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if (chunk <= 0 || chunk > n) chunk = n;
+    const int nchunks = (n + chunk - 1) / chunk;
+    if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addfast bank: scratch too small"); return -1; }
+    float* chunk_phase = static_cast<float*>(d_scratch);
+    const AddFastParams* params = reinterpret_cast<const AddFastParams*>(d_params);
+    addfast_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    dim3 grid((nchunks + 127) / 128, channels);
+    shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);
     CSDRB_CUDA(cudaGetLastError());
     return 2;
 }

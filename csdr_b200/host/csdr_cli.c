@@ -265,6 +265,53 @@ static int cmd_shift_unroll_cc(int argc, char **argv)                      /* cs
     }
 }
 
+static int cmd_shift_addfast_cc(int argc, char **argv)                     /* csdr.c:749-798 */
+{
+    G.wideband = 1;
+    float phase = 0, rate = 0;
+    int ctl = open_control(argc, argv);
+    if (ctl) { while (!poll_control(ctl, "%g\n", &rate)) usleep(10000); }
+    else { if (argc <= 2) return complain("need required parameter (rate)"); sscanf(argv[2], "%g", &rate); }
+    if (!announce_block(open_block())) return -2;
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block), *out = must_alloc(sizeof(complexf) * (size_t)block);
+    for (;;) {
+        shift_addfast_data_t steps = shift_addfast_init(rate);
+        who(); fprintf(stderr, "reinitialized to %g\n", rate);
+        for (;;) {
+            if (feof(stdin)) return 0;
+            if (!fread(in, sizeof(complexf), (size_t)block, stdin)) break;
+            for (int done = 0; done < block;) {
+                int n = block - done > 1024 ? 1024 : block - done;
+                phase = shift_addfast_cc(in + done, out + done, n, &steps, phase);
+                done += n;
+            }
+            fwrite(out, sizeof(complexf), (size_t)block, stdout);
+            if (poll_control(ctl, "%g\n", &rate)) break;
+            end_of_block();
+        }
+    }
+}
+
+static int cmd_decimating_shift_addition_cc(int argc, char **argv)         /* csdr.c:851-875 */
+{
+    G.wideband = 1;
+    if (argc <= 2) return complain("need required parameter (rate)");
+    float rate = 0; sscanf(argv[2], "%g", &rate);
+    int decimation = 1; if (argc > 3) sscanf(argv[3], "%d", &decimation);
+    if (!open_block()) return -2;
+    announce_block(block / decimation);
+    shift_addition_data_t nco = decimating_shift_addition_init(rate, decimation);
+    decimating_shift_addition_status_t st = {0, 0.f, 0};
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block), *out = must_alloc(sizeof(complexf) * (size_t)block);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        if (!fread(in, sizeof(complexf), (size_t)block, stdin)) return 0;
+        st = decimating_shift_addition_cc(in, out, block, nco, decimation, st);
+        fwrite(out, sizeof(complexf), (size_t)st.output_size, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_fft_cc(int argc, char **argv)                               /* csdr.c:1569-1643 (binary output; --octave is not part of this build) */
 {
     if (argc <= 3) return complain("need required parameters (fft_size, out_of_every_n_samples)");
@@ -359,6 +406,26 @@ static int cmd_deemphasis_wfm_ff(int argc, char **argv)                     /* c
         fread(in, sizeof(float), (size_t)block, stdin);
         last = deemphasis_wfm_ff(in, out, block, tau, sample_rate, last);
         fwrite(out, sizeof(float), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_deemphasis_nfm_ff(int argc, char **argv)                     /* csdr.c:1068-1087 */
+{
+    if (argc <= 2) return complain("need required parameter (sample rate)");
+    int sample_rate = 0; sscanf(argv[2], "%d", &sample_rate);
+    if (!announce_block(open_block())) return -2;
+    /* The reference filters its still-unread buffer once before the first read (processed starts at 0, :1075-1079), so the stream
+     * is effectively prefixed by one block of whatever malloc returned -- zeros in practice, zeros by construction here. */
+    float *in = must_alloc(sizeof(float) * (size_t)block), *out = must_alloc(sizeof(float) * (size_t)block);
+    int produced = 0;
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in + block - produced, sizeof(float), (size_t)produced, stdin);
+        produced = deemphasis_nfm_ff(in, out, block, sample_rate);
+        if (!produced) return complain("deemphasis_nfm_ff: invalid sample rate (this function works only with specific sample rates).");
+        memmove(in, in + produced, sizeof(float) * (size_t)(block - produced));
+        fwrite(out, sizeof(float), (size_t)produced, stdout);
         end_of_block();
     }
 }
@@ -558,10 +625,13 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
     {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
     {"shift_unroll_cc", cmd_shift_unroll_cc, "shift_unroll_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
+    {"shift_addfast_cc", cmd_shift_addfast_cc, "shift_addfast_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
+    {"decimating_shift_addition_cc", cmd_decimating_shift_addition_cc, "decimating_shift_addition_cc <rate> [decimation]"},
     {"fft_cc", cmd_fft_cc, "fft_cc <fft_size> <out_of_every_n_samples> [window]"},
     {"logpower_cf", cmd_logpower_cf, "logpower_cf [add_db]"},
     {"logaveragepower_cf", cmd_logaveragepower_cf, "logaveragepower_cf <add_db> <fft_size> <avgnumber>"},
     {"deemphasis_wfm_ff", cmd_deemphasis_wfm_ff, "deemphasis_wfm_ff <sample_rate> <tau>"},
+    {"deemphasis_nfm_ff", cmd_deemphasis_nfm_ff, "deemphasis_nfm_ff <one_of_the_predefined_sample_rates>"},
     {"bandpass_fir_fft_cc", cmd_bandpass_fir_fft_cc, "bandpass_fir_fft_cc <low_cut> <high_cut> <transition_bw> [window] | --fifo <fifo_path> <transition_bw> [window]"},
     {"fastddc_fwd_cc", cmd_fastddc_fwd_cc, "fastddc_fwd_cc <decimation> [transition_bw [window]]"},
     {"fastddc_inv_cc", cmd_fastddc_inv_cc, "fastddc_inv_cc <shift_rate> <decimation> [transition_bw [window]] | --fifo <fifo_path> ... | --fd <fd> ..."},

@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include "nfm_deemph_taps.h"
 
 #define PI_F ((float)3.14159265358979323846)     /* libcsdr.h:65: PI is a float constant */
 
@@ -126,6 +127,33 @@ shift_addition_data_t shift_addition_init(float rate)
 shift_addition_data_t decimating_shift_addition_init(float rate, int decimation)
 {
     return shift_addition_init(rate * decimation);
+}
+
+/* ---- shift_addfast steps (libcsdr.c:307-317): the phasor after 1..4 increments ---------------------------------- */
+shift_addfast_data_t shift_addfast_init(float rate)
+{
+    shift_addfast_data_t d;
+    d.phase_increment = 2 * rate * PI_F;
+    for (int k = 0; k < 4; k++) {
+        const float angle = d.phase_increment * (k + 1);
+        d.dsin[k] = (float)sin((double)angle);
+        d.dcos[k] = (float)cos((double)angle);
+    }
+    return d;
+}
+
+/* ---- fixed NFM de-emphasis FIRs (libcsdr.c:1099-1119 picks one by sample rate; tables: nfm_deemph_taps.h) ---------- */
+const float *csdrb_deemphasis_nfm_taps(int sample_rate, int *taps_length)
+{
+    static const struct { int rate; const float *taps; int length; } table[] = {
+        {48000, kNfmDeemph48000, (int)(sizeof kNfmDeemph48000 / sizeof(float))},
+        {44100, kNfmDeemph44100, (int)(sizeof kNfmDeemph44100 / sizeof(float))},
+        {8000, kNfmDeemph8000, (int)(sizeof kNfmDeemph8000 / sizeof(float))},
+        {11025, kNfmDeemph11025, (int)(sizeof kNfmDeemph11025 / sizeof(float))}};
+    for (size_t k = 0; k < sizeof table / sizeof table[0]; k++)
+        if (table[k].rate == sample_rate) { if (taps_length) *taps_length = table[k].length; return table[k].taps; }
+    if (taps_length) *taps_length = 0;
+    return NULL;
 }
 
 /* ---- window table and shift_unroll table (libcsdr.c:1256-1267, 283-299): one-off host work ------------ */

@@ -87,6 +87,9 @@ void fastagc_ff(fastagc_ff_t *input, float *output);
 /* audio tail of the WFM graph, SURVEY 8(f) rank 1 (libcsdr.h:100-105; libcsdr.c:1081-1097, 1130-1137) */
 float deemphasis_wfm_ff(float *input, float *output, int input_size, float tau, int sample_rate, float last_output);
 void  limit_ff(float *input, float *output, int input_size, float max_amplitude);
+/* NFM audio tail (libcsdr.h:106; libcsdr.c:1099-1128, tables predefined.h:56-68): fixed FIR chosen by sample rate
+ * (48000, 44100, 11025, 8000); returns the number of outputs = input_size - taps_length, 0 for any other rate */
+int   deemphasis_nfm_ff(float *input, float *output, int input_size, int sample_rate);
 
 /* spectrum side path and shift_unroll, SURVEY 8(f) ranks 3-4 (libcsdr.h:142-149, 199-207; libcsdr.c:1245-1276, 1296-1314, 283-320) */
 float *precalculate_window(int size, window_t window);                                   /* host table, malloc'ed like the reference's */
@@ -98,6 +101,11 @@ void  log_ff(float *input, float *output, int size, float add_db);
 typedef struct shift_unroll_data_s { float *dsin; float *dcos; float phase_increment; int size; } shift_unroll_data_t;
 shift_unroll_data_t shift_unroll_init(float rate, int size);
 float shift_unroll_cc(complexf *input, complexf *output, int input_size, shift_unroll_data_t *d, float starting_phase);
+/* shift_addfast (libcsdr.h:189-197; libcsdr.c:307-317, 396-433): recursion advanced once per four samples; only input_size/4*4
+ * samples of `output` are written, like the reference */
+typedef struct shift_addfast_data_s { float dsin[4]; float dcos[4]; float phase_increment; } shift_addfast_data_t;
+shift_addfast_data_t shift_addfast_init(float rate);
+float shift_addfast_cc(complexf *input, complexf *output, int input_size, shift_addfast_data_t *d, float starting_phase);
 
 /* FFT abstraction (fft_fftw.h:10-27; fft_fftw.c:6-46).  Callers read ->size/->input/->output directly
  * (libcsdr.c:822-835, fastddc.c:112-116), so the first three members keep the reference layout. */
@@ -207,12 +215,25 @@ int csdrb_limit_ff(const float *d_in, float *d_out, long n, float max_amplitude,
 int csdrb_deemphasis_wfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
                                  float tau, int sample_rate, float *d_last_io, void *stream);
 
+/* NFM de-emphasis bank: every row through the fixed FIR of `sample_rate`; returns outputs per row (input_size - taps_length),
+ * 0 when the rate has no table.  limit_max > 0 fuses the preceding `limit_ff limit_max` of the NFM graph (README.md:87) into the load.
+ * csdrb_deemphasis_nfm_taps() exposes the (host) table: NULL / *taps_length = 0 for an unknown rate. */
+int csdrb_deemphasis_nfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
+                                 int sample_rate, float limit_max, void *stream);
+const float *csdrb_deemphasis_nfm_taps(int sample_rate, int *taps_length);
+
 /* spectrum side path on device buffers: `rows` frames of `size` values share one window table; power modes as the reference's
  * logpower_cf / accumulate_power_cf (d_out is read-modify-write) / log_ff */
 int csdrb_apply_window_rows_c(const complexf *d_in, complexf *d_out, const float *d_window, int size, long rows, void *stream);
 int csdrb_logpower_cf(const complexf *d_in, float *d_out, long n, float add_db, void *stream);
 int csdrb_accumulate_power_cf(const complexf *d_in, float *d_acc, long n, void *stream);
 int csdrb_log_ff(const float *d_in, float *d_out, long n, float add_db, void *stream);
+/* shift_addfast_cc bank: d_params[c] = shift_addfast_init(rate_c); one reference call per `chunk` samples (csdr.c:781-791 uses 1024);
+ * scratch as for the shift_addition bank (csdrb_shift_addition_bank_scratch_bytes) */
+int csdrb_shift_addfast_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
+                                const shift_addfast_data_t *d_params, float *d_phase_io, int chunk, void *d_scratch, size_t scratch_bytes,
+                                void *stream);
+
 /* shift_unroll_cc bank: d_params as for the shift_addition bank (shift_addition_init(rate_c): its .rate is the same 2*rate), tables
  * d_dsin/d_dcos [channels][table_stride] from shift_unroll_init(rate_c, table_size); one reference call per table_size samples */
 int csdrb_shift_unroll_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,

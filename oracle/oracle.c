@@ -323,6 +323,21 @@ float oracle_deemphasis_wfm_ff(const float *in, float *out, int n, float tau, in
     return n > 0 ? out[n - 1] : last_output;
 }
 
+/* [ref libcsdr.c:1101-1128] fixed-FIR NFM de-emphasis: out[i] = sum_t taps[t]*in[i+t] for i < n - taps_length, returns that count.
+ * The reference picks `taps` by sample rate from predefined.h:56-68; the oracle takes them as an argument (tests pass the tables
+ * read out of the compiled reference / the golden fixture) so that the product's own copy of the tables is checked, not trusted. */
+int oracle_deemphasis_nfm_ff(const float *in, float *out, int n, const float *taps, int taps_length)
+{
+    if (taps_length <= 0) return 0;
+    int i;
+    for (i = 0; i < n - taps_length; i++) {
+        float acc = 0;
+        for (int t = 0; t < taps_length; t++) acc += taps[t] * in[i + t];
+        out[i] = acc;
+    }
+    return i;
+}
+
 /* [ref libcsdr.c:1130-1137] clamp to +-max_amplitude.  The reference's own build flags (-ffast-math) compile the two selects to
  * minss/maxss, which return the non-NaN operand: a NaN sample leaves as +max_amplitude in every shipped libcsdr (verified against
  * oracle/_ref), so that is what we pin (the strict C expression would pass the NaN through). */
@@ -401,6 +416,40 @@ float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *ds
         out[k].q = s * in[k].i + c * in[k].q;
     }
     return wrap_pm_pi(starting_phase + n * phase_increment);
+}
+
+/* [ref libcsdr.c:307-317] shift_addfast_init: the phasor after 1..4 steps of phase_increment = 2*rate*PI (float), each angle a float
+ * product, sin/cos in double rounded to float.  out9 = dsin[4], dcos[4], phase_increment (libcsdr.h:189-194 member order). */
+void oracle_shift_addfast_init(float rate, float *out9)
+{
+    float inc = 2 * rate * kPi;
+    for (int k = 0; k < 4; k++) {
+        out9[k] = (float)sin((double)(inc * (k + 1)));
+        out9[4 + k] = (float)cos((double)(inc * (k + 1)));
+    }
+    out9[8] = inc;
+}
+
+/* [ref libcsdr.c:396-433, the plain-C branch every non-NEON build takes] groups of four samples: each group's four phasors come from
+ * the LAST phasor of the previous group times the four fixed steps; the recursion therefore advances once per four samples.  Only
+ * input_size/4 groups are touched (a tail of input_size%4 samples is left as it was); the float phase moves by input_size*increment. */
+float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d9, float starting_phase)
+{
+    float c0 = (float)cos((double)starting_phase), s0 = (float)sin((double)starting_phase);
+    for (int g = 0; g < n / 4; g++) {
+        float c[4], s[4];
+        for (int j = 0; j < 4; j++) {
+            c[j] = c0 * d9[4 + j] - s0 * d9[j];
+            s[j] = s0 * d9[4 + j] + c0 * d9[j];
+        }
+        for (int j = 0; j < 4; j++) {
+            const ocf32 v = in[4 * g + j];
+            out[4 * g + j].i = c[j] * v.i - s[j] * v.q;
+            out[4 * g + j].q = s[j] * v.i + c[j] * v.q;
+        }
+        c0 = c[3]; s0 = s[3];
+    }
+    return wrap_pm_pi(starting_phase + n * d9[8]);
 }
 
 /* ------------------------------------------------------------------------------------------------

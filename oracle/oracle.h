@@ -73,6 +73,7 @@ void oracle_fastagc_ff(oracle_fastagc_t *st, float *hist1, float *hist2, const f
 /* audio tail of the WFM/NFM graphs: libcsdr.c:1081-1097 (1-pole de-emphasis IIR), 1130-1137 (hard limiter) */
 float oracle_deemphasis_wfm_ff(const float *in, float *out, int n, float tau, int sample_rate, float last_output);
 void  oracle_limit_ff(const float *in, float *out, int n, float max_amplitude);
+int   oracle_deemphasis_nfm_ff(const float *in, float *out, int n, const float *taps, int taps_length);   /* libcsdr.c:1101-1128 */
 
 /* spectrum side path + shift_unroll: libcsdr.c:1245-1276 (windows), 1296-1314 (log power),
  * 283-315 (shift_unroll_init / shift_unroll_cc) */
@@ -83,6 +84,10 @@ void  oracle_accumulate_power_cf(const ocf32 *in, float *acc, int size);
 void  oracle_log_ff(const float *in, float *out, int size, float add_db);
 float oracle_shift_unroll_init(float rate, int size, float *dsin, float *dcos);            /* returns phase_increment */
 float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *dsin, const float *dcos, float phase_increment, float starting_phase);
+
+/* shift_addfast: libcsdr.h:189-197, libcsdr.c:307-317, 396-433.  d9 = dsin[4], dcos[4], phase_increment */
+void  oracle_shift_addfast_init(float rate, float *d9);
+float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d9, float starting_phase);
 
 /* mathematical DFT in float64, rounded once to float (stands in for FFTW3f; fft_fftw.c:6-41) */
 void oracle_dft_c2c(const ocf32 *in, ocf32 *out, int n, int forward);

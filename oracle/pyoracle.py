@@ -101,6 +101,7 @@ class Oracle:
         L.oracle_deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
         L.oracle_deemphasis_wfm_ff.restype = C.c_float
         L.oracle_limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
+        L.oracle_deemphasis_nfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int]
         fp = C.POINTER(C.c_float)
         L.oracle_precalculate_window.argtypes = [fp, C.c_int, C.c_int]
         L.oracle_apply_precalculated_window_c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp]
@@ -110,6 +111,8 @@ class Oracle:
         L.oracle_shift_unroll_init.argtypes = [C.c_float, C.c_int, fp, fp]; L.oracle_shift_unroll_init.restype = C.c_float
         L.oracle_shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, fp, C.c_float, C.c_float]
         L.oracle_shift_unroll_cc.restype = C.c_float
+        L.oracle_shift_addfast_init.argtypes = [C.c_float, fp]
+        L.oracle_shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, C.c_float]; L.oracle_shift_addfast_cc.restype = C.c_float
         L.oracle_dft_c2c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int]
         L.oracle_apply_fir_fft_cc.argtypes = [C.POINTER(_CF)] * 3 + [C.c_int, C.POINTER(_CF), C.c_int]
         L.oracle_fastddc_init.argtypes = [C.POINTER(self._Ddc), C.c_float, C.c_int, C.c_float]
@@ -207,6 +210,11 @@ class Oracle:
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
         self.L.oracle_limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
 
+    def deemphasis_nfm_ff(self, x, taps):
+        x = np.ascontiguousarray(x, np.float32); taps = np.ascontiguousarray(taps, np.float32); y = np.empty_like(x)
+        n = self.L.oracle_deemphasis_nfm_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, _p(taps, C.c_float), taps.size)
+        return y[:n].copy()
+
     # ---- spectrum side path, shift_unroll
     def precalculate_window(self, size, window="HAMMING"):
         w = np.empty(size, np.float32); self.L.oracle_precalculate_window(_p(w, C.c_float), size, WINDOWS[window]); return w
@@ -237,6 +245,17 @@ class Oracle:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = self.L.oracle_shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, _p(ds, C.c_float), _p(dc, C.c_float), inc, phase)
+        return y, float(np.float32(phase))
+
+    def shift_addfast_init(self, rate):
+        d = np.empty(9, np.float32); self.L.oracle_shift_addfast_init(rate, _p(d, C.c_float)); return d
+
+    def shift_addfast_cc(self, x, rate, phase=0.0, chunk=1024):
+        """calls of <= chunk samples like csdr.c:781-791; samples a call leaves untouched (n % 4) come back as 0"""
+        x = _c64(x); y = np.zeros_like(x); d = self.shift_addfast_init(rate); chunk = chunk or max(x.size, 1)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = self.L.oracle_shift_addfast_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, _p(d, C.c_float), phase)
         return y, float(np.float32(phase))
 
     # ---- FFT family
@@ -343,6 +362,9 @@ class Ref:
     class _Unroll(C.Structure):             # libcsdr.h:199-205
         _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
+    class _AddFast(C.Structure):            # libcsdr.h:189-194
+        _fields_ = [("dsin", C.c_float * 4), ("dcos", C.c_float * 4), ("phase_increment", C.c_float)]
+
     class _Plan(C.Structure):               # fft_fftw.h:14-20
         _fields_ = [("size", C.c_int), ("input", C.c_void_p), ("output", C.c_void_p), ("plan", C.c_void_p)]
 
@@ -376,6 +398,7 @@ class Ref:
         L.deemphasis_wfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_int, C.c_float]
         L.deemphasis_wfm_ff.restype = C.c_float
         L.limit_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_float]
+        L.deemphasis_nfm_ff.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_int]
         fp = C.POINTER(C.c_float)
         L.precalculate_window.argtypes = [C.c_int, C.c_int]; L.precalculate_window.restype = fp
         L.apply_precalculated_window_c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp]
@@ -384,6 +407,8 @@ class Ref:
         L.log_ff.argtypes = [fp, fp, C.c_int, C.c_float]
         L.shift_unroll_init.argtypes = [C.c_float, C.c_int]; L.shift_unroll_init.restype = self._Unroll
         L.shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
+        L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = self._AddFast
+        L.shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
         L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
         L.fft_execute.argtypes = [C.POINTER(self._Plan)]
         L.fft_destroy.argtypes = [C.POINTER(self._Plan)]
@@ -476,6 +501,23 @@ class Ref:
         x = np.ascontiguousarray(x, np.float32); y = np.empty_like(x)
         self.L.limit_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, max_amplitude); return y
 
+    NFM_RATES = (48000, 44100, 11025, 8000)
+
+    def deemphasis_nfm_ff(self, x, sample_rate):
+        x = np.ascontiguousarray(x, np.float32); y = np.zeros_like(x)
+        n = self.L.deemphasis_nfm_ff(_p(x, C.c_float), _p(y, C.c_float), x.size, sample_rate)
+        return y[:n].copy()
+
+    def deemphasis_nfm_taps(self, sample_rate):
+        """the table the compiled reference exports for this rate (length from the ELF symbol size)"""
+        import re, subprocess
+        for line in subprocess.check_output(["nm", "-S", "--defined-only", self.L._name], text=True).splitlines():
+            m = re.match(r"^[0-9a-f]+ ([0-9a-f]+) D deemphasis_nfm_predefined_fir_%d$" % sample_rate, line)
+            if m:
+                n = int(m.group(1), 16) // 4
+                return np.array((C.c_float * n).in_dll(self.L, "deemphasis_nfm_predefined_fir_%d" % sample_rate), np.float32)
+        return None
+
     def precalculate_window(self, size, window="HAMMING"):
         p = self.L.precalculate_window(size, WINDOWS[window]); return np.ctypeslib.as_array(p, shape=(size,)).copy()
 
@@ -504,6 +546,16 @@ class Ref:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = self.L.shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
+        return y, float(np.float32(phase))
+
+    def shift_addfast_init(self, rate):
+        d = self.L.shift_addfast_init(rate); return np.array(list(d.dsin) + list(d.dcos) + [d.phase_increment], np.float32)
+
+    def shift_addfast_cc(self, x, rate, phase=0.0, chunk=1024):
+        x = _c64(x); y = np.zeros_like(x); d = self.L.shift_addfast_init(rate); chunk = chunk or max(x.size, 1)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = self.L.shift_addfast_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
         return y, float(np.float32(phase))
 
     def dft(self, x, forward=True):

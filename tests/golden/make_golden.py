@@ -106,6 +106,18 @@ def main():
     spectra = r.fastddc_fwd(g["ddc_in"], ddc)
     g["ddc_fwd_out"] = np.stack(spectra)
     g["ddc_inv_out"] = r.fastddc_inv(spectra, 0.05, 8, 0.123, "HAMMING")
+    # --- NFM audio tail (8f rank 1): the four fixed de-emphasis FIRs (tables as the compiled reference exports them) on one input;
+    #     own generator so that the arrays above keep their values
+    rng2 = np.random.default_rng(20260923)
+    g["nfm_in"] = rng2.uniform(-1.0, 1.0, 3000).astype(np.float32)
+    for sr in r.NFM_RATES:
+        g[f"nfm_taps_{sr}"] = r.deemphasis_nfm_taps(sr)
+        g[f"nfm_out_{sr}"] = r.deemphasis_nfm_ff(g["nfm_in"], sr)
+    # --- shift_addfast_cc (8f rank 3): the reference build's own step table (its init goes through libmvec sinf/cosf under
+    #     -ffast-math, up to 1 ulp off the correctly rounded value) and the stream it produces from it in 1024-sample calls
+    g["addfast_steps"] = r.shift_addfast_init(-0.085)
+    y, ph = r.shift_addfast_cc(g["shift_in"], -0.085, 0.0, 1024)
+    g["addfast_out"], g["addfast_phase"] = y, np.float32(ph)
     out = Path(__file__).with_name("hotpath_golden.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out} ({out.stat().st_size} bytes, {len(g)} arrays)")

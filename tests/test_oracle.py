@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from oracle.pyoracle import rel_rms
+from oracle.pyoracle import have_ref, rel_rms
 
 GOLD = np.load(Path(__file__).parent / "golden" / "hotpath_golden.npz")
 TIGHT = 1e-6
@@ -95,6 +95,52 @@ def test_ref_audio_tail(oracle, ref):
     for tau, fs, last, blk in ((50e-6, 48000, 0.0, 1024), (75e-6, 240000, float("nan"), None), (50e-6, 44100, 0.3, 4096)):
         ya, la = oracle.deemphasis_wfm_ff(x, tau, fs, last, blk); yb, lb = ref.deemphasis_wfm_ff(x, tau, fs, last, blk)
         assert np.array_equal(ya, yb) and np.float32(la) == np.float32(lb)
+
+
+def test_golden_and_ref_deemphasis_nfm(oracle):
+    """8(f) rank 1: the oracle's FIR on the tables the compiled reference exports (golden copies) reproduces the reference's outputs;
+    when oracle/_ref is built here, also live and on the tables read straight out of it."""
+    for rate in (48000, 44100, 11025, 8000):
+        taps = GOLD[f"nfm_taps_{rate}"]
+        assert taps.size == {48000: 201, 44100: 123, 11025: 81, 8000: 81}[rate]
+        y = oracle.deemphasis_nfm_ff(GOLD["nfm_in"], taps)
+        assert y.size == GOLD["nfm_in"].size - taps.size and rel_rms(y, GOLD[f"nfm_out_{rate}"]) < 1e-6
+    assert oracle.deemphasis_nfm_ff(GOLD["nfm_in"][:201], GOLD["nfm_taps_48000"]).size == 0
+    if have_ref():
+        from oracle.pyoracle import Ref
+        r = Ref()
+        x = np.random.default_rng(4).uniform(-1, 1, 20_000).astype(np.float32)
+        for rate in r.NFM_RATES:
+            assert np.array_equal(r.deemphasis_nfm_taps(rate), GOLD[f"nfm_taps_{rate}"])
+            assert rel_rms(oracle.deemphasis_nfm_ff(x, GOLD[f"nfm_taps_{rate}"]), r.deemphasis_nfm_ff(x, rate)) < 1e-6
+        assert r.deemphasis_nfm_ff(x, 22050).size == 0
+
+
+def test_golden_and_ref_shift_addfast(oracle):
+    """8(f) rank 3: given the reference's step table the oracle's recursion is bit-exact; the strict init is within 1 ulp of the
+    reference build's (whose -ffast-math init goes through libmvec), which the 256-step recursion turns into < 1e-5 per 1024-call."""
+    import ctypes as C
+    from oracle.pyoracle import _CF, _p
+    x = GOLD["shift_in"]; y = np.zeros_like(x); ph = 0.0
+    steps = np.ascontiguousarray(GOLD["addfast_steps"])
+    for s0 in range(0, x.size, 1024):
+        ph = oracle.L.oracle_shift_addfast_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), min(1024, x.size - s0), _p(steps, C.c_float), ph)
+    assert np.array_equal(y, GOLD["addfast_out"]) and np.float32(ph) == GOLD["addfast_phase"]
+    mine = oracle.shift_addfast_init(-0.085)
+    assert np.abs(mine.view(np.int32) - steps.view(np.int32)).max() <= 1 and mine[8] == steps[8]
+    y2, ph2 = oracle.shift_addfast_cc(x, -0.085, 0.0, 1024)
+    assert rel_rms(y2, GOLD["addfast_out"]) < 1e-5 and np.float32(ph2) == GOLD["addfast_phase"]
+    if have_ref():
+        from oracle.pyoracle import Ref
+        r = Ref()
+        z = (np.random.default_rng(8).standard_normal(20_000) + 1j * np.random.default_rng(9).standard_normal(20_000)).astype(np.complex64)
+        for rate in (0.25, 0.125):                                        # rates where both inits agree: only a call's seed can differ by
+            assert np.array_equal(oracle.shift_addfast_init(rate), r.shift_addfast_init(rate))     # an ulp (the -ffast-math build seeds with sincosf)
+            for chunk in (1024, 4096, None):
+                a, pa = oracle.shift_addfast_cc(z, rate, 0.3, chunk); b, pb = r.shift_addfast_cc(z, rate, 0.3, chunk)
+                assert rel_rms(a, b) < 1e-7 and pa == pb, (rate, chunk)
+        a, pa = oracle.shift_addfast_cc(z, 0.25, -1.0, 1022); b, pb = r.shift_addfast_cc(z, 0.25, -1.0, 1022)    # n % 4 tails stay untouched
+        assert rel_rms(a, b) < 1e-6 and pa == pb and np.all(a[1020:1022] == 0) and np.all(b[1020:1022] == 0)
 
 
 def test_golden_spectrum_and_unroll(oracle, ref=None):

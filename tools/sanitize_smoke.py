@@ -25,4 +25,8 @@ for D, bw in ((50, 0.005), (10, 0.0201), (10, 0.05)):
     T = cb.firdes_filter_len(bw)
     for demod in (True, False): cb.ddc_bank(cplx(40000 + 14), np.linspace(-0.4, 0.4, 37), D, cb.firdes_lowpass_f(T, 0.5 / D), demod=demod, chunk=1024, offset=100)
 x = rng.integers(0, 256, 5000).astype(np.uint8); cb.libcsdr.convert_u8_f(x); cb.libcsdr.fir_decimate_cc(rng.normal(size=4000).astype(np.complex64), 10, taps)
+for sr in (48000, 44100, 11025, 8000):
+    for n in (202, 1024 + 201, 1024 + 202, 5000): cb.deemphasis_nfm_bank_ff(a[:, :n], sr, limit_max=0.5 if n & 1 else 0.0)
+cb.shift_addfast_bank_cc(cplx(16384 + 777), [0.1, -0.3, 0.45], chunk=1024); cb.shift_addfast_bank_cc(cplx(3, 1001), [0.1, -0.3, 0.45], chunk=37)
+cb.libcsdr.shift_addfast_cc(rng.normal(size=1022).astype(np.complex64), 0.2); cb.libcsdr.deemphasis_nfm_ff(rng.normal(size=3000).astype(np.float32), 48000)
 torch.cuda.synchronize(); print("sanitize_smoke: all kernels ran")
