@@ -131,6 +131,7 @@ def lib() -> C.CDLL:
     L.deemphasis_nfm_ff.argtypes = [vp, vp, it, it]
     L.csdrb_deemphasis_nfm_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp]
     L.csdrb_deemphasis_nfm_taps.argtypes = [it, C.POINTER(it)]; L.csdrb_deemphasis_nfm_taps.restype = C.POINTER(C.c_float)
+    L.csdrb_fir_valid_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.POINTER(C.c_float), it, C.c_float, vp]
     L.deemphasis_wfm_ff.argtypes = [vp, vp, it, C.c_float, it, C.c_float]; L.deemphasis_wfm_ff.restype = C.c_float
     L.csdrb_fastddc_fwd_cc.argtypes = [vp, vp, vp, it, it, it, vp]
     L.csdrb_fastddc_inv_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastddc_inv_bank_scratch_bytes.restype = sz
@@ -780,6 +781,18 @@ def deemphasis_nfm_bank_ff(x, sample_rate: int, limit_max: float = 0.0, out=None
     out = torch.empty((ch, n), dtype=torch.float32, device=x.device) if out is None else out
     rc = _check(lib().csdrb_deemphasis_nfm_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, sample_rate, limit_max, _stream()),
                 "deemphasis_nfm_bank_ff")
+    return out[:, :rc]
+
+
+def fir_valid_bank_ff(x, taps, limit_max: float = 0.0, out=None):
+    """x [C, N] float32, taps (host, <= 208) -> y [C, N - taps]: the de-emphasis FIR kernel with caller-supplied taps."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    taps = np.ascontiguousarray(taps, np.float32)
+    ch, n = x.shape
+    out = torch.empty((ch, n), dtype=torch.float32, device=x.device) if out is None else out
+    rc = _check(lib().csdrb_fir_valid_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, n, _fp(taps), taps.size, limit_max, _stream()),
+                "fir_valid_bank_ff")
     return out[:, :rc]
 
 

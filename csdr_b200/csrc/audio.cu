@@ -322,23 +322,31 @@ nfm_deemph_bank_kernel(const float* __restrict__ in, long in_stride, float* __re
     if (o + 768 < n_out) orow[o + 768] = acc3;
 }
 
-// returns the number of outputs per channel (n - T), 0 when the rate has no table or the block is too short, < 0 on error
-int launch_deemphasis_nfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, int sample_rate,
-                               float limit_max, cudaStream_t st)
+// returns the number of outputs per channel (n - T), 0 when the block is too short, < 0 on error
+int launch_fir_valid_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, const float* h_taps, int T,
+                          float limit_max, cudaStream_t st)
 {
-    int T = 0;
-    const float* h = csdrb_deemphasis_nfm_taps(sample_rate, &T);
-    if (!h || T <= 0) return 0;                                         // libcsdr.c:1119: unknown rate -> 0 samples processed
-    if (T > kNfmMaxTaps) { set_error("deemphasis_nfm: tap table longer than the kernel's window"); return -1; }
+    if (!h_taps || T <= 0) { set_error("fir_valid bank: no taps"); return -1; }
+    if (T > kNfmMaxTaps) { set_error("fir_valid bank: more than %d taps", kNfmMaxTaps); return -1; }
     if (channels <= 0 || n - T <= 0) return 0;
-    if (channels > 65535) { set_error("deemphasis_nfm: more than 65535 channels in one call"); return -1; }
+    if (channels > 65535) { set_error("fir_valid bank: more than 65535 channels in one call"); return -1; }
     NfmTaps taps;
-    for (int t = 0; t < kNfmMaxTaps; t++) taps.v[t] = t < T ? h[t] : 0.f;
+    for (int t = 0; t < kNfmMaxTaps; t++) taps.v[t] = t < T ? h_taps[t] : 0.f;
     const dim3 grid((unsigned)((n - T + 1023) / 1024), (unsigned)channels);
     if (limit_max > 0.f) nfm_deemph_bank_kernel<true><<<grid, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, taps, limit_max);
     else nfm_deemph_bank_kernel<false><<<grid, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, taps, 0.f);
     CSDRB_CUDA(cudaGetLastError());
     return n - T;
+}
+
+// deemphasis_nfm_ff: the table of this sample rate, or 0 outputs when there is none (libcsdr.c:1119)
+int launch_deemphasis_nfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, int sample_rate,
+                               float limit_max, cudaStream_t st)
+{
+    int T = 0;
+    const float* h = csdrb_deemphasis_nfm_taps(sample_rate, &T);
+    if (!h || T <= 0) return 0;
+    return launch_fir_valid_bank(d_in, in_stride, d_out, out_stride, channels, n, h, T, limit_max, st);
 }
 
 // ---------------------------------------------------------------------------------------------- K6

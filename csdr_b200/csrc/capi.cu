@@ -434,6 +434,15 @@ int csdrb_deemphasis_wfm_bank_ff(const float* d_in, long in_stride, float* d_out
     return rc < 0 ? rc : counted(0, rc);
 }
 
+int csdrb_fir_valid_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int input_size, const float* taps,
+                            int taps_length, float limit_max, void* stream)
+{
+    if (!d_in || !d_out || !taps) { set_error("fir_valid bank: null pointer"); return -1; }
+    int rc = launch_fir_valid_bank(d_in, in_stride, d_out, out_stride, channels, input_size, taps, taps_length, limit_max, S(stream));
+    if (rc > 0) counted(0, 1);
+    return rc;
+}
+
 int csdrb_deemphasis_nfm_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int input_size, int sample_rate,
                                  float limit_max, void* stream)
 {

@@ -24,6 +24,8 @@ int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, 
 // deemphasis_nfm_ff: the tap tables live in host/firdes.c (public accessor, see include/csdr_b200.h)
 constexpr int kNfmMaxTaps = 208;
 extern "C" const float* csdrb_deemphasis_nfm_taps(int sample_rate, int* taps_length);
+int launch_fir_valid_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, const float* h_taps, int T,
+                          float limit_max, cudaStream_t st);
 int launch_deemphasis_nfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, int sample_rate,
                                float limit_max, cudaStream_t st);
 

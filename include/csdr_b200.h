@@ -221,6 +221,10 @@ int csdrb_deemphasis_wfm_bank_ff(const float *d_in, long in_stride, float *d_out
 int csdrb_deemphasis_nfm_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
                                  int sample_rate, float limit_max, void *stream);
 const float *csdrb_deemphasis_nfm_taps(int sample_rate, int *taps_length);
+/* the same kernel with caller-supplied (host) taps, taps_length <= 208: out[c][i] = sum_t taps[t] * in[c][i+t], i < input_size - taps_length
+ * (e.g. a de-emphasis FIR designed for a sample rate the reference has no table for) */
+int csdrb_fir_valid_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
+                            const float *taps, int taps_length, float limit_max, void *stream);
 
 /* spectrum side path on device buffers: `rows` frames of `size` values share one window table; power modes as the reference's
  * logpower_cf / accumulate_power_cf (d_out is read-modify-write) / log_ff */

@@ -70,6 +70,16 @@ def test_deemphasis_nfm_bank_with_fused_limit(gpu, oracle):
     for c in (0, 1, ch - 1):
         assert _rel(y[c], oracle.deemphasis_nfm_ff(xs[c], GOLD["nfm_taps_11025"])) < 1e-6
 
+    # caller-supplied taps through the same kernel (odd length, maximum length, one tap)
+    for T in (1, 77, 208):
+        taps = rng.uniform(-1, 1, T).astype(np.float32)
+        y = gpu.fir_valid_bank_ff(dx[:5], taps).cpu().numpy()
+        assert y.shape == (5, n - T)
+        xl = np.nan_to_num(x[4], nan=0.0, posinf=0.0, neginf=0.0)
+        assert _rel(gpu.fir_valid_bank_ff(torch.from_numpy(xl[None]).cuda(), taps).cpu().numpy()[0], oracle.deemphasis_nfm_ff(xl, taps)) < 1e-6, T
+    with pytest.raises(gpu.CsdrB200Error):
+        gpu.fir_valid_bank_ff(dx[:1], np.ones(209, np.float32))
+
 
 def test_readme_nfm_graph_as_a_bank(gpu, oracle):
     """README.md:87 for a whole bank, audio leaving the GPU as s16: fused shift|fir_decimate 50|fmdemod kernel -> limit fused into the
