@@ -39,7 +39,10 @@ def test_deemphasis_nfm_dropin_golden_and_oracle(gpu, oracle, rate):
         y = gpu.libcsdr.deemphasis_nfm_ff(x, rate)
         want = oracle.deemphasis_nfm_ff(x, taps)
         assert y.size == want.size == n - taps.size
-        assert _rel(y, want) < 1e-6, n
+        # each output is a ~200-term sum with cancellation: bound the error by the size of the terms, not of the (possibly tiny) result
+        assert np.abs(y - want).max() <= 1e-6 * np.abs(taps).sum(), n
+        if n >= 4096:
+            assert _rel(y, want) < 1e-6, n
 
 
 def test_deemphasis_nfm_degenerate_calls(gpu):
