@@ -21,9 +21,19 @@ n_out = cb.fir_out_len(N, D, T)
 out = torch.empty((shard.count, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
 ddc = cb.DdcBank(rates, D, taps, demod=True, chunk=CHUNK)          # owns phases/history; pre-pass of block k+1 overlaps block k
 
+TAIL = int(os.environ.get("NFM_TAIL", "0"))                         # 1: the whole README.md:87 graph -- ... | limit_ff | deemphasis_nfm_ff 48000 | fastagc_ff | convert_f_s16
+NFM_T = cb.deemphasis_nfm_taps(48000).size
+deemph = torch.empty((shard.count, n_out), dtype=torch.float32, device=dev)
+agc_state = torch.zeros((shard.count, 3), dtype=torch.float32, device=dev); agc_hist = torch.zeros((shard.count, 2, 1024), dtype=torch.float32, device=dev)
+pcm = torch.empty((shard.count, ((n_out - NFM_T) // 1024) * 1024), dtype=torch.int16, device=dev)
+
 def compute(buf, sh):
     # (a streaming caller would re-present the unconsumed tail; for the throughput measurement every block is processed whole)
-    return ddc.process(buf, out=out)
+    audio = ddc.process(buf, out=out)
+    if not TAIL: return audio
+    y = cb.deemphasis_nfm_bank_ff(audio, 48000, limit_max=1.0, out=deemph)         # limiter fused into the FIR's load
+    y, _, _ = cb.fastagc_bank_ff(y, 1024, 1.0, state=agc_state, hist=agc_hist)     # state carried block to block
+    return cb.convert_f_s16(y, out=pcm)                                             # only s16 audio would leave the GPU
 
 bank = SharedInputBank(shard, lambda: torch.zeros(N, dtype=torch.complex64, device=dev), compute, src=0)
 g = torch.Generator(device=dev).manual_seed(1)
@@ -41,7 +51,8 @@ t = torch.tensor([ms], dtype=torch.float64, device=dev)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     ms = float(t.item()); wide = N * NBLK / ms / 1e3
-    print(json.dumps({"config": "cfg4 NFM bank: shift|fir_decimate 50 (801 taps)|fmdemod, 128 ch/GPU, NCCL broadcast of the wideband block",
+    print(json.dumps({"config": "cfg4 NFM bank: shift|fir_decimate 50 (801 taps)|fmdemod" + ("|limit|deemphasis_nfm 48000|fastagc|convert_f_s16" if TAIL else "") +
+                                ", 128 ch/GPU, NCCL broadcast of the wideband block",
                       "n_gpus": world, "channels": C, "block_samples": N, "blocks": NBLK, "ms_per_block": ms / NBLK,
                       "wideband_msps": wide, "channel_msps_aggregate": wide * C, "realtime_factor_at_2p4Msps": wide / 2.4}), flush=True)
 if world > 1: dist.destroy_process_group()
