@@ -36,7 +36,7 @@ def _stale(target: Path, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
-    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [ROOT / "include" / "csdr_b200.h", Path(__file__)]
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(HOST.glob("*.h")) + [ROOT / "include" / "csdr_b200.h", Path(__file__)]
     objs = []
     for src in sorted(CSRC.glob("*.cu")):
         if src.name.startswith("bench_") or src.name.startswith("tool_"):
