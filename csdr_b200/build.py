@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cli_src = HOST / "csdr_cli.c"
     cli = PKG / "csdr"
     if cli_src.exists() and (force or _stale(cli, [cli_src, LIB] + headers)):
-        subprocess.run(["gcc", "-std=gnu99", "-O2", f"-I{ROOT / 'include'}", str(cli_src), "-o", str(cli),
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wno-unused-result", f"-I{ROOT / 'include'}", str(cli_src), "-o", str(cli),
                         f"-L{PKG}", "-lcsdr_b200", "-lm", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
