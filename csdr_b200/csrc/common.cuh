@@ -97,7 +97,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 // q = round(c/u) independent of M (c/u is never a tie for the float 2*pi = 0xC90FDB * 2^-21, checked for all E),
 // as long as the exact difference stays in the binade, i.e. M >= 2^23 + ceil(c/u).  So whole runs of iterations
 // collapse into one integer multiply; the binade-crossing steps are done with a real float subtraction.
-// Bit-exact with the loop (tests/test_gpu_parity2.py::test_phase_wrap_fast_forward_is_exact), ~25 steps instead of ~400.
+// Bit-exact with the loop (tests/test_gpu_parity2.py::test_phase_wrap_fast_forward_is_exact on the GPU; tests/test_phase_wrap_host.py compiles
+// this very function for the host and sweeps every binade on the CPU tier), ~25 steps instead of ~400.
 template <int E>
 __device__ __forceinline__ float wrap_binade_step(float a)
 {
@@ -122,7 +123,7 @@ __device__ __forceinline__ float wrap_binade_step(float a)
 __device__ __forceinline__ float wrap_phase_pm_pi(float ph)
 {
     const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;   // float(2)*PI rounds to the same float
-    const bool neg = ph < 0.f;
+    const bool neg = (__float_as_uint(ph) >> 31) != 0u;   // sign bit, so that -0.0 stays -0.0 like the loop leaves it
     float a = fabsf(ph);
     if (!(a < 67108864.f)) return ph;                // |ph| >= 2^26 (or nan): subtracting 2*pi no longer changes it; the reference would spin
     if (a >= 1048576.f) {                            // 2^20 and up: rare
