@@ -8,6 +8,7 @@
  *   fastddc.c:38-104 (fastddc_init, fastddc_print, fft_swap_sides).
  * Compiled with -fno-fast-math -ffp-contract=off: promotions below are the C language's, spelled out.
  */
+#define _GNU_SOURCE                               /* sincosf */
 #include "csdr_b200.h"
 #include <math.h>
 #include <stdlib.h>
@@ -116,10 +117,13 @@ int next_pow2(int x)
 /* ---- NCO parameters (libcsdr_gpl.c:81-89, 126-129) --------------------------------------------- */
 shift_addition_data_t shift_addition_init(float rate)
 {
+    /* One build-flag fact pinned on purpose: under the reference's -ffast-math gcc narrows sin()/cos() of this float argument to a single
+     * sincosf() call (seen in every build of libcsdr_gpl.c:84-85).  glibc's sincosf is within an ulp of, but not always equal to, the
+     * correctly rounded value (~3 % of rates differ), and the 1024-step phasor recursion turns one ulp in a delta into ~3e-5 of the
+     * stream -- so we make the same libm call and get a co-located reference build's deltas bit for bit (tests/test_oracle.py). */
     shift_addition_data_t d;
     rate *= 2;
-    d.sindelta = (float)sin((double)(rate * PI_F));
-    d.cosdelta = (float)cos((double)(rate * PI_F));
+    sincosf(rate * PI_F, &d.sindelta, &d.cosdelta);
     d.rate = rate;
     return d;
 }

@@ -97,6 +97,15 @@ def test_ref_audio_tail(oracle, ref):
         assert np.array_equal(ya, yb) and np.float32(la) == np.float32(lb)
 
 
+def test_ref_nco_deltas_over_many_rates(oracle, ref):
+    """shift_addition_init / decimating_shift_addition_init: the shipped build evaluates the deltas with sincosf (a -ffast-math narrowing); the
+    oracle makes the same call and must agree bit for bit for every rate, because the recursion amplifies a one-ulp delta to ~3e-5."""
+    rng = np.random.default_rng(0)
+    rates = np.concatenate([rng.uniform(-0.5, 0.5, 6000), rng.uniform(-5, 5, 500), [0, 0.25, -0.25, 0.5, -0.5, 1e-7, -1e-7]]).astype(np.float32)
+    for rate in rates:
+        assert oracle.shift_addition_init(float(rate)) == ref.shift_addition_init(float(rate)), rate
+
+
 def test_golden_and_ref_deemphasis_nfm(oracle):
     """8(f) rank 1: the oracle's FIR on the tables the compiled reference exports (golden copies) reproduces the reference's outputs;
     when oracle/_ref is built here, also live and on the tables read straight out of it."""

@@ -1,0 +1,95 @@
+"""CPU tier, property-based: the oracle restatement against the compiled, unmodified reference (oracle/_ref) on randomly drawn
+shapes and parameters -- the same pinning as tests/test_oracle.py, but over the parameter space instead of a few hand-picked cases.
+Skipped when oracle/_ref is not built (it needs /root/reference at build time)."""
+import numpy as np
+import pytest
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+from oracle.pyoracle import rel_rms  # noqa: E402
+
+COMMON = dict(deadline=None, max_examples=40, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow], derandomize=True)
+
+
+def _cplx(seed, n):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(0, 5000))
+def test_conversions_any_bytes(oracle, ref, seed, n):
+    rng = np.random.default_rng(seed)
+    u8 = rng.integers(0, 256, n, dtype=np.uint8)
+    assert np.array_equal(oracle.convert_u8_f(u8), ref.convert_u8_f(u8))
+    s16 = rng.integers(-32768, 32768, n).astype(np.int16)
+    assert np.array_equal(oracle.convert_s16_f(s16), ref.convert_s16_f(s16))
+    f = (rng.standard_normal(n) * rng.choice([1e-3, 0.5, 1.0, 3.0])).astype(np.float32)      # 3.0: beyond +-1, the wrap-around cases
+    assert np.array_equal(oracle.convert_f_s16(f), ref.convert_f_s16(f))
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 6000), D=st.integers(1, 64), T=st.integers(1, 400))
+def test_fir_decimate_any_geometry(oracle, ref, seed, n, D, T):
+    x = _cplx(seed, n)
+    taps = np.random.default_rng(seed + 1).uniform(-1, 1, T).astype(np.float32)
+    a, b = oracle.fir_decimate_cc(x, D, taps), ref.fir_decimate_cc(x, D, taps)
+    assert a.size == b.size                                                       # output count is the reference's, whatever it is
+    if a.size:
+        scale = np.abs(taps).sum()                                                # sums of <= 400 terms with cancellation: bound by the terms
+        assert np.abs(a - b).max() <= 4e-6 * scale
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), phase=st.floats(-3.0, 3.0, width=32),
+       chunk=st.sampled_from([None, 1, 37, 1000, 1024, 4096]))
+def test_shift_addition_any_rate_and_chunking(oracle, ref, seed, n, rate, phase, chunk):
+    x = _cplx(seed, n)
+    a, pa = oracle.shift_addition_cc(x, rate, phase, chunk)
+    b, pb = ref.shift_addition_cc(x, rate, phase, chunk)
+    assert np.float32(pa) == np.float32(pb)                                       # the carried float phase: same rounding sequence
+    # deltas are bit-equal (sincosf, like the shipped build); a call's SEED is (float)cos((double)phase) here and sincosf(phase) in the
+    # -ffast-math build: one ulp apart for ~3 % of phases, after which the two recursions round differently and drift apart like
+    # sqrt(steps) * 4e-8 -- 1.5e-6 after a 1400-sample call, far inside the 1e-5 bar
+    assert rel_rms(a, b) < 5e-6
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), dec=st.integers(1, 40))
+def test_decimating_shift_any_rate(oracle, ref, seed, n, rate, dec):
+    x = _cplx(seed, n)
+    (ya, sa), (yb, sb) = oracle.decimating_shift_addition_cc(x, rate, dec, 0, 0.0), ref.decimating_shift_addition_cc(x, rate, dec, 0, 0.0)
+    assert ya.size == yb.size and sa[0] == sb[0] and np.float32(sa[1]) == np.float32(sb[1])      # output count, decimation_remain, carried phase
+    assert ya.size == 0 or rel_rms(ya, yb) < 1e-6
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(2, 8000))
+def test_fmdemod_any_length(oracle, ref, seed, n):
+    x = _cplx(seed, n)
+    (a, la), (b, lb) = oracle.fmdemod_quadri_cf(x), ref.fmdemod_quadri_cf(x)
+    assert np.array_equal(a, b) and la == lb
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(200, 20000), rate=st.floats(1.0078125, 12.0, width=32), points=st.sampled_from([2, 4, 8, 12, 16]))
+def test_fractional_decimator_any_rate(oracle, ref, seed, n, rate, points):
+    x = np.random.default_rng(seed).uniform(-1, 1, n).astype(np.float32)
+    ya, yb = oracle.fractional_decimator_ff(x, rate, points), ref.fractional_decimator_ff(x, rate, points)
+    assert ya.size == yb.size                                                     # the float position chain picks the same indices
+    assert ya.size == 0 or rel_rms(ya, yb) < 1e-6
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), blocks=st.integers(3, 12), block=st.sampled_from([16, 256, 1000, 1024]), reference=st.floats(0.125, 2.0, width=32),
+       scale=st.sampled_from([0.0, 1e-4, 0.3, 1.0, 50.0]))
+def test_fastagc_any_block(oracle, ref, seed, blocks, block, reference, scale):
+    x = (np.random.default_rng(seed).uniform(-1, 1, blocks * block) * scale).astype(np.float32)
+    a, b = oracle.fastagc_ff(x, block, reference), ref.fastagc_ff(x, block, reference)
+    if block & (block - 1) == 0:
+        assert np.array_equal(a, b, equal_nan=True)                               # power-of-two blocks (the CLI default is 1024): bit-exact
+    else:
+        # the -ffast-math build turns the gain ramp's division by input_size into a multiplication by its reciprocal: exact only for
+        # powers of two, one or two ulps otherwise
+        assert np.all(np.isfinite(a) == np.isfinite(b)) and np.abs(a - b).max() <= 3e-7 * max(np.abs(b).max(), 1e-30)
