@@ -93,3 +93,59 @@ def test_fastagc_any_block(oracle, ref, seed, blocks, block, reference, scale):
         # the -ffast-math build turns the gain ramp's division by input_size into a multiplication by its reciprocal: exact only for
         # powers of two, one or two ulps otherwise
         assert np.all(np.isfinite(a) == np.isfinite(b)) and np.abs(a - b).max() <= 3e-7 * max(np.abs(b).max(), 1e-30)
+
+
+@settings(**COMMON)
+@given(length=st.integers(1, 600).map(lambda v: v | 1), cutoff=st.floats(0.0078125, 0.5, width=32), window=st.sampled_from(["BOXCAR", "BLACKMAN", "HAMMING"]))
+def test_firdes_lowpass_any_length(oracle, ref, length, cutoff, window):
+    a, b = oracle.firdes_lowpass_f(length, cutoff, window), ref.firdes_lowpass_f(length, cutoff, window)
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max()                          # the -ffast-math build re-associates the normalising sum
+
+
+@settings(**COMMON)
+@given(length=st.integers(1, 400).map(lambda v: v | 1), lo=st.floats(-0.5, 0.25, width=32), width=st.floats(0.015625, 0.25, width=32))
+def test_firdes_bandpass_any_band(oracle, ref, length, lo, width):
+    a, b = oracle.firdes_bandpass_c(length, lo, lo + width), ref.firdes_bandpass_c(length, lo, lo + width)
+    assert np.abs(a - b).max() <= 4e-6 * np.abs(b).max()
+
+
+@settings(**COMMON)
+@given(bw=st.floats(0.001953125, 0.25, width=32), dec=st.integers(1, 200), shift=st.floats(-0.5, 0.5, width=32))
+def test_fastddc_geometry_any_parameters(oracle, ref, bw, dec, shift):
+    a, b = oracle.fastddc_geometry(bw, dec, shift), ref.fastddc_geometry(bw, dec, shift)
+    assert list(a) == list(b)
+    for k in a:
+        assert np.float32(a[k]) == np.float32(b[k]), (k, a[k], b[k])
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), tau=st.sampled_from([50e-6, 75e-6, 1e-3]), fs=st.sampled_from([8000, 44100, 48000, 240000]),
+       last=st.floats(-1.0, 1.0, width=32), limit=st.floats(0.0625, 4.0, width=32))
+def test_audio_tail_any_parameters(oracle, ref, seed, n, tau, fs, last, limit):
+    x = np.random.default_rng(seed).uniform(-2, 2, n).astype(np.float32)
+    (a, la), (b, lb) = oracle.deemphasis_wfm_ff(x, tau, fs, last), ref.deemphasis_wfm_ff(x, tau, fs, last)
+    assert np.array_equal(a, b) and np.float32(la) == np.float32(lb)
+    assert np.array_equal(oracle.limit_ff(x, limit), ref.limit_ff(x, limit))
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 9000), rate=st.floats(-0.5, 0.5, width=32), phase=st.floats(-3.0, 3.0, width=32),
+       size=st.sampled_from([64, 1000, 1024]))
+def test_shift_unroll_any_rate(oracle, ref, seed, n, rate, phase, size):
+    x = _cplx(seed, n)
+    (a, pa), (b, pb) = oracle.shift_unroll_cc(x, rate, phase, size), ref.shift_unroll_cc(x, rate, phase, size)
+    assert np.float32(pa) == np.float32(pb)
+    assert rel_rms(a, b) < 1e-6                                                    # no recursion: table and seed differ by at most an ulp each
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), frames=st.integers(1, 6), size=st.sampled_from([16, 256, 1000]), add_db=st.floats(-100.0, 20.0, width=32),
+       window=st.sampled_from(["BOXCAR", "BLACKMAN", "HAMMING"]))
+def test_spectrum_side_path(oracle, ref, seed, frames, size, add_db, window):
+    x = _cplx(seed, frames * size)
+    wa, wb = oracle.precalculate_window(size, window), ref.precalculate_window(size, window)
+    assert np.abs(wa - wb).max() <= 1e-6                                          # the build evaluates cos through libmvec (a few ulp)
+    ya = np.concatenate([oracle.apply_precalculated_window_c(x[f * size:(f + 1) * size], wb) for f in range(frames)])
+    yb = np.concatenate([ref.apply_precalculated_window_c(x[f * size:(f + 1) * size], wb) for f in range(frames)])
+    assert np.array_equal(ya, yb)
+    assert np.abs(oracle.logpower_cf(x, add_db) - ref.logpower_cf(x, add_db)).max() <= 2e-5      # dB; log10f vs log10 of the build
