@@ -65,7 +65,7 @@ def build(out_dir: Path, name: str, cu_files, wrappers: str, extra_includes=(), 
                        check=True, capture_output=True)
         objs.append(str(obj))
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
-                        f"-I{ROOT / 'include'}", str(cpp)] + objs + ["-o", str(so), "-lm"], capture_output=True, text=True)
+                        f"-I{ROOT / 'include'}", str(cpp)] + objs + ["-o", str(so), "-lm", "-Wl,-Bsymbolic"], capture_output=True, text=True)   # -Bsymbolic: our cuda* stubs, not a libcudart another test loaded
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed for {name}:\n{r.stderr[-4000:]}")
     return so
