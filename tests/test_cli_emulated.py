@@ -26,7 +26,7 @@ def clis(tmp_path_factory):
         pytest.skip("needs g++ and the CUDA toolkit headers")
     if not g.REF.exists():
         pytest.skip("oracle/_ref/csdr_ref not built (needs /root/reference at build time)")
-    lib, cli = emul_build.build_full(tmp_path_factory.mktemp("emul_full"))
+    lib, cli = emul_build.build_full_once(tmp_path_factory)
     saved = g.LIB
     g.LIB = lib                                                            # what the LD_PRELOAD test injects into the reference binary
     yield str(cli), str(g.REF)
