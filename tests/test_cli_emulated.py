@@ -44,3 +44,6 @@ test_fft_commands = g.test_fft_commands
 test_spectrum_and_unroll_commands = g.test_spectrum_and_unroll_commands
 test_dynamic_bufsize_preamble = g.test_dynamic_bufsize_preamble
 test_reference_binary_runs_on_our_library = g.test_reference_binary_runs_on_our_library
+
+import test_gpu_zz_shift_math as zz  # noqa: E402
+test_shift_math_command = zz.test_shift_math_command

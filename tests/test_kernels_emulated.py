@@ -184,6 +184,22 @@ def test_k2_decimating_and_unroll(shift, oracle):
         assert np.float32(wph) == ph[c] and rel_rms(out[c], want) < 1e-7
 
 
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 10_001, 40_000])
+def test_shift_math_bank(shift, oracle, n):
+    """one rounded phase addition per sample: the per-channel chain thread drops a seed every 256 samples, the lanes re-walk their segment"""
+    rng = np.random.default_rng(n)
+    rates = np.array([-0.5, -0.31, -0.085, 0.0, 1e-4, 0.2, 0.4999, 0.5], np.float32); ch = rates.size
+    x = _cplx(rng, n)
+    ph0 = np.array([0.0, 3.0, -7.5, 100.0, 6.2831855, 1.0, 2.0, -0.0], np.float32); ph = ph0.copy()   # starts outside [0, 2*PI] take the reference's loops
+    out = np.zeros((ch, n), np.complex64)
+    sb = shift.emul_shift_math_scratch_bytes(ch, n); scratch = np.zeros(sb + 16, np.uint8)
+    assert shift.emul_launch_shift_math_bank(P(x), 0, P(out), n, ch, n, P(rates), P(ph), P(scratch), sb) >= 0, shift.emul_last_error()
+    for c, r in enumerate(rates):
+        want, wph = oracle.shift_math_cc(x, float(r), float(ph0[c]))
+        assert np.float32(wph).view(np.uint32) == ph[c].view(np.uint32), (c, wph, ph[c])    # the carried phase, bit for bit
+        assert rel_rms(out[c], want) < 1e-7, c
+
+
 # ------------------------------------------------------------------------------------------------------------------ K5 / K6 / audio tail
 @pytest.mark.parametrize("rate,points,n", [(5.0, 12, 20_000), (1.25, 12, 9_000), (2.5, 4, 5_001), (7.123, 16, 30_000)])
 def test_k5_fractional_decimator_bit_exact(audio, oracle, rate, points, n):
