@@ -153,6 +153,9 @@ int main(int argc, char **argv)
     if (!nfm && strcmp(tail, "none")) die("--tail is nfm or none");
     if (C == 0) die("no channels (RATE:SINK ...)");
     if (block <= 0 || (block & 1)) die("--block must be a positive even number of samples");
+    if (D <= 0 || (D & 1)) die("--decimation must be a positive even number (the fused kernels exist for 10 and 50)");
+    if (!(bw > 0.f && bw < 0.5f)) die("--bw must be a transition bandwidth between 0 and 0.5");
+    if (!(limit > 0.f) || !(agc_ref > 0.f)) die("--limit and --agc-ref must be positive");
     signal(SIGPIPE, SIG_IGN);
 
     /* ---- filter and bank ---------------------------------------------------------------------------------------------------- */
