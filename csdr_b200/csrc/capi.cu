@@ -479,6 +479,21 @@ int csdrb_copy2d_d2h(void* h_dst, size_t dst_pitch_bytes, const void* d_src, siz
     return 0;
 }
 
+int csdrb_encode_ima_adpcm_rows_i16_u8(const short* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int input_length,
+                                       ima_adpcm_state_t* d_state_io, void* stream)
+{
+    if (!d_in || !d_out || !d_state_io) { set_error("encode_ima_adpcm rows: null pointer"); return -1; }
+    int rc = launch_adpcm_encode_rows(d_in, in_stride, d_out, out_stride, rows, input_length, d_state_io, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_compress_fft_adpcm_rows_f_u8(const float* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int fft_size, void* stream)
+{
+    if (!d_in || !d_out) { set_error("compress_fft_adpcm rows: null pointer"); return -1; }
+    int rc = launch_compress_fft_adpcm_rows(d_in, in_stride, d_out, out_stride, rows, fft_size, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, void* stream)
 {
     if (!d_in || !d_out) { set_error("limit_ff: null pointer"); return -1; }
@@ -903,6 +918,22 @@ float shift_unroll_cc(complexf* input, complexf* output, int input_size, shift_u
     A_DOWN(output, 1, (size_t)input_size * 8, who);
     A_SYNC(who);
     return new_phase;
+}
+
+ima_adpcm_state_t encode_ima_adpcm_i16_u8(short* input, unsigned char* output, int input_length, ima_adpcm_state_t state)
+{
+    const char* who = "encode_ima_adpcm_i16_u8";
+    if (input_length < 2) return state;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_length * 2, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_length / 2 + 16), who);
+    A_UP(2, &state, sizeof state, who);
+    A_CHECK(csdrb_encode_ima_adpcm_rows_i16_u8((const short*)g_ctx.buf[0], input_length, (unsigned char*)g_ctx.buf[1], input_length / 2, 1, input_length,
+                                               (ima_adpcm_state_t*)g_ctx.buf[2], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)(input_length / 2), who);
+    A_CUDA(cudaMemcpyAsync(&state, g_ctx.buf[2], sizeof state, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return state;
 }
 
 void limit_ff(float* input, float* output, int input_size, float max_amplitude)
