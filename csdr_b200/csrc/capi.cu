@@ -102,9 +102,19 @@ int csdrb_set_device(int device) { CSDRB_CUDA(cudaSetDevice(device)); return 0; 
 int csdrb_stream_synchronize(void* stream) { CSDRB_CUDA(cudaStreamSynchronize(S(stream))); return 0; }
 long csdrb_kernel_launches(void) { return g_launches.load(); }
 
-int csdrb_convert_u8_f(const unsigned char* d_in, float* d_out, long n, void* stream) { return counted(launch_convert_u8_f(d_in, d_out, n, S(stream))); }
-int csdrb_convert_s16_f(const short* d_in, float* d_out, long n, void* stream) { return counted(launch_convert_s16_f(d_in, d_out, n, S(stream))); }
-int csdrb_convert_f_s16(const float* d_in, short* d_out, long n, void* stream) { return counted(launch_convert_f_s16(d_in, d_out, n, S(stream))); }
+static inline bool null_io(const void* in, const void* out, const char* who) { if (in && out) return false; set_error("%s: null pointer", who); return true; }
+int csdrb_convert_u8_f(const unsigned char* d_in, float* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_u8_f") ? -1 : counted(launch_convert_u8_f(d_in, d_out, n, S(stream)));
+}
+int csdrb_convert_s16_f(const short* d_in, float* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_s16_f") ? -1 : counted(launch_convert_s16_f(d_in, d_out, n, S(stream)));
+}
+int csdrb_convert_f_s16(const float* d_in, short* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_f_s16") ? -1 : counted(launch_convert_f_s16(d_in, d_out, n, S(stream)));
+}
 
 int csdrb_fir_bank_variants(void) { return fir_bank_variant_count(); }
 
@@ -451,30 +461,35 @@ void csdrb_stream_destroy(void* stream) { if (stream) cudaStreamDestroy(S(stream
 int csdrb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(h_src, d_dst, "copy_h2d")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(d_src, h_dst, "copy_d2h")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, S(stream)));
     return 0;
 }
 int csdrb_copy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(d_src, d_dst, "copy_d2d")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy2d_d2d(void* d_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
 {
     if (!width_bytes || !rows) return 0;
+    if (null_io(d_src, d_dst, "copy2d_d2d")) return -1;
     CSDRB_CUDA(cudaMemcpy2DAsync(d_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy2d_d2h(void* h_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
 {
     if (!width_bytes || !rows) return 0;
+    if (null_io(d_src, h_dst, "copy2d_d2h")) return -1;
     CSDRB_CUDA(cudaMemcpy2DAsync(h_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, S(stream)));
     return 0;
 }
@@ -569,6 +584,10 @@ struct csdrb_ddc_bank_s {
 csdrb_ddc_bank_t* csdrb_ddc_bank_create(int channels, const float* h_rates, int decimation, const float* h_taps, int taps_length, int demod, int chunk)
 {
     if (channels <= 0 || !h_rates || !h_taps || decimation <= 0 || taps_length <= 0) { set_error("ddc bank create: bad argument"); return nullptr; }
+    if (!((decimation == 50 && taps_length <= 850) || (decimation == 10 && taps_length <= 200))) {     // the geometries launch_ddc_main has fused kernels for
+        set_error("ddc bank create: no fused kernel for decimation %d / %d taps (compiled: d=50 T<=850, d=10 T<=200); run the unfused bank calls", decimation, taps_length);
+        return nullptr;
+    }
     auto* b = new csdrb_ddc_bank_s();
     b->channels = channels; b->decimation = decimation; b->taps_length = taps_length; b->demod = demod ? 1 : 0; b->chunk = chunk > 0 ? chunk : 1024;
     b->taps.assign(h_taps, h_taps + taps_length);
