@@ -393,6 +393,24 @@ static int cmd_logaveragepower_cf(int argc, char **argv)                   /* cs
     }
 }
 
+static int cmd_fft_exchange_sides_ff(int argc, char **argv)                /* csdr.c:1697-1715: pure I/O, the two halves of every line swap places */
+{
+    if (argc <= 2) return complain("need required parameters (fft_size)");
+    int fft_size = 0; sscanf(argv[2], "%d", &fft_size);
+    if (!incoming_block_size()) return -2;
+    announce_block(fft_size);
+    const size_t half = (size_t)(fft_size / 2);
+    float *lower = must_alloc(sizeof(float) * half), *upper = must_alloc(sizeof(float) * half);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(lower, sizeof(float), half, stdin);
+        fread(upper, sizeof(float), half, stdin);
+        fwrite(upper, sizeof(float), half, stdout);
+        fwrite(lower, sizeof(float), half, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_compress_fft_adpcm_f_u8(int argc, char **argv)              /* csdr.c:1739-1767 */
 {
     enum { PAD = 10 };                                                   /* the encoder needs a few values to settle: the line starts with ten copies of its first */
@@ -679,6 +697,7 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fractional_decimator_ff", cmd_fractional_decimator_ff, "fractional_decimator_ff <decimation_rate> [num_poly_points ( [transition_bw [window]] | --prefilter )]"},
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
     {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
+    {"fft_exchange_sides_ff", cmd_fft_exchange_sides_ff, "fft_exchange_sides_ff <fft_size>"},
     {"compress_fft_adpcm_f_u8", cmd_compress_fft_adpcm_f_u8, "compress_fft_adpcm_f_u8 <fft_size>"},
     {"encode_ima_adpcm_i16_u8", cmd_encode_ima_adpcm, "encode_ima_adpcm_i16_u8"},
     {"encode_ima_adpcm_s16_u8", cmd_encode_ima_adpcm, "encode_ima_adpcm_s16_u8"},

@@ -50,3 +50,4 @@ test_shift_math_command = zz.test_shift_math_command
 
 import test_gpu_zz_adpcm as za  # noqa: E402
 test_adpcm_commands = za.test_adpcm_commands
+test_openwebrx_waterfall_chain = za.test_openwebrx_waterfall_chain

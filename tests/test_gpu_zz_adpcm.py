@@ -50,3 +50,19 @@ def test_adpcm_commands(clis):
     pcm = (rng.standard_normal(20_000) * 3000).clip(-32768, 32767).astype(np.int16).tobytes()
     for name in ("encode_ima_adpcm_i16_u8", "encode_ima_adpcm_s16_u8"):
         assert run_graph(ours, [name], pcm) == run_graph(ref, [name], pcm)
+
+
+def test_openwebrx_waterfall_chain(clis):
+    """fft_cc | logaveragepower_cf | fft_exchange_sides_ff | compress_fft_adpcm_f_u8 (the OpenWebRX waterfall): same framing as the reference CLI;
+    the dB values agree to 2e-5 dB, so after *100 and truncation a few centi-dB steps may differ -- the compressed lines must agree almost everywhere."""
+    ours, ref = clis
+    rng = np.random.default_rng(8)
+    n = 1024 * 64
+    t = np.arange(n)
+    z = (0.5 * np.exp(2j * np.pi * 0.11 * t) + 0.05 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64).tobytes()
+    half = np.arange(4096, dtype=np.float32).tobytes()
+    assert run_graph(ours, ["fft_exchange_sides_ff 1024"], half) == run_graph(ref, ["fft_exchange_sides_ff 1024"], half)
+    stages = ["fft_cc 1024 2048", "logaveragepower_cf -70 1024 4", "fft_exchange_sides_ff 1024", "compress_fft_adpcm_f_u8 1024"]
+    a = np.frombuffer(run_graph(ours, stages, z), np.uint8); b = np.frombuffer(run_graph(ref, stages, z), np.uint8)
+    assert a.size == b.size and a.size >= 4 * 517
+    assert np.mean(a == b) > 0.98
