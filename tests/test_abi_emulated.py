@@ -74,6 +74,8 @@ def test_refusals_have_codes_and_messages(L):
     L.csdrb_fir_valid_bank_ff.argtypes = [vp, C.c_long, vp, C.c_long, C.c_int, C.c_int, vp, C.c_int, C.c_float, vp]
     big = np.ones(209, np.float32)
     assert L.csdrb_fir_valid_bank_ff(f.ctypes.data, 4096, g.ctypes.data, 4096, 1, 4096, big.ctypes.data, 209, 0.0, None) < 0
+    # channels ride in gridDim.y: a bank of more than 65535 channels is refused with a message, not with a launch-configuration error
+    assert L.csdrb_fir_decimate_bank_cc(x.ctypes.data, 200, y.ctypes.data, 14, 70000, 200, 10, t79.ctypes.data, 79, -1, None) < 0 and b"65535" in L.csdrb_last_error()
     assert L.csdrb_kernel_launches() == before                              # none of the refused calls launched anything
 
 
