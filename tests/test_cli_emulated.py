@@ -51,3 +51,6 @@ test_shift_math_command = zz.test_shift_math_command
 import test_gpu_zz_adpcm as za  # noqa: E402
 test_adpcm_commands = za.test_adpcm_commands
 test_openwebrx_waterfall_chain = za.test_openwebrx_waterfall_chain
+
+import test_gpu_zz_control as zc  # noqa: E402
+test_initial_tuning_through_the_control_channel = zc.test_initial_tuning_through_the_control_channel
