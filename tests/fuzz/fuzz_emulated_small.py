@@ -21,7 +21,7 @@ def aligned(shape, dtype):
 def cplx(*s): return (rng.uniform(-1, 1, s) + 1j * rng.uniform(-1, 1, s)).astype(np.complex64)
 it = 0; counts = {}
 while time.time() < t_end:
-    it += 1; kind = int(rng.integers(0, 8)); counts[kind] = counts.get(kind, 0) + 1
+    it += 1; kind = int(rng.integers(0, 10)); counts[kind] = counts.get(kind, 0) + 1
     if kind == 0:      # conversions
         n = int(rng.integers(1, 70000))
         u8 = aligned(n, np.uint8); u8[:] = rng.integers(0, 256, n); f = aligned(n, np.float32)
@@ -90,6 +90,26 @@ while time.time() < t_end:
         assert sh.emul_launch_shift_unroll_bank(P(x), 0, P(y), n, ch, n, P(params), P(dsin), P(dcos), size, size, P(ph), P(scr), sb) >= 0
         for c, r in enumerate(rates):
             w, wp = o.shift_unroll_cc(x, float(r), float(ph0[c]), size); assert np.float32(wp) == ph[c] and rel_rms(y[c], w) < 2e-7, ('unroll', n, size, c)
+    elif kind == 8:    # shift_table bank: bit-exact with the oracle's restatement of the reference build's index arithmetic
+        n = int(rng.integers(1, 12000)); size = int([16, 100, 1024, 65536][rng.integers(0, 4)]); ch = int(rng.integers(1, 5))
+        rates = rng.uniform(-0.5, 0.5, ch).astype(np.float32); x = cplx(n); table = o.shift_table_init(size)
+        ph0 = rng.uniform(0, 6.28, ch).astype(np.float32); ph = ph0.copy(); y = np.zeros((ch, n), np.complex64)
+        sb = sh.emul_shift_math_scratch_bytes(ch, n); scr = np.zeros(sb + 16, np.uint8)
+        assert sh.emul_launch_shift_table_bank(P(x), 0, P(y), n, ch, n, P(rates), P(ph), P(table), size, P(scr), sb) >= 0
+        for c, r in enumerate(rates):
+            w, wp, _bad = o.shift_table_cc(x, float(r), table, float(ph0[c]))
+            assert np.float32(wp).view(np.uint32) == ph[c].view(np.uint32) and np.array_equal(y[c], w), ('table', n, size, c)
+    elif kind == 9:    # IMA ADPCM rows and waterfall lines
+        rows = int(rng.integers(1, 70)); n = int(rng.integers(2, 3000))
+        x = (rng.standard_normal((rows, n)) * rng.choice([10, 300, 5000, 40000], (rows, 1))).clip(-32768, 32767).astype(np.int16)
+        st = np.stack([rng.integers(0, 89, rows), rng.integers(-32768, 32768, rows)], 1).astype(np.int32); st0 = st.copy(); y = np.zeros((rows, n // 2 + 1), np.uint8)
+        assert el.emul_launch_adpcm_encode_rows(P(x), n, P(y), y.shape[1], rows, n, P(st)) >= 0
+        for r_ in range(0, rows, max(1, rows // 5)):
+            w, (wi, wp) = o.encode_ima_adpcm_i16_u8(x[r_], int(st0[r_, 0]), int(st0[r_, 1]))
+            assert np.array_equal(y[r_, :n // 2], w) and (st[r_, 0], st[r_, 1]) == (wi, wp), ('adpcm', rows, n, r_)
+        fft_size = int(rng.integers(2, 3000)); db = rng.uniform(-400, 100, (rows, fft_size)).astype(np.float32); y = np.zeros((rows, (fft_size + 10) // 2), np.uint8)
+        assert el.emul_launch_compress_fft_adpcm_rows(P(db), fft_size, P(y), y.shape[1], rows, fft_size) >= 0
+        assert np.array_equal(y, o.compress_fft_adpcm_f_u8(db, fft_size)), ('waterfall', rows, fft_size)
     else:              # decimating shift bank
         n = int(rng.integers(1, 12000)); dec = int(rng.integers(1, 30)); ch = int(rng.integers(1, 5)); rates = rng.uniform(-0.5, 0.5, ch).astype(np.float32)
         xs = cplx(ch, n); params = np.array([o.shift_addition_init(float(np.float32(r) * dec)) for r in rates], np.float32)
