@@ -66,6 +66,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if cli_src.exists() and (force or _stale(cli, [cli_src, LIB] + headers)):
         subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wno-unused-result", f"-I{ROOT / 'include'}", str(cli_src), "-o", str(cli),
                         f"-L{PKG}", "-lcsdr_b200", "-lm", "-Wl,-rpath,$ORIGIN"], check=True)
+    bankd_src = HOST / "bankd.c"
+    bankd = PKG / "csdr-bankd"
+    if bankd_src.exists() and (force or _stale(bankd, [bankd_src, LIB] + headers)):
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wall", f"-I{ROOT / 'include'}", str(bankd_src), "-o", str(bankd),
+                        f"-L{PKG}", "-lcsdr_b200", "-lm", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

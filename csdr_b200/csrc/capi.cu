@@ -419,6 +419,55 @@ int csdrb_shift_unroll_bank_cc(const complexf* d_in, long in_stride, complexf* d
     return rc < 0 ? rc : counted(0, rc);
 }
 
+// ---- device memory / streams for CUDA-header-free hosts ------------------------------------------------------------------
+void* csdrb_device_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes ? bytes : 16);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc/cudaMemset", __FILE__, __LINE__); if (p) cudaFree(p); return nullptr; }
+    return p;
+}
+void csdrb_device_free(void* d_ptr) { if (d_ptr) cudaFree(d_ptr); }
+void* csdrb_stream_create(void)
+{
+    cudaStream_t st = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__); return nullptr; }
+    return st;
+}
+void csdrb_stream_destroy(void* stream) { if (stream) cudaStreamDestroy(S(stream)); }
+int csdrb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream)
+{
+    if (!bytes) return 0;
+    CSDRB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, S(stream)));
+    return 0;
+}
+int csdrb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream)
+{
+    if (!bytes) return 0;
+    CSDRB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    return 0;
+}
+int csdrb_copy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream)
+{
+    if (!bytes) return 0;
+    CSDRB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+    return 0;
+}
+int csdrb_copy2d_d2d(void* d_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
+{
+    if (!width_bytes || !rows) return 0;
+    CSDRB_CUDA(cudaMemcpy2DAsync(d_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToDevice, S(stream)));
+    return 0;
+}
+int csdrb_copy2d_d2h(void* h_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
+{
+    if (!width_bytes || !rows) return 0;
+    CSDRB_CUDA(cudaMemcpy2DAsync(h_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, S(stream)));
+    return 0;
+}
+
 int csdrb_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, void* stream)
 {
     if (!d_in || !d_out) { set_error("limit_ff: null pointer"); return -1; }

@@ -1,0 +1,267 @@
+/*
+ * bankd.c -- csdr-bankd: a whole bank of FM receivers on ONE wideband IQ stream, in one process.
+ *
+ * SURVEY.md 8(f) rank 2.  What the reference does with processes -- `nmux` fanning the IQ stream out over TCP (nmux.cpp:246-353)
+ * to one `csdr shift_addition_cc | csdr fir_decimate_cc | csdr fmdemod_quadri_cf | ...` chain per listener (ddcd_old.h:51-57,
+ * README.md:87) -- becomes: read the stream once (stdin, or as a TCP client of an nmux server: nmux's wire format is the raw byte
+ * stream, no framing), copy each block to the GPU once, run the fused bank kernel for all channels, and hand every channel's audio
+ * to its own sink (file / FIFO / `tcp:PORT` listener).  Plain C on the C ABI of libcsdr_b200 (no CUDA headers).
+ *
+ * Per channel the sample stream is exactly the README graph's:
+ *   convert_u8_f | shift_addition_cc r | fir_decimate_cc D bw W | fmdemod_quadri_cf [| limit_ff L | deemphasis_nfm_ff 48000 | fastagc_ff 1024 R | convert_f_s16]
+ * as ONE continuous stream (the CLI's per-process block framing -- stale tail blocks at EOF, the zero block deemphasis_nfm_ff emits
+ * first -- is process plumbing and is not reproduced; tests/test_gpu_bankd.py compares against the oracle run over the whole stream).
+ *
+ * usage: csdr-bankd [--in -|HOST:PORT] [--u8|--f32] [--decimation D] [--bw TRANSITION_BW] [--window W] [--block SAMPLES]
+ *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N]  RATE:SINK [RATE:SINK ...]
+ *   RATE  shift_addition_cc rate (fraction of the wideband sample rate), SINK a path (file or FIFO) or tcp:PORT (one listener).
+ */
+#define _GNU_SOURCE
+#include "csdr_b200.h"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <signal.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <sys/types.h>
+#include <unistd.h>
+
+#define AGC_BLOCK 1024                                   /* fastagc_ff's default block (csdr.c:1382) */
+#define NFM_RATE 48000                                   /* the README graph's audio rate: 2.4 Msps / 50 */
+
+typedef struct { float rate; const char *sink; int fd; } channel_t;
+
+static int die(const char *what)
+{
+    fprintf(stderr, "csdr-bankd: %s", what);
+    const char *e = csdrb_last_error();
+    if (e && *e) fprintf(stderr, " (%s)", e);
+    fprintf(stderr, "\n");
+    exit(1);
+}
+#define OK(call) do { if ((call) < 0) die(#call " failed"); } while (0)
+
+/* ---- input: stdin or a TCP client of an nmux server ------------------------------------------------------------------ */
+static int open_input(const char *spec)
+{
+    if (!strcmp(spec, "-")) return STDIN_FILENO;
+    char host[256];
+    const char *colon = strrchr(spec, ':');
+    if (!colon || (size_t)(colon - spec) >= sizeof host) die("--in wants - or HOST:PORT");
+    memcpy(host, spec, (size_t)(colon - spec)); host[colon - spec] = 0;
+    struct addrinfo hints = {0}, *res = NULL;
+    hints.ai_family = AF_UNSPEC; hints.ai_socktype = SOCK_STREAM;
+    if (getaddrinfo(host, colon + 1, &hints, &res) || !res) die("cannot resolve the --in address");
+    int fd = -1;
+    for (struct addrinfo *a = res; a; a = a->ai_next) {
+        fd = socket(a->ai_family, a->ai_socktype, a->ai_protocol);
+        if (fd < 0) continue;
+        if (!connect(fd, a->ai_addr, a->ai_addrlen)) break;
+        close(fd); fd = -1;
+    }
+    freeaddrinfo(res);
+    if (fd < 0) die("cannot connect to the --in address");
+    return fd;
+}
+
+/* all-or-EOF read: returns 1 when `bytes` bytes arrived, 0 at end of stream (a partial last block is dropped) */
+static int read_block(int fd, unsigned char *dst, size_t bytes)
+{
+    size_t have = 0;
+    while (have < bytes) {
+        ssize_t got = read(fd, dst + have, bytes - have);
+        if (got > 0) have += (size_t)got;
+        else if (got == 0) return 0;
+        else if (errno != EINTR && errno != EAGAIN) return 0;
+    }
+    return 1;
+}
+
+/* ---- sinks ----------------------------------------------------------------------------------------------------------------- */
+static int open_sink(const char *spec)
+{
+    if (!strncmp(spec, "tcp:", 4)) {                     /* one listener per channel, accepted before the stream starts */
+        int ls = socket(AF_INET, SOCK_STREAM, 0), yes = 1;
+        if (ls < 0) die("socket() failed");
+        setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &yes, sizeof yes);
+        struct sockaddr_in addr = {0};
+        addr.sin_family = AF_INET; addr.sin_addr.s_addr = htonl(INADDR_ANY); addr.sin_port = htons((unsigned short)atoi(spec + 4));
+        if (bind(ls, (struct sockaddr *)&addr, sizeof addr) || listen(ls, 1)) die("cannot listen on a tcp: sink");
+        fprintf(stderr, "csdr-bankd: waiting for a listener on %s\n", spec);
+        int fd = accept(ls, NULL, NULL);
+        close(ls);
+        if (fd < 0) die("accept() failed");
+        return fd;
+    }
+    int fd = open(spec, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { fprintf(stderr, "csdr-bankd: cannot open %s: %s\n", spec, strerror(errno)); exit(1); }
+    return fd;
+}
+
+/* a sink that fails (listener gone) is closed and skipped from then on, like nmux drops a client (nmux.cpp:339-346) */
+static void write_sink(channel_t *ch, const void *data, size_t bytes)
+{
+    const unsigned char *p = data;
+    while (ch->fd >= 0 && bytes) {
+        ssize_t put = write(ch->fd, p, bytes);
+        if (put > 0) { p += put; bytes -= (size_t)put; }
+        else if (put < 0 && (errno == EINTR || errno == EAGAIN)) continue;
+        else { fprintf(stderr, "csdr-bankd: sink %s closed\n", ch->sink); close(ch->fd); ch->fd = -1; }
+    }
+}
+
+int main(int argc, char **argv)
+{
+    const char *in_spec = "-", *tail = "nfm";
+    int u8 = 1, D = 50, block = 1 << 18, device = 0;
+    float bw = 0.005f, limit = 1.0f, agc_ref = 1.0f;
+    window_t window = WINDOW_HAMMING;
+    channel_t *chan = calloc((size_t)argc, sizeof *chan);
+    int C = 0;
+    for (int a = 1; a < argc; a++) {
+        const char *o = argv[a];
+        const char *v = a + 1 < argc ? argv[a + 1] : NULL;
+        if (!strcmp(o, "--u8")) u8 = 1;
+        else if (!strcmp(o, "--f32")) u8 = 0;
+        else if (!strcmp(o, "--in") && v) { in_spec = v; a++; }
+        else if (!strcmp(o, "--decimation") && v) { D = atoi(v); a++; }
+        else if (!strcmp(o, "--bw") && v) { bw = (float)atof(v); a++; }
+        else if (!strcmp(o, "--window") && v) { window = firdes_get_window_from_string((char *)v); a++; }
+        else if (!strcmp(o, "--block") && v) { block = atoi(v); a++; }
+        else if (!strcmp(o, "--tail") && v) { tail = v; a++; }
+        else if (!strcmp(o, "--limit") && v) { limit = (float)atof(v); a++; }
+        else if (!strcmp(o, "--agc-ref") && v) { agc_ref = (float)atof(v); a++; }
+        else if (!strcmp(o, "--device") && v) { device = atoi(v); a++; }
+        else if (strchr(o, ':') && o[0] != '-' ) {
+            char *end = NULL;
+            chan[C].rate = strtof(o, &end);
+            if (!end || *end != ':') die("channels are RATE:SINK");
+            chan[C].sink = end + 1; chan[C].fd = -1; C++;
+        } else if (o[0] == '-' && strchr(o + 1, ':') && (o[1] == '.' || (o[1] >= '0' && o[1] <= '9'))) {      /* negative rate */
+            char *end = NULL;
+            chan[C].rate = strtof(o, &end);
+            if (!end || *end != ':') die("channels are RATE:SINK");
+            chan[C].sink = end + 1; chan[C].fd = -1; C++;
+        } else { fprintf(stderr, "csdr-bankd: unknown argument %s\n", o); return 2; }
+    }
+    const int nfm = !strcmp(tail, "nfm");
+    if (!nfm && strcmp(tail, "none")) die("--tail is nfm or none");
+    if (C == 0) die("no channels (RATE:SINK ...)");
+    if (block <= 0 || (block & 1)) die("--block must be a positive even number of samples");
+    signal(SIGPIPE, SIG_IGN);
+
+    /* ---- filter and bank ---------------------------------------------------------------------------------------------------- */
+    const int T = firdes_filter_len(bw);
+    float *taps = malloc(sizeof(float) * (size_t)T);
+    firdes_lowpass_f(taps, T, 0.5f / (float)D, window);
+    if (block < 2 * T) die("--block is shorter than two filter lengths");
+    OK(csdrb_set_device(device));
+    float *rates = malloc(sizeof(float) * (size_t)C);
+    for (int c = 0; c < C; c++) rates[c] = chan[c].rate;
+    csdrb_ddc_bank_t *bank = csdrb_ddc_bank_create(C, rates, D, taps, T, 1, 1024);   /* 1024 = the CLI's shift_addition_cc call size (csdr.c:911) */
+    if (!bank) die("cannot create the bank");
+    int Tn = 0;
+    if (nfm && !csdrb_deemphasis_nfm_taps(NFM_RATE, &Tn)) die("no de-emphasis table");
+    void *stream = csdrb_stream_create();
+    if (!stream) die("cannot create a stream");
+
+    /* ---- buffers ----------------------------------------------------------------------------------------------------------------
+     * wide[2]  : [tail of the previous block | new block] cf32, ping-pong so the tail copy never overlaps
+     * demod    : [C][ds] float  : [Tn carried inputs of the de-emphasis FIR | new discriminator output]
+     * agc_in   : [C][gs] float  : [remainder (< AGC_BLOCK) | new de-emphasised samples]
+     * agc_out  : [C][nb*AGC_BLOCK] float, pcm the same as s16 (contiguous so one flat conversion serves all rows) */
+    const size_t in_bytes = (size_t)block * (u8 ? 2 : 8);
+    unsigned char *h_in = csdrb_host_alloc(in_bytes);
+    const int wide_cap = block + T + D + 16;
+    complexf *d_wide[2] = {csdrb_device_alloc(sizeof(complexf) * (size_t)wide_cap), csdrb_device_alloc(sizeof(complexf) * (size_t)wide_cap)};
+    unsigned char *d_raw = u8 ? csdrb_device_alloc(in_bytes + 16) : NULL;
+    const int out_cap = wide_cap / D + 2;                          /* discriminator samples one block can add */
+    const long ds = ((long)Tn + out_cap + 3) & ~3L;
+    const long gs = ((long)AGC_BLOCK + out_cap + 3) & ~3L;
+    float *d_demod = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)ds);
+    float *d_carry = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)(AGC_BLOCK + Tn + 4));
+    float *d_agc_in = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)gs) : NULL;
+    float *d_agc_out = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)gs) : NULL;
+    short *d_pcm = nfm ? csdrb_device_alloc(sizeof(short) * (size_t)C * (size_t)gs + 16) : NULL;
+    csdrb_fastagc_state_t *d_agc_state = nfm ? csdrb_device_alloc(sizeof(csdrb_fastagc_state_t) * (size_t)C) : NULL;
+    float *d_agc_hist = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * 2 * AGC_BLOCK) : NULL;
+    const size_t agc_sb = nfm ? csdrb_fastagc_bank_scratch_bytes(C, (int)(gs / AGC_BLOCK) + 1) : 0;
+    void *d_agc_scratch = nfm ? csdrb_device_alloc(agc_sb + 16) : NULL;
+    const size_t h_out_bytes = (size_t)C * (size_t)(gs > ds ? gs : ds) * sizeof(float);
+    unsigned char *h_out = csdrb_host_alloc(h_out_bytes);
+    if (!h_in || !d_wide[0] || !d_wide[1] || (u8 && !d_raw) || !d_demod || !d_carry || !h_out ||
+        (nfm && (!d_agc_in || !d_agc_out || !d_pcm || !d_agc_state || !d_agc_hist || !d_agc_scratch))) die("out of memory");
+
+    /* sinks last: tcp: sinks block until their listener arrives */
+    for (int c = 0; c < C; c++) chan[c].fd = open_sink(chan[c].sink);
+    const int in_fd = open_input(in_spec);
+    fprintf(stderr, "csdr-bankd: %d channels, decimation %d, %d taps, %s input, blocks of %d samples, tail %s\n", C, D, T, u8 ? "u8" : "f32", block, tail);
+
+    int cur = 0, keep = 0, a_have = 0, g_have = 0;
+    long blocks = 0;
+    while (read_block(in_fd, h_in, in_bytes)) {
+        /* 1. the new block lands behind the unconsumed tail (keep is even because block and D are: 16-byte alignment holds) */
+        complexf *fresh = d_wide[cur] + keep;
+        if (u8) {
+            OK(csdrb_copy_h2d(d_raw, h_in, in_bytes, stream));
+            OK(csdrb_convert_u8_f(d_raw, (float *)fresh, 2L * block, stream));
+        } else OK(csdrb_copy_h2d(fresh, h_in, in_bytes, stream));
+        const int n_in = keep + block;
+
+        /* 2. shift | fir_decimate | fmdemod for every channel, new discriminator samples behind the FIR's carried inputs */
+        const int n_out = csdrb_ddc_bank_process(bank, d_wide[cur], n_in, d_demod + a_have, ds, stream);
+        if (n_out < 0) die("csdrb_ddc_bank_process failed");
+        const int consumed = n_out * D;
+        keep = n_in - consumed;
+        OK(csdrb_copy_d2d(d_wide[cur ^ 1], d_wide[cur] + consumed, sizeof(complexf) * (size_t)keep, stream));
+        cur ^= 1;
+        const int a_n = a_have + n_out;
+
+        if (!nfm) {                                                /* raw discriminator output, float */
+            OK(csdrb_copy2d_d2h(h_out, sizeof(float) * (size_t)a_n, d_demod, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)a_n, (size_t)C, stream));
+            OK(csdrb_stream_synchronize(stream));
+            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out + sizeof(float) * (size_t)c * (size_t)a_n, sizeof(float) * (size_t)a_n);
+            a_have = 0; blocks++;
+            continue;
+        }
+
+        /* 3. limit_ff fused into deemphasis_nfm_ff: a_n inputs -> a_n - Tn outputs behind the AGC remainder; keep the last Tn inputs */
+        int m = 0;
+        if (a_n > Tn) {
+            m = csdrb_deemphasis_nfm_bank_ff(d_demod, ds, d_agc_in + g_have, gs, C, a_n, NFM_RATE, limit, stream);
+            if (m < 0) die("csdrb_deemphasis_nfm_bank_ff failed");
+            OK(csdrb_copy2d_d2d(d_carry, sizeof(float) * (size_t)Tn, d_demod + m, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)Tn, (size_t)C, stream));
+            OK(csdrb_copy2d_d2d(d_demod, sizeof(float) * (size_t)ds, d_carry, sizeof(float) * (size_t)Tn, sizeof(float) * (size_t)Tn, (size_t)C, stream));
+            a_have = Tn;
+        } else a_have = a_n;
+
+        /* 4. fastagc_ff over the whole AGC blocks available, then convert_f_s16; the remainder waits for the next block */
+        const int g_n = g_have + m, nb = g_n / AGC_BLOCK, whole = nb * AGC_BLOCK;
+        if (nb > 0) {
+            OK(csdrb_fastagc_bank_ff(d_agc_in, gs, d_agc_out, whole, C, AGC_BLOCK, nb, agc_ref, d_agc_state, d_agc_hist, d_agc_scratch, agc_sb + 16, stream));
+            OK(csdrb_convert_f_s16(d_agc_out, d_pcm, (long)C * whole, stream));
+            OK(csdrb_copy_d2h(h_out, d_pcm, sizeof(short) * (size_t)C * (size_t)whole, stream));
+            const int rest = g_n - whole;
+            OK(csdrb_copy2d_d2d(d_carry, sizeof(float) * (size_t)AGC_BLOCK, d_agc_in + whole, sizeof(float) * (size_t)gs, sizeof(float) * (size_t)rest, (size_t)C, stream));
+            OK(csdrb_copy2d_d2d(d_agc_in, sizeof(float) * (size_t)gs, d_carry, sizeof(float) * (size_t)AGC_BLOCK, sizeof(float) * (size_t)rest, (size_t)C, stream));
+            g_have = rest;
+            OK(csdrb_stream_synchronize(stream));
+            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out + sizeof(short) * (size_t)c * (size_t)whole, sizeof(short) * (size_t)whole);
+        } else {
+            g_have = g_n;
+            OK(csdrb_stream_synchronize(stream));
+        }
+        blocks++;
+    }
+    OK(csdrb_stream_synchronize(stream));
+    fprintf(stderr, "csdr-bankd: end of input after %ld blocks, %ld kernel launches\n", blocks, csdrb_kernel_launches());
+    for (int c = 0; c < C; c++) if (chan[c].fd >= 0) close(chan[c].fd);
+    csdrb_ddc_bank_destroy(bank);
+    csdrb_stream_destroy(stream);
+    return 0;
+}

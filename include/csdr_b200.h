@@ -146,6 +146,18 @@ int  csdrb_set_device(int device);
 int  csdrb_stream_synchronize(void *stream);
 long csdrb_kernel_launches(void);                /* kernels this library has launched so far (per process) */
 
+/* Device memory and streams for hosts that do not want the CUDA headers (the csdr-bankd daemon is plain C on top of these).
+ * Copies are asynchronous on `stream` (NULL = the default stream); host buffers should come from csdrb_host_alloc(). */
+void *csdrb_device_alloc(size_t bytes);          /* zero-filled; NULL on failure (csdrb_last_error) */
+void  csdrb_device_free(void *d_ptr);
+void *csdrb_stream_create(void);
+void  csdrb_stream_destroy(void *stream);
+int csdrb_copy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int csdrb_copy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int csdrb_copy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+int csdrb_copy2d_d2d(void *d_dst, size_t dst_pitch_bytes, const void *d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void *stream);
+int csdrb_copy2d_d2h(void *h_dst, size_t dst_pitch_bytes, const void *d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void *stream);
+
 /* K1 conversions on device buffers (16-byte aligned) */
 int csdrb_convert_u8_f(const unsigned char *d_in, float *d_out, long n, void *stream);
 int csdrb_convert_s16_f(const short *d_in, float *d_out, long n, void *stream);

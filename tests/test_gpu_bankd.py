@@ -1,0 +1,127 @@
+"""GPU tests (-m gpu) of csdr-bankd (csdr_b200/host/bankd.c): one process turns one wideband u8/f32 IQ stream
+(stdin or an nmux-style raw TCP stream) into per-channel NFM audio.  Per channel the stream must equal the README.md:87 graph run by
+the oracle over the whole stream, whatever the daemon's block size."""
+import os
+import socket
+import subprocess
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+ROOT = Path(__file__).resolve().parent.parent
+BANKD = ROOT / "csdr_b200" / "csdr-bankd"
+GOLD = np.load(Path(__file__).parent / "golden" / "hotpath_golden.npz")
+RATES = (-0.41, -0.2, 0.03, 0.27, 0.44)
+D, BW = 50, 0.005
+
+
+@pytest.fixture(scope="module")
+def bankd():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a CUDA device")
+    from csdr_b200.build import build
+    build()
+    assert BANKD.exists()
+    return str(BANKD)
+
+
+def wideband_u8(n, seed=7):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    z = sum(0.17 * np.exp(1j * (2 * np.pi * (-r) * t + np.cumsum(2 * np.pi * 3000.0 / 2.4e6 * np.sin(2 * np.pi * (700.0 + 300 * k) / 2.4e6 * t))))
+            for k, r in enumerate(RATES))
+    z = z + 0.003 * (rng.normal(size=n) + 1j * rng.normal(size=n))
+    iq = np.empty(2 * n); iq[0::2] = z.real; iq[1::2] = z.imag
+    return np.clip(np.floor(iq * 127.5 + 128), 0, 255).astype(np.uint8)
+
+
+def oracle_channel(oracle, wide_c64, rate, taps, tail):
+    sh, _ = oracle.shift_addition_cc(wide_c64, float(np.float32(rate)), 0.0, 1024)
+    d = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0]
+    if tail == "none":
+        return d
+    return oracle.convert_f_s16(oracle.fastagc_ff(oracle.deemphasis_nfm_ff(oracle.limit_ff(d, 1.0), GOLD["nfm_taps_48000"]), 1024, 1.0))
+
+
+def run(bankd, args, data, sinks, timeout=180):
+    cmd = [bankd] + args + [f"{r}:{p}" for r, p in zip(RATES, sinks)]
+    r = subprocess.run(cmd, input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stderr.decode()
+
+
+@pytest.mark.parametrize("block", [262144, 100_000])
+def test_nfm_bank_equals_the_readme_graph_per_channel(bankd, oracle, tmp_path, block):
+    n = 6 * 262144
+    u8 = wideband_u8(n)
+    used = (n // block) * block                                           # a partial last block is dropped
+    sinks = [tmp_path / f"ch{k}.s16" for k in range(len(RATES))]
+    run(bankd, ["--block", str(block)], u8.tobytes(), sinks)
+    wide = oracle.convert_u8_f(u8[:2 * used]).view(np.complex64)
+    taps = oracle.firdes_lowpass_f(oracle.firdes_filter_len(BW), 0.5 / D)
+    for rate, path in zip(RATES, sinks):
+        got = np.fromfile(path, np.int16)
+        want = oracle_channel(oracle, wide, rate, taps, "nfm")
+        assert got.size == want.size and got.size >= 25 * 1024, (rate, got.size, want.size)
+        assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1, rate       # floats equal to ~1e-6 -> s16 within one count
+
+
+def test_raw_discriminator_output_and_f32_input(bankd, oracle, tmp_path):
+    n = 3 * 131072
+    u8 = wideband_u8(n, seed=9)
+    wide = oracle.convert_u8_f(u8).view(np.complex64)
+    sinks = [tmp_path / f"ch{k}.f32" for k in range(len(RATES))]
+    run(bankd, ["--tail", "none", "--f32", "--block", "131072"], wide.tobytes(), sinks)
+    taps = oracle.firdes_lowpass_f(oracle.firdes_filter_len(BW), 0.5 / D)
+    from oracle.pyoracle import rel_rms
+    for rate, path in zip(RATES, sinks):
+        got = np.fromfile(path, np.float32)
+        want = oracle_channel(oracle, wide, rate, taps, "none")
+        assert got.size == want.size and rel_rms(got, want) < 1e-5, rate
+
+
+def test_tcp_ingest_and_tcp_sink(bankd, tmp_path):
+    """--in HOST:PORT reads the raw stream an nmux server would send; a tcp:PORT sink serves one listener.  Same bytes as stdin/file."""
+    n = 4 * 65536
+    u8 = wideband_u8(n, seed=11).tobytes()
+    files = [tmp_path / f"a{k}.s16" for k in range(len(RATES))]
+    run(bankd, ["--block", "65536"], u8, files)
+
+    srv = socket.socket(); srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1); srv.bind(("127.0.0.1", 0)); srv.listen(1)
+    in_port = srv.getsockname()[1]
+    probe = socket.socket(); probe.bind(("127.0.0.1", 0)); out_port = probe.getsockname()[1]; probe.close()
+
+    def feed():
+        conn, _ = srv.accept()
+        conn.sendall(u8); conn.close()
+
+    received = bytearray()
+
+    def listen():
+        import time
+        for _ in range(200):                                              # the daemon opens its listener after creating the bank
+            try:
+                c = socket.create_connection(("127.0.0.1", out_port), timeout=1); break
+            except OSError:
+                time.sleep(0.1)
+        else:
+            return
+        c.settimeout(60)
+        while True:
+            chunk = c.recv(1 << 16)
+            if not chunk:
+                break
+            received.extend(chunk)
+
+    t1 = threading.Thread(target=feed, daemon=True); t2 = threading.Thread(target=listen, daemon=True)
+    t1.start(); t2.start()
+    sinks = [f"tcp:{out_port}"] + [str(tmp_path / f"b{k}.s16") for k in range(1, len(RATES))]
+    run(bankd, ["--block", "65536", "--in", f"127.0.0.1:{in_port}"], b"", sinks)
+    t1.join(30); t2.join(30)
+    assert bytes(received) == files[0].read_bytes() and len(received) > 0
+    for k in range(1, len(RATES)):
+        assert (tmp_path / f"b{k}.s16").read_bytes() == files[k].read_bytes()
