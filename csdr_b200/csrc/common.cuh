@@ -7,6 +7,11 @@
 #error "csdr_b200 kernels are written for sm_100a (B200) only"
 #endif
 
+// dynamic shared memory of a kernel; the CPU-tier emulator (tests/host_shim/cuda_emul.h) supplies its own definition
+#ifndef CSDRB_DYN_SMEM
+#define CSDRB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace csdrb {
 
 // ---- error plumbing (host) ---------------------------------------------------------------------

@@ -16,6 +16,7 @@
 // twiddle is within ~2 ulp and the whole transform stays ~1e-7*log2 N from the exact DFT.
 #pragma once
 #include "common.cuh"
+#include <cmath>
 
 namespace csdrb {
 
@@ -487,6 +488,22 @@ struct FftRowOut {
         else { y[i] = a; y[i + 1] = b; }
     }
 };
+
+// host: the three twiddle planes (w^1, w^2, w^4) of an n-point transform, 3*n entries; a radix-8 pass over sub-size NS reads index
+// NS + k, k < NS.  Angles in double, rounded once to float.
+inline void fft_fill_twiddles(int n, float2* h)
+{
+    for (long i = 0; i < 3L * n; i++) h[i] = make_float2(1.f, 0.f);
+    int lg = 0; while ((1 << lg) < n) lg++;
+    int ns = lg % 3 == 1 ? 2 : (lg % 3 == 2 ? 4 : 1);
+    if (ns == 1) ns = 8;                                                // the first pass (NS = 1) needs no twiddles
+    for (; ns < n; ns *= 8)
+        for (int k = 0; k < ns; k++)
+            for (int c = 0; c < 3; c++) {
+                const double a = -2.0 * 3.14159265358979323846 * (double)((1 << c) * k) / (double)(ns * 8);
+                h[(size_t)c * n + ns + k] = make_float2((float)cos(a), (float)sin(a));
+            }
+}
 
 constexpr int fft_threads(int n) { return n / 16 < 32 ? 32 : n / 16; }
 constexpr int FFT_MAX_N = 16384;

@@ -1,0 +1,398 @@
+// fft_kernels.cuh -- the __global__ kernels of fft.cu (K7 batched c2c, K9 overlap-add bank, fastddc forward / inverse), kept apart from
+// their launchers so that a host build can execute them thread by thread (tests/host_shim/cuda_emul.h: every CUDA thread a fiber,
+// __syncthreads() a real barrier) in the CPU test tier.  The product includes this file from fft.cu only.
+#pragma once
+#include "fft.cuh"
+
+namespace csdrb {
+
+template <int N, bool INV>
+__global__ void __launch_bounds__(fft_threads(N))
+fft_c2c_batch_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x;
+    const float2* x = in + (long)blockIdx.x * in_stride;
+    float2* y = out + (long)blockIdx.x * out_stride;
+    FftRowIn src(x); FftRowOut dst(y);
+    block_fft_io<N, NT, INV>(s, tw, tid, src, dst);                    // first pass reads the row, last pass writes it: no staging copies
+}
+
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N), (N <= 4096 ? 2 : 1))
+olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                   const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                   int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    float2* tail = s + fft_smem_elems(N);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const float inv_n = 1.0f / (float)N;                           // N is a power of two: exact, same as /N
+    // A block's result r[i] = ifft[i]/N + (i < overlap ? previous r[input_size + i] : 0)  (libcsdr.c:837-847 with the
+    // ping-pong output buffers of csdr.c:1852-1878).  When overlap > input_size the carried tail chains through
+    // ceil(overlap/input_size) earlier blocks, so a run that starts mid-stream recomputes that many lead-in blocks
+    // from a zero tail; everything that zero start gets wrong has been shifted out by the first emitted block.
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+    for (int b = b_start; b < b_last; b++) {
+        const bool emit = b >= b_first;
+        { const float2* xb = x + (long)b * input_size;
+          fft_stage_in<N, NT>(s, tid, [&](int i) { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }); }
+        __syncthreads();
+        block_fft<N, NT, false>(s, tw, tid);
+        {
+            constexpr int PERH = (N + NT - 1) / NT;
+            float2 hh[PERH];                                            // all taps_fft loads first (L2 latency once, not PERH times)
+#pragma unroll
+            for (int k = 0; k < PERH; k++) { const int i = tid + k * NT; hh[k] = (N % NT == 0 || i < N) ? __ldg(H + i) : make_float2(0.f, 0.f); }
+#pragma unroll
+            for (int k = 0; k < PERH; k++) {
+                const int i = tid + k * NT;
+                if (N % NT == 0 || i < N) {
+                    const float2 a = s[fft_pad(i)], h = hh[k];
+                    // same rounding sequence as libcsdr.c:827-828 (separate products, no FMA)
+                    s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+                }
+            }
+        }
+        __syncthreads();
+        block_fft<N, NT, true>(s, tw, tid);
+        for (int i = tid; i < N; i += NT) {
+            const float2 raw = s[fft_pad(i)];
+            float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
+            if (i < overlap) v = make_float2(__fadd_rn(v.x, tail[i].x), __fadd_rn(v.y, tail[i].y));
+            s[fft_pad(i)] = v;
+            if (emit && i < input_size) y[(long)b * input_size + i] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < overlap; i += NT) tail[i] = s[fft_pad(input_size + i)];
+        __syncthreads();
+    }
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
+}
+
+// Same operation with the transforms' ends fused: the forward FFT's first pass reads the zero-padded block straight from global
+// memory, its last pass hands the spectrum x taps_fft product to the inverse FFT's first pass in registers (4096 = 8^4; other sizes go
+// through shared memory once), the inverse FFT's last pass scales, adds the carried tail and writes the result and the next tail.
+// taps_fft is fetched (L2) into registers while the last forward butterflies run, tails ping-pong between two shared arrays.
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N), (N <= 4096 ? 2 : 1))
+olafir_bank_fused_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                         const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                         int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    using LP = FftLastPass<N, NT>;
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    float2* tail_cur = s + fft_smem_elems(N);
+    float2* tail_next = tail_cur + overlap;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;      // see olafir_bank_kernel
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail_cur[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+
+    struct TapsMap {                                                    // spectrum * taps_fft, rounding sequence of libcsdr.c:827-828
+        const float2* H; float2 hh[LP::PER][8];
+        __device__ __forceinline__ static float2 mul(float2 a, float2 h)
+        {
+            return make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        }
+        __device__ __forceinline__ void prefetch(int b, int r, int i) { hh[b][r] = __ldg(H + i); }
+        __device__ __forceinline__ float2 at(int b, int r, int, float2 v) const { return mul(v, hh[b][r]); }
+        __device__ __forceinline__ float2 any(int i, float2 v) const { return mul(v, __ldg(H + i)); }
+    } map;
+    map.H = H;
+    const float inv_n = 1.0f / (float)N;                               // N is a power of two: exact, same as /N
+    for (int b = b_start; b < b_last; b++) {
+        struct BlockIn {                                                // input_size samples followed by zeros (csdr.c:1872-1876)
+            const float2* xb; int input_size;
+            __device__ __forceinline__ float2 load(int i) const { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }
+            __device__ __forceinline__ float4 load2(int i) const { const float2 a = load(i), c = load(i + 1); return make_float4(a.x, a.y, c.x, c.y); }
+        } src{x + (long)b * input_size, input_size};
+        struct BlockOut {                                               // r[i] = ifft[i]/N + (i < overlap ? previous r[input_size + i] : 0)
+            float2* yb; const float2* tail_cur; float2* tail_next; int input_size, overlap; float inv_n; bool emit;
+            __device__ __forceinline__ void store(int i, float2 raw) const
+            {
+                float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
+                if (i < overlap) v = make_float2(__fadd_rn(v.x, tail_cur[i].x), __fadd_rn(v.y, tail_cur[i].y));
+                if (i < input_size) { if (emit) yb[i] = v; }
+                else tail_next[i - input_size] = v;
+            }
+            __device__ __forceinline__ void store2(int i, float2 a, float2 c) const { store(i, a); store(i + 1, c); }
+        } dst{y + (long)b * input_size, tail_cur, tail_next, input_size, overlap, inv_n, b >= b_first};
+        block_fft_map_ifft<N, NT>(s, tw, tid, src, map, dst);
+        float2* t = tail_cur; tail_cur = tail_next; tail_next = t;       // the next block's first read of its tail is three barriers away
+    }
+    __syncthreads();
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail_cur[i];
+}
+
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N))
+fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, const float2* __restrict__ overlap_in,
+                   int input_size, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int overlap = N - input_size;
+    // block b transforms stream samples [b*input_size - overlap, (b+1)*input_size); negative positions come from the carried overlap
+    const long start = (long)b * input_size - overlap;
+    struct SlideIn {                                                    // stream position start + i; before the stream: the carried overlap
+        const float2* in; const float2* ov; long start; int overlap;
+        __device__ __forceinline__ float2 load(int i) const { const long p = start + i; return p >= 0 ? __ldg(in + p) : ov[overlap + p]; }
+        __device__ __forceinline__ float4 load2(int i) const { const float2 a = load(i), b = load(i + 1); return make_float4(a.x, a.y, b.x, b.y); }
+    } src{in, overlap_in, start, overlap};
+    FftRowOut dst(spectra + (long)b * N);
+    block_fft_io<N, NT, false>(s, tw, tid, src, dst);
+}
+
+__global__ void __launch_bounds__(1024)
+fastddc_carry_overlap_kernel(const float2* __restrict__ in, float2* __restrict__ overlap_io, int overlap, long total)
+{
+    // new carried overlap = last `overlap` samples of (old overlap ++ in[0..total)); one CTA, read everything, barrier, write
+    float2 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = threadIdx.x + k * 1024;
+        if (i < overlap) { const long p = total - overlap + i; v[k] = p >= 0 ? in[p] : overlap_io[overlap + p]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int i = threadIdx.x + k * 1024;
+        if (i < overlap) overlap_io[i] = v[k];
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N))
+apply_fir_fft_kernel(const float2* __restrict__ in, const float2* __restrict__ H, const float2* __restrict__ last_overlap, int overlap_size,
+                     float2* __restrict__ out, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    const int tid = threadIdx.x;
+    fft_stage_in<N, NT>(s, tid, [&](int i) { return in[i]; });
+    __syncthreads();
+    block_fft<N, NT, false>(s, tw, tid);
+    for (int i = tid; i < N; i += NT) {
+        const float2 a = s[fft_pad(i)], h = H[i];
+        s[fft_pad(i)] = make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+    }
+    __syncthreads();
+    block_fft<N, NT, true>(s, tw, tid);
+    const float inv_n = 1.0f / (float)N;
+    for (int i = tid; i < N; i += NT) {
+        float2 v = make_float2(s[fft_pad(i)].x * inv_n, s[fft_pad(i)].y * inv_n);
+        if (i < overlap_size) v = make_float2(__fadd_rn(v.x, last_overlap[i].x), __fadd_rn(v.y, last_overlap[i].y));
+        out[i] = v;
+    }
+}
+
+struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per channel: fastddc_t.offsetbin + dsadata
+#define PI_F 3.14159265358979323846f
+__device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph); }
+
+// per channel: walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
+__global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
+                                           int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
+                                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    int remain = remain_io[c], off = 0;
+    float ph = phase_io[c];
+    const float rate = chan[c].rate;
+    // when post_decimation divides post_input_size (every fastddc geometry with an even scrap, e.g. 448/2) and the carried
+    // remainder is in range, both the per-block output count and the remainder are constants: no integer division in the loop
+    const bool steady = (post_input_size % post_decimation == 0) && remain >= 0 && remain < post_decimation;
+    const int k_const = post_input_size / post_decimation;
+    const float adv_const = __fmul_rn(__fmul_rn(rate, PI_F), (float)k_const);
+    for (int b = 0; b < nblocks; b++) {
+        blk_remain[(long)b * channels + c] = remain;                    // [block][channel]: consecutive lanes store consecutive words
+        blk_phase[(long)b * channels + c] = ph;
+        blk_offset[(long)b * channels + c] = off;
+        if (steady) {
+            ph = ddc_wrap(__fadd_rn(ph, adv_const));
+            off += k_const;
+        } else {
+            int k = 0, pos = remain;
+            if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
+            remain = pos - post_input_size;
+            ph = ddc_wrap(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate, PI_F), (float)k)));
+            off += k;
+        }
+    }
+    remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off;
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+fastddc_inv_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
+                   const int* __restrict__ blk_remain, const float* __restrict__ blk_phase, const int* __restrict__ blk_offset,
+                   float2* __restrict__ out, long out_stride, int N, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                   int nblocks, const float2* __restrict__ tw)
+{
+    __shared__ float2 s[fft_smem_elems(M)];
+    constexpr int NT = 256;
+    static_assert(M <= 16 * NT, "fft_inv_size too large for this kernel");
+    const int tid = threadIdx.x, b = blockIdx.x, c = blockIdx.y;
+    const float2* X = spectra + (long)b * N;
+    const float2* H = taps_fft + (long)c * N;
+    const DdcChan cp = chan[c];
+    const int half = N / 2;
+    // fold: inv_input[(N + i - offsetbin + M/2) % M] += Xs[i] * H[i], Xs = spectrum with halves swapped (fastddc.c:123-141)
+    // destination depends on i mod M only; each thread owns whole residue classes and adds in ascending i like the reference.
+    const float inv_pre = 1.0f / (float)pre_decimation;            // power of two: exact
+    for (int r = tid; r < M; r += NT) {
+        float ai = 0.f, aq = 0.f;
+        for (int i = r; i < N; i += M) {
+            const float2 x = X[i < half ? i + half : i - half];
+            const float2 h = H[i];
+            ai = __fadd_rn(ai, __fsub_rn(__fmul_rn(x.x, h.x), __fmul_rn(x.y, h.y)));
+            aq = __fadd_rn(aq, __fadd_rn(__fmul_rn(x.x, h.y), __fmul_rn(x.y, h.x)));
+        }
+        int dst = (N + r - cp.offsetbin + M / 2) % M;
+        if (dst < 0) dst += M;
+        // second swap (fastddc.c:150) folded into the store index
+        const int d2 = dst < M / 2 ? dst + M / 2 : dst - M / 2;
+        s[fft_pad(d2)] = make_float2(ai * inv_pre, aq * inv_pre);
+    }
+    __syncthreads();
+    block_fft<M, NT, true>(s, tw, tid);
+    // normalise, drop the scrap, post shift + decimate (sequential phasor chain: one thread)
+    if (tid == 0) {
+        const float inv_m = 1.0f / (float)M;
+        const long bi = (long)b * gridDim.y + c;
+        const double ph = (double)blk_phase[bi];
+        float co = (float)cos(ph), si = (float)sin(ph);
+        float2* y = out + (long)c * out_stride + blk_offset[bi];
+        int k = 0;
+        for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
+            const float2 raw = s[fft_pad(scrap + pos)];
+            const float2 v = make_float2(raw.x * inv_m, raw.y * inv_m);
+            y[k++] = make_float2(__fsub_rn(__fmul_rn(co, v.x), __fmul_rn(si, v.y)), __fadd_rn(__fmul_rn(si, v.x), __fmul_rn(co, v.y)));
+            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            co = cn; si = sn;
+        }
+    }
+}
+
+// Tiled variant for M <= 1024: one CTA folds CT channels x BT blocks at once, so every spectrum bin is fetched once per CT
+// channels and every tap once per BT blocks (r01: the untiled kernel moved 256 KB of L2 traffic per (channel, block) and ran
+// at the L2 bandwidth limit).  The CT*BT inverse FFTs run four at a time (64 threads each); the CT*BT sequential post-shift
+// chains run on CT*BT different lanes in parallel.  Summation order per destination bin is still ascending, as in the reference.
+template <int M, int CT, int BT>
+__global__ void __launch_bounds__(256)
+fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __restrict__ taps_fft, const DdcChan* __restrict__ chan,
+                         const int* __restrict__ blk_remain, const float* __restrict__ blk_phase, const int* __restrict__ blk_offset,
+                         float2* __restrict__ out, long out_stride, int N, int pre_decimation, int scrap, int post_input_size, int post_decimation,
+                         int nblocks, int channels, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);                    // CT*BT padded arrays of M
+    constexpr int NT = 256, NTG = 64, GROUPS = NT / NTG, ELEMS = fft_smem_elems(M), PERT = (M + NT - 1) / NT;
+    static_assert(M <= 16 * NTG, "tiled fastddc_inv needs M <= 1024");
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * BT, c0 = blockIdx.y * CT;
+    const int half = N / 2;
+    const float inv_pre = 1.0f / (float)pre_decimation;                 // power of two: exact
+    int cidx[CT], bidx[BT];
+#pragma unroll
+    for (int u = 0; u < CT; u++) cidx[u] = min(c0 + u, channels - 1);   // ragged edges shadow the last valid channel / block
+#pragma unroll
+    for (int v = 0; v < BT; v++) bidx[v] = min(b0 + v, nblocks - 1);
+#pragma unroll 1
+    for (int rr = 0; rr < PERT; rr++) {
+        const int r = tid + rr * NT;
+        if (r >= M) break;
+        float2 acc[CT][BT];
+#pragma unroll
+        for (int u = 0; u < CT; u++)
+#pragma unroll
+            for (int v = 0; v < BT; v++) acc[u][v] = make_float2(0.f, 0.f);
+        // two bins per step, all eight loads of both bins issued before the arithmetic of the first (r01: long_scoreboard dominated)
+        for (int i = r; i < N; i += 2 * M) {
+            const int i2 = i + M;                                       // N / M is even for every fastddc geometry (pre_decimation >= 2)
+            const int xi = i < half ? i + half : i - half, xi2 = i2 < half ? i2 + half : i2 - half;
+            float2 x[BT], h[CT], x2[BT], h2[CT];
+#pragma unroll
+            for (int v = 0; v < BT; v++) { x[v] = __ldg(spectra + (long)bidx[v] * N + xi); x2[v] = __ldg(spectra + (long)bidx[v] * N + xi2); }
+#pragma unroll
+            for (int u = 0; u < CT; u++) { h[u] = __ldg(taps_fft + (long)cidx[u] * N + i); h2[u] = __ldg(taps_fft + (long)cidx[u] * N + i2); }
+#pragma unroll
+            for (int u = 0; u < CT; u++)
+#pragma unroll
+                for (int v = 0; v < BT; v++) {
+                    acc[u][v].x = __fadd_rn(acc[u][v].x, __fsub_rn(__fmul_rn(x[v].x, h[u].x), __fmul_rn(x[v].y, h[u].y)));
+                    acc[u][v].y = __fadd_rn(acc[u][v].y, __fadd_rn(__fmul_rn(x[v].x, h[u].y), __fmul_rn(x[v].y, h[u].x)));
+                }
+#pragma unroll
+            for (int u = 0; u < CT; u++)
+#pragma unroll
+                for (int v = 0; v < BT; v++) {
+                    acc[u][v].x = __fadd_rn(acc[u][v].x, __fsub_rn(__fmul_rn(x2[v].x, h2[u].x), __fmul_rn(x2[v].y, h2[u].y)));
+                    acc[u][v].y = __fadd_rn(acc[u][v].y, __fadd_rn(__fmul_rn(x2[v].x, h2[u].y), __fmul_rn(x2[v].y, h2[u].x)));
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < CT; u++) {
+            int dst = (N + r - chan[cidx[u]].offsetbin + M / 2) % M;
+            if (dst < 0) dst += M;
+            const int d2 = dst < M / 2 ? dst + M / 2 : dst - M / 2;   // second swap folded into the store index
+#pragma unroll
+            for (int v = 0; v < BT; v++) s[(u * BT + v) * ELEMS + fft_pad(d2)] = make_float2(acc[u][v].x * inv_pre, acc[u][v].y * inv_pre);
+        }
+    }
+    __syncthreads();
+    const int g = tid / NTG, tg = tid % NTG;
+#pragma unroll 1
+    for (int a = 0; a < CT * BT; a += GROUPS) block_fft<M, NTG, true>(s + (a + g) * ELEMS, tw, tg);   // CT*BT is a multiple of GROUPS
+    if (tid < CT * BT) {
+        const int u = tid / BT, v = tid % BT;
+        if (c0 + u < channels && b0 + v < nblocks) {
+            const DdcChan cp = chan[c0 + u];
+            const float2* src = s + tid * ELEMS;
+            const float inv_m = 1.0f / (float)M;
+            const long bi = (long)(b0 + v) * channels + (c0 + u);
+            const double ph = (double)blk_phase[bi];
+            float co = (float)cos(ph), si = (float)sin(ph);
+            float2* y = out + (long)(c0 + u) * out_stride + blk_offset[bi];
+            int k = 0;
+            for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
+                const float2 raw = src[fft_pad(scrap + pos)];
+                const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
+                y[k++] = make_float2(__fsub_rn(__fmul_rn(co, w.x), __fmul_rn(si, w.y)), __fadd_rn(__fmul_rn(si, w.x), __fmul_rn(co, w.y)));
+                const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+                const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+                co = cn; si = sn;
+            }
+        }
+    }
+}
+
+}  // namespace csdrb
