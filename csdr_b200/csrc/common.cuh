@@ -25,6 +25,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (e_ != cudaSuccess) return ::csdrb::cuda_fail(e_, #call, __FILE__, __LINE__);  \
     } while (0)
 
+// The inline-PTX helpers below have C++ models in tests/host_shim/cuda_emul.h (CPU test tier); the product never defines this macro.
+#ifndef CSDRB_HOST_EMULATION
 // ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2) --------------------------------------------
 // One instruction does the I and the Q lane of a complex sample.  Each half is an IEEE-754 fp32
 // operation (round-to-nearest-even), so results are identical to two scalar FFMA/FADD/FMUL.
@@ -94,6 +96,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+#endif  // CSDRB_HOST_EMULATION
 
 // ---- exact fast-forward of the reference's phase wrap ----------------------------------------------
 //   while (ph >  PI) ph -= 2*PI;   while (ph < -PI) ph += 2*PI;        (libcsdr_gpl.c:49-50, PI = (float)3.14159...)

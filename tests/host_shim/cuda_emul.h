@@ -4,11 +4,12 @@
 // (no GPU) are still EXECUTED, with their real index arithmetic, barriers and rounding, before GPU minutes are spent on them.
 // Model: one CTA at a time; every CUDA thread of the CTA is a ucontext fiber on one OS thread; __syncthreads() / __syncwarp() are
 // real barriers between fibers (a fiber that reaches one yields until all live fibers of the CTA / warp have arrived);
-// threadIdx/blockIdx/blockDim/gridDim are per-fiber values; dynamic shared memory is one zeroed buffer per CTA; IEEE single-precision
+// threadIdx/blockIdx/blockDim/gridDim are per-fiber values; dynamic shared memory is one buffer per CTA (pre-filled with a NaN pattern); IEEE single-precision
 // intrinsics map onto the same operations (fmaf is a true fused multiply-add on the host as well).
 // Not modelled: inline PTX (kernels that use it are not emulated), warp shuffles/votes, atomics, memory-model subtleties -- a data race
 // a GPU could expose may go unnoticed here (fibers switch only at barriers).
 #pragma once
+#define CSDRB_HOST_EMULATION 1
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -25,10 +26,16 @@ namespace cuda_emul {
 
 struct Fiber {
     ucontext_t ctx;
-    std::vector<unsigned char> stack;
+    unsigned char* stack = nullptr;              // from a pool that lives as long as the library (never zeroed, never freed)
     uint3 tid;
     bool done = false;
 };
+inline unsigned char* fiber_stack(size_t index, size_t bytes)
+{
+    static std::vector<unsigned char*> pool;
+    while (pool.size() <= index) pool.push_back(static_cast<unsigned char*>(std::malloc(bytes)));
+    return pool[index];
+}
 
 struct State {
     ucontext_t sched;
@@ -109,7 +116,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, A... args)
         for (unsigned by = 0; by < grid.y; by++)
             for (unsigned bx = 0; bx < grid.x; bx++) {
                 s.bid = make_uint3(bx, by, bz);
-                s.smem.assign(smem_bytes + 64, 0);
+                s.smem.assign(smem_bytes + 64, 0xFF);                 // NaN pattern: reading shared memory nobody wrote shows up
                 s.fibers.clear(); s.fibers.resize((size_t)nthreads);
                 s.live = nthreads; s.arrived = 0; s.generation = 0;
                 const int nwarps = (nthreads + 31) / 32;
@@ -117,9 +124,9 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, A... args)
                 for (int t = 0; t < nthreads; t++) {
                     Fiber& f = s.fibers[(size_t)t];
                     f.tid = make_uint3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
-                    f.stack.resize(stack_bytes);
+                    f.stack = fiber_stack((size_t)t, stack_bytes);
                     getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = f.stack.data(); f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
+                    f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = nullptr;
                     makecontext(&f.ctx, (void (*)())trampoline, 0);
                     s.warp_live[(size_t)(t / 32)]++;
                 }
@@ -142,6 +149,39 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, A... args)
                     sweep++;
                 }
             }
+}
+
+// `k<<<grid, block, smem, stream>>>(args...)` of a launcher is rewritten (tests/host_shim/emul_build.py) to cfg(grid, block, smem, stream).run(k, args...)
+struct Cfg {
+    dim3 grid, block; size_t smem;
+    template <typename K, typename... A> void run(K kernel, A... args) const { launch(grid, block, smem, kernel, args...); }
+};
+inline Cfg cfg(dim3 grid, dim3 block, size_t smem = 0, void* /*stream*/ = nullptr) { return Cfg{grid, block, smem}; }
+
+// ---- warp shuffle: lanes publish, meet at a warp barrier, read their partner, meet again -----------------------------------------
+inline unsigned char* warp_scratch() { static unsigned char buf[64][32][16]; return &buf[0][0][0]; }
+template <typename T> T shfl_xor(T v, int lane_mask)
+{
+    static_assert(sizeof(T) <= 16, "shuffle payload");
+    State& s = st();
+    const int t = linear_tid(s.cur), w = t / 32, l = t % 32;
+    unsigned char* base = warp_scratch() + ((size_t)w * 32) * 16;
+    std::memcpy(base + (size_t)l * 16, &v, sizeof(T));
+    sync_warp();
+    T r; std::memcpy(&r, base + (size_t)(l ^ lane_mask) * 16, sizeof(T));
+    sync_warp();
+    return r;
+}
+
+// ---- named barriers (bar.sync id, count) --------------------------------------------------------------------------------------------
+struct NamedBar { int arrived = 0; unsigned long generation = 0; };
+inline NamedBar& named_bar(int id) { static NamedBar b[16]; return b[id & 15]; }
+inline void named_sync(int id, int nthreads)
+{
+    NamedBar& b = named_bar(id);
+    const unsigned long my = b.generation;
+    if (++b.arrived == nthreads) { b.arrived = 0; b.generation++; return; }
+    while (b.generation == my) yield();
 }
 
 }  // namespace cuda_emul
@@ -169,3 +209,53 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline size_t __cvta_generic_to_shared(const void*) { return 0; }
+static inline int __float2int_rz(float f) { return (int)f; }                       // callers guard the range, as they must on the GPU
+static inline int __float2int_rn(float f) { return (int)nearbyintf(f); }
+static inline float __int2float_rn(int i) { return (float)i; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+template <typename T> static inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return ::cuda_emul::shfl_xor(v, lane_mask); }
+
+// ---- C++ models of the inline-PTX helpers of csdr_b200/csrc/common.cuh (which steps aside under CSDRB_HOST_EMULATION) ------------
+namespace csdrb {
+static inline float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }     // two IEEE FMAs, like FFMA2
+static inline float2 fadd2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+static inline float2 fmul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+static inline uint32_t smem_u32(const void*) { return 0; }
+// one-phase mbarrier model: word 0 = arrivals still expected, word 1 = transaction bytes still in flight; complete when both are 0
+static inline void mbar_init(uint64_t* bar, uint32_t count) { int32_t* w = reinterpret_cast<int32_t*>(bar); w[0] = (int32_t)count; w[1] = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { int32_t* w = reinterpret_cast<int32_t*>(bar); w[1] += (int32_t)bytes; w[0] -= 1; }
+static inline void mbar_arrive(uint64_t* bar) { reinterpret_cast<int32_t*>(bar)[0] -= 1; }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (parity != 0) { std::fprintf(stderr, "cuda_emul: only phase 0 of an mbarrier is modelled\n"); std::abort(); }
+    volatile int32_t* w = reinterpret_cast<volatile int32_t*>(bar);
+    while (w[0] != 0 || w[1] != 0) ::cuda_emul::yield();
+}
+static inline void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+    if ((reinterpret_cast<uintptr_t>(smem_dst) & 15) || (reinterpret_cast<uintptr_t>(gmem_src) & 15) || (bytes & 15)) {
+        std::fprintf(stderr, "cuda_emul: cp.async.bulk needs 16-byte aligned addresses and size\n"); std::abort();          // the GPU would fault here
+    }
+    std::memcpy(smem_dst, gmem_src, bytes);
+    reinterpret_cast<int32_t*>(bar)[1] -= (int32_t)bytes;
+}
+static inline void st_na_f4(float4* p, float4 v)
+{
+    if (reinterpret_cast<uintptr_t>(p) & 15) { std::fprintf(stderr, "cuda_emul: misaligned 128-bit store\n"); std::abort(); }
+    *p = v;
+}
+static inline void named_bar_sync(int id, int nthreads) { ::cuda_emul::named_sync(id, nthreads); }
+}  // namespace csdrb
+
+// ---- the handful of runtime calls the launchers make ("device" memory is host memory here) ------------------------------------------
+extern "C" {
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t bytes) { *p = std::calloc(1, bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memcpy(dst, src, bytes); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "cuda_emul"; }
+}

@@ -1,0 +1,119 @@
+"""Build a host library that EXECUTES the shipped .cu files under tests/host_shim/cuda_emul.h (CPU test tier; test infrastructure only).
+
+The kernel sources are used as they are; only two CUDA-only spellings are rewritten on the fly, textually:
+    kernel<<<grid, block, smem, stream>>>(args)   ->   ::cuda_emul::cfg(grid, block, smem, stream).run(kernel, args)
+    extern __shared__ __align__(N) unsigned char name[];   ->   unsigned char* name = ::cuda_emul::dyn_smem();
+so the launchers (grid and shared-memory arithmetic, dispatch on sizes) run too.  The wrappers appended after the sources export plain C
+entry points for ctypes.
+"""
+import re
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+CSRC = ROOT / "csdr_b200" / "csrc"
+SHIM = ROOT / "tests" / "host_shim"
+CUDA_INC = Path("/usr/local/cuda/include")
+
+_LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;(){}]*>)?)\s*<<<(.+?)>>>\s*\(", re.S)
+_DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned\s+char\s+(\w+)\[\];")
+
+
+def transform(text: str) -> str:
+    text = _DYN.sub(lambda m: f"unsigned char* {m.group(1)} = ::cuda_emul::dyn_smem();", text)
+    return _LAUNCH.sub(lambda m: f"::cuda_emul::cfg({m.group(2)}).run({m.group(1)}, ", text)
+
+
+def available() -> bool:
+    return bool(shutil.which("g++")) and (CUDA_INC / "cuda_runtime.h").exists()
+
+
+PRELUDE = """#include <algorithm>
+#include <cstdarg>
+using std::max;
+using std::min;
+#include "cuda_emul.h"
+#include "../../csdr_b200/csrc/common.cuh"
+namespace csdrb {
+static char g_emul_error[512];
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_emul_error, sizeof g_emul_error, fmt, ap); va_end(ap); }
+int cuda_fail(cudaError_t, const char* what, const char*, int) { set_error("cuda_emul: %s failed", what); return -100; }
+}
+extern "C" const char* emul_last_error(void) { return csdrb::g_emul_error; }
+extern "C" long emul_barriers(void) { return cuda_emul::st().barriers; }
+"""
+
+
+def build(out_dir: Path, name: str, cu_files, wrappers: str, extra_includes=(), host_c=()) -> Path:
+    """one translation unit: prelude, the transformed .cu files, the extern "C" wrappers"""
+    parts = [PRELUDE]
+    for inc in extra_includes:
+        parts.append(f'#include "{inc}"\n')
+    for cu in cu_files:
+        src = transform((CSRC / cu).read_text())
+        src = src.replace('#include "', f'#include "{CSRC}/')                     # the sources include their neighbours by bare name
+        parts.append(f"// ======== {cu} (transformed) ========\n{src}\n")
+    parts.append(wrappers)
+    cpp = out_dir / f"{name}.cpp"
+    cpp.write_text("\n".join(parts))
+    so = out_dir / f"{name}.so"
+    objs = []
+    for c in host_c:                                                               # host C of the product that a launcher calls (filter tables ...)
+        obj = out_dir / (Path(c).stem + ".o")
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", f"-I{ROOT / 'include'}", "-c", str(ROOT / c), "-o", str(obj)],
+                       check=True, capture_output=True)
+        objs.append(str(obj))
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
+                        f"-I{ROOT / 'include'}", str(cpp)] + objs + ["-o", str(so), "-lm", "-Wl,-Bsymbolic"], capture_output=True, text=True)   # -Bsymbolic: our cuda* stubs, not a libcudart another test loaded
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {name}:\n{r.stderr[-4000:]}")
+    return so
+
+
+# ---- wrappers generated from the launcher prototypes of csdr_b200/csrc/kernels.h ----------------------------------------------------
+_PROTO = re.compile(r"^(int|size_t|void)\s+(\w+)\s*\(([^;{}]*?)\)\s*;", re.S | re.M)
+
+
+def launcher_prototypes():
+    text = (CSRC / "kernels.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for ret, name, args in _PROTO.findall(text):
+        params = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",") if x.strip()]:
+            m = re.match(r"(.*?)(\w+)$", a)
+            params.append((m.group(1).strip(), m.group(2)))
+        protos[name] = (ret, params)
+    return protos
+
+
+def _ctype(ctype_text: str):
+    import ctypes as C
+    t = ctype_text.replace("const", "").strip()
+    if "*" in t or t == "cudaStream_t":
+        return C.c_void_p
+    return {"int": C.c_int, "long": C.c_long, "float": C.c_float, "size_t": C.c_size_t, "bool": C.c_bool}[t]
+
+
+def build_file(out_dir: Path, cu: str, extra: str = "", host_c=()):
+    """library for one .cu file: every launcher of kernels.h that the file defines is exported as emul_<name> (stream argument dropped)"""
+    import ctypes as C
+    text = (CSRC / cu).read_text()
+    protos = {n: p for n, p in launcher_prototypes().items() if re.search(r"\b%s\s*\(" % n, text) and re.search(r"^\w[\w\s\*]*\b%s\s*\(" % n, text, re.M)}
+    w = []
+    for name, (ret, params) in protos.items():
+        decl = ", ".join(f"{t} {n}" for t, n in params if t != "cudaStream_t")
+        call = ", ".join("nullptr" if t == "cudaStream_t" else n for t, n in params)
+        body = f"csdrb::{name}({call});" if ret == "void" else f"return csdrb::{name}({call});"
+        w.append(f'extern "C" {ret} emul_{name}({decl}) {{ {body} }}')
+    so = build(out_dir, "emul_" + Path(cu).stem, [cu], "\n".join(w) + "\n" + extra, host_c=host_c)
+    lib = C.CDLL(str(so))
+    for name, (ret, params) in protos.items():
+        f = getattr(lib, "emul_" + name)
+        f.argtypes = [_ctype(t) for t, n in params if t != "cudaStream_t"]
+        f.restype = {"int": C.c_int, "size_t": C.c_size_t, "void": None}[ret]
+    lib.emul_last_error.restype = C.c_char_p
+    lib.emul_barriers.restype = C.c_long
+    return lib, sorted(protos)

@@ -1,0 +1,389 @@
+"""CPU tier: the SHIPPED CUDA sources executed thread by thread on the host.
+
+tests/host_shim/cuda_emul.h turns every CUDA thread of a CTA into a fiber and __syncthreads() / __syncwarp() / bar.sync / mbarrier
+waits into real barriers between fibers; tests/host_shim/emul_build.py compiles each csdr_b200/csrc/*.cu file with g++ after two textual
+rewrites (`k<<<...>>>(...)` and `extern __shared__`), so kernels AND launchers run with their real index arithmetic, shared-memory
+traffic, barrier structure, alignment requirements (128-bit stores and bulk copies are checked) and IEEE single-precision rounding -- in a
+container without a GPU.  Every test is repeated under three fiber scheduling orders so that a missing barrier produces a wrong result
+in at least one of them.  Test infrastructure only: nothing in the product can reach it, and the product still fails loudly without a
+GPU (tests/test_abi.py).  It complements the -m gpu parity tests, it does not replace them.
+"""
+import ctypes as C
+import os
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests" / "host_shim"))
+import emul_build  # noqa: E402
+
+from oracle.pyoracle import rel_rms  # noqa: E402
+
+GOLD = np.load(Path(__file__).parent / "golden" / "hotpath_golden.npz")
+ORDERS = ["alternate", "reverse", "random"]
+_built = {}
+
+
+def _lib(tmp_path_factory, cu, order, host_c=()):
+    """build once per .cu file, load one private copy per scheduling order (the order is read when a copy initialises)"""
+    if not emul_build.available():
+        pytest.skip("needs g++ and the CUDA toolkit headers")
+    if cu not in _built:
+        out = tmp_path_factory.mktemp("emul_" + Path(cu).stem)
+        lib, names = emul_build.build_file(out, cu, host_c=host_c)
+        _built[cu] = (Path(lib._name), names, lib)
+    so, names, proto_lib = _built[cu]
+    copy = so.with_name(f"{so.stem}_{order}.so")
+    if not copy.exists():
+        shutil.copy(so, copy)
+    os.environ["CUDA_EMUL_ORDER"] = order
+    lib = C.CDLL(str(copy))
+    for n in names:
+        f = getattr(lib, "emul_" + n); g = getattr(proto_lib, "emul_" + n)
+        f.argtypes, f.restype = g.argtypes, g.restype
+    lib.emul_last_error.restype = C.c_char_p; lib.emul_barriers.restype = C.c_long
+    return lib
+
+
+def _fixture(cu, host_c=()):
+    @pytest.fixture(scope="module", params=ORDERS)
+    def fx(request, tmp_path_factory):
+        return _lib(tmp_path_factory, cu, request.param, host_c)
+    return fx
+
+
+elementwise = _fixture("elementwise.cu")
+shift = _fixture("shift.cu")
+audio = _fixture("audio.cu", ("csdr_b200/host/firdes.c",))
+ddc = _fixture("ddc_bank.cu")
+fir = _fixture("fir_decimate.cu")
+fft = _fixture("fft.cu")
+
+
+def P(a):
+    return a.ctypes.data
+
+
+def _cplx(rng, *shape, amp=1.0):
+    return ((rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)) * amp).astype(np.complex64)
+
+
+def _aligned(shape, dtype):
+    """16-byte aligned array (cudaMalloc gives 256; the kernels' 128-bit paths need 16)"""
+    n = int(np.prod(shape)); item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + 32, np.uint8)
+    off = (-raw.ctypes.data) % 16
+    return raw[off:off + n * item].view(dtype).reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------------------------ K1 / K4 / tail / spectrum
+def test_k1_conversions_bit_exact(elementwise, oracle):
+    codes = np.arange(256, dtype=np.uint8)
+    rng = np.random.default_rng(0)
+    for n in (256, 1, 15, 16, 17, 4099, 20_000):
+        src = (codes if n == 256 else rng.integers(0, 256, n, dtype=np.uint8))
+        u8 = _aligned(n, np.uint8); u8[:] = src; out = _aligned(n, np.float32)
+        assert elementwise.emul_launch_convert_u8_f(P(u8), P(out), n) >= 0
+        assert np.array_equal(out, oracle.convert_u8_f(u8)), n
+        s16 = _aligned(n, np.int16); s16[:] = rng.integers(-32768, 32768, n); out = _aligned(n, np.float32)
+        assert elementwise.emul_launch_convert_s16_f(P(s16), P(out), n) >= 0
+        assert np.array_equal(out, oracle.convert_s16_f(s16)), n
+        f = _aligned(n, np.float32); f[:] = rng.standard_normal(n) * 0.7
+        if n > 16:
+            f[:8] = [1.0, -1.0, 1.5, -1.5, 3.0, np.nan, np.inf, -np.inf]  # full scale, wrap-around, NaN, infinities
+        out = _aligned(n, np.int16)
+        assert elementwise.emul_launch_convert_f_s16(P(f), P(out), n) >= 0
+        assert np.array_equal(out, oracle.convert_f_s16(f)), n
+    assert np.array_equal(oracle.convert_u8_f(codes), GOLD["u8_table"]) if "u8_table" in GOLD.files else True
+
+
+def test_k4_fmdemod_bank_and_audio_tail(elementwise, oracle):
+    rng = np.random.default_rng(1)
+    ch, n = 3, 10_001
+    x = _cplx(rng, ch, n + 1)[:, :n]                                       # odd length inside an even stride
+    stride = x.strides[0] // 8
+    last = _cplx(rng, ch); last_out = np.zeros(ch, np.complex64)
+    out = np.zeros((ch, n + 3), np.float32)
+    assert elementwise.emul_launch_fmdemod_quadri_bank(P(x), stride, P(out), out.shape[1], ch, n, P(last), P(last_out)) >= 0
+    for c in range(ch):
+        want, wl = oracle.fmdemod_quadri_cf(np.ascontiguousarray(x[c]), complex(last[c]))
+        assert np.abs(out[c, :n] - want).max() <= 2e-7 and last_out[c] == np.complex64(wl)
+    f = _aligned(20_003, np.float32); f[:] = rng.uniform(-2, 2, f.size); f[7] = np.nan; f[9] = np.inf; f[11] = -np.inf
+    out = _aligned(f.size, np.float32)
+    assert elementwise.emul_launch_limit_ff(P(f), P(out), f.size, 0.7) >= 0
+    assert np.array_equal(out, oracle.limit_ff(f, 0.7))                    # NaN -> +max like the reference build
+
+
+def test_spectrum_side_path(elementwise, oracle):
+    rng = np.random.default_rng(2)
+    size, rows = 1000, 5
+    x = _cplx(rng, rows * size); w = oracle.precalculate_window(size, "BLACKMAN"); out = np.zeros_like(x)
+    assert elementwise.emul_launch_apply_window_rows(P(x), P(out), P(w), size, rows) >= 0
+    want = np.concatenate([oracle.apply_precalculated_window_c(x[r * size:(r + 1) * size], w) for r in range(rows)])
+    assert np.array_equal(out, want)
+    p = np.zeros(x.size, np.float32)
+    assert elementwise.emul_launch_power(P(x), None, P(p), x.size, -70.0, 0) >= 0
+    assert np.abs(p - oracle.logpower_cf(x, -70.0)).max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------------------ K2 and shift variants
+@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37)])
+def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):
+    rng = np.random.default_rng(n)
+    rates = np.array([-0.41, -0.085, 0.0, 0.2, 0.4999, 1e-4], np.float32)
+    ch = rates.size
+    x = _cplx(rng, n)
+    params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
+    ph0 = rng.uniform(-3, 3, ch).astype(np.float32); ph = ph0.copy()
+    out = np.zeros((ch, n), np.complex64)
+    sb = shift.emul_shift_bank_scratch_bytes(ch, n, chunk); scratch = np.zeros(sb + 16, np.uint8)
+    assert shift.emul_launch_shift_addition_bank(P(x), 0, P(out), n, ch, n, P(params), P(ph), chunk, P(scratch), sb) >= 0, shift.emul_last_error()
+    for c, r in enumerate(rates):
+        want, wph = oracle.shift_addition_cc(x, float(r), float(ph0[c]), chunk or None)
+        assert np.float32(wph) == ph[c], (c, wph, ph[c])                  # carried phase: bit-exact (exact wrap fast-forward included)
+        assert rel_rms(out[c], want) < 1e-7, c
+    # shift_addfast: same decomposition, one recursion step per four samples, n % 4 tails untouched
+    steps = np.stack([oracle.shift_addfast_init(float(r)) for r in rates]); ph = ph0.copy(); out[:] = 0
+    assert shift.emul_launch_shift_addfast_bank(P(x), 0, P(out), n, ch, n, P(steps), P(ph), chunk, P(scratch), sb) >= 0
+    for c, r in enumerate(rates):
+        want, wph = oracle.shift_addfast_cc(x, float(r), float(ph0[c]), chunk or None)
+        assert np.float32(wph) == ph[c] and rel_rms(out[c], want) < 1e-7 and np.array_equal(out[c] == 0, want == 0), c
+
+
+def test_k2_decimating_and_unroll(shift, oracle):
+    rng = np.random.default_rng(5)
+    n, dec = 10_007, 7
+    rates = np.array([0.1, -0.3, 0.05], np.float32); ch = rates.size
+    xs = _cplx(rng, ch, n)
+    params = np.array([oracle.shift_addition_init(float(np.float32(r) * dec)) for r in rates], np.float32)      # decimating_shift_addition_init
+    remain = np.array([0, 3, 6], np.int32); ph = np.array([0.0, 1.0, -2.0], np.float32); outsz = np.zeros(ch, np.int32)
+    r0, p0 = remain.copy(), ph.copy()
+    out = np.zeros((ch, n // dec + 2), np.complex64)
+    assert shift.emul_launch_decimating_shift_bank(P(xs), n, P(out), out.shape[1], ch, n, P(params), dec, P(remain), P(ph), P(outsz)) >= 0
+    for c, r in enumerate(rates):
+        want, (wr, wp) = oracle.decimating_shift_addition_cc(xs[c], float(r), dec, int(r0[c]), float(p0[c]))
+        assert outsz[c] == want.size and remain[c] == wr and ph[c] == np.float32(wp)
+        assert rel_rms(out[c, :want.size], want) < 1e-7
+    # shift_unroll: table of 1024 steps per channel, one reference call per 1024 samples
+    size = 1024; n = 5000
+    x = _cplx(rng, n)
+    tabs = [np.empty(size, np.float32) for _ in range(2 * ch)]
+    for c, r in enumerate(rates):
+        oracle.L.oracle_shift_unroll_init(float(r), size, tabs[2 * c].ctypes.data_as(C.POINTER(C.c_float)), tabs[2 * c + 1].ctypes.data_as(C.POINTER(C.c_float)))
+    dsin = np.stack(tabs[0::2]); dcos = np.stack(tabs[1::2])
+    params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
+    ph = np.zeros(ch, np.float32); out = np.zeros((ch, n), np.complex64)
+    sb = shift.emul_shift_bank_scratch_bytes(ch, n, size); scratch = np.zeros(sb + 16, np.uint8)
+    assert shift.emul_launch_shift_unroll_bank(P(x), 0, P(out), n, ch, n, P(params), P(dsin), P(dcos), size, size, P(ph), P(scratch), sb) >= 0
+    for c, r in enumerate(rates):
+        want, wph = oracle.shift_unroll_cc(x, float(r), 0.0, size)
+        assert np.float32(wph) == ph[c] and rel_rms(out[c], want) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------------------------ K5 / K6 / audio tail
+@pytest.mark.parametrize("rate,points,n", [(5.0, 12, 20_000), (1.25, 12, 9_000), (2.5, 4, 5_001), (7.123, 16, 30_000)])
+def test_k5_fractional_decimator_bit_exact(audio, oracle, rate, points, n):
+    rng = np.random.default_rng(int(rate * 100))
+    ch = 3
+    x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)
+    cap = int(n / rate) + 8
+    out = np.zeros((ch, cap), np.float32)
+    state = np.zeros((ch, 3), np.int32); state[:, 0] = np.array([points // 2 - 1], np.float32).view(np.int32)[0]       # where = -xifirst at init
+    sb = audio.emul_fracdec_scratch_bytes(ch, n, rate); scratch = np.zeros(sb + 16, np.uint8)
+    assert audio.emul_launch_fractional_decimator_bank(P(x), n, P(out), cap, ch, n, rate, points, None, 0, P(state), P(scratch), sb) >= 0, audio.emul_last_error()
+    for c in range(ch):
+        want = oracle.fractional_decimator_ff(x[c], rate, points)
+        assert state[c, 2] == want.size                                   # the float position chain picked the same indices ...
+        assert np.array_equal(out[c, :want.size], want)                   # ... and the Lagrange evaluation is the same rounding sequence
+
+
+def test_k6_fastagc_and_deemphasis_bit_exact(audio, oracle):
+    rng = np.random.default_rng(7)
+    ch, block, nblocks = 4, 1024, 9
+    env = np.repeat(rng.uniform(0.001, 1.0, nblocks).astype(np.float32), block)
+    x = np.stack([rng.uniform(-1, 1, env.size).astype(np.float32) * env * s for s in (1.0, 0.01, 0.0, 30.0)])
+    out = np.zeros_like(x); state = np.zeros((ch, 3), np.float32); hist = np.zeros((ch, 2, block), np.float32)
+    sb = audio.emul_fastagc_scratch_bytes(ch, nblocks); scratch = np.zeros(sb + 16, np.uint8)
+    assert audio.emul_launch_fastagc_bank(P(x), x.shape[1], P(out), out.shape[1], ch, block, nblocks, 0.8, P(state), P(hist), P(scratch), sb) >= 0
+    for c in range(ch):
+        assert np.array_equal(out[c], oracle.fastagc_ff(x[c], block, 0.8), equal_nan=True), c
+    xb = rng.uniform(-1, 1, (37, 5_001)).astype(np.float32); last = np.linspace(-0.5, 0.5, 37).astype(np.float32); last[3] = np.nan
+    l0 = last.copy(); yb = np.zeros_like(xb)
+    assert audio.emul_launch_deemphasis_wfm_bank(P(xb), xb.shape[1], P(yb), yb.shape[1], 37, xb.shape[1], 75e-6, 240000, P(last)) >= 0
+    for c in range(37):
+        want, wl = oracle.deemphasis_wfm_ff(xb[c], 75e-6, 240000, float(l0[c]))
+        assert np.array_equal(yb[c], want) and np.float32(wl) == last[c]
+
+
+@pytest.mark.parametrize("rate", [48000, 44100, 11025, 8000])
+def test_nfm_deemphasis_fir_and_fused_limiter(audio, oracle, rate):
+    taps = GOLD[f"nfm_taps_{rate}"]; T = taps.size
+    rng = np.random.default_rng(rate)
+    for n in (T + 1, T + 1024, T + 1025, 5000):
+        ch = 2
+        x = rng.uniform(-2.5, 2.5, (ch, n)).astype(np.float32); x[0, min(17, n - 1)] = np.nan
+        out = np.full((ch, n), np.nan, np.float32)
+        rc = audio.emul_launch_deemphasis_nfm_bank(P(x), n, P(out), n, ch, n, rate, 1.0)
+        assert rc == n - T
+        for c in range(ch):
+            want = oracle.deemphasis_nfm_ff(oracle.limit_ff(x[c], 1.0), taps)
+            assert np.abs(out[c, :rc] - want).max() <= 1e-6 * np.abs(taps).sum(), (n, c)
+    y = np.zeros(GOLD["nfm_in"].size, np.float32); xin = np.ascontiguousarray(GOLD["nfm_in"])
+    rc = audio.emul_launch_deemphasis_nfm_bank(P(xin), xin.size, P(y), y.size, 1, xin.size, rate, 0.0)
+    assert rel_rms(y[:rc], GOLD[f"nfm_out_{rate}"]) < 1e-5                # the compiled reference's output
+    assert audio.emul_launch_deemphasis_nfm_bank(P(xin), xin.size, P(y), y.size, 1, xin.size, 22050, 0.0) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------ K3: the headline kernel
+@pytest.mark.parametrize("D,T,n,variant", [(10, 199, 9_999, -1), (10, 199, 30_011, 0), (10, 199, 30_011, 3), (10, 199, 4_000, 7), (10, 79, 20_000, -1),
+                                           (50, 801, 70_000, -1), (7, 79, 5_001, -1), (10, 199, 199, -1), (10, 199, 208, -1), (10, 199, 150, -1)])
+def test_k3_fir_decimate_bank(fir, oracle, D, T, n, variant):
+    """bulk-copy tile loads on an mbarrier, polyphase register tiling, FFMA2, pair reduction through named barriers, streaming stores --
+    executed on the host against the oracle; n == T, n < T and ragged ends included."""
+    rng = np.random.default_rng(D * 1000 + T + n)
+    ch = 3
+    stride = n + (n & 1)
+    x = _aligned((ch, stride), np.complex64); x[:, :n] = _cplx(rng, ch, n); x[:, n:] = np.nan     # whatever follows a row must never be used
+    taps = oracle.firdes_lowpass_f(T, 0.5 / D)
+    n_out = (n - T) // D + 1 if n >= T else 0
+    ostride = max(n_out + (n_out & 1), 2)
+    out = _aligned((ch, ostride), np.complex64); out[:] = np.nan
+    fp = taps.ctypes.data_as(C.c_void_p)
+    rc = fir.emul_launch_fir_decimate_bank(P(x), stride, P(out), ostride, ch, n, D, fp, fp, 0, T, variant)          # "device" taps for the generic path: the same host array
+    assert rc == n_out, fir.emul_last_error()
+    for c in range(ch):
+        want = oracle.fir_decimate_cc(np.ascontiguousarray(x[c, :n]), D, taps)
+        assert want.size == n_out
+        if n_out:
+            assert rel_rms(out[c, :n_out], want) < 2e-6, (c, rel_rms(out[c, :n_out], want))
+
+
+# ------------------------------------------------------------------------------------------------------------------ fused DDC bank (config 4)
+@pytest.mark.parametrize("D,bw,demod", [(50, 0.005, 1), (10, 0.0201, 1), (10, 0.05, 0), (50, 0.005, 0)])
+def test_fused_ddc_bank_matches_the_unfused_chain(ddc, oracle, D, bw, demod):
+    T = oracle.firdes_filter_len(bw)
+    taps = oracle.firdes_lowpass_f(T, 0.5 / D)
+    n = 20_000 + 14
+    rng = np.random.default_rng(D)
+    t = np.arange(n)
+    rates = np.array([-0.41, -0.27, -0.13, 0.01, 0.15, 0.29, 0.43], np.float32); ch = rates.size
+    wide = sum(0.3 * np.exp(1j * (2 * np.pi * (-float(r)) * t + np.cumsum(0.05 * np.sin(2 * np.pi * t / (2000.0 + 100 * k))))) for k, r in enumerate(rates))
+    x = _aligned(n, np.complex64); x[:] = (wide + 0.01 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
+    params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
+    ph = np.zeros(ch, np.float32)
+    n_out = (n - T) // D + 1
+    stride = n_out + (n_out & 1)
+    out = np.zeros((ch, stride), np.float32 if demod else np.complex64)
+    last_out = np.zeros(ch, np.complex64); launches = C.c_int(0)
+    sb = ddc.emul_ddc_bank_scratch_bytes(ch, n, 1024, 0); scratch = np.zeros(sb + 64, np.uint8)
+    fp = taps.ctypes.data_as(C.c_void_p)
+    rc = ddc.emul_launch_ddc_bank(P(x), n, ch, P(params), P(ph), 1024, 0, D, fp, T, demod, P(out), stride, None, P(last_out) if demod else None, P(scratch), sb,
+                                  C.addressof(launches))
+    assert rc == n_out, ddc.emul_last_error()
+    for c, r in enumerate(rates):
+        sh, _ = oracle.shift_addition_cc(x, float(r), 0.0, 1024)
+        base = oracle.fir_decimate_cc(sh, D, taps)
+        want = oracle.fmdemod_quadri_cf(base)[0] if demod else base
+        assert rel_rms(out[c, :n_out], want) < (1e-5 if demod else 2e-6), (c, rel_rms(out[c, :n_out], want))
+
+
+# ------------------------------------------------------------------------------------------------------------------ K7 / K9 / K8
+def test_k7_fft_every_size_both_directions(fft):
+    rng = np.random.default_rng(0)
+    for n in (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
+        x = _aligned((2, n), np.complex64); x[:] = _cplx(rng, 2, n); y = _aligned((2, n), np.complex64)
+        for inv in (0, 1):
+            assert fft.emul_launch_fft_c2c_batch(P(x), n, P(y), n, n, 2, inv) >= 0, fft.emul_last_error()
+            want = np.fft.ifft(x.astype(np.complex128), axis=1) * n if inv else np.fft.fft(x.astype(np.complex128), axis=1)
+            assert rel_rms(y, want) < 1e-6, (n, inv)                      # same bar as tests/test_gpu_parity2.py::test_fft_all_sizes_vs_float64_dft
+        buf = _cplx(rng, n + 3); out = np.zeros(n + 3, np.complex64)
+        off = 1 if (buf.ctypes.data % 16) == 0 else 0                     # a row that is only 8-byte aligned
+        fft.emul_launch_fft_c2c_batch(P(buf[off:]), n, P(out[off:]), n, n, 1, 0)
+        assert rel_rms(out[off:off + n], np.fft.fft(buf[off:off + n].astype(np.complex128))) < 1e-6
+    assert fft.emul_barriers() > 100                                       # the barriers were real
+
+
+def _overlap_add(x, H, N, isz):
+    nb = x.size // isz; out = np.zeros(nb * isz + N - isz, np.complex128)
+    for b in range(nb):
+        blk = np.zeros(N, np.complex128); blk[:isz] = x[b * isz:(b + 1) * isz]
+        out[b * isz:b * isz + N] += np.fft.ifft(np.fft.fft(blk) * H)
+    return out[:nb * isz], out[nb * isz:]
+
+
+@pytest.mark.parametrize("N,isz,nb,bpc", [(4096, 2098, 5, 2), (4096, 2098, 3, 0), (512, 300, 7, 3), (64, 40, 9, 4), (256, 178, 6, 6), (1024, 224, 12, 5),
+                                          (2048, 1500, 4, 2), (16, 9, 11, 3), (128, 128, 3, 2), (32, 1, 70, 16)])
+def test_k9_overlap_add_bank(fft, N, isz, nb, bpc):
+    """bandpass_fir_fft_cc block loop: CTA runs of `bpc` blocks (lead-in recomputation), overlap > input_size, no overlap, streaming tails."""
+    rng = np.random.default_rng(N + isz)
+    ch = 2
+    x = _cplx(rng, ch, nb * isz); H = _cplx(rng, ch, N)
+    y = np.zeros_like(x); tail = np.zeros((ch, N), np.complex64)
+    assert fft.emul_launch_olafir_bank(P(x), x.shape[1], P(y), y.shape[1], ch, N, isz, nb, P(H), N, P(tail), bpc) >= 0, fft.emul_last_error()
+    for c in range(ch):
+        want, wt = _overlap_add(x[c].astype(np.complex128), H[c].astype(np.complex128), N, isz)
+        assert rel_rms(y[c], want) < 2e-6
+        if N > isz:
+            assert rel_rms(tail[c, :N - isz], wt) < 2e-6
+    h = nb // 2                                                            # two calls carrying the tail == one call
+    xa = np.ascontiguousarray(x[:, :h * isz]); xb = np.ascontiguousarray(x[:, h * isz:]); ya = np.zeros_like(xa); yb = np.zeros_like(xb)
+    t = np.zeros((ch, N), np.complex64)
+    fft.emul_launch_olafir_bank(P(xa), xa.shape[1], P(ya), ya.shape[1], ch, N, isz, h, P(H), N, P(t), bpc)
+    fft.emul_launch_olafir_bank(P(xb), xb.shape[1], P(yb), yb.shape[1], ch, N, isz, nb - h, P(H), N, P(t), bpc)
+    assert rel_rms(np.concatenate([ya, yb], 1), y) < 1e-6
+    if N > isz:
+        assert rel_rms(t[:, :N - isz], tail[:, :N - isz]) < 1e-6
+
+
+def test_k9_golden_and_dropin_kernel(fft, oracle):
+    """the golden bandpass stream of the compiled reference through the bank kernel, and apply_fir_fft_cc's one-block kernel"""
+    T = oracle.firdes_filter_len(0.05); N = 256; isz = N - T + 1
+    taps = np.zeros(N, np.complex64); taps[:T] = oracle.firdes_bandpass_c(T, -0.1, 0.2)
+    H = oracle.dft(taps)
+    x = np.ascontiguousarray(GOLD["bp_in"]); nb = x.size // isz
+    y = np.zeros(nb * isz, np.complex64); tail = np.zeros((1, N), np.complex64)
+    assert fft.emul_launch_olafir_bank(P(x), x.size, P(y), y.size, 1, N, isz, nb, P(H), N, P(tail), 4) >= 0
+    assert rel_rms(y, GOLD["bp_out"][:y.size]) < 5e-6                      # same bar as the GPU test
+    rng = np.random.default_rng(3)
+    blk = np.zeros(N, np.complex64); blk[:isz] = _cplx(rng, isz); last = _cplx(rng, T - 1); out = np.zeros(N, np.complex64)
+    assert fft.emul_launch_apply_fir_fft(P(blk), P(H), P(last), T - 1, P(out), N) >= 0
+    want = np.fft.ifft(np.fft.fft(blk.astype(np.complex128)) * H.astype(np.complex128)); want[:T - 1] += last
+    assert rel_rms(out, want) < 2e-6
+
+
+@pytest.mark.parametrize("bw,dec,shift", [(0.05, 8, 0.123), (0.05, 3, -0.2), (0.01, 6, 0.25)])
+def test_k8_fastddc_forward_and_inverse(fft, oracle, bw, dec, shift):
+    """a12/a13 against the oracle (and, for the first geometry, the golden spectra / channel output of the compiled reference);
+    decimation 3 has pre_decimation 1 and takes the one-CTA-per-(block, channel) kernel, the others the tiled one."""
+    from oracle.pyoracle import _CF, _p, WINDOWS
+    g, _ = oracle.fastddc_init(bw, dec, shift)
+    rng = np.random.default_rng(dec)
+    if (bw, dec) == (0.05, 8):
+        x = np.ascontiguousarray(GOLD["ddc_in"])
+    else:
+        n = 5 * g.input_size; t = np.arange(n)
+        x = ((np.exp(2j * np.pi * (-shift + 0.002) * t) * 0.5).astype(np.complex64) + _cplx(rng, n, amp=0.05)).astype(np.complex64)
+    nb = x.size // g.input_size
+    sp = np.zeros((nb, g.fft_size), np.complex64); carry = np.zeros(max(g.overlap_length, 1), np.complex64)
+    assert fft.emul_launch_fastddc_fwd(P(x), P(sp), P(carry), g.fft_size, g.input_size, nb) >= 0
+    want_sp = np.stack(oracle.fastddc_fwd(x, g))
+    assert rel_rms(sp, want_sp) < 1e-6
+    assert np.array_equal(carry[:g.overlap_length], x[nb * g.input_size - g.overlap_length:nb * g.input_size])
+    tf = np.empty(g.fft_size, np.complex64)
+    oracle.L.oracle_fastddc_make_taps_fft(C.byref(g), shift, dec, WINDOWS["HAMMING"], _p(tf, _CF))
+    chan = np.zeros(1, np.dtype([("offsetbin", np.int32), ("sindelta", np.float32), ("cosdelta", np.float32), ("rate", np.float32)]))
+    chan["offsetbin"] = g.offsetbin; chan["sindelta"] = g.dsadata.sindelta; chan["cosdelta"] = g.dsadata.cosdelta; chan["rate"] = g.dsadata.rate
+    remain = np.zeros(1, np.int32); phase = np.zeros(1, np.float32); total = np.zeros(1, np.int32)
+    out = np.zeros((1, nb * (g.post_input_size // g.post_decimation + 1) + 2), np.complex64)
+    sb = fft.emul_fastddc_inv_scratch_bytes(1, nb); scratch = np.zeros(sb + 16, np.uint8)
+    rc = fft.emul_launch_fastddc_inv_bank(P(want_sp), nb, P(tf), P(chan), 1, g.fft_size, g.fft_inv_size, g.pre_decimation, g.scrap, g.post_input_size, g.post_decimation,
+                                          P(remain), P(phase), P(out), out.shape[1], P(total), P(scratch), sb)
+    assert rc >= 0, fft.emul_last_error()
+    want = oracle.fastddc_inv(list(want_sp), bw, dec, shift)
+    assert total[0] == want.size and rel_rms(out[0, :want.size], want) < 5e-6
+    if (bw, dec) == (0.05, 8):
+        assert rel_rms(sp, GOLD["ddc_fwd_out"]) < 1e-6 and rel_rms(out[0, :total[0]], GOLD["ddc_inv_out"]) < 5e-6
