@@ -250,12 +250,4 @@ static inline void st_na_f4(float4* p, float4 v)
 static inline void named_bar_sync(int id, int nthreads) { ::cuda_emul::named_sync(id, nthreads); }
 }  // namespace csdrb
 
-// ---- the handful of runtime calls the launchers make ("device" memory is host memory here) ------------------------------------------
-extern "C" {
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
-cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-cudaError_t cudaMalloc(void** p, size_t bytes) { *p = std::calloc(1, bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t) { std::memcpy(dst, src, bytes); return cudaSuccess; }
-cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-const char* cudaGetErrorString(cudaError_t) { return "cuda_emul"; }
-}
+// the CUDA runtime calls launchers and the C ABI make are stubbed in cuda_emul_runtime.cpp (one copy per emulated library)

@@ -65,7 +65,7 @@ def build(out_dir: Path, name: str, cu_files, wrappers: str, extra_includes=(), 
                        check=True, capture_output=True)
         objs.append(str(obj))
     r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
-                        f"-I{ROOT / 'include'}", str(cpp)] + objs + ["-o", str(so), "-lm", "-Wl,-Bsymbolic"], capture_output=True, text=True)   # -Bsymbolic: our cuda* stubs, not a libcudart another test loaded
+                        f"-I{ROOT / 'include'}", str(cpp), str(SHIM / "cuda_emul_runtime.cpp")] + objs + ["-o", str(so), "-lm", "-Wl,-Bsymbolic"], capture_output=True, text=True)   # -Bsymbolic: our cuda* stubs, not a libcudart another test loaded
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed for {name}:\n{r.stderr[-4000:]}")
     return so
@@ -117,3 +117,54 @@ def build_file(out_dir: Path, cu: str, extra: str = "", host_c=()):
     lib.emul_last_error.restype = C.c_char_p
     lib.emul_barriers.restype = C.c_long
     return lib, sorted(protos)
+
+
+# ---- the whole library under emulation: libcsdr_b200_emul.so with the real C ABI, plus the CLI linked against it ----------------------
+PRELUDE_FULL = """#include <algorithm>
+using std::max;
+using std::min;
+#include "cuda_emul.h"
+"""
+
+
+def build_full(out_dir: Path):
+    """Every product translation unit (kernels, launchers, csrc/capi.cu, host C) compiled for the host under cuda_emul.h and linked into
+    ONE shared library that exports the product's C ABI, so host-side code on top of the ABI (the csdr CLI, Part A's workspace and
+    streaming logic in capi.cu) runs in the CPU tier.  Returns (library path, CLI path).  Test artefacts only -- built into a temporary
+    directory, never installed next to the product."""
+    from concurrent.futures import ThreadPoolExecutor
+    out_dir.mkdir(exist_ok=True)
+    cus = sorted(p.name for p in CSRC.glob("*.cu") if not p.name.startswith(("bench_", "tool_")))
+
+    def compile_cu(cu):
+        src = transform((CSRC / cu).read_text()).replace('#include "', f'#include "{CSRC}/')
+        src = src.replace(f'#include "{CSRC}/csdr_b200.h"', '#include "csdr_b200.h"')
+        cpp = out_dir / f"full_{Path(cu).stem}.cpp"
+        cpp.write_text(PRELUDE_FULL + src)
+        obj = cpp.with_suffix(".o")
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
+                            f"-I{ROOT / 'include'}", "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {cu}:\n{r.stderr[-3000:]}")
+        return str(obj)
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_cu, cus))
+    rt = out_dir / "cuda_emul_runtime.o"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-w", f"-I{CUDA_INC}", "-c", str(SHIM / "cuda_emul_runtime.cpp"), "-o", str(rt)], check=True, capture_output=True)
+    host = []
+    for c in sorted((ROOT / "csdr_b200" / "host").glob("*.c")):
+        if c.name in ("csdr_cli.c", "bankd.c"):
+            continue
+        obj = out_dir / (c.stem + ".host.o")
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", f"-I{ROOT / 'include'}", "-c", str(c), "-o", str(obj)],
+                       check=True, capture_output=True)
+        host.append(str(obj))
+    lib = out_dir / "libcsdr_b200_emul.so"
+    r = subprocess.run(["g++", "-shared", "-o", str(lib)] + objs + [str(rt)] + host + ["-lm", "-lpthread", "-Wl,-Bsymbolic"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stderr[-3000:])
+    cli = out_dir / "csdr_emul"
+    subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wno-unused-result", f"-I{ROOT / 'include'}", str(ROOT / "csdr_b200" / "host" / "csdr_cli.c"), "-o", str(cli),
+                    f"-L{out_dir}", "-lcsdr_b200_emul", "-lm", f"-Wl,-rpath,{out_dir}"], check=True, capture_output=True)
+    return lib, cli
