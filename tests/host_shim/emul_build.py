@@ -167,4 +167,8 @@ def build_full(out_dir: Path):
     cli = out_dir / "csdr_emul"
     subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wno-unused-result", f"-I{ROOT / 'include'}", str(ROOT / "csdr_b200" / "host" / "csdr_cli.c"), "-o", str(cli),
                     f"-L{out_dir}", "-lcsdr_b200_emul", "-lm", f"-Wl,-rpath,{out_dir}"], check=True, capture_output=True)
+    bankd_src = ROOT / "csdr_b200" / "host" / "bankd.c"
+    if bankd_src.exists():                                                 # the ingest daemon is plain C on the ABI too
+        subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wall", f"-I{ROOT / 'include'}", str(bankd_src), "-o", str(out_dir / "csdr-bankd_emul"),
+                        f"-L{out_dir}", "-lcsdr_b200_emul", "-lm", f"-Wl,-rpath,{out_dir}"], check=True, capture_output=True)
     return lib, cli
