@@ -122,6 +122,9 @@ def lib() -> C.CDLL:
     L.log_ff.argtypes = [vp, vp, it, C.c_float]
     L.shift_unroll_init.argtypes = [C.c_float, it]; L.shift_unroll_init.restype = _Unroll
     L.shift_unroll_cc.argtypes = [vp, vp, it, C.POINTER(_Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
+    L.shift_math_cc.argtypes = [vp, vp, it, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
+    L.csdrb_shift_math_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_shift_math_bank_scratch_bytes.restype = sz
+    L.csdrb_shift_math_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp, sz, vp]
     L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = _AddFast
     L.shift_addfast_cc.argtypes = [vp, vp, it, C.POINTER(_AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
     L.csdrb_shift_addfast_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, it, vp, sz, vp]
@@ -461,6 +464,14 @@ class libcsdr:
         return y, float(np.float32(phase))
 
     @staticmethod
+    def shift_math_cc(x, rate, phase=0.0, chunk=None):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = lib().shift_math_cc(x[s0:].ctypes.data, y[s0:].ctypes.data, n, rate, phase)
+        return y, float(np.float32(phase))
+
+    @staticmethod
     def shift_addfast_cc(x, rate=None, phase=0.0, chunk=1024, steps=None):
         """calls of <= chunk samples like csdr.c:781-791; `steps` (9 floats: dsin[4], dcos[4], increment) overrides shift_addfast_init(rate);
         samples a call leaves untouched (n % 4) come back as 0"""
@@ -560,6 +571,26 @@ def shift_addition_bank_cc(x, rates, phases=None, chunk: int = 1024, out=None):
     scratch = _scratch(sb, xr.device)
     _check(lib().csdrb_shift_addition_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_params.data_ptr(), d_phase.data_ptr(), chunk,
                                               scratch.data_ptr(), scratch.numel(), _stream()), "shift_addition_bank_cc")
+    return out, d_phase
+
+
+def shift_math_bank_cc(x, rates, phases=None, out=None):
+    """x: [N] (one shared wideband stream) or [C, N] complex64; returns (y [C, N], new phases [C])."""
+    import torch
+    rates = np.atleast_1d(np.asarray(rates, np.float32)); ch = rates.size
+    shared = (x.dim() == 1) if x.dtype == torch.complex64 else (x.dim() == 2)
+    xr, ptr, stride, xc, n = _as_cf32_rows(x)
+    if shared:
+        stride = 0
+    else:
+        assert xc == ch
+    d_rates = torch.from_numpy(rates).to(xr.device)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=xr.device) if phases is None else phases.clone()
+    if out is None:
+        out = torch.empty((ch, n), dtype=torch.complex64, device=xr.device)
+    scratch = _scratch(lib().csdrb_shift_math_bank_scratch_bytes(ch, n), xr.device)
+    _check(lib().csdrb_shift_math_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_rates.data_ptr(), d_phase.data_ptr(),
+                                          scratch.data_ptr(), scratch.numel(), _stream()), "shift_math_bank_cc")
     return out, d_phase
 
 

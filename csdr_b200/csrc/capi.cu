@@ -308,6 +308,17 @@ int csdrb_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf*
     return rc < 0 ? rc : counted(0, rc);
 }
 
+size_t csdrb_shift_math_bank_scratch_bytes(int channels, int input_size) { return shift_math_scratch_bytes(channels, input_size); }
+
+int csdrb_shift_math_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                             const float* d_rates, float* d_phase_io, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (!d_in || !d_out || !d_rates || !d_phase_io) { set_error("shift_math bank: null pointer"); return -1; }
+    int rc = launch_shift_math_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                    d_rates, d_phase_io, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_shift_addfast_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                                 const shift_addfast_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
 {
@@ -678,6 +689,29 @@ float shift_addition_cc(complexf* input, complexf* output, int input_size, shift
     float* d_phase = reinterpret_cast<float*>(static_cast<char*>(g_ctx.buf[2]) + offsetof(decltype(blob), phase));
     A_CHECK(csdrb_shift_addition_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
                                          (const shift_addition_data_t*)g_ctx.buf[2], d_phase, input_size, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)input_size * 8, who);
+    float new_phase = 0.f;
+    A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return new_phase;
+}
+
+float shift_math_cc(complexf* input, complexf* output, int input_size, float rate, float starting_phase)
+{
+    const char* who = "shift_math_cc";
+    if (input_size <= 0) return starting_phase;
+    A_BEGIN(who);
+    // slot 0: input, 1: output, 2: rate at +0 and phase at +64, 3: scratch
+    A_UP(0, input, (size_t)input_size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 8 + 16), who);
+    float blob[17] = {0};
+    blob[0] = rate; blob[16] = starting_phase;
+    A_UP(2, blob, sizeof blob, who);
+    const size_t sb = csdrb_shift_math_bank_scratch_bytes(1, input_size);
+    A_CHECK(g_ctx.reserve(3, sb + 16), who);
+    float* d_rate = reinterpret_cast<float*>(g_ctx.buf[2]);
+    float* d_phase = d_rate + 16;
+    A_CHECK(csdrb_shift_math_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size, d_rate, d_phase, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
     A_DOWN(output, 1, (size_t)input_size * 8, who);
     float new_phase = 0.f;
     A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);

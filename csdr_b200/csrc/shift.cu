@@ -183,6 +183,84 @@ shift_addfast_bank_kernel(const float2* __restrict__ in, long in_stride, float2*
     }
 }
 
+// shift_math_cc (libcsdr.c:186-209): no phasor recursion -- each sample is rotated by cos/sin of a float phase that advances by ONE ROUNDED
+// ADDITION PER SAMPLE and is wrapped into [0, 2*PI] by the reference's while loops.  That chain is sequential over the whole stream, so it
+// is walked once per channel by one thread which drops a seed every MATH_SEG samples (shift_math_chain_kernel); the expensive part, a
+// double-precision sincos per sample, then runs with one lane per (channel, segment) re-walking its MATH_SEG additions
+// (shift_math_bank_kernel, same padded-tile data movement as shift_bank_kernel).  Bit-exact phases, samples within an ulp of the seed.
+constexpr int MATH_SEG = 256;
+#define TWO_PI_F 6.28318530717958647692f          // 2*PI in float arithmetic: (float)2 * PI_F rounds to this float
+
+__device__ __forceinline__ float math_step(float ph, float inc)
+{
+    ph = __fadd_rn(ph, inc);
+    if (!(fabsf(ph) < 67108864.f)) return ph;                 // the reference's loops would not terminate here either (2*PI below one ulp)
+    while (ph > TWO_PI_F) ph = __fsub_rn(ph, TWO_PI_F);       // libcsdr.c:205-206, literally: a huge starting phase takes many rounded steps
+    while (ph < 0.f) ph = __fadd_rn(ph, TWO_PI_F);
+    return ph;
+}
+
+__global__ void shift_math_chain_kernel(const float* __restrict__ rates, float* __restrict__ phase_io, float* __restrict__ seg_phase,
+                                        int channels, int n, int nseg)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= channels) return;
+    const float inc = __fmul_rn(__fmul_rn(rates[c], 2.f), PI_F);     // rate *= 2; phase_increment = rate*PI  (:188,191)
+    float ph = phase_io[c];
+    for (int k = 0; k < nseg; k++) {
+        seg_phase[(long)c * nseg + k] = ph;
+        const int len = min(MATH_SEG, n - k * MATH_SEG);
+        for (int j = 0; j < len; j++) ph = math_step(ph, inc);
+    }
+    phase_io[c] = ph;
+}
+
+__global__ void __launch_bounds__(128)
+shift_math_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                       const float* __restrict__ rates, const float* __restrict__ seg_phase, int n, int nseg)
+{
+    __shared__ float2 tile_all[4][32 * SH_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = tile_all[warp];
+    const int ch = blockIdx.y;
+    const int k0 = (blockIdx.x * 4 + warp) * 32;              // first segment of this warp
+    if (k0 >= nseg) return;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float inc = __fmul_rn(__fmul_rn(rates[ch], 2.f), PI_F);
+    const int k = k0 + lane;
+    const bool live = k < nseg;
+    const int my_len = live ? min(MATH_SEG, n - k * MATH_SEG) : 0;
+    float ph = live ? seg_phase[(long)ch * nseg + k] : 0.f;
+    const int rows = min(32, nseg - k0);
+    const int max_len = min(MATH_SEG, n - k0 * MATH_SEG);    // the first segment of the warp is never the short one
+    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * MATH_SEG + t0 + lane;
+            const int len_r = min(MATH_SEG, n - (k0 + r) * MATH_SEG);
+            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+        if (live) {
+            float2* row = tile + lane * SH_PITCH;
+            const int steps = min(SH_TILE, my_len - t0);
+            for (int j = 0; j < steps; j++) {
+                const float c = (float)cos((double)ph), s = (float)sin((double)ph);
+                const float2 v = row[j];
+                row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                ph = math_step(ph, inc);
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * MATH_SEG + t0 + lane;
+            const int len_r = min(MATH_SEG, n - (k0 + r) * MATH_SEG);
+            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
+        }
+        __syncwarp();
+    }
+}
+
 // decimating variant: status per channel {decimation_remain, starting_phase, output_size} (libcsdr_gpl.h:39-44)
 __global__ void dshift_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                               const float3* __restrict__ params, int n, int decimation, int* __restrict__ remain_io,
@@ -296,6 +374,27 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+size_t shift_math_scratch_bytes(int channels, int n)
+{
+    const size_t nseg = (size_t)(((n > 0 ? n : 1) + MATH_SEG - 1) / MATH_SEG);
+    return (size_t)(channels > 0 ? channels : 1) * nseg * sizeof(float) + 16;
+}
+
+int launch_shift_math_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, const float* d_rates,
+                           float* d_phase_io, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    const int nseg = (n + MATH_SEG - 1) / MATH_SEG;
+    if (!d_scratch || scratch_bytes < (size_t)channels * nseg * sizeof(float)) { set_error("shift_math bank: scratch too small"); return -1; }
+    float* seg_phase = static_cast<float*>(d_scratch);
+    shift_math_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(d_rates, d_phase_io, seg_phase, channels, n, nseg);
+    CSDRB_CUDA(cudaGetLastError());
+    dim3 grid((nseg + 127) / 128, channels);
+    shift_math_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, d_rates, seg_phase, n, nseg);
     CSDRB_CUDA(cudaGetLastError());
     return 2;
 }

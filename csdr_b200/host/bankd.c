@@ -10,7 +10,7 @@
  * Per channel the sample stream is exactly the README graph's:
  *   convert_u8_f | shift_addition_cc r | fir_decimate_cc D bw W | fmdemod_quadri_cf [| limit_ff L | deemphasis_nfm_ff 48000 | fastagc_ff 1024 R | convert_f_s16]
  * as ONE continuous stream (the CLI's per-process block framing -- stale tail blocks at EOF, the zero block deemphasis_nfm_ff emits
- * first -- is process plumbing and is not reproduced; tests/test_gpu_bankd.py compares against the oracle run over the whole stream).
+ * first -- is process plumbing and is not reproduced; tests/test_gpu_zz_bankd.py compares against the oracle run over the whole stream).
  *
  * usage: csdr-bankd [--in -|HOST:PORT] [--u8|--f32] [--decimation D] [--bw TRANSITION_BW] [--window W] [--block SAMPLES]
  *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N]  RATE:SINK [RATE:SINK ...]
@@ -153,6 +153,9 @@ int main(int argc, char **argv)
     if (!nfm && strcmp(tail, "none")) die("--tail is nfm or none");
     if (C == 0) die("no channels (RATE:SINK ...)");
     if (block <= 0 || (block & 1)) die("--block must be a positive even number of samples");
+    if (D <= 0 || (D & 1)) die("--decimation must be a positive even number (the fused kernels exist for 10 and 50)");
+    if (!(bw > 0.f && bw < 0.5f)) die("--bw must be a transition bandwidth between 0 and 0.5");
+    if (!(limit > 0.f) || !(agc_ref > 0.f)) die("--limit and --agc-ref must be positive");
     signal(SIGPIPE, SIG_IGN);
 
     /* ---- filter and bank ---------------------------------------------------------------------------------------------------- */

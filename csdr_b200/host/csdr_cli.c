@@ -265,6 +265,21 @@ static int cmd_shift_unroll_cc(int argc, char **argv)                      /* cs
     }
 }
 
+static int cmd_shift_math_cc(int argc, char **argv)                        /* csdr.c:703-718 */
+{
+    if (argc <= 2) return complain("need required parameter (rate)");
+    float phase = 0, rate = 0; sscanf(argv[2], "%g", &rate);
+    if (!announce_block(open_block())) return -2;
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block), *out = must_alloc(sizeof(complexf) * (size_t)block);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        if (!fread(in, sizeof(complexf), (size_t)block, stdin)) return 0;
+        phase = shift_math_cc(in, out, block, rate, phase);
+        fwrite(out, sizeof(complexf), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_shift_addfast_cc(int argc, char **argv)                     /* csdr.c:749-798 */
 {
     G.wideband = 1;
@@ -625,6 +640,7 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
     {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
     {"shift_unroll_cc", cmd_shift_unroll_cc, "shift_unroll_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
+    {"shift_math_cc", cmd_shift_math_cc, "shift_math_cc <rate>"},
     {"shift_addfast_cc", cmd_shift_addfast_cc, "shift_addfast_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
     {"decimating_shift_addition_cc", cmd_decimating_shift_addition_cc, "decimating_shift_addition_cc <rate> [decimation]"},
     {"fft_cc", cmd_fft_cc, "fft_cc <fft_size> <out_of_every_n_samples> [window]"},

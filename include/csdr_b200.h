@@ -101,6 +101,8 @@ void  log_ff(float *input, float *output, int size, float add_db);
 typedef struct shift_unroll_data_s { float *dsin; float *dcos; float phase_increment; int size; } shift_unroll_data_t;
 shift_unroll_data_t shift_unroll_init(float rate, int size);
 float shift_unroll_cc(complexf *input, complexf *output, int input_size, shift_unroll_data_t *d, float starting_phase);
+/* shift_math (libcsdr.h:171; libcsdr.c:186-209): cos/sin of a float phase advanced by one rounded addition per sample, wrapped to [0, 2*PI] */
+float shift_math_cc(complexf *input, complexf *output, int input_size, float rate, float starting_phase);
 /* shift_addfast (libcsdr.h:189-197; libcsdr.c:307-317, 396-433): recursion advanced once per four samples; only input_size/4*4
  * samples of `output` are written, like the reference */
 typedef struct shift_addfast_data_s { float dsin[4]; float dcos[4]; float phase_increment; } shift_addfast_data_t;
@@ -244,6 +246,11 @@ int csdrb_apply_window_rows_c(const complexf *d_in, complexf *d_out, const float
 int csdrb_logpower_cf(const complexf *d_in, float *d_out, long n, float add_db, void *stream);
 int csdrb_accumulate_power_cf(const complexf *d_in, float *d_acc, long n, void *stream);
 int csdrb_log_ff(const float *d_in, float *d_out, long n, float add_db, void *stream);
+/* shift_math_cc bank: d_rates[c] is the plain rate argument; d_phase_io[c] the carried float phase.  The phase chain is sequential over the
+ * whole block (one thread per channel walks it), the rotation itself runs fully parallel. */
+size_t csdrb_shift_math_bank_scratch_bytes(int channels, int input_size);
+int csdrb_shift_math_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
+                             const float *d_rates, float *d_phase_io, void *d_scratch, size_t scratch_bytes, void *stream);
 /* shift_addfast_cc bank: d_params[c] = shift_addfast_init(rate_c); one reference call per `chunk` samples (csdr.c:781-791 uses 1024);
  * scratch as for the shift_addition bank (csdrb_shift_addition_bank_scratch_bytes) */
 int csdrb_shift_addfast_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,

@@ -423,6 +423,24 @@ float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *ds
     return wrap_pm_pi(starting_phase + n * phase_increment);
 }
 
+/* [ref libcsdr.c:186-209] shift_math_cc: no recursion at all -- every sample is rotated by cos/sin of a float phase that advances by
+ * one rounded addition per sample and is wrapped into [0, 2*PI] with the reference's while loops (2*PI is the float product). */
+float oracle_shift_math_cc(const ocf32 *in, ocf32 *out, int n, float rate, float starting_phase)
+{
+    rate *= 2;
+    float phase = starting_phase;
+    const float inc = rate * kPi;
+    for (int k = 0; k < n; k++) {
+        const float c = (float)cos((double)phase), s = (float)sin((double)phase);
+        out[k].i = c * in[k].i - s * in[k].q;
+        out[k].q = s * in[k].i + c * in[k].q;
+        phase += inc;
+        while (phase > 2 * kPi) phase -= 2 * kPi;
+        while (phase < 0) phase += 2 * kPi;
+    }
+    return phase;
+}
+
 /* [ref libcsdr.c:307-317] shift_addfast_init: the phasor after 1..4 steps of phase_increment = 2*rate*PI (float), each angle a float
  * product, sin/cos in double rounded to float.  out9 = dsin[4], dcos[4], phase_increment (libcsdr.h:189-194 member order). */
 void oracle_shift_addfast_init(float rate, float *out9)

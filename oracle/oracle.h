@@ -85,6 +85,8 @@ void  oracle_log_ff(const float *in, float *out, int size, float add_db);
 float oracle_shift_unroll_init(float rate, int size, float *dsin, float *dcos);            /* returns phase_increment */
 float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *dsin, const float *dcos, float phase_increment, float starting_phase);
 
+/* shift_math: libcsdr.c:186-209 */
+float oracle_shift_math_cc(const ocf32 *in, ocf32 *out, int n, float rate, float starting_phase);
 /* shift_addfast: libcsdr.h:189-197, libcsdr.c:307-317, 396-433.  d9 = dsin[4], dcos[4], phase_increment */
 void  oracle_shift_addfast_init(float rate, float *d9);
 float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d9, float starting_phase);

@@ -111,6 +111,7 @@ class Oracle:
         L.oracle_shift_unroll_init.argtypes = [C.c_float, C.c_int, fp, fp]; L.oracle_shift_unroll_init.restype = C.c_float
         L.oracle_shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, fp, C.c_float, C.c_float]
         L.oracle_shift_unroll_cc.restype = C.c_float
+        L.oracle_shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.oracle_shift_math_cc.restype = C.c_float
         L.oracle_shift_addfast_init.argtypes = [C.c_float, fp]
         L.oracle_shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, C.c_float]; L.oracle_shift_addfast_cc.restype = C.c_float
         L.oracle_dft_c2c.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_int]
@@ -245,6 +246,14 @@ class Oracle:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = self.L.oracle_shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, _p(ds, C.c_float), _p(dc, C.c_float), inc, phase)
+        return y, float(np.float32(phase))
+
+    def shift_math_cc(self, x, rate, phase=0.0, chunk=None):
+        """one call per `chunk` samples (the CLI uses its 1024-sample buffer, csdr.c:703-718); the phase chain does not depend on the cut"""
+        x = _c64(x); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = self.L.oracle_shift_math_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, rate, phase)
         return y, float(np.float32(phase))
 
     def shift_addfast_init(self, rate):
@@ -407,6 +416,7 @@ class Ref:
         L.log_ff.argtypes = [fp, fp, C.c_int, C.c_float]
         L.shift_unroll_init.argtypes = [C.c_float, C.c_int]; L.shift_unroll_init.restype = self._Unroll
         L.shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
+        L.shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
         L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = self._AddFast
         L.shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
         L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
@@ -546,6 +556,13 @@ class Ref:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = self.L.shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
+        return y, float(np.float32(phase))
+
+    def shift_math_cc(self, x, rate, phase=0.0, chunk=None):
+        x = _c64(x); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = self.L.shift_math_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, rate, phase)
         return y, float(np.float32(phase))
 
     def shift_addfast_init(self, rate):

@@ -118,6 +118,9 @@ def main():
     g["addfast_steps"] = r.shift_addfast_init(-0.085)
     y, ph = r.shift_addfast_cc(g["shift_in"], -0.085, 0.0, 1024)
     g["addfast_out"], g["addfast_phase"] = y, np.float32(ph)
+    # --- shift_math_cc (8f rank 3): one call per 1024 samples like the CLI, starting phase outside [0, 2*PI]
+    y, ph = r.shift_math_cc(g["shift_in"], -0.085, -7.5, 1024)
+    g["math_out"], g["math_phase"] = y, np.float32(ph)
     out = Path(__file__).with_name("hotpath_golden.npz")
     np.savez_compressed(out, **g)
     print(f"wrote {out} ({out.stat().st_size} bytes, {len(g)} arrays)")

@@ -172,3 +172,14 @@ def build_full(out_dir: Path):
         subprocess.run(["gcc", "-std=gnu99", "-O2", "-Wall", f"-I{ROOT / 'include'}", str(bankd_src), "-o", str(out_dir / "csdr-bankd_emul"),
                         f"-L{out_dir}", "-lcsdr_b200_emul", "-lm", f"-Wl,-rpath,{out_dir}"], check=True, capture_output=True)
     return lib, cli
+
+
+_full = None
+
+
+def build_full_once(tmp_path_factory):
+    """one build of the whole emulated library per test process, shared by the modules that need it"""
+    global _full
+    if _full is None:
+        _full = build_full(tmp_path_factory.mktemp("emul_full"))
+    return _full

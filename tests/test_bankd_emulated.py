@@ -1,6 +1,6 @@
 """CPU tier: csdr-bankd (host/bankd.c) linked against the emulated library -- the daemon's streaming bookkeeping (tails of the wideband
 stream, the de-emphasis FIR's carried inputs, AGC block remainders), TCP ingest and TCP sink, checked against the oracle without a GPU.
-Same test bodies as tests/test_gpu_bankd.py."""
+Same test bodies as tests/test_gpu_zz_bankd.py."""
 import sys
 from pathlib import Path
 
@@ -12,16 +12,15 @@ sys.path.insert(0, str(ROOT / "tests"))
 import emul_build  # noqa: E402
 
 pytest.importorskip("torch")
-import test_gpu_bankd as g  # noqa: E402
+import test_gpu_zz_bankd as g  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def bankd(tmp_path_factory):
     if not emul_build.available():
         pytest.skip("needs g++ and the CUDA toolkit headers")
-    out = tmp_path_factory.mktemp("emul_full")
-    emul_build.build_full(out)
-    return str(out / "csdr-bankd_emul")
+    lib, _cli = emul_build.build_full_once(tmp_path_factory)
+    return str(lib.parent / "csdr-bankd_emul")
 
 
 test_nfm_bank_equals_the_readme_graph_per_channel = g.test_nfm_bank_equals_the_readme_graph_per_channel

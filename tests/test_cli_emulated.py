@@ -26,7 +26,7 @@ def clis(tmp_path_factory):
         pytest.skip("needs g++ and the CUDA toolkit headers")
     if not g.REF.exists():
         pytest.skip("oracle/_ref/csdr_ref not built (needs /root/reference at build time)")
-    lib, cli = emul_build.build_full(tmp_path_factory.mktemp("emul_full"))
+    lib, cli = emul_build.build_full_once(tmp_path_factory)
     saved = g.LIB
     g.LIB = lib                                                            # what the LD_PRELOAD test injects into the reference binary
     yield str(cli), str(g.REF)
@@ -44,3 +44,6 @@ test_fft_commands = g.test_fft_commands
 test_spectrum_and_unroll_commands = g.test_spectrum_and_unroll_commands
 test_dynamic_bufsize_preamble = g.test_dynamic_bufsize_preamble
 test_reference_binary_runs_on_our_library = g.test_reference_binary_runs_on_our_library
+
+import test_gpu_zz_shift_math as zz  # noqa: E402
+test_shift_math_command = zz.test_shift_math_command

@@ -68,6 +68,34 @@ def P(a):
     return a.ctypes.data
 
 
+# ---- write guards: every array made by Z()/ZL() sits between two canary regions that are checked when the test ends -------------------
+_GUARD = 512
+_guarded = []
+
+
+def Z(shape, dtype=np.float64):
+    """np.zeros with canaries before and after (and 16-byte alignment): an out-of-bounds write of a kernel trips the check below"""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.full(n + 2 * _GUARD + 32, 0xA5, np.uint8)
+    off = _GUARD + ((-(raw.ctypes.data + _GUARD)) % 16)
+    raw[off:off + n] = 0
+    _guarded.append((raw, off, n))
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def ZL(a):
+    return Z(a.shape, a.dtype)
+
+
+@pytest.fixture(autouse=True)
+def _check_guards():
+    _guarded.clear()
+    yield
+    for raw, off, n in _guarded:
+        assert np.all(raw[:off] == 0xA5) and np.all(raw[off + n:] == 0xA5), "a kernel wrote outside one of its buffers"
+    _guarded.clear()
+
+
 def _cplx(rng, *shape, amp=1.0):
     return ((rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)) * amp).astype(np.complex64)
 
@@ -106,8 +134,8 @@ def test_k4_fmdemod_bank_and_audio_tail(elementwise, oracle):
     ch, n = 3, 10_001
     x = _cplx(rng, ch, n + 1)[:, :n]                                       # odd length inside an even stride
     stride = x.strides[0] // 8
-    last = _cplx(rng, ch); last_out = np.zeros(ch, np.complex64)
-    out = np.zeros((ch, n + 3), np.float32)
+    last = _cplx(rng, ch); last_out = Z(ch, np.complex64)
+    out = Z((ch, n + 3), np.float32)
     assert elementwise.emul_launch_fmdemod_quadri_bank(P(x), stride, P(out), out.shape[1], ch, n, P(last), P(last_out)) >= 0
     for c in range(ch):
         want, wl = oracle.fmdemod_quadri_cf(np.ascontiguousarray(x[c]), complex(last[c]))
@@ -121,11 +149,11 @@ def test_k4_fmdemod_bank_and_audio_tail(elementwise, oracle):
 def test_spectrum_side_path(elementwise, oracle):
     rng = np.random.default_rng(2)
     size, rows = 1000, 5
-    x = _cplx(rng, rows * size); w = oracle.precalculate_window(size, "BLACKMAN"); out = np.zeros_like(x)
+    x = _cplx(rng, rows * size); w = oracle.precalculate_window(size, "BLACKMAN"); out = ZL(x)
     assert elementwise.emul_launch_apply_window_rows(P(x), P(out), P(w), size, rows) >= 0
     want = np.concatenate([oracle.apply_precalculated_window_c(x[r * size:(r + 1) * size], w) for r in range(rows)])
     assert np.array_equal(out, want)
-    p = np.zeros(x.size, np.float32)
+    p = Z(x.size, np.float32)
     assert elementwise.emul_launch_power(P(x), None, P(p), x.size, -70.0, 0) >= 0
     assert np.abs(p - oracle.logpower_cf(x, -70.0)).max() <= 2e-5
 
@@ -139,8 +167,8 @@ def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):
     x = _cplx(rng, n)
     params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
     ph0 = rng.uniform(-3, 3, ch).astype(np.float32); ph = ph0.copy()
-    out = np.zeros((ch, n), np.complex64)
-    sb = shift.emul_shift_bank_scratch_bytes(ch, n, chunk); scratch = np.zeros(sb + 16, np.uint8)
+    out = Z((ch, n), np.complex64)
+    sb = shift.emul_shift_bank_scratch_bytes(ch, n, chunk); scratch = Z(sb + 16, np.uint8)
     assert shift.emul_launch_shift_addition_bank(P(x), 0, P(out), n, ch, n, P(params), P(ph), chunk, P(scratch), sb) >= 0, shift.emul_last_error()
     for c, r in enumerate(rates):
         want, wph = oracle.shift_addition_cc(x, float(r), float(ph0[c]), chunk or None)
@@ -160,9 +188,9 @@ def test_k2_decimating_and_unroll(shift, oracle):
     rates = np.array([0.1, -0.3, 0.05], np.float32); ch = rates.size
     xs = _cplx(rng, ch, n)
     params = np.array([oracle.shift_addition_init(float(np.float32(r) * dec)) for r in rates], np.float32)      # decimating_shift_addition_init
-    remain = np.array([0, 3, 6], np.int32); ph = np.array([0.0, 1.0, -2.0], np.float32); outsz = np.zeros(ch, np.int32)
+    remain = np.array([0, 3, 6], np.int32); ph = np.array([0.0, 1.0, -2.0], np.float32); outsz = Z(ch, np.int32)
     r0, p0 = remain.copy(), ph.copy()
-    out = np.zeros((ch, n // dec + 2), np.complex64)
+    out = Z((ch, n // dec + 2), np.complex64)
     assert shift.emul_launch_decimating_shift_bank(P(xs), n, P(out), out.shape[1], ch, n, P(params), dec, P(remain), P(ph), P(outsz)) >= 0
     for c, r in enumerate(rates):
         want, (wr, wp) = oracle.decimating_shift_addition_cc(xs[c], float(r), dec, int(r0[c]), float(p0[c]))
@@ -176,12 +204,28 @@ def test_k2_decimating_and_unroll(shift, oracle):
         oracle.L.oracle_shift_unroll_init(float(r), size, tabs[2 * c].ctypes.data_as(C.POINTER(C.c_float)), tabs[2 * c + 1].ctypes.data_as(C.POINTER(C.c_float)))
     dsin = np.stack(tabs[0::2]); dcos = np.stack(tabs[1::2])
     params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
-    ph = np.zeros(ch, np.float32); out = np.zeros((ch, n), np.complex64)
-    sb = shift.emul_shift_bank_scratch_bytes(ch, n, size); scratch = np.zeros(sb + 16, np.uint8)
+    ph = Z(ch, np.float32); out = Z((ch, n), np.complex64)
+    sb = shift.emul_shift_bank_scratch_bytes(ch, n, size); scratch = Z(sb + 16, np.uint8)
     assert shift.emul_launch_shift_unroll_bank(P(x), 0, P(out), n, ch, n, P(params), P(dsin), P(dcos), size, size, P(ph), P(scratch), sb) >= 0
     for c, r in enumerate(rates):
         want, wph = oracle.shift_unroll_cc(x, float(r), 0.0, size)
         assert np.float32(wph) == ph[c] and rel_rms(out[c], want) < 1e-7
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 10_001, 40_000])
+def test_shift_math_bank(shift, oracle, n):
+    """one rounded phase addition per sample: the per-channel chain thread drops a seed every 256 samples, the lanes re-walk their segment"""
+    rng = np.random.default_rng(n)
+    rates = np.array([-0.5, -0.31, -0.085, 0.0, 1e-4, 0.2, 0.4999, 0.5], np.float32); ch = rates.size
+    x = _cplx(rng, n)
+    ph0 = np.array([0.0, 3.0, -7.5, 100.0, 6.2831855, 1.0, 2.0, -0.0], np.float32); ph = ph0.copy()   # starts outside [0, 2*PI] take the reference's loops
+    out = Z((ch, n), np.complex64)
+    sb = shift.emul_shift_math_scratch_bytes(ch, n); scratch = Z(sb + 16, np.uint8)
+    assert shift.emul_launch_shift_math_bank(P(x), 0, P(out), n, ch, n, P(rates), P(ph), P(scratch), sb) >= 0, shift.emul_last_error()
+    for c, r in enumerate(rates):
+        want, wph = oracle.shift_math_cc(x, float(r), float(ph0[c]))
+        assert np.float32(wph).view(np.uint32) == ph[c].view(np.uint32), (c, wph, ph[c])    # the carried phase, bit for bit
+        assert rel_rms(out[c], want) < 1e-7, c
 
 
 # ------------------------------------------------------------------------------------------------------------------ K5 / K6 / audio tail
@@ -191,9 +235,9 @@ def test_k5_fractional_decimator_bit_exact(audio, oracle, rate, points, n):
     ch = 3
     x = rng.uniform(-1, 1, (ch, n)).astype(np.float32)
     cap = int(n / rate) + 8
-    out = np.zeros((ch, cap), np.float32)
-    state = np.zeros((ch, 3), np.int32); state[:, 0] = np.array([points // 2 - 1], np.float32).view(np.int32)[0]       # where = -xifirst at init
-    sb = audio.emul_fracdec_scratch_bytes(ch, n, rate); scratch = np.zeros(sb + 16, np.uint8)
+    out = Z((ch, cap), np.float32)
+    state = Z((ch, 3), np.int32); state[:, 0] = np.array([points // 2 - 1], np.float32).view(np.int32)[0]       # where = -xifirst at init
+    sb = audio.emul_fracdec_scratch_bytes(ch, n, rate); scratch = Z(sb + 16, np.uint8)
     assert audio.emul_launch_fractional_decimator_bank(P(x), n, P(out), cap, ch, n, rate, points, None, 0, P(state), P(scratch), sb) >= 0, audio.emul_last_error()
     for c in range(ch):
         want = oracle.fractional_decimator_ff(x[c], rate, points)
@@ -206,13 +250,13 @@ def test_k6_fastagc_and_deemphasis_bit_exact(audio, oracle):
     ch, block, nblocks = 4, 1024, 9
     env = np.repeat(rng.uniform(0.001, 1.0, nblocks).astype(np.float32), block)
     x = np.stack([rng.uniform(-1, 1, env.size).astype(np.float32) * env * s for s in (1.0, 0.01, 0.0, 30.0)])
-    out = np.zeros_like(x); state = np.zeros((ch, 3), np.float32); hist = np.zeros((ch, 2, block), np.float32)
-    sb = audio.emul_fastagc_scratch_bytes(ch, nblocks); scratch = np.zeros(sb + 16, np.uint8)
+    out = ZL(x); state = Z((ch, 3), np.float32); hist = Z((ch, 2, block), np.float32)
+    sb = audio.emul_fastagc_scratch_bytes(ch, nblocks); scratch = Z(sb + 16, np.uint8)
     assert audio.emul_launch_fastagc_bank(P(x), x.shape[1], P(out), out.shape[1], ch, block, nblocks, 0.8, P(state), P(hist), P(scratch), sb) >= 0
     for c in range(ch):
         assert np.array_equal(out[c], oracle.fastagc_ff(x[c], block, 0.8), equal_nan=True), c
     xb = rng.uniform(-1, 1, (37, 5_001)).astype(np.float32); last = np.linspace(-0.5, 0.5, 37).astype(np.float32); last[3] = np.nan
-    l0 = last.copy(); yb = np.zeros_like(xb)
+    l0 = last.copy(); yb = ZL(xb)
     assert audio.emul_launch_deemphasis_wfm_bank(P(xb), xb.shape[1], P(yb), yb.shape[1], 37, xb.shape[1], 75e-6, 240000, P(last)) >= 0
     for c in range(37):
         want, wl = oracle.deemphasis_wfm_ff(xb[c], 75e-6, 240000, float(l0[c]))
@@ -232,7 +276,7 @@ def test_nfm_deemphasis_fir_and_fused_limiter(audio, oracle, rate):
         for c in range(ch):
             want = oracle.deemphasis_nfm_ff(oracle.limit_ff(x[c], 1.0), taps)
             assert np.abs(out[c, :rc] - want).max() <= 1e-6 * np.abs(taps).sum(), (n, c)
-    y = np.zeros(GOLD["nfm_in"].size, np.float32); xin = np.ascontiguousarray(GOLD["nfm_in"])
+    y = Z(GOLD["nfm_in"].size, np.float32); xin = np.ascontiguousarray(GOLD["nfm_in"])
     rc = audio.emul_launch_deemphasis_nfm_bank(P(xin), xin.size, P(y), y.size, 1, xin.size, rate, 0.0)
     assert rel_rms(y[:rc], GOLD[f"nfm_out_{rate}"]) < 1e-5                # the compiled reference's output
     assert audio.emul_launch_deemphasis_nfm_bank(P(xin), xin.size, P(y), y.size, 1, xin.size, 22050, 0.0) == 0
@@ -274,12 +318,12 @@ def test_fused_ddc_bank_matches_the_unfused_chain(ddc, oracle, D, bw, demod):
     wide = sum(0.3 * np.exp(1j * (2 * np.pi * (-float(r)) * t + np.cumsum(0.05 * np.sin(2 * np.pi * t / (2000.0 + 100 * k))))) for k, r in enumerate(rates))
     x = _aligned(n, np.complex64); x[:] = (wide + 0.01 * (rng.normal(size=n) + 1j * rng.normal(size=n))).astype(np.complex64)
     params = np.array([oracle.shift_addition_init(float(r)) for r in rates], np.float32)
-    ph = np.zeros(ch, np.float32)
+    ph = Z(ch, np.float32)
     n_out = (n - T) // D + 1
     stride = n_out + (n_out & 1)
-    out = np.zeros((ch, stride), np.float32 if demod else np.complex64)
-    last_out = np.zeros(ch, np.complex64); launches = C.c_int(0)
-    sb = ddc.emul_ddc_bank_scratch_bytes(ch, n, 1024, 0); scratch = np.zeros(sb + 64, np.uint8)
+    out = Z((ch, stride), np.float32 if demod else np.complex64)
+    last_out = Z(ch, np.complex64); launches = C.c_int(0)
+    sb = ddc.emul_ddc_bank_scratch_bytes(ch, n, 1024, 0); scratch = Z(sb + 64, np.uint8)
     fp = taps.ctypes.data_as(C.c_void_p)
     rc = ddc.emul_launch_ddc_bank(P(x), n, ch, P(params), P(ph), 1024, 0, D, fp, T, demod, P(out), stride, None, P(last_out) if demod else None, P(scratch), sb,
                                   C.addressof(launches))
@@ -300,7 +344,7 @@ def test_k7_fft_every_size_both_directions(fft):
             assert fft.emul_launch_fft_c2c_batch(P(x), n, P(y), n, n, 2, inv) >= 0, fft.emul_last_error()
             want = np.fft.ifft(x.astype(np.complex128), axis=1) * n if inv else np.fft.fft(x.astype(np.complex128), axis=1)
             assert rel_rms(y, want) < 1e-6, (n, inv)                      # same bar as tests/test_gpu_parity2.py::test_fft_all_sizes_vs_float64_dft
-        buf = _cplx(rng, n + 3); out = np.zeros(n + 3, np.complex64)
+        buf = _cplx(rng, n + 3); out = Z(n + 3, np.complex64)
         off = 1 if (buf.ctypes.data % 16) == 0 else 0                     # a row that is only 8-byte aligned
         fft.emul_launch_fft_c2c_batch(P(buf[off:]), n, P(out[off:]), n, n, 1, 0)
         assert rel_rms(out[off:off + n], np.fft.fft(buf[off:off + n].astype(np.complex128))) < 1e-6
@@ -308,9 +352,9 @@ def test_k7_fft_every_size_both_directions(fft):
 
 
 def _overlap_add(x, H, N, isz):
-    nb = x.size // isz; out = np.zeros(nb * isz + N - isz, np.complex128)
+    nb = x.size // isz; out = Z(nb * isz + N - isz, np.complex128)
     for b in range(nb):
-        blk = np.zeros(N, np.complex128); blk[:isz] = x[b * isz:(b + 1) * isz]
+        blk = Z(N, np.complex128); blk[:isz] = x[b * isz:(b + 1) * isz]
         out[b * isz:b * isz + N] += np.fft.ifft(np.fft.fft(blk) * H)
     return out[:nb * isz], out[nb * isz:]
 
@@ -322,7 +366,7 @@ def test_k9_overlap_add_bank(fft, N, isz, nb, bpc):
     rng = np.random.default_rng(N + isz)
     ch = 2
     x = _cplx(rng, ch, nb * isz); H = _cplx(rng, ch, N)
-    y = np.zeros_like(x); tail = np.zeros((ch, N), np.complex64)
+    y = ZL(x); tail = Z((ch, N), np.complex64)
     assert fft.emul_launch_olafir_bank(P(x), x.shape[1], P(y), y.shape[1], ch, N, isz, nb, P(H), N, P(tail), bpc) >= 0, fft.emul_last_error()
     for c in range(ch):
         want, wt = _overlap_add(x[c].astype(np.complex128), H[c].astype(np.complex128), N, isz)
@@ -330,8 +374,8 @@ def test_k9_overlap_add_bank(fft, N, isz, nb, bpc):
         if N > isz:
             assert rel_rms(tail[c, :N - isz], wt) < 2e-6
     h = nb // 2                                                            # two calls carrying the tail == one call
-    xa = np.ascontiguousarray(x[:, :h * isz]); xb = np.ascontiguousarray(x[:, h * isz:]); ya = np.zeros_like(xa); yb = np.zeros_like(xb)
-    t = np.zeros((ch, N), np.complex64)
+    xa = np.ascontiguousarray(x[:, :h * isz]); xb = np.ascontiguousarray(x[:, h * isz:]); ya = ZL(xa); yb = ZL(xb)
+    t = Z((ch, N), np.complex64)
     fft.emul_launch_olafir_bank(P(xa), xa.shape[1], P(ya), ya.shape[1], ch, N, isz, h, P(H), N, P(t), bpc)
     fft.emul_launch_olafir_bank(P(xb), xb.shape[1], P(yb), yb.shape[1], ch, N, isz, nb - h, P(H), N, P(t), bpc)
     assert rel_rms(np.concatenate([ya, yb], 1), y) < 1e-6
@@ -342,14 +386,14 @@ def test_k9_overlap_add_bank(fft, N, isz, nb, bpc):
 def test_k9_golden_and_dropin_kernel(fft, oracle):
     """the golden bandpass stream of the compiled reference through the bank kernel, and apply_fir_fft_cc's one-block kernel"""
     T = oracle.firdes_filter_len(0.05); N = 256; isz = N - T + 1
-    taps = np.zeros(N, np.complex64); taps[:T] = oracle.firdes_bandpass_c(T, -0.1, 0.2)
+    taps = Z(N, np.complex64); taps[:T] = oracle.firdes_bandpass_c(T, -0.1, 0.2)
     H = oracle.dft(taps)
     x = np.ascontiguousarray(GOLD["bp_in"]); nb = x.size // isz
-    y = np.zeros(nb * isz, np.complex64); tail = np.zeros((1, N), np.complex64)
+    y = Z(nb * isz, np.complex64); tail = Z((1, N), np.complex64)
     assert fft.emul_launch_olafir_bank(P(x), x.size, P(y), y.size, 1, N, isz, nb, P(H), N, P(tail), 4) >= 0
     assert rel_rms(y, GOLD["bp_out"][:y.size]) < 5e-6                      # same bar as the GPU test
     rng = np.random.default_rng(3)
-    blk = np.zeros(N, np.complex64); blk[:isz] = _cplx(rng, isz); last = _cplx(rng, T - 1); out = np.zeros(N, np.complex64)
+    blk = Z(N, np.complex64); blk[:isz] = _cplx(rng, isz); last = _cplx(rng, T - 1); out = Z(N, np.complex64)
     assert fft.emul_launch_apply_fir_fft(P(blk), P(H), P(last), T - 1, P(out), N) >= 0
     want = np.fft.ifft(np.fft.fft(blk.astype(np.complex128)) * H.astype(np.complex128)); want[:T - 1] += last
     assert rel_rms(out, want) < 2e-6
@@ -368,18 +412,18 @@ def test_k8_fastddc_forward_and_inverse(fft, oracle, bw, dec, shift):
         n = 5 * g.input_size; t = np.arange(n)
         x = ((np.exp(2j * np.pi * (-shift + 0.002) * t) * 0.5).astype(np.complex64) + _cplx(rng, n, amp=0.05)).astype(np.complex64)
     nb = x.size // g.input_size
-    sp = np.zeros((nb, g.fft_size), np.complex64); carry = np.zeros(max(g.overlap_length, 1), np.complex64)
+    sp = Z((nb, g.fft_size), np.complex64); carry = Z(max(g.overlap_length, 1), np.complex64)
     assert fft.emul_launch_fastddc_fwd(P(x), P(sp), P(carry), g.fft_size, g.input_size, nb) >= 0
     want_sp = np.stack(oracle.fastddc_fwd(x, g))
     assert rel_rms(sp, want_sp) < 1e-6
     assert np.array_equal(carry[:g.overlap_length], x[nb * g.input_size - g.overlap_length:nb * g.input_size])
     tf = np.empty(g.fft_size, np.complex64)
     oracle.L.oracle_fastddc_make_taps_fft(C.byref(g), shift, dec, WINDOWS["HAMMING"], _p(tf, _CF))
-    chan = np.zeros(1, np.dtype([("offsetbin", np.int32), ("sindelta", np.float32), ("cosdelta", np.float32), ("rate", np.float32)]))
+    chan = Z(1, np.dtype([("offsetbin", np.int32), ("sindelta", np.float32), ("cosdelta", np.float32), ("rate", np.float32)]))
     chan["offsetbin"] = g.offsetbin; chan["sindelta"] = g.dsadata.sindelta; chan["cosdelta"] = g.dsadata.cosdelta; chan["rate"] = g.dsadata.rate
-    remain = np.zeros(1, np.int32); phase = np.zeros(1, np.float32); total = np.zeros(1, np.int32)
-    out = np.zeros((1, nb * (g.post_input_size // g.post_decimation + 1) + 2), np.complex64)
-    sb = fft.emul_fastddc_inv_scratch_bytes(1, nb); scratch = np.zeros(sb + 16, np.uint8)
+    remain = Z(1, np.int32); phase = Z(1, np.float32); total = Z(1, np.int32)
+    out = Z((1, nb * (g.post_input_size // g.post_decimation + 1) + 2), np.complex64)
+    sb = fft.emul_fastddc_inv_scratch_bytes(1, nb); scratch = Z(sb + 16, np.uint8)
     rc = fft.emul_launch_fastddc_inv_bank(P(want_sp), nb, P(tf), P(chan), 1, g.fft_size, g.fft_inv_size, g.pre_decimation, g.scrap, g.post_input_size, g.post_decimation,
                                           P(remain), P(phase), P(out), out.shape[1], P(total), P(scratch), sb)
     assert rc >= 0, fft.emul_last_error()

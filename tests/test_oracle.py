@@ -152,6 +152,19 @@ def test_golden_and_ref_shift_addfast(oracle):
         assert rel_rms(a, b) < 1e-6 and pa == pb and np.all(a[1020:1022] == 0) and np.all(b[1020:1022] == 0)
 
 
+def test_golden_and_ref_shift_math(oracle):
+    y, ph = oracle.shift_math_cc(GOLD["shift_in"], -0.085, -7.5, 1024)
+    assert np.float32(ph) == GOLD["math_phase"] and rel_rms(y, GOLD["math_out"]) < TIGHT     # phase chain bit-exact; seeds: sincosf in the build
+    if have_ref():
+        from oracle.pyoracle import Ref
+        r = Ref()
+        z = (np.random.default_rng(8).standard_normal(30_000) + 1j * np.random.default_rng(9).standard_normal(30_000)).astype(np.complex64)
+        for rate in (-0.5, -0.31, 0.0, 1e-4, 0.2, 0.4999, 0.5):
+            for ph0, chunk in ((0.0, 1024), (3.0, None), (-7.5, 1000), (100.0, 1024)):
+                (a, pa), (b, pb) = oracle.shift_math_cc(z, rate, ph0, chunk), r.shift_math_cc(z, rate, ph0, chunk)
+                assert np.float32(pa) == np.float32(pb) and rel_rms(a, b) < TIGHT, (rate, ph0, chunk)
+
+
 def test_golden_spectrum_and_unroll(oracle, ref=None):
     assert rel_rms(oracle.precalculate_window(1024, "HAMMING"), GOLD["win_hamming_1024"]) < TIGHT
     assert np.abs(oracle.logpower_cf(GOLD["spec_in"], -70.0) - GOLD["logpower_out"]).max() < 2e-5          # dB; an ulp at |x| ~ 100

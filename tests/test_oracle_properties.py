@@ -60,6 +60,14 @@ def test_shift_addition_any_rate_and_chunking(oracle, ref, seed, n, rate, phase,
 
 
 @settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), phase=st.floats(-50.0, 50.0, width=32))
+def test_shift_math_any_rate(oracle, ref, seed, n, rate, phase):
+    x = _cplx(seed, n)
+    (a, pa), (b, pb) = oracle.shift_math_cc(x, rate, phase), ref.shift_math_cc(x, rate, phase)
+    assert np.float32(pa) == np.float32(pb) and rel_rms(a, b) < 1e-6               # n rounded additions and wraps: the same float sequence
+
+
+@settings(**COMMON)
 @given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), dec=st.integers(1, 40))
 def test_decimating_shift_any_rate(oracle, ref, seed, n, rate, dec):
     x = _cplx(seed, n)
