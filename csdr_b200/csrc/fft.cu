@@ -185,14 +185,25 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {
-        constexpr int CT = 4, BT = 4;
-        const dim3 tgrid((nblocks + BT - 1) / BT, (channels + CT - 1) / CT);
-        const size_t smem = sizeof(float2) * (size_t)CT * BT * fft_smem_elems(fft_inv_size);
+        // Tile = CT channels x BT blocks per CTA (each spectrum bin fetched once per CT channels, each tap once per BT blocks).  Big tiles
+        // save L2 traffic but a bank of 64 channels x 16 blocks is only 64 CTAs of 4x4 on 148 SMs (r01: the launch was latency-bound),
+        // so the tile shrinks until the grid covers the machine about twice.  CSDRB_INV_TILE=44|22 forces one for A/B runs.
+        static const char* forced = getenv("CSDRB_INV_TILE");
+        const long ctas44 = (long)((nblocks + 3) / 4) * ((channels + 3) / 4);
+        const bool small_tile = forced ? (forced[0] == '2') : (ctas44 < 2 * 148);
+        const int CTv = small_tile ? 2 : 4, BTv = small_tile ? 2 : 4;
+        const dim3 tgrid((nblocks + BTv - 1) / BTv, (channels + CTv - 1) / CTv);
+        const size_t smem = sizeof(float2) * (size_t)CTv * BTv * fft_smem_elems(fft_inv_size);
         switch (fft_inv_size) {
-#define X(M) case M: if constexpr (M >= 8 && M <= 1024) { auto k = fastddc_inv_tiled_kernel<M, CT, BT>; \
-            if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
-                                       fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
+#define X(M) case M: if constexpr (M >= 8 && M <= 1024) { \
+            if (small_tile) { auto k = fastddc_inv_tiled_kernel<M, 2, 2>; \
+                if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                           fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } \
+            else { auto k = fastddc_inv_tiled_kernel<M, 4, 4>; \
+                if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                           fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } } break;
             CSDRB_FFT_SIZES(X)
 #undef X
         }
