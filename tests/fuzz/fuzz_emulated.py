@@ -1,9 +1,9 @@
 """Fuzz the SHIPPED kernels on the CPU: random geometries through the real launchers under tests/host_shim/cuda_emul.h, checked against the
 oracle (FIR bank incl. forced tilings and the generic path, fused DDC bank with chunk offsets, shift_addition / shift_math banks, fractional
-decimator).  usage: python tools/fuzz_emulated.py [seed] [seconds]   -- test infrastructure, needs g++ and the CUDA headers only."""
+decimator).  usage: python tests/fuzz/fuzz_emulated.py [seed] [seconds]   -- test infrastructure, needs g++ and the CUDA headers only."""
 import sys, time, ctypes as C, numpy as np
 from pathlib import Path as _P
-_ROOT = str(_P(__file__).resolve().parents[1])
+_ROOT = str(_P(__file__).resolve().parents[2])
 sys.path.insert(0, _ROOT); sys.path.insert(0, _ROOT + '/tests/host_shim')
 import emul_build as eb
 from pathlib import Path

@@ -1,8 +1,8 @@
 """Fuzz the SHIPPED FFT-family kernels on the CPU (tests/host_shim/cuda_emul.h): random overlap-add geometries against numpy, random fastddc
-geometries against the oracle.  usage: python tools/fuzz_emulated_fft.py [seed] [seconds]   -- test infrastructure."""
+geometries against the oracle.  usage: python tests/fuzz/fuzz_emulated_fft.py [seed] [seconds]   -- test infrastructure."""
 import sys, time, tempfile, ctypes as C, numpy as np
 from pathlib import Path
-_ROOT = str(Path(__file__).resolve().parents[1])
+_ROOT = str(Path(__file__).resolve().parents[2])
 sys.path.insert(0, _ROOT); sys.path.insert(0, _ROOT + '/tests/host_shim')
 import emul_build as eb
 from oracle.pyoracle import Oracle, rel_rms, _CF, _p, WINDOWS
