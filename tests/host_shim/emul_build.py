@@ -25,6 +25,13 @@ def transform(text: str) -> str:
     return _LAUNCH.sub(lambda m: f"::cuda_emul::cfg({m.group(2)}).run({m.group(1)}, ", text)
 
 
+import os
+
+# CUDA_EMUL_SANITIZE=1: build the emulated code with UBSan (misaligned float4/float2 accesses, out-of-range shifts, signed overflow ...) and
+# abort on the first report -- alignment is what a CPU would otherwise forgive and a GPU would not
+SANITIZE = ["-fsanitize=undefined", "-fno-sanitize-recover=all", "-fno-sanitize=vptr"] if os.environ.get("CUDA_EMUL_SANITIZE") else []
+
+
 def available() -> bool:
     return bool(shutil.which("g++")) and (CUDA_INC / "cuda_runtime.h").exists()
 
@@ -64,7 +71,7 @@ def build(out_dir: Path, name: str, cu_files, wrappers: str, extra_includes=(), 
         subprocess.run(["gcc", "-std=gnu99", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", f"-I{ROOT / 'include'}", "-c", str(ROOT / c), "-o", str(obj)],
                        check=True, capture_output=True)
         objs.append(str(obj))
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w"] + SANITIZE + [f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
                         f"-I{ROOT / 'include'}", str(cpp), str(SHIM / "cuda_emul_runtime.cpp")] + objs + ["-o", str(so), "-lm", "-Wl,-Bsymbolic"], capture_output=True, text=True)   # -Bsymbolic: our cuda* stubs, not a libcudart another test loaded
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed for {name}:\n{r.stderr[-4000:]}")
@@ -142,7 +149,7 @@ def build_full(out_dir: Path):
         cpp = out_dir / f"full_{Path(cu).stem}.cpp"
         cpp.write_text(PRELUDE_FULL + src)
         obj = cpp.with_suffix(".o")
-        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w", f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w"] + SANITIZE + [f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
                             f"-I{ROOT / 'include'}", "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for {cu}:\n{r.stderr[-3000:]}")
@@ -161,7 +168,7 @@ def build_full(out_dir: Path):
                        check=True, capture_output=True)
         host.append(str(obj))
     lib = out_dir / "libcsdr_b200_emul.so"
-    r = subprocess.run(["g++", "-shared", "-o", str(lib)] + objs + [str(rt)] + host + ["-lm", "-lpthread", "-Wl,-Bsymbolic"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared"] + SANITIZE + ["-o", str(lib)] + objs + [str(rt)] + host + ["-lm", "-lpthread", "-Wl,-Bsymbolic"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-3000:])
     cli = out_dir / "csdr_emul"
