@@ -1,0 +1,16 @@
+#!/bin/bash
+# Round-2 first GPU call (one B200): validate the branch, then A/B the kernels that only ran under the CPU emulator so far.
+#   gpurun --timeout 900 -- 'bash tools/r2_ab.sh'
+# Everything lands in gpurun_out/r2_ab_*.  Nothing here is a bench value for bench.py; it decides what gets merged.
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/r2_ab_tests.log
+for staged in 0 1; do
+  for tile in 44 22; do
+    tag="staged${staged}_tile${tile}"
+    env $( [ $staged = 1 ] && echo CSDRB_OLAFIR_STAGED=1 ) CSDRB_INV_TILE=$tile python tools/bench_configs.py c3 c5 2>&1 | tee gpurun_out/r2_ab_configs_${tag}.txt | tail -12
+    cp gpurun_out/configs.json gpurun_out/r2_ab_configs_${tag}.json 2>/dev/null
+  done
+done
+python tools/bench_configs.py k 2>&1 | grep -i "fft\|K7" | tee gpurun_out/r2_ab_fft.txt
+timeout 120 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py 2>&1 | tail -3 | tee gpurun_out/r2_ab_memcheck.log
