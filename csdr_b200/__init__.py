@@ -48,6 +48,10 @@ class _Unroll(C.Structure):             # shift_unroll_data_t (= libcsdr.h:199-2
     _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
 
+class _Ima(C.Structure):                # ima_adpcm_state_t (= ima_adpcm.h:35-38)
+    _fields_ = [("index", C.c_int), ("previousValue", C.c_int)]
+
+
 class _AddFast(C.Structure):            # shift_addfast_data_t (= libcsdr.h:189-194)
     _fields_ = [("dsin", C.c_float * 4), ("dcos", C.c_float * 4), ("phase_increment", C.c_float)]
 
@@ -123,6 +127,9 @@ def lib() -> C.CDLL:
     L.shift_unroll_init.argtypes = [C.c_float, it]; L.shift_unroll_init.restype = _Unroll
     L.shift_unroll_cc.argtypes = [vp, vp, it, C.POINTER(_Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
     L.shift_math_cc.argtypes = [vp, vp, it, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
+    L.encode_ima_adpcm_i16_u8.argtypes = [vp, vp, it, _Ima]; L.encode_ima_adpcm_i16_u8.restype = _Ima
+    L.csdrb_encode_ima_adpcm_rows_i16_u8.argtypes = [vp, lg, vp, lg, it, it, vp, vp]
+    L.csdrb_compress_fft_adpcm_rows_f_u8.argtypes = [vp, lg, vp, lg, it, it, vp]
     L.csdrb_shift_math_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_shift_math_bank_scratch_bytes.restype = sz
     L.csdrb_shift_math_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp, sz, vp]
     L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = _AddFast
@@ -464,6 +471,12 @@ class libcsdr:
         return y, float(np.float32(phase))
 
     @staticmethod
+    def encode_ima_adpcm_i16_u8(x, index=0, previous=0):
+        x = np.ascontiguousarray(x, np.int16); y = np.empty(x.size // 2, np.uint8)
+        st = lib().encode_ima_adpcm_i16_u8(x.ctypes.data, y.ctypes.data, x.size, _Ima(index, previous))
+        return y, (st.index, st.previousValue)
+
+    @staticmethod
     def shift_math_cc(x, rate, phase=0.0, chunk=None):
         x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
         for s0 in range(0, x.size, chunk):
@@ -572,6 +585,27 @@ def shift_addition_bank_cc(x, rates, phases=None, chunk: int = 1024, out=None):
     _check(lib().csdrb_shift_addition_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_params.data_ptr(), d_phase.data_ptr(), chunk,
                                               scratch.data_ptr(), scratch.numel(), _stream()), "shift_addition_bank_cc")
     return out, d_phase
+
+
+def encode_ima_adpcm_rows_i16_u8(x, state=None):
+    """x [R, N] int16 -> (bytes [R, N/2] uint8, state [R, 2] int32 = index, previousValue carried per row)"""
+    import torch
+    assert x.dtype == torch.int16 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    rows, n = x.shape
+    out = torch.empty((rows, n // 2), dtype=torch.uint8, device=x.device)
+    state = torch.zeros((rows, 2), dtype=torch.int32, device=x.device) if state is None else state
+    _check(lib().csdrb_encode_ima_adpcm_rows_i16_u8(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, n, state.data_ptr(), _stream()), "encode_ima_adpcm_rows")
+    return out, state
+
+
+def compress_fft_adpcm_rows_f_u8(db):
+    """db [R, fft_size] float32 (dB) -> [R, (fft_size + 10) / 2] uint8: one fresh ADPCM encoder per waterfall line (csdr.c:1745-1767)"""
+    import torch
+    assert db.dtype == torch.float32 and db.is_cuda and db.dim() == 2 and db.stride(1) == 1
+    rows, n = db.shape
+    out = torch.empty((rows, (n + 10) // 2), dtype=torch.uint8, device=db.device)
+    _check(lib().csdrb_compress_fft_adpcm_rows_f_u8(db.data_ptr(), db.stride(0), out.data_ptr(), out.stride(0), rows, n, _stream()), "compress_fft_adpcm_rows")
+    return out
 
 
 def shift_math_bank_cc(x, rates, phases=None, out=None):

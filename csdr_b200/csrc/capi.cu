@@ -102,15 +102,33 @@ int csdrb_set_device(int device) { CSDRB_CUDA(cudaSetDevice(device)); return 0; 
 int csdrb_stream_synchronize(void* stream) { CSDRB_CUDA(cudaStreamSynchronize(S(stream))); return 0; }
 long csdrb_kernel_launches(void) { return g_launches.load(); }
 
-int csdrb_convert_u8_f(const unsigned char* d_in, float* d_out, long n, void* stream) { return counted(launch_convert_u8_f(d_in, d_out, n, S(stream))); }
-int csdrb_convert_s16_f(const short* d_in, float* d_out, long n, void* stream) { return counted(launch_convert_s16_f(d_in, d_out, n, S(stream))); }
-int csdrb_convert_f_s16(const float* d_in, short* d_out, long n, void* stream) { return counted(launch_convert_f_s16(d_in, d_out, n, S(stream))); }
+// channels ride in gridDim.y (limit 65535) in the bank kernels: refuse larger banks with a message instead of an "invalid configuration" launch error
+static inline bool too_many_channels(int channels, const char* who)
+{
+    if (channels <= 65535) return false;
+    set_error("%s: %d channels in one call (at most 65535; split the bank)", who, channels);
+    return true;
+}
+static inline bool null_io(const void* in, const void* out, const char* who) { if (in && out) return false; set_error("%s: null pointer", who); return true; }
+int csdrb_convert_u8_f(const unsigned char* d_in, float* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_u8_f") ? -1 : counted(launch_convert_u8_f(d_in, d_out, n, S(stream)));
+}
+int csdrb_convert_s16_f(const short* d_in, float* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_s16_f") ? -1 : counted(launch_convert_s16_f(d_in, d_out, n, S(stream)));
+}
+int csdrb_convert_f_s16(const float* d_in, short* d_out, long n, void* stream)
+{
+    return null_io(d_in, d_out, "convert_f_s16") ? -1 : counted(launch_convert_f_s16(d_in, d_out, n, S(stream)));
+}
 
 int csdrb_fir_bank_variants(void) { return fir_bank_variant_count(); }
 
 int csdrb_fir_decimate_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels,
                                int input_size, int decimation, const float* h_taps, int taps_length, int variant, void* stream)
 {
+    if (too_many_channels(channels, "fir_decimate bank")) return -1;
     if (!d_in || !d_out || !h_taps) { set_error("fir_decimate bank: null pointer"); return -1; }
     // the generic kernel reads taps from device memory: keep a small per-process copy
     static float* d_taps = nullptr; static int d_taps_cap = 0; static std::mutex mu;
@@ -134,6 +152,7 @@ int csdrb_fir_decimate_bank_cc(const complexf* d_in, long in_stride, complexf* d
 int csdrb_fmdemod_quadri_bank_cf(const complexf* d_in, long in_stride, float* d_out, long out_stride, int channels,
                                  int input_size, const complexf* d_last_in, complexf* d_last_out, void* stream)
 {
+    if (too_many_channels(channels, "fmdemod_quadri bank")) return -1;
     if (!d_in || !d_out) { set_error("fmdemod_quadri bank: null pointer"); return -1; }
     return counted(launch_fmdemod_quadri_bank(reinterpret_cast<const float2*>(d_in), in_stride, d_out, out_stride, channels, input_size,
                                               reinterpret_cast<const float2*>(d_last_in), reinterpret_cast<float2*>(d_last_out), S(stream)));
@@ -302,6 +321,7 @@ size_t csdrb_shift_addition_bank_scratch_bytes(int channels, int input_size, int
 int csdrb_shift_addition_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                                  const shift_addition_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "shift_addition bank")) return -1;
     if (!d_in || !d_out || !d_params || !d_phase_io) { set_error("shift_addition bank: null pointer"); return -1; }
     int rc = launch_shift_addition_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
                                         reinterpret_cast<const float*>(d_params), d_phase_io, chunk, d_scratch, scratch_bytes, S(stream));
@@ -313,6 +333,7 @@ size_t csdrb_shift_math_bank_scratch_bytes(int channels, int input_size) { retur
 int csdrb_shift_math_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                              const float* d_rates, float* d_phase_io, void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "shift_math bank")) return -1;
     if (!d_in || !d_out || !d_rates || !d_phase_io) { set_error("shift_math bank: null pointer"); return -1; }
     int rc = launch_shift_math_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
                                     d_rates, d_phase_io, d_scratch, scratch_bytes, S(stream));
@@ -322,6 +343,7 @@ int csdrb_shift_math_bank_cc(const complexf* d_in, long in_stride, complexf* d_o
 int csdrb_shift_addfast_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                                 const shift_addfast_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "shift_addfast bank")) return -1;
     if (!d_in || !d_out || !d_params || !d_phase_io) { set_error("shift_addfast bank: null pointer"); return -1; }
     int rc = launch_shift_addfast_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
                                        reinterpret_cast<const float*>(d_params), d_phase_io, chunk, d_scratch, scratch_bytes, S(stream));
@@ -343,6 +365,7 @@ int csdrb_fractional_decimator_bank_ff(const float* d_in, long in_stride, float*
                                        int num_poly_points, const float* d_taps, int taps_length, csdrb_fracdec_state_t* d_state,
                                        void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "fractional_decimator bank")) return -1;
     if (!d_in || !d_out || !d_state) { set_error("fractional_decimator bank: null pointer"); return -1; }
     int rc = launch_fractional_decimator_bank(d_in, in_stride, d_out, out_stride, channels, input_size, rate, num_poly_points, d_taps, taps_length, d_state,
                                               d_scratch, scratch_bytes, S(stream));
@@ -354,6 +377,7 @@ size_t csdrb_fastagc_bank_scratch_bytes(int channels, int nblocks) { return fast
 int csdrb_fastagc_bank_ff(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks, float reference,
                           csdrb_fastagc_state_t* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "fastagc bank")) return -1;
     if (!d_in || !d_out || !d_state || !d_hist) { set_error("fastagc bank: null pointer"); return -1; }
     int rc = launch_fastagc_bank(d_in, in_stride, d_out, out_stride, channels, block, nblocks, reference, d_state, d_hist, d_scratch, scratch_bytes, S(stream));
     return rc < 0 ? rc : counted(0, rc);
@@ -369,6 +393,7 @@ int csdrb_fft_c2c_batch(const complexf* d_in, long in_stride, complexf* d_out, l
 int csdrb_bandpass_fir_fft_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int fft_size, int input_size,
                                    int nblocks, const complexf* d_taps_fft, long taps_stride, complexf* d_tail_io, void* stream)
 {
+    if (too_many_channels(channels, "bandpass_fir_fft bank")) return -1;
     if (!d_in || !d_out || !d_taps_fft || !d_tail_io) { set_error("bandpass_fir_fft bank: null pointer"); return -1; }
     int rc = launch_olafir_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, fft_size, input_size,
                                 nblocks, reinterpret_cast<const float2*>(d_taps_fft), taps_stride, reinterpret_cast<float2*>(d_tail_io), 0, S(stream));
@@ -389,6 +414,7 @@ int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const comp
                               const fastddc_t* g, int* d_remain_io, float* d_phase_io, complexf* d_out, long out_stride, int* d_out_total,
                               void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "fastddc_inv bank")) return -1;
     if (!d_spectra || !d_taps_fft || !d_chan || !g || !d_remain_io || !d_phase_io || !d_out || !d_out_total) { set_error("fastddc_inv bank: null pointer"); return -1; }
     int rc = launch_fastddc_inv_bank(reinterpret_cast<const float2*>(d_spectra), nblocks, reinterpret_cast<const float2*>(d_taps_fft), d_chan, channels,
                                      g->fft_size, g->fft_inv_size, g->pre_decimation, g->scrap, g->post_input_size, g->post_decimation,
@@ -424,6 +450,7 @@ int csdrb_shift_unroll_bank_cc(const complexf* d_in, long in_stride, complexf* d
                                const shift_addition_data_t* d_params, const float* d_dsin, const float* d_dcos, long table_stride, int table_size,
                                float* d_phase_io, void* d_scratch, size_t scratch_bytes, void* stream)
 {
+    if (too_many_channels(channels, "shift_unroll bank")) return -1;
     if (!d_in || !d_out || !d_params || !d_dsin || !d_dcos || !d_phase_io) { set_error("shift_unroll bank: null pointer"); return -1; }
     int rc = launch_shift_unroll_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
                                       reinterpret_cast<const float*>(d_params), d_dsin, d_dcos, table_stride, table_size, d_phase_io, d_scratch, scratch_bytes, S(stream));
@@ -451,32 +478,52 @@ void csdrb_stream_destroy(void* stream) { if (stream) cudaStreamDestroy(S(stream
 int csdrb_copy_h2d(void* d_dst, const void* h_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(h_src, d_dst, "copy_h2d")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy_d2h(void* h_dst, const void* d_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(d_src, h_dst, "copy_d2h")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, S(stream)));
     return 0;
 }
 int csdrb_copy_d2d(void* d_dst, const void* d_src, size_t bytes, void* stream)
 {
     if (!bytes) return 0;
+    if (null_io(d_src, d_dst, "copy_d2d")) return -1;
     CSDRB_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy2d_d2d(void* d_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
 {
     if (!width_bytes || !rows) return 0;
+    if (null_io(d_src, d_dst, "copy2d_d2d")) return -1;
     CSDRB_CUDA(cudaMemcpy2DAsync(d_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToDevice, S(stream)));
     return 0;
 }
 int csdrb_copy2d_d2h(void* h_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
 {
     if (!width_bytes || !rows) return 0;
+    if (null_io(d_src, h_dst, "copy2d_d2h")) return -1;
     CSDRB_CUDA(cudaMemcpy2DAsync(h_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToHost, S(stream)));
     return 0;
+}
+
+int csdrb_encode_ima_adpcm_rows_i16_u8(const short* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int input_length,
+                                       ima_adpcm_state_t* d_state_io, void* stream)
+{
+    if (!d_in || !d_out || !d_state_io) { set_error("encode_ima_adpcm rows: null pointer"); return -1; }
+    int rc = launch_adpcm_encode_rows(d_in, in_stride, d_out, out_stride, rows, input_length, d_state_io, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
+int csdrb_compress_fft_adpcm_rows_f_u8(const float* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int fft_size, void* stream)
+{
+    if (!d_in || !d_out) { set_error("compress_fft_adpcm rows: null pointer"); return -1; }
+    int rc = launch_compress_fft_adpcm_rows(d_in, in_stride, d_out, out_stride, rows, fft_size, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
 }
 
 int csdrb_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, void* stream)
@@ -554,6 +601,10 @@ struct csdrb_ddc_bank_s {
 csdrb_ddc_bank_t* csdrb_ddc_bank_create(int channels, const float* h_rates, int decimation, const float* h_taps, int taps_length, int demod, int chunk)
 {
     if (channels <= 0 || !h_rates || !h_taps || decimation <= 0 || taps_length <= 0) { set_error("ddc bank create: bad argument"); return nullptr; }
+    if (!((decimation == 50 && taps_length <= 850) || (decimation == 10 && taps_length <= 200))) {     // the geometries launch_ddc_main has fused kernels for
+        set_error("ddc bank create: no fused kernel for decimation %d / %d taps (compiled: d=50 T<=850, d=10 T<=200); run the unfused bank calls", decimation, taps_length);
+        return nullptr;
+    }
     auto* b = new csdrb_ddc_bank_s();
     b->channels = channels; b->decimation = decimation; b->taps_length = taps_length; b->demod = demod ? 1 : 0; b->chunk = chunk > 0 ? chunk : 1024;
     b->taps.assign(h_taps, h_taps + taps_length);
@@ -903,6 +954,22 @@ float shift_unroll_cc(complexf* input, complexf* output, int input_size, shift_u
     A_DOWN(output, 1, (size_t)input_size * 8, who);
     A_SYNC(who);
     return new_phase;
+}
+
+ima_adpcm_state_t encode_ima_adpcm_i16_u8(short* input, unsigned char* output, int input_length, ima_adpcm_state_t state)
+{
+    const char* who = "encode_ima_adpcm_i16_u8";
+    if (input_length < 2) return state;
+    A_BEGIN(who);
+    A_UP(0, input, (size_t)input_length * 2, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_length / 2 + 16), who);
+    A_UP(2, &state, sizeof state, who);
+    A_CHECK(csdrb_encode_ima_adpcm_rows_i16_u8((const short*)g_ctx.buf[0], input_length, (unsigned char*)g_ctx.buf[1], input_length / 2, 1, input_length,
+                                               (ima_adpcm_state_t*)g_ctx.buf[2], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)(input_length / 2), who);
+    A_CUDA(cudaMemcpyAsync(&state, g_ctx.buf[2], sizeof state, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return state;
 }
 
 void limit_ff(float* input, float* output, int input_size, float max_amplitude)

@@ -89,6 +89,76 @@ __global__ void __launch_bounds__(256) convert_f_s16_kernel(const float* __restr
     for (long i = nvec * 8 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (short)f_to_s16_bits(in[i]);
 }
 
+// ---- waterfall compression: IMA ADPCM, 4 bits per value ------------------------------------------------------------
+// encode_ima_adpcm_i16_u8 (ima_adpcm.c:95-150) is a predictor/step-index recursion, sequential by definition; OpenWebRX runs one per audio stream and one
+// per waterfall line (csdr.c:1745-1767, state reset every line), so the bank form is one thread per row.  Integer arithmetic: bit-exact.
+__constant__ int c_ima_step[89] = {7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45, 50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157,
+    173, 190, 209, 230, 253, 279, 307, 337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066, 2272, 2499, 2749,
+    3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899, 15289, 16818, 18500, 20350, 22385, 24623, 27086,
+    29794, 32767};                                                       // the IMA/DVI ADPCM standard's step table
+
+__device__ __forceinline__ unsigned ima_encode_one(int sample, int& index, int& previous)
+{
+    const int step = c_ima_step[index];
+    int diff = sample - previous, s = step;
+    unsigned code = 0;
+    if (diff < 0) { code = 8; diff = -diff; }
+    if (diff >= s) { code |= 4; diff -= s; }
+    s >>= 1;
+    if (diff >= s) { code |= 2; diff -= s; }
+    s >>= 1;
+    if (diff >= s) code |= 1;
+    int delta = step >> 3;                                               // the decoder's reconstruction keeps encoder and decoder in step
+    if (code & 1) delta += step >> 2;
+    if (code & 2) delta += step >> 1;
+    if (code & 4) delta += step;
+    previous += (code & 8) ? -delta : delta;
+    previous = min(32767, max(-32768, previous));
+    index += (code & 4) ? 2 * (int)(code & 3) + 2 : -1;                  // index adjust table {-1,-1,-1,-1,2,4,6,8}
+    index = min(88, max(0, index));
+    return code;
+}
+
+struct ImaState { int index, previous; };                               // = ima_adpcm_state_t (ima_adpcm.h:35-38)
+
+__global__ void adpcm_encode_rows_kernel(const short* __restrict__ in, long in_stride, unsigned char* __restrict__ out, long out_stride, int rows, int n,
+                                         ImaState* __restrict__ state_io)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const short* x = in + (long)r * in_stride;
+    unsigned char* y = out + (long)r * out_stride;
+    int index = state_io[r].index, previous = state_io[r].previous;
+    index = min(88, max(0, index));                                      // a caller's garbage must not index outside the table
+    for (int k = 0; k < n / 2; k++) {
+        const unsigned lo = ima_encode_one(x[2 * k], index, previous), hi = ima_encode_one(x[2 * k + 1], index, previous);
+        y[k] = (unsigned char)(lo | (hi << 4));
+    }
+    state_io[r].index = index; state_io[r].previous = previous;
+}
+
+// one waterfall line per thread: ten copies of the first value in front, dB * 100 truncated to short (x86 cvttss2si + 16-bit store), fresh state
+__global__ void compress_fft_adpcm_rows_kernel(const float* __restrict__ in, long in_stride, unsigned char* __restrict__ out, long out_stride, int rows, int fft_size)
+{
+    constexpr int PAD = 10;                                              // csdr.c:1739
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* x = in + (long)r * in_stride;
+    unsigned char* y = out + (long)r * out_stride;
+    int index = 0, previous = 0;
+    for (int k = 0; k < (fft_size + PAD) / 2; k++) {
+        unsigned code[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * k + h;
+            const float s = __fmul_rn(x[i < PAD ? 0 : i - PAD], 100.0f);
+            const int w = (s >= 2147483648.0f || s < -2147483648.0f || s != s) ? INT_MIN : __float2int_rz(s);
+            code[h] = ima_encode_one((int)(short)(w & 0xffff), index, previous);
+        }
+        y[k] = (unsigned char)(code[0] | (code[1] << 4));
+    }
+}
+
 static int grid_for(long work_items, int block)
 {
     long g = (work_items + block - 1) / block;
@@ -133,6 +203,22 @@ __global__ void __launch_bounds__(256) limit_ff_kernel(const float* __restrict__
                              fmaxf(-max_amplitude, fminf(max_amplitude, a.z)), fmaxf(-max_amplitude, fminf(max_amplitude, a.w))));
     }
     for (long i = nvec * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = fmaxf(-max_amplitude, fminf(max_amplitude, in[i]));
+}
+
+int launch_adpcm_encode_rows(const short* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int n, void* d_state_io, cudaStream_t st)
+{
+    if (rows <= 0 || n < 2) return 0;
+    adpcm_encode_rows_kernel<<<(rows + 63) / 64, 64, 0, st>>>(d_in, in_stride, d_out, out_stride, rows, n, static_cast<ImaState*>(d_state_io));
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
+int launch_compress_fft_adpcm_rows(const float* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int fft_size, cudaStream_t st)
+{
+    if (rows <= 0 || fft_size <= 0) return 0;
+    compress_fft_adpcm_rows_kernel<<<(rows + 63) / 64, 64, 0, st>>>(d_in, in_stride, d_out, out_stride, rows, fft_size);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
 }
 
 int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, cudaStream_t st)

@@ -182,6 +182,7 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
                              cudaStream_t st)
 {
     if (channels <= 0 || D <= 0 || T <= 0) { set_error("fir_decimate bank: bad geometry (C=%d D=%d T=%d)", channels, D, T); return -1; }
+    if (variant >= fir_bank_variant_count()) { set_error("fir_decimate bank: tiling %d does not exist (0..%d, or < 0 for the automatic choice)", variant, fir_bank_variant_count() - 1); return -1; }
     const int n_out = n_in >= T ? (n_in - T) / D + 1 : 0;
     if (n_out == 0) return 0;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && (in_stride % 2 == 0);

@@ -17,6 +17,8 @@ int launch_convert_f_s16(const float* d_in, short* d_out, long n, cudaStream_t s
 int launch_fmdemod_quadri_bank(const float2* d_in, long in_stride, float* d_out, long out_stride, int channels, int n,
                                const float2* d_last_in, float2* d_last_out, cudaStream_t st);
 
+int launch_adpcm_encode_rows(const short* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int n, void* d_state_io, cudaStream_t st);
+int launch_compress_fft_adpcm_rows(const float* d_in, long in_stride, unsigned char* d_out, long out_stride, int rows, int fft_size, cudaStream_t st);
 int launch_limit_ff(const float* d_in, float* d_out, long n, float max_amplitude, cudaStream_t st);
 int launch_deemphasis_wfm_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int n, float tau, int sample_rate,
                                float* d_last_io, cudaStream_t st);

@@ -393,6 +393,64 @@ static int cmd_logaveragepower_cf(int argc, char **argv)                   /* cs
     }
 }
 
+static int cmd_fft_exchange_sides_ff(int argc, char **argv)                /* csdr.c:1697-1715: pure I/O, the two halves of every line swap places */
+{
+    if (argc <= 2) return complain("need required parameters (fft_size)");
+    int fft_size = 0; sscanf(argv[2], "%d", &fft_size);
+    if (!incoming_block_size()) return -2;
+    announce_block(fft_size);
+    const size_t half = (size_t)(fft_size / 2);
+    float *lower = must_alloc(sizeof(float) * half), *upper = must_alloc(sizeof(float) * half);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(lower, sizeof(float), half, stdin);
+        fread(upper, sizeof(float), half, stdin);
+        fwrite(upper, sizeof(float), half, stdout);
+        fwrite(lower, sizeof(float), half, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_compress_fft_adpcm_f_u8(int argc, char **argv)              /* csdr.c:1739-1767 */
+{
+    enum { PAD = 10 };                                                   /* the encoder needs a few values to settle: the line starts with ten copies of its first */
+    if (argc <= 2) return complain("need required parameters (fft_size)");
+    int fft_size = 0; sscanf(argv[2], "%d", &fft_size);
+    const int line = fft_size + PAD;
+    if (!incoming_block_size()) return -2;                               /* consumes a preamble if there is one (:1751) */
+    announce_block(line);
+    float *in = must_alloc(sizeof(float) * (size_t)line);
+    short *scaled = must_alloc(sizeof(short) * (size_t)line);
+    unsigned char *out = must_alloc((size_t)line / 2 + 1);
+    const ima_adpcm_state_t fresh = {0, 0};
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in + PAD, sizeof(float), (size_t)fft_size, stdin);
+        for (int k = 0; k < PAD; k++) in[k] = in[PAD];
+        for (int k = 0; k < line; k++) scaled[k] = (short)(in[k] * 100);   /* dB -> centi-dB, C conversion like the reference's */
+        encode_ima_adpcm_i16_u8(scaled, out, line, fresh);               /* every line starts from the initial state (:1764) */
+        fwrite(out, 1, (size_t)line / 2, stdout);
+        end_of_block();
+    }
+}
+
+static int cmd_encode_ima_adpcm(int argc, char **argv)                     /* csdr.c:1891-1904 */
+{
+    (void)argc; (void)argv;
+    if (!open_block()) return -2;
+    announce_block(block / 2);
+    short *in = must_alloc(sizeof(short) * (size_t)block);
+    unsigned char *out = must_alloc((size_t)block / 2 + 1);
+    ima_adpcm_state_t st = {0, 0};
+    for (;;) {
+        if (feof(stdin)) return 0;
+        fread(in, sizeof(short), (size_t)block, stdin);
+        st = encode_ima_adpcm_i16_u8(in, out, block, st);
+        fwrite(out, 1, (size_t)block / 2, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_limit_ff(int argc, char **argv)                              /* csdr.c:673-686 */
 {
     float max_amplitude = 1.0f; if (argc >= 3) sscanf(argv[2], "%g", &max_amplitude);
@@ -639,6 +697,10 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"fractional_decimator_ff", cmd_fractional_decimator_ff, "fractional_decimator_ff <decimation_rate> [num_poly_points ( [transition_bw [window]] | --prefilter )]"},
     {"fastagc_ff", cmd_fastagc_ff, "fastagc_ff [block_size [reference]]"},
     {"limit_ff", cmd_limit_ff, "limit_ff [max_amplitude]"},
+    {"fft_exchange_sides_ff", cmd_fft_exchange_sides_ff, "fft_exchange_sides_ff <fft_size>"},
+    {"compress_fft_adpcm_f_u8", cmd_compress_fft_adpcm_f_u8, "compress_fft_adpcm_f_u8 <fft_size>"},
+    {"encode_ima_adpcm_i16_u8", cmd_encode_ima_adpcm, "encode_ima_adpcm_i16_u8"},
+    {"encode_ima_adpcm_s16_u8", cmd_encode_ima_adpcm, "encode_ima_adpcm_s16_u8"},
     {"shift_unroll_cc", cmd_shift_unroll_cc, "shift_unroll_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
     {"shift_math_cc", cmd_shift_math_cc, "shift_math_cc <rate>"},
     {"shift_addfast_cc", cmd_shift_addfast_cc, "shift_addfast_cc <rate> | --fifo <fifo_path> | --fd <fd>"},

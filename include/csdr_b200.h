@@ -91,6 +91,10 @@ void  limit_ff(float *input, float *output, int input_size, float max_amplitude)
  * (48000, 44100, 11025, 8000); returns the number of outputs = input_size - taps_length, 0 for any other rate */
 int   deemphasis_nfm_ff(float *input, float *output, int input_size, int sample_rate);
 
+/* waterfall / audio compression, SURVEY 8(f) rank 4 (ima_adpcm.h:35-41; ima_adpcm.c:95-150): IMA ADPCM, two samples per output byte */
+typedef struct ImaState { int index; int previousValue; } ima_adpcm_state_t;
+ima_adpcm_state_t encode_ima_adpcm_i16_u8(short *input, unsigned char *output, int input_length, ima_adpcm_state_t state);
+
 /* spectrum side path and shift_unroll, SURVEY 8(f) ranks 3-4 (libcsdr.h:142-149, 199-207; libcsdr.c:1245-1276, 1296-1314, 283-320) */
 float *precalculate_window(int size, window_t window);                                   /* host table, malloc'ed like the reference's */
 void  apply_window_c(complexf *input, complexf *output, int size, window_t window);
@@ -239,6 +243,12 @@ const float *csdrb_deemphasis_nfm_taps(int sample_rate, int *taps_length);
  * (e.g. a de-emphasis FIR designed for a sample rate the reference has no table for) */
 int csdrb_fir_valid_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int input_size,
                             const float *taps, int taps_length, float limit_max, void *stream);
+
+/* IMA ADPCM on device rows: d_state_io[r] carries row r's encoder state between calls.  csdrb_compress_fft_adpcm_rows_f_u8 is the waterfall line of
+ * csdr.c:1745-1767 for many lines at once: each row of fft_size dB values -> (fft_size + 10) / 2 bytes, encoder state fresh per row. */
+int csdrb_encode_ima_adpcm_rows_i16_u8(const short *d_in, long in_stride, unsigned char *d_out, long out_stride, int rows, int input_length,
+                                       ima_adpcm_state_t *d_state_io, void *stream);
+int csdrb_compress_fft_adpcm_rows_f_u8(const float *d_in, long in_stride, unsigned char *d_out, long out_stride, int rows, int fft_size, void *stream);
 
 /* spectrum side path on device buffers: `rows` frames of `size` values share one window table; power modes as the reference's
  * logpower_cf / accumulate_power_cf (d_out is read-modify-write) / log_ff */

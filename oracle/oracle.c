@@ -476,6 +476,69 @@ float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * waterfall compression: IMA ADPCM, 4 bits per value
+ * ---------------------------------------------------------------------------------------------- */
+
+/* the IMA/DVI ADPCM standard's two tables (the reference carries the same numbers, ima_adpcm.c:75-93) */
+static const int kImaIndexAdjust[8] = {-1, -1, -1, -1, 2, 4, 6, 8};
+static const int kImaStep[89] = {7, 8, 9, 10, 11, 12, 13, 14, 16, 17, 19, 21, 23, 25, 28, 31, 34, 37, 41, 45, 50, 55, 60, 66, 73, 80, 88, 97, 107, 118, 130, 143, 157,
+    173, 190, 209, 230, 253, 279, 307, 337, 371, 408, 449, 494, 544, 598, 658, 724, 796, 876, 963, 1060, 1166, 1282, 1411, 1552, 1707, 1878, 2066, 2272, 2499, 2749,
+    3024, 3327, 3660, 4026, 4428, 4871, 5358, 5894, 6484, 7132, 7845, 8630, 9493, 10442, 11487, 12635, 13899, 15289, 16818, 18500, 20350, 22385, 24623, 27086,
+    29794, 32767};
+
+/* [ref ima_adpcm.c:95-139] one sample: quantise the difference to the predictor against the current step (sign + 3 magnitude bits by
+ * successive comparison), then move the predictor exactly as a decoder would and adapt the step index. */
+static unsigned ima_encode_one(int sample, int *index, int *previous)
+{
+    const int step = kImaStep[*index];
+    int diff = sample - *previous, code = 0, s = step;
+    if (diff < 0) { code = 8; diff = -diff; }
+    if (diff >= s) { code |= 4; diff -= s; }
+    s >>= 1;
+    if (diff >= s) { code |= 2; diff -= s; }
+    s >>= 1;
+    if (diff >= s) code |= 1;
+    int delta = step >> 3;
+    if (code & 1) delta += step >> 2;
+    if (code & 2) delta += step >> 1;
+    if (code & 4) delta += step;
+    *previous += (code & 8) ? -delta : delta;
+    if (*previous > 32767) *previous = 32767; else if (*previous < -32768) *previous = -32768;
+    *index += kImaIndexAdjust[code & 7];
+    if (*index < 0) *index = 0; else if (*index > 88) *index = 88;
+    return (unsigned)code;
+}
+
+/* [ref ima_adpcm.c:141-150] two samples per output byte, low nibble first; state = {index, previousValue} in and out */
+void oracle_encode_ima_adpcm_i16_u8(const short *in, unsigned char *out, int n, int *index, int *previous)
+{
+    for (int k = 0; k < n / 2; k++) {
+        unsigned lo = ima_encode_one(in[2 * k], index, previous);
+        unsigned hi = ima_encode_one(in[2 * k + 1], index, previous);
+        out[k] = (unsigned char)(lo | (hi << 4));
+    }
+}
+
+/* [ref csdr.c:1739-1767] one waterfall line: ten copies of the first value in front (the encoder needs a few samples to settle), dB * 100
+ * truncated to short like the C conversion on x86, ADPCM from a fresh state.  out receives (fft_size + 10) / 2 bytes. */
+void oracle_compress_fft_adpcm_f_u8(const float *in, unsigned char *out, int fft_size)
+{
+    enum { PAD = 10 };
+    int index = 0, previous = 0;
+    short pair[2];
+    for (int k = 0; k < (fft_size + PAD) / 2; k++) {
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * k + h;
+            const float scaled = in[i < PAD ? 0 : i - PAD] * 100;
+            const int wide = (scaled >= 2147483648.0f || scaled < -2147483648.0f || scaled != scaled) ? INT_MIN : (int)scaled;
+            pair[h] = (short)(unsigned short)(wide & 0xffff);
+        }
+        unsigned lo = ima_encode_one(pair[0], &index, &previous), hi = ima_encode_one(pair[1], &index, &previous);
+        out[k] = (unsigned char)(lo | (hi << 4));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * DFT (stands in for FFTW3f)
  * ---------------------------------------------------------------------------------------------- */
 

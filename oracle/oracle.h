@@ -91,6 +91,10 @@ float oracle_shift_math_cc(const ocf32 *in, ocf32 *out, int n, float rate, float
 void  oracle_shift_addfast_init(float rate, float *d9);
 float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d9, float starting_phase);
 
+/* waterfall compression: ima_adpcm.c:95-150, csdr.c:1739-1767 */
+void oracle_encode_ima_adpcm_i16_u8(const short *in, unsigned char *out, int n, int *index, int *previous);
+void oracle_compress_fft_adpcm_f_u8(const float *in, unsigned char *out, int fft_size);
+
 /* mathematical DFT in float64, rounded once to float (stands in for FFTW3f; fft_fftw.c:6-41) */
 void oracle_dft_c2c(const ocf32 *in, ocf32 *out, int n, int forward);
 

@@ -111,6 +111,8 @@ class Oracle:
         L.oracle_shift_unroll_init.argtypes = [C.c_float, C.c_int, fp, fp]; L.oracle_shift_unroll_init.restype = C.c_float
         L.oracle_shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, fp, C.c_float, C.c_float]
         L.oracle_shift_unroll_cc.restype = C.c_float
+        L.oracle_encode_ima_adpcm_i16_u8.argtypes = [C.POINTER(C.c_short), C.POINTER(C.c_ubyte), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_compress_fft_adpcm_f_u8.argtypes = [fp, C.POINTER(C.c_ubyte), C.c_int]
         L.oracle_shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.oracle_shift_math_cc.restype = C.c_float
         L.oracle_shift_addfast_init.argtypes = [C.c_float, fp]
         L.oracle_shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, C.c_float]; L.oracle_shift_addfast_cc.restype = C.c_float
@@ -248,6 +250,18 @@ class Oracle:
             phase = self.L.oracle_shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, _p(ds, C.c_float), _p(dc, C.c_float), inc, phase)
         return y, float(np.float32(phase))
 
+    def encode_ima_adpcm_i16_u8(self, x, index=0, previous=0):
+        x = np.ascontiguousarray(x, np.int16); y = np.empty(x.size // 2, np.uint8); i = C.c_int(index); p = C.c_int(previous)
+        self.L.oracle_encode_ima_adpcm_i16_u8(_p(x, C.c_short), _p(y, C.c_ubyte), x.size, C.byref(i), C.byref(p))
+        return y, (i.value, p.value)
+
+    def compress_fft_adpcm_f_u8(self, x, fft_size):
+        """rows of fft_size dB values -> rows of (fft_size + 10) / 2 bytes"""
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, fft_size); y = np.empty((x.shape[0], (fft_size + 10) // 2), np.uint8)
+        for r in range(x.shape[0]):
+            self.L.oracle_compress_fft_adpcm_f_u8(_p(x[r], C.c_float), _p(y[r], C.c_ubyte), fft_size)
+        return y
+
     def shift_math_cc(self, x, rate, phase=0.0, chunk=None):
         """one call per `chunk` samples (the CLI uses its 1024-sample buffer, csdr.c:703-718); the phase chain does not depend on the cut"""
         x = _c64(x); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
@@ -371,6 +385,9 @@ class Ref:
     class _Unroll(C.Structure):             # libcsdr.h:199-205
         _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
+    class _Ima(C.Structure):                # ima_adpcm.h:35-38
+        _fields_ = [("index", C.c_int), ("previousValue", C.c_int)]
+
     class _AddFast(C.Structure):            # libcsdr.h:189-194
         _fields_ = [("dsin", C.c_float * 4), ("dcos", C.c_float * 4), ("phase_increment", C.c_float)]
 
@@ -417,6 +434,7 @@ class Ref:
         L.shift_unroll_init.argtypes = [C.c_float, C.c_int]; L.shift_unroll_init.restype = self._Unroll
         L.shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
         L.shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
+        L.encode_ima_adpcm_i16_u8.argtypes = [C.POINTER(C.c_short), C.POINTER(C.c_ubyte), C.c_int, self._Ima]; L.encode_ima_adpcm_i16_u8.restype = self._Ima
         L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = self._AddFast
         L.shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
         L.make_fft_c2c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]; L.make_fft_c2c.restype = C.POINTER(self._Plan)
@@ -557,6 +575,11 @@ class Ref:
             n = min(size, x.size - s0)
             phase = self.L.shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
         return y, float(np.float32(phase))
+
+    def encode_ima_adpcm_i16_u8(self, x, index=0, previous=0):
+        x = np.ascontiguousarray(x, np.int16); y = np.empty(x.size // 2, np.uint8)
+        st = self.L.encode_ima_adpcm_i16_u8(_p(x, C.c_short), _p(y, C.c_ubyte), x.size, self._Ima(index, previous))
+        return y, (st.index, st.previousValue)
 
     def shift_math_cc(self, x, rate, phase=0.0, chunk=None):
         x = _c64(x); y = np.empty_like(x); chunk = chunk or max(x.size, 1)

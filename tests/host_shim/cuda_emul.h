@@ -51,6 +51,7 @@ struct State {
     std::vector<unsigned char> smem;
     long barriers = 0, switches = 0;
     int order_mode = 0;                       // 0 alternate, 1 reverse, 2 random, 3 forward
+    bool launch_error = false;                // a launch configuration the hardware would refuse; cleared by cudaGetLastError()
     unsigned long long rng = 88172645463325252ULL;
 };
 inline State& st()
@@ -108,6 +109,12 @@ template <typename K, typename... A>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, K kernel, A... args)
 {
     State& s = st();
+    // what cudaLaunchKernel would refuse on sm_100 (cudaErrorInvalidConfiguration / invalid value): recorded for cudaGetLastError()
+    if (grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535u || grid.z > 65535u || grid.x > 2147483647u || block.x * block.y * block.z == 0 ||
+        block.x * block.y * block.z > 1024u || block.x > 1024u || block.y > 1024u || block.z > 64u || smem_bytes > 227u * 1024u) {
+        s.launch_error = true;
+        return;
+    }
     s.grid = grid; s.block = block;
     const int nthreads = (int)(block.x * block.y * block.z);
     const size_t stack_bytes = 256 * 1024;
@@ -184,7 +191,11 @@ inline void named_sync(int id, int nthreads)
     while (b.generation == my) yield();
 }
 
+inline bool take_launch_error() { State& s = st(); const bool e = s.launch_error; s.launch_error = false; return e; }
+
 }  // namespace cuda_emul
+
+extern "C" int cuda_emul_take_launch_error(void);     // cuda_emul_runtime.cpp asks through this (defined once per library, below or in the harness)
 
 // ---- the CUDA surface the kernels use ----------------------------------------------------------------------------------------
 #define threadIdx (::cuda_emul::st().cur->tid)

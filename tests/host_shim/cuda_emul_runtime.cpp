@@ -5,7 +5,8 @@
 #include <cuda_runtime.h>
 
 extern "C" {
-cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+extern "C" int cuda_emul_take_launch_error(void);
+cudaError_t cudaGetLastError(void) { return cuda_emul_take_launch_error() ? cudaErrorInvalidConfiguration : cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
 cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }

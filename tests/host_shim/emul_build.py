@@ -48,6 +48,7 @@ void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(
 int cuda_fail(cudaError_t, const char* what, const char*, int) { set_error("cuda_emul: %s failed", what); return -100; }
 }
 extern "C" const char* emul_last_error(void) { return csdrb::g_emul_error; }
+extern "C" int cuda_emul_take_launch_error(void) { return cuda_emul::take_launch_error() ? 1 : 0; }
 extern "C" long emul_barriers(void) { return cuda_emul::st().barriers; }
 """
 
@@ -147,7 +148,8 @@ def build_full(out_dir: Path):
         src = transform((CSRC / cu).read_text()).replace('#include "', f'#include "{CSRC}/')
         src = src.replace(f'#include "{CSRC}/csdr_b200.h"', '#include "csdr_b200.h"')
         cpp = out_dir / f"full_{Path(cu).stem}.cpp"
-        cpp.write_text(PRELUDE_FULL + src)
+        hook = 'extern "C" int cuda_emul_take_launch_error(void) { return cuda_emul::take_launch_error() ? 1 : 0; }\n' if cu == "capi.cu" else ""
+        cpp.write_text(PRELUDE_FULL + hook + src)
         obj = cpp.with_suffix(".o")
         r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-w"] + SANITIZE + [f"-I{CUDA_INC}", f"-I{SHIM}", f"-I{CSRC}",
                             f"-I{ROOT / 'include'}", "-c", str(cpp), "-o", str(obj)], capture_output=True, text=True)

@@ -47,3 +47,10 @@ test_reference_binary_runs_on_our_library = g.test_reference_binary_runs_on_our_
 
 import test_gpu_zz_shift_math as zz  # noqa: E402
 test_shift_math_command = zz.test_shift_math_command
+
+import test_gpu_zz_adpcm as za  # noqa: E402
+test_adpcm_commands = za.test_adpcm_commands
+test_openwebrx_waterfall_chain = za.test_openwebrx_waterfall_chain
+
+import test_gpu_zz_control as zc  # noqa: E402
+test_initial_tuning_through_the_control_channel = zc.test_initial_tuning_through_the_control_channel

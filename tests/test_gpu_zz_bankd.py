@@ -47,7 +47,7 @@ def oracle_channel(oracle, wide_c64, rate, taps, tail):
     return oracle.convert_f_s16(oracle.fastagc_ff(oracle.deemphasis_nfm_ff(oracle.limit_ff(d, 1.0), GOLD["nfm_taps_48000"]), 1024, 1.0))
 
 
-def run(bankd, args, data, sinks, timeout=180):
+def run(bankd, args, data, sinks, timeout=300):
     cmd = [bankd] + args + [f"{r}:{p}" for r, p in zip(RATES, sinks)]
     r = subprocess.run(cmd, input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -103,7 +103,7 @@ def test_tcp_ingest_and_tcp_sink(bankd, tmp_path):
 
     def listen():
         import time
-        for _ in range(200):                                              # the daemon opens its listener after creating the bank
+        for _ in range(900):                                              # the daemon opens its listener after creating the bank (CUDA start-up first)
             try:
                 c = socket.create_connection(("127.0.0.1", out_port), timeout=1); break
             except OSError:

@@ -158,6 +158,24 @@ def test_spectrum_side_path(elementwise, oracle):
     assert np.abs(p - oracle.logpower_cf(x, -70.0)).max() <= 2e-5
 
 
+def test_ima_adpcm_rows_bit_exact(elementwise, oracle):
+    """8(f) rank 4: the audio / waterfall ADPCM encoder, one thread per row, integer arithmetic -> identical bytes and states"""
+    rng = np.random.default_rng(4)
+    rows, n = 37, 2050
+    x = (rng.standard_normal((rows, n)) * rng.choice([10, 300, 5000, 40000], (rows, 1))).clip(-32768, 32767).astype(np.int16)
+    st = np.stack([rng.integers(0, 89, rows), rng.integers(-32768, 32768, rows)], 1).astype(np.int32); st0 = st.copy()
+    out = Z((rows, n // 2), np.uint8)
+    assert elementwise.emul_launch_adpcm_encode_rows(P(x), n, P(out), n // 2, rows, n, P(st)) >= 0
+    for r in range(rows):
+        want, (wi, wp) = oracle.encode_ima_adpcm_i16_u8(x[r], int(st0[r, 0]), int(st0[r, 1]))
+        assert np.array_equal(out[r], want) and (st[r, 0], st[r, 1]) == (wi, wp), r
+    for fft_size in (16, 511, 512, 2048):
+        db = rng.uniform(-130, 10, (rows, fft_size)).astype(np.float32); db[0, :3] = [np.nan, 400.0, -400.0]      # beyond +-327.67 dB the short wraps, like the reference
+        out = Z((rows, (fft_size + 10) // 2), np.uint8)
+        assert elementwise.emul_launch_compress_fft_adpcm_rows(P(db), fft_size, P(out), out.shape[1], rows, fft_size) >= 0
+        assert np.array_equal(out, oracle.compress_fft_adpcm_f_u8(db, fft_size)), fft_size
+
+
 # ------------------------------------------------------------------------------------------------------------------ K2 and shift variants
 @pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37)])
 def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):

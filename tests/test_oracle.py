@@ -165,6 +165,26 @@ def test_golden_and_ref_shift_math(oracle):
                 assert np.float32(pa) == np.float32(pb) and rel_rms(a, b) < TIGHT, (rate, ph0, chunk)
 
 
+def test_ref_ima_adpcm(oracle):
+    """8(f) rank 4: the oracle's IMA ADPCM encoder against the compiled reference's (bytes and carried state), and the waterfall line
+    compression against the reference CLI's output"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    from oracle.pyoracle import Ref, REF_CLI
+    r = Ref()
+    rng = np.random.default_rng(0)
+    for n in (2, 10, 1000, 4097):
+        x = (rng.standard_normal(n) * rng.choice([10, 300, 5000, 40000])).clip(-32768, 32767).astype(np.int16)
+        (a, sa), (b, sb) = oracle.encode_ima_adpcm_i16_u8(x, 3, -200), r.encode_ima_adpcm_i16_u8(x, 3, -200)
+        assert np.array_equal(a, b) and sa == sb
+    fft_size, frames = 512, 5
+    db = rng.uniform(-120, -20, (frames, fft_size)).astype(np.float32)
+    p = subprocess.run(["bash", "-c", f"{REF_CLI} compress_fft_adpcm_f_u8 {fft_size}"], input=db.tobytes(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    got = np.frombuffer(p.stdout, np.uint8); want = oracle.compress_fft_adpcm_f_u8(db, fft_size).reshape(-1)
+    assert p.returncode == 0 and np.array_equal(got[:want.size], want)
+
+
 def test_golden_spectrum_and_unroll(oracle, ref=None):
     assert rel_rms(oracle.precalculate_window(1024, "HAMMING"), GOLD["win_hamming_1024"]) < TIGHT
     assert np.abs(oracle.logpower_cf(GOLD["spec_in"], -70.0) - GOLD["logpower_out"]).max() < 2e-5          # dB; an ulp at |x| ~ 100
