@@ -42,6 +42,40 @@ int get_twiddles(int n, const float2** out, cudaStream_t st)
     return 0;
 }
 
+static std::map<int, float2*> g_tw16;
+int get_twiddles16(int n, const float2** out, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw16.find(n);
+    if (it != g_tw16.end()) { *out = it->second; return 0; }
+    std::vector<float2> h((size_t)4 * n);
+    fft16_fill_twiddles(n, h.data());
+    float2* d = nullptr;
+    CSDRB_CUDA(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CSDRB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, st));
+    CSDRB_CUDA(cudaStreamSynchronize(st));
+    g_tw16[n] = d;
+    *out = d;
+    return 0;
+}
+
+template <int N>
+static int launch_c2c16_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw16, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * fft_smem_elems(N);
+    if (inverse) {
+        auto k = fft_c2c_batch16_kernel<N, true>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft16_threads(N), smem, st>>>(in, is, out, os, tw16);
+    } else {
+        auto k = fft_c2c_batch16_kernel<N, false>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft16_threads(N), smem, st>>>(in, is, out, os, tw16);
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ---- K7: batched c2c -------------------------------------------------------------------------------
 template <int N>
 static int launch_c2c_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw, cudaStream_t st)
@@ -66,6 +100,16 @@ int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long
 {
     if (batch <= 0) return 0;
     if (n < 2 || n > FFT_MAX_N || (n & (n - 1))) { set_error("fft: size %d unsupported (power of two, 2..%d)", n, FFT_MAX_N); return -1; }
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    if (radix16 && n >= 32) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(n, &tw16, st)) return rc;
+        switch (n) {
+#define X(N) case N: if constexpr (N >= 32) return launch_c2c16_n<N>(d_in, in_stride, d_out, out_stride, batch, inverse != 0, tw16, st); break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+    }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(n, &tw, st)) return rc;
     switch (n) {

@@ -3,6 +3,7 @@
 // __syncthreads() a real barrier) in the CPU test tier.  The product includes this file from fft.cu only.
 #pragma once
 #include "fft.cuh"
+#include "fft16.cuh"
 
 namespace csdrb {
 
@@ -81,6 +82,17 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
         __syncthreads();
     }
     if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
+}
+
+// EXPERIMENT: the batched transform with radix-16 passes (fft16.cuh); tw16 = the four-plane table of fft16_fill_twiddles
+template <int N, bool INV>
+__global__ void __launch_bounds__(fft16_threads(N))
+fft_c2c_batch16_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    FftRowIn src(in + (long)blockIdx.x * in_stride); FftRowOut dst(out + (long)blockIdx.x * out_stride);
+    block_fft16_io<N, fft16_threads(N), INV>(s, tw16, threadIdx.x, src, dst);
 }
 
 // Same operation with the transforms' ends fused: the forward FFT's first pass reads the zero-padded block straight from global

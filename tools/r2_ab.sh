@@ -13,4 +13,5 @@ for staged in 0 1; do
   done
 done
 python tools/bench_configs.py k 2>&1 | grep -i "fft\|K7" | tee gpurun_out/r2_ab_fft.txt
+CSDRB_FFT_RADIX16=1 python tools/bench_configs.py k 2>&1 | grep -i "fft\|K7" | tee gpurun_out/r2_ab_fft_radix16.txt
 timeout 120 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py 2>&1 | tail -3 | tee gpurun_out/r2_ab_memcheck.log
