@@ -137,6 +137,22 @@ int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long o
     }
     const dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, channels);
     static const bool staged = getenv("CSDRB_OLAFIR_STAGED") != nullptr;            // A/B switch: the r01 kernel with staged copies
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT: radix-16 passes for 16^k sizes (256, 4096)
+    if (radix16 && !staged && (fft_size == 256 || fft_size == 4096)) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
+        const size_t fsmem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + 2 * (size_t)(fft_size - input_size));
+        if (fft_size == 256) {
+            auto k = olafir_bank_fused16_kernel<256>;
+            k<<<grid, fft16_threads(256), fsmem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw16);
+        } else {
+            auto k = olafir_bank_fused16_kernel<4096>;
+            if (fsmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<grid, fft16_threads(4096), fsmem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw16);
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        return 1;
+    }
     if (fft_size >= 16 && !staged) {
         const size_t fsmem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + 2 * (size_t)(fft_size - input_size));
         switch (fft_size) {

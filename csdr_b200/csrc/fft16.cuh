@@ -149,6 +149,16 @@ __device__ __forceinline__ void fft16_rest(float2* __restrict__ s, const float2*
     }
 }
 
+template <int N, int NT, int NS, bool INV>
+__device__ __forceinline__ void fft16_rest_but_last(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
+{
+    if constexpr (NS * 16 < N) {
+        struct Nowhere { __device__ __forceinline__ void store(int, float2) const {} } nowhere;
+        fft16_pass<N, NT, NS, INV, false>(s, tw, tid, nowhere);
+        fft16_rest_but_last<N, NT, NS * 16, INV>(s, tw, tid);
+    }
+}
+
 // N-point transform in.load(i) -> out.store(i), N >= 32 (smaller sizes stay on block_fft_io); `s` is scratch; NT = fft16_threads(N)
 template <int N, int NT, bool INV, typename In, typename Out>
 __device__ __forceinline__ void block_fft16_io(float2* __restrict__ s, const float2* __restrict__ tw, int tid, In& in, Out& out)
@@ -158,6 +168,42 @@ __device__ __forceinline__ void block_fft16_io(float2* __restrict__ s, const flo
     static_assert(R0 < N, "at least one radix-16 pass follows the first pass");
     fft16_pass_first<N, NT, R0, INV>(s, tid, in);
     fft16_rest<N, NT, R0, INV>(s, tw, tid, out);
+}
+
+// FFT_N(in) -> map -> IFFT_N -> out for N = 16^k (256, 4096): the forward transform's last radix-16 pass leaves elements j + r*N/16 in the
+// registers of thread j, which are exactly the inputs of the inverse transform's first pass -- the spectrum never returns to shared memory.
+//   map.prefetch(r, i) / map.at(r, i, v): per-element data of slot r (element i = j + r*N/16), fetched while the butterfly runs.
+template <int N, int NT, typename In, typename Map, typename Out>
+__device__ __forceinline__ void block_fft16_map_ifft(float2* __restrict__ s, const float2* __restrict__ tw, int tid, In& in, Map& map, Out& out)
+{
+    static_assert(fft16_first_radix(N) == 16 && N >= 256, "register hand-over needs radix 16 at both ends");
+    constexpr int NB = N / 16, NSL = N / 16;                              // last pass: sub-transform size N/16
+    struct Nowhere { __device__ __forceinline__ void store(int, float2) const {} } nowhere;
+    fft16_pass_first<N, NT, 16, false>(s, tid, in);
+    if constexpr (N > 256) fft16_rest_but_last<N, NT, 16, false>(s, tw, tid);
+    {   // forward last pass + map + inverse first pass, all in registers
+        float2 v[16];
+        const int j = tid;
+        const bool live = (NB >= NT) || j < NB;
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) map.prefetch(r, j + r * NSL);
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = s[fft_pad(j + r * NB)];
+            fft16_butterfly<N, NSL, false>(v, j, tw);
+        }
+        __syncthreads();                                                 // reads of s done
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = map.at(r, j + r * NSL, v[r]);
+            dft16<true>(v);                                              // inverse transform, first pass: inputs j + r*NB, no twiddles
+#pragma unroll
+            for (int r = 0; r < 16; r++) s[fft_pad(j * 16 + r)] = v[r];
+        }
+        __syncthreads();
+    }
+    fft16_rest<N, NT, 16, true>(s, tw, tid, out);
+    (void)nowhere;
 }
 
 }  // namespace csdrb

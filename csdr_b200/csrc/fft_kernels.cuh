@@ -84,6 +84,62 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
     if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
 }
 
+// EXPERIMENT: the fused overlap-add kernel on radix-16 passes, sizes 16^k (config 5's 4096): 4R+4W shared accesses per point and block
+template <int N>
+__global__ void __launch_bounds__(fft16_threads(N), (N <= 4096 ? 2 : 1))
+olafir_bank_fused16_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                           const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                           int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft16_threads(N);
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    float2* tail_cur = s + fft_smem_elems(N);
+    float2* tail_next = tail_cur + overlap;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;      // see olafir_bank_kernel
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail_cur[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+    struct TapsMap16 {                                                  // spectrum * taps_fft, rounding sequence of libcsdr.c:827-828
+        const float2* H; float2 hh[16];
+        __device__ __forceinline__ void prefetch(int r, int i) { hh[r] = __ldg(H + i); }
+        __device__ __forceinline__ float2 at(int r, int, float2 a) const
+        {
+            const float2 h = hh[r];
+            return make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        }
+    } map;
+    map.H = H;
+    const float inv_n = 1.0f / (float)N;
+    for (int b = b_start; b < b_last; b++) {
+        struct BlockIn {
+            const float2* xb; int input_size;
+            __device__ __forceinline__ float2 load(int i) const { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }
+        } src{x + (long)b * input_size, input_size};
+        struct BlockOut {
+            float2* yb; const float2* tail_cur; float2* tail_next; int input_size, overlap; float inv_n; bool emit;
+            __device__ __forceinline__ void store(int i, float2 raw) const
+            {
+                float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
+                if (i < overlap) v = make_float2(__fadd_rn(v.x, tail_cur[i].x), __fadd_rn(v.y, tail_cur[i].y));
+                if (i < input_size) { if (emit) yb[i] = v; }
+                else tail_next[i - input_size] = v;
+            }
+        } dst{y + (long)b * input_size, tail_cur, tail_next, input_size, overlap, inv_n, b >= b_first};
+        block_fft16_map_ifft<N, NT>(s, tw16, tid, src, map, dst);
+        float2* t = tail_cur; tail_cur = tail_next; tail_next = t;
+    }
+    __syncthreads();
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail_cur[i];
+}
+
 // EXPERIMENT: the batched transform with radix-16 passes (fft16.cuh); tw16 = the four-plane table of fft16_fill_twiddles
 template <int N, bool INV>
 __global__ void __launch_bounds__(fft16_threads(N))
