@@ -182,6 +182,27 @@ int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_
 {
     if (nblocks <= 0) return 0;
     if (fft_size < 4 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("fastddc_fwd: fft_size %d unsupported", fft_size); return -1; }
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    if (radix16 && fft_size >= 32) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
+        const size_t smem16 = sizeof(float2) * (size_t)fft_smem_elems(fft_size);
+        switch (fft_size) {
+#define X(N) case N: if constexpr (N >= 32) { auto k = fastddc_fwd16_kernel<N>; \
+            if (smem16 > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16)); \
+            k<<<nblocks, fft16_threads(N), smem16, st>>>(d_in, d_spectra, d_overlap_io, input_size, tw16); } break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        const int ov16 = fft_size - input_size;
+        if (ov16 > 0) {
+            fastddc_carry_overlap_kernel<<<1, 1024, 0, st>>>(d_in, d_overlap_io, ov16, (long)nblocks * input_size);
+            CSDRB_CUDA(cudaGetLastError());
+            return 2;
+        }
+        return 1;
+    }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
     const size_t smem = sizeof(float2) * (size_t)fft_smem_elems(fft_size);

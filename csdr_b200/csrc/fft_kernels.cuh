@@ -236,6 +236,25 @@ fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, 
     block_fft_io<N, NT, false>(s, tw, tid, src, dst);
 }
 
+// EXPERIMENT: the same forward step on radix-16 passes (16384 = 4*16^3: four passes instead of five)
+template <int N>
+__global__ void __launch_bounds__(fft16_threads(N))
+fastddc_fwd16_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, const float2* __restrict__ overlap_in,
+                     int input_size, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    const int b = blockIdx.x;
+    const int overlap = N - input_size;
+    const long start = (long)b * input_size - overlap;
+    struct SlideIn {
+        const float2* in; const float2* ov; long start; int overlap;
+        __device__ __forceinline__ float2 load(int i) const { const long p = start + i; return p >= 0 ? __ldg(in + p) : ov[overlap + p]; }
+    } src{in, overlap_in, start, overlap};
+    FftRowOut dst(spectra + (long)b * N);
+    block_fft16_io<N, fft16_threads(N), false>(s, tw16, threadIdx.x, src, dst);
+}
+
 __global__ void __launch_bounds__(1024)
 fastddc_carry_overlap_kernel(const float2* __restrict__ in, float2* __restrict__ overlap_io, int overlap, long total)
 {
