@@ -2,12 +2,16 @@
 //
 // Not a CPU fallback: nothing under csdr_b200/ can reach this file; it exists so that kernels which cannot be run in this container
 // (no GPU) are still EXECUTED, with their real index arithmetic, barriers and rounding, before GPU minutes are spent on them.
-// Model: one CTA at a time; every CUDA thread of the CTA is a ucontext fiber on one OS thread; __syncthreads() / __syncwarp() are
-// real barriers between fibers (a fiber that reaches one yields until all live fibers of the CTA / warp have arrived);
-// threadIdx/blockIdx/blockDim/gridDim are per-fiber values; dynamic shared memory is one buffer per CTA (pre-filled with a NaN pattern); IEEE single-precision
-// intrinsics map onto the same operations (fmaf is a true fused multiply-add on the host as well).
-// Not modelled: inline PTX (kernels that use it are not emulated), warp shuffles/votes, atomics, memory-model subtleties -- a data race
-// a GPU could expose may go unnoticed here (fibers switch only at barriers).
+// Model: one CTA at a time; every CUDA thread of the CTA is a ucontext fiber on one OS thread; __syncthreads(), __syncwarp(), named
+// barriers (bar.sync id, n) and mbarrier waits are real barriers between fibers (a fiber that reaches one yields until the others have
+// arrived); the order in which fibers run between barriers alternates / reverses / is shuffled (CUDA_EMUL_ORDER) so that a missing
+// barrier shows as a wrong result; threadIdx/blockIdx/blockDim/gridDim are per-fiber values; dynamic shared memory is one buffer per CTA
+// pre-filled with a NaN pattern; IEEE single-precision intrinsics map onto the same operations (fmaf is a true FMA on the host too);
+// __shfl_xor_sync goes through a per-warp exchange; the inline-PTX helpers of csrc/common.cuh have C++ models here (FFMA2 = two FMAs,
+// cp.async.bulk = alignment-checked memcpy that completes an mbarrier, st.global.L1::no_allocate = alignment-checked store); launch
+// configurations the hardware would refuse (gridDim.y/z > 65535, > 1024 threads, > 227 KB shared) fail like they would on the GPU.
+// Not modelled: the memory model (fibers switch only at barriers, so a race that needs true concurrency can go unnoticed), occupancy and
+// register limits, alignment of plain vector loads (build with CUDA_EMUL_SANITIZE=1 for that), atomics, votes, clusters, tensor cores.
 #pragma once
 #define CSDRB_HOST_EMULATION 1
 #include <cmath>
