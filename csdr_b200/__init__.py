@@ -48,6 +48,10 @@ class _Unroll(C.Structure):             # shift_unroll_data_t (= libcsdr.h:199-2
     _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
 
+class _Table(C.Structure):              # shift_table_data_t (= libcsdr.h:180-184)
+    _fields_ = [("table", C.POINTER(C.c_float)), ("table_size", C.c_int)]
+
+
 class _Ima(C.Structure):                # ima_adpcm_state_t (= ima_adpcm.h:35-38)
     _fields_ = [("index", C.c_int), ("previousValue", C.c_int)]
 
@@ -127,6 +131,10 @@ def lib() -> C.CDLL:
     L.shift_unroll_init.argtypes = [C.c_float, it]; L.shift_unroll_init.restype = _Unroll
     L.shift_unroll_cc.argtypes = [vp, vp, it, C.POINTER(_Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
     L.shift_math_cc.argtypes = [vp, vp, it, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
+    L.shift_table_init.argtypes = [it]; L.shift_table_init.restype = _Table
+    L.shift_table_deinit.argtypes = [_Table]
+    L.shift_table_cc.argtypes = [vp, vp, it, C.c_float, _Table, C.c_float]; L.shift_table_cc.restype = C.c_float
+    L.csdrb_shift_table_bank_cc.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp, it, vp, sz, vp]
     L.encode_ima_adpcm_i16_u8.argtypes = [vp, vp, it, _Ima]; L.encode_ima_adpcm_i16_u8.restype = _Ima
     L.csdrb_encode_ima_adpcm_rows_i16_u8.argtypes = [vp, lg, vp, lg, it, it, vp, vp]
     L.csdrb_compress_fft_adpcm_rows_f_u8.argtypes = [vp, lg, vp, lg, it, it, vp]
@@ -477,6 +485,19 @@ class libcsdr:
         return y, (st.index, st.previousValue)
 
     @staticmethod
+    def shift_table_init(size=65536):
+        d = lib().shift_table_init(size); t = np.ctypeslib.as_array(d.table, shape=(size,)).copy(); lib().shift_table_deinit(d); return t
+
+    @staticmethod
+    def shift_table_cc(x, rate, table, phase=0.0, chunk=None):
+        x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x); table = np.ascontiguousarray(table, np.float32); chunk = chunk or max(x.size, 1)
+        d = _Table(table.ctypes.data_as(C.POINTER(C.c_float)), table.size)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = lib().shift_table_cc(x[s0:].ctypes.data, y[s0:].ctypes.data, n, rate, d, phase)
+        return y, float(np.float32(phase))
+
+    @staticmethod
     def shift_math_cc(x, rate, phase=0.0, chunk=None):
         x = np.ascontiguousarray(x, np.complex64); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
         for s0 in range(0, x.size, chunk):
@@ -625,6 +646,27 @@ def shift_math_bank_cc(x, rates, phases=None, out=None):
     scratch = _scratch(lib().csdrb_shift_math_bank_scratch_bytes(ch, n), xr.device)
     _check(lib().csdrb_shift_math_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_rates.data_ptr(), d_phase.data_ptr(),
                                           scratch.data_ptr(), scratch.numel(), _stream()), "shift_math_bank_cc")
+    return out, d_phase
+
+
+def shift_table_bank_cc(x, rates, table, phases=None, out=None):
+    """x: [N] (one shared wideband stream) or [C, N] complex64; table: quarter-wave sine table (numpy or CUDA tensor); returns (y [C, N], new phases [C])."""
+    import torch
+    rates = np.atleast_1d(np.asarray(rates, np.float32)); ch = rates.size
+    shared = (x.dim() == 1) if x.dtype == torch.complex64 else (x.dim() == 2)
+    xr, ptr, stride, xc, n = _as_cf32_rows(x)
+    if shared:
+        stride = 0
+    else:
+        assert xc == ch
+    d_table = table if isinstance(table, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(table, np.float32)).to(xr.device)
+    d_rates = torch.from_numpy(rates).to(xr.device)
+    d_phase = torch.zeros(ch, dtype=torch.float32, device=xr.device) if phases is None else phases.clone()
+    if out is None:
+        out = torch.empty((ch, n), dtype=torch.complex64, device=xr.device)
+    scratch = _scratch(lib().csdrb_shift_math_bank_scratch_bytes(ch, n), xr.device)
+    _check(lib().csdrb_shift_table_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, d_rates.data_ptr(), d_phase.data_ptr(), d_table.data_ptr(),
+                                           d_table.numel(), scratch.data_ptr(), scratch.numel(), _stream()), "shift_table_bank_cc")
     return out, d_phase
 
 

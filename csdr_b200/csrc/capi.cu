@@ -340,6 +340,16 @@ int csdrb_shift_math_bank_cc(const complexf* d_in, long in_stride, complexf* d_o
     return rc < 0 ? rc : counted(0, rc);
 }
 
+int csdrb_shift_table_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
+                              const float* d_rates, float* d_phase_io, const float* d_table, int table_size, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (too_many_channels(channels, "shift_table bank")) return -1;
+    if (!d_in || !d_out || !d_rates || !d_phase_io || !d_table) { set_error("shift_table bank: null pointer"); return -1; }
+    int rc = launch_shift_table_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size,
+                                     d_rates, d_phase_io, d_table, table_size, d_scratch, scratch_bytes, S(stream));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_shift_addfast_bank_cc(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int channels, int input_size,
                                 const shift_addfast_data_t* d_params, float* d_phase_io, int chunk, void* d_scratch, size_t scratch_bytes, void* stream)
 {
@@ -740,6 +750,39 @@ float shift_addition_cc(complexf* input, complexf* output, int input_size, shift
     float* d_phase = reinterpret_cast<float*>(static_cast<char*>(g_ctx.buf[2]) + offsetof(decltype(blob), phase));
     A_CHECK(csdrb_shift_addition_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size,
                                          (const shift_addition_data_t*)g_ctx.buf[2], d_phase, input_size, g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
+    A_DOWN(output, 1, (size_t)input_size * 8, who);
+    float new_phase = 0.f;
+    A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);
+    A_SYNC(who);
+    return new_phase;
+}
+
+float shift_table_cc(complexf* input, complexf* output, int input_size, float rate, shift_table_data_t table_data, float starting_phase)
+{
+    const char* who = "shift_table_cc";
+    if (input_size <= 0 || !table_data.table || table_data.table_size < 2) return starting_phase;
+    A_BEGIN(who);
+    // slot 0: input, 1: output, 2: rate at +0 and phase at +64, 3: scratch.  The table has its own device buffer and is sent with every call
+    // (256 KB for the default size: a host pointer is no proof that the contents are the ones sent last time).
+    static float* d_table = nullptr; static int d_table_cap = 0;
+    A_UP(0, input, (size_t)input_size * 8, who);
+    A_CHECK(g_ctx.reserve(1, (size_t)input_size * 8 + 16), who);
+    float blob[17] = {0};
+    blob[0] = rate; blob[16] = starting_phase;
+    A_UP(2, blob, sizeof blob, who);
+    float* d_rate = reinterpret_cast<float*>(g_ctx.buf[2]);
+    float* d_phase = d_rate + 16;
+    if (table_data.table_size > d_table_cap) {
+        if (d_table) A_CUDA(cudaFree(d_table), who);
+        d_table = nullptr; d_table_cap = 0;
+        A_CUDA(cudaMalloc(&d_table, (size_t)table_data.table_size * 4), who);
+        d_table_cap = table_data.table_size;
+    }
+    A_CUDA(cudaMemcpyAsync(d_table, table_data.table, (size_t)table_data.table_size * 4, cudaMemcpyHostToDevice, g_ctx.stream), who);
+    const size_t sb = csdrb_shift_math_bank_scratch_bytes(1, input_size);
+    A_CHECK(g_ctx.reserve(3, sb + 16), who);
+    A_CHECK(csdrb_shift_table_bank_cc((const complexf*)g_ctx.buf[0], 0, (complexf*)g_ctx.buf[1], 0, 1, input_size, d_rate, d_phase, d_table, table_data.table_size,
+                                      g_ctx.buf[3], g_ctx.cap[3], g_ctx.stream), who);
     A_DOWN(output, 1, (size_t)input_size * 8, who);
     float new_phase = 0.f;
     A_CUDA(cudaMemcpyAsync(&new_phase, d_phase, 4, cudaMemcpyDeviceToHost, g_ctx.stream), who);

@@ -48,6 +48,8 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
 size_t shift_math_scratch_bytes(int channels, int n);
 int launch_shift_math_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, const float* d_rates,
                            float* d_phase_io, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+int launch_shift_table_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, const float* d_rates,
+                            float* d_phase_io, const float* d_table, int table_size, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
 int launch_decimating_shift_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
                                  const float* d_params, int decimation, int* d_remain_io, float* d_phase_io, int* d_out_size, cudaStream_t st);
 

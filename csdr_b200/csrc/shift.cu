@@ -18,6 +18,7 @@
 //   dshift_kernel            : decimating variant, one thread per channel (chains of a few hundred outputs).
 // All products/sums use __fmul_rn/__fadd_rn/__fsub_rn so nvcc cannot contract them into FMAs.
 #include "common.cuh"
+#include <climits>
 #include "kernels.h"
 
 namespace csdrb {
@@ -267,6 +268,69 @@ shift_math_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __
     }
 }
 
+// shift_table_cc (libcsdr.c:223-260): the same per-sample phase chain as shift_math_cc (seeds from shift_math_chain_kernel), but cos/sin come
+// from a quarter-wave table.  A table step is 2.4e-5 rad, far above the 1e-5 bar, so the index arithmetic has to be the reference BUILD's:
+// under -ffast-math its two divisions by PI/2 are multiplications by float constants (see oracle.c).  Indices the source would read outside
+// the table (it is marked "RTODO") are clamped.
+__global__ void __launch_bounds__(128)
+shift_table_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                        const float* __restrict__ rates, const float* __restrict__ seg_phase, const float* __restrict__ table, int table_size,
+                        int n, int nseg)
+{
+    __shared__ float2 tile_all[4][32 * SH_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = tile_all[warp];
+    const int ch = blockIdx.y;
+    const int k0 = (blockIdx.x * 4 + warp) * 32;
+    if (k0 >= nseg) return;
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float inc = __fmul_rn(__fmul_rn(rates[ch], 2.f), PI_F);
+    const float K = 0.6366197466850281f;                                 // fl(1 / fl(PI/2)), the constant the reference build multiplies by
+    const float HALF_PI = 1.5707963705062866f;                           // fl(PI/2)
+    const float K2 = __fmul_rn((float)table_size, K);
+    const int k = k0 + lane;
+    const bool live = k < nseg;
+    const int my_len = live ? min(MATH_SEG, n - k * MATH_SEG) : 0;
+    float ph = live ? seg_phase[(long)ch * nseg + k] : 0.f;
+    const int rows = min(32, nseg - k0);
+    const int max_len = min(MATH_SEG, n - k0 * MATH_SEG);
+    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * MATH_SEG + t0 + lane;
+            const int len_r = min(MATH_SEG, n - (k0 + r) * MATH_SEG);
+            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+        if (live) {
+            float2* row = tile + lane * SH_PITCH;
+            const int steps = min(SH_TILE, my_len - t0);
+            for (int j = 0; j < steps; j++) {
+                const float qf = __fmul_rn(ph, K);
+                const int quadrant = (fabsf(qf) < 2147483648.0f) ? __float2int_rz(qf) : INT_MIN;     // cvttss2si
+                const float vphase = __fsub_rn(ph, __fmul_rn((float)quadrant, HALF_PI));
+                const float fi = __fmul_rn(vphase, K2);
+                int si = (fabsf(fi) < 2147483648.0f) ? __float2int_rz(fi) : INT_MIN;
+                int ci = table_size - 1 - si;
+                if (quadrant & 1) { const int t = si; si = ci; ci = t; }
+                si = min(table_size - 1, max(0, si)); ci = min(table_size - 1, max(0, ci));           // the source would read outside the table here
+                const float s = (quadrant > 1 ? -1.0f : 1.0f) * __ldg(table + si);
+                const float c = ((quadrant && quadrant < 3) ? -1.0f : 1.0f) * __ldg(table + ci);
+                const float2 v = row[j];
+                row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                ph = math_step(ph, inc);
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * MATH_SEG + t0 + lane;
+            const int len_r = min(MATH_SEG, n - (k0 + r) * MATH_SEG);
+            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
+        }
+        __syncwarp();
+    }
+}
+
 // decimating variant: status per channel {decimation_remain, starting_phase, output_size} (libcsdr_gpl.h:39-44)
 __global__ void dshift_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                               const float3* __restrict__ params, int n, int decimation, int* __restrict__ remain_io,
@@ -401,6 +465,22 @@ int launch_shift_math_bank(const float2* d_in, long in_stride, float2* d_out, lo
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nseg + 127) / 128, channels);
     shift_math_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, d_rates, seg_phase, n, nseg);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
+
+int launch_shift_table_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, const float* d_rates,
+                            float* d_phase_io, const float* d_table, int table_size, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    if (!d_table || table_size < 2) { set_error("shift_table bank: a table of at least two entries is needed"); return -1; }
+    const int nseg = (n + MATH_SEG - 1) / MATH_SEG;
+    if (!d_scratch || scratch_bytes < (size_t)channels * nseg * sizeof(float)) { set_error("shift_table bank: scratch too small"); return -1; }
+    float* seg_phase = static_cast<float*>(d_scratch);
+    shift_math_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(d_rates, d_phase_io, seg_phase, channels, n, nseg);   // the same phase chain as shift_math_cc
+    CSDRB_CUDA(cudaGetLastError());
+    dim3 grid((nseg + 127) / 128, channels);
+    shift_table_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, d_rates, seg_phase, d_table, table_size, n, nseg);
     CSDRB_CUDA(cudaGetLastError());
     return 2;
 }

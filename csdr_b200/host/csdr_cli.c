@@ -280,6 +280,25 @@ static int cmd_shift_math_cc(int argc, char **argv)                        /* cs
     }
 }
 
+static int cmd_shift_table_cc(int argc, char **argv)                       /* csdr.c:725-747 */
+{
+    G.wideband = 1;
+    if (argc <= 2) return complain("need required parameter (rate)");
+    float phase = 0, rate = 0; sscanf(argv[2], "%g", &rate);
+    int table_size = 65536; if (argc > 3) sscanf(argv[3], "%d", &table_size);
+    if (!announce_block(open_block())) return -2;
+    shift_table_data_t table = shift_table_init(table_size);
+    who(); fprintf(stderr, "LUT initialized\n");
+    complexf *in = must_alloc(sizeof(complexf) * (size_t)block), *out = must_alloc(sizeof(complexf) * (size_t)block);
+    for (;;) {
+        if (feof(stdin)) return 0;
+        if (!fread(in, sizeof(complexf), (size_t)block, stdin)) return 0;
+        phase = shift_table_cc(in, out, block, rate, table, phase);
+        fwrite(out, sizeof(complexf), (size_t)block, stdout);
+        end_of_block();
+    }
+}
+
 static int cmd_shift_addfast_cc(int argc, char **argv)                     /* csdr.c:749-798 */
 {
     G.wideband = 1;
@@ -703,6 +722,7 @@ static const struct { const char *name; int (*run)(int, char **); const char *sy
     {"encode_ima_adpcm_s16_u8", cmd_encode_ima_adpcm, "encode_ima_adpcm_s16_u8"},
     {"shift_unroll_cc", cmd_shift_unroll_cc, "shift_unroll_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
     {"shift_math_cc", cmd_shift_math_cc, "shift_math_cc <rate>"},
+    {"shift_table_cc", cmd_shift_table_cc, "shift_table_cc <rate> [table_size]"},
     {"shift_addfast_cc", cmd_shift_addfast_cc, "shift_addfast_cc <rate> | --fifo <fifo_path> | --fd <fd>"},
     {"decimating_shift_addition_cc", cmd_decimating_shift_addition_cc, "decimating_shift_addition_cc <rate> [decimation]"},
     {"fft_cc", cmd_fft_cc, "fft_cc <fft_size> <out_of_every_n_samples> [window]"},

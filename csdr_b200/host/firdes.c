@@ -133,6 +133,18 @@ shift_addition_data_t decimating_shift_addition_init(float rate, int decimation)
     return shift_addition_init(rate * decimation);
 }
 
+/* ---- shift_table quarter-wave sine table (libcsdr.c:210-222) ------------------------------------------------------------------ */
+shift_table_data_t shift_table_init(int table_size)
+{
+    shift_table_data_t d;
+    d.table_size = table_size;
+    d.table = (float *)malloc(sizeof(float) * (size_t)(table_size > 0 ? table_size : 1));
+    for (int i = 0; i < table_size; i++) d.table[i] = (float)sin((double)(((float)i / table_size) * (PI_F / 2)));
+    return d;
+}
+
+void shift_table_deinit(shift_table_data_t table_data) { free(table_data.table); }
+
 /* ---- shift_addfast steps (libcsdr.c:307-317): the phasor after 1..4 increments ---------------------------------- */
 shift_addfast_data_t shift_addfast_init(float rate)
 {

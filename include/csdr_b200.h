@@ -107,6 +107,12 @@ shift_unroll_data_t shift_unroll_init(float rate, int size);
 float shift_unroll_cc(complexf *input, complexf *output, int input_size, shift_unroll_data_t *d, float starting_phase);
 /* shift_math (libcsdr.h:171; libcsdr.c:186-209): cos/sin of a float phase advanced by one rounded addition per sample, wrapped to [0, 2*PI] */
 float shift_math_cc(complexf *input, complexf *output, int input_size, float rate, float starting_phase);
+/* shift_table (libcsdr.h:180-186; libcsdr.c:210-260): cos/sin from a quarter-wave table (host memory, made by shift_table_init).  Index
+ * arithmetic as the reference's own build executes it; an index the source would read outside the table is clamped. */
+typedef struct shift_table_data_s { float *table; int table_size; } shift_table_data_t;
+shift_table_data_t shift_table_init(int table_size);
+void  shift_table_deinit(shift_table_data_t table_data);
+float shift_table_cc(complexf *input, complexf *output, int input_size, float rate, shift_table_data_t table_data, float starting_phase);
 /* shift_addfast (libcsdr.h:189-197; libcsdr.c:307-317, 396-433): recursion advanced once per four samples; only input_size/4*4
  * samples of `output` are written, like the reference */
 typedef struct shift_addfast_data_s { float dsin[4]; float dcos[4]; float phase_increment; } shift_addfast_data_t;
@@ -261,6 +267,10 @@ int csdrb_log_ff(const float *d_in, float *d_out, long n, float add_db, void *st
 size_t csdrb_shift_math_bank_scratch_bytes(int channels, int input_size);
 int csdrb_shift_math_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
                              const float *d_rates, float *d_phase_io, void *d_scratch, size_t scratch_bytes, void *stream);
+/* shift_table_cc bank: like the shift_math bank plus the quarter-wave table in DEVICE memory (d_table, table_size floats) */
+int csdrb_shift_table_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,
+                              const float *d_rates, float *d_phase_io, const float *d_table, int table_size, void *d_scratch, size_t scratch_bytes,
+                              void *stream);
 /* shift_addfast_cc bank: d_params[c] = shift_addfast_init(rate_c); one reference call per `chunk` samples (csdr.c:781-791 uses 1024);
  * scratch as for the shift_addition bank (csdrb_shift_addition_bank_scratch_bytes) */
 int csdrb_shift_addfast_bank_cc(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int channels, int input_size,

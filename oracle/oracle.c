@@ -441,6 +441,51 @@ float oracle_shift_math_cc(const ocf32 *in, ocf32 *out, int n, float rate, float
     return phase;
 }
 
+/* [ref libcsdr.c:210-216] quarter-wave sine table: table[i] = sin((i/size) * PI/2), the quotient and product in float, sin in double */
+void oracle_shift_table_init(float *table, int size)
+{
+    for (int i = 0; i < size; i++) table[i] = (float)sin((double)(((float)i / size) * (kPi / 2)));
+}
+
+/* [ref libcsdr.c:223-260] shift_table_cc AS THE REFERENCE'S OWN BUILD EXECUTES IT.  The source divides by PI/2 twice; under the Makefile's
+ * -ffast-math gcc turns both divisions into multiplications by float constants (objdump of oracle/_ref: mulss by 0x3f22f983 = fl(1/fl(PI/2)),
+ * and by fl((float)table_size * that)), and a table index moves the result by 2.4e-5 rad, so the shipped arithmetic is the only thing
+ * worth pinning: quadrant = trunc(phase * K), vphase = phase - (float)quadrant * fl(PI/2), index = trunc(vphase * fl(size * K)).
+ * The source reads table[size] / table[-1] when rounding pushes an index out of range (it is marked "RTODO"); such samples are reported
+ * through *out_of_range (count) and computed with the index clamped, which is what the product does. */
+float oracle_shift_table_cc(const ocf32 *in, ocf32 *out, int n, float rate, const float *table, int table_size, float starting_phase, int *out_of_range)
+{
+    const float K = 0.6366197466850281f;                                /* 0x3f22f983 */
+    const float half_pi = kPi / 2;                                       /* 0x3fc90fdb */
+    const float K2 = (float)table_size * K;
+    float phase = starting_phase;
+    const float inc = (rate * 2) * kPi;
+    int bad = 0;
+    for (int k = 0; k < n; k++) {
+        const float qf = phase * K;
+        const int quadrant = (int)qf;
+        const float whole = (float)quadrant * half_pi;
+        const float vphase = phase - whole;
+        int sin_index = (int)(vphase * K2);
+        int cos_index = table_size - 1 - sin_index;
+        if (quadrant & 1) { int t = sin_index; sin_index = cos_index; cos_index = t; }
+        if (sin_index < 0 || sin_index >= table_size || cos_index < 0 || cos_index >= table_size) {
+            bad++;
+            if (sin_index < 0) sin_index = 0; else if (sin_index >= table_size) sin_index = table_size - 1;
+            if (cos_index < 0) cos_index = 0; else if (cos_index >= table_size) cos_index = table_size - 1;
+        }
+        const float sinval = (quadrant > 1 ? -1.0f : 1.0f) * table[sin_index];
+        const float cosval = ((quadrant && quadrant < 3) ? -1.0f : 1.0f) * table[cos_index];
+        out[k].i = cosval * in[k].i - sinval * in[k].q;
+        out[k].q = sinval * in[k].i + cosval * in[k].q;
+        phase += inc;
+        while (phase > 2 * kPi) phase -= 2 * kPi;
+        while (phase < 0) phase += 2 * kPi;
+    }
+    if (out_of_range) *out_of_range = bad;
+    return phase;
+}
+
 /* [ref libcsdr.c:307-317] shift_addfast_init: the phasor after 1..4 steps of phase_increment = 2*rate*PI (float), each angle a float
  * product, sin/cos in double rounded to float.  out9 = dsin[4], dcos[4], phase_increment (libcsdr.h:189-194 member order). */
 void oracle_shift_addfast_init(float rate, float *out9)

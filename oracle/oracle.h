@@ -87,6 +87,9 @@ float oracle_shift_unroll_cc(const ocf32 *in, ocf32 *out, int n, const float *ds
 
 /* shift_math: libcsdr.c:186-209 */
 float oracle_shift_math_cc(const ocf32 *in, ocf32 *out, int n, float rate, float starting_phase);
+/* shift_table: libcsdr.c:210-260, pinned to the arithmetic of the reference's -ffast-math build (see oracle.c) */
+void  oracle_shift_table_init(float *table, int size);
+float oracle_shift_table_cc(const ocf32 *in, ocf32 *out, int n, float rate, const float *table, int table_size, float starting_phase, int *out_of_range);
 /* shift_addfast: libcsdr.h:189-197, libcsdr.c:307-317, 396-433.  d9 = dsin[4], dcos[4], phase_increment */
 void  oracle_shift_addfast_init(float rate, float *d9);
 float oracle_shift_addfast_cc(const ocf32 *in, ocf32 *out, int n, const float *d9, float starting_phase);

@@ -113,6 +113,9 @@ class Oracle:
         L.oracle_shift_unroll_cc.restype = C.c_float
         L.oracle_encode_ima_adpcm_i16_u8.argtypes = [C.POINTER(C.c_short), C.POINTER(C.c_ubyte), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.oracle_compress_fft_adpcm_f_u8.argtypes = [fp, C.POINTER(C.c_ubyte), C.c_int]
+        L.oracle_shift_table_init.argtypes = [fp, C.c_int]
+        L.oracle_shift_table_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, fp, C.c_int, C.c_float, C.POINTER(C.c_int)]
+        L.oracle_shift_table_cc.restype = C.c_float
         L.oracle_shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.oracle_shift_math_cc.restype = C.c_float
         L.oracle_shift_addfast_init.argtypes = [C.c_float, fp]
         L.oracle_shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, fp, C.c_float]; L.oracle_shift_addfast_cc.restype = C.c_float
@@ -262,6 +265,17 @@ class Oracle:
             self.L.oracle_compress_fft_adpcm_f_u8(_p(x[r], C.c_float), _p(y[r], C.c_ubyte), fft_size)
         return y
 
+    def shift_table_init(self, size=65536):
+        t = np.empty(size, np.float32); self.L.oracle_shift_table_init(_p(t, C.c_float), size); return t
+
+    def shift_table_cc(self, x, rate, table, phase=0.0, chunk=None):
+        """returns (y, phase, number of samples whose table index left the table in the reference's arithmetic)"""
+        x = _c64(x); y = np.empty_like(x); table = np.ascontiguousarray(table, np.float32); chunk = chunk or max(x.size, 1); bad = 0
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0); b = C.c_int(0)
+            phase = self.L.oracle_shift_table_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, rate, _p(table, C.c_float), table.size, phase, C.byref(b)); bad += b.value
+        return y, float(np.float32(phase)), bad
+
     def shift_math_cc(self, x, rate, phase=0.0, chunk=None):
         """one call per `chunk` samples (the CLI uses its 1024-sample buffer, csdr.c:703-718); the phase chain does not depend on the cut"""
         x = _c64(x); y = np.empty_like(x); chunk = chunk or max(x.size, 1)
@@ -385,6 +399,9 @@ class Ref:
     class _Unroll(C.Structure):             # libcsdr.h:199-205
         _fields_ = [("dsin", C.POINTER(C.c_float)), ("dcos", C.POINTER(C.c_float)), ("phase_increment", C.c_float), ("size", C.c_int)]
 
+    class _Table(C.Structure):              # libcsdr.h:180-184
+        _fields_ = [("table", C.POINTER(C.c_float)), ("table_size", C.c_int)]
+
     class _Ima(C.Structure):                # ima_adpcm.h:35-38
         _fields_ = [("index", C.c_int), ("previousValue", C.c_int)]
 
@@ -434,6 +451,8 @@ class Ref:
         L.shift_unroll_init.argtypes = [C.c_float, C.c_int]; L.shift_unroll_init.restype = self._Unroll
         L.shift_unroll_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._Unroll), C.c_float]; L.shift_unroll_cc.restype = C.c_float
         L.shift_math_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, C.c_float]; L.shift_math_cc.restype = C.c_float
+        L.shift_table_init.argtypes = [C.c_int]; L.shift_table_init.restype = self._Table
+        L.shift_table_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.c_float, self._Table, C.c_float]; L.shift_table_cc.restype = C.c_float
         L.encode_ima_adpcm_i16_u8.argtypes = [C.POINTER(C.c_short), C.POINTER(C.c_ubyte), C.c_int, self._Ima]; L.encode_ima_adpcm_i16_u8.restype = self._Ima
         L.shift_addfast_init.argtypes = [C.c_float]; L.shift_addfast_init.restype = self._AddFast
         L.shift_addfast_cc.argtypes = [C.POINTER(_CF), C.POINTER(_CF), C.c_int, C.POINTER(self._AddFast), C.c_float]; L.shift_addfast_cc.restype = C.c_float
@@ -574,6 +593,17 @@ class Ref:
         for s0 in range(0, x.size, size):
             n = min(size, x.size - s0)
             phase = self.L.shift_unroll_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, C.byref(d), phase)
+        return y, float(np.float32(phase))
+
+    def shift_table_init(self, size=65536):
+        d = self.L.shift_table_init(size); return np.ctypeslib.as_array(d.table, shape=(size,)).copy()
+
+    def shift_table_cc(self, x, rate, table, phase=0.0, chunk=None):
+        x = _c64(x); y = np.empty_like(x); table = np.ascontiguousarray(table, np.float32); chunk = chunk or max(x.size, 1)
+        d = self._Table(_p(table, C.c_float), table.size)
+        for s0 in range(0, x.size, chunk):
+            n = min(chunk, x.size - s0)
+            phase = self.L.shift_table_cc(_p(x[s0:], _CF), _p(y[s0:], _CF), n, rate, d, phase)
         return y, float(np.float32(phase))
 
     def encode_ima_adpcm_i16_u8(self, x, index=0, previous=0):

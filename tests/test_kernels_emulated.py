@@ -246,6 +246,22 @@ def test_shift_math_bank(shift, oracle, n):
         assert rel_rms(out[c], want) < 1e-7, c
 
 
+@pytest.mark.parametrize("n,size", [(257, 65536), (10_001, 65536), (20_000, 1024), (5_000, 100)])
+def test_shift_table_bank_bit_exact(shift, oracle, n, size):
+    """the table-lookup mixer: same phase chain as shift_math_cc, index arithmetic of the reference BUILD (reciprocal multiplies) -> identical samples"""
+    rng = np.random.default_rng(n + size)
+    rates = np.array([-0.5, -0.31, -0.085, 0.0, 1e-4, 0.2, 0.4999, 0.5], np.float32); ch = rates.size
+    x = _cplx(rng, n); table = oracle.shift_table_init(size)
+    ph0 = np.array([0.0, 3.0, 1.5707964, 6.2831855, 0.5, 1.0, 2.0, 4.7], np.float32); ph = ph0.copy()
+    out = Z((ch, n), np.complex64)
+    sb = shift.emul_shift_math_scratch_bytes(ch, n); scratch = Z(sb + 16, np.uint8)
+    assert shift.emul_launch_shift_table_bank(P(x), 0, P(out), n, ch, n, P(rates), P(ph), P(table), size, P(scratch), sb) >= 0, shift.emul_last_error()
+    for c, r in enumerate(rates):
+        want, wph, _bad = oracle.shift_table_cc(x, float(r), table, float(ph0[c]))
+        assert np.float32(wph).view(np.uint32) == ph[c].view(np.uint32), c
+        assert np.array_equal(out[c], want), (c, int(np.sum(out[c] != want)))
+
+
 # ------------------------------------------------------------------------------------------------------------------ K5 / K6 / audio tail
 @pytest.mark.parametrize("rate,points,n", [(5.0, 12, 20_000), (1.25, 12, 9_000), (2.5, 4, 5_001), (7.123, 16, 30_000)])
 def test_k5_fractional_decimator_bit_exact(audio, oracle, rate, points, n):

@@ -152,6 +152,22 @@ def test_golden_and_ref_shift_addfast(oracle):
         assert rel_rms(a, b) < 1e-6 and pa == pb and np.all(a[1020:1022] == 0) and np.all(b[1020:1022] == 0)
 
 
+def test_ref_shift_table_bit_exact(oracle):
+    """8(f) rank 3: with the reference's own table, the oracle's restatement of the BUILD's index arithmetic gives identical samples and phases"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from oracle.pyoracle import Ref
+    r = Ref()
+    x = (np.random.default_rng(1).standard_normal(60_000) + 1j * np.random.default_rng(2).standard_normal(60_000)).astype(np.complex64)
+    assert np.abs(r.shift_table_init(65536) - oracle.shift_table_init(65536)).max() <= 1.2e-7        # the build's sin() is libmvec's: an ulp here and there
+    for size in (65536, 1024, 100):
+        t = r.shift_table_init(size)
+        for rate in (-0.5, -0.31, -0.085, 0.0, 1e-4, 0.2, 0.25, 0.4999, 0.5):
+            for ph0 in (0.0, 3.0, 1.5707964, 6.2831855):
+                a, pa, _bad = oracle.shift_table_cc(x, rate, t, ph0); b, pb = r.shift_table_cc(x, rate, t, ph0)
+                assert np.array_equal(a, b) and np.float32(pa) == np.float32(pb), (size, rate, ph0)
+
+
 def test_golden_and_ref_shift_math(oracle):
     y, ph = oracle.shift_math_cc(GOLD["shift_in"], -0.085, -7.5, 1024)
     assert np.float32(ph) == GOLD["math_phase"] and rel_rms(y, GOLD["math_out"]) < TIGHT     # phase chain bit-exact; seeds: sincosf in the build

@@ -68,6 +68,17 @@ def test_shift_math_any_rate(oracle, ref, seed, n, rate, phase):
 
 
 @settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), phase=st.floats(0.0, 6.28125, width=32),
+       size=st.sampled_from([64, 1000, 65536]))
+def test_shift_table_any_rate(oracle, ref, seed, n, rate, phase, size):
+    x = _cplx(seed, n); table = ref.shift_table_init(size)
+    (a, pa, bad), (b, pb) = oracle.shift_table_cc(x, rate, table, phase), ref.shift_table_cc(x, rate, table, phase)
+    assert np.float32(pa) == np.float32(pb)
+    if bad == 0:                                                                    # an index outside the table is undefined behaviour in the reference
+        assert np.array_equal(a, b)
+
+
+@settings(**COMMON)
 @given(seed=st.integers(0, 2 ** 31), n=st.integers(1, 20000), rate=st.floats(-0.5, 0.5, width=32), dec=st.integers(1, 40))
 def test_decimating_shift_any_rate(oracle, ref, seed, n, rate, dec):
     x = _cplx(seed, n)
