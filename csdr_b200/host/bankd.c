@@ -10,7 +10,7 @@
  * Per channel the sample stream is exactly the README graph's:
  *   convert_u8_f | shift_addition_cc r | fir_decimate_cc D bw W | fmdemod_quadri_cf [| limit_ff L | deemphasis_nfm_ff 48000 | fastagc_ff 1024 R | convert_f_s16]
  * as ONE continuous stream (the CLI's per-process block framing -- stale tail blocks at EOF, the zero block deemphasis_nfm_ff emits
- * first -- is process plumbing and is not reproduced; tests/test_gpu_zz_bankd.py compares against the oracle run over the whole stream).
+ * first -- is process plumbing and is not reproduced; tests/test_gpu_zzz_bankd.py compares against the oracle run over the whole stream).
  *
  * usage: csdr-bankd [--in -|HOST:PORT] [--u8|--f32] [--decimation D] [--bw TRANSITION_BW] [--window W] [--block SAMPLES]
  *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N]  RATE:SINK [RATE:SINK ...]

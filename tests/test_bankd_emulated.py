@@ -1,6 +1,6 @@
 """CPU tier: csdr-bankd (host/bankd.c) linked against the emulated library -- the daemon's streaming bookkeeping (tails of the wideband
 stream, the de-emphasis FIR's carried inputs, AGC block remainders), TCP ingest and TCP sink, checked against the oracle without a GPU.
-Same test bodies as tests/test_gpu_zz_bankd.py."""
+Same test bodies as tests/test_gpu_zzz_bankd.py."""
 import sys
 from pathlib import Path
 
@@ -12,7 +12,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 import emul_build  # noqa: E402
 
 pytest.importorskip("torch")
-import test_gpu_zz_bankd as g  # noqa: E402
+import test_gpu_zzz_bankd as g  # noqa: E402
 
 
 @pytest.fixture(scope="module")
