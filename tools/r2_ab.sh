@@ -14,6 +14,7 @@ for staged in 0 1; do
 done
 # config 5 with the radix-16 overlap-add kernel (4096 = 16^3: 8 barriers and 4R+4W shared accesses per block instead of 12 / 6R+6W, round 1: 20 / 11R+11W)
 CSDRB_FFT_RADIX16=1 python tools/bench_configs.py c3 c5 2>&1 | tee gpurun_out/r2_ab_configs_radix16.txt | tail -10
-python tools/bench_configs.py k 2>&1 | grep -i "fft\|K7" | tee gpurun_out/r2_ab_fft.txt
+python tools/bench_configs.py k 2>&1 | tee gpurun_out/r2_ab_kernels.txt | tail -20        # K2 (staged row loads on this branch), K7 FFT sizes, ...
 CSDRB_FFT_RADIX16=1 python tools/bench_configs.py k 2>&1 | grep -i "fft\|K7" | tee gpurun_out/r2_ab_fft_radix16.txt
+# compare gpurun_out/r2_ab_kernels.txt with profiles/r01_configs_latest.txt (main, round 1) for the K2 / de-emphasis / FFT lines
 timeout 120 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py 2>&1 | tail -3 | tee gpurun_out/r2_ab_memcheck.log
