@@ -253,7 +253,13 @@ deemphasis_wfm_bank_kernel(const float* __restrict__ in, long in_stride, float* 
     if (y != y) y = 0.f;                                               // NaN carry restarts from 0 (libcsdr.c:1092)
     for (int t0 = 0; t0 < n; t0 += 32) {
         const int len = min(32, n - t0);
-        for (int r = 0; r < rows; r++) tile[r * 33 + lane] = lane < len ? in[(long)(c0 + r) * in_stride + t0 + lane] : 0.f;
+        for (int r0 = 0; r0 < rows; r0 += 8) {                       // eight rows' loads in flight before the first shared store
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = (r0 + u < rows && lane < len) ? in[(long)(c0 + r0 + u) * in_stride + t0 + lane] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (r0 + u < rows) tile[(r0 + u) * 33 + lane] = v[u];
+        }
         __syncwarp();
         if (live) {
             float* row = tile + lane * 33;

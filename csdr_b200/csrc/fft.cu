@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -41,6 +42,40 @@ int get_twiddles(int n, const float2** out, cudaStream_t st)
     return 0;
 }
 
+static std::map<int, float2*> g_tw16;
+int get_twiddles16(int n, const float2** out, cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw16.find(n);
+    if (it != g_tw16.end()) { *out = it->second; return 0; }
+    std::vector<float2> h((size_t)4 * n);
+    fft16_fill_twiddles(n, h.data());
+    float2* d = nullptr;
+    CSDRB_CUDA(cudaMalloc(&d, sizeof(float2) * h.size()));
+    CSDRB_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(float2) * h.size(), cudaMemcpyHostToDevice, st));
+    CSDRB_CUDA(cudaStreamSynchronize(st));
+    g_tw16[n] = d;
+    *out = d;
+    return 0;
+}
+
+template <int N>
+static int launch_c2c16_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw16, cudaStream_t st)
+{
+    const size_t smem = sizeof(float2) * fft_smem_elems(N);
+    if (inverse) {
+        auto k = fft_c2c_batch16_kernel<N, true>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft16_threads(N), smem, st>>>(in, is, out, os, tw16);
+    } else {
+        auto k = fft_c2c_batch16_kernel<N, false>;
+        if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<batch, fft16_threads(N), smem, st>>>(in, is, out, os, tw16);
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // ---- K7: batched c2c -------------------------------------------------------------------------------
 template <int N>
 static int launch_c2c_n(const float2* in, long is, float2* out, long os, int batch, bool inverse, const float2* tw, cudaStream_t st)
@@ -65,6 +100,16 @@ int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long
 {
     if (batch <= 0) return 0;
     if (n < 2 || n > FFT_MAX_N || (n & (n - 1))) { set_error("fft: size %d unsupported (power of two, 2..%d)", n, FFT_MAX_N); return -1; }
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    if (radix16 && n >= 32) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(n, &tw16, st)) return rc;
+        switch (n) {
+#define X(N) case N: if constexpr (N >= 32) return launch_c2c16_n<N>(d_in, in_stride, d_out, out_stride, batch, inverse != 0, tw16, st); break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+    }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(n, &tw, st)) return rc;
     switch (n) {
@@ -91,6 +136,35 @@ int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long o
         if (blocks_per_cta < 16) blocks_per_cta = nblocks < 16 ? nblocks : 16;
     }
     const dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, channels);
+    static const bool staged = getenv("CSDRB_OLAFIR_STAGED") != nullptr;            // A/B switch: the r01 kernel with staged copies
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT: radix-16 passes for 16^k sizes (256, 4096)
+    if (radix16 && !staged && (fft_size == 256 || fft_size == 4096)) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
+        const size_t fsmem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + 2 * (size_t)(fft_size - input_size));
+        if (fft_size == 256) {
+            auto k = olafir_bank_fused16_kernel<256>;
+            k<<<grid, fft16_threads(256), fsmem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw16);
+        } else {
+            auto k = olafir_bank_fused16_kernel<4096>;
+            if (fsmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<grid, fft16_threads(4096), fsmem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw16);
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        return 1;
+    }
+    if (fft_size >= 16 && !staged) {
+        const size_t fsmem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + 2 * (size_t)(fft_size - input_size));
+        switch (fft_size) {
+#define X(N) case N: if constexpr (N >= 16 && N <= 8192) { auto k = olafir_bank_fused_kernel<N>; \
+            if (fsmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+            k<<<grid, fft_threads(N), fsmem, st>>>(d_in, in_stride, d_out, out_stride, d_taps_fft, taps_stride, d_tail_io, input_size, nblocks, blocks_per_cta, tw); } break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        return 1;
+    }
     const size_t smem = sizeof(float2) * ((size_t)fft_smem_elems(fft_size) + (size_t)fft_size);
     switch (fft_size) {
 #define X(N) case N: if constexpr (N >= 4 && N <= 8192) { auto k = olafir_bank_kernel<N>; \
@@ -108,6 +182,27 @@ int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_
 {
     if (nblocks <= 0) return 0;
     if (fft_size < 4 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("fastddc_fwd: fft_size %d unsupported", fft_size); return -1; }
+    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    if (radix16 && fft_size >= 32) {
+        const float2* tw16 = nullptr;
+        if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
+        const size_t smem16 = sizeof(float2) * (size_t)fft_smem_elems(fft_size);
+        switch (fft_size) {
+#define X(N) case N: if constexpr (N >= 32) { auto k = fastddc_fwd16_kernel<N>; \
+            if (smem16 > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16)); \
+            k<<<nblocks, fft16_threads(N), smem16, st>>>(d_in, d_spectra, d_overlap_io, input_size, tw16); } break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        const int ov16 = fft_size - input_size;
+        if (ov16 > 0) {
+            fastddc_carry_overlap_kernel<<<1, 1024, 0, st>>>(d_in, d_overlap_io, ov16, (long)nblocks * input_size);
+            CSDRB_CUDA(cudaGetLastError());
+            return 2;
+        }
+        return 1;
+    }
     const float2* tw = nullptr;
     if (int rc = get_twiddles(fft_size, &tw, st)) return rc;
     const size_t smem = sizeof(float2) * (size_t)fft_smem_elems(fft_size);
@@ -171,14 +266,25 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {
-        constexpr int CT = 4, BT = 4;
-        const dim3 tgrid((nblocks + BT - 1) / BT, (channels + CT - 1) / CT);
-        const size_t smem = sizeof(float2) * (size_t)CT * BT * fft_smem_elems(fft_inv_size);
+        // Tile = CT channels x BT blocks per CTA (each spectrum bin fetched once per CT channels, each tap once per BT blocks).  Big tiles
+        // save L2 traffic but a bank of 64 channels x 16 blocks is only 64 CTAs of 4x4 on 148 SMs (r01: the launch was latency-bound),
+        // so the tile shrinks until the grid covers the machine about twice.  CSDRB_INV_TILE=44|22 forces one for A/B runs.
+        static const char* forced = getenv("CSDRB_INV_TILE");
+        const long ctas44 = (long)((nblocks + 3) / 4) * ((channels + 3) / 4);
+        const bool small_tile = forced ? (forced[0] == '2') : (ctas44 < 2 * 148);
+        const int CTv = small_tile ? 2 : 4, BTv = small_tile ? 2 : 4;
+        const dim3 tgrid((nblocks + BTv - 1) / BTv, (channels + CTv - 1) / CTv);
+        const size_t smem = sizeof(float2) * (size_t)CTv * BTv * fft_smem_elems(fft_inv_size);
         switch (fft_inv_size) {
-#define X(M) case M: if constexpr (M >= 8 && M <= 1024) { auto k = fastddc_inv_tiled_kernel<M, CT, BT>; \
-            if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
-                                       fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
+#define X(M) case M: if constexpr (M >= 8 && M <= 1024) { \
+            if (small_tile) { auto k = fastddc_inv_tiled_kernel<M, 2, 2>; \
+                if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                           fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } \
+            else { auto k = fastddc_inv_tiled_kernel<M, 4, 4>; \
+                if (smem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                k<<<tgrid, 256, smem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                           fft_size, pre_decimation, scrap, post_input_size, post_decimation, nblocks, channels, tw); } } break;
             CSDRB_FFT_SIZES(X)
 #undef X
         }

@@ -181,6 +181,152 @@ __device__ __forceinline__ void block_fft(float2* __restrict__ s, const float2* 
     else fft_r8_passes<N, NT, 1, INV>(s, tw, tid);
 }
 
+// ---- transform with fused input / output -----------------------------------------------------------------------------------------
+// The first pass needs no twiddles and reads element j + r*N/R: it can take its inputs straight from the caller (global memory, a
+// zero-padded block, a product of two spectra ...) instead of from a staged copy, and the last pass (NS*8 == N) produces element
+// j + r*N/8 per thread, which can go straight to the caller as well.  That removes one shared-memory write + read + barrier at each
+// end of a transform (5R+5W -> 3R+3W shared accesses per point for a 4-pass size).  When first and last pass have the same radix
+// (log2 N divisible by 3: 8, 64, 512, 4096) a thread's last-pass outputs are exactly its first-pass inputs of the next transform of
+// the same size, so FFT -> pointwise product -> IFFT can hand over in registers (block_fft_chain below).
+//
+// IO concept (i = natural element index 0..N-1):  float2 load(int i);  float4 load2(int i)  = elements (i, i+1), i even;
+//                                                  void store(int i, float2 v);  void store2(int i, float2 a, float2 b), i even.
+// Barrier contract: nobody may still be reading `s` when a FIRST pass is entered (a LAST pass ends its reads with a barrier, so
+// back-to-back transforms on the same buffer are safe); after a LAST pass the buffer is free.
+template <int N, int NT, int R, bool INV, typename In>
+__device__ __forceinline__ void fft_pass_first(float2* __restrict__ s, int tid, In& in)
+{
+    constexpr int NB = N / R;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    constexpr bool PAIRED = (PER % 2 == 0) && (NB % (NT * PER) == 0);
+    float2 v[PER][R];
+    if constexpr (PAIRED) {
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float4 two = in.load2(j + r * NB);                // elements (i, i+1), i even
+                v[b][r] = make_float2(two.x, two.y); v[b + 1][r] = make_float2(two.z, two.w);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < PER; b++) dft_small<R, INV>(v[b]);
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;                                // the two butterflies write 2R consecutive elements
+#pragma unroll
+            for (int r = 0; r < R; r += 2) {
+                *reinterpret_cast<float4*>(s + fft_pad(j * R + r)) = make_float4(v[b][r].x, v[b][r].y, v[b][r + 1].x, v[b][r + 1].y);
+                *reinterpret_cast<float4*>(s + fft_pad((j + 1) * R + r)) = make_float4(v[b + 1][r].x, v[b + 1][r].y, v[b + 1][r + 1].x, v[b + 1][r + 1].y);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = in.load(j + r * NB);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+                dft_small<R, INV>(v[b]);
+#pragma unroll
+                for (int r = 0; r < R; r++) s[fft_pad(j * R + r)] = v[b][r];
+            }
+        }
+    }
+    __syncthreads();                                                    // writes visible to the next pass
+}
+
+// last pass: radix 8 over sub-transforms of size NS = N/8, so butterfly j (< N/8) produces elements j + r*N/8
+template <int N, int NT, bool INV, typename Out>
+__device__ __forceinline__ void fft_pass_last(float2* __restrict__ s, const float2* __restrict__ tw, int tid, Out& out)
+{
+    constexpr int R = 8, NB = N / 8, NS = N / 8;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    constexpr bool PAIRED = (PER % 2 == 0) && (NB % (NT * PER) == 0);
+    float2 v[PER][R];
+    if constexpr (PAIRED) {
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float4 two = *reinterpret_cast<const float4*>(s + fft_pad(j + r * NB));
+                v[b][r] = make_float2(two.x, two.y); v[b + 1][r] = make_float2(two.z, two.w);
+            }
+            fft_butterfly<N, R, NS, INV>(v[b], j, tw);
+            fft_butterfly<N, R, NS, INV>(v[b + 1], j + 1, tw);
+        }
+        __syncthreads();                                                // every read of s has happened: the buffer is free again
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r++) out.store2(j + r * NS, v[b][r], v[b + 1][r]);     // elements (i, i+1), i even
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
+                fft_butterfly<N, R, NS, INV>(v[b], j, tw);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) out.store(j + r * NS, v[b][r]);
+            }
+        }
+    }
+}
+
+template <int N, int NT, int NS, bool INV>
+__device__ __forceinline__ void fft_r8_middle_passes(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
+{
+    if constexpr (NS * 8 < N) {                                         // stop before the last pass
+        fft_pass<N, NT, 8, NS, INV>(s, tw, tid);
+        fft_r8_middle_passes<N, NT, NS * 8, INV>(s, tw, tid);
+    }
+}
+
+constexpr int fft_first_radix(int n) { return ilog2_c(n) % 3 == 1 ? 2 : (ilog2_c(n) % 3 == 2 ? 4 : 8); }
+
+// N-point transform in.load(i) -> out.store(i); `s` (fft_smem_elems(N) slots) is scratch only.  All NT threads must call.
+template <int N, int NT, bool INV, typename In, typename Out>
+__device__ __forceinline__ void block_fft_io(float2* __restrict__ s, const float2* __restrict__ tw, int tid, In& in, Out& out)
+{
+    static_assert((N & (N - 1)) == 0 && N >= 2, "power of two sizes only");
+    constexpr int R0 = fft_first_radix(N);
+    if constexpr (R0 == N) {                                            // 2, 4, 8 points: one butterfly, no shared memory at all
+        if (tid == 0) {
+            float2 v[R0];
+#pragma unroll
+            for (int r = 0; r < R0; r++) v[r] = in.load(r);
+            dft_small<R0, INV>(v);
+#pragma unroll
+            for (int r = 0; r < R0; r++) out.store(r, v[r]);
+        }
+    } else {
+        fft_pass_first<N, NT, R0, INV>(s, tid, in);
+        fft_r8_middle_passes<N, NT, R0, INV>(s, tw, tid);
+        fft_pass_last<N, NT, INV>(s, tw, tid, out);
+    }
+}
+
 // Prologue copy global -> padded shared array.  All of a thread's loads are issued before the first store: the r01 source-level
 // profile had 58 % of the 4096-point kernel's stall samples on the first STS of a load-then-store loop (16 serial DRAM round trips).
 template <int N, int NT, typename Fetch>
@@ -204,6 +350,144 @@ __device__ __forceinline__ void fft_stage_in_vec(float2* __restrict__ s, int tid
 #pragma unroll
     for (int k = 0; k < PER; k++) *reinterpret_cast<float4*>(s + fft_pad(2 * (tid + k * NT))) = t[k];
 }
+
+// which butterflies the last pass (radix 8, N/8 butterflies) gives to thread `tid`: slot b -> butterfly index j
+template <int N, int NT> struct FftLastPass {
+    static constexpr int NB = N / 8;
+    static constexpr int PER = (NB + NT - 1) / NT;
+    static constexpr bool PAIRED = (PER % 2 == 0) && (NB % (NT * PER) == 0);
+    static constexpr bool GUARD = !(NB % NT == 0 || PAIRED);           // some slots fall beyond the transform
+    __device__ static __forceinline__ int j(int tid, int b) { return PAIRED ? tid * PER + b : tid + b * NT; }
+};
+
+// Last pass of a forward transform, a pointwise map, and the first pass of the inverse transform of the same size in one go, for
+// sizes whose first pass is radix 8 (8^k): the thread that finishes elements j + r*N/8 of the spectrum is the thread that needs them.
+//   map.at(b, r, i, v) -> the value of element i of the inverse transform's input (e.g. spectrum * taps_fft); (b, r) is the thread's
+//   compile-time slot of that element (butterfly b, leg r: i = fft_last_pass_j(tid, b) + r*N/8), so a map can keep per-element data
+//   in registers; map.prefetch(b, r, i) is called for every slot before the pass starts so that those loads overlap the butterflies.
+//   map.any(i, v): the same without a slot (sizes that hand over through shared memory).
+template <int N, int NT, typename Map>
+__device__ __forceinline__ void fft_chain_fwd_last_inv_first(float2* __restrict__ s, const float2* __restrict__ tw, int tid, Map& map)
+{
+    static_assert(fft_first_radix(N) == 8 && N >= 64, "register hand-over needs radix 8 at both ends");
+    constexpr int R = 8, NB = N / 8, NS = N / 8;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    constexpr bool PAIRED = (PER % 2 == 0) && (NB % (NT * PER) == 0);
+    float2 v[PER][R];
+#pragma unroll
+    for (int b = 0; b < PER; b++) {                                     // let the map start fetching its per-element data (global/L2 latency
+        const int j = PAIRED ? tid * PER + b : tid + b * NT;            // hides behind the butterflies below)
+        if (NB % NT == 0 || PAIRED || j < NB) {
+#pragma unroll
+            for (int r = 0; r < R; r++) map.prefetch(b, r, j + r * NS);
+        }
+    }
+    if constexpr (PAIRED) {
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float4 two = *reinterpret_cast<const float4*>(s + fft_pad(j + r * NB));
+                v[b][r] = make_float2(two.x, two.y); v[b + 1][r] = make_float2(two.z, two.w);
+            }
+            fft_butterfly<N, R, NS, false>(v[b], j, tw);
+            fft_butterfly<N, R, NS, false>(v[b + 1], j + 1, tw);
+        }
+        __syncthreads();                                                // reads of s done
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r++) v[b][r] = map.at(b, r, j + r * NS, v[b][r]);    // b, r are compile-time after unrolling
+            dft8<true>(v[b]);                                           // inverse transform, first pass: inputs j + r*NB, no twiddles
+        }
+#pragma unroll
+        for (int b = 0; b < PER; b += 2) {
+            const int j = tid * PER + b;
+#pragma unroll
+            for (int r = 0; r < R; r += 2) {
+                *reinterpret_cast<float4*>(s + fft_pad(j * R + r)) = make_float4(v[b][r].x, v[b][r].y, v[b][r + 1].x, v[b][r + 1].y);
+                *reinterpret_cast<float4*>(s + fft_pad((j + 1) * R + r)) = make_float4(v[b + 1][r].x, v[b + 1][r].y, v[b + 1][r + 1].x, v[b + 1][r + 1].y);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
+                fft_butterfly<N, R, NS, false>(v[b], j, tw);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < PER; b++) {
+            const int j = tid + b * NT;
+            if (NB % NT == 0 || j < NB) {
+#pragma unroll
+                for (int r = 0; r < R; r++) v[b][r] = map.at(b, r, j + r * NS, v[b][r]);
+                dft8<true>(v[b]);
+#pragma unroll
+                for (int r = 0; r < R; r++) s[fft_pad(j * R + r)] = v[b][r];
+            }
+        }
+    }
+    __syncthreads();                                                    // first inverse pass visible
+}
+
+// FFT_N(in) -> map -> IFFT_N -> out (unnormalised), `s` is scratch.  Register hand-over in the middle when N is a power of 8.
+template <int N, int NT, typename In, typename Map, typename Out>
+__device__ __forceinline__ void block_fft_map_ifft(float2* __restrict__ s, const float2* __restrict__ tw, int tid, In& in, Map& map, Out& out)
+{
+    constexpr int R0 = fft_first_radix(N);
+    static_assert(N >= 16, "use two block_fft_io calls for tiny sizes");
+    fft_pass_first<N, NT, R0, false>(s, tid, in);
+    fft_r8_middle_passes<N, NT, R0, false>(s, tw, tid);
+    if constexpr (R0 == 8) {
+        fft_chain_fwd_last_inv_first<N, NT>(s, tw, tid, map);
+    } else {
+        struct ToShared {                                               // last forward pass writes map(spectrum) back into s ...
+            float2* s; Map& map;
+            __device__ __forceinline__ void store(int i, float2 v) const { s[fft_pad(i)] = map.any(i, v); }
+            __device__ __forceinline__ void store2(int i, float2 a, float2 b) const
+            {
+                const float2 ma = map.any(i, a), mb = map.any(i + 1, b);
+                *reinterpret_cast<float4*>(s + fft_pad(i)) = make_float4(ma.x, ma.y, mb.x, mb.y);
+            }
+        } mid{s, map};
+        fft_pass_last<N, NT, false>(s, tw, tid, mid);
+        __syncthreads();
+        fft_pass<N, NT, R0, 1, true>(s, tw, tid);                      // ... and the inverse starts from shared memory
+    }
+    fft_r8_middle_passes<N, NT, R0, true>(s, tw, tid);
+    fft_pass_last<N, NT, true>(s, tw, tid, out);
+}
+
+// dense global rows as transform input / output; 128-bit accesses when the row is 16-byte aligned
+struct FftRowIn {
+    const float2* x; bool vec;
+    __device__ __forceinline__ explicit FftRowIn(const float2* p) : x(p), vec((reinterpret_cast<uintptr_t>(p) & 15) == 0) {}
+    __device__ __forceinline__ float2 load(int i) const { return __ldg(x + i); }
+    __device__ __forceinline__ float4 load2(int i) const
+    {
+        if (vec) return __ldg(reinterpret_cast<const float4*>(x + i));
+        const float2 a = __ldg(x + i), b = __ldg(x + i + 1);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+struct FftRowOut {
+    float2* y; bool vec;
+    __device__ __forceinline__ explicit FftRowOut(float2* p) : y(p), vec((reinterpret_cast<uintptr_t>(p) & 15) == 0) {}
+    __device__ __forceinline__ void store(int i, float2 v) const { y[i] = v; }
+    __device__ __forceinline__ void store2(int i, float2 a, float2 b) const
+    {
+        if (vec) *reinterpret_cast<float4*>(y + i) = make_float4(a.x, a.y, b.x, b.y);
+        else { y[i] = a; y[i + 1] = b; }
+    }
+};
 
 // host: the three twiddle planes (w^1, w^2, w^4) of an n-point transform, 3*n entries; a radix-8 pass over sub-size NS reads index
 // NS + k, k < NS.  Angles in double, rounded once to float.

@@ -3,6 +3,7 @@
 // __syncthreads() a real barrier) in the CPU test tier.  The product includes this file from fft.cu only.
 #pragma once
 #include "fft.cuh"
+#include "fft16.cuh"
 
 namespace csdrb {
 
@@ -16,13 +17,8 @@ fft_c2c_batch_kernel(const float2* __restrict__ in, long in_stride, float2* __re
     const int tid = threadIdx.x;
     const float2* x = in + (long)blockIdx.x * in_stride;
     float2* y = out + (long)blockIdx.x * out_stride;
-    if constexpr (N >= 2 * NT) {
-        if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) fft_stage_in_vec<N, NT>(s, tid, x);
-        else fft_stage_in<N, NT>(s, tid, [&](int i) { return x[i]; });
-    } else fft_stage_in<N, NT>(s, tid, [&](int i) { return x[i]; });
-    __syncthreads();
-    block_fft<N, NT, INV>(s, tw, tid);
-    for (int i = tid; i < N; i += NT) y[i] = s[fft_pad(i)];
+    FftRowIn src(x); FftRowOut dst(y);
+    block_fft_io<N, NT, INV>(s, tw, tid, src, dst);                    // first pass reads the row, last pass writes it: no staging copies
 }
 
 template <int N>
@@ -88,6 +84,137 @@ olafir_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __rest
     if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail[i];
 }
 
+// EXPERIMENT: the fused overlap-add kernel on radix-16 passes, sizes 16^k (config 5's 4096): 4R+4W shared accesses per point and block
+template <int N>
+__global__ void __launch_bounds__(fft16_threads(N), (N <= 4096 ? 2 : 1))
+olafir_bank_fused16_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                           const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                           int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft16_threads(N);
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    float2* tail_cur = s + fft_smem_elems(N);
+    float2* tail_next = tail_cur + overlap;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;      // see olafir_bank_kernel
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail_cur[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+    struct TapsMap16 {                                                  // spectrum * taps_fft, rounding sequence of libcsdr.c:827-828
+        const float2* H; float2 hh[16];
+        __device__ __forceinline__ void prefetch(int r, int i) { hh[r] = __ldg(H + i); }
+        __device__ __forceinline__ float2 at(int r, int, float2 a) const
+        {
+            const float2 h = hh[r];
+            return make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        }
+    } map;
+    map.H = H;
+    const float inv_n = 1.0f / (float)N;
+    for (int b = b_start; b < b_last; b++) {
+        struct BlockIn {
+            const float2* xb; int input_size;
+            __device__ __forceinline__ float2 load(int i) const { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }
+        } src{x + (long)b * input_size, input_size};
+        struct BlockOut {
+            float2* yb; const float2* tail_cur; float2* tail_next; int input_size, overlap; float inv_n; bool emit;
+            __device__ __forceinline__ void store(int i, float2 raw) const
+            {
+                float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
+                if (i < overlap) v = make_float2(__fadd_rn(v.x, tail_cur[i].x), __fadd_rn(v.y, tail_cur[i].y));
+                if (i < input_size) { if (emit) yb[i] = v; }
+                else tail_next[i - input_size] = v;
+            }
+        } dst{y + (long)b * input_size, tail_cur, tail_next, input_size, overlap, inv_n, b >= b_first};
+        block_fft16_map_ifft<N, NT>(s, tw16, tid, src, map, dst);
+        float2* t = tail_cur; tail_cur = tail_next; tail_next = t;
+    }
+    __syncthreads();
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail_cur[i];
+}
+
+// EXPERIMENT: the batched transform with radix-16 passes (fft16.cuh); tw16 = the four-plane table of fft16_fill_twiddles
+template <int N, bool INV>
+__global__ void __launch_bounds__(fft16_threads(N))
+fft_c2c_batch16_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    FftRowIn src(in + (long)blockIdx.x * in_stride); FftRowOut dst(out + (long)blockIdx.x * out_stride);
+    block_fft16_io<N, fft16_threads(N), INV>(s, tw16, threadIdx.x, src, dst);
+}
+
+// Same operation with the transforms' ends fused: the forward FFT's first pass reads the zero-padded block straight from global
+// memory, its last pass hands the spectrum x taps_fft product to the inverse FFT's first pass in registers (4096 = 8^4; other sizes go
+// through shared memory once), the inverse FFT's last pass scales, adds the carried tail and writes the result and the next tail.
+// taps_fft is fetched (L2) into registers while the last forward butterflies run, tails ping-pong between two shared arrays.
+template <int N>
+__global__ void __launch_bounds__(fft_threads(N), (N <= 4096 ? 2 : 1))
+olafir_bank_fused_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+                         const float2* __restrict__ taps_fft, long taps_stride, float2* __restrict__ tail_io /*[C][N]*/,
+                         int input_size, int nblocks, int blocks_per_cta, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NT = fft_threads(N);
+    using LP = FftLastPass<N, NT>;
+    const int tid = threadIdx.x, ch = blockIdx.y;
+    const int overlap = N - input_size;
+    float2* tail_cur = s + fft_smem_elems(N);
+    float2* tail_next = tail_cur + overlap;
+    const int b_first = blockIdx.x * blocks_per_cta;
+    if (b_first >= nblocks) return;
+    const int b_last = min(nblocks, b_first + blocks_per_cta);
+    const float2* x = in + (long)ch * in_stride;
+    float2* y = out + (long)ch * out_stride;
+    const float2* H = taps_fft + (long)ch * taps_stride;
+    const int lead = overlap > 0 ? (overlap + input_size - 1) / input_size : 0;      // see olafir_bank_kernel
+    const int b_start = b_first - lead > 0 ? b_first - lead : 0;
+    for (int i = tid; i < overlap; i += NT) tail_cur[i] = b_start == 0 ? tail_io[(long)ch * N + i] : make_float2(0.f, 0.f);
+
+    struct TapsMap {                                                    // spectrum * taps_fft, rounding sequence of libcsdr.c:827-828
+        const float2* H; float2 hh[LP::PER][8];
+        __device__ __forceinline__ static float2 mul(float2 a, float2 h)
+        {
+            return make_float2(__fsub_rn(__fmul_rn(a.x, h.x), __fmul_rn(a.y, h.y)), __fadd_rn(__fmul_rn(a.x, h.y), __fmul_rn(a.y, h.x)));
+        }
+        __device__ __forceinline__ void prefetch(int b, int r, int i) { hh[b][r] = __ldg(H + i); }
+        __device__ __forceinline__ float2 at(int b, int r, int, float2 v) const { return mul(v, hh[b][r]); }
+        __device__ __forceinline__ float2 any(int i, float2 v) const { return mul(v, __ldg(H + i)); }
+    } map;
+    map.H = H;
+    const float inv_n = 1.0f / (float)N;                               // N is a power of two: exact, same as /N
+    for (int b = b_start; b < b_last; b++) {
+        struct BlockIn {                                                // input_size samples followed by zeros (csdr.c:1872-1876)
+            const float2* xb; int input_size;
+            __device__ __forceinline__ float2 load(int i) const { return i < input_size ? __ldg(xb + i) : make_float2(0.f, 0.f); }
+            __device__ __forceinline__ float4 load2(int i) const { const float2 a = load(i), c = load(i + 1); return make_float4(a.x, a.y, c.x, c.y); }
+        } src{x + (long)b * input_size, input_size};
+        struct BlockOut {                                               // r[i] = ifft[i]/N + (i < overlap ? previous r[input_size + i] : 0)
+            float2* yb; const float2* tail_cur; float2* tail_next; int input_size, overlap; float inv_n; bool emit;
+            __device__ __forceinline__ void store(int i, float2 raw) const
+            {
+                float2 v = make_float2(raw.x * inv_n, raw.y * inv_n);
+                if (i < overlap) v = make_float2(__fadd_rn(v.x, tail_cur[i].x), __fadd_rn(v.y, tail_cur[i].y));
+                if (i < input_size) { if (emit) yb[i] = v; }
+                else tail_next[i - input_size] = v;
+            }
+            __device__ __forceinline__ void store2(int i, float2 a, float2 c) const { store(i, a); store(i + 1, c); }
+        } dst{y + (long)b * input_size, tail_cur, tail_next, input_size, overlap, inv_n, b >= b_first};
+        block_fft_map_ifft<N, NT>(s, tw, tid, src, map, dst);
+        float2* t = tail_cur; tail_cur = tail_next; tail_next = t;       // the next block's first read of its tail is three barriers away
+    }
+    __syncthreads();
+    if (b_last == nblocks) for (int i = tid; i < overlap; i += NT) tail_io[(long)ch * N + i] = tail_cur[i];
+}
+
 template <int N>
 __global__ void __launch_bounds__(fft_threads(N))
 fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, const float2* __restrict__ overlap_in,
@@ -100,11 +227,32 @@ fastddc_fwd_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, 
     const int overlap = N - input_size;
     // block b transforms stream samples [b*input_size - overlap, (b+1)*input_size); negative positions come from the carried overlap
     const long start = (long)b * input_size - overlap;
-    fft_stage_in<N, NT>(s, tid, [&](int i) { const long p = start + i; return p >= 0 ? __ldg(in + p) : overlap_in[overlap + p]; });
-    __syncthreads();
-    block_fft<N, NT, false>(s, tw, tid);
-    float2* y = spectra + (long)b * N;
-    for (int i = tid; i < N; i += NT) y[i] = s[fft_pad(i)];
+    struct SlideIn {                                                    // stream position start + i; before the stream: the carried overlap
+        const float2* in; const float2* ov; long start; int overlap;
+        __device__ __forceinline__ float2 load(int i) const { const long p = start + i; return p >= 0 ? __ldg(in + p) : ov[overlap + p]; }
+        __device__ __forceinline__ float4 load2(int i) const { const float2 a = load(i), b = load(i + 1); return make_float4(a.x, a.y, b.x, b.y); }
+    } src{in, overlap_in, start, overlap};
+    FftRowOut dst(spectra + (long)b * N);
+    block_fft_io<N, NT, false>(s, tw, tid, src, dst);
+}
+
+// EXPERIMENT: the same forward step on radix-16 passes (16384 = 4*16^3: four passes instead of five)
+template <int N>
+__global__ void __launch_bounds__(fft16_threads(N))
+fastddc_fwd16_kernel(const float2* __restrict__ in, float2* __restrict__ spectra, const float2* __restrict__ overlap_in,
+                     int input_size, const float2* __restrict__ tw16)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    const int b = blockIdx.x;
+    const int overlap = N - input_size;
+    const long start = (long)b * input_size - overlap;
+    struct SlideIn {
+        const float2* in; const float2* ov; long start; int overlap;
+        __device__ __forceinline__ float2 load(int i) const { const long p = start + i; return p >= 0 ? __ldg(in + p) : ov[overlap + p]; }
+    } src{in, overlap_in, start, overlap};
+    FftRowOut dst(spectra + (long)b * N);
+    block_fft16_io<N, fft16_threads(N), false>(s, tw16, threadIdx.x, src, dst);
 }
 
 __global__ void __launch_bounds__(1024)

@@ -48,6 +48,24 @@ __global__ void shift_phase_chain_kernel(const float3* __restrict__ params, floa
 }
 
 constexpr int SH_TILE = 32;                       // samples per lane per sub-step
+
+// Load `rows` rows of 32 consecutive samples into the padded tile: row r covers stream positions (k0 + r)*seg + t0 .. +31 (zeros past the row's
+// length).  Eight rows' loads are issued before the first shared store -- a load-then-store loop serialises one DRAM/L2 round trip per row
+// (the r01 FFT profile showed exactly that pattern costing 58 % of the stall samples).
+__device__ __forceinline__ void tile_load_rows(float2* __restrict__ tile, const float2* __restrict__ x, int rows, int k0, int seg, int n, int t0, int lane, int pitch)
+{
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int r = r0 + u;
+            const int len_r = r < rows ? min(seg, n - (k0 + r) * seg) : 0;
+            v[u] = (t0 + lane < len_r) ? x[(long)(k0 + r) * seg + t0 + lane] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (r0 + u < rows) tile[(r0 + u) * pitch + lane] = v[u];
+    }
+}
 constexpr int SH_PITCH = SH_TILE + 1;             // odd pitch in 8-byte units: row-wise walks are conflict-free
 
 __global__ void __launch_bounds__(128)
@@ -76,11 +94,7 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
     const int max_len = min(chunk, n - k0 * chunk);          // the first chunk of the warp is never the short one
     for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
         // coalesced load: row r = chunk k0+r, 32 consecutive samples starting at t0
-        for (int r = 0; r < rows; r++) {
-            const long pos = (long)(k0 + r) * chunk + t0 + lane;
-            const int len_r = min(chunk, n - (k0 + r) * chunk);
-            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
-        }
+        tile_load_rows(tile, x, rows, k0, chunk, n, t0, lane, SH_PITCH);
         __syncwarp();
         if (live) {
             float2* row = tile + lane * SH_PITCH;
@@ -150,11 +164,7 @@ shift_addfast_bank_kernel(const float2* __restrict__ in, long in_stride, float2*
     const int rows = min(32, nchunks - k0);
     const int max_len = min(chunk, n - k0 * chunk);          // the first call of the warp is never the short one
     for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
-        for (int r = 0; r < rows; r++) {
-            const long pos = (long)(k0 + r) * chunk + t0 + lane;
-            const int len_r = min(chunk, n - (k0 + r) * chunk);
-            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
-        }
+        tile_load_rows(tile, x, rows, k0, chunk, n, t0, lane, SH_PITCH);
         __syncwarp();
         if (live) {
             float2* row = tile + lane * SH_PITCH;
@@ -236,11 +246,7 @@ shift_math_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __
     const int rows = min(32, nseg - k0);
     const int max_len = min(MATH_SEG, n - k0 * MATH_SEG);    // the first segment of the warp is never the short one
     for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
-        for (int r = 0; r < rows; r++) {
-            const long pos = (long)(k0 + r) * MATH_SEG + t0 + lane;
-            const int len_r = min(MATH_SEG, n - (k0 + r) * MATH_SEG);
-            tile[r * SH_PITCH + lane] = (t0 + lane < len_r) ? x[pos] : make_float2(0.f, 0.f);
-        }
+        tile_load_rows(tile, x, rows, k0, MATH_SEG, n, t0, lane, SH_PITCH);
         __syncwarp();
         if (live) {
             float2* row = tile + lane * SH_PITCH;

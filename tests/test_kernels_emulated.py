@@ -385,6 +385,31 @@ def test_k7_fft_every_size_both_directions(fft):
     assert fft.emul_barriers() > 100                                       # the barriers were real
 
 
+def test_k7_radix16_experiment(fft, tmp_path_factory):
+    """branch r2-prep: the radix-16 batched FFT (fft16.cuh) behind CSDRB_FFT_RADIX16 -- a private copy of the library reads the switch"""
+    so, names, proto = _built["fft.cu"]
+    copy = so.with_name(f"{so.stem}_radix16.so")
+    if not copy.exists():
+        shutil.copy(so, copy)
+    os.environ["CSDRB_FFT_RADIX16"] = "1"
+    try:
+        lib = C.CDLL(str(copy))
+        f = lib.emul_launch_fft_c2c_batch; f.argtypes, f.restype = proto.emul_launch_fft_c2c_batch.argtypes, proto.emul_launch_fft_c2c_batch.restype
+        lib.emul_barriers.restype = C.c_long
+        rng = np.random.default_rng(16)
+        for n in (32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
+            x = _aligned((2, n), np.complex64); x[:] = _cplx(rng, 2, n); y = _aligned((2, n), np.complex64)
+            for inv in (0, 1):
+                b0 = lib.emul_barriers()
+                assert f(P(x), n, P(y), n, n, 2, inv) >= 0
+                want = np.fft.ifft(x.astype(np.complex128), axis=1) * n if inv else np.fft.fft(x.astype(np.complex128), axis=1)
+                assert rel_rms(y, want) < 1e-6, (n, inv)
+            if n == 4096:
+                assert (lib.emul_barriers() - b0) // 2 == 4               # three passes: it really is the radix-16 path
+    finally:
+        del os.environ["CSDRB_FFT_RADIX16"]
+
+
 def _overlap_add(x, H, N, isz):
     nb = x.size // isz; out = Z(nb * isz + N - isz, np.complex128)
     for b in range(nb):
