@@ -960,7 +960,7 @@ def shift_unroll_bank_cc(x, rates, phases=None, table_size: int = 1024, out=None
     d_ds, d_dc = torch.from_numpy(ds).to(dev), torch.from_numpy(dc).to(dev)
     d_phase = torch.zeros(ch, dtype=torch.float32, device=dev) if phases is None else phases.clone()
     out = torch.empty((ch, n), dtype=torch.complex64, device=dev) if out is None else out
-    scratch = _scratch(ch * ((n + table_size - 1) // table_size + 1) * 4, dev)
+    scratch = _scratch(lib().csdrb_shift_addition_bank_scratch_bytes(ch, n, min(table_size, n)) + 16, dev)
     _check(lib().csdrb_shift_unroll_bank_cc(ptr, stride, out.data_ptr(), out.stride(0), ch, n, params.data_ptr(), d_ds.data_ptr(), d_dc.data_ptr(), table_size,
                                             table_size, d_phase.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "shift_unroll_bank_cc")
     return out, d_phase

@@ -597,6 +597,7 @@ struct csdrb_ddc_bank_s {
     float* d_phase[2] = {nullptr, nullptr};          // phase at the start of the chunk holding the next block's first sample (ping-pong)
     float2* d_last[2] = {nullptr, nullptr};          // previous baseband sample per channel (ping-pong across blocks)
     void* d_scratch[2] = {nullptr, nullptr};
+    void* d_tables = nullptr;                         // phase-wrap tables (phase_table.cuh), one per channel; rebuilt when a rate changes
     size_t scratch_cap = 0;
     int cur = 0;                                      // which phase/scratch buffer holds the state for the NEXT process() call
     int last_sel = 0;
@@ -627,6 +628,8 @@ csdrb_ddc_bank_t* csdrb_ddc_bank_create(int channels, const float* h_rates, int 
         if (ok) { cudaMemset(b->d_phase[k], 0, sizeof(float) * (size_t)channels); cudaMemset(b->d_last[k], 0, sizeof(float2) * (size_t)channels); }
     }
     ok = ok && cudaMemcpy(b->d_params, b->h_params.data(), sizeof(shift_addition_data_t) * (size_t)channels, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMalloc(&b->d_tables, ddc_bank_tables_bytes(channels)) == cudaSuccess;
+    ok = ok && launch_ddc_tables(channels, b->d_params, b->chunk, b->d_tables, nullptr) >= 0 && cudaStreamSynchronize(nullptr) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&b->ev_prepass, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&b->ev_pre_inline, cudaEventDisableTiming) == cudaSuccess;
@@ -642,7 +645,7 @@ void csdrb_ddc_bank_destroy(csdrb_ddc_bank_t* b)
     if (b->ev_prepass) cudaEventDestroy(b->ev_prepass);
     if (b->ev_pre_inline) cudaEventDestroy(b->ev_pre_inline);
     for (int k = 0; k < 2; k++) if (b->ev_main[k]) cudaEventDestroy(b->ev_main[k]);
-    cudaFree(b->d_params);
+    cudaFree(b->d_params); cudaFree(b->d_tables);
     for (int k = 0; k < 2; k++) { cudaFree(b->d_phase[k]); cudaFree(b->d_last[k]); cudaFree(b->d_scratch[k]); }
     delete b;
 }
@@ -670,16 +673,26 @@ int csdrb_ddc_bank_process(csdrb_ddc_bank_t* b, const complexf* d_wide, int inpu
         for (int k = 0; k < 2; k++) { if (b->d_scratch[k]) CSDRB_CUDA(cudaFree(b->d_scratch[k])); CSDRB_CUDA(cudaMalloc(&b->d_scratch[k], need)); }
         b->scratch_cap = need; b->ahead_valid = false;
     }
-    if (b->params_dirty) {                            // retune: the phases stay, the deltas change, a pre-pass made with the old ones is void
+    int launches = 0;
+    if (b->params_dirty) {                            // retune: a pre-pass made with the old deltas is void
         CSDRB_CUDA(cudaStreamSynchronize(b->side));
-        if (b->ahead_valid) {
-            // the look-ahead already advanced phase[cur^1] from phase[cur]; phase[cur] is still the state before it: just forget it
-            b->ahead_valid = false;
+        // the look-ahead already advanced phase[cur^1] from phase[cur]; phase[cur] is still the state before it: just forget it
+        b->ahead_valid = false;
+        // The phase stays continuous across a retune only if the new deltas start from the phase AT the retune sample.  phase[cur] is the
+        // phase at the start of the current chunk, `offset` samples back: close that chunk here -- advance every channel by `offset` samples
+        // at its OLD rate, exactly what the reference does when a caller hands shift_addition_cc a shorter buffer (libcsdr_gpl.c:48-50) -- and
+        // start a fresh chunk at this block's first sample.
+        if (b->offset > 0) {
+            int rc = launch_ddc_rechunk(b->channels, b->d_params, b->d_phase[b->cur], b->offset, st);
+            if (rc < 0) return rc;
+            launches += rc;
+            b->offset = 0;
         }
         CSDRB_CUDA(cudaMemcpyAsync(b->d_params, b->h_params.data(), sizeof(shift_addition_data_t) * (size_t)b->channels, cudaMemcpyHostToDevice, st));
+        { int rc = launch_ddc_tables(b->channels, b->d_params, b->chunk, b->d_tables, st); if (rc < 0) return rc; launches += rc; }
+        CSDRB_CUDA(cudaStreamSynchronize(st));        // h_params may change again as soon as we return; the side stream reads the new tables next
         b->params_dirty = false;
     }
-    int launches = 0;
     int sel;                                          // scratch buffer holding this block's seeds
     if (b->ahead_valid && b->ahead_input_size == input_size) {
         sel = b->cur ^ 1;                             // the side stream produced seeds[sel] and advanced phase[sel] from phase[cur]
@@ -690,7 +703,7 @@ int csdrb_ddc_bank_process(csdrb_ddc_bank_t* b, const complexf* d_wide, int inpu
         // phase[sel] <- phase[cur], then run the pre-pass on the caller's stream (it advances phase[sel])
         CSDRB_CUDA(cudaMemcpyAsync(b->d_phase[sel], b->d_phase[b->cur], sizeof(float) * (size_t)b->channels, cudaMemcpyDeviceToDevice, st));
         int rc = launch_ddc_prepass(input_size, b->channels, b->d_params, b->d_phase[sel], b->chunk, b->offset, b->decimation, b->taps_length,
-                                    b->d_scratch[sel], b->scratch_cap, st);
+                                    b->d_scratch[sel], b->scratch_cap, b->d_tables, st);
         if (rc < 0) return rc;
         launches += rc;
         CSDRB_CUDA(cudaEventRecord(b->ev_pre_inline, st));             // the look-ahead below starts from the phases this pre-pass produced
@@ -715,7 +728,7 @@ int csdrb_ddc_bank_process(csdrb_ddc_bank_t* b, const complexf* d_wide, int inpu
         if (b->blocks > 0) CSDRB_CUDA(cudaStreamWaitEvent(b->side, b->ev_main[(b->blocks - 1) & 1], 0));
         CSDRB_CUDA(cudaMemcpyAsync(b->d_phase[nxt], b->d_phase[b->cur], sizeof(float) * (size_t)b->channels, cudaMemcpyDeviceToDevice, b->side));
         int rp = launch_ddc_prepass(input_size, b->channels, b->d_params, b->d_phase[nxt], b->chunk, b->offset, b->decimation, b->taps_length,
-                                    b->d_scratch[nxt], b->scratch_cap, b->side);
+                                    b->d_scratch[nxt], b->scratch_cap, b->d_tables, b->side);
         if (rp < 0) return rp;
         launches += rp;
         CSDRB_CUDA(cudaEventRecord(b->ev_prepass, b->side));

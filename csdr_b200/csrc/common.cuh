@@ -30,6 +30,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // ---- packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2) --------------------------------------------
 // One instruction does the I and the Q lane of a complex sample.  Each half is an IEEE-754 fp32
 // operation (round-to-nearest-even), so results are identical to two scalar FFMA/FADD/FMUL.
+// CAUTION: ptxas (12.9) contracts fadd2(fmul2(a, b), c) into ONE FFMA2 despite the explicit .rn and even under --fmad=false,
+// unlike the scalar __fmul_rn/__fadd_rn pair.  Where a product has to be rounded on its own, add with scalar __fadd_rn.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
 {
     uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b),

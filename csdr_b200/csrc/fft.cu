@@ -22,6 +22,15 @@
 
 namespace csdrb {
 
+// Radix-16 passes (fft16.cuh) are the default since the round-2 A/B on a B200 (profiles/r02_ab_*): 4096-pt 313 -> 379 Gsamples/s, 16384-pt 188 -> 211,
+// fastddc forward 101 -> 113, config-5 overlap-add 84.6 -> 97.5.  CSDRB_FFT_RADIX16=0 selects the radix-8 kernels (kept for A/B runs and for sizes
+// without a radix-16 plan).
+static bool fft_radix16_enabled()
+{
+    const char* e = getenv("CSDRB_FFT_RADIX16");
+    return !(e && e[0] == '0');
+}
+
 // ---- twiddle tables ------------------------------------------------------------------------------
 static std::map<int, float2*> g_tw;
 static std::mutex g_tw_mu;
@@ -100,7 +109,7 @@ int launch_fft_c2c_batch(const float2* d_in, long in_stride, float2* d_out, long
 {
     if (batch <= 0) return 0;
     if (n < 2 || n > FFT_MAX_N || (n & (n - 1))) { set_error("fft: size %d unsupported (power of two, 2..%d)", n, FFT_MAX_N); return -1; }
-    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    static const bool radix16 = fft_radix16_enabled();
     if (radix16 && n >= 32) {
         const float2* tw16 = nullptr;
         if (int rc = get_twiddles16(n, &tw16, st)) return rc;
@@ -137,7 +146,7 @@ int launch_olafir_bank(const float2* d_in, long in_stride, float2* d_out, long o
     }
     const dim3 grid((nblocks + blocks_per_cta - 1) / blocks_per_cta, channels);
     static const bool staged = getenv("CSDRB_OLAFIR_STAGED") != nullptr;            // A/B switch: the r01 kernel with staged copies
-    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT: radix-16 passes for 16^k sizes (256, 4096)
+    static const bool radix16 = fft_radix16_enabled();
     if (radix16 && !staged && (fft_size == 256 || fft_size == 4096)) {
         const float2* tw16 = nullptr;
         if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
@@ -182,7 +191,7 @@ int launch_fastddc_fwd(const float2* d_in, float2* d_spectra, float2* d_overlap_
 {
     if (nblocks <= 0) return 0;
     if (fft_size < 4 || fft_size > FFT_MAX_N || (fft_size & (fft_size - 1))) { set_error("fastddc_fwd: fft_size %d unsupported", fft_size); return -1; }
-    static const bool radix16 = getenv("CSDRB_FFT_RADIX16") != nullptr;              // EXPERIMENT switch (fft16.cuh)
+    static const bool radix16 = fft_radix16_enabled();
     if (radix16 && fft_size >= 32) {
         const float2* tw16 = nullptr;
         if (int rc = get_twiddles16(fft_size, &tw16, st)) return rc;
@@ -245,7 +254,10 @@ int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const flo
 // ---- fastddc inverse bank ----------------------------------------------------------------------------
 
 
-size_t fastddc_inv_scratch_bytes(int channels, int nblocks) { return (size_t)channels * nblocks * 12 + 64; }
+size_t fastddc_inv_scratch_bytes(int channels, int nblocks)
+{
+    return (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15) + (nblocks > 96 ? (size_t)channels * sizeof(WrapTable) : 0);
+}
 
 int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* d_taps_fft, const void* d_chan, int channels,
                             int fft_size, int fft_inv_size, int pre_decimation, int scrap, int post_input_size, int post_decimation,
@@ -262,8 +274,9 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     int* blk_remain = static_cast<int*>(d_scratch);
     float* blk_phase = reinterpret_cast<float*>(blk_remain + (size_t)channels * nblocks);
     int* blk_offset = reinterpret_cast<int*>(blk_phase + (size_t)channels * nblocks);
-    fastddc_state_chain_kernel<<<(channels + 63) / 64, 64, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
-                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation);
+    WrapTable* tables = nblocks > 96 ? reinterpret_cast<WrapTable*>(static_cast<char*>(d_scratch) + (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15)) : nullptr;
+    fastddc_state_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {
         // Tile = CT channels x BT blocks per CTA (each spectrum bin fetched once per CT channels, each tap once per BT blocks).  Big tiles

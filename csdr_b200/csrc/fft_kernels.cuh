@@ -4,6 +4,7 @@
 #pragma once
 #include "fft.cuh"
 #include "fft16.cuh"
+#include "phase_table.cuh"
 
 namespace csdrb {
 
@@ -306,7 +307,8 @@ __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph
 // per channel: walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
 __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
                                            int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
-                                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation)
+                                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation,
+                                           WrapTable* __restrict__ tables)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
@@ -318,12 +320,14 @@ __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int
     const bool steady = (post_input_size % post_decimation == 0) && remain >= 0 && remain < post_decimation;
     const int k_const = post_input_size / post_decimation;
     const float adv_const = __fmul_rn(__fmul_rn(rate, PI_F), (float)k_const);
+    const bool tab = steady && tables != nullptr && nblocks > 96;      // a long steady chain runs on its increment's wrap table (phase_table.cuh)
+    if (tab) wrap_table_build(adv_const, tables + c);
     for (int b = 0; b < nblocks; b++) {
         blk_remain[(long)b * channels + c] = remain;                    // [block][channel]: consecutive lanes store consecutive words
         blk_phase[(long)b * channels + c] = ph;
         blk_offset[(long)b * channels + c] = off;
         if (steady) {
-            ph = ddc_wrap(__fadd_rn(ph, adv_const));
+            ph = tab ? wrap_after_add(__fadd_rn(ph, adv_const), tables + c) : ddc_wrap(__fadd_rn(ph, adv_const));
             off += k_const;
         } else {
             int k = 0, pos = remain;

@@ -77,8 +77,11 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
 
 // fused shared-input DDC bank, ddc_bank.cu
 size_t ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset);
+size_t ddc_bank_tables_bytes(int channels);                            // persistent phase-wrap tables of a bank (phase_table.cuh), one per channel
+int launch_ddc_rechunk(int channels, const float* d_params, float* d_phase_io, int n, cudaStream_t st);
+int launch_ddc_tables(int channels, const float* d_params, int chunk, void* d_tables, cudaStream_t st);
 int launch_ddc_prepass(int input_size, int channels, const float* d_params, float* d_phase_io, int chunk, int offset, int decimation,
-                       int taps_length, void* d_scratch, size_t scratch_bytes, cudaStream_t st);
+                       int taps_length, void* d_scratch, size_t scratch_bytes, const void* d_tables, cudaStream_t st);   // d_tables NULL: built per call in d_scratch
 int launch_ddc_main(const float2* d_wide, int input_size, int channels, const float* d_params, int chunk, int offset, int decimation,
                     const float* h_taps, int taps_length, int demod, void* d_out, long out_stride, const float2* d_last_in, float2* d_last_out,
                     const void* d_scratch, cudaStream_t st);

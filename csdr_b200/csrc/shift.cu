@@ -18,6 +18,7 @@
 //   dshift_kernel            : decimating variant, one thread per channel (chains of a few hundred outputs).
 // All products/sums use __fmul_rn/__fadd_rn/__fsub_rn so nvcc cannot contract them into FMAs.
 #include "common.cuh"
+#include "phase_table.cuh"
 #include <climits>
 #include "kernels.h"
 
@@ -32,17 +33,24 @@ __device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
     return wrap_pm_pi(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate2, PI_F), (float)n)));
 }
 
+// A chain of more than kChainTableMin steps first builds its increment's wrap table (phase_table.cuh: ~150 dependent cycles per step
+// instead of ~1 200; the build costs about as much as thirty direct steps).  The last, shorter chunk has its own increment: direct.
+constexpr int kChainTableMin = 96;
+
 __global__ void shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                                         int channels, int n, int chunk, int nchunks)
+                                         int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
     const float rate2 = params[c].z;
     float ph = phase_io[c];
+    const bool tab = tables != nullptr && nchunks > kChainTableMin;
+    const float inc = __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk);
+    if (tab) wrap_table_build(inc, tables + c);
     for (int k = 0; k < nchunks; k++) {
         chunk_phase[(long)c * nchunks + k] = ph;
         const int len = min(chunk, n - k * chunk);
-        ph = advance_phase(ph, rate2, len);
+        ph = (tab && len == chunk) ? wrap_after_add(__fadd_rn(ph, inc), tables + c) : advance_phase(ph, rate2, len);
     }
     phase_io[c] = ph;
 }
@@ -124,16 +132,20 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
 struct AddFastParams { float dsin[4], dcos[4], inc; };                 // = shift_addfast_data_t (libcsdr.h:189-194)
 
 __global__ void addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                                           int channels, int n, int chunk, int nchunks)
+                                           int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= channels) return;
     const float inc = params[c].inc;
     float ph = phase_io[c];
+    const bool tab = tables != nullptr && nchunks > kChainTableMin;
+    const float step = __fmul_rn((float)chunk, inc);
+    if (tab) wrap_table_build(step, tables + c);
     for (int k = 0; k < nchunks; k++) {
         chunk_phase[(long)c * nchunks + k] = ph;
         const int len = min(chunk, n - k * chunk);
-        ph = wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc)));      // starting_phase += input_size * d->phase_increment  (:428)
+        // starting_phase += input_size * d->phase_increment  (:428)
+        ph = (tab && len == chunk) ? wrap_after_add(__fadd_rn(ph, step), tables + c) : wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc)));
     }
     phase_io[c] = ph;
 }
@@ -381,6 +393,8 @@ shift_unroll_bank_kernel(const float2* __restrict__ in, long in_stride, float2* 
     }
 }
 
+static inline WrapTable* chain_tables(void* d_scratch, size_t scratch_bytes, int channels, int nchunks);
+
 int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
                              const float* d_params, const float* d_dsin, const float* d_dcos, long table_stride, int table_size,
                              float* d_phase_io, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
@@ -391,7 +405,8 @@ int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, 
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    shift_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+                                                               chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
     shift_unroll_bank_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, d_dsin, d_dcos, table_stride, chunk_phase, n, chunk, nchunks);
@@ -410,7 +425,15 @@ size_t shift_bank_scratch_bytes(int channels, int n, int chunk)
 {
     if (chunk <= 0 || chunk > n) chunk = n > 0 ? n : 1;
     const int nchunks = (n + chunk - 1) / chunk;
-    return (size_t)channels * (size_t)(nchunks > 0 ? nchunks : 1) * sizeof(float);
+    const size_t phases = ((size_t)channels * (size_t)(nchunks > 0 ? nchunks : 1) * sizeof(float) + 15) & ~(size_t)15;
+    return phases + (nchunks > kChainTableMin ? (size_t)channels * sizeof(WrapTable) : 0);
+}
+// the wrap tables sit behind the chunk phases when the caller's scratch has room for them (it has, if it was sized by the function above)
+static inline WrapTable* chain_tables(void* d_scratch, size_t scratch_bytes, int channels, int nchunks)
+{
+    const size_t phases = ((size_t)channels * (size_t)nchunks * sizeof(float) + 15) & ~(size_t)15;
+    if (nchunks <= kChainTableMin || scratch_bytes < phases + (size_t)channels * sizeof(WrapTable)) return nullptr;
+    return reinterpret_cast<WrapTable*>(static_cast<char*>(d_scratch) + phases);
 }
 
 int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,
@@ -422,7 +445,8 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addition bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    shift_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+                                                               chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, reinterpret_cast<const float3*>(d_params), chunk_phase, n, chunk, nchunks);
@@ -440,7 +464,7 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addfast bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
     const AddFastParams* params = reinterpret_cast<const AddFastParams*>(d_params);
-    addfast_phase_chain_kernel<<<(channels + 127) / 128, 128, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks);
+    addfast_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);

@@ -230,7 +230,10 @@ int csdrb_ddc_bank(const complexf *d_wide, int input_size, int channels, const s
 typedef struct csdrb_ddc_bank_s csdrb_ddc_bank_t;
 csdrb_ddc_bank_t *csdrb_ddc_bank_create(int channels, const float *h_rates, int decimation, const float *h_taps, int taps_length, int demod, int chunk);
 void csdrb_ddc_bank_destroy(csdrb_ddc_bank_t *bank);
-int  csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t *bank, int channel, float rate);     /* retune one channel; effective from the next block */
+/* retune one channel; effective from the first sample of the next block.  The phase is continuous across the retune: the bank closes the current NCO
+ * chunk at that sample for every channel (a shorter shift_addition_cc call, libcsdr_gpl.c:48-50) and starts a fresh chunk there, like the reference CLI
+ * re-initialises between two buffers (csdr.c:897-925) */
+int  csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t *bank, int channel, float rate);
 int  csdrb_ddc_bank_offset(const csdrb_ddc_bank_t *bank);                          /* samples of the current NCO chunk already consumed */
 int  csdrb_ddc_bank_process(csdrb_ddc_bank_t *bank, const complexf *d_wide, int input_size, void *d_out, long out_stride, void *stream);
 

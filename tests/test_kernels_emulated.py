@@ -177,7 +177,7 @@ def test_ima_adpcm_rows_bit_exact(elementwise, oracle):
 
 
 # ------------------------------------------------------------------------------------------------------------------ K2 and shift variants
-@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37)])
+@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37), (120 * 1024 + 5, 1024), (9000, 64)])   # the last two: > 96 chunks, the chain runs on its wrap table (phase_table.cuh)
 def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):
     rng = np.random.default_rng(n)
     rates = np.array([-0.41, -0.085, 0.0, 0.2, 0.4999, 1e-4], np.float32)
@@ -385,13 +385,17 @@ def test_k7_fft_every_size_both_directions(fft):
     assert fft.emul_barriers() > 100                                       # the barriers were real
 
 
-def test_k7_radix16_experiment(fft, tmp_path_factory):
-    """branch r2-prep: the radix-16 batched FFT (fft16.cuh) behind CSDRB_FFT_RADIX16 -- a private copy of the library reads the switch"""
+def test_k7_radix8_kernels_behind_the_switch(fft, tmp_path_factory):
+    """radix-16 passes (fft16.cuh) are the default since round 2; CSDRB_FFT_RADIX16=0 selects the radix-8 kernels, which stay shipped (sizes without a
+    radix-16 plan, A/B runs) -- a private copy of the library reads the switch, so both generations run every size here.  Also covers the overlap-add
+    bank and the fastddc forward step of that generation."""
     so, names, proto = _built["fft.cu"]
-    copy = so.with_name(f"{so.stem}_radix16.so")
+    copy = so.with_name(f"{so.stem}_radix8.so")
     if not copy.exists():
         shutil.copy(so, copy)
-    os.environ["CSDRB_FFT_RADIX16"] = "1"
+    z = _aligned((1, 32), np.complex64); z[:] = 1
+    assert fft.emul_launch_fft_c2c_batch(P(z), 32, P(z.copy()), 32, 32, 1, 0) >= 0      # the default library latches its (unset) switch now
+    os.environ["CSDRB_FFT_RADIX16"] = "0"
     try:
         lib = C.CDLL(str(copy))
         f = lib.emul_launch_fft_c2c_batch; f.argtypes, f.restype = proto.emul_launch_fft_c2c_batch.argtypes, proto.emul_launch_fft_c2c_batch.restype
@@ -400,12 +404,24 @@ def test_k7_radix16_experiment(fft, tmp_path_factory):
         for n in (32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384):
             x = _aligned((2, n), np.complex64); x[:] = _cplx(rng, 2, n); y = _aligned((2, n), np.complex64)
             for inv in (0, 1):
-                b0 = lib.emul_barriers()
+                b0 = lib.emul_barriers()                                # (the emulator's counters are one per process: inline-function statics are GNU-unique)
                 assert f(P(x), n, P(y), n, n, 2, inv) >= 0
+                passes8 = (lib.emul_barriers() - b0) // 2
                 want = np.fft.ifft(x.astype(np.complex128), axis=1) * n if inv else np.fft.fft(x.astype(np.complex128), axis=1)
                 assert rel_rms(y, want) < 1e-6, (n, inv)
+                y2 = _aligned((2, n), np.complex64); b1 = fft.emul_barriers()
+                assert fft.emul_launch_fft_c2c_batch(P(x), n, P(y2), n, n, 2, inv) >= 0 and rel_rms(y2, want) < 1e-6
+                passes16 = (fft.emul_barriers() - b1) // 2
             if n == 4096:
-                assert (lib.emul_barriers() - b0) // 2 == 4               # three passes: it really is the radix-16 path
+                assert passes16 == 4 and passes8 > 4                      # default library: three radix-16 passes; the copy: four radix-8 passes
+        g = lib.emul_launch_olafir_bank; g.argtypes, g.restype = proto.emul_launch_olafir_bank.argtypes, proto.emul_launch_olafir_bank.restype
+        N, isz, nb = 4096, 2098, 3
+        x = _aligned((1, nb * isz), np.complex64); x[:] = _cplx(rng, 1, nb * isz)
+        H = _aligned(N, np.complex64); H[:] = _cplx(rng, N)
+        tail = _aligned((1, N), np.complex64); tail[:] = 0; out = _aligned((1, nb * isz), np.complex64)
+        assert g(P(x), nb * isz, P(out), nb * isz, 1, N, isz, nb, P(H), 0, P(tail), 0) >= 0
+        want, _ = _overlap_add(x[0].astype(np.complex128), H.astype(np.complex128), N, isz)
+        assert rel_rms(out[0], want) < 5e-6
     finally:
         del os.environ["CSDRB_FFT_RADIX16"]
 
