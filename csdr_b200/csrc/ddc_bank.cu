@@ -52,30 +52,37 @@ __global__ void ddc_seed_kernel(const float* __restrict__ chunk_phase, float2* _
 // phase chain over ABSOLUTE chunks: the block starts `offset` samples into chunk 0; phase_io holds the phase at the start of
 // chunk 0 on entry and, on return, the phase at the start of the chunk that contains sample `advance` (the next block's start).
 // Every step adds the same increment, so the wrap is a table lookup (phase_table.cuh): ~150 dependent cycles per chunk instead of ~1 200.
-__global__ void ddc_wrap_tables_kernel(const float3* __restrict__ params, int chunk, WrapTable* __restrict__ tables, int channels)
+// One WARP per channel: lane 0 builds the table (32 different control flows in one warp would serialise), the chain itself keeps the table in
+// registers across the lanes (wrap_after_add_warp) and stores 32 chunk phases at a time.
+__global__ void __launch_bounds__(32)
+ddc_wrap_tables_kernel(const float3* __restrict__ params, int chunk, WrapTable* __restrict__ tables, int channels)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < channels) wrap_table_build(__fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk), tables + c);
+    const int c = blockIdx.x;
+    if (c < channels && threadIdx.x == 0) wrap_table_build(__fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk), tables + c);
 }
 
-__global__ void ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                                       int channels, int nchunks, int chunk, int next_chunk, const WrapTable* __restrict__ tables)
+__global__ void __launch_bounds__(32)
+ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                       int channels, int nchunks, int chunk, int next_chunk, const WrapTable* __restrict__ tables)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= channels) return;
     const float inc = __fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk);
-    const WrapTable* t = tables + c;
-    float ph = phase_io[c], keep = ph;
+    const WrapLanes w = wrap_lanes_load(tables + c, lane);
+    float ph = phase_io[c], keep = ph, mine = 0.f;
+    __syncwarp();                                      // every lane has read the carried phase before lane 0 overwrites it
+    float* dst = chunk_phase + (long)c * nchunks;
     for (int k = 0; k < nchunks; k++) {
-        chunk_phase[(long)c * nchunks + k] = ph;
+        if ((k & 31) == lane) mine = ph;
+        if ((k & 31) == 31 || k == nchunks - 1) { if ((k & ~31) + lane <= k) dst[(k & ~31) + lane] = mine; }     // one coalesced store per 32 steps
         if (k == next_chunk) keep = ph;
-        ph = wrap_after_add(__fadd_rn(ph, inc), t);
+        ph = wrap_after_add_warp(__fadd_rn(ph, inc), w);
     }
     if (next_chunk >= nchunks) {                       // the next block starts beyond the chunks this block touched
-        for (int k = nchunks; k < next_chunk; k++) ph = wrap_after_add(__fadd_rn(ph, inc), t);
+        for (int k = nchunks; k < next_chunk; k++) ph = wrap_after_add_warp(__fadd_rn(ph, inc), w);
         keep = ph;
     }
-    phase_io[c] = keep;
+    if (lane == 0) phase_io[c] = keep;
 }
 
 // retune support: close the current chunk `n` samples in (every channel advances by n samples at its present rate), see csdrb_ddc_bank_process
@@ -257,8 +264,8 @@ struct DdcWalk {
     }
 };
 
-template <int D, int M, int CPL, bool DEMOD>
-__global__ void __launch_bounds__(128)
+template <int D, int M, int CPL, bool DEMOD, bool PF>
+__global__ void __launch_bounds__(128, 3)
 ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, int chunk, int nchunks,
                        const float3* __restrict__ params, const float2* __restrict__ seeds, int channels, int sets,
                        void* __restrict__ out_v, long out_stride, int n_out, int seg_outputs, int nsegs,
@@ -321,19 +328,35 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
         constexpr int JLO = decltype(jlo)::value, JHI = decltype(jhi)::value;
         constexpr int UU = (JLO == 0 && JHI == MP) ? U : 2;             // the steady-state body is unrolled deeper than the ramps
         const long base = (long)q * D;
+        // the wideband samples of a group are fetched while the previous group is being multiplied (r02 ncu: one exposed L1/L2 round trip per
+        // group was the largest stall after the FMA pipe itself); only the steady-state body bothers
+        constexpr bool PREFETCH = PF && UU >= 8;
+        float4 nx[UU / 2];
+        bool have = false;
 #pragma unroll 1
         for (int p0 = 0; p0 < D; p0 += UU) {
             if (left >= UU && base + p0 + UU <= n_in) {
                 const float4* src = reinterpret_cast<const float4*>(wide + base + p0);     // D, UU even: 16-byte aligned
                 const float4* tp = staps + p0 * (MP / 2);
+                float4 cur[UU / 2];
+#pragma unroll
+                for (int e = 0; e < UU / 2; e++) cur[e] = (PREFETCH && have) ? nx[e] : __ldg(src + e);
+                if (PREFETCH) {
+                    have = p0 + UU < D && left >= 2 * UU && base + p0 + 2 * UU <= n_in;    // the next group takes this branch too
+                    if (have) {
+#pragma unroll
+                        for (int e = 0; e < UU / 2; e++) nx[e] = __ldg(src + UU / 2 + e);
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < UU; e += 2) {
-                    const float4 xx = __ldg(src + e / 2);
+                    const float4 xx = cur[e / 2];
                     w.template sample<JLO, JHI>(xx.x, xx.y, tp + e * (MP / 2));
                     w.template sample<JLO, JHI>(xx.z, xx.w, tp + (e + 1) * (MP / 2));
                 }
                 left -= UU;
             } else {
+                have = false;
 #pragma unroll 1
                 for (int e = 0; e < UU; e++) checked(jlo, jhi, base + p0 + e, p0 + e);
             }
@@ -396,7 +419,7 @@ int launch_ddc_rechunk(int channels, const float* d_params, float* d_phase_io, i
 size_t ddc_bank_tables_bytes(int channels) { return (size_t)channels * sizeof(WrapTable); }
 int launch_ddc_tables(int channels, const float* d_params, int chunk, void* d_tables, cudaStream_t st)
 {
-    ddc_wrap_tables_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), chunk, static_cast<WrapTable*>(d_tables), channels);
+    ddc_wrap_tables_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), chunk, static_cast<WrapTable*>(d_tables), channels);
     CSDRB_CUDA(cudaGetLastError());
     return 1;
 }
@@ -417,7 +440,7 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
     // channels per lane and resident-warp target per SM
     static const int ver_env = getenv("CSDRB_DDC_V") ? atoi(getenv("CSDRB_DDC_V")) : 2;
     static const int cpl_env = getenv("CSDRB_DDC_CPL") ? atoi(getenv("CSDRB_DDC_CPL")) : (ver_env == 1 ? 1 : 2);
-    static const int wps_env = getenv("CSDRB_DDC_WPS") ? atoi(getenv("CSDRB_DDC_WPS")) : (ver_env == 1 ? 24 : 16);
+    static const int wps_env = getenv("CSDRB_DDC_WPS") ? atoi(getenv("CSDRB_DDC_WPS")) : (ver_env == 1 ? 24 : 12);
     const int cpl = cpl_env == 2 ? 2 : 1;
     const int warps_per_seg = (channels + 32 * cpl - 1) / (32 * cpl);
     // enough warps to fill the machine while keeping the M-1 trailing periods of every segment a small fraction
@@ -428,9 +451,12 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
     if (ver_env != 1) {
         const long warps = (long)nsegs * warps_per_seg;
         const unsigned ctas = (unsigned)((warps + 3) / 4);
-#define CSDRB_DDC_LAUNCH2(CPLV, DM) ddc_bank_fused2_kernel<D, M, CPLV, DM><<<ctas, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, warps_per_seg, out, out_stride, n_out, seg, nsegs, last_in, last_out, tp)
-        if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH2(2, true); else CSDRB_DDC_LAUNCH2(2, false); }
-        else { if (demod) CSDRB_DDC_LAUNCH2(1, true); else CSDRB_DDC_LAUNCH2(1, false); }
+        static const bool pf = !(getenv("CSDRB_DDC_PF") && getenv("CSDRB_DDC_PF")[0] == '0');     // register prefetch of the next sample group
+#define CSDRB_DDC_LAUNCH2(CPLV, DM, PFV) ddc_bank_fused2_kernel<D, M, CPLV, DM, PFV><<<ctas, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, warps_per_seg, out, out_stride, n_out, seg, nsegs, last_in, last_out, tp)
+#define CSDRB_DDC_LAUNCH2B(CPLV, DM) do { if (pf) CSDRB_DDC_LAUNCH2(CPLV, DM, true); else CSDRB_DDC_LAUNCH2(CPLV, DM, false); } while (0)
+        if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH2B(2, true); else CSDRB_DDC_LAUNCH2B(2, false); }
+        else { if (demod) CSDRB_DDC_LAUNCH2B(1, true); else CSDRB_DDC_LAUNCH2B(1, false); }
+#undef CSDRB_DDC_LAUNCH2B
 #undef CSDRB_DDC_LAUNCH2
         CSDRB_CUDA(cudaGetLastError());
         return 0;
@@ -467,7 +493,7 @@ int launch_ddc_prepass(int input_size, int channels, const float* d_params, floa
     }
     const long advance = (long)n_out * decimation;                      // the next block starts here (the caller re-presents the tail)
     const int next_chunk = (int)((offset + advance) / chunk);
-    ddc_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
+    ddc_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
                                                              static_cast<const WrapTable*>(d_tables));
     CSDRB_CUDA(cudaGetLastError());
     const long total = (long)channels * nchunks;

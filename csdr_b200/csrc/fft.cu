@@ -252,6 +252,23 @@ int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const flo
 }
 
 // ---- fastddc inverse bank ----------------------------------------------------------------------------
+// one private side stream + fork/join events per device, for work that is independent of the data path of a call
+struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; std::mutex mu; };
+static SideStream* side_stream()
+{
+    static std::map<int, SideStream*> per_dev;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = per_dev.find(dev);
+    if (it != per_dev.end()) return it->second;
+    auto* s = new SideStream();
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) { set_error("side stream: CUDA object creation failed"); delete s; return nullptr; }
+    per_dev[dev] = s;
+    return s;
+}
 
 
 size_t fastddc_inv_scratch_bytes(int channels, int nblocks)
@@ -275,7 +292,49 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     float* blk_phase = reinterpret_cast<float*>(blk_remain + (size_t)channels * nblocks);
     int* blk_offset = reinterpret_cast<int*>(blk_phase + (size_t)channels * nblocks);
     WrapTable* tables = nblocks > 96 ? reinterpret_cast<WrapTable*>(static_cast<char*>(d_scratch) + (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15)) : nullptr;
-    fastddc_state_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+    // Round-2 path: fold as a batched contraction (fastddc_fold_kernel), IFFT + post shift in a second kernel, and the data-independent
+    // block-to-block state chain on a side stream meanwhile.  Needs whole 64-residue CTAs and an even pre-decimation (the half swap of the
+    // spectrum is then a rotation of the fold's k index); anything else takes the round-1 kernels below.  CSDRB_INV_FOLD=0 forces those.
+    static const bool fold_off = getenv("CSDRB_INV_FOLD") && getenv("CSDRB_INV_FOLD")[0] == '0';
+    const int P = fft_size / fft_inv_size;
+    if (!fold_off && fft_inv_size >= 64 && fft_inv_size <= 1024 && P >= 2 && P % 2 == 0) {
+        SideStream* ss = side_stream();
+        if (!ss) return -1;
+        float2* folded = nullptr;
+        CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&folded), sizeof(float2) * (size_t)channels * nblocks * fft_inv_size, st));
+        {
+            std::lock_guard<std::mutex> lk(ss->mu);                     // the fork/join events are shared by every call on this device
+            CSDRB_CUDA(cudaEventRecord(ss->fork, st));
+            CSDRB_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+            fastddc_state_chain_kernel<<<channels, 32, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+                                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
+            CSDRB_CUDA(cudaGetLastError());
+            CSDRB_CUDA(cudaEventRecord(ss->join, ss->stream));
+            const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
+            static bool attr_done = false;
+            if (!attr_done) { CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); attr_done = true; }
+            const dim3 fgrid(fft_inv_size / FOLD_R, (channels + 2 * FOLD_CT - 1) / (2 * FOLD_CT), (nblocks + 2 * FOLD_BT - 1) / (2 * FOLD_BT));
+            if (fgrid.y > 65535u || fgrid.z > 65535u) { set_error("fastddc_inv: bank too large for one call"); return -1; }
+            fastddc_fold_kernel<<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
+                                                          1.0f / (float)pre_decimation);
+            CSDRB_CUDA(cudaGetLastError());
+            CSDRB_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+        }
+        const long npairs = (long)channels * nblocks;
+        const size_t psmem = sizeof(float2) * 4 * (size_t)fft_smem_elems(fft_inv_size);
+        switch (fft_inv_size) {
+#define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
+            if (psmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+            k<<<(unsigned)((npairs + 3) / 4), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
+            CSDRB_FFT_SIZES(X)
+#undef X
+        }
+        CSDRB_CUDA(cudaGetLastError());
+        CSDRB_CUDA(cudaFreeAsync(folded, st));
+        return 3;
+    }
+    fastddc_state_chain_kernel<<<channels, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {

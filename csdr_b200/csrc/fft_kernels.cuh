@@ -304,16 +304,18 @@ struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per ch
 #define PI_F 3.14159265358979323846f
 __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph); }
 
-// per channel: walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
-__global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
-                                           int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
-                                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation,
-                                           WrapTable* __restrict__ tables)
+// per channel (one WARP each): walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
+__global__ void __launch_bounds__(32)
+fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
+                           int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
+                           int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation,
+                           WrapTable* __restrict__ tables)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x, lane = threadIdx.x;
     if (c >= channels) return;
     int remain = remain_io[c], off = 0;
     float ph = phase_io[c];
+    __syncwarp();                                                       // every lane has read the carried state before lane 0 overwrites it
     const float rate = chan[c].rate;
     // when post_decimation divides post_input_size (every fastddc geometry with an even scrap, e.g. 448/2) and the carried
     // remainder is in range, both the per-block output count and the remainder are constants: no integer division in the loop
@@ -321,13 +323,20 @@ __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int
     const int k_const = post_input_size / post_decimation;
     const float adv_const = __fmul_rn(__fmul_rn(rate, PI_F), (float)k_const);
     const bool tab = steady && tables != nullptr && nblocks > 96;      // a long steady chain runs on its increment's wrap table (phase_table.cuh)
-    if (tab) wrap_table_build(adv_const, tables + c);
+    WrapLanes w; w.n = 0; w.lo = w.hi = w.thr0 = w.thr1 = 0.f; w.K0 = w.K1 = 0.0;
+    if (tab) {
+        if (lane == 0) wrap_table_build(adv_const, tables + c);
+        __syncwarp();
+        w = wrap_lanes_load(tables + c, lane);
+    }
     for (int b = 0; b < nblocks; b++) {
-        blk_remain[(long)b * channels + c] = remain;                    // [block][channel]: consecutive lanes store consecutive words
-        blk_phase[(long)b * channels + c] = ph;
-        blk_offset[(long)b * channels + c] = off;
+        if (lane == 0) {                                                // [block][channel] like the consumers index it
+            blk_remain[(long)b * channels + c] = remain;
+            blk_phase[(long)b * channels + c] = ph;
+            blk_offset[(long)b * channels + c] = off;
+        }
         if (steady) {
-            ph = tab ? wrap_after_add(__fadd_rn(ph, adv_const), tables + c) : ddc_wrap(__fadd_rn(ph, adv_const));
+            ph = tab ? wrap_after_add_warp(__fadd_rn(ph, adv_const), w) : ddc_wrap(__fadd_rn(ph, adv_const));
             off += k_const;
         } else {
             int k = 0, pos = remain;
@@ -337,7 +346,7 @@ __global__ void fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int
             off += k;
         }
     }
-    remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off;
+    if (lane == 0) { remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off; }
 }
 
 template <int M>
@@ -482,6 +491,135 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
                 const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
                 co = cn; si = sn;
             }
+        }
+    }
+}
+
+
+// ---- fastddc inverse, round 2: fold as a batched complex contraction + a separate IFFT / post-shift kernel ------------------------------
+// Round 1's tiled kernel above reached 10 Gsamples/s (2.7 % of the HBM roof, 8 % of FP32): ncu showed 13 warps per issue waiting on the
+// fold's global loads, and a 4x4 tile still pulls 1.07 GB through L2 per 64 ch x 256 blocks.  The fold is, per residue r of M,
+//     F[c][b][r] = sum_{k < P}  Xs[b][r + k*M] * H[c][r + k*M],           P = N / M  (= pre_decimation)
+// i.e. M independent complex (C x P) * (P x B) products.  fastddc_fold_kernel runs it like a GEMM: a CTA owns 64 residues x 16 channels x
+// 16 blocks; per k-step the 16 spectrum rows and 16 tap rows (8 KB each) arrive by cp.async into a 3-stage ring, every value is read from
+// shared memory by two thread groups, and a thread keeps an 8 x 8 accumulator tile for its residue (128 FFMA2 per 16 LDS.64).  L2 traffic
+// drops to 0.27 GB, the inner loop is FMA-pipe bound.  Summation per destination bin is still ascending in the bin index, as in
+// fastddc.c:126-141 (k ascending = bin index ascending); products and sums are fused (FFMA2), inside the 1e-5 budget.
+// The folded bins go to a scratch array (L2-sized: 64 ch x 256 blocks x 512 bins = 67 MB), fastddc_ifft_post_kernel does IFFT_M, /M,
+// scrap and the post shift; the block-to-block state chain runs on a side stream meanwhile (it is data-independent).
+constexpr int FOLD_R = 64, FOLD_CT = 8, FOLD_BT = 8, FOLD_ST = 3;     // residues per CTA, thread tile (channels x blocks), pipeline stages
+
+__global__ void __launch_bounds__(256, 1)
+fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
+                    float2* __restrict__ folded /*[C][nblocks][M]*/, int N, int M, int nblocks, int channels, float inv_pre)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* sm = reinterpret_cast<float2*>(smem_raw);                   // FOLD_ST stages of { x[16][64], h[16][64] }
+    constexpr int ROWS = 2 * FOLD_BT, STAGE = 2 * ROWS * FOLD_R;        // float2 per stage
+    const int tid = threadIdx.x;
+    const int rl = tid & 63, g = tid >> 6, gc = g & 1, gb = g >> 1;
+    const int r0 = blockIdx.x * FOLD_R, c0 = blockIdx.y * (2 * FOLD_CT), b0 = blockIdx.z * (2 * FOLD_BT);
+    const int P = N / M, halfP = P / 2;                                 // the half swap of the spectrum (fastddc.c:123) is a rotation of k by P/2
+    // this thread's four 16-byte copies per k-step: chunk ids tid + 256*q, q < 4; 32 chunks per row, rows 0..15 = spectrum, 16..31 = taps
+    const float2* src[4]; int dsto[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int id = tid + 256 * q, row = id >> 5, col = (id & 31) * 2;
+        if (row < ROWS) src[q] = spectra + (long)min(b0 + row, nblocks - 1) * N + r0 + col;          // ragged edges shadow the last valid row
+        else src[q] = taps_fft + (long)min(c0 + row - ROWS, channels - 1) * N + r0 + col;
+        dsto[q] = row * FOLD_R + col;
+    }
+    auto issue = [&](int k, int stage) {
+        const int kx = k + halfP < P ? k + halfP : k + halfP - P;
+#pragma unroll
+        for (int q = 0; q < 4; q++) cp_async16(sm + stage * STAGE + dsto[q], src[q] + (long)(q < 2 ? kx : k) * M);
+    };
+    float2 acc[FOLD_CT][FOLD_BT];
+#pragma unroll
+    for (int u = 0; u < FOLD_CT; u++)
+#pragma unroll
+        for (int v = 0; v < FOLD_BT; v++) acc[u][v] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < FOLD_ST - 1; s++) { if (s < P) issue(s, s); cp_async_commit(); }
+    for (int k = 0; k < P; k++) {
+        cp_async_wait<FOLD_ST - 2>();
+        __syncthreads();                                                // stage k has landed for everyone; stage (k-1) is free again
+        if (k + FOLD_ST - 1 < P) issue(k + FOLD_ST - 1, (k + FOLD_ST - 1) % FOLD_ST);
+        cp_async_commit();
+        const float2* xs = sm + (k % FOLD_ST) * STAGE + (gb * FOLD_BT) * FOLD_R + rl;
+        const float2* hs = sm + (k % FOLD_ST) * STAGE + (ROWS + gc * FOLD_CT) * FOLD_R + rl;
+        float2 x[FOLD_BT], h[FOLD_CT];
+#pragma unroll
+        for (int v = 0; v < FOLD_BT; v++) x[v] = xs[v * FOLD_R];
+#pragma unroll
+        for (int u = 0; u < FOLD_CT; u++) h[u] = hs[u * FOLD_R];
+#pragma unroll
+        for (int u = 0; u < FOLD_CT; u++)
+#pragma unroll
+            for (int v = 0; v < FOLD_BT; v++) {
+                // acc += x*h = xr*(hr, hi) + xi*(-hi, hr): two packed FMAs, scalar-broadcast x against h and against h swapped/negated (operand
+                // modifiers of FFMA2: no register moves)
+                acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
+                acc[u][v] = ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
+            }
+    }
+    // /pre_decimation, and both half swaps (fastddc.c:143-150) folded into the destination index (r - offsetbin) mod M
+    const int r = r0 + rl;
+#pragma unroll
+    for (int u = 0; u < FOLD_CT; u++) {
+        const int c = c0 + gc * FOLD_CT + u;
+        if (c >= channels) break;
+        int d2 = (r - chan[c].offsetbin) % M;
+        if (d2 < 0) d2 += M;
+#pragma unroll
+        for (int v = 0; v < FOLD_BT; v++) {
+            const int b = b0 + gb * FOLD_BT + v;
+            if (b < nblocks) folded[((long)c * nblocks + b) * M + d2] = make_float2(acc[u][v].x * inv_pre, acc[u][v].y * inv_pre);
+        }
+    }
+}
+
+// IFFT_M of four folded (channel, block) rows per CTA (64 threads each), /M, drop the scrap, post shift + decimate (one lane per row walks its
+// phasor chain).  Pairs are numbered p = c * nblocks + b.
+template <int M>
+__global__ void __launch_bounds__(256)
+fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __restrict__ chan, const int* __restrict__ blk_remain,
+                         const float* __restrict__ blk_phase, const int* __restrict__ blk_offset, float2* __restrict__ out, long out_stride,
+                         int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    float2* s = reinterpret_cast<float2*>(smem_raw);
+    constexpr int NTG = 64, GROUPS = 4, ELEMS = fft_smem_elems(M), PER = M / NTG;
+    static_assert(M >= 64 && M <= 16 * NTG, "fastddc_ifft_post_kernel: 64 <= M <= 1024");
+    const int tid = threadIdx.x, g = tid / NTG, tg = tid % NTG;
+    const long npairs = (long)channels * nblocks;
+    const long p = min((long)blockIdx.x * GROUPS + g, npairs - 1);      // a ragged last CTA repeats the last pair (nothing is stored twice: see below)
+    const bool mine = (long)blockIdx.x * GROUPS + g < npairs;
+    const float2* src = folded + p * M;
+    float2* mys = s + g * ELEMS;
+    float2 v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);     // all loads first
+#pragma unroll
+    for (int k = 0; k < PER; k++) mys[fft_pad(tg + k * NTG)] = v[k];
+    __syncthreads();
+    block_fft<M, NTG, true>(mys, tw, tg);
+    if (tg == 0 && mine) {
+        const int c = (int)(p / nblocks), b = (int)(p % nblocks);
+        const DdcChan cp = chan[c];
+        const float inv_m = 1.0f / (float)M;
+        const long bi = (long)b * channels + c;
+        const double ph = (double)blk_phase[bi];
+        float co = (float)cos(ph), si = (float)sin(ph);
+        float2* y = out + (long)c * out_stride + blk_offset[bi];
+        int k = 0;
+        for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
+            const float2 raw = mys[fft_pad(scrap + pos)];
+            const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
+            y[k++] = make_float2(__fsub_rn(__fmul_rn(co, w.x), __fmul_rn(si, w.y)), __fadd_rn(__fmul_rn(si, w.x), __fmul_rn(co, w.y)));
+            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            co = cn; si = sn;
         }
     }
 }

@@ -47,9 +47,11 @@ __host__ __device__ inline long long wrap_rounded_two_pi(int j)
 
 __host__ __device__ inline int wrap_ilog2(long long v)     // floor(log2(v)), v > 0
 {
-    int b = 0;
-    while (v >> (b + 1)) b++;
-    return b;
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll(v);
+#else
+    return 63 - __builtin_clzll((unsigned long long)v);
+#endif
 }
 
 // smallest float >= v * 2^-21 (v > 0)
@@ -145,5 +147,46 @@ __device__ __forceinline__ float wrap_after_add(float x, const WrapTable* __rest
     return (__float_as_uint(x) >> 31) ? -a : a;
 }
 
+
+#if defined(__CUDACC__) || defined(CSDRB_HOST_EMULATION)
+// ---- one warp per chain: the table lives in registers, a step is two votes and a shuffle ------------------------------------------------
+// Thread-per-channel lookups read 32 different tables per load instruction (32 L1 wavefronts each; measured 1 100 cycles per step).  With a
+// whole warp on ONE chain every lane keeps two thresholds and their K's, the piece index is popc(ballot(a >= thr)), K comes by shuffle:
+// no memory traffic at all inside the chain.  All 32 lanes pass the same x and get the same result.
+struct WrapLanes { float thr0, thr1, lo, hi; double K0, K1; int n; };
+
+__device__ __forceinline__ WrapLanes wrap_lanes_load(const WrapTable* __restrict__ t, int lane)
+{
+    static_assert(kWrapPieces <= 64, "two pieces per lane");
+    WrapLanes w;
+    w.n = t->n; w.lo = t->lo; w.hi = t->hi;
+    const unsigned inf = 0x7f800000u;
+    w.thr0 = lane < w.n ? t->thr[lane] : __uint_as_float(inf);
+    w.K0 = lane < w.n ? t->K[lane] : 0.0;
+    w.thr1 = lane + 32 < w.n ? t->thr[lane + 32] : __uint_as_float(inf);
+    w.K1 = lane + 32 < w.n ? t->K[lane + 32] : 0.0;
+    return w;
+}
+
+__device__ __forceinline__ float wrap_after_add_warp(float x, const WrapLanes& w)
+{
+    const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;
+    float a = fabsf(x);
+    if (a >= 16.f) {                                                    // every branch here is warp-uniform (same x, same table in all lanes)
+        if (w.n == 0 || !(a >= w.lo && a <= w.hi)) return wrap_phase_pm_pi(x);
+        int idx = __popc(__ballot_sync(0xffffffffu, a >= w.thr0)) - 1;
+        double K = __shfl_sync(0xffffffffu, w.K0, idx & 31);
+        if (w.n > 32) {
+            const int more = __popc(__ballot_sync(0xffffffffu, a >= w.thr1));
+            const double K1 = __shfl_sync(0xffffffffu, w.K1, (more - 1) & 31);
+            if (more > 0) K = K1;
+        }
+        a = (float)((double)a - K);                                     // exact; the float the loop would hold when it first drops below 16
+    }
+    while (a > PI_F32) a = __fsub_rn(a, TWO_PI_F32);
+    return (__float_as_uint(x) >> 31) ? -a : a;
+}
+
+#endif  // device (or emulated device) code
 
 }  // namespace csdrb

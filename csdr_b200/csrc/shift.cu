@@ -37,22 +37,40 @@ __device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
 // instead of ~1 200; the build costs about as much as thirty direct steps).  The last, shorter chunk has its own increment: direct.
 constexpr int kChainTableMin = 96;
 
-__global__ void shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                                         int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
+// chain of nchunks starting phases, one WARP per channel: steps with the full-chunk increment go through the register-resident wrap table
+// (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases are stored at a time.  `step(ph, len)` is the direct form.
+template <class Step>
+__device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, int c, int n, int chunk, int nchunks, float inc_full,
+                                           WrapTable* __restrict__ tables, Step step)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x;
+    const bool tab = tables != nullptr && nchunks > kChainTableMin;
+    WrapLanes w; w.n = 0; w.lo = w.hi = w.thr0 = w.thr1 = 0.f; w.K0 = w.K1 = 0.0;
+    if (tab) {
+        if (lane == 0) wrap_table_build(inc_full, tables + c);
+        __syncwarp();
+        w = wrap_lanes_load(tables + c, lane);
+    }
+    float ph = phase_io[c], mine = 0.f;
+    __syncwarp();                                                       // every lane has read the carried phase before lane 0 overwrites it
+    for (int k = 0; k < nchunks; k++) {
+        if ((k & 31) == lane) mine = ph;
+        if ((k & 31) == 31 || k == nchunks - 1) { if ((k & ~31) + lane <= k) dst[(k & ~31) + lane] = mine; }
+        const int len = min(chunk, n - k * chunk);
+        ph = (tab && len == chunk) ? wrap_after_add_warp(__fadd_rn(ph, inc_full), w) : step(ph, len);
+    }
+    if (lane == 0) phase_io[c] = ph;
+}
+
+__global__ void __launch_bounds__(32)
+shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                         int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
+{
+    const int c = blockIdx.x;
     if (c >= channels) return;
     const float rate2 = params[c].z;
-    float ph = phase_io[c];
-    const bool tab = tables != nullptr && nchunks > kChainTableMin;
-    const float inc = __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk);
-    if (tab) wrap_table_build(inc, tables + c);
-    for (int k = 0; k < nchunks; k++) {
-        chunk_phase[(long)c * nchunks + k] = ph;
-        const int len = min(chunk, n - k * chunk);
-        ph = (tab && len == chunk) ? wrap_after_add(__fadd_rn(ph, inc), tables + c) : advance_phase(ph, rate2, len);
-    }
-    phase_io[c] = ph;
+    chain_walk(phase_io, chunk_phase + (long)c * nchunks, c, n, chunk, nchunks, __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk), tables,
+               [rate2](float ph, int len) { return advance_phase(ph, rate2, len); });
 }
 
 constexpr int SH_TILE = 32;                       // samples per lane per sub-step
@@ -131,23 +149,16 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
 // (channel, call) walking its own shared-memory row.  A call only touches input_size/4 groups: the n%4 tail is not written.
 struct AddFastParams { float dsin[4], dcos[4], inc; };                 // = shift_addfast_data_t (libcsdr.h:189-194)
 
-__global__ void addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                                           int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
+__global__ void __launch_bounds__(32)
+addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
+                           int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x;
     if (c >= channels) return;
     const float inc = params[c].inc;
-    float ph = phase_io[c];
-    const bool tab = tables != nullptr && nchunks > kChainTableMin;
-    const float step = __fmul_rn((float)chunk, inc);
-    if (tab) wrap_table_build(step, tables + c);
-    for (int k = 0; k < nchunks; k++) {
-        chunk_phase[(long)c * nchunks + k] = ph;
-        const int len = min(chunk, n - k * chunk);
-        // starting_phase += input_size * d->phase_increment  (:428)
-        ph = (tab && len == chunk) ? wrap_after_add(__fadd_rn(ph, step), tables + c) : wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc)));
-    }
-    phase_io[c] = ph;
+    // starting_phase += input_size * d->phase_increment  (:428)
+    chain_walk(phase_io, chunk_phase + (long)c * nchunks, c, n, chunk, nchunks, __fmul_rn((float)chunk, inc), tables,
+               [inc](float ph, int len) { return wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc))); });
 }
 
 __global__ void __launch_bounds__(128)
@@ -405,7 +416,7 @@ int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, 
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+    shift_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
                                                                chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
@@ -445,7 +456,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addition bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+    shift_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
                                                                chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
@@ -464,7 +475,7 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addfast bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
     const AddFastParams* params = reinterpret_cast<const AddFastParams*>(d_params);
-    addfast_phase_chain_kernel<<<(channels + 31) / 32, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
+    addfast_phase_chain_kernel<<<channels, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);

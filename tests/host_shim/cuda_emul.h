@@ -11,7 +11,7 @@
 // cp.async.bulk = alignment-checked memcpy that completes an mbarrier, st.global.L1::no_allocate = alignment-checked store); launch
 // configurations the hardware would refuse (gridDim.y/z > 65535, > 1024 threads, > 227 KB shared) fail like they would on the GPU.
 // Not modelled: the memory model (fibers switch only at barriers, so a race that needs true concurrency can go unnoticed), occupancy and
-// register limits, alignment of plain vector loads (build with CUDA_EMUL_SANITIZE=1 for that), atomics, votes, clusters, tensor cores.
+// register limits, alignment of plain vector loads (build with CUDA_EMUL_SANITIZE=1 for that), atomics, partial-warp votes, clusters, tensor cores.
 #pragma once
 #define CSDRB_HOST_EMULATION 1
 #include <cmath>
@@ -184,6 +184,28 @@ template <typename T> T shfl_xor(T v, int lane_mask)
     return r;
 }
 
+// warp-wide exchange of one value per lane: every lane publishes, all meet, every lane reads what it wants, all meet again
+template <typename T, typename F> auto warp_exchange(T v, F pick)
+{
+    static_assert(sizeof(T) <= 16, "exchange payload");
+    State& s = st();
+    const int t = linear_tid(s.cur), w = t / 32, l = t % 32;
+    unsigned char* base = warp_scratch() + ((size_t)w * 32) * 16;
+    std::memcpy(base + (size_t)l * 16, &v, sizeof(T));
+    sync_warp();
+    auto r = pick(reinterpret_cast<const unsigned char*>(base), l);
+    sync_warp();
+    return r;
+}
+template <typename T> T shfl_idx(T v, int src)
+{
+    return warp_exchange(v, [src](const unsigned char* base, int) { T r; std::memcpy(&r, base + (size_t)(src & 31) * 16, sizeof(T)); return r; });
+}
+inline unsigned ballot(int pred)                 // full, converged warps only (what the kernels use): a lane that has exited would hang the barrier on the GPU too
+{
+    return warp_exchange(pred, [](const unsigned char* base, int) { unsigned m = 0; for (int i = 0; i < 32; i++) { int p; std::memcpy(&p, base + (size_t)i * 16, 4); if (p) m |= 1u << i; } return m; });
+}
+
 // ---- named barriers (bar.sync id, count) --------------------------------------------------------------------------------------------
 struct NamedBar { int arrived = 0; unsigned long generation = 0; };
 inline NamedBar& named_bar(int id) { static NamedBar b[16]; return b[id & 15]; }
@@ -231,6 +253,9 @@ static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); retur
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return ::cuda_emul::shfl_xor(v, lane_mask); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src_lane) { return ::cuda_emul::shfl_idx(v, src_lane); }
+static inline unsigned __ballot_sync(unsigned, int pred) { return ::cuda_emul::ballot(pred); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
 // ---- C++ models of the inline-PTX helpers of csdr_b200/csrc/common.cuh (which steps aside under CSDRB_HOST_EMULATION) ------------
 namespace csdrb {
@@ -263,6 +288,16 @@ static inline void st_na_f4(float4* p, float4 v)
     *p = v;
 }
 static inline void named_bar_sync(int id, int nthreads) { ::cuda_emul::named_sync(id, nthreads); }
+// cp.async: the copy happens at once (alignment checked like the hardware would); commit / wait are no-ops, so a MISSING wait goes unnoticed here
+static inline void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    if ((reinterpret_cast<uintptr_t>(smem_dst) & 15) || (reinterpret_cast<uintptr_t>(gmem_src) & 15)) {
+        std::fprintf(stderr, "cuda_emul: cp.async 16 needs 16-byte aligned addresses\n"); std::abort();
+    }
+    std::memcpy(smem_dst, gmem_src, 16);
+}
+static inline void cp_async_commit() {}
+template <int PENDING> static inline void cp_async_wait() {}
 }  // namespace csdrb
 
 // the CUDA runtime calls launchers and the C ABI make are stubbed in cuda_emul_runtime.cpp (one copy per emulated library)

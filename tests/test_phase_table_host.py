@@ -38,20 +38,21 @@ def test_every_float_of_the_window_for_large_increments(wrap):
     """coarse grids: the whole window is a few ten thousand floats -- all of them are compared"""
     rng = np.random.default_rng(0)
     total = 0; most = 0
-    for inc in np.concatenate([rng.uniform(600, 4000, 60), -rng.uniform(600, 4000, 20), [1024.0, 2048.0, 4096.0, 2047.9999, 3216.99]]).astype(np.float32):
+    for inc in np.concatenate([rng.uniform(600, 4000, 24), -rng.uniform(600, 4000, 8), [1024.0, 2048.0, 4096.0, 2047.9999, 3216.99]]).astype(np.float32):
         p, n = _check(wrap, inc, 1)
         assert p > 0, inc                                                  # these do get a table
         total += n; most = max(most, p)
-    assert total > 1_000_000 and most <= 48
+    assert total > 400_000 and most <= 48
 
 
 def test_strided_windows_across_all_binades(wrap):
     rng = np.random.default_rng(1)
     seen = set()
     for E in range(0, 20):
-        for inc in rng.uniform(2.0 ** E, 2.0 ** (E + 1), 12).astype(np.float32):
+        for inc in rng.uniform(2.0 ** E, 2.0 ** (E + 1), 8).astype(np.float32):
             ulps = 9.0 / np.spacing(np.float32(inc))
-            p, n = _check(wrap, inc, max(1, int(ulps // 40_000)))
+            budget = max(300.0, min(25_000.0, 1.5e7 / (float(inc) / 6.28 + 1.0)))     # the reference loop costs |x| / 2 pi iterations per value
+            p, n = _check(wrap, inc, max(1, int(ulps // budget)))
             seen.add((E, p > 0))
     assert (2, False) in seen and (9, True) in seen                        # tiny increments need no table, the common ones have one
 
