@@ -59,8 +59,7 @@ long table_check(float inc, long stride, int* pieces, long* checked, float* bad)
     };
     const float ainc = std::fabs(inc);
     float lo = t.n ? t.lo : (ainc > 4.5f ? ainc - 4.5f : 0.f), hi = t.n ? t.hi : ainc + 4.5f;
-    long k = 0;
-    for (float a = lo; a <= hi; a = std::nextafterf(a, INFINITY), k++) if (k % stride == 0) one(a);
+    for (unsigned u = __float_as_uint(lo), e = __float_as_uint(hi); u <= e; u += (unsigned)stride) one(__uint_as_float(u));   // positive floats: +1 in the bits = next float
     for (int i = 0; i < t.n; i++) {
         float a = t.thr[i];
         for (int d = 0; d < 3; d++) a = std::nextafterf(a, 0.f);
