@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.csdrb_fmdemod_quadri_bank_cf.argtypes = [vp, lg, vp, lg, it, it, vp, vp, vp]
     L.csdrb_stream_synchronize.argtypes = [vp]
     L.csdrb_fir_decimate_bank_cc_host.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, it]
+    L.csdrb_fir_decimate_bank_u8_cc.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, vp]
+    L.csdrb_fir_decimate_bank_u8_host.argtypes = [vp, lg, vp, lg, it, it, it, C.POINTER(C.c_float), it, it]
     L.csdrb_host_alloc.argtypes = [C.c_size_t]; L.csdrb_host_alloc.restype = vp
     L.csdrb_host_free.argtypes = [vp]
     sz = C.c_size_t
@@ -322,6 +324,38 @@ def fir_decimate_bank_cc_host(x: np.ndarray, decimation: int, taps: np.ndarray, 
     assert out.dtype == np.complex64 and out.shape[0] == ch and out.shape[1] >= n_out and out.strides[1] == 8
     rc = _check(lib().csdrb_fir_decimate_bank_cc_host(x.ctypes.data, x.strides[0] // 8, out.ctypes.data, out.strides[0] // 8, ch, n,
                                                       decimation, _fp(taps), taps.size, chunk_channels), "fir_decimate_bank_cc_host")
+    assert rc == n_out
+    return out[:, :n_out]
+
+
+def fir_decimate_bank_u8_cc(x, decimation: int, taps: np.ndarray, out=None):
+    """convert_u8_f | fir_decimate_cc fused: x [C, N, 2] uint8 CUDA tensor (interleaved I,Q; rows N samples apart or padded) -> [C, n_out] cf32."""
+    import torch
+    assert x.dtype == torch.uint8 and x.dim() == 3 and x.shape[2] == 2 and x.stride(2) == 1 and x.stride(1) == 2 and x.stride(0) % 2 == 0
+    ch, n = x.shape[0], x.shape[1]
+    taps = np.ascontiguousarray(taps, np.float32)
+    n_out = fir_out_len(n, decimation, taps.size)
+    if out is None:
+        out = torch.empty((ch, n_out + (n_out & 1)), dtype=torch.complex64, device=x.device)
+    orr, optr, ostride, och, on = _as_cf32_rows(out)
+    assert och == ch and on >= n_out
+    rc = _check(lib().csdrb_fir_decimate_bank_u8_cc(x.data_ptr(), x.stride(0) // 2, optr, ostride, ch, n, decimation, _fp(taps), taps.size, _stream()),
+                "fir_decimate_bank_u8_cc")
+    assert rc == n_out, (rc, n_out)
+    return out[:, :n_out]
+
+
+def fir_decimate_bank_u8_host(x: np.ndarray, decimation: int, taps: np.ndarray, out: np.ndarray | None = None, chunk_channels: int = 0):
+    """End-to-end call on HOST arrays with rtl_sdr-style input: x [C, N, 2] uint8 -> out [C, n_out] complex64 (2 bytes per sample over PCIe)."""
+    assert x.dtype == np.uint8 and x.ndim == 3 and x.shape[2] == 2 and x.strides[2] == 1 and x.strides[1] == 2
+    taps = np.ascontiguousarray(taps, np.float32)
+    ch, n = x.shape[0], x.shape[1]
+    n_out = fir_out_len(n, decimation, taps.size)
+    if out is None:
+        out = np.empty((ch, n_out), np.complex64)
+    assert out.dtype == np.complex64 and out.shape[0] == ch and out.shape[1] >= n_out and out.strides[1] == 8
+    rc = _check(lib().csdrb_fir_decimate_bank_u8_host(x.ctypes.data, x.strides[0] // 2, out.ctypes.data, out.strides[0] // 8, ch, n,
+                                                      decimation, _fp(taps), taps.size, chunk_channels), "fir_decimate_bank_u8_host")
     assert rc == n_out
     return out[:, :n_out]
 

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#include <sched.h>
 
 namespace csdrb {
 
@@ -59,7 +60,20 @@ struct HostCtx {
         return 0;
     }
 };
-static HostCtx g_ctx;
+// one workspace per device (a process may csdrb_set_device() between calls): the buffers, like the stream, belong to the device that was
+// current when they were made
+static HostCtx& host_ctx()
+{
+    static std::mutex mu;
+    static std::vector<HostCtx*> per_dev;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((size_t)dev >= per_dev.size()) per_dev.resize((size_t)dev + 1, nullptr);
+    if (!per_dev[(size_t)dev]) per_dev[(size_t)dev] = new HostCtx();
+    return *per_dev[(size_t)dev];
+}
+#define g_ctx (host_ctx())
 
 // CSDRB_TRACE=1: report at exit how many kernels this process launched (lets a caller verify that a
 // preloaded/linked libcsdr_b200 really did the work instead of some other libcsdr).
@@ -130,23 +144,43 @@ int csdrb_fir_decimate_bank_cc(const complexf* d_in, long in_stride, complexf* d
 {
     if (too_many_channels(channels, "fir_decimate bank")) return -1;
     if (!d_in || !d_out || !h_taps) { set_error("fir_decimate bank: null pointer"); return -1; }
-    // the generic kernel reads taps from device memory: keep a small per-process copy
-    static float* d_taps = nullptr; static int d_taps_cap = 0; static std::mutex mu;
-    const float* dt = nullptr;
+    // the generic kernel reads its taps from device memory: a stream-ordered allocation per call, so that two callers on different streams (or
+    // devices) never share a buffer that one of them is still reading
+    float* dt = nullptr;
     const bool fast = ((decimation == 10 && taps_length <= 200) || (decimation == 50 && taps_length <= 900)) && (in_stride % 2 == 0) &&
                       ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
     if (!fast) {
-        std::lock_guard<std::mutex> lk(mu);
-        if (taps_length > d_taps_cap) {
-            if (d_taps) CSDRB_CUDA(cudaFree(d_taps));
-            CSDRB_CUDA(cudaMalloc(&d_taps, sizeof(float) * (size_t)taps_length * 2));
-            d_taps_cap = taps_length * 2;
-        }
-        CSDRB_CUDA(cudaMemcpyAsync(d_taps, h_taps, sizeof(float) * (size_t)taps_length, cudaMemcpyHostToDevice, S(stream)));
-        dt = d_taps;
+        CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dt), sizeof(float) * (size_t)taps_length, S(stream)));
+        CSDRB_CUDA(cudaMemcpyAsync(dt, h_taps, sizeof(float) * (size_t)taps_length, cudaMemcpyHostToDevice, S(stream)));
+        CSDRB_CUDA(cudaStreamSynchronize(S(stream)));       // h_taps is the caller's (possibly pageable) memory: it may change once we return
     }
-    return counted(launch_fir_decimate_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride,
-                                            channels, input_size, decimation, h_taps, dt, 0, taps_length, variant, S(stream)));
+    const int rc = counted(launch_fir_decimate_bank(reinterpret_cast<const float2*>(d_in), in_stride, reinterpret_cast<float2*>(d_out), out_stride,
+                                                    channels, input_size, decimation, h_taps, dt, 0, taps_length, variant, S(stream)));
+    if (dt) CSDRB_CUDA(cudaFreeAsync(dt, S(stream)));
+    return rc;
+}
+
+// convert_u8_f | fir_decimate_cc in one launch for rtl_sdr-style input: d_in holds interleaved unsigned 8-bit I,Q (2 bytes per sample), in_stride counts
+// SAMPLES between channel rows.  Fused for the compiled tilings (d=10 T<=200, d=50 T<=900) when rows start on 16-byte boundaries (in_stride % 8 == 0);
+// any other geometry converts into a stream-ordered temporary and runs the cf32 bank.
+int csdrb_fir_decimate_bank_u8_cc(const unsigned char* d_in, long in_stride, complexf* d_out, long out_stride, int channels,
+                                  int input_size, int decimation, const float* h_taps, int taps_length, void* stream)
+{
+    if (too_many_channels(channels, "fir_decimate u8 bank")) return -1;
+    if (!d_in || !d_out || !h_taps) { set_error("fir_decimate u8 bank: null pointer"); return -1; }
+    int rc = launch_fir_decimate_bank_u8(d_in, in_stride, reinterpret_cast<float2*>(d_out), out_stride, channels, input_size, decimation, h_taps, taps_length, S(stream));
+    if (rc != -2) return counted(rc);
+    const long fstride = (input_size + 1) & ~1L;
+    float* tmp = nullptr;
+    CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), sizeof(float) * 2 * (size_t)fstride * channels, S(stream)));
+    for (int c = 0; c < channels; c++) {
+        rc = launch_convert_u8_f(d_in + (long)c * in_stride * 2, tmp + (long)c * fstride * 2, 2L * input_size, S(stream));
+        if (rc < 0) { cudaFreeAsync(tmp, S(stream)); return rc; }
+    }
+    g_launches += channels;
+    rc = csdrb_fir_decimate_bank_cc(reinterpret_cast<const complexf*>(tmp), fstride, d_out, out_stride, channels, input_size, decimation, h_taps, taps_length, -1, stream);
+    CSDRB_CUDA(cudaFreeAsync(tmp, S(stream)));
+    return rc;
 }
 
 int csdrb_fmdemod_quadri_bank_cf(const complexf* d_in, long in_stride, float* d_out, long out_stride, int channels,
@@ -187,47 +221,107 @@ struct HostBank {
         return 0;
     }
 };
-static HostBank g_hb;
+static HostBank& host_bank()                                     // one per device, like the Part A workspace
+{
+    static std::mutex mu;
+    static std::vector<HostBank*> per_dev;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((size_t)dev >= per_dev.size()) per_dev.resize((size_t)dev + 1, nullptr);
+    if (!per_dev[(size_t)dev]) per_dev[(size_t)dev] = new HostBank();
+    return *per_dev[(size_t)dev];
+}
+
+// Page-locked memory on the NUMA node the current device hangs off.  cudaHostAlloc places the pages where the calling thread runs; with one
+// process per GPU on a two-socket host half the ranks would otherwise stream their H2D traffic across the socket interconnect (SCALE_r01: e2e
+// efficiency 0.56 at 8 GPUs).  The thread is moved onto the device's node for the duration of the allocation (sysfs: the PCI device's
+// numa_node and that node's cpulist), then gets its old affinity back.  Any failure along the way just leaves the default placement.
+static bool cpus_of_device_node(cpu_set_t* set)
+{
+    int dev = 0; char bus[32] = "";
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return false;
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[128]; snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r"); if (!f) return false;
+    int node = -1; const int got = fscanf(f, "%d", &node); fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r"); if (!f) return false;
+    char list[4096] = ""; const bool ok = fgets(list, sizeof list, f) != nullptr; fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char* p = list; *p && *p != '\n';) {                         // "0-31,64-95"
+        char* e; long a = strtol(p, &e, 10); if (e == p) break; long b = a;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); n++; }
+        p = (*e == ',') ? e + 1 : e;
+    }
+    return n > 0;
+}
 }  // namespace csdrb
 extern "C" {
 
 void* csdrb_host_alloc(size_t bytes)
 {
+    cpu_set_t old_set, node_set;
+    const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    const bool moved = have_old && !(getenv("CSDRB_NO_NUMA") && getenv("CSDRB_NO_NUMA")[0] == '1') && cpus_of_device_node(&node_set) &&
+                       sched_setaffinity(0, sizeof node_set, &node_set) == 0;
     void* p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e == cudaSuccess && moved) memset(p, 0, bytes ? bytes : 1);  // first touch from the node, in case the driver only reserved the range
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
     if (e != cudaSuccess) { cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__); return nullptr; }
     return p;
 }
 void csdrb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int csdrb_fir_decimate_bank_cc_host(const complexf* h_in, long in_stride, complexf* h_out, long out_stride, int channels,
-                                    int input_size, int decimation, const float* h_taps, int taps_length, int chunk_channels)
+// in_bytes = bytes per input sample: 8 (cf32) or 2 (u8 IQ, converted inside the FIR kernel)
+static int fir_bank_host(const void* h_in, int in_bytes, long in_stride, complexf* h_out, long out_stride, int channels,
+                         int input_size, int decimation, const float* h_taps, int taps_length, int chunk_channels)
 {
     if (!h_in || !h_out || !h_taps || channels <= 0 || decimation <= 0 || taps_length <= 0) { set_error("fir_decimate host bank: bad argument"); return -1; }
     const int n_out = input_size >= taps_length ? (input_size - taps_length) / decimation + 1 : 0;
     if (n_out == 0) return 0;
-    std::lock_guard<std::mutex> lk(g_hb.mu);
-    const long dstride_in = (input_size + 1) & ~1L, dstride_out = (n_out + 1) & ~1L;
-    if (chunk_channels <= 0) {                                 // ~192 MiB of input per chunk keeps all three stages busy
+    HostBank& hb = host_bank();
+    std::lock_guard<std::mutex> lk(hb.mu);
+    const long dstride_in = in_bytes == 2 ? (input_size + 7) & ~7L : (input_size + 1) & ~1L, dstride_out = (n_out + 1) & ~1L;
+    if (chunk_channels <= 0) {                                 // ~192 MiB of cf32 input (48 MiB of u8) per chunk keeps all three stages busy
         chunk_channels = (int)((192L << 20) / (dstride_in * 8));
         if (chunk_channels < 1) chunk_channels = 1;
     }
     if (chunk_channels > channels) chunk_channels = channels;
-    if (int rc = g_hb.ensure((size_t)chunk_channels * dstride_in * 8, (size_t)chunk_channels * dstride_out * 8)) return rc;
+    if (int rc = hb.ensure((size_t)chunk_channels * dstride_in * in_bytes, (size_t)chunk_channels * dstride_out * 8)) return rc;
     int slot = 0;
     for (int c0 = 0; c0 < channels; c0 += chunk_channels, slot = (slot + 1) % HostBank::NS) {
         const int nc = channels - c0 < chunk_channels ? channels - c0 : chunk_channels;
-        cudaStream_t s = g_hb.st[slot];
-        CSDRB_CUDA(cudaMemcpy2DAsync(g_hb.din[slot], (size_t)dstride_in * 8, h_in + (long)c0 * in_stride, (size_t)in_stride * 8,
-                                     (size_t)input_size * 8, nc, cudaMemcpyHostToDevice, s));
-        int rc = csdrb_fir_decimate_bank_cc((const complexf*)g_hb.din[slot], dstride_in, (complexf*)g_hb.dout[slot], dstride_out, nc,
-                                            input_size, decimation, h_taps, taps_length, -1, s);
+        cudaStream_t s = hb.st[slot];
+        CSDRB_CUDA(cudaMemcpy2DAsync(hb.din[slot], (size_t)dstride_in * in_bytes, static_cast<const char*>(h_in) + (long)c0 * in_stride * in_bytes,
+                                     (size_t)in_stride * in_bytes, (size_t)input_size * in_bytes, nc, cudaMemcpyHostToDevice, s));
+        int rc = in_bytes == 2
+            ? csdrb_fir_decimate_bank_u8_cc((const unsigned char*)hb.din[slot], dstride_in, (complexf*)hb.dout[slot], dstride_out, nc, input_size, decimation, h_taps, taps_length, s)
+            : csdrb_fir_decimate_bank_cc((const complexf*)hb.din[slot], dstride_in, (complexf*)hb.dout[slot], dstride_out, nc, input_size, decimation, h_taps, taps_length, -1, s);
         if (rc < 0) return rc;
-        CSDRB_CUDA(cudaMemcpy2DAsync(h_out + (long)c0 * out_stride, (size_t)out_stride * 8, g_hb.dout[slot], (size_t)dstride_out * 8,
+        CSDRB_CUDA(cudaMemcpy2DAsync(h_out + (long)c0 * out_stride, (size_t)out_stride * 8, hb.dout[slot], (size_t)dstride_out * 8,
                                      (size_t)n_out * 8, nc, cudaMemcpyDeviceToHost, s));
     }
-    for (int k = 0; k < HostBank::NS; k++) CSDRB_CUDA(cudaStreamSynchronize(g_hb.st[k]));
+    for (int k = 0; k < HostBank::NS; k++) CSDRB_CUDA(cudaStreamSynchronize(hb.st[k]));
     return n_out;
+}
+
+int csdrb_fir_decimate_bank_cc_host(const complexf* h_in, long in_stride, complexf* h_out, long out_stride, int channels,
+                                    int input_size, int decimation, const float* h_taps, int taps_length, int chunk_channels)
+{
+    return fir_bank_host(h_in, 8, in_stride, h_out, out_stride, channels, input_size, decimation, h_taps, taps_length, chunk_channels);
+}
+
+// the same with rtl_sdr-style u8 IQ on the host side (2 bytes per sample over PCIe instead of 8): convert_u8_f | fir_decimate_cc, csdr-fm:41
+int csdrb_fir_decimate_bank_u8_host(const unsigned char* h_in, long in_stride, complexf* h_out, long out_stride, int channels,
+                                    int input_size, int decimation, const float* h_taps, int taps_length, int chunk_channels)
+{
+    return fir_bank_host(h_in, 2, in_stride, h_out, out_stride, channels, input_size, decimation, h_taps, taps_length, chunk_channels);
 }
 
 // =====================================================================================================

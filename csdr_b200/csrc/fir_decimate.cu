@@ -39,6 +39,8 @@ struct FirCfg {
     static constexpr size_t SMEM_IN = (size_t)IN_TILE * sizeof(float2);
     static constexpr size_t SMEM_RED = (size_t)OUT_TILE * sizeof(float2);
     static constexpr size_t SMEM_BYTES = SMEM_IN + SMEM_RED + 16;
+    static constexpr size_t SMEM_LUT = SMEM_BYTES;                   // u8 front end only: 256 floats behind the mbarrier
+    static constexpr size_t SMEM_BYTES_U8 = SMEM_BYTES + 256 * sizeof(float);
 };
 
 template <int TPAD>
@@ -68,9 +70,14 @@ __device__ __forceinline__ void fir_accumulate(const float2* __restrict__ base, 
     }
 }
 
-template <int D, int M, int R, int NPAIR, int MINB>
+// U8 = true: the input is rtl_sdr-style unsigned 8-bit IQ (2 bytes per sample, what csdr-fm:41 feeds convert_u8_f) and the conversion of
+// libcsdr.c:2363-2366 happens on the way into the tile: the bytes arrive by the same bulk copy (a quarter of the HBM / PCIe traffic of cf32)
+// at the tail of the tile buffer, every thread pulls its share into registers, and after a barrier writes the floats over the whole buffer.
+// The 256 possible values come from a table filled with the reference's own expression in double, so the samples the FIR sees are bit-identical
+// to convert_u8_f's output.
+template <int D, int M, int R, int NPAIR, int MINB, bool U8>
 __global__ void __launch_bounds__(NPAIR * 64, MINB)
-fir_bank_fast_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
+fir_bank_fast_kernel(const void* __restrict__ in_v, long in_stride, float2* __restrict__ out, long out_stride,
                      int n_in, int n_out, const __grid_constant__ FirTaps<D * M> taps)
 {
     using C = FirCfg<D, M, R, NPAIR>;
@@ -83,20 +90,50 @@ fir_bank_fast_kernel(const float2* __restrict__ in, long in_stride, float2* __re
     const int pair = warp >> 1, half = warp & 1;
     const int tile = blockIdx.x, ch = blockIdx.y;
     const long s0 = (long)tile * C::OUT_TILE * D;            // first input sample of the tile
-    const float2* src = in + (long)ch * in_stride + s0;
     int valid = n_in - s0 < C::IN_TILE ? (int)(n_in - s0) : C::IN_TILE;   // samples that exist
-    const int bulk_n = valid & ~1;
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar, (uint32_t)bulk_n * 8u);
-        if (bulk_n) bulk_g2s(xs, src, (uint32_t)bulk_n * 8u, bar);
+    if constexpr (U8) {
+        float* lut = reinterpret_cast<float*>(smem_raw + C::SMEM_LUT);
+        for (int i = tid; i < 256; i += C::THREADS) lut[i] = (float)((double)(float)i / (255 / 2.0) - 1.0);     // libcsdr.c:2365, same promotions
     }
-    for (int s = bulk_n + tid; s < C::IN_TILE; s += C::THREADS)         // ragged end of the stream: zero fill
-        xs[s] = s < valid ? src[s] : make_float2(0.f, 0.f);
-    mbar_wait(bar, 0);
     __syncthreads();
+    if constexpr (!U8) {
+        const float2* src = static_cast<const float2*>(in_v) + (long)ch * in_stride + s0;
+        const int bulk_n = valid & ~1;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)bulk_n * 8u);
+            if (bulk_n) bulk_g2s(xs, src, (uint32_t)bulk_n * 8u, bar);
+        }
+        for (int s = bulk_n + tid; s < C::IN_TILE; s += C::THREADS)         // ragged end of the stream: zero fill
+            xs[s] = s < valid ? src[s] : make_float2(0.f, 0.f);
+        mbar_wait(bar, 0);
+        __syncthreads();
+    } else {
+        // 2 bytes per sample; tile starts are multiples of OUT_TILE*D samples = a multiple of 16 bytes, row strides are checked by the launcher
+        const unsigned char* src = static_cast<const unsigned char*>(in_v) + ((long)ch * in_stride + s0) * 2;
+        unsigned char* stage = smem_raw + (((size_t)C::IN_TILE * 6) & ~(size_t)15);   // the last quarter of the float tile, 16-byte aligned for the bulk copy
+        const int bulk_b = (2 * valid) & ~15;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)bulk_b);
+            if (bulk_b) bulk_g2s(stage, src, (uint32_t)bulk_b, bar);
+        }
+        for (int b = bulk_b + tid; b < 2 * valid; b += C::THREADS) stage[b] = src[b];
+        mbar_wait(bar, 0);
+        __syncthreads();
+        constexpr int PER = (C::IN_TILE + C::THREADS - 1) / C::THREADS;
+        unsigned short v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) { const int sidx = tid + k * C::THREADS; v[k] = sidx < valid ? reinterpret_cast<const unsigned short*>(stage)[sidx] : (unsigned short)0; }
+        __syncthreads();                                                     // everyone holds its bytes: the floats may now overwrite the staging area
+        const float* lut = reinterpret_cast<const float*>(smem_raw + C::SMEM_LUT);
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int sidx = tid + k * C::THREADS;
+            if (sidx < C::IN_TILE) xs[sidx] = sidx < valid ? make_float2(lut[v[k] & 0xff], lut[v[k] >> 8]) : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+    }
 
     // ---- polyphase accumulate -------------------------------------------------------------------
     // The branch on `half` is warp-uniform; inside each arm every tap index depends only on the loop
@@ -158,20 +195,39 @@ fir_bank_generic_kernel(const float2* __restrict__ in, long in_stride, float2* _
 }
 
 // ---- host launchers ------------------------------------------------------------------------------
-template <int D, int M, int R, int NPAIR, int MINB>
-static int launch_fast(const float2* in, long in_stride, float2* out, long out_stride, int channels, int n_in,
+template <int D, int M, int R, int NPAIR, int MINB, bool U8 = false>
+static int launch_fast(const void* in, long in_stride, float2* out, long out_stride, int channels, int n_in,
                        int n_out, const float* h_taps, int T, cudaStream_t st)
 {
     using C = FirCfg<D, M, R, NPAIR>;
-    auto kern = fir_bank_fast_kernel<D, M, R, NPAIR, MINB>;
+    static_assert(!U8 || (C::OUT_TILE * D * 2) % 16 == 0, "u8 tiles must start on 16-byte boundaries");
+    auto kern = fir_bank_fast_kernel<D, M, R, NPAIR, MINB, U8>;
+    constexpr size_t smem = U8 ? C::SMEM_BYTES_U8 : C::SMEM_BYTES;
     // per call, not cached: the attribute is per device and a process may switch devices (it costs ~1 us)
-    CSDRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    CSDRB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FirTaps<D * M> tp;
     for (int k = 0; k < D * M; k++) { float h = k < T ? h_taps[k] : 0.f; tp.hh[k] = make_float2(h, h); }
     dim3 grid((n_out + C::OUT_TILE - 1) / C::OUT_TILE, channels);
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(in, in_stride, out, out_stride, n_in, n_out, tp);
+    kern<<<grid, C::THREADS, smem, st>>>(in, in_stride, out, out_stride, n_in, n_out, tp);
     CSDRB_CUDA(cudaGetLastError());
     return 0;
+}
+
+// u8 IQ in (2 bytes per sample, row stride in samples, a multiple of 8 so that rows start on 16-byte boundaries), cf32 out: convert_u8_f | fir_decimate_cc
+// in one kernel.  Returns outputs per channel, or -2 when (D, T) has no fused tiling -- the caller then converts and filters in two launches.
+int launch_fir_decimate_bank_u8(const unsigned char* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n_in,
+                                int D, const float* h_taps, int T, cudaStream_t st)
+{
+    if (channels <= 0 || D <= 0 || T <= 0 || !h_taps) { set_error("fir_decimate u8 bank: bad geometry (C=%d D=%d T=%d)", channels, D, T); return -1; }
+    const int n_out = n_in >= T ? (n_in - T) / D + 1 : 0;
+    if (n_out == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (in_stride % 8)) return -2;
+    int rc = -2;
+    if (D == 10 && T <= 80) rc = launch_fast<10, 8, 15, 2, 3, true>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st);
+    else if (D == 10 && T <= 200) rc = launch_fast<10, 20, 13, 2, 3, true>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st);
+    else if (D == 50 && T <= 900) rc = launch_fast<50, 18, 3, 2, 2, true>(d_in, in_stride, d_out, out_stride, channels, n_in, n_out, h_taps, T, st);
+    else return -2;
+    return rc < 0 ? rc : n_out;
 }
 
 int fir_bank_variant_count() { return 8; }

@@ -188,8 +188,19 @@ int csdrb_fir_bank_variants(void);
  * Page-locked host memory (csdrb_host_alloc) is needed for full PCIe rate. */
 int csdrb_fir_decimate_bank_cc_host(const complexf *h_in, long in_stride, complexf *h_out, long out_stride, int channels,
                                     int input_size, int decimation, const float *h_taps, int taps_length, int chunk_channels);
+/* page-locked host memory placed on the NUMA node of the current device (CSDRB_NO_NUMA=1: wherever the calling thread happens to run) */
 void *csdrb_host_alloc(size_t bytes);
 void  csdrb_host_free(void *p);
+
+/* convert_u8_f | fir_decimate_cc fused (libcsdr.c:2363-2366 + :528-549; the front of csdr-fm:41): the bank reads rtl_sdr-style interleaved unsigned 8-bit
+ * I,Q -- 2 bytes per sample instead of 8 over HBM and PCIe -- and converts on the way into the FIR tile with the reference's own expression, so the
+ * result equals convert_u8_f followed by fir_decimate_cc bit for bit in the conversion and like the cf32 bank in the filter.  in_stride counts
+ * SAMPLES between rows.  Fused tilings: d=10 T<=200, d=50 T<=900 with in_stride % 8 == 0 and a 16-byte aligned d_in; other geometries convert into a
+ * temporary and run the cf32 bank.  The _host form is the end-to-end call (chunked three-stream pipeline, see above). */
+int csdrb_fir_decimate_bank_u8_cc(const unsigned char *d_in, long in_stride, complexf *d_out, long out_stride, int channels,
+                                  int input_size, int decimation, const float *h_taps, int taps_length, void *stream);
+int csdrb_fir_decimate_bank_u8_host(const unsigned char *h_in, long in_stride, complexf *h_out, long out_stride, int channels,
+                                    int input_size, int decimation, const float *h_taps, int taps_length, int chunk_channels);
 
 /* K4 fmdemod_quadri_cf bank: d_last_in[c] is the sample preceding channel c's block (NULL = zeros),
  * d_last_out[c] receives its last sample (may be NULL; must not alias d_last_in). */

@@ -15,6 +15,7 @@ cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaDeviceGetPCIBusId(char*, int, int) { return cudaErrorInvalidDevice; }     // no PCI device: csdrb_host_alloc keeps the default placement
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return posix_memalign(p, 256, bytes ? bytes : 256) ? cudaErrorMemoryAllocation : cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMemset(void* p, int v, size_t bytes) { std::memset(p, v, bytes); return cudaSuccess; }

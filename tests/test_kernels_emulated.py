@@ -340,6 +340,34 @@ def test_k3_fir_decimate_bank(fir, oracle, D, T, n, variant):
             assert rel_rms(out[c, :n_out], want) < 2e-6, (c, rel_rms(out[c, :n_out], want))
 
 
+@pytest.mark.parametrize("D,T,n", [(10, 199, 40_007), (10, 79, 16_384 + 5), (50, 801, 30_011), (10, 199, 8321), (10, 199, 205)])
+def test_k3_u8_front_end_equals_convert_then_filter(fir, oracle, D, T, n):
+    """convert_u8_f | fir_decimate_cc in one kernel (csdr-fm:41): the samples the FIR sees are convert_u8_f's bit for bit, so the result must equal the cf32
+    bank's on the converted stream EXACTLY (same kernel, same summation order), and the oracle's within the usual bar"""
+    rng = np.random.default_rng(n)
+    ch = 3
+    stride = (n + 7) & ~7
+    u8 = _aligned((ch, stride, 2), np.uint8); u8[:] = rng.integers(0, 256, u8.shape, dtype=np.uint8); u8[:, n:] = 0x5A      # row padding must not matter
+    if n >= 256:
+        u8[0, :256, 0] = np.arange(256); u8[0, :256, 1] = np.arange(255, -1, -1)                                               # every code on both components
+    taps = oracle.firdes_lowpass_f(T, 0.5 / D)
+    n_out = (n - T) // D + 1
+    ostride = n_out + (n_out & 1)
+    out = _aligned((ch, ostride), np.complex64); out[:] = np.nan
+    fp = taps.ctypes.data_as(C.c_void_p)
+    rc = fir.emul_launch_fir_decimate_bank_u8(P(u8), stride, P(out), ostride, ch, n, D, fp, T)
+    assert rc == n_out, fir.emul_last_error()
+    f = np.stack([oracle.convert_u8_f(np.ascontiguousarray(u8[c, :n]).reshape(-1)).view(np.complex64) for c in range(ch)])
+    fs = n + (n & 1); xf = _aligned((ch, fs), np.complex64); xf[:] = 0; xf[:, :n] = f
+    ref = _aligned((ch, ostride), np.complex64)
+    assert fir.emul_launch_fir_decimate_bank(P(xf), fs, P(ref), ostride, ch, n, D, fp, fp, 0, T, -1) == n_out
+    assert np.array_equal(out[:, :n_out], ref[:, :n_out])
+    for c in range(ch):
+        assert rel_rms(out[c, :n_out], oracle.fir_decimate_cc(np.ascontiguousarray(f[c]), D, taps)) < 2e-6
+    # a row stride that is not a multiple of 8 samples has no fused path: the launcher says so (-2) and the C ABI falls back to two launches
+    assert fir.emul_launch_fir_decimate_bank_u8(P(u8), stride + 2, P(out), ostride, 1, n, D, fp, T) == -2
+
+
 # ------------------------------------------------------------------------------------------------------------------ fused DDC bank (config 4)
 @pytest.mark.parametrize("D,bw,demod", [(50, 0.005, 1), (10, 0.0201, 1), (10, 0.05, 0), (50, 0.005, 0)])
 def test_fused_ddc_bank_matches_the_unfused_chain(ddc, oracle, D, bw, demod):
