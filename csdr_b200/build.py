@@ -27,6 +27,19 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def declared_functions():
+    """every function name include/csdr_b200.h declares = the library's export list"""
+    import re
+    text = (ROOT / "include" / "csdr_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    names = set()
+    for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text):
+        if m.group(1) not in {"sizeof", "defined", "if", "while", "for", "return"}:
+            names.add(m.group(1))
+    return sorted(names)
+
+
 def _stale(target: Path, deps) -> bool:
     if not target.exists():
         return True
@@ -52,14 +65,20 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                 print(r.stderr)
         objs.append(obj)
     for src in sorted(HOST.glob("*.c")):
-        if src.name == "csdr_cli.c":
+        if src.name in ("csdr_cli.c", "bankd.c"):                      # programs ON TOP of the C ABI, not part of the library (bankd.c has a main())
             continue
         obj = OBJ / (src.stem + ".host.o")
         if force or _stale(obj, [src] + headers):
             subprocess.run(["gcc"] + GCC_FLAGS + ["-c", str(src), "-o", str(obj)], check=True)
         objs.append(obj)
     if force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB)] + [str(o) for o in objs] + ["-lm"]
+        # export exactly what include/csdr_b200.h declares (the drop-in is LD_PRELOADed into other programs: no stray `main`, no mangled internals)
+        vs = OBJ / "exports.map"
+        vs.write_text("{ global: " + " ".join(n + ";" for n in declared_functions()) + " local: *; };\n")
+        stale = OBJ / "bankd.host.o"
+        if stale.exists():
+            stale.unlink()
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", f"--version-script={vs}", "-o", str(LIB)] + [str(o) for o in objs] + ["-lm"]
         subprocess.run(cmd, check=True)
     cli_src = HOST / "csdr_cli.c"
     cli = PKG / "csdr"

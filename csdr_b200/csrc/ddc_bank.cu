@@ -264,8 +264,8 @@ struct DdcWalk {
     }
 };
 
-template <int D, int M, int CPL, bool DEMOD, bool PF>
-__global__ void __launch_bounds__(128, 3)
+template <int D, int M, int CPL, bool DEMOD>
+__global__ void __launch_bounds__(128)
 ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, int chunk, int nchunks,
                        const float3* __restrict__ params, const float2* __restrict__ seeds, int channels, int sets,
                        void* __restrict__ out_v, long out_stride, int n_out, int seg_outputs, int nsegs,
@@ -328,11 +328,8 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
         constexpr int JLO = decltype(jlo)::value, JHI = decltype(jhi)::value;
         constexpr int UU = (JLO == 0 && JHI == MP) ? U : 2;             // the steady-state body is unrolled deeper than the ramps
         const long base = (long)q * D;
-        // the wideband samples of a group are fetched while the previous group is being multiplied (r02 ncu: one exposed L1/L2 round trip per
-        // group was the largest stall after the FMA pipe itself); only the steady-state body bothers
-        constexpr bool PREFETCH = PF && UU >= 8;
-        float4 nx[UU / 2];
-        bool have = false;
+        // (fetching the next group's samples into registers while this one is multiplied was measured: 762 vs 724 us -- the extra registers cost more
+        // than the exposed L1 round trip)
 #pragma unroll 1
         for (int p0 = 0; p0 < D; p0 += UU) {
             if (left >= UU && base + p0 + UU <= n_in) {
@@ -340,14 +337,7 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
                 const float4* tp = staps + p0 * (MP / 2);
                 float4 cur[UU / 2];
 #pragma unroll
-                for (int e = 0; e < UU / 2; e++) cur[e] = (PREFETCH && have) ? nx[e] : __ldg(src + e);
-                if (PREFETCH) {
-                    have = p0 + UU < D && left >= 2 * UU && base + p0 + 2 * UU <= n_in;    // the next group takes this branch too
-                    if (have) {
-#pragma unroll
-                        for (int e = 0; e < UU / 2; e++) nx[e] = __ldg(src + UU / 2 + e);
-                    }
-                }
+                for (int e = 0; e < UU / 2; e++) cur[e] = __ldg(src + e);
 #pragma unroll
                 for (int e = 0; e < UU; e += 2) {
                     const float4 xx = cur[e / 2];
@@ -356,7 +346,6 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
                 }
                 left -= UU;
             } else {
-                have = false;
 #pragma unroll 1
                 for (int e = 0; e < UU; e++) checked(jlo, jhi, base + p0 + e, p0 + e);
             }
@@ -451,12 +440,9 @@ static int launch_fused(const float2* wide, int n_in, int offset, int chunk, int
     if (ver_env != 1) {
         const long warps = (long)nsegs * warps_per_seg;
         const unsigned ctas = (unsigned)((warps + 3) / 4);
-        static const bool pf = !(getenv("CSDRB_DDC_PF") && getenv("CSDRB_DDC_PF")[0] == '0');     // register prefetch of the next sample group
-#define CSDRB_DDC_LAUNCH2(CPLV, DM, PFV) ddc_bank_fused2_kernel<D, M, CPLV, DM, PFV><<<ctas, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, warps_per_seg, out, out_stride, n_out, seg, nsegs, last_in, last_out, tp)
-#define CSDRB_DDC_LAUNCH2B(CPLV, DM) do { if (pf) CSDRB_DDC_LAUNCH2(CPLV, DM, true); else CSDRB_DDC_LAUNCH2(CPLV, DM, false); } while (0)
-        if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH2B(2, true); else CSDRB_DDC_LAUNCH2B(2, false); }
-        else { if (demod) CSDRB_DDC_LAUNCH2B(1, true); else CSDRB_DDC_LAUNCH2B(1, false); }
-#undef CSDRB_DDC_LAUNCH2B
+#define CSDRB_DDC_LAUNCH2(CPLV, DM) ddc_bank_fused2_kernel<D, M, CPLV, DM><<<ctas, 128, 0, st>>>(wide, n_in, offset, chunk, nchunks, params, seeds, channels, warps_per_seg, out, out_stride, n_out, seg, nsegs, last_in, last_out, tp)
+        if (cpl == 2) { if (demod) CSDRB_DDC_LAUNCH2(2, true); else CSDRB_DDC_LAUNCH2(2, false); }
+        else { if (demod) CSDRB_DDC_LAUNCH2(1, true); else CSDRB_DDC_LAUNCH2(1, false); }
 #undef CSDRB_DDC_LAUNCH2
         CSDRB_CUDA(cudaGetLastError());
         return 0;

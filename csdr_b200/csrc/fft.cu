@@ -266,6 +266,10 @@ static SideStream* side_stream()
     auto* s = new SideStream();
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) { set_error("side stream: CUDA object creation failed"); delete s; return nullptr; }
+    // stream-ordered scratch (cudaMallocAsync) must not go back to the OS at every synchronisation: keep the pool's memory (r02: re-mapping 67 MB per
+    // fastddc call cost more than the kernels)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { unsigned long long keep = ~0ULL; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
     per_dev[dev] = s;
     return s;
 }

@@ -553,15 +553,17 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
         for (int v = 0; v < FOLD_BT; v++) x[v] = xs[v * FOLD_R];
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++) h[u] = hs[u * FOLD_R];
+        // acc += x*h = xr*(hr, hi) + xi*(-hi, hr): two packed FMAs per accumulator, scalar-broadcast x against h and against h swapped/negated
+        // (operand modifiers of FFMA2: no register moves).  Two sweeps over the tile, so the two FMAs of one accumulator sit 64 instructions apart.
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
-            for (int v = 0; v < FOLD_BT; v++) {
-                // acc += x*h = xr*(hr, hi) + xi*(-hi, hr): two packed FMAs, scalar-broadcast x against h and against h swapped/negated (operand
-                // modifiers of FFMA2: no register moves)
-                acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
+            for (int v = 0; v < FOLD_BT; v++) acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
+#pragma unroll
+        for (int u = 0; u < FOLD_CT; u++)
+#pragma unroll
+            for (int v = 0; v < FOLD_BT; v++)
                 acc[u][v] = ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
-            }
     }
     // /pre_decimation, and both half swaps (fastddc.c:143-150) folded into the destination index (r - offsetbin) mod M
     const int r = r0 + rl;

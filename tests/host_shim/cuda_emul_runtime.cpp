@@ -14,6 +14,8 @@ cudaError_t cudaMalloc(void** p, size_t bytes) { return posix_memalign(p, 256, b
 cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
+cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t*, int) { return cudaErrorNotSupported; }
+cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
 cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaDeviceGetPCIBusId(char*, int, int) { return cudaErrorInvalidDevice; }     // no PCI device: csdrb_host_alloc keeps the default placement
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return posix_memalign(p, 256, bytes ? bytes : 256) ? cudaErrorMemoryAllocation : cudaSuccess; }

@@ -22,6 +22,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"] and "256-channel fir_decimate_cc" in d["config"]["workload"]
+    # the two arms must describe the SAME configuration (the driver compares key sets): both take it from base_config()
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.base_config(1)
+    src = (ROOT / "bench.py").read_text()
+    assert src.count('"config": base_config(') == 2
 
 
 def test_non_zero_ranks_of_the_reference_arm_stay_silent():
