@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         stale = OBJ / "bankd.host.o"
         if stale.exists():
             stale.unlink()
-        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", f"--version-script={vs}", "-o", str(LIB)] + [str(o) for o in objs] + ["-lm"]
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", f"--version-script={vs}", "-o", str(LIB)] + [str(o) for o in objs] + ["-lm", "-ldl"]
         subprocess.run(cmd, check=True)
     cli_src = HOST / "csdr_cli.c"
     cli = PKG / "csdr"

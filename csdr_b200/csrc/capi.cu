@@ -752,6 +752,15 @@ int csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t* b, int channel, float rate)
     return 0;
 }
 
+// close the current NCO chunk at the next block's first sample without changing a rate (what a retune does to every channel of the bank): lets
+// several banks that share a stream stay chunk-aligned with each other when only one of them retunes (csrc/multi.cu)
+int csdrb_ddc_bank_rechunk(csdrb_ddc_bank_t* b)
+{
+    if (!b) { set_error("ddc bank rechunk: null pointer"); return -1; }
+    b->params_dirty = true;
+    return 0;
+}
+
 int csdrb_ddc_bank_offset(const csdrb_ddc_bank_t* b) { return b ? b->offset : -1; }
 
 int csdrb_ddc_bank_process(csdrb_ddc_bank_t* b, const complexf* d_wide, int input_size, void* d_out, long out_stride, void* stream)

@@ -245,8 +245,27 @@ void csdrb_ddc_bank_destroy(csdrb_ddc_bank_t *bank);
  * chunk at that sample for every channel (a shorter shift_addition_cc call, libcsdr_gpl.c:48-50) and starts a fresh chunk there, like the reference CLI
  * re-initialises between two buffers (csdr.c:897-925) */
 int  csdrb_ddc_bank_set_rate(csdrb_ddc_bank_t *bank, int channel, float rate);
+int  csdrb_ddc_bank_rechunk(csdrb_ddc_bank_t *bank);                               /* close the NCO chunk at the next block's first sample, rates unchanged */
 int  csdrb_ddc_bank_offset(const csdrb_ddc_bank_t *bank);                          /* samples of the current NCO chunk already consumed */
 int  csdrb_ddc_bank_process(csdrb_ddc_bank_t *bank, const complexf *d_wide, int input_size, void *d_out, long out_stride, void *stream);
+
+/* The same bank sliced over several GPUs of one node, driven from ONE process (what nmux + one process chain per channel do in the reference,
+ * nmux.cpp:246-353, ddcd_old.h:51-57): contiguous channel slices per device, the wideband block goes host -> devices[0] once and on to the other
+ * devices by ncclBroadcast (NCCL is loaded with dlopen on first use; a one-device bank never needs it).  submit() only enqueues (H2D, broadcast, slice
+ * kernels, D2H of the results) and returns a ticket; collect(ticket) waits for that block.  Up to two blocks may be in flight, so a caller that submits
+ * block k+1 before collecting block k has the broadcast of k+1 under the kernels of k.  h_wide / h_out of a submitted block belong to the library until
+ * its collect returns (page-locked memory from csdrb_host_alloc for full PCIe rate).  h_out is [channels][out_stride] floats (demod = 1) or complexf.
+ * Block contract as for csdrb_ddc_bank_process: a block consumes n_out*decimation samples, the caller re-presents the tail.  devices == NULL: 0..ndev-1. */
+typedef struct csdrb_multi_bank_s csdrb_multi_bank_t;
+csdrb_multi_bank_t *csdrb_multi_bank_create(int ndev, const int *devices, int channels, const float *h_rates, int decimation, const float *h_taps,
+                                            int taps_length, int demod, int chunk, int max_block);
+void csdrb_multi_bank_destroy(csdrb_multi_bank_t *bank);
+int  csdrb_multi_bank_devices(const csdrb_multi_bank_t *bank);
+int  csdrb_multi_bank_slice(const csdrb_multi_bank_t *bank, int index, int *device, int *first_channel, int *channels);
+int  csdrb_multi_bank_set_rate(csdrb_multi_bank_t *bank, int channel, float rate);
+int  csdrb_multi_bank_submit(csdrb_multi_bank_t *bank, const complexf *h_wide, int input_size, void *h_out, long out_stride);
+int  csdrb_multi_bank_collect(csdrb_multi_bank_t *bank, int ticket);
+int  csdrb_multi_bank_process_host(csdrb_multi_bank_t *bank, const complexf *h_wide, int input_size, void *h_out, long out_stride);   /* submit + collect */
 
 /* audio tail banks: hard limiter (elementwise) and the 1-pole de-emphasis IIR (d_last_io[c] = previous output of channel c) */
 int csdrb_limit_ff(const float *d_in, float *d_out, long n, float max_amplitude, void *stream);

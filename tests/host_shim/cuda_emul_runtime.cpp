@@ -8,15 +8,18 @@ extern "C" {
 extern "C" int cuda_emul_take_launch_error(void);
 cudaError_t cudaGetLastError(void) { return cuda_emul_take_launch_error() ? cudaErrorInvalidConfiguration : cudaSuccess; }
 cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int) { return cudaSuccess; }
-cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidDevice; }
+// CUDA_EMUL_DEVICES=n pretends to have n devices (all of them the host): enough to run the one-process multi-GPU host logic (csrc/multi.cu)
+static int emul_devices() { const char* e = std::getenv("CUDA_EMUL_DEVICES"); const int n = e ? std::atoi(e) : 1; return n > 0 ? n : 1; }
+static thread_local int emul_current_device = 0;
+cudaError_t cudaGetDeviceCount(int* n) { *n = emul_devices(); return cudaSuccess; }
+cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emul_devices()) return cudaErrorInvalidDevice; emul_current_device = d; return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t bytes) { return posix_memalign(p, 256, bytes ? bytes : 256) ? cudaErrorMemoryAllocation : (std::memset(*p, 0xFF, bytes), cudaSuccess); }
 cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
 cudaError_t cudaFreeAsync(void* p, cudaStream_t) { std::free(p); return cudaSuccess; }
 cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t*, int) { return cudaErrorNotSupported; }
 cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
-cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = emul_current_device; return cudaSuccess; }
 cudaError_t cudaDeviceGetPCIBusId(char*, int, int) { return cudaErrorInvalidDevice; }     // no PCI device: csdrb_host_alloc keeps the default placement
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return posix_memalign(p, 256, bytes ? bytes : 256) ? cudaErrorMemoryAllocation : cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
@@ -34,6 +37,7 @@ cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(std::malloc(8)); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
 const char* cudaGetErrorString(cudaError_t) { return "cuda_emul"; }
 }

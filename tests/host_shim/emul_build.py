@@ -170,7 +170,7 @@ def build_full(out_dir: Path):
                        check=True, capture_output=True)
         host.append(str(obj))
     lib = out_dir / "libcsdr_b200_emul.so"
-    r = subprocess.run(["g++", "-shared"] + SANITIZE + ["-o", str(lib)] + objs + [str(rt)] + host + ["-lm", "-lpthread", "-Wl,-Bsymbolic"], capture_output=True, text=True)
+    r = subprocess.run(["g++", "-shared"] + SANITIZE + ["-o", str(lib)] + objs + [str(rt)] + host + ["-lm", "-lpthread", "-ldl", "-Wl,-Bsymbolic"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-3000:])
     cli = out_dir / "csdr_emul"

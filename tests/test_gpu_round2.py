@@ -51,9 +51,9 @@ def test_u8_fir_bank_equals_convert_then_filter(gpu, oracle, D, T, n):
     taps = oracle.firdes_lowpass_f(T, 0.5 / D)
     d8 = _dev(u8)[:, :n]                                                  # rows padded to a multiple of 8 samples (16-byte row starts): the fused path
     y = gpu.fir_decimate_bank_u8_cc(d8, D, taps).cpu().numpy()
-    f = gpu.convert_u8_f(_dev(u8[:, :n].reshape(ch, -1)))
-    assert np.array_equal(f.cpu().numpy()[0], oracle.convert_u8_f(u8[0, :n].reshape(-1)))
-    y2 = gpu.fir_decimate_bank_cc(f.view(ch, n, 2), D, taps).cpu().numpy()
+    f = gpu.convert_u8_f(_dev(u8.reshape(ch, -1)))                        # the padded rows: an even row stride keeps the cf32 bank on the same (fast) kernel
+    assert np.array_equal(f.cpu().numpy()[0, : 2 * n], oracle.convert_u8_f(u8[0, :n].reshape(-1)))
+    y2 = gpu.fir_decimate_bank_cc(f.view(ch, stride, 2)[:, :n], D, taps).cpu().numpy()
     if (D, T) != (7, 33):
         assert np.array_equal(y, y2), "fused u8 path must equal convert_u8_f followed by the cf32 bank bit for bit"
     worst = 0.0
