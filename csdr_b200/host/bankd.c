@@ -13,8 +13,12 @@
  * first -- is process plumbing and is not reproduced; tests/test_gpu_zzz_bankd.py compares against the oracle run over the whole stream).
  *
  * usage: csdr-bankd [--in -|HOST:PORT] [--u8|--f32] [--decimation D] [--bw TRANSITION_BW] [--window W] [--block SAMPLES]
- *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N]  RATE:SINK [RATE:SINK ...]
+ *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N | --devices N0,N1,...]  RATE:SINK [RATE:SINK ...]
  *   RATE  shift_addition_cc rate (fraction of the wideband sample rate), SINK a path (file or FIFO) or tcp:PORT (one listener).
+ *   --devices: the channels are sliced over several GPUs of this node (csdrb_multi_bank_*: the block goes to the first device once and on to
+ *   the others by NCCL broadcast); raw discriminator output only (--tail none), one block of latency more (two blocks are kept in flight).
+ * Sinks never hold the stream up: a sink that cannot take a block within 200 ms loses the rest of that block (counted on stderr at exit), one
+ * that fails is dropped -- nmux's policy for slow clients (tsmpool.cpp:101-117, nmux.cpp:339-346).
  */
 #define _GNU_SOURCE
 #include "csdr_b200.h"
@@ -23,9 +27,11 @@
 #include <fcntl.h>
 #include <netdb.h>
 #include <netinet/in.h>
+#include <poll.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <string.h>
 #include <sys/socket.h>
 #include <sys/types.h>
@@ -34,7 +40,7 @@
 #define AGC_BLOCK 1024                                   /* fastagc_ff's default block (csdr.c:1382) */
 #define NFM_RATE 48000                                   /* the README graph's audio rate: 2.4 Msps / 50 */
 
-typedef struct { float rate; const char *sink; int fd; } channel_t;
+typedef struct { float rate; const char *sink; int fd; long dropped; } channel_t;
 
 static int die(const char *what)
 {
@@ -77,7 +83,8 @@ static int read_block(int fd, unsigned char *dst, size_t bytes)
         ssize_t got = read(fd, dst + have, bytes - have);
         if (got > 0) have += (size_t)got;
         else if (got == 0) return 0;
-        else if (errno != EINTR && errno != EAGAIN) return 0;
+        else if (errno == EAGAIN || errno == EWOULDBLOCK) { struct pollfd p = {fd, POLLIN, 0}; poll(&p, 1, 1000); }   /* a non-blocking input: wait, do not spin */
+        else if (errno != EINTR) return 0;
     }
     return 1;
 }
@@ -102,23 +109,90 @@ static int open_sink(const char *spec)
     if (fd < 0) { fprintf(stderr, "csdr-bankd: cannot open %s: %s\n", spec, strerror(errno)); exit(1); }
     return fd;
 }
+static void sink_nonblocking(int fd) { const int fl = fcntl(fd, F_GETFL, 0); if (fl >= 0) fcntl(fd, F_SETFL, fl | O_NONBLOCK); }
 
-/* a sink that fails (listener gone) is closed and skipped from then on, like nmux drops a client (nmux.cpp:339-346) */
+/* a sink that fails (listener gone) is closed and skipped from then on, like nmux drops a client (nmux.cpp:339-346); one that is merely slow gets
+ * 200 ms per block, then loses the rest of the block -- the other channels and the input never wait for it (nmux's readers are lossy too) */
 static void write_sink(channel_t *ch, const void *data, size_t bytes)
 {
     const unsigned char *p = data;
+    int budget_ms = 200;
     while (ch->fd >= 0 && bytes) {
         ssize_t put = write(ch->fd, p, bytes);
         if (put > 0) { p += put; bytes -= (size_t)put; }
-        else if (put < 0 && (errno == EINTR || errno == EAGAIN)) continue;
+        else if (put < 0 && errno == EINTR) continue;
+        else if (put < 0 && (errno == EAGAIN || errno == EWOULDBLOCK)) {
+            if (budget_ms <= 0) { ch->dropped += (long)bytes; return; }
+            struct pollfd pf = {ch->fd, POLLOUT, 0};
+            poll(&pf, 1, 20); budget_ms -= 20;
+        }
         else { fprintf(stderr, "csdr-bankd: sink %s closed\n", ch->sink); close(ch->fd); ch->fd = -1; }
     }
+}
+
+/* ---- several GPUs: csdrb_multi_bank, raw discriminator output ------------------------------------------------------------------------ */
+static int parse_devices(const char *list, int *dev, int max)
+{
+    int n = 0;
+    for (const char *p = list; *p && n < max;) {
+        char *e; long v = strtol(p, &e, 10);
+        if (e == p) break;
+        dev[n++] = (int)v;
+        p = (*e == ',') ? e + 1 : e;
+        if (*e && *e != ',') break;
+    }
+    return n;
+}
+
+static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *chan, int C, const float *rates, int D, const float *taps, int T, int block)
+{
+    csdrb_multi_bank_t *mb = csdrb_multi_bank_create(ndev, dev, C, rates, D, taps, T, 1, 1024, block);
+    if (!mb) die("cannot create the multi-GPU bank");
+    const int n_out = (block - T) / D + 1, consumed = n_out * D, keep = block - consumed;
+    float lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = (float)((float)i / (UCHAR_MAX / 2.0) - 1.0);      /* convert_u8_f, libcsdr.c:2365 */
+    complexf *h_wide[2] = {csdrb_host_alloc(sizeof(complexf) * (size_t)block), csdrb_host_alloc(sizeof(complexf) * (size_t)block)};
+    float *h_out[2] = {csdrb_host_alloc(sizeof(float) * (size_t)C * (size_t)n_out), csdrb_host_alloc(sizeof(float) * (size_t)C * (size_t)n_out)};
+    unsigned char *raw = malloc((size_t)block * 2);
+    if (!h_wide[0] || !h_wide[1] || !h_out[0] || !h_out[1] || !raw) die("out of memory");
+    long blocks = 0;
+    int ticket[2] = {-1, -1};
+    for (int first = 1;; first = 0) {
+        const int slot = (int)(blocks & 1), fresh = first ? block : consumed;
+        complexf *w = h_wide[slot];
+        /* this buffer's previous block (two submits ago) must be done before it is overwritten; its results go out meanwhile */
+        if (ticket[slot] >= 0) {
+            if (csdrb_multi_bank_collect(mb, ticket[slot]) < 0) die("csdrb_multi_bank_collect failed");
+            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out[slot] + (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out);
+            ticket[slot] = -1;
+        }
+        if (!first) memcpy(w, h_wide[slot ^ 1] + consumed, sizeof(complexf) * (size_t)keep);   /* the unconsumed tail (csdr.c:1172-1174) */
+        complexf *dst = w + (first ? 0 : keep);
+        int ok;
+        if (u8) {
+            ok = read_block(in_fd, raw, (size_t)fresh * 2);
+            if (ok) for (int i = 0; i < fresh; i++) { dst[i].i = lut[raw[2 * i]]; dst[i].q = lut[raw[2 * i + 1]]; }
+        } else ok = read_block(in_fd, (unsigned char *)dst, sizeof(complexf) * (size_t)fresh);
+        if (!ok) break;
+        ticket[slot] = csdrb_multi_bank_submit(mb, w, block, h_out[slot], n_out);
+        if (ticket[slot] < 0) die("csdrb_multi_bank_submit failed");
+        blocks++;
+    }
+    for (int k = 0; k < 2; k++) {                                  /* drain in submission order */
+        const int slot = (int)((blocks + k) & 1);
+        if (ticket[slot] < 0) continue;
+        if (csdrb_multi_bank_collect(mb, ticket[slot]) < 0) die("csdrb_multi_bank_collect failed");
+        for (int c = 0; c < C; c++) write_sink(&chan[c], h_out[slot] + (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out);
+    }
+    fprintf(stderr, "csdr-bankd: end of input after %ld blocks on %d devices, %ld kernel launches\n", blocks, ndev, csdrb_kernel_launches());
+    csdrb_multi_bank_destroy(mb);
+    return 0;
 }
 
 int main(int argc, char **argv)
 {
     const char *in_spec = "-", *tail = "nfm";
-    int u8 = 1, D = 50, block = 1 << 18, device = 0;
+    int u8 = 1, D = 50, block = 1 << 18, device = 0, ndev = 0, devs[64];
     float bw = 0.005f, limit = 1.0f, agc_ref = 1.0f;
     window_t window = WINDOW_HAMMING;
     channel_t *chan = calloc((size_t)argc, sizeof *chan);
@@ -137,16 +211,17 @@ int main(int argc, char **argv)
         else if (!strcmp(o, "--limit") && v) { limit = (float)atof(v); a++; }
         else if (!strcmp(o, "--agc-ref") && v) { agc_ref = (float)atof(v); a++; }
         else if (!strcmp(o, "--device") && v) { device = atoi(v); a++; }
+        else if (!strcmp(o, "--devices") && v) { ndev = parse_devices(v, devs, 64); if (ndev <= 0) die("--devices wants N0,N1,..."); a++; }
         else if (strchr(o, ':') && o[0] != '-' ) {
             char *end = NULL;
             chan[C].rate = strtof(o, &end);
             if (!end || *end != ':') die("channels are RATE:SINK");
-            chan[C].sink = end + 1; chan[C].fd = -1; C++;
+            chan[C].sink = end + 1; chan[C].fd = -1; chan[C].dropped = 0; C++;
         } else if (o[0] == '-' && strchr(o + 1, ':') && (o[1] == '.' || (o[1] >= '0' && o[1] <= '9'))) {      /* negative rate */
             char *end = NULL;
             chan[C].rate = strtof(o, &end);
             if (!end || *end != ':') die("channels are RATE:SINK");
-            chan[C].sink = end + 1; chan[C].fd = -1; C++;
+            chan[C].sink = end + 1; chan[C].fd = -1; chan[C].dropped = 0; C++;
         } else { fprintf(stderr, "csdr-bankd: unknown argument %s\n", o); return 2; }
     }
     const int nfm = !strcmp(tail, "nfm");
@@ -163,9 +238,19 @@ int main(int argc, char **argv)
     float *taps = malloc(sizeof(float) * (size_t)T);
     firdes_lowpass_f(taps, T, 0.5f / (float)D, window);
     if (block < 2 * T) die("--block is shorter than two filter lengths");
-    OK(csdrb_set_device(device));
     float *rates = malloc(sizeof(float) * (size_t)C);
     for (int c = 0; c < C; c++) rates[c] = chan[c].rate;
+    if (ndev > 0) {
+        if (nfm) die("--devices runs the raw discriminator bank: add --tail none");
+        if (ndev > C) die("more devices than channels");
+        for (int c = 0; c < C; c++) { chan[c].fd = open_sink(chan[c].sink); sink_nonblocking(chan[c].fd); }
+        const int fd = open_input(in_spec);
+        fprintf(stderr, "csdr-bankd: %d channels over %d devices, decimation %d, %d taps, %s input, blocks of %d samples\n", C, ndev, D, T, u8 ? "u8" : "f32", block);
+        const int rc = run_multi(fd, u8, devs, ndev, chan, C, rates, D, taps, T, block);
+        for (int c = 0; c < C; c++) { if (chan[c].dropped) fprintf(stderr, "csdr-bankd: sink %s lost %ld bytes (too slow)\n", chan[c].sink, chan[c].dropped); if (chan[c].fd >= 0) close(chan[c].fd); }
+        return rc;
+    }
+    OK(csdrb_set_device(device));
     csdrb_ddc_bank_t *bank = csdrb_ddc_bank_create(C, rates, D, taps, T, 1, 1024);   /* 1024 = the CLI's shift_addition_cc call size (csdr.c:911) */
     if (!bank) die("cannot create the bank");
     int Tn = 0;
@@ -201,20 +286,26 @@ int main(int argc, char **argv)
         (nfm && (!d_agc_in || !d_agc_out || !d_pcm || !d_agc_state || !d_agc_hist || !d_agc_scratch))) die("out of memory");
 
     /* sinks last: tcp: sinks block until their listener arrives */
-    for (int c = 0; c < C; c++) chan[c].fd = open_sink(chan[c].sink);
+    for (int c = 0; c < C; c++) { chan[c].fd = open_sink(chan[c].sink); sink_nonblocking(chan[c].fd); }
     const int in_fd = open_input(in_spec);
     fprintf(stderr, "csdr-bankd: %d channels, decimation %d, %d taps, %s input, blocks of %d samples, tail %s\n", C, D, T, u8 ? "u8" : "f32", block, tail);
 
     int cur = 0, keep = 0, a_have = 0, g_have = 0;
     long blocks = 0;
-    while (read_block(in_fd, h_in, in_bytes)) {
-        /* 1. the new block lands behind the unconsumed tail (keep is even because block and D are: 16-byte alignment holds) */
+    /* Every call presents exactly `block` samples: the unconsumed tail plus as many new ones as the previous call consumed -- how csdr.c:1172-1174
+     * feeds fir_decimate_cc.  A constant size keeps the bank's look-ahead pre-pass valid from block to block (a size that wobbles with
+     * block % D made it miss, and re-run inline, on most blocks). */
+    for (;;) {
+        const int fresh_n = block - keep;                            /* first block: everything; later: what the last call consumed (even) */
+        const size_t fresh_bytes = (size_t)fresh_n * (u8 ? 2 : 8);
+        if (!read_block(in_fd, h_in, fresh_bytes)) break;
+        /* 1. the new samples land behind the unconsumed tail (keep is even because block and D are: 16-byte alignment holds) */
         complexf *fresh = d_wide[cur] + keep;
         if (u8) {
-            OK(csdrb_copy_h2d(d_raw, h_in, in_bytes, stream));
-            OK(csdrb_convert_u8_f(d_raw, (float *)fresh, 2L * block, stream));
-        } else OK(csdrb_copy_h2d(fresh, h_in, in_bytes, stream));
-        const int n_in = keep + block;
+            OK(csdrb_copy_h2d(d_raw, h_in, fresh_bytes, stream));
+            OK(csdrb_convert_u8_f(d_raw, (float *)fresh, 2L * fresh_n, stream));
+        } else OK(csdrb_copy_h2d(fresh, h_in, fresh_bytes, stream));
+        const int n_in = block;
 
         /* 2. shift | fir_decimate | fmdemod for every channel, new discriminator samples behind the FIR's carried inputs */
         const int n_out = csdrb_ddc_bank_process(bank, d_wide[cur], n_in, d_demod + a_have, ds, stream);
@@ -263,7 +354,7 @@ int main(int argc, char **argv)
     }
     OK(csdrb_stream_synchronize(stream));
     fprintf(stderr, "csdr-bankd: end of input after %ld blocks, %ld kernel launches\n", blocks, csdrb_kernel_launches());
-    for (int c = 0; c < C; c++) if (chan[c].fd >= 0) close(chan[c].fd);
+    for (int c = 0; c < C; c++) { if (chan[c].dropped) fprintf(stderr, "csdr-bankd: sink %s lost %ld bytes (too slow)\n", chan[c].sink, chan[c].dropped); if (chan[c].fd >= 0) close(chan[c].fd); }
     csdrb_ddc_bank_destroy(bank);
     csdrb_stream_destroy(stream);
     return 0;

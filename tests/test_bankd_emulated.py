@@ -20,7 +20,14 @@ def bankd(tmp_path_factory):
     if not emul_build.available():
         pytest.skip("needs g++ and the CUDA toolkit headers")
     lib, _cli = emul_build.build_full_once(tmp_path_factory)
-    return str(lib.parent / "csdr-bankd_emul")
+    # --devices 0,1 in the CPU tier: two pretend devices and a memcpy stand-in for NCCL (tests/host_shim/fake_nccl.c), inherited by the daemon
+    import os, subprocess
+    fake = tmp_path_factory.mktemp("fake_nccl_d") / "libfake_nccl.so"
+    subprocess.run(["gcc", "-O1", "-fPIC", "-shared", str(ROOT / "tests" / "host_shim" / "fake_nccl.c"), "-o", str(fake)], check=True)
+    os.environ["CUDA_EMUL_DEVICES"] = "2"; os.environ["CSDRB_NCCL_LIB"] = str(fake)
+    g.MULTI_DEVICES = lambda: ["0", "0,1"]
+    yield str(lib.parent / "csdr-bankd_emul")
+    del os.environ["CUDA_EMUL_DEVICES"], os.environ["CSDRB_NCCL_LIB"]
 
 
 test_nfm_bank_equals_the_readme_graph_per_channel = g.test_nfm_bank_equals_the_readme_graph_per_channel

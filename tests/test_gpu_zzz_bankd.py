@@ -47,6 +47,23 @@ def oracle_channel(oracle, wide_c64, rate, taps, tail):
     return oracle.convert_f_s16(oracle.fastagc_ff(oracle.deemphasis_nfm_ff(oracle.limit_ff(d, 1.0), GOLD["nfm_taps_48000"]), 1024, 1.0))
 
 
+def MULTI_DEVICES():
+    """device lists for the daemon's --devices mode: one device always; two when the box has them"""
+    try:
+        import torch
+        return ["0", "0,1"] if torch.cuda.device_count() >= 2 else ["0"]
+    except Exception:
+        return ["0"]
+
+
+def stream_used(oracle, n, block):
+    """samples of an n-sample stream the daemon processes: the first call takes `block`, every later one as many new samples as the previous call
+    consumed (constant presented size, csdr.c:1172-1174); a partial last read is dropped"""
+    T = oracle.firdes_filter_len(BW)
+    consumed = ((block - T) // D + 1) * D
+    return block + ((n - block) // consumed) * consumed if n >= block else 0
+
+
 def run(bankd, args, data, sinks, timeout=300):
     cmd = [bankd] + args + [f"{r}:{p}" for r, p in zip(RATES, sinks)]
     r = subprocess.run(cmd, input=data, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
@@ -58,7 +75,7 @@ def run(bankd, args, data, sinks, timeout=300):
 def test_nfm_bank_equals_the_readme_graph_per_channel(bankd, oracle, tmp_path, block):
     n = 6 * 262144
     u8 = wideband_u8(n)
-    used = (n // block) * block                                           # a partial last block is dropped
+    used = stream_used(oracle, n, block)
     sinks = [tmp_path / f"ch{k}.s16" for k in range(len(RATES))]
     run(bankd, ["--block", str(block)], u8.tobytes(), sinks)
     wide = oracle.convert_u8_f(u8[:2 * used]).view(np.complex64)
@@ -77,11 +94,19 @@ def test_raw_discriminator_output_and_f32_input(bankd, oracle, tmp_path):
     sinks = [tmp_path / f"ch{k}.f32" for k in range(len(RATES))]
     run(bankd, ["--tail", "none", "--f32", "--block", "131072"], wide.tobytes(), sinks)
     taps = oracle.firdes_lowpass_f(oracle.firdes_filter_len(BW), 0.5 / D)
+    used = stream_used(oracle, n, 131072)
     from oracle.pyoracle import rel_rms
     for rate, path in zip(RATES, sinks):
         got = np.fromfile(path, np.float32)
-        want = oracle_channel(oracle, wide, rate, taps, "none")
-        assert got.size == want.size and rel_rms(got, want) < 1e-5, rate
+        want = oracle_channel(oracle, wide[:used], rate, taps, "none")
+        assert got.size == want.size and rel_rms(got, want) < 1e-5, (rate, got.size, want.size)
+    # the same stream through the one-process multi-GPU bank (csdrb_multi_bank_*): on one device it must give the same bytes (no NCCL involved),
+    # with u8 input converted on the host; MULTI_DEVICES lists what the box offers (the CPU tier pretends to have two)
+    for devices in MULTI_DEVICES():
+        msinks = [tmp_path / f"m{devices.replace(',', '_')}_{k}.f32" for k in range(len(RATES))]
+        run(bankd, ["--tail", "none", "--u8", "--block", "131072", "--devices", devices], u8.tobytes(), msinks)
+        for a, b in zip(sinks, msinks):
+            assert a.read_bytes() == b.read_bytes(), devices
 
 
 def test_tcp_ingest_and_tcp_sink(bankd, tmp_path):
