@@ -65,6 +65,16 @@ class SharedInputBank:
         self.pending = None                      # (work handle, buffer index) of the broadcast in flight
         self.turn = 0
 
+    def _more(self, have_block: bool) -> bool:
+        """The SOURCE decides whether another block follows: one int travels ahead of every block (control plane), the other ranks follow it.
+        Without it a rank whose own iterable is shorter, longer or empty would leave the others waiting in a broadcast forever."""
+        if self.shard.world == 1:
+            return have_block
+        import torch
+        flag = torch.tensor([1 if have_block else 0], dtype=torch.int32, device=self.buffers[0].device)
+        self.dist.broadcast(flag, src=self.src)
+        return bool(flag.item())
+
     def _post(self, block):
         buf = self.buffers[self.turn]
         if self.shard.rank == self.src:
@@ -74,23 +84,24 @@ class SharedInputBank:
         self.turn ^= 1
 
     def run(self, blocks):
-        """`blocks`: iterable of wideband blocks (only read on the source rank; other ranks may pass None items).
-        Yields this rank's result per block, in order."""
-        it = iter(blocks)
-        first = next(it, None)
-        if first is None and self.shard.rank == self.src:
-            return
-        self._post(first)
-        for nxt in it:
+        """`blocks`: iterable of wideband blocks, read on the source rank only (the other ranks may pass anything, e.g. None: how many blocks
+        there are is the source's call).  Yields this rank's result per block, in order."""
+        it = iter(blocks) if self.shard.rank == self.src else iter(())
+        nxt = next(it, None)
+        if not self._more(nxt is not None):
+            return                                   # empty stream: every rank returns
+        self._post(nxt)
+        while True:
+            nxt = next(it, None)
+            more = self._more(nxt is not None)
             work, idx = self.pending
             if work is not None:
                 work.wait()
-            self._post(nxt)                      # block k+1 starts moving ...
+            if more:
+                self._post(nxt)                      # block k+1 starts moving ...
             yield self.compute(self.buffers[idx], self.shard)   # ... while block k is processed
-        work, idx = self.pending
-        if work is not None:
-            work.wait()
-        yield self.compute(self.buffers[idx], self.shard)
+            if not more:
+                return
 
 
 def gather_counts(shard: BankShard, local_count: int) -> list[int]:

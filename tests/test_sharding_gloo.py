@@ -62,7 +62,9 @@ def _worker(rank, world, port, q):
             return np.stack(out) if out else np.zeros((0, 0), np.complex64)
 
         bank = SharedInputBank(shard, lambda: torch.zeros(N, dtype=torch.complex64), compute, src=0)
-        feed = [torch.from_numpy(b) for b in blocks] if rank == 0 else [None] * NBLK
+        # only the SOURCE's iterable counts: rank 1 passes a wrong-length one on purpose (round 1 deadlocked on that), and an empty stream ends at once
+        assert list(bank.run([] if rank == 0 else [None] * 3)) == []
+        feed = [torch.from_numpy(b) for b in blocks] if rank == 0 else [None] * (NBLK + 2)
         results = list(bank.run(feed))
         counts = gather_counts(shard, sum(r.shape[0] for r in results))
         q.put((rank, shard.start, shard.count, [r.copy() for r in results], counts))
