@@ -119,6 +119,15 @@ def lib() -> C.CDLL:
     L.csdrb_ddc_bank_set_rate.argtypes = [vp, it, C.c_float]
     L.csdrb_ddc_bank_offset.argtypes = [vp]
     L.csdrb_ddc_bank_process.argtypes = [vp, vp, it, vp, lg, vp]
+    L.csdrb_ddc_bank_rechunk.argtypes = [vp]
+    L.csdrb_multi_bank_create.argtypes = [it, C.POINTER(C.c_int), it, C.POINTER(C.c_float), it, C.POINTER(C.c_float), it, it, it, it]; L.csdrb_multi_bank_create.restype = vp
+    L.csdrb_multi_bank_destroy.argtypes = [vp]
+    L.csdrb_multi_bank_devices.argtypes = [vp]
+    L.csdrb_multi_bank_slice.argtypes = [vp, it, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.csdrb_multi_bank_set_rate.argtypes = [vp, it, C.c_float]
+    L.csdrb_multi_bank_submit.argtypes = [vp, vp, it, vp, lg]
+    L.csdrb_multi_bank_collect.argtypes = [vp, it]
+    L.csdrb_multi_bank_process_host.argtypes = [vp, vp, it, vp, lg]
     L.csdrb_apply_window_rows_c.argtypes = [vp, vp, vp, it, lg, vp]
     L.csdrb_logpower_cf.argtypes = [vp, vp, lg, C.c_float, vp]
     L.csdrb_accumulate_power_cf.argtypes = [vp, vp, lg, vp]
@@ -969,6 +978,53 @@ class DdcBank:
     def close(self):
         if getattr(self, "h", None):
             lib().csdrb_ddc_bank_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiBank:
+    """One process, several GPUs (csdrb_multi_bank_*): the shared-input DDC/NFM bank in contiguous channel slices over `devices`, the wideband block
+    broadcast from devices[0] with NCCL.  Host (ideally pinned) numpy buffers in and out; submit()/collect() pipeline two blocks."""
+
+    def __init__(self, devices, rates, decimation: int, taps: np.ndarray, demod: bool = True, chunk: int = 1024, max_block: int = 1 << 21):
+        self.rates = np.ascontiguousarray(np.atleast_1d(rates), np.float32)
+        self.taps = np.ascontiguousarray(taps, np.float32)
+        self.decimation, self.demod, self.channels = decimation, demod, self.rates.size
+        devs = (C.c_int * len(devices))(*devices)
+        self.h = lib().csdrb_multi_bank_create(len(devices), devs, self.channels, _fp(self.rates), decimation, _fp(self.taps), self.taps.size, 1 if demod else 0,
+                                               chunk, max_block)
+        if not self.h:
+            raise CsdrB200Error(f"csdrb_multi_bank_create: {lib().csdrb_last_error().decode()}")
+
+    def slices(self):
+        out = []
+        for i in range(lib().csdrb_multi_bank_devices(self.h)):
+            d, c0, n = C.c_int(), C.c_int(), C.c_int()
+            _check(lib().csdrb_multi_bank_slice(self.h, i, C.byref(d), C.byref(c0), C.byref(n)), "multi_bank_slice")
+            out.append((d.value, c0.value, n.value))
+        return out
+
+    def submit(self, wide: np.ndarray, out: np.ndarray) -> int:
+        assert wide.dtype == np.complex64 and wide.ndim == 1 and out.ndim == 2 and out.shape[0] == self.channels and out.strides[1] == out.itemsize
+        assert out.dtype == (np.float32 if self.demod else np.complex64)
+        return _check(lib().csdrb_multi_bank_submit(self.h, wide.ctypes.data, wide.size, out.ctypes.data, out.strides[0] // out.itemsize), "multi_bank_submit")
+
+    def collect(self, ticket: int) -> int:
+        return _check(lib().csdrb_multi_bank_collect(self.h, ticket), "multi_bank_collect")
+
+    def process(self, wide: np.ndarray, out: np.ndarray) -> int:
+        return self.collect(self.submit(wide, out))
+
+    def set_rate(self, channel: int, rate: float):
+        _check(lib().csdrb_multi_bank_set_rate(self.h, channel, rate), "multi_bank_set_rate")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().csdrb_multi_bank_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

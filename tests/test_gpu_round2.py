@@ -196,3 +196,45 @@ def test_ddc_bank_retune_keeps_the_phase_continuous(gpu, oracle):
         want2 = oracle.fir_decimate_cc(sh2, D, taps)
         e2 = _rel(o2[c], want2)
         assert e2 < 2e-6, f"channel {c} after the retune: rel-RMS {e2:.3e} (a phase jump at the retune sample would show as O(1))"
+
+
+# ------------------------------------------------------------------------------------------ one process, several GPUs (csdrb_multi_bank_*)
+def test_multi_gpu_bank_equals_the_single_gpu_bank(gpu, oracle):
+    """The sharded bank against the unsharded one (no multi-GPU parity on GPUs): contiguous channel slices per device, the wideband block
+    broadcast with NCCL from device 0, two blocks in flight.  One device always (no NCCL involved); two when the box has them."""
+    D, bw = 50, 0.005
+    T = oracle.firdes_filter_len(bw)
+    taps = oracle.firdes_lowpass_f(T, 0.5 / D)
+    Cn, N, NB = 24, 200_000, 4
+    rates = np.linspace(-0.44, 0.43, Cn).astype(np.float32)
+    rng = np.random.default_rng(21)
+    n_out = (N - T) // D + 1
+    adv = n_out * D
+    stream = _cplx(rng, adv * (NB - 1) + N, amp=0.4)
+    ref_bank = gpu.DdcBank(rates, D, taps, demod=True, chunk=1024)
+    want = np.concatenate([ref_bank.process(_dev(stream[k * adv:k * adv + N])).cpu().numpy() for k in range(NB)], axis=1)
+    ref_bank.close()
+    device_sets = [[0]] + ([[0, 1]] if torch.cuda.device_count() >= 2 else [])
+    for devs in device_sets:
+        mb = gpu.MultiBank(devs, rates, D, taps, demod=True, chunk=1024, max_block=N)
+        assert sum(n for _, _, n in mb.slices()) == Cn and [d for d, _, _ in mb.slices()] == devs
+        wide = [gpu.PinnedArray((N,), np.complex64) for _ in range(2)]
+        outs = [gpu.PinnedArray((Cn, n_out), np.float32) for _ in range(NB)]
+        tickets = []
+        for k in range(NB):
+            if k >= 2:
+                assert mb.collect(tickets[k - 2]) == n_out             # frees wide[k & 1]
+            wide[k & 1].array[:] = stream[k * adv:k * adv + N]
+            tickets.append(mb.submit(wide[k & 1].array, outs[k].array))
+        for t in tickets[-2:]:
+            assert mb.collect(t) == n_out
+        got = np.concatenate([o.array for o in outs], axis=1)
+        assert np.array_equal(got, want), f"devices {devs}: sharded bank differs from the unsharded one"
+        mb.close()
+        [w.close() for w in wide]; [o.close() for o in outs]
+    # one channel against the reference chain itself
+    c = 5
+    sh, _ = oracle.shift_addition_cc(stream, float(rates[c]), 0.0, 1024)
+    ref = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0][:want.shape[1]]
+    e = _rel(want[c], ref)
+    assert e < TOL, f"rel-RMS {e:.3e}"
