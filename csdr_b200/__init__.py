@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.csdrb_fractional_decimator_bank_ff.argtypes = [vp, lg, vp, lg, it, it, C.c_float, it, vp, it, vp, vp, sz, vp]
     L.csdrb_fastagc_bank_scratch_bytes.argtypes = [it, it]; L.csdrb_fastagc_bank_scratch_bytes.restype = sz
     L.csdrb_fastagc_bank_ff.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp, vp, vp, sz, vp]
+    L.csdrb_fastagc_bank_f_s16.argtypes = [vp, lg, vp, lg, it, it, it, C.c_float, vp, vp, vp, sz, vp]
     L.csdrb_fft_c2c_batch.argtypes = [vp, lg, vp, lg, it, it, it, vp]
     L.csdrb_bandpass_fir_fft_bank_cc.argtypes = [vp, lg, vp, lg, it, it, it, it, vp, lg, vp, vp]
     L.csdrb_ddc_bank_scratch_bytes.argtypes = [it, it, it, it]; L.csdrb_ddc_bank_scratch_bytes.restype = sz
@@ -776,6 +777,21 @@ def fastagc_bank_ff(x, block: int = 1024, reference: float = 1.0, state=None, hi
     scratch = _scratch(lib().csdrb_fastagc_bank_scratch_bytes(ch, nblocks), x.device)
     _check(lib().csdrb_fastagc_bank_ff(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, block, nblocks, reference,
                                        state.data_ptr(), hist.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "fastagc_bank_ff")
+    return out, state, hist
+
+
+def fastagc_bank_f_s16(x, block: int = 1024, reference: float = 1.0, state=None, hist=None):
+    """fastagc_ff | convert_f_s16 in one pass: x [C, nblocks*block] float32 -> int16 of the same shape; returns (y, state, hist)."""
+    import torch
+    assert x.dtype == torch.float32 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    ch, n = x.shape
+    nblocks = n // block
+    out = torch.empty((ch, nblocks * block), dtype=torch.int16, device=x.device)
+    state = torch.zeros((ch, 3), dtype=torch.float32, device=x.device) if state is None else state
+    hist = torch.zeros((ch, 2, block), dtype=torch.float32, device=x.device) if hist is None else hist
+    scratch = _scratch(lib().csdrb_fastagc_bank_scratch_bytes(ch, nblocks), x.device)
+    _check(lib().csdrb_fastagc_bank_f_s16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), ch, block, nblocks, reference,
+                                          state.data_ptr(), hist.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()), "fastagc_bank_f_s16")
     return out, state, hist
 
 

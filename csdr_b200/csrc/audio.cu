@@ -103,6 +103,10 @@ __global__ void fracdec_segments_kernel(FracDecState* __restrict__ state, FdSeg*
     nsegs[c] = ns;
 }
 
+// PTS > 0: the point count is a compile-time constant (the CLI default is 12, libcsdr.c:717 / csdr.c:1476): the 16 x 16 predicated loop nest of the
+// generic form (512 multiplies and 16 divisions per output, most of them masked) becomes PTS*(PTS-1) multiplies, PTS divisions and constant
+// denominators -- same operations in the same order on the live points, so the result is unchanged bit for bit.
+template <int PTS>
 __global__ void __launch_bounds__(128)
 fracdec_interp_seg_kernel(const float* __restrict__ in, long in_stride, float* __restrict__ out, long out_stride,
                           const FracDecState* __restrict__ state, const FdSeg* __restrict__ segs, const int* __restrict__ nsegs,
@@ -125,7 +129,19 @@ fracdec_interp_seg_kernel(const float* __restrict__ in, long in_stride, float* _
         const int low = (int)ceilf(where) - 1;
         const float xw = __fsub_rn(where, (float)low);
         float acc = 0.f;
-        if (!taps && num_poly_points <= 16) {
+        if (PTS > 0) {
+            float pts[PTS > 0 ? PTS : 1], dxj[PTS > 0 ? PTS : 1];
+#pragma unroll
+            for (int w = 0; w < PTS; w++) { pts[w] = x[low + w]; dxj[w] = __fsub_rn(xw, (float)(1 - PTS / 2 + w)); }
+#pragma unroll
+            for (int wi = 0; wi < PTS; wi++) {
+                float coef = 1.f, den = 1.f;
+#pragma unroll
+                for (int wj = 0; wj < PTS; wj++)
+                    if (wj != wi) { coef = __fmul_rn(coef, dxj[wj]); den = __fmul_rn(den, (float)(wi - wj)); }     // den folds to a constant
+                acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(coef, den), pts[wi]));
+            }
+        } else if (!taps && num_poly_points <= 16) {
             // common case (12 points, no prefilter): fetch all points and form all (xw - xj) first, then the products -- the loads are
             // independent of the accumulation chain, issuing them up front hides their latency once instead of once per point
             float pts[16], dxj[16];
@@ -219,8 +235,12 @@ int launch_fractional_decimator_bank(const float* d_in, long in_stride, float* d
                                                                      xifirst, taps_length, cap);
         CSDRB_CUDA(cudaGetLastError());
         int gx2 = (cap + 127) / 128; if (gx2 > 2048) gx2 = 2048;
-        fracdec_interp_seg_kernel<<<dim3(gx2, channels), 128, 0, st>>>(d_in, in_stride, d_out, out_stride, static_cast<const FracDecState*>(d_state), segs, nsegs,
-                                                                       num_poly_points, xifirst, xilast, d_taps, taps_length);
+        if (!d_taps && num_poly_points == 12)
+            fracdec_interp_seg_kernel<12><<<dim3(gx2, channels), 128, 0, st>>>(d_in, in_stride, d_out, out_stride, static_cast<const FracDecState*>(d_state), segs, nsegs,
+                                                                               num_poly_points, xifirst, xilast, d_taps, taps_length);
+        else
+            fracdec_interp_seg_kernel<0><<<dim3(gx2, channels), 128, 0, st>>>(d_in, in_stride, d_out, out_stride, static_cast<const FracDecState*>(d_state), segs, nsegs,
+                                                                              num_poly_points, xifirst, xilast, d_taps, taps_length);
         CSDRB_CUDA(cudaGetLastError());
         return 2;
     }
@@ -437,7 +457,93 @@ fastagc_carry_kernel(const float* __restrict__ in, long in_stride, int block, in
     }
 }
 
+// Fused form for blocks of up to 1024 samples (the CLI default, csdr.c:1382): a CTA walks a run of consecutive blocks of one channel, computing
+// each block's peak as it streams by and keeping the last two blocks in registers, so out[b] = in[b-2] * ramp(target_{b-1} -> target_b) leaves in the same
+// pass.  Every input block is read once (plus three lead-in blocks per run for their peaks) instead of twice, and one launch replaces two.  Same
+// arithmetic as the kernels above, element for element.  Peaks go to the scratch array for fastagc_carry_kernel.
+constexpr int AGC_RUN = 16, AGC_PER = 4;
+
+// S16 = true: the output leaves as convert_f_s16 of the scaled sample (libcsdr.c:2390-2398) -- the last two blocks of the README.md:87 NFM graph in one pass.
+template <bool S16>
+__global__ void __launch_bounds__(256)
+fastagc_fused_kernel(const float* __restrict__ in, long in_stride, void* __restrict__ out_v, long out_stride, int block, int nblocks,
+                     float reference, const FastAgcState* __restrict__ state, const float* __restrict__ hist, float* __restrict__ peaks)
+{
+    __shared__ float red[2][8];
+    const int c = blockIdx.y, tid = threadIdx.x;
+    const int b0 = blockIdx.x * AGC_RUN, b1 = min(nblocks, b0 + AGC_RUN);
+    if (b0 >= nblocks) return;
+    const FastAgcState st = state[c];
+    const float* x = in + (long)c * in_stride;
+    const float* h1 = hist + (long)c * 2 * block;
+    float* pk_out = peaks + (long)c * nblocks;
+    float* y = S16 ? nullptr : static_cast<float*>(out_v) + (long)c * out_stride;
+    short* ys = S16 ? static_cast<short*>(out_v) + (long)c * out_stride : nullptr;
+    float d2[AGC_PER], d1[AGC_PER], d0[AGC_PER];                        // data of blocks j-2, j-1, j
+    float p3 = 0.f, p2 = 0.f, p1 = 0.f;                                 // peaks of blocks j-3, j-2, j-1
+#pragma unroll
+    for (int k = 0; k < AGC_PER; k++) d2[k] = d1[k] = 0.f;
+    for (int j = b0 - 3; j < b1; j++) {
+        // block j: from this call's input, from the carried history (j = -2, -1), or before it (only its peak matters: the state has it)
+        float m = 0.f;
+        if (j >= -2) {
+            const float* src = j >= 0 ? x + (long)j * block : (j == -2 ? h1 : h1 + block);
+#pragma unroll
+            for (int k = 0; k < AGC_PER; k++) { const int i = tid + k * 256; d0[k] = i < block ? src[i] : 0.f; m = fmaxf(m, fabsf(d0[k])); }
+        }
+        float pj;
+        if (j >= 0) {
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float* r = red[j & 1];
+            if ((tid & 31) == 0) r[tid >> 5] = m;
+            __syncthreads();
+            pj = r[0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) pj = fmaxf(pj, r[w]);
+            if (j >= b0 && tid == 0) pk_out[j] = pj;
+        } else pj = j == -1 ? st.peak_2 : (j == -2 ? st.peak_1 : 0.f);   // blocks before this call: their peaks are the carried state
+        if (j >= b0) {
+            // target_j from (p_j, p_{j-1}, p_{j-2}), target_{j-1} from (p_{j-1}, p_{j-2}, p_{j-3}); for j == 0 the previous target is the carried last_gain
+            float t = pj; if (t < p1) t = p1; if (t < p2) t = p2;
+            float target = __fdiv_rn(reference, t); if (target > 50.f) target = 50.f;
+            float last_gain;
+            if (j == 0) last_gain = st.last_gain;
+            else { float u = p1; if (u < p2) u = p2; if (u < p3) u = p3; last_gain = __fdiv_rn(reference, u); if (last_gain > 50.f) last_gain = 50.f; }
+#pragma unroll
+            for (int k = 0; k < AGC_PER; k++) {
+                const int i = tid + k * 256;
+                if (i < block) {
+                    const float r = __fdiv_rn((float)i, (float)block);
+                    const float gain = (float)((double)last_gain * (1.0 - (double)r) + (double)__fmul_rn(target, r));
+                    const float v = __fmul_rn(d2[k], gain);
+                    if (S16) ys[(long)j * block + i] = (short)f_to_s16_bits(v); else y[(long)j * block + i] = v;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < AGC_PER; k++) { d2[k] = d1[k]; d1[k] = d0[k]; }
+        p3 = p2; p2 = p1; p1 = pj;
+    }
+}
+
 size_t fastagc_scratch_bytes(int channels, int nblocks) { return (size_t)channels * (size_t)(nblocks > 0 ? nblocks : 1) * sizeof(float); }
+
+// fastagc_ff | convert_f_s16 in one pass (blocks of up to 1024 samples); -2: the block size has no fused kernel
+int launch_fastagc_bank_s16(const float* d_in, long in_stride, short* d_out, long out_stride, int channels, int block, int nblocks,
+                            float reference, void* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    if (channels <= 0 || nblocks <= 0) return 0;
+    if (block <= 0) { set_error("fastagc: block size must be positive"); return -1; }
+    if (block > 256 * AGC_PER) return -2;
+    if (!d_scratch || scratch_bytes < fastagc_scratch_bytes(channels, nblocks)) { set_error("fastagc: scratch too small"); return -1; }
+    float* peaks = static_cast<float*>(d_scratch);
+    fastagc_fused_kernel<true><<<dim3((nblocks + AGC_RUN - 1) / AGC_RUN, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, block, nblocks, reference,
+                                                                                                 static_cast<const FastAgcState*>(d_state), d_hist, peaks);
+    CSDRB_CUDA(cudaGetLastError());
+    fastagc_carry_kernel<<<channels, 256, 0, st>>>(d_in, in_stride, block, nblocks, reference, static_cast<FastAgcState*>(d_state), d_hist, peaks);
+    CSDRB_CUDA(cudaGetLastError());
+    return 2;
+}
 
 int launch_fastagc_bank(const float* d_in, long in_stride, float* d_out, long out_stride, int channels, int block, int nblocks,
                         float reference, void* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, cudaStream_t st)
@@ -447,6 +553,14 @@ int launch_fastagc_bank(const float* d_in, long in_stride, float* d_out, long ou
     if (d_out == d_in) { set_error("fastagc: in-place operation is not supported (output lags input by two blocks)"); return -1; }
     if (!d_scratch || scratch_bytes < fastagc_scratch_bytes(channels, nblocks)) { set_error("fastagc: scratch too small"); return -1; }
     float* peaks = static_cast<float*>(d_scratch);
+    if (block <= 256 * AGC_PER) {
+        fastagc_fused_kernel<false><<<dim3((nblocks + AGC_RUN - 1) / AGC_RUN, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, block, nblocks, reference,
+                                                                                               static_cast<const FastAgcState*>(d_state), d_hist, peaks);
+        CSDRB_CUDA(cudaGetLastError());
+        fastagc_carry_kernel<<<channels, 256, 0, st>>>(d_in, in_stride, block, nblocks, reference, static_cast<FastAgcState*>(d_state), d_hist, peaks);
+        CSDRB_CUDA(cudaGetLastError());
+        return 2;
+    }
     const dim3 grid(nblocks, channels);
     fastagc_peaks_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, block, nblocks, peaks);
     CSDRB_CUDA(cudaGetLastError());

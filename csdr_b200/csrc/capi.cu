@@ -487,6 +487,23 @@ int csdrb_fastagc_bank_ff(const float* d_in, long in_stride, float* d_out, long 
     return rc < 0 ? rc : counted(0, rc);
 }
 
+// fastagc_ff | convert_f_s16 fused (the last two blocks of the NFM graph, README.md:87).  Block sizes without a fused kernel (> 1024) run the two steps.
+int csdrb_fastagc_bank_f_s16(const float* d_in, long in_stride, short* d_out, long out_stride, int channels, int block, int nblocks, float reference,
+                             csdrb_fastagc_state_t* d_state, float* d_hist, void* d_scratch, size_t scratch_bytes, void* stream)
+{
+    if (too_many_channels(channels, "fastagc bank")) return -1;
+    if (!d_in || !d_out || !d_state || !d_hist) { set_error("fastagc s16 bank: null pointer"); return -1; }
+    int rc = launch_fastagc_bank_s16(d_in, in_stride, d_out, out_stride, channels, block, nblocks, reference, d_state, d_hist, d_scratch, scratch_bytes, S(stream));
+    if (rc != -2) return rc < 0 ? rc : counted(0, rc);
+    float* tmp = nullptr;                                              // unusual block size: AGC into a stream-ordered temporary, then the conversion row by row
+    const long n = (long)block * nblocks;
+    CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), sizeof(float) * (size_t)n * channels, S(stream)));
+    rc = launch_fastagc_bank(d_in, in_stride, tmp, n, channels, block, nblocks, reference, d_state, d_hist, d_scratch, scratch_bytes, S(stream));
+    for (int c = 0; c < channels && rc >= 0; c++) { const int r2 = launch_convert_f_s16(tmp + (long)c * n, d_out + (long)c * out_stride, n, S(stream)); rc = r2 < 0 ? r2 : rc + 1; }
+    CSDRB_CUDA(cudaFreeAsync(tmp, S(stream)));
+    return rc < 0 ? rc : counted(0, rc);
+}
+
 int csdrb_fft_c2c_batch(const complexf* d_in, long in_stride, complexf* d_out, long out_stride, int size, int batch, int inverse, void* stream)
 {
     if (!d_in || !d_out) { set_error("fft: null pointer"); return -1; }

@@ -110,6 +110,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 #endif  // CSDRB_HOST_EMULATION
 
+// ---- convert_f_s16 of one value (libcsdr.c:2390-2398): float multiply by 32767, truncate toward zero, keep the low 16 bits of the int32 ----
+// (what cvttss2si + a 16-bit store do on the reference's x86 build; out-of-range / NaN -> INT_MIN -> 0)
+__device__ __forceinline__ unsigned f_to_s16_bits(float x)
+{
+    const float s = __fmul_rn(x, 32767.0f);
+    const int w = (s >= 2147483648.0f || s < -2147483648.0f || s != s) ? (-2147483647 - 1) : __float2int_rz(s);
+    return (unsigned)w & 0xffffu;
+}
+
 // ---- exact fast-forward of the reference's phase wrap ----------------------------------------------
 //   while (ph >  PI) ph -= 2*PI;   while (ph < -PI) ph += 2*PI;        (libcsdr_gpl.c:49-50, PI = (float)3.14159...)
 // Every subtraction rounds, so the loop cannot be replaced by fmod.  But while |ph| stays in one binade

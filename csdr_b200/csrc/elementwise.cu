@@ -64,15 +64,7 @@ __global__ void __launch_bounds__(256) convert_s16_f_kernel(const short* __restr
     for (long i = nw * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __fmul_rn((float)in[i], recip);
 }
 
-// f32 -> s16: float multiply by 32767, truncate toward zero, keep the low 16 bits of the int32
-// (what cvttss2si + a 16-bit store do on the reference's x86 build; out-of-range/NaN -> INT_MIN -> 0).
-__device__ __forceinline__ unsigned f_to_s16_bits(float x)
-{
-    const float s = __fmul_rn(x, 32767.0f);
-    int w = (s >= 2147483648.0f || s < -2147483648.0f || s != s) ? INT_MIN : __float2int_rz(s);
-    return (unsigned)w & 0xffffu;
-}
-
+// f32 -> s16: f_to_s16_bits (common.cuh) = float multiply by 32767, truncate toward zero, keep the low 16 bits of the int32
 __global__ void __launch_bounds__(256) convert_f_s16_kernel(const float* __restrict__ in, short* __restrict__ out, long n)
 {
     const long nvec = n / 8;

@@ -337,8 +337,7 @@ int main(int argc, char **argv)
         /* 4. fastagc_ff over the whole AGC blocks available, then convert_f_s16; the remainder waits for the next block */
         const int g_n = g_have + m, nb = g_n / AGC_BLOCK, whole = nb * AGC_BLOCK;
         if (nb > 0) {
-            OK(csdrb_fastagc_bank_ff(d_agc_in, gs, d_agc_out, whole, C, AGC_BLOCK, nb, agc_ref, d_agc_state, d_agc_hist, d_agc_scratch, agc_sb + 16, stream));
-            OK(csdrb_convert_f_s16(d_agc_out, d_pcm, (long)C * whole, stream));
+            OK(csdrb_fastagc_bank_f_s16(d_agc_in, gs, d_pcm, whole, C, AGC_BLOCK, nb, agc_ref, d_agc_state, d_agc_hist, d_agc_scratch, agc_sb + 16, stream));   /* AGC and s16 in one pass */
             OK(csdrb_copy_d2h(h_out, d_pcm, sizeof(short) * (size_t)C * (size_t)whole, stream));
             const int rest = g_n - whole;
             OK(csdrb_copy2d_d2d(d_carry, sizeof(float) * (size_t)AGC_BLOCK, d_agc_in + whole, sizeof(float) * (size_t)gs, sizeof(float) * (size_t)rest, (size_t)C, stream));

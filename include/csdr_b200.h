@@ -331,6 +331,10 @@ size_t csdrb_fastagc_bank_scratch_bytes(int channels, int nblocks);
 int csdrb_fastagc_bank_ff(const float *d_in, long in_stride, float *d_out, long out_stride, int channels, int block, int nblocks,
                           float reference, csdrb_fastagc_state_t *d_state, float *d_hist, void *d_scratch, size_t scratch_bytes, void *stream);
 
+/* fastagc_ff | convert_f_s16 in one pass: d_out is short [channels][out_stride]; everything else as above */
+int csdrb_fastagc_bank_f_s16(const float *d_in, long in_stride, short *d_out, long out_stride, int channels, int block, int nblocks,
+                             float reference, csdrb_fastagc_state_t *d_state, float *d_hist, void *d_scratch, size_t scratch_bytes, void *stream);
+
 /* K7 batched unnormalised c2c DFT (power-of-two size 2..16384), sign -1 forward / +1 inverse */
 int csdrb_fft_c2c_batch(const complexf *d_in, long in_stride, complexf *d_out, long out_stride, int size, int batch, int inverse, void *stream);
 

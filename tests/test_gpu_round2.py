@@ -238,3 +238,19 @@ def test_multi_gpu_bank_equals_the_single_gpu_bank(gpu, oracle):
     ref = oracle.fmdemod_quadri_cf(oracle.fir_decimate_cc(sh, D, taps))[0][:want.shape[1]]
     e = _rel(want[c], ref)
     assert e < TOL, f"rel-RMS {e:.3e}"
+
+
+# ------------------------------------------------------------------------------------------ fastagc_ff | convert_f_s16 fused
+@pytest.mark.parametrize("block", [1024, 1000, 256, 2048])
+def test_fastagc_s16_fused_is_bit_exact(gpu, oracle, block):
+    rng = np.random.default_rng(block)
+    ch, nb = 5, 37
+    x = (rng.uniform(-1, 1, (ch, nb * block)) * rng.uniform(0.01, 3.0, (ch, 1))).astype(np.float32)
+    x[1, 3 * block:5 * block] = 0.0                                        # silence: gain capped at 50
+    cut = 11 * block
+    y1, st, hist = gpu.fastagc_bank_f_s16(_dev(x[:, :cut]), block, 0.8)
+    y2, _, _ = gpu.fastagc_bank_f_s16(_dev(x[:, cut:]), block, 0.8, state=st, hist=hist)            # streamed in two calls
+    got = np.concatenate([y1.cpu().numpy(), y2.cpu().numpy()], axis=1)
+    for c in range(ch):
+        want = oracle.convert_f_s16(oracle.fastagc_ff(x[c], block, 0.8))
+        assert np.array_equal(got[c], want), (block, c)

@@ -297,6 +297,33 @@ def test_k6_fastagc_and_deemphasis_bit_exact(audio, oracle):
         assert np.array_equal(yb[c], want) and np.float32(wl) == last[c]
 
 
+@pytest.mark.parametrize("block", [1024, 1000, 77, 2048])
+def test_k6_fused_run_kernel_and_s16_output(audio, oracle, block):
+    """blocks <= 1024 take the one-pass kernel (a CTA walks runs of 16 blocks, peaks rolling, two blocks in registers): 37 blocks = three runs, streamed in
+    two calls; with the s16 epilogue the result is convert_f_s16(fastagc_ff(x)) bit for bit.  2048 has no fused kernel (the float bank falls back)."""
+    rng = np.random.default_rng(block)
+    ch, nb = 3, 37
+    x = (rng.uniform(-1, 1, (ch, nb * block)) * np.array([[1.0], [0.02], [3.0]])).astype(np.float32)
+    x[1, 3 * block:5 * block] = 0.0
+    cut = 20 * block
+    state = Z((ch, 3), np.float32); hist = Z((ch, 2, block), np.float32)
+    sb = audio.emul_fastagc_scratch_bytes(ch, nb); scratch = Z(sb + 16, np.uint8)
+    outf = Z((ch, nb * block), np.float32); s16 = Z((ch, nb * block), np.int16)
+    st2 = Z((ch, 3), np.float32); h2 = Z((ch, 2, block), np.float32)
+    for lo, hi in ((0, cut), (cut, nb * block)):
+        xs = np.ascontiguousarray(x[:, lo:hi]); n = (hi - lo) // block
+        of = Z((ch, hi - lo), np.float32); os_ = Z((ch, hi - lo), np.int16)
+        assert audio.emul_launch_fastagc_bank(P(xs), xs.shape[1], P(of), of.shape[1], ch, block, n, 0.8, P(state), P(hist), P(scratch), sb) >= 0
+        rc = audio.emul_launch_fastagc_bank_s16(P(xs), xs.shape[1], P(os_), os_.shape[1], ch, block, n, 0.8, P(st2), P(h2), P(scratch), sb)
+        assert rc == (-2 if block > 1024 else 2)
+        outf[:, lo:hi] = of; s16[:, lo:hi] = os_
+    for c in range(ch):
+        want = oracle.fastagc_ff(x[c], block, 0.8)
+        assert np.array_equal(outf[c], want), c
+        if block <= 1024:
+            assert np.array_equal(s16[c], oracle.convert_f_s16(want)), c
+
+
 @pytest.mark.parametrize("rate", [48000, 44100, 11025, 8000])
 def test_nfm_deemphasis_fir_and_fused_limiter(audio, oracle, rate):
     taps = GOLD[f"nfm_taps_{rate}"]; T = taps.size
