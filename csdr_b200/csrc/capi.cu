@@ -173,11 +173,9 @@ int csdrb_fir_decimate_bank_u8_cc(const unsigned char* d_in, long in_stride, com
     const long fstride = (input_size + 1) & ~1L;
     float* tmp = nullptr;
     CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), sizeof(float) * 2 * (size_t)fstride * channels, S(stream)));
-    for (int c = 0; c < channels; c++) {
-        rc = launch_convert_u8_f(d_in + (long)c * in_stride * 2, tmp + (long)c * fstride * 2, 2L * input_size, S(stream));
-        if (rc < 0) { cudaFreeAsync(tmp, S(stream)); return rc; }
-    }
-    g_launches += channels;
+    rc = launch_u8_rows_to_cf32(d_in, in_stride, reinterpret_cast<float2*>(tmp), fstride, channels, input_size, S(stream));
+    if (rc < 0) { cudaFreeAsync(tmp, S(stream)); return rc; }
+    g_launches += 1;
     rc = csdrb_fir_decimate_bank_cc(reinterpret_cast<const complexf*>(tmp), fstride, d_out, out_stride, channels, input_size, decimation, h_taps, taps_length, -1, stream);
     CSDRB_CUDA(cudaFreeAsync(tmp, S(stream)));
     return rc;

@@ -325,11 +325,11 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
             CSDRB_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
         }
         const long npairs = (long)channels * nblocks;
-        const size_t psmem = sizeof(float2) * 4 * (size_t)fft_smem_elems(fft_inv_size);
+        const size_t psmem = sizeof(float2) * (size_t)POST_PAIRS * (size_t)fft_smem_elems(fft_inv_size);
         switch (fft_inv_size) {
 #define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
             if (psmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-            k<<<(unsigned)((npairs + 3) / 4), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
+            k<<<(unsigned)((npairs + POST_PAIRS - 1) / POST_PAIRS), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
                                                                 scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
             CSDRB_FFT_SIZES(X)
 #undef X

@@ -581,8 +581,12 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
     }
 }
 
-// IFFT_M of four folded (channel, block) rows per CTA (64 threads each), /M, drop the scrap, post shift + decimate (one lane per row walks its
-// phasor chain).  Pairs are numbered p = c * nblocks + b.
+// IFFT_M of POST_PAIRS folded (channel, block) rows per CTA (64 threads per transform, four at a time), /M, drop the scrap, post shift + decimate.
+// The post shift is the reference's phasor recursion (libcsdr_gpl.c:131-160): sequential per row, so ONE LANE PER ROW walks it -- with sixteen rows in the
+// CTA's shared memory sixteen lanes of one warp do that side by side (the first version gave every row its own warp: 5 active threads per instruction
+// on average, 113 us; r02 ncu).  With the padded pitch of 578 complex values the sixteen lanes' LDS.64 land two to a bank at worst.  Pairs are p = c * nblocks + b.
+constexpr int POST_PAIRS = 16;
+
 template <int M>
 __global__ void __launch_bounds__(256)
 fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __restrict__ chan, const int* __restrict__ blk_remain,
@@ -591,24 +595,29 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
 {
     CSDRB_DYN_SMEM(smem_raw);
     float2* s = reinterpret_cast<float2*>(smem_raw);
-    constexpr int NTG = 64, GROUPS = 4, ELEMS = fft_smem_elems(M), PER = M / NTG;
+    constexpr int NTG = 64, GROUPS = 4, PITCH = fft_smem_elems(M), PER = M / NTG;      // even pitch: rows stay 16-byte aligned for block_fft's 128-bit accesses
     static_assert(M >= 64 && M <= 16 * NTG, "fastddc_ifft_post_kernel: 64 <= M <= 1024");
     const int tid = threadIdx.x, g = tid / NTG, tg = tid % NTG;
-    const long npairs = (long)channels * nblocks;
-    const long p = min((long)blockIdx.x * GROUPS + g, npairs - 1);      // a ragged last CTA repeats the last pair (nothing is stored twice: see below)
-    const bool mine = (long)blockIdx.x * GROUPS + g < npairs;
-    const float2* src = folded + p * M;
-    float2* mys = s + g * ELEMS;
-    float2 v[PER];
+    const long npairs = (long)channels * nblocks, p0 = (long)blockIdx.x * POST_PAIRS;
+#pragma unroll 1
+    for (int a = 0; a < POST_PAIRS; a += GROUPS) {                       // every thread takes part in every round (block_fft has barriers inside)
+        const long p = min(p0 + a + g, npairs - 1);                     // a ragged last CTA repeats the last pair into its own row: harmless
+        const float2* src = folded + p * M;
+        float2* mys = s + (a + g) * PITCH;
+        float2 v[PER];
 #pragma unroll
-    for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);     // all loads first
+        for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);  // all loads first
 #pragma unroll
-    for (int k = 0; k < PER; k++) mys[fft_pad(tg + k * NTG)] = v[k];
+        for (int k = 0; k < PER; k++) mys[fft_pad(tg + k * NTG)] = v[k];
+        __syncthreads();
+        block_fft<M, NTG, true>(mys, tw, tg);
+    }
     __syncthreads();
-    block_fft<M, NTG, true>(mys, tw, tg);
-    if (tg == 0 && mine) {
+    if (tid < POST_PAIRS && p0 + tid < npairs) {
+        const long p = p0 + tid;
         const int c = (int)(p / nblocks), b = (int)(p % nblocks);
         const DdcChan cp = chan[c];
+        const float2* row = s + tid * PITCH;
         const float inv_m = 1.0f / (float)M;
         const long bi = (long)b * channels + c;
         const double ph = (double)blk_phase[bi];
@@ -616,7 +625,7 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         float2* y = out + (long)c * out_stride + blk_offset[bi];
         int k = 0;
         for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
-            const float2 raw = mys[fft_pad(scrap + pos)];
+            const float2 raw = row[fft_pad(scrap + pos)];
             const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
             y[k++] = make_float2(__fsub_rn(__fmul_rn(co, w.x), __fmul_rn(si, w.y)), __fadd_rn(__fmul_rn(si, w.x), __fmul_rn(co, w.y)));
             const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));

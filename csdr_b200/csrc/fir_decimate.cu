@@ -213,6 +213,24 @@ static int launch_fast(const void* in, long in_stride, float2* out, long out_str
     return 0;
 }
 
+// rows of u8 IQ at any alignment -> cf32 rows (the front end of the two-launch path for geometries without a fused tiling): libcsdr.c:2365 per value
+__global__ void __launch_bounds__(256)
+u8_rows_to_cf32_kernel(const unsigned char* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride, int n)
+{
+    const unsigned char* src = in + (long)blockIdx.y * in_stride * 2;
+    float2* dst = out + (long)blockIdx.y * out_stride;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[i] = make_float2((float)((double)(float)src[2 * i] / (255 / 2.0) - 1.0), (float)((double)(float)src[2 * i + 1] / (255 / 2.0) - 1.0));
+}
+int launch_u8_rows_to_cf32(const unsigned char* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, cudaStream_t st)
+{
+    if (channels <= 0 || n <= 0) return 0;
+    int gx = (n + 255) / 256; if (gx > 1024) gx = 1024;
+    u8_rows_to_cf32_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n);
+    CSDRB_CUDA(cudaGetLastError());
+    return 1;
+}
+
 // u8 IQ in (2 bytes per sample, row stride in samples, a multiple of 8 so that rows start on 16-byte boundaries), cf32 out: convert_u8_f | fir_decimate_cc
 // in one kernel.  Returns outputs per channel, or -2 when (D, T) has no fused tiling -- the caller then converts and filters in two launches.
 int launch_fir_decimate_bank_u8(const unsigned char* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n_in,

@@ -9,6 +9,7 @@ int launch_fir_decimate_bank(const float2* d_in, long in_stride, float2* d_out, 
                              int D, const float* h_taps, const float* d_taps, long taps_stride, int T, int variant,
                              cudaStream_t st);
 int fir_bank_variant_count();
+int launch_u8_rows_to_cf32(const unsigned char* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n, cudaStream_t st);
 int launch_fir_decimate_bank_u8(const unsigned char* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n_in,
                                 int D, const float* h_taps, int T, cudaStream_t st);
 
