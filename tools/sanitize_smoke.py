@@ -29,4 +29,12 @@ for sr in (48000, 44100, 11025, 8000):
     for n in (202, 1024 + 201, 1024 + 202, 5000): cb.deemphasis_nfm_bank_ff(a[:, :n], sr, limit_max=0.5 if n & 1 else 0.0)
 cb.shift_addfast_bank_cc(cplx(16384 + 777), [0.1, -0.3, 0.45], chunk=1024); cb.shift_addfast_bank_cc(cplx(3, 1001), [0.1, -0.3, 0.45], chunk=37)
 cb.libcsdr.shift_addfast_cc(rng.normal(size=1022).astype(np.complex64), 0.2); cb.libcsdr.deemphasis_nfm_ff(rng.normal(size=3000).astype(np.float32), 48000)
+# round 2: u8 front end (fused and two-launch), long phase chains on the wrap table, fold-path fastddc on ragged banks, fused AGC + s16, streaming bank + retune
+u8 = torch.randint(0, 256, (3, 20008, 2), dtype=torch.uint8, device=dev)
+cb.fir_decimate_bank_u8_cc(u8[:, :20001], 10, taps); cb.fir_decimate_bank_u8_cc(u8[:, :20001], 50, cb.firdes_lowpass_f(801, 0.01)); cb.fir_decimate_bank_u8_cc(u8[:, :9999].contiguous(), 7, cb.firdes_lowpass_f(33, 0.1))
+cb.shift_addition_bank_cc(cplx(130 * 1024 + 5), [0.1, -0.3, 0.45, 1e-4], chunk=1024); cb.shift_addfast_bank_cc(cplx(9000), [0.2, -0.4], chunk=64)
+d = cb.fastddc_init(0.002, 64, 0.0); sp, ov = cb.fastddc_fwd_cc(cplx(130 * d.input_size), d); cb.fastddc_inv_bank_cc(sp, list(np.linspace(-0.4, 0.4, 17)), 64, 0.002)
+cb.fastagc_bank_f_s16(a[:, :19 * 1024], 1024, 1.0); cb.fastagc_bank_f_s16(a[:, :19 * 1000], 1000, 1.0); cb.fastagc_bank_f_s16(a[:, :8 * 2048], 2048, 1.0)
+bank = cb.DdcBank(np.linspace(-0.4, 0.4, 37), 50, cb.firdes_lowpass_f(801, 0.5 / 50), demod=True, chunk=1024)
+w = cplx(60000); o1 = bank.process(w[:20000]); bank.set_rate(3, 0.11); bank.process(w[o1.shape[1] * 50:o1.shape[1] * 50 + 30000]); bank.close()
 torch.cuda.synchronize(); print("sanitize_smoke: all kernels ran")
