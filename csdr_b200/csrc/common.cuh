@@ -45,6 +45,12 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2*>(&rd);
 }
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b)
+{
+    uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b), rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
 {
     uint64_t ra = *reinterpret_cast<uint64_t*>(&a), rb = *reinterpret_cast<uint64_t*>(&b), rd;

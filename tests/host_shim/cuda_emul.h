@@ -262,6 +262,7 @@ namespace csdrb {
 static inline float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }     // two IEEE FMAs, like FFMA2
 static inline float2 fadd2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 static inline float2 fmul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+static inline float2 fsub2(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
 static inline uint32_t smem_u32(const void*) { return 0; }
 // one-phase mbarrier model: word 0 = arrivals still expected, word 1 = transaction bytes still in flight; complete when both are 0
 static inline void mbar_init(uint64_t* bar, uint32_t count) { int32_t* w = reinterpret_cast<int32_t*>(bar); w[0] = (int32_t)count; w[1] = 0; }
