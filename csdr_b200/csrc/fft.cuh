@@ -27,25 +27,20 @@ namespace csdrb {
 __host__ __device__ constexpr int fft_pad(int i) { return i + 2 * (i >> 4); }
 __host__ __device__ constexpr int fft_smem_elems(int n) { return n + 2 * (n >> 4) + 2; }
 
-// Complex arithmetic on packed fp32 (FADD2 / FMUL2 / FFMA2: one instruction for the real and the imaginary lane).  A complex product
-// a*w = a.x*(w.x, w.y) + a.y*(-w.y, w.x) is one FMUL2 and one FFMA2 with a scalar-broadcast a.x / a.y; sign flips are integer XORs so that
-// ptxas folds them, like the lane swaps, into the operand modifiers of the packed instructions.  Round 2: the butterflies of every FFT-family
-// kernel were scalar FADD/FMUL/FFMA (two thirds of their instructions); packed they issue half as many.
-__device__ __forceinline__ float fneg(float x) { return __uint_as_float(__float_as_uint(x) ^ 0x80000000u); }
 template <bool INV>
 __device__ __forceinline__ float2 cmul_w(float2 a, float2 w)
 {
     // a * w (forward) or a * conj(w) (inverse)
-    return INV ? ffma2(make_float2(a.x, a.x), make_float2(w.x, fneg(w.y)), fmul2(make_float2(a.y, a.y), make_float2(w.y, w.x)))
-               : ffma2(make_float2(a.x, a.x), w, fmul2(make_float2(a.y, a.y), make_float2(fneg(w.y), w.x)));
+    return INV ? make_float2(fmaf(a.x, w.x, a.y * w.y), fmaf(a.y, w.x, -a.x * w.y))
+               : make_float2(fmaf(a.x, w.x, -a.y * w.y), fmaf(a.y, w.x, a.x * w.y));
 }
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a)       // a * (-i) forward, a * (+i) inverse
 {
-    return INV ? make_float2(fneg(a.y), a.x) : make_float2(a.y, fneg(a.x));
+    return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return fadd2(a, b); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return fsub2(a, b); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 template <bool INV>
 __device__ __forceinline__ void dft2(float2& a, float2& b) { float2 t = a; a = cadd(t, b); b = csub(t, b); }
@@ -65,11 +60,9 @@ __device__ __forceinline__ void dft8(float2 (&v)[8])
     dft4<INV>(o0, o1, o2, o3);
     const float h = 0.70710678118654752440f;
     // W8^1 = h*(1 -+ i), W8^2 = -+i, W8^3 = h*(-1 -+ i)
-    const float2 hh = make_float2(h, h);
-    // o1 * W8^1 = h * (o1 + o1*(-+i)),   o3 * W8^3 = h * (o3*(-+i) - o3)
-    const float2 t1 = fmul2(fadd2(o1, mul_mi<INV>(o1)), hh);
+    const float2 t1 = INV ? make_float2(h * (o1.x - o1.y), h * (o1.x + o1.y)) : make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));
     const float2 t2 = mul_mi<INV>(o2);
-    const float2 t3 = fmul2(fsub2(mul_mi<INV>(o3), o3), hh);
+    const float2 t3 = INV ? make_float2(-h * (o3.x + o3.y), h * (o3.x - o3.y)) : make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));
     v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
     v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
     v[2] = cadd(e2, t2); v[6] = csub(e2, t2);

@@ -37,8 +37,8 @@ __device__ __forceinline__ float2 mul_w16(float2 a)
     constexpr float WI0 = M == 0 ? 0.f : M == 1 ? -S1 : M == 2 ? -H : M == 3 ? -C1 : M == 4 ? -1.f : M == 6 ? -H : /* M == 9 */ S1;
     constexpr float WI = INV ? -WI0 : WI0;
     if constexpr (M == 0) return a;
-    else if constexpr (M == 4) return fmul2(make_float2(a.y, a.x), make_float2(-WI, WI));
-    else return ffma2(make_float2(a.x, a.x), make_float2(WR, WI), fmul2(make_float2(a.y, a.y), make_float2(-WI, WR)));     // a.x*(WR, WI) + a.y*(-WI, WR)
+    else if constexpr (M == 4) return make_float2(-a.y * WI, a.x * WI);
+    else return make_float2(fmaf(a.x, WR, -a.y * WI), fmaf(a.x, WI, a.y * WR));
 }
 
 template <bool INV>
@@ -70,7 +70,7 @@ __device__ __forceinline__ void dft_any(float2 (&v)[R])
     else dft_small<R, INV>(v);
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return ffma2(make_float2(a.x, a.x), b, fmul2(make_float2(a.y, a.y), make_float2(fneg(b.y), b.x))); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
 
 // twiddled radix-16 butterfly j of a pass over sub-transforms of size NS (> 1)
 template <int N, int NS, bool INV>

@@ -507,7 +507,7 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
 // fastddc.c:126-141 (k ascending = bin index ascending); products and sums are fused (FFMA2), inside the 1e-5 budget.
 // The folded bins go to a scratch array (L2-sized: 64 ch x 256 blocks x 512 bins = 67 MB), fastddc_ifft_post_kernel does IFFT_M, /M,
 // scrap and the post shift; the block-to-block state chain runs on a side stream meanwhile (it is data-independent).
-constexpr int FOLD_R = 64, FOLD_CT = 8, FOLD_BT = 8, FOLD_ST = 4;     // residues per CTA, thread tile (channels x blocks), pipeline stages
+constexpr int FOLD_R = 64, FOLD_CT = 8, FOLD_BT = 8, FOLD_ST = 3;     // residues per CTA, thread tile (channels x blocks), pipeline stages
 
 __global__ void __launch_bounds__(256, 1)
 fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
@@ -534,34 +534,26 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 #pragma unroll
         for (int q = 0; q < 4; q++) cp_async16(sm + stage * STAGE + dsto[q], src[q] + (long)(q < 2 ? kx : k) * M);
     };
+    // (a 4-stage ring with the next step's operands pulled into registers during the FMAs was measured slower: 96 vs 88 us, 233 registers)
     float2 acc[FOLD_CT][FOLD_BT];
 #pragma unroll
     for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
         for (int v = 0; v < FOLD_BT; v++) acc[u][v] = make_float2(0.f, 0.f);
-    // Software pipeline, two levels: cp.async keeps FOLD_ST - 1 k-steps in flight from L2 into the shared ring, and the operands of step k+1 are pulled
-    // from shared memory into registers while the 128 FMAs of step k issue (r02 ncu: with the loads at the head of each step both warps of a scheduler sat
-    // in the LDS latency together after every barrier -- FMA pipe 50 %).
 #pragma unroll
     for (int s = 0; s < FOLD_ST - 1; s++) { if (s < P) issue(s, s); cp_async_commit(); }
-    float2 x[FOLD_BT], h[FOLD_CT], xn[FOLD_BT], hn[FOLD_CT];
-    auto fetch = [&](int stage, float2 (&xd)[FOLD_BT], float2 (&hd)[FOLD_CT]) {
-        const float2* xs = sm + stage * STAGE + (gb * FOLD_BT) * FOLD_R + rl;
-        const float2* hs = sm + stage * STAGE + (ROWS + gc * FOLD_CT) * FOLD_R + rl;
-#pragma unroll
-        for (int v = 0; v < FOLD_BT; v++) xd[v] = xs[v * FOLD_R];
-#pragma unroll
-        for (int u = 0; u < FOLD_CT; u++) hd[u] = hs[u * FOLD_R];
-    };
-    cp_async_wait<FOLD_ST - 2>();                                       // step 0 has landed
-    __syncthreads();
-    fetch(0, x, h);
     for (int k = 0; k < P; k++) {
-        cp_async_wait<FOLD_ST - 3>();                                   // step k+1 has landed (for this thread's copies) ...
-        __syncthreads();                                                // ... and for everyone's; the ring slot of step k-1 is free again
+        cp_async_wait<FOLD_ST - 2>();
+        __syncthreads();                                                // stage k has landed for everyone; stage (k-1) is free again
         if (k + FOLD_ST - 1 < P) issue(k + FOLD_ST - 1, (k + FOLD_ST - 1) % FOLD_ST);
         cp_async_commit();
-        if (k + 1 < P) fetch((k + 1) % FOLD_ST, xn, hn);
+        const float2* xs = sm + (k % FOLD_ST) * STAGE + (gb * FOLD_BT) * FOLD_R + rl;
+        const float2* hs = sm + (k % FOLD_ST) * STAGE + (ROWS + gc * FOLD_CT) * FOLD_R + rl;
+        float2 x[FOLD_BT], h[FOLD_CT];
+#pragma unroll
+        for (int v = 0; v < FOLD_BT; v++) x[v] = xs[v * FOLD_R];
+#pragma unroll
+        for (int u = 0; u < FOLD_CT; u++) h[u] = hs[u * FOLD_R];
         // acc += x*h = xr*(hr, hi) + xi*(-hi, hr): two packed FMAs per accumulator, scalar-broadcast x against h and against h swapped/negated
         // (operand modifiers of FFMA2: no register moves).  Two sweeps over the tile, so the two FMAs of one accumulator sit 64 instructions apart.
 #pragma unroll
@@ -573,10 +565,6 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 #pragma unroll
             for (int v = 0; v < FOLD_BT; v++)
                 acc[u][v] = ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
-#pragma unroll
-        for (int v = 0; v < FOLD_BT; v++) x[v] = xn[v];
-#pragma unroll
-        for (int u = 0; u < FOLD_CT; u++) h[u] = hn[u];
     }
     // /pre_decimation, and both half swaps (fastddc.c:143-150) folded into the destination index (r - offsetbin) mod M
     const int r = r0 + rl;

@@ -54,6 +54,7 @@ test_openwebrx_waterfall_chain = za.test_openwebrx_waterfall_chain
 
 import test_gpu_zz_control as zc  # noqa: E402
 test_initial_tuning_through_the_control_channel = zc.test_initial_tuning_through_the_control_channel
+test_midstream_retune_at_a_known_block = zc.test_midstream_retune_at_a_known_block
 
 import test_gpu_zz_shift_table as zt  # noqa: E402
 test_shift_table_command = zt.test_shift_table_command
