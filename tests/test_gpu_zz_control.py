@@ -85,7 +85,7 @@ def _retune_run(cli, args_before, args_after, first, second, blocks, out_block_b
 
     def drain():
         while True:
-            chunk = p.stdout.read(65536)
+            chunk = p.stdout.read1(65536)                                 # whatever has arrived (read() would wait for 64 KiB: blocks can be tiny)
             if not chunk:
                 return
             got.extend(chunk)
