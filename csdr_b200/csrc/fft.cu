@@ -305,7 +305,10 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
         SideStream* ss = side_stream();
         if (!ss) return -1;
         float2* folded = nullptr;
-        CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&folded), sizeof(float2) * (size_t)channels * nblocks * fft_inv_size, st));
+        const int kmax = (post_input_size + post_decimation - 1) / post_decimation;      // outputs one block can emit
+        const size_t folded_elems = (size_t)channels * nblocks * fft_inv_size, phasor_elems = (size_t)channels * nblocks * (size_t)kmax;
+        CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&folded), sizeof(float2) * (folded_elems + phasor_elems), st));
+        float2* phasor = folded + folded_elems;
         {
             std::lock_guard<std::mutex> lk(ss->mu);                     // the fork/join events are shared by every call on this device
             CSDRB_CUDA(cudaEventRecord(ss->fork, st));
@@ -313,14 +316,23 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
             fastddc_state_chain_kernel<<<channels, 32, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
             CSDRB_CUDA(cudaGetLastError());
+            fastddc_phasor_kernel<<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
+            CSDRB_CUDA(cudaGetLastError());
             CSDRB_CUDA(cudaEventRecord(ss->join, ss->stream));
             const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
+            static const bool wide_cta = getenv("CSDRB_FOLD_BT") && getenv("CSDRB_FOLD_BT")[0] == '4';     // A/B: 512-thread CTAs with 8 x 4 thread tiles
             static bool attr_done = false;
-            if (!attr_done) { CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); attr_done = true; }
+            if (!attr_done) {
+                CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                attr_done = true;
+            }
             const dim3 fgrid(fft_inv_size / FOLD_R, (channels + 2 * FOLD_CT - 1) / (2 * FOLD_CT), (nblocks + 2 * FOLD_BT - 1) / (2 * FOLD_BT));
             if (fgrid.y > 65535u || fgrid.z > 65535u) { set_error("fastddc_inv: bank too large for one call"); return -1; }
-            fastddc_fold_kernel<<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
-                                                          1.0f / (float)pre_decimation);
+            if (wide_cta) fastddc_fold_kernel<4><<<fgrid, 512, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
+                                                                           1.0f / (float)pre_decimation);
+            else fastddc_fold_kernel<8><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
+                                                                   1.0f / (float)pre_decimation);
             CSDRB_CUDA(cudaGetLastError());
             CSDRB_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
         }
@@ -330,13 +342,13 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
 #define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
             if (psmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
             k<<<(unsigned)((npairs + POST_PAIRS - 1) / POST_PAIRS), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
-                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw); } break;
+                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor); } break;
             CSDRB_FFT_SIZES(X)
 #undef X
         }
         CSDRB_CUDA(cudaGetLastError());
         CSDRB_CUDA(cudaFreeAsync(folded, st));
-        return 3;
+        return 4;
     }
     fastddc_state_chain_kernel<<<channels, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);

@@ -509,22 +509,26 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
 // scrap and the post shift; the block-to-block state chain runs on a side stream meanwhile (it is data-independent).
 constexpr int FOLD_R = 64, FOLD_CT = 8, FOLD_BT = 8, FOLD_ST = 3;     // residues per CTA, thread tile (channels x blocks), pipeline stages
 
-__global__ void __launch_bounds__(256, 1)
+// BT = blocks per thread tile: 8 -> 256 threads (8 warps per SM), 4 -> 512 threads (16 warps, half the accumulators per thread: more latency hiding, more
+// shared-memory reads per FMA).  The CTA tile is 64 residues x 16 channels x 16 blocks either way.
+template <int BT>
+__global__ void __launch_bounds__(64 * 2 * (2 * FOLD_BT / BT), 1)
 fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
                     float2* __restrict__ folded /*[C][nblocks][M]*/, int N, int M, int nblocks, int channels, float inv_pre)
 {
     CSDRB_DYN_SMEM(smem_raw);
     float2* sm = reinterpret_cast<float2*>(smem_raw);                   // FOLD_ST stages of { x[16][64], h[16][64] }
     constexpr int ROWS = 2 * FOLD_BT, STAGE = 2 * ROWS * FOLD_R;        // float2 per stage
+    constexpr int NT = 64 * 2 * (ROWS / BT), CPT = (2 * ROWS * (FOLD_R / 2)) / NT;   // threads; 16-byte copies per thread and k-step
     const int tid = threadIdx.x;
     const int rl = tid & 63, g = tid >> 6, gc = g & 1, gb = g >> 1;
     const int r0 = blockIdx.x * FOLD_R, c0 = blockIdx.y * (2 * FOLD_CT), b0 = blockIdx.z * (2 * FOLD_BT);
     const int P = N / M, halfP = P / 2;                                 // the half swap of the spectrum (fastddc.c:123) is a rotation of k by P/2
-    // this thread's four 16-byte copies per k-step: chunk ids tid + 256*q, q < 4; 32 chunks per row, rows 0..15 = spectrum, 16..31 = taps
-    const float2* src[4]; int dsto[4];
+    // this thread's CPT 16-byte copies per k-step: chunk ids tid + NT*q; 32 chunks per row, rows 0..15 = spectrum, 16..31 = taps
+    const float2* src[CPT]; int dsto[CPT];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const int id = tid + 256 * q, row = id >> 5, col = (id & 31) * 2;
+    for (int q = 0; q < CPT; q++) {
+        const int id = tid + NT * q, row = id >> 5, col = (id & 31) * 2;
         if (row < ROWS) src[q] = spectra + (long)min(b0 + row, nblocks - 1) * N + r0 + col;          // ragged edges shadow the last valid row
         else src[q] = taps_fft + (long)min(c0 + row - ROWS, channels - 1) * N + r0 + col;
         dsto[q] = row * FOLD_R + col;
@@ -532,14 +536,14 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
     auto issue = [&](int k, int stage) {
         const int kx = k + halfP < P ? k + halfP : k + halfP - P;
 #pragma unroll
-        for (int q = 0; q < 4; q++) cp_async16(sm + stage * STAGE + dsto[q], src[q] + (long)(q < 2 ? kx : k) * M);
+        for (int q = 0; q < CPT; q++) cp_async16(sm + stage * STAGE + dsto[q], src[q] + (long)(q < CPT / 2 ? kx : k) * M);
     };
     // (a 4-stage ring with the next step's operands pulled into registers during the FMAs was measured slower: 96 vs 88 us, 233 registers)
-    float2 acc[FOLD_CT][FOLD_BT];
+    float2 acc[FOLD_CT][BT];
 #pragma unroll
     for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
-        for (int v = 0; v < FOLD_BT; v++) acc[u][v] = make_float2(0.f, 0.f);
+        for (int v = 0; v < BT; v++) acc[u][v] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < FOLD_ST - 1; s++) { if (s < P) issue(s, s); cp_async_commit(); }
     for (int k = 0; k < P; k++) {
@@ -547,11 +551,11 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
         __syncthreads();                                                // stage k has landed for everyone; stage (k-1) is free again
         if (k + FOLD_ST - 1 < P) issue(k + FOLD_ST - 1, (k + FOLD_ST - 1) % FOLD_ST);
         cp_async_commit();
-        const float2* xs = sm + (k % FOLD_ST) * STAGE + (gb * FOLD_BT) * FOLD_R + rl;
+        const float2* xs = sm + (k % FOLD_ST) * STAGE + (gb * BT) * FOLD_R + rl;
         const float2* hs = sm + (k % FOLD_ST) * STAGE + (ROWS + gc * FOLD_CT) * FOLD_R + rl;
-        float2 x[FOLD_BT], h[FOLD_CT];
+        float2 x[BT], h[FOLD_CT];
 #pragma unroll
-        for (int v = 0; v < FOLD_BT; v++) x[v] = xs[v * FOLD_R];
+        for (int v = 0; v < BT; v++) x[v] = xs[v * FOLD_R];
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++) h[u] = hs[u * FOLD_R];
         // acc += x*h = xr*(hr, hi) + xi*(-hi, hr): two packed FMAs per accumulator, scalar-broadcast x against h and against h swapped/negated
@@ -559,11 +563,11 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
-            for (int v = 0; v < FOLD_BT; v++) acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
+            for (int v = 0; v < BT; v++) acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
-            for (int v = 0; v < FOLD_BT; v++)
+            for (int v = 0; v < BT; v++)
                 acc[u][v] = ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
     }
     // /pre_decimation, and both half swaps (fastddc.c:143-150) folded into the destination index (r - offsetbin) mod M
@@ -575,24 +579,45 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
         int d2 = (r - chan[c].offsetbin) % M;
         if (d2 < 0) d2 += M;
 #pragma unroll
-        for (int v = 0; v < FOLD_BT; v++) {
-            const int b = b0 + gb * FOLD_BT + v;
+        for (int v = 0; v < BT; v++) {
+            const int b = b0 + gb * BT + v;
             if (b < nblocks) folded[((long)c * nblocks + b) * M + d2] = make_float2(acc[u][v].x * inv_pre, acc[u][v].y * inv_pre);
         }
     }
 }
 
+// The post shift's phasors (libcsdr_gpl.c:131-160: seeded from the block's carried phase in double, advanced by the float recursion once per output) do not depend
+// on the data: one thread per (channel, block) pair walks its <= kmax steps here, on the side stream behind the state chain and under the fold, and stores
+// phasor[k][pair] (lanes = consecutive pairs: coalesced).  The IFFT kernel then only multiplies -- every output in parallel instead of one lane per row.
+__global__ void __launch_bounds__(128)
+fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict__ blk_phase, float2* __restrict__ phasor, int channels, int nblocks, int kmax)
+{
+    const long npairs = (long)channels * nblocks;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int c = (int)(p / nblocks), b = (int)(p % nblocks);
+    const DdcChan cp = chan[c];
+    const double ph = (double)blk_phase[(long)b * channels + c];
+    float co = (float)cos(ph), si = (float)sin(ph);
+    for (int k = 0; k < kmax; k++) {
+        phasor[(long)k * npairs + p] = make_float2(co, si);
+        const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+        const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+        co = cn; si = sn;
+    }
+}
+
 // IFFT_M of POST_PAIRS folded (channel, block) rows per CTA (64 threads per transform, four at a time), /M, drop the scrap, post shift + decimate.
-// The post shift is the reference's phasor recursion (libcsdr_gpl.c:131-160): sequential per row, so ONE LANE PER ROW walks it -- with sixteen rows in the
-// CTA's shared memory sixteen lanes of one warp do that side by side (the first version gave every row its own warp: 5 active threads per instruction
-// on average, 113 us; r02 ncu).  With the padded pitch of 578 complex values the sixteen lanes' LDS.64 land two to a bank at worst.  Pairs are p = c * nblocks + b.
+// The post shift multiplies by the phasors fastddc_phasor_kernel prepared (the recursion itself is sequential per row: walking it here, first with a warp per
+// row -- 5 active threads per instruction, 113 us -- then with a lane per row -- 58 us -- left the SMs idle behind sixteen serial walks).  Pairs are p = c * nblocks + b.
 constexpr int POST_PAIRS = 16;
 
 template <int M>
 __global__ void __launch_bounds__(256)
 fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __restrict__ chan, const int* __restrict__ blk_remain,
                          const float* __restrict__ blk_phase, const int* __restrict__ blk_offset, float2* __restrict__ out, long out_stride,
-                         int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw)
+                         int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw,
+                         const float2* __restrict__ phasor)
 {
     CSDRB_DYN_SMEM(smem_raw);
     float2* s = reinterpret_cast<float2*>(smem_raw);
@@ -614,24 +639,22 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         block_fft<M, NTG, true>(mys, tw, tg);
     }
     __syncthreads();
-    if (tid < POST_PAIRS && p0 + tid < npairs) {
-        const long p = p0 + tid;
+    // /M, drop the scrap, decimate, rotate by the precomputed phasor: all outputs of the CTA's rows in parallel, coalesced along each row
+    const float inv_m = 1.0f / (float)M;
+    for (int a = 0; a < POST_PAIRS; a++) {
+        const long p = p0 + a;
+        if (p >= npairs) break;
         const int c = (int)(p / nblocks), b = (int)(p % nblocks);
-        const DdcChan cp = chan[c];
-        const float2* row = s + tid * PITCH;
-        const float inv_m = 1.0f / (float)M;
         const long bi = (long)b * channels + c;
-        const double ph = (double)blk_phase[bi];
-        float co = (float)cos(ph), si = (float)sin(ph);
+        const int first = blk_remain[bi];
+        const int cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
+        const float2* row = s + a * PITCH;
         float2* y = out + (long)c * out_stride + blk_offset[bi];
-        int k = 0;
-        for (int pos = blk_remain[bi]; pos < post_input_size; pos += post_decimation) {
-            const float2 raw = row[fft_pad(scrap + pos)];
+        for (int k = tid; k < cnt; k += 256) {
+            const float2 raw = row[fft_pad(scrap + first + k * post_decimation)];
             const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
-            y[k++] = make_float2(__fsub_rn(__fmul_rn(co, w.x), __fmul_rn(si, w.y)), __fadd_rn(__fmul_rn(si, w.x), __fmul_rn(co, w.y)));
-            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
-            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
-            co = cn; si = sn;
+            const float2 ph = __ldg(phasor + (long)k * npairs + p);
+            y[k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
         }
     }
 }

@@ -12,6 +12,7 @@ static inline float __fsub_rn(float a, float b) { volatile float r = a - b; retu
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline size_t __cvta_generic_to_shared(const void*) { return 0; }
+static inline int __float2int_rz(float f) { return (int)f; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 
 #include "../../csdr_b200/csrc/common.cuh"
