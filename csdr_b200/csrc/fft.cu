@@ -342,7 +342,7 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
 #define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
             if (psmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
             k<<<(unsigned)((npairs + POST_PAIRS - 1) / POST_PAIRS), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
-                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor); } break;
+                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor, kmax); } break;
             CSDRB_FFT_SIZES(X)
 #undef X
         }

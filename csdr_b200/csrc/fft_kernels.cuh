@@ -587,23 +587,36 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 }
 
 // The post shift's phasors (libcsdr_gpl.c:131-160: seeded from the block's carried phase in double, advanced by the float recursion once per output) do not depend
-// on the data: one thread per (channel, block) pair walks its <= kmax steps here, on the side stream behind the state chain and under the fold, and stores
-// phasor[k][pair] (lanes = consecutive pairs: coalesced).  The IFFT kernel then only multiplies -- every output in parallel instead of one lane per row.
+// on the data: one lane per (channel, block) pair walks its <= kmax steps here, on the side stream behind the state chain and under the fold, and the table
+// phasor[pair][k] is written 32 steps at a time through a padded shared tile, so both this kernel's stores and the IFFT kernel's loads are coalesced rows.
+// The IFFT kernel then only multiplies -- every output in parallel instead of one lane per row.
 __global__ void __launch_bounds__(128)
 fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict__ blk_phase, float2* __restrict__ phasor, int channels, int nblocks, int kmax)
 {
+    __shared__ float2 tile_all[4][32 * 33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* tile = tile_all[warp];
     const long npairs = (long)channels * nblocks;
-    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
+    const long p_first = ((long)blockIdx.x * 4 + warp) * 32;            // this warp's 32 pairs
+    if (p_first >= npairs) return;
+    const long p = min(p_first + lane, npairs - 1);                     // lanes past the end shadow the last pair (they compute, they do not store)
     const int c = (int)(p / nblocks), b = (int)(p % nblocks);
     const DdcChan cp = chan[c];
     const double ph = (double)blk_phase[(long)b * channels + c];
     float co = (float)cos(ph), si = (float)sin(ph);
-    for (int k = 0; k < kmax; k++) {
-        phasor[(long)k * npairs + p] = make_float2(co, si);
-        const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
-        const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
-        co = cn; si = sn;
+    const int rows = (int)min((long)32, npairs - p_first);
+    for (int k0 = 0; k0 < kmax; k0 += 32) {
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            tile[lane * 33 + j] = make_float2(co, si);
+            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            co = cn; si = sn;
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; r++)
+            if (k0 + lane < kmax) phasor[(p_first + r) * kmax + k0 + lane] = tile[r * 33 + lane];
+        __syncwarp();
     }
 }
 
@@ -617,7 +630,7 @@ __global__ void __launch_bounds__(256)
 fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __restrict__ chan, const int* __restrict__ blk_remain,
                          const float* __restrict__ blk_phase, const int* __restrict__ blk_offset, float2* __restrict__ out, long out_stride,
                          int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw,
-                         const float2* __restrict__ phasor)
+                         const float2* __restrict__ phasor, int kmax)
 {
     CSDRB_DYN_SMEM(smem_raw);
     float2* s = reinterpret_cast<float2*>(smem_raw);
@@ -653,7 +666,7 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         for (int k = tid; k < cnt; k += 256) {
             const float2 raw = row[fft_pad(scrap + first + k * post_decimation)];
             const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
-            const float2 ph = __ldg(phasor + (long)k * npairs + p);
+            const float2 ph = __ldg(phasor + p * kmax + k);
             y[k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
         }
     }
