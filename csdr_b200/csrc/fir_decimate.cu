@@ -121,16 +121,37 @@ fir_bank_fast_kernel(const void* __restrict__ in_v, long in_stride, float2* __re
         for (int b = bulk_b + tid; b < 2 * valid; b += C::THREADS) stage[b] = src[b];
         mbar_wait(bar, 0);
         __syncthreads();
-        constexpr int PER = (C::IN_TILE + C::THREADS - 1) / C::THREADS;
-        unsigned short v[PER];
-#pragma unroll
-        for (int k = 0; k < PER; k++) { const int sidx = tid + k * C::THREADS; v[k] = sidx < valid ? reinterpret_cast<const unsigned short*>(stage)[sidx] : (unsigned short)0; }
-        __syncthreads();                                                     // everyone holds its bytes: the floats may now overwrite the staging area
+        // two samples (four bytes) per step: one 32-bit shared load, four table look-ups, one 128-bit shared store
+        static_assert(C::IN_TILE % 2 == 0, "the tile holds whole sample pairs");
+        constexpr int PAIRS = C::IN_TILE / 2, PER = (PAIRS + C::THREADS - 1) / C::THREADS;
+        const int vpairs = valid >> 1;                                        // whole pairs that exist (a trailing odd sample is handled below)
+        unsigned v[PER];
         const float* lut = reinterpret_cast<const float*>(smem_raw + C::SMEM_LUT);
+        if (valid == C::IN_TILE) {                                           // a whole tile (all but the last of a row): no per-element checks
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int sidx = tid + k * C::THREADS;
-            if (sidx < C::IN_TILE) xs[sidx] = sidx < valid ? make_float2(lut[v[k] & 0xff], lut[v[k] >> 8]) : make_float2(0.f, 0.f);
+            for (int k = 0; k < PER; k++) { const int i = tid + k * C::THREADS; if (PAIRS % C::THREADS == 0 || i < PAIRS) v[k] = reinterpret_cast<const unsigned*>(stage)[i]; }
+            __syncthreads();                                                 // everyone holds its bytes: the floats may now overwrite the staging area
+#pragma unroll
+            for (int k = 0; k < PER; k++) {
+                const int i = tid + k * C::THREADS;
+                if (PAIRS % C::THREADS == 0 || i < PAIRS)
+                    reinterpret_cast<float4*>(xs)[i] = make_float4(lut[v[k] & 0xffu], lut[(v[k] >> 8) & 0xffu], lut[(v[k] >> 16) & 0xffu], lut[v[k] >> 24]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; k++) { const int i = tid + k * C::THREADS; v[k] = i < vpairs ? reinterpret_cast<const unsigned*>(stage)[i] : 0u; }
+            const unsigned short odd = (valid & 1) ? reinterpret_cast<const unsigned short*>(stage)[valid - 1] : (unsigned short)0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < PER; k++) {                                  // (unrolled: a dynamic index would push v[] into local memory for the fast path too)
+                const int i = tid + k * C::THREADS;
+                if (i < PAIRS) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i < vpairs) o = make_float4(lut[v[k] & 0xffu], lut[(v[k] >> 8) & 0xffu], lut[(v[k] >> 16) & 0xffu], lut[v[k] >> 24]);
+                    else if (i == vpairs && (valid & 1)) { o.x = lut[odd & 0xffu]; o.y = lut[odd >> 8]; }
+                    reinterpret_cast<float4*>(xs)[i] = o;
+                }
+            }
         }
         __syncthreads();
     }
