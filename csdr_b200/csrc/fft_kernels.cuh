@@ -638,6 +638,20 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
     static_assert(M >= 64 && M <= 16 * NTG, "fastddc_ifft_post_kernel: 64 <= M <= 1024");
     const int tid = threadIdx.x, g = tid / NTG, tg = tid % NTG;
     const long npairs = (long)channels * nblocks, p0 = (long)blockIdx.x * POST_PAIRS;
+    __shared__ int row_first[POST_PAIRS], row_cnt[POST_PAIRS];
+    __shared__ long row_dst[POST_PAIRS];
+    if (tid < POST_PAIRS) {                                              // row bookkeeping, read long before it is needed
+        const long p = p0 + tid;
+        int first = 0, cnt = 0; long dst = 0;
+        if (p < npairs) {
+            const int c = (int)(p / nblocks), b = (int)(p % nblocks);
+            const long bi = (long)b * channels + c;
+            first = blk_remain[bi];
+            cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
+            dst = (long)c * out_stride + blk_offset[bi];
+        }
+        row_first[tid] = first; row_cnt[tid] = cnt; row_dst[tid] = dst;
+    }
 #pragma unroll 1
     for (int a = 0; a < POST_PAIRS; a += GROUPS) {                       // every thread takes part in every round (block_fft has barriers inside)
         const long p = min(p0 + a + g, npairs - 1);                     // a ragged last CTA repeats the last pair into its own row: harmless
@@ -652,23 +666,19 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         block_fft<M, NTG, true>(mys, tw, tg);
     }
     __syncthreads();
-    // /M, drop the scrap, decimate, rotate by the precomputed phasor: all outputs of the CTA's rows in parallel, coalesced along each row
+    // /M, drop the scrap, decimate, rotate by the precomputed phasor: every output of the CTA's rows is an independent item (row a, output k).  The per-row
+    // bookkeeping (first sample, count, destination) was fetched into shared memory by sixteen threads before the transforms started: no dependent global load
+    // sits in front of the items (a first version looked the rows up one after the other: 83 us for the kernel, worse than the serial walk it replaced).
     const float inv_m = 1.0f / (float)M;
-    for (int a = 0; a < POST_PAIRS; a++) {
-        const long p = p0 + a;
-        if (p >= npairs) break;
-        const int c = (int)(p / nblocks), b = (int)(p % nblocks);
-        const long bi = (long)b * channels + c;
-        const int first = blk_remain[bi];
-        const int cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
-        const float2* row = s + a * PITCH;
-        float2* y = out + (long)c * out_stride + blk_offset[bi];
-        for (int k = tid; k < cnt; k += 256) {
-            const float2 raw = row[fft_pad(scrap + first + k * post_decimation)];
-            const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
-            const float2 ph = __ldg(phasor + p * kmax + k);
-            y[k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
-        }
+    const int items = POST_PAIRS * kmax;
+#pragma unroll 2
+    for (int it = tid; it < items; it += 256) {
+        const int a = it / kmax, k = it - a * kmax;
+        if (k >= row_cnt[a]) continue;
+        const float2 raw = s[a * PITCH + fft_pad(scrap + row_first[a] + k * post_decimation)];
+        const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
+        const float2 ph = __ldg(phasor + (p0 + a) * kmax + k);
+        out[row_dst[a] + k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
     }
 }
 

@@ -36,6 +36,12 @@ if "k" in which:
     report("K1 convert_f_s16", timed(lambda: cb.convert_f_s16(f, out=s16)), n, n * 6)
     report("K1 convert_s16_f", timed(lambda: cb.convert_s16_f(s16, out=f)), n, n * 6)
     del u8, s16
+    taps3 = cb.firdes_lowpass_f(199, 0.05)
+    u8b = torch.randint(0, 256, (256, 2_400_000, 2), dtype=torch.uint8, device=dev)
+    n3 = cb.fir_out_len(2_400_000, 10, 199); y3 = torch.empty((256, n3 + (n3 & 1)), dtype=torch.complex64, device=dev)
+    report("K1+K3 u8 front end fused into the FIR bank 256x2.4M (2 + 8/D B/sample)", timed(lambda: cb.fir_decimate_bank_u8_cc(u8b, 10, taps3, out=y3)), 256 * 2_400_000, 256 * 2_400_000 * 2.8,
+           f"{256 * n3 * 199 * 4 / 1e9:.0f} Gflop per launch")
+    del u8b, y3
     C, N = 64, 2_400_000
     x = torch.rand((C, N, 2), device=dev) * 2 - 1
     y = torch.empty((C, N), dtype=torch.float32, device=dev)

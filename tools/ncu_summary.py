@@ -72,6 +72,6 @@ for arg in args:
                "duration_unit_in_report": d.get("gpu__time_duration.sum", {}).get("unit"),
                "dram_bytes_per_launch": (to_bytes(rd) or 0) + (to_bytes(wr) or 0) if rd and wr else None, "metrics": {k: v for k, v in d.items() if k != "Kernel Name"}, "stall_sampling": stalls(rep),
                "how": "ncu --set full --clock-control none --import-source on, one launch after warm-up (cold caches, serialised: compare shares and ratios, not absolutes)"}
-    out = OUT_DIR / (rep.stem.replace("r2_g6_", "r02_").replace("r2_g5_", "r02_").replace("r2_g3_", "r02_").replace("r2_g7_", "r02_").replace("r2_g8_", "r02_") + "_ncu_summary.json")
+    out = OUT_DIR / (rep.stem.replace("r2_g6_", "r02_").replace("r2_g5_", "r02_").replace("r2_g3_", "r02_").replace("r2_g7_", "r02_").replace("r2_g8_", "r02_").replace("r2_g10_", "r02_") + "_ncu_summary.json")
     out.write_text(json.dumps(summary, indent=1))
     print(out.name, summary["kernel"][:60] if summary["kernel"] else None, summary["duration_us"], summary["duration_unit_in_report"])
