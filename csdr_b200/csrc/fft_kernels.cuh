@@ -652,16 +652,23 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         }
         row_first[tid] = first; row_cnt[tid] = cnt; row_dst[tid] = dst;
     }
-#pragma unroll 1
-    for (int a = 0; a < POST_PAIRS; a += GROUPS) {                       // every thread takes part in every round (block_fft has barriers inside)
-        const long p = min(p0 + a + g, npairs - 1);                     // a ragged last CTA repeats the last pair into its own row: harmless
-        const float2* src = folded + p * M;
-        float2* mys = s + (a + g) * PITCH;
-        float2 v[PER];
+    // every thread takes part in every round (block_fft has barriers inside); the next round's row is fetched while this round's transform runs
+    float2 v[PER];
+    {
+        const float2* src = folded + min(p0 + g, npairs - 1) * M;        // a ragged last CTA repeats the last pair into its own row: harmless
 #pragma unroll
-        for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);  // all loads first
+        for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);
+    }
+#pragma unroll 1
+    for (int a = 0; a < POST_PAIRS; a += GROUPS) {
+        float2* mys = s + (a + g) * PITCH;
 #pragma unroll
         for (int k = 0; k < PER; k++) mys[fft_pad(tg + k * NTG)] = v[k];
+        if (a + GROUPS < POST_PAIRS) {
+            const float2* src = folded + min(p0 + a + GROUPS + g, npairs - 1) * M;
+#pragma unroll
+            for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);
+        }
         __syncthreads();
         block_fft<M, NTG, true>(mys, tw, tg);
     }
