@@ -290,6 +290,7 @@ def run_b200(args):
 
     for k in range(args.warmup):
         fir_step(k)
+    barrier()              # the first collective sets the communicator up (hundreds of ms): do it here, or the timed loop's own barrier lets the GPU cool off after the pre-heat
     with ClockSampler(physical_gpu_index(local)) as clk:
         if not args.quick:
             t_hold = time.perf_counter()                         # pre-heat: the timed steps below run at the clock the GPU settles to under this kernel

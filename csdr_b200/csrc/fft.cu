@@ -15,6 +15,7 @@
 #include "kernels.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -309,16 +310,24 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
         const size_t folded_elems = (size_t)channels * nblocks * fft_inv_size, phasor_elems = (size_t)channels * nblocks * (size_t)kmax;
         CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&folded), sizeof(float2) * (folded_elems + phasor_elems), st));
         float2* phasor = folded + folded_elems;
+        // CSDRB_INV_TRACE=1 (tools only): timestamps around every piece of this call, printed after a synchronize.
+        static const bool trace = getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1';
+        cudaEvent_t tev[7] = {};
+        if (trace) for (auto& e : tev) CSDRB_CUDA(cudaEventCreate(&e));
         {
             std::lock_guard<std::mutex> lk(ss->mu);                     // the fork/join events are shared by every call on this device
             CSDRB_CUDA(cudaEventRecord(ss->fork, st));
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[0], st));
             CSDRB_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[1], ss->stream));
             fastddc_state_chain_kernel<<<channels, 32, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
             CSDRB_CUDA(cudaGetLastError());
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[2], ss->stream));
             fastddc_phasor_kernel<<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
             CSDRB_CUDA(cudaGetLastError());
             CSDRB_CUDA(cudaEventRecord(ss->join, ss->stream));
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[3], ss->stream));
             const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
             static const bool wide_cta = getenv("CSDRB_FOLD_BT") && getenv("CSDRB_FOLD_BT")[0] == '4';     // A/B: 512-thread CTAs with 8 x 4 thread tiles
             static bool attr_done = false;
@@ -334,7 +343,9 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
             else fastddc_fold_kernel<8><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
                                                                    1.0f / (float)pre_decimation);
             CSDRB_CUDA(cudaGetLastError());
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[4], st));
             CSDRB_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[5], st));
         }
         const long npairs = (long)channels * nblocks;
         const size_t psmem = sizeof(float2) * (size_t)POST_PAIRS * (size_t)fft_smem_elems(fft_inv_size);
@@ -347,6 +358,15 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
 #undef X
         }
         CSDRB_CUDA(cudaGetLastError());
+        if (trace) {
+            CSDRB_CUDA(cudaEventRecord(tev[6], st));
+            CSDRB_CUDA(cudaStreamSynchronize(st));
+            float t[7] = {};
+            for (int i = 1; i < 7; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+            fprintf(stderr, "[inv trace] us from call start: side stream starts %.1f, chain done %.1f, phasors done %.1f | fold done %.1f, join passed %.1f, post done %.1f\n",
+                    t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, t[6] * 1e3f);
+            for (auto& e : tev) cudaEventDestroy(e);
+        }
         CSDRB_CUDA(cudaFreeAsync(folded, st));
         return 4;
     }

@@ -18,6 +18,8 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def raw(rep):
     out = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
+    if len(rows) < 3:                                                     # the capture's kernel filter matched no launch: nothing to summarise
+        raise SystemExit(f"{rep}: no kernel in this report (check the -k filter of the capture: it matches the base name, not the template arguments)")
     hdr = rows[0]; units = rows[1]; vals = rows[2]
     d = {}
     for h, u, v in zip(hdr, units, vals):
@@ -72,6 +74,7 @@ for arg in args:
                "duration_unit_in_report": d.get("gpu__time_duration.sum", {}).get("unit"),
                "dram_bytes_per_launch": (to_bytes(rd) or 0) + (to_bytes(wr) or 0) if rd and wr else None, "metrics": {k: v for k, v in d.items() if k != "Kernel Name"}, "stall_sampling": stalls(rep),
                "how": "ncu --set full --clock-control none --import-source on, one launch after warm-up (cold caches, serialised: compare shares and ratios, not absolutes)"}
-    out = OUT_DIR / (rep.stem.replace("r2_g6_", "r02_").replace("r2_g5_", "r02_").replace("r2_g3_", "r02_").replace("r2_g7_", "r02_").replace("r2_g8_", "r02_").replace("r2_g10_", "r02_") + "_ncu_summary.json")
+    import re
+    out = OUT_DIR / (re.sub(r"^r2_g\d+_", "r02_", rep.stem) + "_ncu_summary.json")
     out.write_text(json.dumps(summary, indent=1))
     print(out.name, summary["kernel"][:60] if summary["kernel"] else None, summary["duration_us"], summary["duration_unit_in_report"])
