@@ -324,7 +324,9 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
             CSDRB_CUDA(cudaGetLastError());
             if (trace) CSDRB_CUDA(cudaEventRecord(tev[2], ss->stream));
-            fastddc_phasor_kernel<<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
+            static const bool walk_f32 = getenv("CSDRB_PHASOR_F64") && getenv("CSDRB_PHASOR_F64")[0] == '0';     // A/B: the FMA-pipe form of the walk
+            if (walk_f32) fastddc_phasor_kernel<false><<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
+            else fastddc_phasor_kernel<true><<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
             CSDRB_CUDA(cudaGetLastError());
             CSDRB_CUDA(cudaEventRecord(ss->join, ss->stream));
             if (trace) CSDRB_CUDA(cudaEventRecord(tev[3], ss->stream));
@@ -348,6 +350,18 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
             if (trace) CSDRB_CUDA(cudaEventRecord(tev[5], st));
         }
         const long npairs = (long)channels * nblocks;
+        static const bool tiled_post = getenv("CSDRB_INV_POST") && getenv("CSDRB_INV_POST")[0] == '0';               // A/B: the sixteen-rows-per-CTA form
+        if (!tiled_post) {
+            const int rows_per_cta = 1024 / fft_inv_size;
+            const size_t rsmem = sizeof(float2) * (size_t)rows_per_cta * (size_t)fft_smem_elems(fft_inv_size);
+            switch (fft_inv_size) {
+#define X(M) case M: if constexpr (M >= 64 && M <= 1024) { \
+                fastddc_ifft_rows_kernel<M><<<(unsigned)((npairs + rows_per_cta - 1) / rows_per_cta), 128, rsmem, st>>>(folded, blk_remain, blk_offset, d_out, out_stride, \
+                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor, kmax); } break;
+                CSDRB_FFT_SIZES(X)
+#undef X
+            }
+        } else {
         const size_t psmem = sizeof(float2) * (size_t)POST_PAIRS * (size_t)fft_smem_elems(fft_inv_size);
         switch (fft_inv_size) {
 #define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
@@ -356,6 +370,7 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                                                                 scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor, kmax); } break;
             CSDRB_FFT_SIZES(X)
 #undef X
+        }
         }
         CSDRB_CUDA(cudaGetLastError());
         if (trace) {

@@ -294,6 +294,32 @@ __device__ __forceinline__ void fft_pass_last(float2* __restrict__ s, const floa
     }
 }
 
+// fft_pass_last with the thread's compile-time slot handed to the sink: out.slot(b, r, i, v) gets butterfly b, leg r (i = j(b) + r*N/8), so a sink can
+// keep per-element data it fetched EARLIER (before the middle passes) in registers indexed [b][r] -- out.prefetch() is the caller's business.
+template <int N, int NT, bool INV, typename Out>
+__device__ __forceinline__ void fft_pass_last_slots(float2* __restrict__ s, const float2* __restrict__ tw, int tid, Out& out)
+{
+    constexpr int R = 8, NB = N / 8, NS = N / 8;
+    constexpr int PER = (NB + NT - 1) / NT;
+    static_assert(PER * R <= 16, "block_fft needs NT >= N/16 threads");
+    static_assert(NB % NT == 0, "slot sinks want every slot populated");
+    float2 v[PER][R];
+#pragma unroll
+    for (int b = 0; b < PER; b++) {
+        const int j = tid + b * NT;
+#pragma unroll
+        for (int r = 0; r < R; r++) v[b][r] = s[fft_pad(j + r * NB)];
+        fft_butterfly<N, R, NS, INV>(v[b], j, tw);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < PER; b++) {
+        const int j = tid + b * NT;
+#pragma unroll
+        for (int r = 0; r < R; r++) out.slot(b, r, j + r * NS, v[b][r]);
+    }
+}
+
 template <int N, int NT, int NS, bool INV>
 __device__ __forceinline__ void fft_r8_middle_passes(float2* __restrict__ s, const float2* __restrict__ tw, int tid)
 {

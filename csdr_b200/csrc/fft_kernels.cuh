@@ -590,6 +590,11 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 // on the data: one lane per (channel, block) pair walks its <= kmax steps here, on the side stream behind the state chain and under the fold, and the table
 // phasor[pair][k] is written 32 steps at a time through a padded shared tile, so both this kernel's stores and the IFFT kernel's loads are coalesced rows.
 // The IFFT kernel then only multiplies -- every output in parallel instead of one lane per row.
+// F64 = the same recursion on the FP64 pipe: a product of two floats is exact in double and a sum of two floats rounded to double and then to float equals the
+// float sum (53 >= 2*24 + 2 bits: double rounding is innocuous for + - *), so (float)((double)a * (double)b) and (float)((double)x - (double)y) ARE
+// __fmul_rn / __fsub_rn, bit for bit -- but DMUL / DADD / F2F do not queue behind the fold kernel's FFMA2 stream on the FMA pipe, which this kernel shares
+// the SMs with (timeline r02: 57 us under the fold with FMUL/FADD, 9.7 us alone).
+template <bool F64>
 __global__ void __launch_bounds__(128)
 fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict__ blk_phase, float2* __restrict__ phasor, int channels, int nblocks, int kmax)
 {
@@ -605,12 +610,21 @@ fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict_
     const double ph = (double)blk_phase[(long)b * channels + c];
     float co = (float)cos(ph), si = (float)sin(ph);
     const int rows = (int)min((long)32, npairs - p_first);
+    const double cd = (double)cp.cosdelta, sd = (double)cp.sindelta;
     for (int k0 = 0; k0 < kmax; k0 += 32) {
 #pragma unroll 4
         for (int j = 0; j < 32; j++) {
             tile[lane * 33 + j] = make_float2(co, si);
-            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
-            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            float cn, sn;
+            if constexpr (F64) {
+                const double cw = (double)co, sw = (double)si;
+                const double a = (double)__double2float_rn(cw * cd), b2 = (double)__double2float_rn(sw * sd);
+                const double e = (double)__double2float_rn(sw * cd), f = (double)__double2float_rn(cw * sd);
+                cn = __double2float_rn(a - b2); sn = __double2float_rn(e + f);
+            } else {
+                cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+                sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
+            }
             co = cn; si = sn;
         }
         __syncwarp();
@@ -687,6 +701,57 @@ fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __res
         const float2 ph = __ldg(phasor + (p0 + a) * kmax + k);
         out[row_dst[a] + k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
     }
+}
+
+
+// The same step with the transform's I/O fused (round 2, second form): a row is M/8 threads, a CTA is 128 threads = 1024/M rows; the first pass reads the folded
+// row from global memory, the last pass hands every finished element to the sink below, which drops the scrap, decimates, multiplies by the phasor fetched
+// BEFORE the middle passes and stores: two shared-memory round trips per row instead of four, no staging copy, no item loop, and 8 KB of shared memory per
+// CTA so that sixteen CTAs share an SM (the tiled form above: three CTAs, 32 % of the warp slots, half of its stall samples on the global loads).
+template <int M>
+struct FastddcPostSink {
+    float2* y; float2 ph[8]; int kk[8]; float inv_m;
+    __device__ __forceinline__ void slot(int /*b*/, int r, int /*i*/, float2 v) const
+    {
+        if (kk[r] < 0) return;
+        const float2 w = make_float2(v.x * inv_m, v.y * inv_m);
+        y[kk[r]] = make_float2(__fsub_rn(__fmul_rn(ph[r].x, w.x), __fmul_rn(ph[r].y, w.y)), __fadd_rn(__fmul_rn(ph[r].y, w.x), __fmul_rn(ph[r].x, w.y)));
+    }
+};
+
+template <int M>
+__global__ void __launch_bounds__(128)
+fastddc_ifft_rows_kernel(const float2* __restrict__ folded, const int* __restrict__ blk_remain, const int* __restrict__ blk_offset, float2* __restrict__ out,
+                         long out_stride, int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw,
+                         const float2* __restrict__ phasor, int kmax)
+{
+    CSDRB_DYN_SMEM(smem_raw);
+    constexpr int NTG = M / 8, G = 128 / NTG, PITCH = fft_smem_elems(M), R0 = fft_first_radix(M);
+    static_assert(M >= 64 && M <= 1024, "fastddc_ifft_rows_kernel: 64 <= M <= 1024");
+    const int tid = threadIdx.x, g = tid / NTG, tg = tid % NTG;
+    float2* s = reinterpret_cast<float2*>(smem_raw) + g * PITCH;
+    const long npairs = (long)channels * nblocks, p = (long)blockIdx.x * G + g;
+    const bool valid = p < npairs;
+    const long pc = valid ? p : npairs - 1;                             // rows past the end shadow the last one (they take part in the barriers, they do not store)
+    const int c = (int)(pc / nblocks), b = (int)(pc % nblocks);
+    const long bi = (long)b * channels + c;
+    const int first = __ldg(blk_remain + bi), off = __ldg(blk_offset + bi);       // in flight while the first pass loads the row
+    FftRowIn src(folded + pc * M);
+    fft_pass_first<M, NTG, R0, true>(s, tg, src);
+    FastddcPostSink<M> sink;
+    sink.inv_m = 1.0f / (float)M;
+    sink.y = out + (long)c * out_stride + off;
+    const int cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {                                       // this thread's last-pass elements are tg + r*M/8: which outputs are they, and their phasors
+        const int q = tg + r * NTG - scrap - first;
+        const int k = q >= 0 ? q / post_decimation : -1;
+        const bool keep = valid && k >= 0 && k < cnt && k * post_decimation == q;
+        sink.kk[r] = keep ? k : -1;
+        sink.ph[r] = keep ? __ldg(phasor + pc * kmax + k) : make_float2(0.f, 0.f);
+    }
+    fft_r8_middle_passes<M, NTG, R0, true>(s, tw, tg);
+    fft_pass_last_slots<M, NTG, true>(s, tw, tg, sink);
 }
 
 }  // namespace csdrb

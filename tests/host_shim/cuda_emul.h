@@ -249,6 +249,7 @@ static inline size_t __cvta_generic_to_shared(const void*) { return 0; }
 static inline int __float2int_rz(float f) { return (int)f; }                       // callers guard the range, as they must on the GPU
 static inline int __float2int_rn(float f) { return (int)nearbyintf(f); }
 static inline float __int2float_rn(int i) { return (float)i; }
+static inline float __double2float_rn(double d) { return (float)d; }         // round to nearest even (the default rounding mode of the host)
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T*, cudaFuncAttribute, int) { return cudaSuccess; }

@@ -530,7 +530,7 @@ def test_k9_golden_and_dropin_kernel(fft, oracle):
     assert rel_rms(out, want) < 2e-6
 
 
-@pytest.mark.parametrize("bw,dec,shift", [(0.05, 8, 0.123), (0.05, 3, -0.2), (0.01, 6, 0.25)])
+@pytest.mark.parametrize("bw,dec,shift", [(0.05, 8, 0.123), (0.05, 3, -0.2), (0.01, 6, 0.25), (0.05, 4, 0.2), (0.02, 4, 0.05), (0.05, 16, -0.3), (0.05, 32, 0.4)])
 def test_k8_fastddc_forward_and_inverse(fft, oracle, bw, dec, shift):
     """a12/a13 against the oracle (and, for the first geometry, the golden spectra / channel output of the compiled reference);
     decimation 3 has pre_decimation 1 and takes the one-CTA-per-(block, channel) kernel, the others the tiled one."""

@@ -75,3 +75,28 @@ def test_whole_chains(wrap):
     # a caller's first phase may be anything: the first steps take the fallback, then the chain is inside the window
     assert wrap.table_chain(2900.0, 1.0e5, 2000) == -1
     assert wrap.table_chain(-2900.0, -7.5, 2000) == -1
+
+
+def test_fp64_pipe_walk_rounds_like_fp32():
+    """fastddc_phasor_kernel<true> runs the float recursion on the FP64 pipe: (float)((double)a * (double)b) and (float)((double)x +- (double)y) must be the
+    float product / sum bit for bit (53 >= 2*24 + 2).  Checked on 4 M random pairs incl. tiny and cancelling operands, and on a 4096-step phasor walk."""
+    rng = np.random.default_rng(11)
+    n = 1 << 22
+    a = (rng.standard_normal(n) * np.exp(rng.uniform(-60, 3, n))).astype(np.float32)
+    b = (rng.standard_normal(n) * np.exp(rng.uniform(-60, 3, n))).astype(np.float32)
+    b[: n // 8] = -a[: n // 8] * np.float32(1 + 2.0 ** -20)                                          # near cancellation
+    with np.errstate(under="ignore"):
+        assert np.array_equal((a.astype(np.float64) * b.astype(np.float64)).astype(np.float32).view(np.uint32), (a * b).view(np.uint32))
+        assert np.array_equal((a.astype(np.float64) + b.astype(np.float64)).astype(np.float32).view(np.uint32), (a + b).view(np.uint32))
+        assert np.array_equal((a.astype(np.float64) - b.astype(np.float64)).astype(np.float32).view(np.uint32), (a - b).view(np.uint32))
+    rate = rng.uniform(-0.5, 0.5, 512).astype(np.float32)
+    cd, sd = np.cos(np.float64(rate) * np.pi).astype(np.float32), np.sin(np.float64(rate) * np.pi).astype(np.float32)
+    c32, s32 = np.ones(512, np.float32), np.zeros(512, np.float32)
+    c64, s64 = c32.copy(), s32.copy()
+    f = lambda v: v.astype(np.float64)
+    for _ in range(4096):
+        c32, s32 = c32 * cd - s32 * sd, s32 * cd + c32 * sd
+        a1, a2 = (f(c64) * f(cd)).astype(np.float32), (f(s64) * f(sd)).astype(np.float32)
+        a3, a4 = (f(s64) * f(cd)).astype(np.float32), (f(c64) * f(sd)).astype(np.float32)
+        c64, s64 = (f(a1) - f(a2)).astype(np.float32), (f(a3) + f(a4)).astype(np.float32)
+    assert np.array_equal(c32.view(np.uint32), c64.view(np.uint32)) and np.array_equal(s32.view(np.uint32), s64.view(np.uint32))
