@@ -477,22 +477,21 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
     shifts_all = list(np.linspace(-0.45, 0.45, c3 * world))
     shifts = shifts_all[rank * c3:(rank + 1) * c3]
     sp, ov = cb.fastddc_fwd_cc(xw, ddc)
-    o3, counts, st = cb.fastddc_inv_bank_cc(sp, shifts, dec3, bw3)
-    _, _, scratch = st[("buffers", nblocks)]
+    plan3 = cb.FastddcInvPlan(shifts, dec3, bw3, nblocks, device=dev)      # csdrb_fastddc_inv_plan_*: the state chain + phasors of step k+1 are prepared during step k
+    o3, counts = plan3.out, plan3.counts
     bc3 = Bcast(xw)
 
     def step3(_k):
         w = bc3.next()
         check(L.csdrb_fastddc_fwd_cc(w.data_ptr(), sp.data_ptr(), ov.data_ptr(), ddc.fft_size, ddc.input_size, nblocks, cur_stream()), "csdrb_fastddc_fwd_cc")
         bc3.release(w)
-        check(L.csdrb_fastddc_inv_bank_cc(sp.data_ptr(), nblocks, st["taps_fft"].data_ptr(), st["chan"].data_ptr(), c3, C.byref(st["geometry"]),
-                                          st["remain"].data_ptr(), st["phase"].data_ptr(), o3.data_ptr(), o3.stride(0), counts.data_ptr(),
-                                          scratch.data_ptr(), scratch.numel(), cur_stream()), "csdrb_fastddc_inv_bank_cc")
+        check(L.csdrb_fastddc_inv_plan_run(plan3.h, sp.data_ptr(), plan3.taps_fft.data_ptr(), o3.data_ptr(), o3.stride(0), counts.data_ptr(), cur_stream()),
+              "csdrb_fastddc_inv_plan_run")
 
     per_blk = ddc.post_input_size // ddc.post_decimation
     flops3 = nblocks * (5.0 * ddc.fft_size * 14 + c3 * (8.0 * ddc.fft_size + 5.0 * ddc.fft_inv_size * 9))
     out.append(leg("cfg3_fastddc", step3, 3, nsamp, nsamp * 8.0 + c3 * nblocks * per_blk * 8.0, flops3, "hbm",
-                   "forward 16384-pt FFT + inverse bank per step; algorithmic bytes = wideband samples in + channel outputs (SURVEY 8(d): 16 B/sample at 64 ch); "
+                   "forward 16384-pt FFT + inverse bank (csdrb_fastddc_inv_plan_run: fold + IFFT, the post-shift state chain of the next step prepared meanwhile) per step; algorithmic bytes = wideband samples in + channel outputs (SURVEY 8(d): 16 B/sample at 64 ch); "
                    "the path is bound on chip (fold = 8*N flop per channel and block), fp32_tflops says how hard",
                    {"workload": "fastddc overlap-save: 16384-pt FFT, 64 output channels from one 61.44 Msps wideband stream (BASELINE configs[2])", "channels_per_gpu": c3,
                     "channels_total": c3 * world, "blocks_per_step": nblocks, "block_samples": ddc.input_size, "fft_size": ddc.fft_size, "fft_inv_size": ddc.fft_inv_size,
@@ -500,7 +499,8 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
                     "scaling": "strong" if world > 1 else "n/a", "x_real_time_at_61.44_Msps": None}))
     out[-1]["config"]["x_real_time_at_61.44_Msps"] = out[-1]["value"] / 61.44
     torch.cuda.synchronize()
-    del xw, sp, o3, st, bc3
+    plan3.close()
+    del xw, sp, o3, bc3
     torch.cuda.empty_cache()
 
     # ---- config 5: bandpass_fir_fft_cc overlap-add bank, 4096-pt, 512 channels (512 / N per GPU), block-size sweep -------------------------

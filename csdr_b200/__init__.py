@@ -121,6 +121,12 @@ def lib() -> C.CDLL:
     L.csdrb_ddc_bank_offset.argtypes = [vp]
     L.csdrb_ddc_bank_process.argtypes = [vp, vp, it, vp, lg, vp]
     L.csdrb_ddc_bank_rechunk.argtypes = [vp]
+    L.csdrb_fastddc_inv_plan_create.argtypes = [vp, it, vp, it]; L.csdrb_fastddc_inv_plan_create.restype = vp
+    L.csdrb_fastddc_inv_plan_run.argtypes = [vp, vp, vp, vp, lg, vp, vp]
+    L.csdrb_fastddc_inv_plan_set_channel.argtypes = [vp, it, vp]
+    L.csdrb_fastddc_inv_plan_get_state.argtypes = [vp, vp, vp]
+    L.csdrb_fastddc_inv_plan_set_state.argtypes = [vp, vp, vp]
+    L.csdrb_fastddc_inv_plan_destroy.argtypes = [vp]
     L.csdrb_multi_bank_create.argtypes = [it, C.POINTER(C.c_int), it, C.POINTER(C.c_float), it, C.POINTER(C.c_float), it, it, it, it]; L.csdrb_multi_bank_create.restype = vp
     L.csdrb_multi_bank_destroy.argtypes = [vp]
     L.csdrb_multi_bank_devices.argtypes = [vp]
@@ -885,6 +891,69 @@ def fastddc_inv_bank_cc(spectra, shifts, decimation: int, transition_bw: float, 
                                            state["remain"].data_ptr(), state["phase"].data_ptr(), out.data_ptr(), out.stride(0), counts.data_ptr(),
                                            scratch.data_ptr(), scratch.numel(), _stream()), "fastddc_inv_bank_cc")
     return out, counts, state
+
+
+def _fastddc_chan_rows(ddcs) -> np.ndarray:
+    chan = np.zeros((len(ddcs), 4), np.float32)                          # csdrb_fastddc_chan_t {int offsetbin; float sindelta, cosdelta, rate}
+    chan.view(np.int32)[:, 0] = [d.offsetbin for d in ddcs]
+    chan[:, 1] = [d.dsadata.sindelta for d in ddcs]; chan[:, 2] = [d.dsadata.cosdelta for d in ddcs]; chan[:, 3] = [d.dsadata.rate for d in ddcs]
+    return chan
+
+
+class FastddcInvPlan:
+    """csdrb_fastddc_inv_plan_*: the fastddc inverse bank with the carried post-shift state inside and a fixed number of blocks per run; the state chain and
+    the phasors of run k+1 are prepared while run k executes.  Same outputs as fastddc_inv_bank_cc, bit for bit."""
+
+    def __init__(self, shifts, decimation: int, transition_bw: float, nblocks: int, window: str = "HAMMING", device="cuda"):
+        import torch
+        self.shifts = [float(s) for s in shifts]
+        self.decimation, self.transition_bw, self.window, self.nblocks, self.device = decimation, transition_bw, window, nblocks, device
+        ddcs = [fastddc_init(transition_bw, decimation, s) for s in self.shifts]
+        self.geometry = ddcs[0]
+        self.channels = len(ddcs)
+        self.taps_fft = torch.stack([fastddc_make_taps_fft(d, s, decimation, window, device) for d, s in zip(ddcs, self.shifts)]).contiguous()
+        chan = _fastddc_chan_rows(ddcs)
+        self.h = lib().csdrb_fastddc_inv_plan_create(chan.ctypes.data, self.channels, C.addressof(self.geometry), nblocks)
+        if not self.h:
+            raise CsdrB200Error(f"csdrb_fastddc_inv_plan_create: {lib().csdrb_last_error().decode()}")
+        per_block = self.geometry.post_input_size // self.geometry.post_decimation + 1
+        self.out = torch.empty((self.channels, nblocks * per_block + 2), dtype=torch.complex64, device=device)
+        self.counts = torch.zeros(self.channels, dtype=torch.int32, device=device)
+
+    def run(self, spectra, out=None):
+        """spectra [nblocks, fft_size] complex64 (fastddc_fwd_cc) -> (out [C, ...], counts [C] int32 on the device)"""
+        assert spectra.shape == (self.nblocks, self.geometry.fft_size) and spectra.is_contiguous()
+        out = self.out if out is None else out
+        _check(lib().csdrb_fastddc_inv_plan_run(self.h, spectra.data_ptr(), self.taps_fft.data_ptr(), out.data_ptr(), out.stride(0), self.counts.data_ptr(), _stream()),
+               "fastddc_inv_plan_run")
+        return out, self.counts
+
+    def set_shift(self, channel: int, shift: float):
+        """retune one channel from the next run on (csdr.c:2342-2351 redone for that channel)"""
+        d = fastddc_init(self.transition_bw, self.decimation, float(shift))
+        self.taps_fft[channel].copy_(fastddc_make_taps_fft(d, float(shift), self.decimation, self.window, self.device))
+        row = _fastddc_chan_rows([d])
+        _check(lib().csdrb_fastddc_inv_plan_set_channel(self.h, channel, row.ctypes.data), "fastddc_inv_plan_set_channel")
+        self.shifts[channel] = float(shift)
+
+    def state(self):
+        remain = np.zeros(self.channels, np.int32); phase = np.zeros(self.channels, np.float32)
+        _check(lib().csdrb_fastddc_inv_plan_get_state(self.h, remain.ctypes.data, phase.ctypes.data), "fastddc_inv_plan_get_state")
+        return remain, phase
+
+    def set_state(self, remain, phase):
+        remain = np.ascontiguousarray(remain, np.int32); phase = np.ascontiguousarray(phase, np.float32)
+        _check(lib().csdrb_fastddc_inv_plan_set_state(self.h, remain.ctypes.data, phase.ctypes.data), "fastddc_inv_plan_set_state")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().csdrb_fastddc_inv_plan_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ddc_bank(wide, rates, decimation: int, taps: np.ndarray, demod: bool = True, chunk: int = 1024, offset: int = 0,

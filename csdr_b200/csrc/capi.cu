@@ -541,6 +541,52 @@ int csdrb_fastddc_inv_bank_cc(const complexf* d_spectra, int nblocks, const comp
     return rc < 0 ? rc : counted(0, rc);
 }
 
+struct csdrb_fastddc_inv_plan { void* impl; };
+
+csdrb_fastddc_inv_plan_t* csdrb_fastddc_inv_plan_create(const csdrb_fastddc_chan_t* chan, int channels, const fastddc_t* g, int nblocks)
+{
+    if (too_many_channels(channels, "fastddc_inv plan")) return nullptr;
+    if (!chan || !g) { set_error("fastddc_inv_plan_create: null pointer"); return nullptr; }
+    void* impl = nullptr;
+    if (fastddc_inv_plan_create(&impl, chan, channels, nblocks, g->fft_size, g->fft_inv_size, g->pre_decimation, g->scrap, g->post_input_size, g->post_decimation) < 0) return nullptr;
+    auto* p = new csdrb_fastddc_inv_plan_t{impl};
+    return p;
+}
+
+int csdrb_fastddc_inv_plan_run(csdrb_fastddc_inv_plan_t* plan, const complexf* d_spectra, const complexf* d_taps_fft, complexf* d_out, long out_stride,
+                               int* d_out_total, void* stream)
+{
+    if (!plan) { set_error("fastddc_inv_plan_run: null plan"); return -1; }
+    int rc = fastddc_inv_plan_run(plan->impl, reinterpret_cast<const float2*>(d_spectra), reinterpret_cast<const float2*>(d_taps_fft), reinterpret_cast<float2*>(d_out),
+                                  out_stride, d_out_total, S(stream));
+    return rc < 0 ? rc : counted(rc, 4);
+}
+
+int csdrb_fastddc_inv_plan_set_channel(csdrb_fastddc_inv_plan_t* plan, int channel, const csdrb_fastddc_chan_t* chan)
+{
+    if (!plan) { set_error("fastddc_inv_plan_set_channel: null plan"); return -1; }
+    return fastddc_inv_plan_set_channel(plan->impl, channel, chan);
+}
+
+int csdrb_fastddc_inv_plan_get_state(csdrb_fastddc_inv_plan_t* plan, int* remain, float* phase)
+{
+    if (!plan) { set_error("fastddc_inv_plan_get_state: null plan"); return -1; }
+    return fastddc_inv_plan_get_state(plan->impl, remain, phase);
+}
+
+int csdrb_fastddc_inv_plan_set_state(csdrb_fastddc_inv_plan_t* plan, const int* remain, const float* phase)
+{
+    if (!plan) { set_error("fastddc_inv_plan_set_state: null plan"); return -1; }
+    return fastddc_inv_plan_set_state(plan->impl, remain, phase);
+}
+
+void csdrb_fastddc_inv_plan_destroy(csdrb_fastddc_inv_plan_t* plan)
+{
+    if (!plan) return;
+    fastddc_inv_plan_destroy(plan->impl);
+    delete plan;
+}
+
 int csdrb_apply_window_rows_c(const complexf* d_in, complexf* d_out, const float* d_window, int size, long rows, void* stream)
 {
     if (!d_in || !d_out || !d_window) { set_error("apply_window: null pointer"); return -1; }

@@ -276,6 +276,73 @@ static SideStream* side_stream()
 }
 
 
+// device arrays of the data-independent half of an inverse-bank call
+struct InvPrep { int* blk_remain; float* blk_phase; int* blk_offset; WrapTable* tables; float2* phasor; int kmax; };
+
+// Geometries the fold path covers: whole 64-residue CTAs and an even pre-decimation (the half swap of the spectrum is then a rotation of the
+// fold's k index).  CSDRB_INV_FOLD=0 sends everything to the round-1 kernels.
+bool fastddc_inv_fold_ok(int fft_size, int fft_inv_size)
+{
+    static const bool fold_off = getenv("CSDRB_INV_FOLD") && getenv("CSDRB_INV_FOLD")[0] == '0';
+    if (fold_off || fft_inv_size < 64 || fft_inv_size > 1024 || (fft_inv_size & (fft_inv_size - 1)) || fft_size % fft_inv_size) return false;
+    const int P = fft_size / fft_inv_size;
+    return P >= 2 && P % 2 == 0;
+}
+
+// The data-independent half of a call: block-to-block {remain, phase} chain (updates the carried state, writes the per-block state and the
+// output counts) and the post-shift phasors of every (channel, block) row.  Everything on stream `s`.
+int launch_fastddc_inv_prepare(const void* d_chan, int channels, int nblocks, int post_input_size, int post_decimation, int* d_remain_io, float* d_phase_io,
+                               int* d_out_total, const InvPrep& p, cudaStream_t s)
+{
+    fastddc_state_chain_kernel<<<channels, 32, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
+                                                       p.blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, p.tables);
+    CSDRB_CUDA(cudaGetLastError());
+    fastddc_phasor_kernel<<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, s>>>(static_cast<const DdcChan*>(d_chan), p.blk_phase, p.phasor, channels, nblocks, p.kmax);
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// The data half: fold on `st`, then (after `prepared`, if given) IFFT + post shift.  `after_fold`, if given, is recorded between the two.
+int launch_fastddc_inv_apply(const float2* d_spectra, int nblocks, const float2* d_taps_fft, const void* d_chan, int channels, int fft_size, int fft_inv_size,
+                             int pre_decimation, int scrap, int post_input_size, int post_decimation, const InvPrep& p, float2* folded, float2* d_out,
+                             long out_stride, cudaEvent_t prepared, cudaEvent_t after_fold, cudaStream_t st)
+{
+    const float2* tw = nullptr;
+    if (int rc = get_twiddles(fft_inv_size, &tw, st)) return rc;
+    const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
+    static const bool wide_cta = getenv("CSDRB_FOLD_BT") && getenv("CSDRB_FOLD_BT")[0] == '4';     // A/B: 512-thread CTAs with 8 x 4 thread tiles
+    static const bool x_first = getenv("CSDRB_FOLD_HFIRST") && getenv("CSDRB_FOLD_HFIRST")[0] == '0';   // A/B: the sample, not the tap pair, as first multiplicand
+    static bool attr_done = false;
+    if (!attr_done) {
+        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        attr_done = true;
+    }
+    const dim3 fgrid(fft_inv_size / FOLD_R, (channels + 2 * FOLD_CT - 1) / (2 * FOLD_CT), (nblocks + 2 * FOLD_BT - 1) / (2 * FOLD_BT));
+    if (fgrid.y > 65535u || fgrid.z > 65535u) { set_error("fastddc_inv: bank too large for one call"); return -1; }
+    const float inv_pre = 1.0f / (float)pre_decimation;
+    const DdcChan* dc = static_cast<const DdcChan*>(d_chan);
+    if (wide_cta) fastddc_fold_kernel<4, true><<<fgrid, 512, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
+    else if (x_first) fastddc_fold_kernel<8, false><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
+    else fastddc_fold_kernel<8, true><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
+    CSDRB_CUDA(cudaGetLastError());
+    if (after_fold) CSDRB_CUDA(cudaEventRecord(after_fold, st));
+    if (prepared) CSDRB_CUDA(cudaStreamWaitEvent(st, prepared, 0));
+    const long npairs = (long)channels * nblocks;
+    const int rows_per_cta = 1024 / fft_inv_size;
+    const size_t rsmem = sizeof(float2) * (size_t)rows_per_cta * (size_t)fft_smem_elems(fft_inv_size);
+    switch (fft_inv_size) {
+#define X(M) case M: if constexpr (M >= 64 && M <= 1024) { \
+        fastddc_ifft_rows_kernel<M><<<(unsigned)((npairs + rows_per_cta - 1) / rows_per_cta), 128, rsmem, st>>>(folded, p.blk_remain, p.blk_offset, d_out, out_stride, \
+                                                        scrap, post_input_size, post_decimation, nblocks, channels, tw, p.phasor, p.kmax); } break;
+        CSDRB_FFT_SIZES(X)
+#undef X
+    }
+    CSDRB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 size_t fastddc_inv_scratch_bytes(int channels, int nblocks)
 {
     return (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15) + (nblocks > 96 ? (size_t)channels * sizeof(WrapTable) : 0);
@@ -298,88 +365,39 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     int* blk_offset = reinterpret_cast<int*>(blk_phase + (size_t)channels * nblocks);
     WrapTable* tables = nblocks > 96 ? reinterpret_cast<WrapTable*>(static_cast<char*>(d_scratch) + (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15)) : nullptr;
     // Round-2 path: fold as a batched contraction (fastddc_fold_kernel), IFFT + post shift in a second kernel, and the data-independent
-    // block-to-block state chain on a side stream meanwhile.  Needs whole 64-residue CTAs and an even pre-decimation (the half swap of the
-    // spectrum is then a rotation of the fold's k index); anything else takes the round-1 kernels below.  CSDRB_INV_FOLD=0 forces those.
-    static const bool fold_off = getenv("CSDRB_INV_FOLD") && getenv("CSDRB_INV_FOLD")[0] == '0';
-    const int P = fft_size / fft_inv_size;
-    if (!fold_off && fft_inv_size >= 64 && fft_inv_size <= 1024 && P >= 2 && P % 2 == 0) {
+    // block-to-block state chain + phasor walk on a side stream meanwhile.  Anything fastddc_inv_fold_ok() refuses takes the round-1 kernels below.
+    if (fastddc_inv_fold_ok(fft_size, fft_inv_size)) {
         SideStream* ss = side_stream();
         if (!ss) return -1;
         float2* folded = nullptr;
         const int kmax = (post_input_size + post_decimation - 1) / post_decimation;      // outputs one block can emit
         const size_t folded_elems = (size_t)channels * nblocks * fft_inv_size, phasor_elems = (size_t)channels * nblocks * (size_t)kmax;
         CSDRB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&folded), sizeof(float2) * (folded_elems + phasor_elems), st));
-        float2* phasor = folded + folded_elems;
-        // CSDRB_INV_TRACE=1 (tools only): timestamps around every piece of this call, printed after a synchronize.
+        InvPrep pr; pr.blk_remain = blk_remain; pr.blk_phase = blk_phase; pr.blk_offset = blk_offset; pr.tables = tables; pr.phasor = folded + folded_elems; pr.kmax = kmax;
+        // CSDRB_INV_TRACE=1 (tools only): timestamps around the pieces of this call, printed after a synchronize.
         static const bool trace = getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1';
-        cudaEvent_t tev[7] = {};
+        cudaEvent_t tev[4] = {};
         if (trace) for (auto& e : tev) CSDRB_CUDA(cudaEventCreate(&e));
+        int rc = 0;
         {
             std::lock_guard<std::mutex> lk(ss->mu);                     // the fork/join events are shared by every call on this device
             CSDRB_CUDA(cudaEventRecord(ss->fork, st));
             if (trace) CSDRB_CUDA(cudaEventRecord(tev[0], st));
             CSDRB_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
-            if (trace) CSDRB_CUDA(cudaEventRecord(tev[1], ss->stream));
-            fastddc_state_chain_kernel<<<channels, 32, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
-                                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
-            CSDRB_CUDA(cudaGetLastError());
-            if (trace) CSDRB_CUDA(cudaEventRecord(tev[2], ss->stream));
-            static const bool walk_f32 = getenv("CSDRB_PHASOR_F64") && getenv("CSDRB_PHASOR_F64")[0] == '0';     // A/B: the FMA-pipe form of the walk
-            if (walk_f32) fastddc_phasor_kernel<false><<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
-            else fastddc_phasor_kernel<true><<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, ss->stream>>>(static_cast<const DdcChan*>(d_chan), blk_phase, phasor, channels, nblocks, kmax);
-            CSDRB_CUDA(cudaGetLastError());
+            rc = launch_fastddc_inv_prepare(d_chan, channels, nblocks, post_input_size, post_decimation, d_remain_io, d_phase_io, d_out_total, pr, ss->stream);
+            if (rc < 0) return rc;
             CSDRB_CUDA(cudaEventRecord(ss->join, ss->stream));
-            if (trace) CSDRB_CUDA(cudaEventRecord(tev[3], ss->stream));
-            const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
-            static const bool wide_cta = getenv("CSDRB_FOLD_BT") && getenv("CSDRB_FOLD_BT")[0] == '4';     // A/B: 512-thread CTAs with 8 x 4 thread tiles
-            static bool attr_done = false;
-            if (!attr_done) {
-                CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-                attr_done = true;
-            }
-            const dim3 fgrid(fft_inv_size / FOLD_R, (channels + 2 * FOLD_CT - 1) / (2 * FOLD_CT), (nblocks + 2 * FOLD_BT - 1) / (2 * FOLD_BT));
-            if (fgrid.y > 65535u || fgrid.z > 65535u) { set_error("fastddc_inv: bank too large for one call"); return -1; }
-            if (wide_cta) fastddc_fold_kernel<4><<<fgrid, 512, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
-                                                                           1.0f / (float)pre_decimation);
-            else fastddc_fold_kernel<8><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, static_cast<const DdcChan*>(d_chan), folded, fft_size, fft_inv_size, nblocks, channels,
-                                                                   1.0f / (float)pre_decimation);
-            CSDRB_CUDA(cudaGetLastError());
-            if (trace) CSDRB_CUDA(cudaEventRecord(tev[4], st));
-            CSDRB_CUDA(cudaStreamWaitEvent(st, ss->join, 0));
-            if (trace) CSDRB_CUDA(cudaEventRecord(tev[5], st));
+            if (trace) CSDRB_CUDA(cudaEventRecord(tev[1], ss->stream));
+            rc = launch_fastddc_inv_apply(d_spectra, nblocks, d_taps_fft, d_chan, channels, fft_size, fft_inv_size, pre_decimation, scrap, post_input_size, post_decimation,
+                                          pr, folded, d_out, out_stride, ss->join, trace ? tev[2] : nullptr, st);
+            if (rc < 0) return rc;
         }
-        const long npairs = (long)channels * nblocks;
-        static const bool tiled_post = getenv("CSDRB_INV_POST") && getenv("CSDRB_INV_POST")[0] == '0';               // A/B: the sixteen-rows-per-CTA form
-        if (!tiled_post) {
-            const int rows_per_cta = 1024 / fft_inv_size;
-            const size_t rsmem = sizeof(float2) * (size_t)rows_per_cta * (size_t)fft_smem_elems(fft_inv_size);
-            switch (fft_inv_size) {
-#define X(M) case M: if constexpr (M >= 64 && M <= 1024) { \
-                fastddc_ifft_rows_kernel<M><<<(unsigned)((npairs + rows_per_cta - 1) / rows_per_cta), 128, rsmem, st>>>(folded, blk_remain, blk_offset, d_out, out_stride, \
-                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor, kmax); } break;
-                CSDRB_FFT_SIZES(X)
-#undef X
-            }
-        } else {
-        const size_t psmem = sizeof(float2) * (size_t)POST_PAIRS * (size_t)fft_smem_elems(fft_inv_size);
-        switch (fft_inv_size) {
-#define X(M) case M: if constexpr (M >= 64 && M <= 1024) { auto k = fastddc_ifft_post_kernel<M>; \
-            if (psmem > 48 * 1024) CSDRB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-            k<<<(unsigned)((npairs + POST_PAIRS - 1) / POST_PAIRS), 256, psmem, st>>>(folded, static_cast<const DdcChan*>(d_chan), blk_remain, blk_phase, blk_offset, d_out, out_stride, \
-                                                                scrap, post_input_size, post_decimation, nblocks, channels, tw, phasor, kmax); } break;
-            CSDRB_FFT_SIZES(X)
-#undef X
-        }
-        }
-        CSDRB_CUDA(cudaGetLastError());
         if (trace) {
-            CSDRB_CUDA(cudaEventRecord(tev[6], st));
+            CSDRB_CUDA(cudaEventRecord(tev[3], st));
             CSDRB_CUDA(cudaStreamSynchronize(st));
-            float t[7] = {};
-            for (int i = 1; i < 7; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
-            fprintf(stderr, "[inv trace] us from call start: side stream starts %.1f, chain done %.1f, phasors done %.1f | fold done %.1f, join passed %.1f, post done %.1f\n",
-                    t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f, t[5] * 1e3f, t[6] * 1e3f);
+            float t[4] = {};
+            for (int i = 1; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+            fprintf(stderr, "[inv trace] us from call start: chain + phasors done %.1f | fold done %.1f, post done %.1f\n", t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f);
             for (auto& e : tev) cudaEventDestroy(e);
         }
         CSDRB_CUDA(cudaFreeAsync(folded, st));
@@ -423,6 +441,171 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
     }
     CSDRB_CUDA(cudaGetLastError());
     return 2;
+}
+
+
+// ---- fastddc inverse bank with look-ahead ---------------------------------------------------------------------------------------------
+// The stateless call above has the chain + phasor walk (57 + 10..57 us for 64 channels x 256 blocks) inside every call, next to a fold that
+// keeps the FMA pipe busy: r02 timeline, the post step waits ~115 us for them while the fold is done after 90..108.  They depend on nothing
+// but the channel parameters and the carried state, so a plan object that OWNS that state prepares call k+1 while call k's IFFT/post step
+// and the caller's next forward FFT run: two sets of {state, per-block arrays, phasors}, set q is written by the side stream while set p is
+// read by the main stream.  Same kernels, same order of operations per channel: the outputs are those of the stateless call, bit for bit
+// (tests/test_kernels_emulated.py, tests/test_gpu_round2.py).
+struct FastddcInvPlan {
+    int dev = 0, channels = 0, nblocks = 0, kmax = 0;
+    int fft_size = 0, fft_inv_size = 0, pre_decimation = 0, scrap = 0, post_input_size = 0, post_decimation = 0;
+    DdcChan* d_chan = nullptr;
+    int* d_remain[2] = {}; float* d_phase[2] = {}; int* d_total[2] = {};
+    void* prep_mem[2] = {}; InvPrep prep[2];
+    float2* folded = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ready[2] = {}, post_done[2] = {}, fold_done = nullptr, chan_set = nullptr;
+    int cur = 0;                    // the set the NEXT run reads
+    bool ahead = false;             // ... has already been enqueued on the side stream
+    bool chan_dirty = false;        // a retune is in flight on the side stream: the next fold waits for it
+    std::mutex mu;
+};
+
+static size_t plan_prep_bytes(int channels, int nblocks, int kmax)
+{
+    return fastddc_inv_scratch_bytes(channels, nblocks) + 16 + sizeof(float2) * (size_t)channels * nblocks * (size_t)kmax;
+}
+
+static int plan_enqueue_prepare(FastddcInvPlan* pl, int q)
+{
+    // state of set q := state of the other set (what the previous preparation left), then the chain advances it in place
+    CSDRB_CUDA(cudaMemcpyAsync(pl->d_remain[q], pl->d_remain[1 - q], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
+    CSDRB_CUDA(cudaMemcpyAsync(pl->d_phase[q], pl->d_phase[1 - q], sizeof(float) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
+    if (int rc = launch_fastddc_inv_prepare(pl->d_chan, pl->channels, pl->nblocks, pl->post_input_size, pl->post_decimation, pl->d_remain[q], pl->d_phase[q],
+                                            pl->d_total[q], pl->prep[q], pl->side)) return rc;
+    CSDRB_CUDA(cudaEventRecord(pl->ready[q], pl->side));
+    return 0;
+}
+
+void fastddc_inv_plan_destroy(void* plan)
+{
+    auto* pl = static_cast<FastddcInvPlan*>(plan);
+    if (!pl) return;
+    int prev = 0; cudaGetDevice(&prev); cudaSetDevice(pl->dev);
+    if (pl->side) cudaStreamSynchronize(pl->side);
+    cudaDeviceSynchronize();
+    cudaFree(pl->d_chan); cudaFree(pl->folded);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(pl->d_remain[i]); cudaFree(pl->d_phase[i]); cudaFree(pl->d_total[i]); cudaFree(pl->prep_mem[i]);
+        if (pl->ready[i]) cudaEventDestroy(pl->ready[i]);
+        if (pl->post_done[i]) cudaEventDestroy(pl->post_done[i]);
+    }
+    if (pl->fold_done) cudaEventDestroy(pl->fold_done);
+    if (pl->chan_set) cudaEventDestroy(pl->chan_set);
+    if (pl->side) cudaStreamDestroy(pl->side);
+    cudaSetDevice(prev);
+    delete pl;
+}
+
+int fastddc_inv_plan_create(void** out_plan, const void* h_chan, int channels, int nblocks, int fft_size, int fft_inv_size, int pre_decimation, int scrap,
+                            int post_input_size, int post_decimation)
+{
+    if (!out_plan || !h_chan || channels <= 0 || nblocks <= 0 || post_decimation <= 0 || post_input_size <= 0) { set_error("fastddc_inv_plan: bad arguments"); return -1; }
+    if (!fastddc_inv_fold_ok(fft_size, fft_inv_size)) {
+        set_error("fastddc_inv_plan: geometry %d/%d is not covered by the fold path (fft_inv_size 64..1024, even pre-decimation): use csdrb_fastddc_inv_bank_cc", fft_size, fft_inv_size);
+        return -1;
+    }
+    auto* pl = new FastddcInvPlan();
+    CSDRB_CUDA(cudaGetDevice(&pl->dev));
+    pl->channels = channels; pl->nblocks = nblocks; pl->fft_size = fft_size; pl->fft_inv_size = fft_inv_size; pl->pre_decimation = pre_decimation; pl->scrap = scrap;
+    pl->post_input_size = post_input_size; pl->post_decimation = post_decimation;
+    pl->kmax = (post_input_size + post_decimation - 1) / post_decimation;
+    bool ok = cudaMalloc(reinterpret_cast<void**>(&pl->d_chan), sizeof(DdcChan) * channels) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&pl->folded), sizeof(float2) * (size_t)channels * nblocks * fft_inv_size) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&pl->fold_done, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pl->chan_set, cudaEventDisableTiming) == cudaSuccess;
+    const size_t state_part = fastddc_inv_scratch_bytes(channels, nblocks);
+    for (int i = 0; i < 2 && ok; i++) {
+        ok = cudaMalloc(reinterpret_cast<void**>(&pl->d_remain[i]), sizeof(int) * channels) == cudaSuccess && cudaMalloc(reinterpret_cast<void**>(&pl->d_phase[i]), sizeof(float) * channels) == cudaSuccess &&
+             cudaMalloc(reinterpret_cast<void**>(&pl->d_total[i]), sizeof(int) * channels) == cudaSuccess && cudaMalloc(&pl->prep_mem[i], plan_prep_bytes(channels, nblocks, pl->kmax)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&pl->ready[i], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pl->post_done[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) break;
+        char* base = static_cast<char*>(pl->prep_mem[i]);
+        InvPrep& pr = pl->prep[i];
+        pr.blk_remain = reinterpret_cast<int*>(base);
+        pr.blk_phase = reinterpret_cast<float*>(pr.blk_remain + (size_t)channels * nblocks);
+        pr.blk_offset = reinterpret_cast<int*>(pr.blk_phase + (size_t)channels * nblocks);
+        pr.tables = nblocks > 96 ? reinterpret_cast<WrapTable*>(base + (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15)) : nullptr;
+        pr.phasor = reinterpret_cast<float2*>(base + ((state_part + 15) & ~(size_t)15));
+        pr.kmax = pl->kmax;
+        ok = cudaMemset(pl->d_remain[i], 0, sizeof(int) * channels) == cudaSuccess && cudaMemset(pl->d_phase[i], 0, sizeof(float) * channels) == cudaSuccess &&
+             cudaMemset(pl->d_total[i], 0, sizeof(int) * channels) == cudaSuccess;
+    }
+    ok = ok && cudaMemcpy(pl->d_chan, h_chan, sizeof(DdcChan) * channels, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) { set_error("fastddc_inv_plan: device allocation failed (%s)", cudaGetErrorString(cudaGetLastError())); fastddc_inv_plan_destroy(pl); return -1; }
+    pl->cur = 0; pl->ahead = false;                                       // the carried state (zeros) sits in set 1, the first preparation goes to set 0
+    *out_plan = pl;
+    return 0;
+}
+
+int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_taps_fft, float2* d_out, long out_stride, int* d_out_total, cudaStream_t st)
+{
+    auto* pl = static_cast<FastddcInvPlan*>(plan);
+    if (!pl || !d_spectra || !d_taps_fft || !d_out || !d_out_total) { set_error("fastddc_inv_plan_run: null pointer"); return -1; }
+    std::lock_guard<std::mutex> lk(pl->mu);
+    const int p = pl->cur;
+    if (!pl->ahead) {                                                     // first run, or the look-ahead was dropped by a retune / set_state
+        if (int rc = plan_enqueue_prepare(pl, p)) return rc;
+    }
+    if (pl->chan_dirty) { CSDRB_CUDA(cudaStreamWaitEvent(st, pl->chan_set, 0)); pl->chan_dirty = false; }
+    if (int rc = launch_fastddc_inv_apply(d_spectra, pl->nblocks, d_taps_fft, pl->d_chan, pl->channels, pl->fft_size, pl->fft_inv_size, pl->pre_decimation, pl->scrap,
+                                          pl->post_input_size, pl->post_decimation, pl->prep[p], pl->folded, d_out, out_stride, pl->ready[p], pl->fold_done, st)) return rc;
+    CSDRB_CUDA(cudaMemcpyAsync(d_out_total, pl->d_total[p], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, st));
+    CSDRB_CUDA(cudaEventRecord(pl->post_done[p], st));
+    // look-ahead: the next run's chain + phasors, behind this run's fold (they would fight it for the FMA pipe), next to its IFFT/post step
+    const int q = 1 - p;
+    CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->fold_done, 0));
+    CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[q], 0));       // set q was last read two runs ago (a never-recorded event does not block)
+    if (int rc = plan_enqueue_prepare(pl, q)) return rc;
+    pl->cur = q; pl->ahead = true;
+    return pl->nblocks;
+}
+
+// Retune channel c from the next run on (the caller replaces that channel's taps_fft on its own stream).  Drops the look-ahead.
+int fastddc_inv_plan_set_channel(void* plan, int c, const void* h_chan_one)
+{
+    auto* pl = static_cast<FastddcInvPlan*>(plan);
+    if (!pl || !h_chan_one || c < 0 || c >= pl->channels) { set_error("fastddc_inv_plan_set_channel: bad arguments"); return -1; }
+    std::lock_guard<std::mutex> lk(pl->mu);
+    // the last run's kernels read d_chan: the copy goes behind them (post_done of the set read last), the next fold behind the copy (chan_set)
+    CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[1 - pl->cur], 0));
+    CSDRB_CUDA(cudaMemcpyAsync(pl->d_chan + c, h_chan_one, sizeof(DdcChan), cudaMemcpyHostToDevice, pl->side));
+    CSDRB_CUDA(cudaStreamSynchronize(pl->side));                          // h_chan_one may be a stack variable of the caller
+    CSDRB_CUDA(cudaEventRecord(pl->chan_set, pl->side));
+    pl->chan_dirty = true;
+    pl->ahead = false;                                                    // set cur was prepared with the old parameters; the state it started from is still in the other set
+    return 0;
+}
+
+// The carried state {remain, phase} per channel BEFORE the next run (what decimating_shift_addition_status_t carries, libcsdr_gpl.c:154-158).
+int fastddc_inv_plan_get_state(void* plan, int* h_remain, float* h_phase)
+{
+    auto* pl = static_cast<FastddcInvPlan*>(plan);
+    if (!pl || !h_remain || !h_phase) { set_error("fastddc_inv_plan_get_state: null pointer"); return -1; }
+    std::lock_guard<std::mutex> lk(pl->mu);
+    CSDRB_CUDA(cudaStreamSynchronize(pl->side));
+    const int src = 1 - pl->cur;
+    CSDRB_CUDA(cudaMemcpy(h_remain, pl->d_remain[src], sizeof(int) * pl->channels, cudaMemcpyDeviceToHost));
+    CSDRB_CUDA(cudaMemcpy(h_phase, pl->d_phase[src], sizeof(float) * pl->channels, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fastddc_inv_plan_set_state(void* plan, const int* h_remain, const float* h_phase)
+{
+    auto* pl = static_cast<FastddcInvPlan*>(plan);
+    if (!pl || !h_remain || !h_phase) { set_error("fastddc_inv_plan_set_state: null pointer"); return -1; }
+    std::lock_guard<std::mutex> lk(pl->mu);
+    CSDRB_CUDA(cudaStreamSynchronize(pl->side));
+    const int dst = 1 - pl->cur;
+    CSDRB_CUDA(cudaMemcpy(pl->d_remain[dst], h_remain, sizeof(int) * pl->channels, cudaMemcpyHostToDevice));
+    CSDRB_CUDA(cudaMemcpy(pl->d_phase[dst], h_phase, sizeof(float) * pl->channels, cudaMemcpyHostToDevice));
+    pl->ahead = false;
+    return 0;
 }
 
 }  // namespace csdrb

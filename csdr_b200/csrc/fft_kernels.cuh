@@ -505,13 +505,15 @@ fastddc_inv_tiled_kernel(const float2* __restrict__ spectra, const float2* __res
 // shared memory by two thread groups, and a thread keeps an 8 x 8 accumulator tile for its residue (128 FFMA2 per 16 LDS.64).  L2 traffic
 // drops to 0.27 GB, the inner loop is FMA-pipe bound.  Summation per destination bin is still ascending in the bin index, as in
 // fastddc.c:126-141 (k ascending = bin index ascending); products and sums are fused (FFMA2), inside the 1e-5 budget.
-// The folded bins go to a scratch array (L2-sized: 64 ch x 256 blocks x 512 bins = 67 MB), fastddc_ifft_post_kernel does IFFT_M, /M,
+// The folded bins go to a scratch array (L2-sized: 64 ch x 256 blocks x 512 bins = 67 MB), fastddc_ifft_rows_kernel does IFFT_M, /M,
 // scrap and the post shift; the block-to-block state chain runs on a side stream meanwhile (it is data-independent).
 constexpr int FOLD_R = 64, FOLD_CT = 8, FOLD_BT = 8, FOLD_ST = 3;     // residues per CTA, thread tile (channels x blocks), pipeline stages
 
 // BT = blocks per thread tile: 8 -> 256 threads (8 warps per SM), 4 -> 512 threads (16 warps, half the accumulators per thread: more latency hiding, more
 // shared-memory reads per FMA).  The CTA tile is 64 residues x 16 channels x 16 blocks either way.
-template <int BT>
+// HFIRST = the tap pair is the FIRST multiplicand of the packed FMA (ptxas keeps the first operand in the reuse cache across consecutive FFMA2: with the
+// pair there an instruction reads 3 registers instead of 4, and swap + negate become modifiers of that slot -- no MOV/FADD to build (-hi, hr)).
+template <int BT, bool HFIRST>
 __global__ void __launch_bounds__(64 * 2 * (2 * FOLD_BT / BT), 1)
 fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const float2* __restrict__ taps_fft /*[C][N]*/, const DdcChan* __restrict__ chan,
                     float2* __restrict__ folded /*[C][nblocks][M]*/, int N, int M, int nblocks, int channels, float inv_pre)
@@ -563,12 +565,14 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
-            for (int v = 0; v < BT; v++) acc[u][v] = ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
+            for (int v = 0; v < BT; v++)
+                acc[u][v] = HFIRST ? ffma2(h[u], make_float2(x[v].x, x[v].x), acc[u][v]) : ffma2(make_float2(x[v].x, x[v].x), h[u], acc[u][v]);
 #pragma unroll
         for (int u = 0; u < FOLD_CT; u++)
 #pragma unroll
             for (int v = 0; v < BT; v++)
-                acc[u][v] = ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
+                acc[u][v] = HFIRST ? ffma2(make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), make_float2(x[v].y, x[v].y), acc[u][v])
+                                   : ffma2(make_float2(x[v].y, x[v].y), make_float2(__uint_as_float(__float_as_uint(h[u].y) ^ 0x80000000u), h[u].x), acc[u][v]);
     }
     // /pre_decimation, and both half swaps (fastddc.c:143-150) folded into the destination index (r - offsetbin) mod M
     const int r = r0 + rl;
@@ -590,11 +594,8 @@ fastddc_fold_kernel(const float2* __restrict__ spectra /*[nblocks][N]*/, const f
 // on the data: one lane per (channel, block) pair walks its <= kmax steps here, on the side stream behind the state chain and under the fold, and the table
 // phasor[pair][k] is written 32 steps at a time through a padded shared tile, so both this kernel's stores and the IFFT kernel's loads are coalesced rows.
 // The IFFT kernel then only multiplies -- every output in parallel instead of one lane per row.
-// F64 = the same recursion on the FP64 pipe: a product of two floats is exact in double and a sum of two floats rounded to double and then to float equals the
-// float sum (53 >= 2*24 + 2 bits: double rounding is innocuous for + - *), so (float)((double)a * (double)b) and (float)((double)x - (double)y) ARE
-// __fmul_rn / __fsub_rn, bit for bit -- but DMUL / DADD / F2F do not queue behind the fold kernel's FFMA2 stream on the FMA pipe, which this kernel shares
-// the SMs with (timeline r02: 57 us under the fold with FMUL/FADD, 9.7 us alone).
-template <bool F64>
+// (Walking the recursion on the FP64 pipe instead -- bit-identical, 53 >= 2*24 + 2 bits make the double rounding innocuous -- to stay out of the fold kernel's
+// FFMA2 stream was measured slower: 113 us under the fold against 57 us for this form, 9.7 us alone; r02 call 13.)
 __global__ void __launch_bounds__(128)
 fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict__ blk_phase, float2* __restrict__ phasor, int channels, int nblocks, int kmax)
 {
@@ -610,21 +611,12 @@ fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict_
     const double ph = (double)blk_phase[(long)b * channels + c];
     float co = (float)cos(ph), si = (float)sin(ph);
     const int rows = (int)min((long)32, npairs - p_first);
-    const double cd = (double)cp.cosdelta, sd = (double)cp.sindelta;
     for (int k0 = 0; k0 < kmax; k0 += 32) {
 #pragma unroll 4
         for (int j = 0; j < 32; j++) {
             tile[lane * 33 + j] = make_float2(co, si);
-            float cn, sn;
-            if constexpr (F64) {
-                const double cw = (double)co, sw = (double)si;
-                const double a = (double)__double2float_rn(cw * cd), b2 = (double)__double2float_rn(sw * sd);
-                const double e = (double)__double2float_rn(sw * cd), f = (double)__double2float_rn(cw * sd);
-                cn = __double2float_rn(a - b2); sn = __double2float_rn(e + f);
-            } else {
-                cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
-                sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
-            }
+            const float cn = __fsub_rn(__fmul_rn(co, cp.cosdelta), __fmul_rn(si, cp.sindelta));
+            const float sn = __fadd_rn(__fmul_rn(si, cp.cosdelta), __fmul_rn(co, cp.sindelta));
             co = cn; si = sn;
         }
         __syncwarp();
@@ -634,80 +626,11 @@ fastddc_phasor_kernel(const DdcChan* __restrict__ chan, const float* __restrict_
     }
 }
 
-// IFFT_M of POST_PAIRS folded (channel, block) rows per CTA (64 threads per transform, four at a time), /M, drop the scrap, post shift + decimate.
-// The post shift multiplies by the phasors fastddc_phasor_kernel prepared (the recursion itself is sequential per row: walking it here, first with a warp per
-// row -- 5 active threads per instruction, 113 us -- then with a lane per row -- 58 us -- left the SMs idle behind sixteen serial walks).  Pairs are p = c * nblocks + b.
-constexpr int POST_PAIRS = 16;
-
-template <int M>
-__global__ void __launch_bounds__(256)
-fastddc_ifft_post_kernel(const float2* __restrict__ folded, const DdcChan* __restrict__ chan, const int* __restrict__ blk_remain,
-                         const float* __restrict__ blk_phase, const int* __restrict__ blk_offset, float2* __restrict__ out, long out_stride,
-                         int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw,
-                         const float2* __restrict__ phasor, int kmax)
-{
-    CSDRB_DYN_SMEM(smem_raw);
-    float2* s = reinterpret_cast<float2*>(smem_raw);
-    constexpr int NTG = 64, GROUPS = 4, PITCH = fft_smem_elems(M), PER = M / NTG;      // even pitch: rows stay 16-byte aligned for block_fft's 128-bit accesses
-    static_assert(M >= 64 && M <= 16 * NTG, "fastddc_ifft_post_kernel: 64 <= M <= 1024");
-    const int tid = threadIdx.x, g = tid / NTG, tg = tid % NTG;
-    const long npairs = (long)channels * nblocks, p0 = (long)blockIdx.x * POST_PAIRS;
-    __shared__ int row_first[POST_PAIRS], row_cnt[POST_PAIRS];
-    __shared__ long row_dst[POST_PAIRS];
-    if (tid < POST_PAIRS) {                                              // row bookkeeping, read long before it is needed
-        const long p = p0 + tid;
-        int first = 0, cnt = 0; long dst = 0;
-        if (p < npairs) {
-            const int c = (int)(p / nblocks), b = (int)(p % nblocks);
-            const long bi = (long)b * channels + c;
-            first = blk_remain[bi];
-            cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
-            dst = (long)c * out_stride + blk_offset[bi];
-        }
-        row_first[tid] = first; row_cnt[tid] = cnt; row_dst[tid] = dst;
-    }
-    // every thread takes part in every round (block_fft has barriers inside); the next round's row is fetched while this round's transform runs
-    float2 v[PER];
-    {
-        const float2* src = folded + min(p0 + g, npairs - 1) * M;        // a ragged last CTA repeats the last pair into its own row: harmless
-#pragma unroll
-        for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);
-    }
-#pragma unroll 1
-    for (int a = 0; a < POST_PAIRS; a += GROUPS) {
-        float2* mys = s + (a + g) * PITCH;
-#pragma unroll
-        for (int k = 0; k < PER; k++) mys[fft_pad(tg + k * NTG)] = v[k];
-        if (a + GROUPS < POST_PAIRS) {
-            const float2* src = folded + min(p0 + a + GROUPS + g, npairs - 1) * M;
-#pragma unroll
-            for (int k = 0; k < PER; k++) v[k] = __ldg(src + tg + k * NTG);
-        }
-        __syncthreads();
-        block_fft<M, NTG, true>(mys, tw, tg);
-    }
-    __syncthreads();
-    // /M, drop the scrap, decimate, rotate by the precomputed phasor: every output of the CTA's rows is an independent item (row a, output k).  The per-row
-    // bookkeeping (first sample, count, destination) was fetched into shared memory by sixteen threads before the transforms started: no dependent global load
-    // sits in front of the items (a first version looked the rows up one after the other: 83 us for the kernel, worse than the serial walk it replaced).
-    const float inv_m = 1.0f / (float)M;
-    const int items = POST_PAIRS * kmax;
-#pragma unroll 2
-    for (int it = tid; it < items; it += 256) {
-        const int a = it / kmax, k = it - a * kmax;
-        if (k >= row_cnt[a]) continue;
-        const float2 raw = s[a * PITCH + fft_pad(scrap + row_first[a] + k * post_decimation)];
-        const float2 w = make_float2(raw.x * inv_m, raw.y * inv_m);
-        const float2 ph = __ldg(phasor + (p0 + a) * kmax + k);
-        out[row_dst[a] + k] = make_float2(__fsub_rn(__fmul_rn(ph.x, w.x), __fmul_rn(ph.y, w.y)), __fadd_rn(__fmul_rn(ph.y, w.x), __fmul_rn(ph.x, w.y)));
-    }
-}
-
-
-// The same step with the transform's I/O fused (round 2, second form): a row is M/8 threads, a CTA is 128 threads = 1024/M rows; the first pass reads the folded
-// row from global memory, the last pass hands every finished element to the sink below, which drops the scrap, decimates, multiplies by the phasor fetched
-// BEFORE the middle passes and stores: two shared-memory round trips per row instead of four, no staging copy, no item loop, and 8 KB of shared memory per
-// CTA so that sixteen CTAs share an SM (the tiled form above: three CTAs, 32 % of the warp slots, half of its stall samples on the global loads).
+// IFFT_M of the folded (channel, block) rows, /M, drop the scrap, decimate, post shift (the phasors come from fastddc_phasor_kernel; pairs are p = c * nblocks + b).
+// A row is M/8 threads, a CTA is 128 threads = 1024/M rows; the first pass reads the folded row from global memory, the last pass hands every finished element
+// to the sink below, which multiplies by the phasor fetched BEFORE the middle passes and stores: two shared-memory round trips per row, no staging copy, 8 KB of
+// shared memory per CTA.  History (64 ch x 256 blocks, M = 512): a warp per row walking the recursion 113 us; sixteen rows per CTA, a lane per row 58 us; phasors
+// precomputed, flat (row, output) items 54.5 us (three 74 KB CTAs per SM, half of the stall samples on global loads); this form 41.5 us.
 template <int M>
 struct FastddcPostSink {
     float2* y; float2 ph[8]; int kk[8]; float inv_m;

@@ -80,6 +80,15 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
                             int* d_remain_io, float* d_phase_io, float2* d_out, long out_stride, int* d_out_total,
                             void* d_scratch, size_t scratch_bytes, cudaStream_t st);
 
+// fastddc inverse bank with look-ahead (fft.cu): a plan owns the post-shift state and prepares the next run's chain + phasors during the current one
+int fastddc_inv_plan_create(void** out_plan, const void* h_chan, int channels, int nblocks, int fft_size, int fft_inv_size, int pre_decimation, int scrap,
+                            int post_input_size, int post_decimation);
+int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_taps_fft, float2* d_out, long out_stride, int* d_out_total, cudaStream_t st);
+int fastddc_inv_plan_set_channel(void* plan, int c, const void* h_chan_one);
+int fastddc_inv_plan_get_state(void* plan, int* h_remain, float* h_phase);
+int fastddc_inv_plan_set_state(void* plan, const int* h_remain, const float* h_phase);
+void fastddc_inv_plan_destroy(void* plan);
+
 // fused shared-input DDC bank, ddc_bank.cu
 size_t ddc_bank_scratch_bytes(int channels, int input_size, int chunk, int offset);
 size_t ddc_bank_tables_bytes(int channels);                            // persistent phase-wrap tables of a bank (phase_table.cuh), one per channel

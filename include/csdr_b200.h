@@ -357,6 +357,21 @@ int csdrb_fastddc_inv_bank_cc(const complexf *d_spectra, int nblocks, const comp
                               int channels, const fastddc_t *geometry, int *d_remain_io, float *d_phase_io, complexf *d_out,
                               long out_stride, int *d_out_total, void *d_scratch, size_t scratch_bytes, void *stream);
 
+/* The same bank as a plan object that OWNS the carried post-shift state (decimating_shift_addition_status_t per channel, fastddc.c:151-165 /
+ * libcsdr_gpl.c:154-158) and a fixed nblocks: the data-independent half of run k+1 (state chain, post-shift phasors) is computed on a private
+ * stream while run k's IFFT step and the caller's next forward FFT execute, so a run is fold + IFFT only.  Outputs are those of
+ * csdrb_fastddc_inv_bank_cc bit for bit.  `chan` is a HOST array; geometries outside the fold path (fft_inv_size 64..1024, even
+ * pre-decimation) are refused -- use the stateless call for them.  set_channel retunes one channel from the next run on (replace that
+ * channel's row of d_taps_fft on your stream as well); get/set_state read and write the state the NEXT run starts from. */
+typedef struct csdrb_fastddc_inv_plan csdrb_fastddc_inv_plan_t;
+csdrb_fastddc_inv_plan_t *csdrb_fastddc_inv_plan_create(const csdrb_fastddc_chan_t *chan, int channels, const fastddc_t *geometry, int nblocks);
+int csdrb_fastddc_inv_plan_run(csdrb_fastddc_inv_plan_t *plan, const complexf *d_spectra, const complexf *d_taps_fft, complexf *d_out, long out_stride,
+                               int *d_out_total, void *stream);
+int csdrb_fastddc_inv_plan_set_channel(csdrb_fastddc_inv_plan_t *plan, int channel, const csdrb_fastddc_chan_t *chan);
+int csdrb_fastddc_inv_plan_get_state(csdrb_fastddc_inv_plan_t *plan, int *remain, float *phase);
+int csdrb_fastddc_inv_plan_set_state(csdrb_fastddc_inv_plan_t *plan, const int *remain, const float *phase);
+void csdrb_fastddc_inv_plan_destroy(csdrb_fastddc_inv_plan_t *plan);
+
 #ifdef __cplusplus
 }
 #endif

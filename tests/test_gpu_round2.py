@@ -104,6 +104,44 @@ def test_long_phase_chains_are_bit_exact(gpu, oracle, chunk, nchunks):
         assert e < 2e-6, f"rate {r}: rel-RMS {e:.3e}"
 
 
+# ------------------------------------------------------------------------------------------ fastddc inverse plan (look-ahead) == stateless bank
+@pytest.mark.parametrize("channels,nblocks", [(5, 7), (64, 256)])
+def test_fastddc_inverse_plan_equals_the_stateless_bank(gpu, oracle, channels, nblocks):
+    """csdrb_fastddc_inv_plan_* prepares run k+1 (state chain + phasors) on its own stream during run k: outputs, counts and carried state must be those
+    of csdrb_fastddc_inv_bank_cc BIT FOR BIT over six runs with a retune in the middle; BASELINE config 3's size is the second case."""
+    import torch
+    bw, dec, runs = 0.002, 64, 6
+    ddc = gpu.fastddc_init(bw, dec, 0.0)
+    rng = np.random.default_rng(channels)
+    shifts = list(np.linspace(-0.43, 0.41, channels))
+    plan = gpu.FastddcInvPlan(shifts, dec, bw, nblocks)
+    st = None; ov = None
+    try:
+        for r in range(runs):
+            x = _dev(_cplx(rng, nblocks * ddc.input_size, amp=0.5))
+            sp, ov = gpu.fastddc_fwd_cc(x, ddc, overlap=ov)
+            if r == 3:                                                  # retune one channel in both
+                c, new = channels // 2, 0.2345
+                plan.set_shift(c, new)
+                shifts[c] = new
+                d = gpu.fastddc_init(bw, dec, new)
+                st["taps_fft"][c].copy_(gpu.fastddc_make_taps_fft(d, new, dec, "HAMMING", "cuda"))
+                row = torch.from_numpy(gpu._fastddc_chan_rows([d])[0]).cuda()
+                st["chan"][c].copy_(row)
+            want, wc, st = gpu.fastddc_inv_bank_cc(sp, shifts, dec, bw, state=st)
+            got, gc = plan.run(sp)
+            torch.cuda.synchronize()
+            assert torch.equal(gc, wc), f"run {r}: counts differ"
+            n = int(wc.max())
+            live = (torch.arange(n, device="cuda")[None, :] < wc[:, None])[..., None]                 # beyond a channel's count the buffers hold whatever they held
+            a = torch.view_as_real(got[:, :n]).view(torch.int32) * live, torch.view_as_real(want[:, :n]).view(torch.int32) * live
+            assert torch.equal(*a), f"run {r}: outputs differ"
+        remain, phase = plan.state()
+        assert np.array_equal(remain, st["remain"].cpu().numpy()) and np.array_equal(phase.view(np.uint32), st["phase"].cpu().numpy().view(np.uint32))
+    finally:
+        plan.close()
+
+
 # ------------------------------------------------------------------------------------------ fastddc inverse: fold path vs round-1 kernels vs oracle
 @pytest.mark.parametrize("channels,nblocks", [(1, 1), (3, 5), (17, 33), (20, 130)])
 def test_fastddc_fold_path_ragged_banks(gpu, oracle, channels, nblocks):

@@ -530,6 +530,65 @@ def test_k9_golden_and_dropin_kernel(fft, oracle):
     assert rel_rms(out, want) < 2e-6
 
 
+def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle):
+    """csdrb_fastddc_inv_plan_* (state inside, next run prepared ahead) against launch_fastddc_inv_bank run for run, bit for bit: three channels,
+    five runs of three blocks, a retune of channel 1 after the second run and a set_state round trip; the last outputs also against the oracle."""
+    from oracle.pyoracle import _CF, _p, WINDOWS
+    bw, dec, nb, runs = 0.05, 8, 3, 5
+    shifts = [0.123, -0.31, 0.02]
+    chan_dt = np.dtype([("offsetbin", np.int32), ("sindelta", np.float32), ("cosdelta", np.float32), ("rate", np.float32)])
+
+    def design(shift):
+        g, _ = oracle.fastddc_init(bw, dec, shift)
+        tf = np.empty(g.fft_size, np.complex64)
+        oracle.L.oracle_fastddc_make_taps_fft(C.byref(g), shift, dec, WINDOWS["HAMMING"], _p(tf, _CF))
+        row = np.zeros(1, chan_dt)
+        row["offsetbin"] = g.offsetbin; row["sindelta"] = g.dsadata.sindelta; row["cosdelta"] = g.dsadata.cosdelta; row["rate"] = g.dsadata.rate
+        return g, tf, row
+    gs, tfs, rows = zip(*[design(s) for s in shifts])
+    g = gs[0]
+    nch = len(shifts)
+    taps = Z((nch, g.fft_size), np.complex64); taps[:] = np.stack(tfs)
+    chan = Z(nch, chan_dt); chan[:] = np.concatenate(rows)
+    rng = np.random.default_rng(5)
+    x = _cplx(rng, runs * nb * g.input_size, amp=0.5)
+    spectra = np.stack(oracle.fastddc_fwd(x, g)).astype(np.complex64)
+    width = nb * (g.post_input_size // g.post_decimation + 1) + 2
+    plan = C.c_void_p()
+    assert fft.emul_fastddc_inv_plan_create(C.addressof(plan), P(chan), nch, nb, g.fft_size, g.fft_inv_size, g.pre_decimation, g.scrap, g.post_input_size, g.post_decimation) == 0, fft.emul_last_error()
+    remain = Z(nch, np.int32); phase = Z(nch, np.float32)
+    sb = fft.emul_fastddc_inv_scratch_bytes(nch, nb); scratch = Z(sb + 16, np.uint8)
+    try:
+        for r in range(runs):
+            sp = Z((nb, g.fft_size), np.complex64); sp[:] = spectra[r * nb:(r + 1) * nb]
+            if r == 2:                                                                            # retune channel 1: both paths from this run on
+                g1, tf1, row1 = design(0.27)
+                taps[1] = tf1; chan[1] = row1[0]
+                one = Z(1, chan_dt); one[:] = row1
+                assert fft.emul_fastddc_inv_plan_set_channel(plan, 1, P(one)) == 0
+            if r == 3:                                                                            # state out and back in: drops the look-ahead, changes nothing
+                hr = Z(nch, np.int32); hp = Z(nch, np.float32)
+                assert fft.emul_fastddc_inv_plan_get_state(plan, P(hr), P(hp)) == 0
+                assert np.array_equal(hr, remain) and np.array_equal(hp.view(np.uint32), phase.view(np.uint32))
+                assert fft.emul_fastddc_inv_plan_set_state(plan, P(hr), P(hp)) == 0
+            want = Z((nch, width), np.complex64); wt = Z(nch, np.int32)
+            assert fft.emul_launch_fastddc_inv_bank(P(sp), nb, P(taps), P(chan), nch, g.fft_size, g.fft_inv_size, g.pre_decimation, g.scrap, g.post_input_size, g.post_decimation,
+                                                    P(remain), P(phase), P(want), width, P(wt), P(scratch), sb) == 4, fft.emul_last_error()
+            got = Z((nch, width), np.complex64); gt = Z(nch, np.int32)
+            assert fft.emul_fastddc_inv_plan_run(plan, P(sp), P(taps), P(got), width, P(gt)) == nb, fft.emul_last_error()
+            assert np.array_equal(gt, wt)
+            for c in range(nch):
+                assert np.array_equal(got[c, :gt[c]].view(np.uint32), want[c, :wt[c]].view(np.uint32)), (r, c)
+        hr = Z(nch, np.int32); hp = Z(nch, np.float32)
+        assert fft.emul_fastddc_inv_plan_get_state(plan, P(hr), P(hp)) == 0
+        assert np.array_equal(hr, remain) and np.array_equal(hp.view(np.uint32), phase.view(np.uint32))
+    finally:
+        fft.emul_fastddc_inv_plan_destroy(plan)
+    # channel 0 was never retuned: its stream over all runs is the oracle's
+    ref0 = oracle.fastddc_inv(list(spectra), bw, dec, shifts[0])
+    assert rel_rms(got[0, :gt[0]], ref0[-gt[0]:]) < 5e-6
+
+
 @pytest.mark.parametrize("bw,dec,shift", [(0.05, 8, 0.123), (0.05, 3, -0.2), (0.01, 6, 0.25), (0.05, 4, 0.2), (0.02, 4, 0.05), (0.05, 16, -0.3), (0.05, 32, 0.4)])
 def test_k8_fastddc_forward_and_inverse(fft, oracle, bw, dec, shift):
     """a12/a13 against the oracle (and, for the first geometry, the golden spectra / channel output of the compiled reference);

@@ -77,6 +77,16 @@ if "c3" in which:
     report("cfg3 fastddc fwd 16384-pt", t_f, nsamp, nsamp * 8 + nblocks * ddc.fft_size * 8)
     report("cfg3 fastddc inv bank 64 ch", t_i, nsamp, nblocks * ddc.fft_size * 8 + C * nblocks * 224 * 8)
     report("cfg3 fastddc fwd+inv (16 B/wideband sample)", t_f + t_i, nsamp, algo, f"= {nsamp / (t_f + t_i) / 1e3 / 61.44:.0f}x real time at 61.44 Msps")
+    plan = cb.FastddcInvPlan(shifts, dec, bw, nblocks)
+    t_p = timed(lambda: plan.run(sp))
+    report("cfg3 fastddc inv bank 64 ch, plan object (look-ahead)", t_p, nsamp, nblocks * ddc.fft_size * 8 + C * nblocks * 224 * 8)
+
+    def both():
+        cb.fastddc_fwd_cc(x, ddc, overlap=ov)
+        plan.run(sp)
+    t_b = timed(both)
+    report("cfg3 fastddc fwd + plan.run, one loop", t_b, nsamp, algo, f"= {nsamp / t_b / 1e3 / 61.44:.0f}x real time at 61.44 Msps")
+    plan.close()
     del x, sp, out
     torch.cuda.empty_cache()
 

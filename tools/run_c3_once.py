@@ -9,7 +9,9 @@ x = torch.view_as_complex(torch.rand((nblocks * ddc.input_size, 2), device="cuda
 sp, ov = cb.fastddc_fwd_cc(x, ddc)
 shifts = list(np.linspace(-0.45, 0.45, C))
 out, counts, st = cb.fastddc_inv_bank_cc(sp, shifts, dec, bw)
+plan = cb.FastddcInvPlan(shifts, dec, bw, nblocks) if len(sys.argv) > 2 and sys.argv[2] == "plan" else None
 for _ in range(reps):
     sp, ov = cb.fastddc_fwd_cc(x, ddc, overlap=ov)
-    cb.fastddc_inv_bank_cc(sp, shifts, dec, bw, state=st)
+    if plan is not None: plan.run(sp)
+    else: cb.fastddc_inv_bank_cc(sp, shifts, dec, bw, state=st)
 torch.cuda.synchronize()
