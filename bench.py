@@ -470,7 +470,7 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
     bw3, dec3, C3 = 0.002, 64, 64
     c3 = max(1, C3 // world)
     ddc = cb.fastddc_init(bw3, dec3, 0.0)
-    nblocks = 256
+    nblocks = 592                                                          # 4 x 148 SMs: whole waves for the forward FFT (a CTA per block) and for the fold (a CTA per 16 blocks x 16 ch x 64 bins)
     nsamp = nblocks * ddc.input_size
     gen = torch.Generator(device=dev).manual_seed(3)
     xw = torch.view_as_complex(torch.rand((nsamp, 2), generator=gen, device=dev) * 2 - 1)

@@ -1,6 +1,6 @@
 """Throughput of the non-headline BASELINE configs and of the standalone streaming kernels on one B200 (device-resident data).
 Prints one line per measurement and writes gpurun_out/configs.json.  Parity for all of these is in tests/ (-m gpu)."""
-import json, sys, time
+import json, os, sys, time
 from pathlib import Path
 import numpy as np, torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -65,7 +65,7 @@ if "k" in which:
 if "c3" in which:
     bw, dec, C = 0.002, 64, 64
     ddc = cb.fastddc_init(bw, dec, 0.0)
-    nblocks = 256
+    nblocks = int(os.environ.get("C3_BLOCKS", "256"))
     x = torch.view_as_complex(torch.rand((nblocks * ddc.input_size, 2), device=dev) * 2 - 1)
     shifts = list(np.linspace(-0.45, 0.45, C))
     sp, ov = cb.fastddc_fwd_cc(x, ddc)

@@ -9,6 +9,7 @@ for v in "hfirst CSDRB_X=0" "xfirst CSDRB_FOLD_HFIRST=0"; do
   env "$@" CSDRB_INV_TRACE=1 python tools/run_c3_once.py 4 2>&1 | grep "inv trace" | tail -2 | tee gpurun_out/r2_g14_trace_$tag.txt
   env "$@" python tools/bench_configs.py c3 2>&1 | grep "cfg3" | tee gpurun_out/r2_g14_c3_$tag.txt
 done
+C3_BLOCKS=592 python tools/bench_configs.py c3 2>&1 | grep "cfg3" | sed "s/^/[592 blocks] /" | tee gpurun_out/r2_g14_c3_592.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_g14_c3_plan_launches.csv python tools/run_c3_once.py 3 plan > /dev/null 2>&1
 python - <<'PY'
 import csv
