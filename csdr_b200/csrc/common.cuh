@@ -110,6 +110,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+// 8-byte form (one complex sample): for tiles whose rows have an odd pitch in shared memory (conflict-free row walks) and cannot take 16-byte pieces
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }

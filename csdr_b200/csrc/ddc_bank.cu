@@ -242,8 +242,11 @@ struct DdcWalk {
         Q[u] = make_float2(__uint_as_float(__float_as_uint(pn.y) ^ 0x80000000u), pn.x);
     }
     // one wideband sample against the taps of its phase p (tp = taps of phase p, MP/2 float4), accumulators JLO..JHI-1 only
+    // The taps come as SCALARS (two per 64-bit shared load) and enter the FFMA2 as (h, h) built from one register: ptxas turns that into the .F32 broadcast
+    // modifier, so the tap operand is one register (and sits in the reuse latch for both channels of the lane) and four taps come with one 128-bit shared load;
+    // the first form kept every tap duplicated (h, h) in shared memory and in a register pair (207 LDS in the kernel instead of 134).
     template <int JLO, int JHI>
-    __device__ __forceinline__ void sample(float xi, float xq, const float4* __restrict__ tp)
+    __device__ __forceinline__ void sample(float xi, float xq, const float2* __restrict__ tp)
     {
         const float2 xi2 = make_float2(xi, xi), xq2 = make_float2(xq, xq);
         float2 sh[CPL];
@@ -254,11 +257,11 @@ struct DdcWalk {
         }
 #pragma unroll
         for (int j = JLO; j < JHI; j += 2) {
-            const float4 h2 = tp[j / 2];
+            const float2 h2 = tp[j / 2];
 #pragma unroll
             for (int u = 0; u < CPL; u++) {
-                acc[u][j] = ffma2(sh[u], make_float2(h2.x, h2.y), acc[u][j]);
-                if (j + 1 < M) acc[u][j + 1] = ffma2(sh[u], make_float2(h2.z, h2.w), acc[u][j + 1]);
+                acc[u][j] = ffma2(sh[u], make_float2(h2.x, h2.x), acc[u][j]);
+                if (j + 1 < M) acc[u][j + 1] = ffma2(sh[u], make_float2(h2.y, h2.y), acc[u][j + 1]);
             }
         }
     }
@@ -274,8 +277,8 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
 {
     constexpr int MP = (M + 1) & ~1;
     constexpr int U = (D % 10 == 0) ? 10 : 2;                           // samples per unchecked group
-    __shared__ float4 staps[D * MP / 2];
-    for (int i = threadIdx.x; i < D * MP / 2; i += 128) staps[i] = taps.hh2[i];
+    __shared__ float2 staps[D * MP / 2];                               // [p][j / 2] = taps (j, j+1) of phase p
+    for (int i = threadIdx.x; i < D * MP / 2; i += 128) { const float4 hh = taps.hh2[i]; staps[i] = make_float2(hh.x, hh.z); }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long wid = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -334,7 +337,7 @@ ddc_bank_fused2_kernel(const float2* __restrict__ wide, int n_in, int offset, in
         for (int p0 = 0; p0 < D; p0 += UU) {
             if (left >= UU && base + p0 + UU <= n_in) {
                 const float4* src = reinterpret_cast<const float4*>(wide + base + p0);     // D, UU even: 16-byte aligned
-                const float4* tp = staps + p0 * (MP / 2);
+                const float2* tp = staps + p0 * (MP / 2);
                 float4 cur[UU / 2];
 #pragma unroll
                 for (int e = 0; e < UU / 2; e++) cur[e] = __ldg(src + e);

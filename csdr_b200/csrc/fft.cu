@@ -13,6 +13,7 @@
 //                           /pre_decimation, swap, IFFT_M, /M, drop `scrap`, post shift + decimate.
 #include "fft_kernels.cuh"
 #include "kernels.h"
+#include "side_stream.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -253,29 +254,6 @@ int launch_apply_fir_fft(const float2* d_in, const float2* d_taps_fft, const flo
 }
 
 // ---- fastddc inverse bank ----------------------------------------------------------------------------
-// one private side stream + fork/join events per device, for work that is independent of the data path of a call
-struct SideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; std::mutex mu; };
-static SideStream* side_stream()
-{
-    static std::map<int, SideStream*> per_dev;
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return nullptr; }
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = per_dev.find(dev);
-    if (it != per_dev.end()) return it->second;
-    auto* s = new SideStream();
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) { set_error("side stream: CUDA object creation failed"); delete s; return nullptr; }
-    // stream-ordered scratch (cudaMallocAsync) must not go back to the OS at every synchronisation: keep the pool's memory (r02: re-mapping 67 MB per
-    // fastddc call cost more than the kernels)
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { unsigned long long keep = ~0ULL; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
-    per_dev[dev] = s;
-    return s;
-}
-
-
 // device arrays of the data-independent half of an inverse-bank call
 struct InvPrep { int* blk_remain; float* blk_phase; int* blk_offset; WrapTable* tables; float2* phasor; int kmax; };
 

@@ -21,6 +21,8 @@
 #include "phase_table.cuh"
 #include <climits>
 #include "kernels.h"
+#include "side_stream.cuh"
+#include <cstdlib>
 
 namespace csdrb {
 
@@ -41,13 +43,13 @@ constexpr int kChainTableMin = 96;
 // (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases are stored at a time.  `step(ph, len)` is the direct form.
 template <class Step>
 __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, int c, int n, int chunk, int nchunks, float inc_full,
-                                           WrapTable* __restrict__ tables, Step step)
+                                           WrapTable* __restrict__ tables, Step step, bool build_table = true)
 {
     const int lane = threadIdx.x;
-    const bool tab = tables != nullptr && nchunks > kChainTableMin;
+    const bool tab = tables != nullptr;
     WrapLanes w; w.n = 0; w.lo = w.hi = w.thr0 = w.thr1 = 0.f; w.K0 = w.K1 = 0.0;
     if (tab) {
-        if (lane == 0) wrap_table_build(inc_full, tables + c);
+        if (build_table && lane == 0) wrap_table_build(inc_full, tables + c);
         __syncwarp();
         w = wrap_lanes_load(tables + c, lane);
     }
@@ -62,15 +64,19 @@ __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* 
     if (lane == 0) phase_io[c] = ph;
 }
 
+// One slice of the chain: chunks k_first .. k_first + k_count - 1 of every channel (the launcher cuts a long chain into slices so that the main kernel can
+// start on slice 0 while slice 1 is still being walked); the carried phase in phase_io moves on slice by slice, the wrap table is built by the first one.
 __global__ void __launch_bounds__(32)
 shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
-                         int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
+                         int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables, int k_first, int k_count)
 {
     const int c = blockIdx.x;
     if (c >= channels) return;
     const float rate2 = params[c].z;
-    chain_walk(phase_io, chunk_phase + (long)c * nchunks, c, n, chunk, nchunks, __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk), tables,
-               [rate2](float ph, int len) { return advance_phase(ph, rate2, len); });
+    const int count = min(k_count, nchunks - k_first);
+    if (count <= 0) return;
+    chain_walk(phase_io, chunk_phase + (long)c * nchunks + k_first, c, n - k_first * chunk, chunk, count, __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk), tables,
+               [rate2](float ph, int len) { return advance_phase(ph, rate2, len); }, k_first == 0);
 }
 
 constexpr int SH_TILE = 32;                       // samples per lane per sub-step
@@ -94,52 +100,85 @@ __device__ __forceinline__ void tile_load_rows(float2* __restrict__ tile, const 
 }
 constexpr int SH_PITCH = SH_TILE + 1;             // odd pitch in 8-byte units: row-wise walks are conflict-free
 
+// Round 2, second form: the 32 x 32 tile of step t+1 arrives by cp.async (8-byte pieces: the odd pitch that keeps the row walks conflict-free rules out
+// 16-byte ones) while step t is computed and stored -- ncu had 72 % of the first form's stall samples on the tile loads, 29 % of the warp slots filled and 46
+// instructions per sample, most of them index arithmetic and predicates; here every chunk of a warp but a channel's last is full, so whole tiles take a
+// check-free path.  [k_first, k_end) is the launcher's slice of the chunk range.
 __global__ void __launch_bounds__(128)
 shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
-                  const float3* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks)
+                  const float3* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks, int k_first, int k_end)
 {
-    __shared__ float2 tile_all[4][32 * SH_PITCH];
+    CSDRB_DYN_SMEM(smem_raw);
+    constexpr int TILE = 32 * SH_PITCH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* tile = tile_all[warp];
+    float2* buf = reinterpret_cast<float2*>(smem_raw) + warp * 2 * TILE;             // two tiles per warp
     const int ch = blockIdx.y;
-    const int k0 = (blockIdx.x * 4 + warp) * 32;              // first chunk of this warp
-    if (k0 >= nchunks) return;
+    const int k0 = k_first + (blockIdx.x * 4 + warp) * 32;              // first chunk of this warp
+    if (k0 >= k_end) return;
     const float2* x = in + (long)ch * in_stride;
     float2* y = out + (long)ch * out_stride;
     const float3 p = params[ch];
     const float sind = p.x, cosd = p.y;
     const int k = k0 + lane;
-    const bool live = k < nchunks;
+    const bool live = k < k_end;
     const int my_len = live ? min(chunk, n - k * chunk) : 0;
     float c = 0.f, s = 0.f;
     if (live) {
         const double ph = (double)chunk_phase[(long)ch * nchunks + k];
         c = (float)cos(ph); s = (float)sin(ph);
     }
-    const int rows = min(32, nchunks - k0);
+    const int rows = min(32, k_end - k0);
     const int max_len = min(chunk, n - k0 * chunk);          // the first chunk of the warp is never the short one
-    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
-        // coalesced load: row r = chunk k0+r, 32 consecutive samples starting at t0
-        tile_load_rows(tile, x, rows, k0, chunk, n, t0, lane, SH_PITCH);
+    const int last_len = min(chunk, n - (k0 + rows - 1) * chunk);       // only the last row can be shorter (the channel's last chunk)
+    const float2* xw = x + (long)k0 * chunk + lane;
+    float2* yw = y + (long)k0 * chunk + lane;
+    auto issue = [&](int t0, float2* tile) {
+        if (t0 + 32 <= last_len) {
+            for (int r = 0; r < rows; r++) cp_async8(tile + r * SH_PITCH + lane, xw + (long)r * chunk + t0);
+        } else {
+            for (int r = 0; r < rows; r++)
+                if (t0 + lane < (r == rows - 1 ? last_len : max_len)) cp_async8(tile + r * SH_PITCH + lane, xw + (long)r * chunk + t0);
+        }
+    };
+    issue(0, buf);
+    cp_async_commit();
+    for (int t0 = 0, it = 0; t0 < max_len; t0 += SH_TILE, it++) {
+        float2* tile = buf + (it & 1) * TILE;
+        if (t0 + SH_TILE < max_len) issue(t0 + SH_TILE, buf + ((it + 1) & 1) * TILE);
+        cp_async_commit();
+        cp_async_wait<1>();                                             // this step's tile has landed (the one just issued may still be in flight)
         __syncwarp();
         if (live) {
             float2* row = tile + lane * SH_PITCH;
             const int steps = min(SH_TILE, my_len - t0);
-            for (int j = 0; j < steps; j++) {
-                const float2 v = row[j];
-                row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
-                const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
-                const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
-                c = cn; s = sn;
+            if (steps == SH_TILE) {
+#pragma unroll 8
+                for (int j = 0; j < SH_TILE; j++) {
+                    const float2 v = row[j];
+                    row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                    const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
+                    const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
+                    c = cn; s = sn;
+                }
+            } else {
+                for (int j = 0; j < steps; j++) {
+                    const float2 v = row[j];
+                    row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                    const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
+                    const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
+                    c = cn; s = sn;
+                }
             }
         }
         __syncwarp();
-        for (int r = 0; r < rows; r++) {
-            const long pos = (long)(k0 + r) * chunk + t0 + lane;
-            const int len_r = min(chunk, n - (k0 + r) * chunk);
-            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
+        if (t0 + 32 <= last_len) {
+#pragma unroll 8
+            for (int r = 0; r < rows; r++) yw[(long)r * chunk + t0] = tile[r * SH_PITCH + lane];
+        } else {
+            for (int r = 0; r < rows; r++)
+                if (t0 + lane < (r == rows - 1 ? last_len : max_len)) yw[(long)r * chunk + t0] = tile[r * SH_PITCH + lane];
         }
-        __syncwarp();
+        __syncwarp();                                                   // the tile is free again for the copy issued two steps from now
     }
 }
 
@@ -417,7 +456,7 @@ int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, 
     if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
     shift_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
-                                                               chain_tables(d_scratch, scratch_bytes, channels, nchunks));
+                                                               chain_tables(d_scratch, scratch_bytes, channels, nchunks), 0, nchunks);
     CSDRB_CUDA(cudaGetLastError());
     int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
     shift_unroll_bank_kernel<<<dim3(gx, channels), 256, 0, st>>>(d_in, in_stride, d_out, out_stride, d_dsin, d_dcos, table_stride, chunk_phase, n, chunk, nchunks);
@@ -456,13 +495,44 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addition bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
-                                                               chain_tables(d_scratch, scratch_bytes, channels, nchunks));
-    CSDRB_CUDA(cudaGetLastError());
-    dim3 grid((nchunks + 127) / 128, channels);
-    shift_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, reinterpret_cast<const float3*>(d_params), chunk_phase, n, chunk, nchunks);
-    CSDRB_CUDA(cudaGetLastError());
-    return 2;
+    const float3* prm = reinterpret_cast<const float3*>(d_params);
+    WrapTable* tables = chain_tables(d_scratch, scratch_bytes, channels, nchunks);
+    constexpr size_t smem = sizeof(float2) * 4 * 2 * 32 * SH_PITCH;     // 4 warps x 2 tiles
+    static bool attr_done = false;
+    if (!attr_done) { CSDRB_CUDA(cudaFuncSetAttribute(shift_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    // The chain is one warp per channel and sequential (150 ns per chunk): a long one is cut into up to eight slices that run on a side stream, the main
+    // kernel follows slice by slice on the caller's stream.  CSDRB_SHIFT_SLICES=1 keeps everything on one stream (A/B, debugging).
+    static const int max_slices = getenv("CSDRB_SHIFT_SLICES") ? atoi(getenv("CSDRB_SHIFT_SLICES")) : kSideSlices;
+    int slices = nchunks / 256;
+    if (slices > max_slices) slices = max_slices;
+    if (slices > kSideSlices) slices = kSideSlices;
+    if (slices < 2) {
+        shift_phase_chain_kernel<<<channels, 32, 0, st>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, 0, nchunks);
+        CSDRB_CUDA(cudaGetLastError());
+        shift_bank_kernel<<<dim3((nchunks + 127) / 128, channels), 128, smem, st>>>(d_in, in_stride, d_out, out_stride, prm, chunk_phase, n, chunk, nchunks, 0, nchunks);
+        CSDRB_CUDA(cudaGetLastError());
+        return 2;
+    }
+    SideStream* ss = side_stream();
+    if (!ss) return -1;
+    const int per = (((nchunks + slices - 1) / slices) + 127) / 128 * 128;           // whole CTAs (4 warps x 32 chunks) per slice
+    std::lock_guard<std::mutex> lk(ss->mu);                             // the events are shared by every call on this device
+    CSDRB_CUDA(cudaEventRecord(ss->fork, st));
+    CSDRB_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    int launches = 0;
+    for (int i = 0; i < slices; i++) {
+        const int k_first = i * per;
+        if (k_first >= nchunks) break;
+        const int k_end = k_first + per < nchunks ? k_first + per : nchunks;
+        shift_phase_chain_kernel<<<channels, 32, 0, ss->stream>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, k_first, k_end - k_first);
+        CSDRB_CUDA(cudaGetLastError());
+        CSDRB_CUDA(cudaEventRecord(ss->slice[i], ss->stream));
+        CSDRB_CUDA(cudaStreamWaitEvent(st, ss->slice[i], 0));
+        shift_bank_kernel<<<dim3((k_end - k_first + 127) / 128, channels), 128, smem, st>>>(d_in, in_stride, d_out, out_stride, prm, chunk_phase, n, chunk, nchunks, k_first, k_end);
+        CSDRB_CUDA(cudaGetLastError());
+        launches += 2;
+    }
+    return launches;
 }
 
 int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out, long out_stride, int channels, int n,

@@ -298,6 +298,13 @@ static inline void cp_async16(void* smem_dst, const void* gmem_src)
     }
     std::memcpy(smem_dst, gmem_src, 16);
 }
+static inline void cp_async8(void* smem_dst, const void* gmem_src)
+{
+    if ((reinterpret_cast<uintptr_t>(smem_dst) & 7) || (reinterpret_cast<uintptr_t>(gmem_src) & 7)) {
+        std::fprintf(stderr, "cuda_emul: cp.async 8 needs 8-byte aligned addresses\n"); std::abort();
+    }
+    std::memcpy(smem_dst, gmem_src, 8);
+}
 static inline void cp_async_commit() {}
 template <int PENDING> static inline void cp_async_wait() {}
 }  // namespace csdrb

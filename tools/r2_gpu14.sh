@@ -16,6 +16,17 @@ import csv
 rows = [r for r in csv.reader(open('gpurun_out/r2_g14_c3_plan_launches.csv')) if len(r) > 10 and r[0].isdigit()]
 for r in rows[-12:]: print(r[4][:70], r[-1])
 PY
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py tests/test_gpu_shift_variants.py tests/test_gpu_fullsize.py -m gpu -x -q -k "shift" 2>&1 | tail -3 | tee gpurun_out/r2_g14_shift_tests.log
+python tools/bench_configs.py k 2>&1 | tee gpurun_out/r2_g14_kernels.txt | grep -E "K2|K5|K6|K1\+K3"
+CSDRB_SHIFT_SLICES=1 python tools/bench_configs.py k 2>&1 | grep -E "K2" | sed "s/^/[one stream] /" | tee -a gpurun_out/r2_g14_kernels.txt
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/r2_g14_shift_launches.csv python tools/run_shift_once.py > /dev/null 2>&1
+python - <<'PY'
+import csv
+rows = [r for r in csv.reader(open('gpurun_out/r2_g14_shift_launches.csv')) if len(r) > 10 and r[0].isdigit()]
+for r in rows[-18:]: print(r[4][:60], r[-1])
+PY
+python tools/bench_configs.py c4 2>&1 | grep -E "FUSED" | tee gpurun_out/r2_g14_c4.txt
+timeout 600 python -m pytest tests/test_gpu_parity2.py tests/test_gpu_round2.py tests/test_gpu_fullsize.py tests/test_gpu_nfm_tail.py -m gpu -x -q -k "ddc or nfm or bank" 2>&1 | tail -3 | tee gpurun_out/r2_g14_ddc_tests.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_g14_bench.json 2> gpurun_out/r2_g14_bench.err; tail -2 gpurun_out/r2_g14_bench.err
 python - <<'PY'
 import json
