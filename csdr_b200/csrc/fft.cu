@@ -270,11 +270,14 @@ bool fastddc_inv_fold_ok(int fft_size, int fft_inv_size)
 // The data-independent half of a call: block-to-block {remain, phase} chain (updates the carried state, writes the per-block state and the
 // output counts) and the post-shift phasors of every (channel, block) row.  Everything on stream `s`.
 int launch_fastddc_inv_prepare(const void* d_chan, int channels, int nblocks, int post_input_size, int post_decimation, int* d_remain_io, float* d_phase_io,
-                               int* d_out_total, const InvPrep& p, cudaStream_t s)
+                               int* d_out_total, const InvPrep& p, cudaStream_t s, cudaEvent_t before_phasors = nullptr)
 {
     fastddc_state_chain_kernel<<<channels, 32, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
                                                        p.blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, p.tables);
     CSDRB_CUDA(cudaGetLastError());
+    // the chain (votes, shuffles, a double add per step) shares an SM with a running fold at no cost to either; the phasor walk is FMUL/FADD and does not --
+    // a caller that has a fold in flight passes the event behind it
+    if (before_phasors) CSDRB_CUDA(cudaStreamWaitEvent(s, before_phasors, 0));
     fastddc_phasor_kernel<<<(unsigned)(((long)channels * nblocks + 127) / 128), 128, 0, s>>>(static_cast<const DdcChan*>(d_chan), p.blk_phase, p.phasor, channels, nblocks, p.kmax);
     CSDRB_CUDA(cudaGetLastError());
     return 0;
@@ -313,7 +316,8 @@ int launch_fastddc_inv_apply(const float2* d_spectra, int nblocks, const float2*
     switch (fft_inv_size) {
 #define X(M) case M: if constexpr (M >= 64 && M <= 1024) { \
         fastddc_ifft_rows_kernel<M><<<(unsigned)((npairs + rows_per_cta - 1) / rows_per_cta), 128, rsmem, st>>>(folded, p.blk_remain, p.blk_offset, d_out, out_stride, \
-                                                        scrap, post_input_size, post_decimation, nblocks, channels, tw, p.phasor, p.kmax); } break;
+                                                        scrap, post_input_size, post_decimation, nblocks, channels, tw, p.phasor, p.kmax, \
+                                                        (M / 8) / post_decimation, (M / 8) % post_decimation); } break;
         CSDRB_FFT_SIZES(X)
 #undef X
     }
@@ -449,13 +453,13 @@ static size_t plan_prep_bytes(int channels, int nblocks, int kmax)
     return fastddc_inv_scratch_bytes(channels, nblocks) + 16 + sizeof(float2) * (size_t)channels * nblocks * (size_t)kmax;
 }
 
-static int plan_enqueue_prepare(FastddcInvPlan* pl, int q)
+static int plan_enqueue_prepare(FastddcInvPlan* pl, int q, cudaEvent_t before_phasors = nullptr)
 {
     // state of set q := state of the other set (what the previous preparation left), then the chain advances it in place
     CSDRB_CUDA(cudaMemcpyAsync(pl->d_remain[q], pl->d_remain[1 - q], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
     CSDRB_CUDA(cudaMemcpyAsync(pl->d_phase[q], pl->d_phase[1 - q], sizeof(float) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
     if (int rc = launch_fastddc_inv_prepare(pl->d_chan, pl->channels, pl->nblocks, pl->post_input_size, pl->post_decimation, pl->d_remain[q], pl->d_phase[q],
-                                            pl->d_total[q], pl->prep[q], pl->side)) return rc;
+                                            pl->d_total[q], pl->prep[q], pl->side, before_phasors)) return rc;
     CSDRB_CUDA(cudaEventRecord(pl->ready[q], pl->side));
     return 0;
 }
@@ -535,11 +539,11 @@ int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_ta
                                           pl->post_input_size, pl->post_decimation, pl->prep[p], pl->folded, d_out, out_stride, pl->ready[p], pl->fold_done, st)) return rc;
     CSDRB_CUDA(cudaMemcpyAsync(d_out_total, pl->d_total[p], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, st));
     CSDRB_CUDA(cudaEventRecord(pl->post_done[p], st));
-    // look-ahead: the next run's chain + phasors, behind this run's fold (they would fight it for the FMA pipe), next to its IFFT/post step
+    // look-ahead: the next run's chain starts at once (next to this run's fold), its phasor walk behind the fold (the two would fight for the FMA pipe),
+    // next to the IFFT/post step and whatever the caller enqueues before the next run
     const int q = 1 - p;
-    CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->fold_done, 0));
     CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[q], 0));       // set q was last read two runs ago (a never-recorded event does not block)
-    if (int rc = plan_enqueue_prepare(pl, q)) return rc;
+    if (int rc = plan_enqueue_prepare(pl, q, pl->fold_done)) return rc;
     pl->cur = q; pl->ahead = true;
     return pl->nblocks;
 }

@@ -646,7 +646,7 @@ template <int M>
 __global__ void __launch_bounds__(128)
 fastddc_ifft_rows_kernel(const float2* __restrict__ folded, const int* __restrict__ blk_remain, const int* __restrict__ blk_offset, float2* __restrict__ out,
                          long out_stride, int scrap, int post_input_size, int post_decimation, int nblocks, int channels, const float2* __restrict__ tw,
-                         const float2* __restrict__ phasor, int kmax)
+                         const float2* __restrict__ phasor, int kmax, int step_k, int step_rem)
 {
     CSDRB_DYN_SMEM(smem_raw);
     constexpr int NTG = M / 8, G = 128 / NTG, PITCH = fft_smem_elems(M), R0 = fft_first_radix(M);
@@ -665,13 +665,19 @@ fastddc_ifft_rows_kernel(const float2* __restrict__ folded, const int* __restric
     sink.inv_m = 1.0f / (float)M;
     sink.y = out + (long)c * out_stride + off;
     const int cnt = first < post_input_size ? (post_input_size - first + post_decimation - 1) / post_decimation : 0;
+    // this thread's last-pass elements are tg + r*M/8, r = 0..7: which outputs are they (position q = k * post_decimation past the row's first kept sample), and
+    // their phasors.  One integer division per thread; from leg to leg q grows by M/8 = step_k * post_decimation + step_rem (the launcher's division).
+    const int q0 = tg - scrap - first;                                  // >= -(scrap + post_decimation): shift it non-negative for the division
+    const int lift = scrap + first;                                     // any multiple count >= (scrap + first) / post_decimation will do
+    int k = (q0 + lift * post_decimation) / post_decimation, rem = (q0 + lift * post_decimation) - k * post_decimation;
+    k -= lift;
 #pragma unroll
-    for (int r = 0; r < 8; r++) {                                       // this thread's last-pass elements are tg + r*M/8: which outputs are they, and their phasors
-        const int q = tg + r * NTG - scrap - first;
-        const int k = q >= 0 ? q / post_decimation : -1;
-        const bool keep = valid && k >= 0 && k < cnt && k * post_decimation == q;
+    for (int r = 0; r < 8; r++) {
+        const bool keep = valid && rem == 0 && k >= 0 && k < cnt;
         sink.kk[r] = keep ? k : -1;
         sink.ph[r] = keep ? __ldg(phasor + pc * kmax + k) : make_float2(0.f, 0.f);
+        k += step_k; rem += step_rem;
+        if (rem >= post_decimation) { rem -= post_decimation; k++; }
     }
     fft_r8_middle_passes<M, NTG, R0, true>(s, tw, tg);
     fft_pass_last_slots<M, NTG, true>(s, tw, tg, sink);

@@ -500,10 +500,11 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     constexpr size_t smem = sizeof(float2) * 4 * 2 * 32 * SH_PITCH;     // 4 warps x 2 tiles
     static bool attr_done = false;
     if (!attr_done) { CSDRB_CUDA(cudaFuncSetAttribute(shift_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
-    // The chain is one warp per channel and sequential (150 ns per chunk): a long one is cut into up to eight slices that run on a side stream, the main
-    // kernel follows slice by slice on the caller's stream.  CSDRB_SHIFT_SLICES=1 keeps everything on one stream (A/B, debugging).
-    static const int max_slices = getenv("CSDRB_SHIFT_SLICES") ? atoi(getenv("CSDRB_SHIFT_SLICES")) : kSideSlices;
-    int slices = nchunks / 256;
+    // The chain is one warp per channel and sequential (150 ns per chunk): a long one is cut into up to three slices that run on a side stream, the main
+    // kernel follows slice by slice on the caller's stream.  A slice must still fill the machine (a warp walks its 32 chunks tile after tile, ~3 us per tile:
+    // eight slices of 384 chunks x 64 channels ran the main kernel at 0.43 waves and gained nothing; r02 call 14).  CSDRB_SHIFT_SLICES=1: one stream.
+    static const int max_slices = getenv("CSDRB_SHIFT_SLICES") ? atoi(getenv("CSDRB_SHIFT_SLICES")) : 3;
+    int slices = (int)(((long)nchunks * channels) / (768L * 64));       // >= 768 chunks x 64 channels (or as many chunk-channels) per slice
     if (slices > max_slices) slices = max_slices;
     if (slices > kSideSlices) slices = kSideSlices;
     if (slices < 2) {

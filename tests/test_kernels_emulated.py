@@ -177,7 +177,7 @@ def test_ima_adpcm_rows_bit_exact(elementwise, oracle):
 
 
 # ------------------------------------------------------------------------------------------------------------------ K2 and shift variants
-@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37), (120 * 1024 + 5, 1024), (9000, 64), (9003, 8), (70_001, 100)])   # from the sixth on: > 96 chunks, the chain runs on its wrap table (phase_table.cuh); the last two: 4 and 2 chain slices
+@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37), (120 * 1024 + 5, 1024), (9000, 64), (9003, 8), (8 * 20_001 + 3, 8)])   # from the sixth on: > 96 chunks, the chain runs on its wrap table (phase_table.cuh); the last one: 20 002 chunks x 6 channels = two chain slices on the side stream
 def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):
     rng = np.random.default_rng(n)
     rates = np.array([-0.41, -0.085, 0.0, 0.2, 0.4999, 1e-4], np.float32)

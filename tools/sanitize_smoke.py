@@ -37,4 +37,9 @@ d = cb.fastddc_init(0.002, 64, 0.0); sp, ov = cb.fastddc_fwd_cc(cplx(130 * d.inp
 cb.fastagc_bank_f_s16(a[:, :19 * 1024], 1024, 1.0); cb.fastagc_bank_f_s16(a[:, :19 * 1000], 1000, 1.0); cb.fastagc_bank_f_s16(a[:, :8 * 2048], 2048, 1.0)
 bank = cb.DdcBank(np.linspace(-0.4, 0.4, 37), 50, cb.firdes_lowpass_f(801, 0.5 / 50), demod=True, chunk=1024)
 w = cplx(60000); o1 = bank.process(w[:20000]); bank.set_rate(3, 0.11); bank.process(w[o1.shape[1] * 50:o1.shape[1] * 50 + 30000]); bank.close()
+# round 2, late: fastddc plan object (look-ahead, retune), sliced K2 chain (>= 512 chunks), ragged sizes
+plan = cb.FastddcInvPlan(list(np.linspace(-0.4, 0.4, 5)), 64, 0.002, 7)
+sp7, _ = cb.fastddc_fwd_cc(cplx(7 * d.input_size), d)
+plan.run(sp7); plan.set_shift(2, 0.123); plan.run(sp7); plan.state(); plan.run(sp7); plan.close()
+cb.shift_addition_bank_cc(cplx(2, 600 * 64 + 13), [0.31, -0.07], chunk=64); cb.shift_addition_bank_cc(cplx(1100 * 1024 + 1), [0.2], chunk=1024)
 torch.cuda.synchronize(); print("sanitize_smoke: all kernels ran")
