@@ -500,7 +500,8 @@ int fastddc_inv_plan_create(void** out_plan, const void* h_chan, int channels, i
     bool ok = cudaMalloc(reinterpret_cast<void**>(&pl->d_chan), sizeof(DdcChan) * channels) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&pl->folded), sizeof(float2) * (size_t)channels * nblocks * fft_inv_size) == cudaSuccess &&
               cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&pl->fold_done, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&pl->chan_set, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&pl->fold_done, (getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1') ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&pl->chan_set, cudaEventDisableTiming) == cudaSuccess;
     const size_t state_part = fastddc_inv_scratch_bytes(channels, nblocks);
     for (int i = 0; i < 2 && ok; i++) {
         ok = cudaMalloc(reinterpret_cast<void**>(&pl->d_remain[i]), sizeof(int) * channels) == cudaSuccess && cudaMalloc(reinterpret_cast<void**>(&pl->d_phase[i]), sizeof(float) * channels) == cudaSuccess &&
@@ -531,6 +532,9 @@ int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_ta
     if (!pl || !d_spectra || !d_taps_fft || !d_out || !d_out_total) { set_error("fastddc_inv_plan_run: null pointer"); return -1; }
     std::lock_guard<std::mutex> lk(pl->mu);
     const int p = pl->cur;
+    static const bool trace = getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1';      // tools only: timeline of this run, printed after a synchronize
+    cudaEvent_t tev[5] = {};
+    if (trace) { for (auto& e : tev) CSDRB_CUDA(cudaEventCreate(&e)); CSDRB_CUDA(cudaEventRecord(tev[0], st)); }
     if (!pl->ahead) {                                                     // first run, or the look-ahead was dropped by a retune / set_state
         if (int rc = plan_enqueue_prepare(pl, p)) return rc;
     }
@@ -539,12 +543,24 @@ int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_ta
                                           pl->post_input_size, pl->post_decimation, pl->prep[p], pl->folded, d_out, out_stride, pl->ready[p], pl->fold_done, st)) return rc;
     CSDRB_CUDA(cudaMemcpyAsync(d_out_total, pl->d_total[p], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, st));
     CSDRB_CUDA(cudaEventRecord(pl->post_done[p], st));
+    if (trace) CSDRB_CUDA(cudaEventRecord(tev[2], st));
     // look-ahead: the next run's chain starts at once (next to this run's fold), its phasor walk behind the fold (the two would fight for the FMA pipe),
     // next to the IFFT/post step and whatever the caller enqueues before the next run
     const int q = 1 - p;
     CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[q], 0));       // set q was last read two runs ago (a never-recorded event does not block)
-    if (int rc = plan_enqueue_prepare(pl, q, pl->fold_done)) return rc;
+    if (trace) CSDRB_CUDA(cudaEventRecord(tev[3], pl->side));
+    static const bool walk_after_ifft = getenv("CSDRB_PLAN_WALK") && getenv("CSDRB_PLAN_WALK")[0] == 'i';       // A/B: the phasor walk behind the IFFT step instead of behind the fold
+    if (int rc = plan_enqueue_prepare(pl, q, walk_after_ifft ? pl->post_done[p] : pl->fold_done)) return rc;
     pl->cur = q; pl->ahead = true;
+    if (trace) {
+        CSDRB_CUDA(cudaEventRecord(tev[4], pl->side));
+        CSDRB_CUDA(cudaStreamSynchronize(st)); CSDRB_CUDA(cudaStreamSynchronize(pl->side));
+        float t[5] = {};
+        for (int i = 2; i < 5; ++i) cudaEventElapsedTime(&t[i], tev[0], tev[i]);
+        cudaEventElapsedTime(&t[1], tev[0], pl->fold_done);
+        fprintf(stderr, "[plan trace] us from run start: fold done %.1f, IFFT done %.1f | look-ahead for the next run: starts %.1f, done %.1f\n", t[1] * 1e3f, t[2] * 1e3f, t[3] * 1e3f, t[4] * 1e3f);
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     return pl->nblocks;
 }
 

@@ -100,18 +100,21 @@ __device__ __forceinline__ void tile_load_rows(float2* __restrict__ tile, const 
 }
 constexpr int SH_PITCH = SH_TILE + 1;             // odd pitch in 8-byte units: row-wise walks are conflict-free
 
-// Round 2, second form: the 32 x 32 tile of step t+1 arrives by cp.async (8-byte pieces: the odd pitch that keeps the row walks conflict-free rules out
-// 16-byte ones) while step t is computed and stored -- ncu had 72 % of the first form's stall samples on the tile loads, 29 % of the warp slots filled and 46
-// instructions per sample, most of them index arithmetic and predicates; here every chunk of a warp but a channel's last is full, so whole tiles take a
-// check-free path.  [k_first, k_end) is the launcher's slice of the chunk range.
+// Round 2, second form: 32 chunks x 16 samples per tile, the tile of step t+1 arriving by cp.async (8-byte pieces: the odd pitch that keeps the row walks
+// conflict-free rules out 16-byte ones) while step t is rotated in registers and stored.  ncu on the first form: 72 % of the stall samples on the tile loads, 46
+// instructions per sample, most of them index arithmetic and predicates; a 32 x 32 double-buffered tile (67 KB per CTA) halved the resident warps and was slower
+// (715 vs 616 us) -- hence half-width tiles: two of them are the first form's shared-memory footprint.  Every chunk of a warp but a channel's last is full, so
+// whole tiles take a check-free path with bumped pointers.  [k_first, k_end) is the launcher's slice of the chunk range.
+constexpr int SH_W = 16, SH_WP = SH_W + 1;                              // tile width in samples, padded pitch
+
 __global__ void __launch_bounds__(128)
 shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                   const float3* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks, int k_first, int k_end)
 {
-    CSDRB_DYN_SMEM(smem_raw);
-    constexpr int TILE = 32 * SH_PITCH;
+    constexpr int TILE = 32 * SH_WP;
+    __shared__ float2 tiles[4][2][TILE];                                // 34.8 KB: two tiles per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* buf = reinterpret_cast<float2*>(smem_raw) + warp * 2 * TILE;             // two tiles per warp
+    float2* buf = &tiles[warp][0][0];
     const int ch = blockIdx.y;
     const int k0 = k_first + (blockIdx.x * 4 + warp) * 32;              // first chunk of this warp
     if (k0 >= k_end) return;
@@ -130,36 +133,46 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
     const int rows = min(32, k_end - k0);
     const int max_len = min(chunk, n - k0 * chunk);          // the first chunk of the warp is never the short one
     const int last_len = min(chunk, n - (k0 + rows - 1) * chunk);       // only the last row can be shorter (the channel's last chunk)
-    const float2* xw = x + (long)k0 * chunk + lane;
-    float2* yw = y + (long)k0 * chunk + lane;
+    // a copy / store instruction moves two rows: lanes 0..15 one row, lanes 16..31 the next
+    const int half = lane >> 4, col = lane & 15;
+    const float2* xw = x + (long)(k0 + half) * chunk + col;
+    float2* yw = y + (long)(k0 + half) * chunk + col;
+    const long step2 = 2L * chunk;
     auto issue = [&](int t0, float2* tile) {
-        if (t0 + 32 <= last_len) {
-            for (int r = 0; r < rows; r++) cp_async8(tile + r * SH_PITCH + lane, xw + (long)r * chunk + t0);
+        const float2* src = xw + t0;
+        float2* dst = tile + half * SH_WP + col;
+        if (rows == 32 && t0 + SH_W <= last_len) {
+#pragma unroll 4
+            for (int r = 0; r < 32; r += 2, src += step2, dst += 2 * SH_WP) cp_async8(dst, src);
         } else {
-            for (int r = 0; r < rows; r++)
-                if (t0 + lane < (r == rows - 1 ? last_len : max_len)) cp_async8(tile + r * SH_PITCH + lane, xw + (long)r * chunk + t0);
+            for (int r = half; r < rows; r += 2, src += step2, dst += 2 * SH_WP)
+                if (t0 + col < (r == rows - 1 ? last_len : max_len)) cp_async8(dst, src);
         }
     };
     issue(0, buf);
     cp_async_commit();
-    for (int t0 = 0, it = 0; t0 < max_len; t0 += SH_TILE, it++) {
+    for (int t0 = 0, it = 0; t0 < max_len; t0 += SH_W, it++) {
         float2* tile = buf + (it & 1) * TILE;
-        if (t0 + SH_TILE < max_len) issue(t0 + SH_TILE, buf + ((it + 1) & 1) * TILE);
+        if (t0 + SH_W < max_len) issue(t0 + SH_W, buf + ((it + 1) & 1) * TILE);
         cp_async_commit();
         cp_async_wait<1>();                                             // this step's tile has landed (the one just issued may still be in flight)
         __syncwarp();
         if (live) {
-            float2* row = tile + lane * SH_PITCH;
-            const int steps = min(SH_TILE, my_len - t0);
-            if (steps == SH_TILE) {
-#pragma unroll 8
-                for (int j = 0; j < SH_TILE; j++) {
-                    const float2 v = row[j];
-                    row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+            float2* row = tile + lane * SH_WP;
+            const int steps = min(SH_W, my_len - t0);
+            if (steps == SH_W) {
+                float2 v[SH_W];
+#pragma unroll
+                for (int j = 0; j < SH_W; j++) v[j] = row[j];
+#pragma unroll
+                for (int j = 0; j < SH_W; j++) {
+                    v[j] = make_float2(__fsub_rn(__fmul_rn(c, v[j].x), __fmul_rn(s, v[j].y)), __fadd_rn(__fmul_rn(s, v[j].x), __fmul_rn(c, v[j].y)));
                     const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
                     const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
                     c = cn; s = sn;
                 }
+#pragma unroll
+                for (int j = 0; j < SH_W; j++) row[j] = v[j];
             } else {
                 for (int j = 0; j < steps; j++) {
                     const float2 v = row[j];
@@ -171,12 +184,16 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
             }
         }
         __syncwarp();
-        if (t0 + 32 <= last_len) {
-#pragma unroll 8
-            for (int r = 0; r < rows; r++) yw[(long)r * chunk + t0] = tile[r * SH_PITCH + lane];
-        } else {
-            for (int r = 0; r < rows; r++)
-                if (t0 + lane < (r == rows - 1 ? last_len : max_len)) yw[(long)r * chunk + t0] = tile[r * SH_PITCH + lane];
+        {
+            float2* dst = yw + t0;
+            const float2* src = tile + half * SH_WP + col;
+            if (rows == 32 && t0 + SH_W <= last_len) {
+#pragma unroll 4
+                for (int r = 0; r < 32; r += 2, dst += step2, src += 2 * SH_WP) *dst = *src;
+            } else {
+                for (int r = half; r < rows; r += 2, dst += step2, src += 2 * SH_WP)
+                    if (t0 + col < (r == rows - 1 ? last_len : max_len)) *dst = *src;
+            }
         }
         __syncwarp();                                                   // the tile is free again for the copy issued two steps from now
     }
@@ -497,9 +514,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     float* chunk_phase = static_cast<float*>(d_scratch);
     const float3* prm = reinterpret_cast<const float3*>(d_params);
     WrapTable* tables = chain_tables(d_scratch, scratch_bytes, channels, nchunks);
-    constexpr size_t smem = sizeof(float2) * 4 * 2 * 32 * SH_PITCH;     // 4 warps x 2 tiles
-    static bool attr_done = false;
-    if (!attr_done) { CSDRB_CUDA(cudaFuncSetAttribute(shift_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    constexpr size_t smem = 0;                                          // the tiles are static shared memory
     // The chain is one warp per channel and sequential (150 ns per chunk): a long one is cut into up to three slices that run on a side stream, the main
     // kernel follows slice by slice on the caller's stream.  A slice must still fill the machine (a warp walks its 32 chunks tile after tile, ~3 us per tile:
     // eight slices of 384 chunks x 64 channels ran the main kernel at 0.43 waves and gained nothing; r02 call 14).  CSDRB_SHIFT_SLICES=1: one stream.
