@@ -270,10 +270,10 @@ bool fastddc_inv_fold_ok(int fft_size, int fft_inv_size)
 // The data-independent half of a call: block-to-block {remain, phase} chain (updates the carried state, writes the per-block state and the
 // output counts) and the post-shift phasors of every (channel, block) row.  Everything on stream `s`.
 int launch_fastddc_inv_prepare(const void* d_chan, int channels, int nblocks, int post_input_size, int post_decimation, int* d_remain_io, float* d_phase_io,
-                               int* d_out_total, const InvPrep& p, cudaStream_t s, cudaEvent_t before_phasors = nullptr)
+                               int* d_out_total, const InvPrep& p, cudaStream_t s, cudaEvent_t before_phasors = nullptr, bool build_tables = true)
 {
-    fastddc_state_chain_kernel<<<channels, 32, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
-                                                       p.blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, p.tables);
+    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
+                                                       p.blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, p.tables, build_tables ? 1 : 0);
     CSDRB_CUDA(cudaGetLastError());
     // the chain (votes, shuffles, a double add per step) shares an SM with a running fold at no cost to either; the phasor walk is FMUL/FADD and does not --
     // a caller that has a fold in flight passes the event behind it
@@ -385,8 +385,8 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
         CSDRB_CUDA(cudaFreeAsync(folded, st));
         return 4;
     }
-    fastddc_state_chain_kernel<<<channels, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
-                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables);
+    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+                                                                    blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables, 1);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {
         // Tile = CT channels x BT blocks per CTA (each spectrum bin fetched once per CT channels, each tap once per BT blocks).  Big tiles
@@ -445,6 +445,8 @@ struct FastddcInvPlan {
     int cur = 0;                    // the set the NEXT run reads
     bool ahead = false;             // ... has already been enqueued on the side stream
     bool chan_dirty = false;        // a retune is in flight on the side stream: the next fold waits for it
+    WrapTable* tables = nullptr;    // one wrap table per channel, shared by both sets (they depend on the channel's increment only)
+    bool tables_built = false;
     std::mutex mu;
 };
 
@@ -459,7 +461,8 @@ static int plan_enqueue_prepare(FastddcInvPlan* pl, int q, cudaEvent_t before_ph
     CSDRB_CUDA(cudaMemcpyAsync(pl->d_remain[q], pl->d_remain[1 - q], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
     CSDRB_CUDA(cudaMemcpyAsync(pl->d_phase[q], pl->d_phase[1 - q], sizeof(float) * pl->channels, cudaMemcpyDeviceToDevice, pl->side));
     if (int rc = launch_fastddc_inv_prepare(pl->d_chan, pl->channels, pl->nblocks, pl->post_input_size, pl->post_decimation, pl->d_remain[q], pl->d_phase[q],
-                                            pl->d_total[q], pl->prep[q], pl->side, before_phasors)) return rc;
+                                            pl->d_total[q], pl->prep[q], pl->side, before_phasors, !pl->tables_built)) return rc;
+    pl->tables_built = true;
     CSDRB_CUDA(cudaEventRecord(pl->ready[q], pl->side));
     return 0;
 }
@@ -471,7 +474,7 @@ void fastddc_inv_plan_destroy(void* plan)
     int prev = 0; cudaGetDevice(&prev); cudaSetDevice(pl->dev);
     if (pl->side) cudaStreamSynchronize(pl->side);
     cudaDeviceSynchronize();
-    cudaFree(pl->d_chan); cudaFree(pl->folded);
+    cudaFree(pl->d_chan); cudaFree(pl->folded); cudaFree(pl->tables);
     for (int i = 0; i < 2; i++) {
         cudaFree(pl->d_remain[i]); cudaFree(pl->d_phase[i]); cudaFree(pl->d_total[i]); cudaFree(pl->prep_mem[i]);
         if (pl->ready[i]) cudaEventDestroy(pl->ready[i]);
@@ -499,6 +502,7 @@ int fastddc_inv_plan_create(void** out_plan, const void* h_chan, int channels, i
     pl->kmax = (post_input_size + post_decimation - 1) / post_decimation;
     bool ok = cudaMalloc(reinterpret_cast<void**>(&pl->d_chan), sizeof(DdcChan) * channels) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&pl->folded), sizeof(float2) * (size_t)channels * nblocks * fft_inv_size) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&pl->tables), sizeof(WrapTable) * channels) == cudaSuccess &&
               cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&pl->fold_done, (getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1') ? cudaEventDefault : cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&pl->chan_set, cudaEventDisableTiming) == cudaSuccess;
@@ -513,7 +517,7 @@ int fastddc_inv_plan_create(void** out_plan, const void* h_chan, int channels, i
         pr.blk_remain = reinterpret_cast<int*>(base);
         pr.blk_phase = reinterpret_cast<float*>(pr.blk_remain + (size_t)channels * nblocks);
         pr.blk_offset = reinterpret_cast<int*>(pr.blk_phase + (size_t)channels * nblocks);
-        pr.tables = nblocks > 96 ? reinterpret_cast<WrapTable*>(base + (((size_t)channels * nblocks * 12 + 64 + 15) & ~(size_t)15)) : nullptr;
+        pr.tables = nblocks > 96 ? pl->tables : nullptr;
         pr.phasor = reinterpret_cast<float2*>(base + ((state_part + 15) & ~(size_t)15));
         pr.kmax = pl->kmax;
         ok = cudaMemset(pl->d_remain[i], 0, sizeof(int) * channels) == cudaSuccess && cudaMemset(pl->d_phase[i], 0, sizeof(float) * channels) == cudaSuccess &&
@@ -544,13 +548,17 @@ int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_ta
     CSDRB_CUDA(cudaMemcpyAsync(d_out_total, pl->d_total[p], sizeof(int) * pl->channels, cudaMemcpyDeviceToDevice, st));
     CSDRB_CUDA(cudaEventRecord(pl->post_done[p], st));
     if (trace) CSDRB_CUDA(cudaEventRecord(tev[2], st));
-    // look-ahead: the next run's chain starts at once (next to this run's fold), its phasor walk behind the fold (the two would fight for the FMA pipe),
-    // next to the IFFT/post step and whatever the caller enqueues before the next run
+    // look-ahead: the next run's chain and phasor walk, on the side stream
     const int q = 1 - p;
     CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[q], 0));       // set q was last read two runs ago (a never-recorded event does not block)
     if (trace) CSDRB_CUDA(cudaEventRecord(tev[3], pl->side));
-    static const bool walk_after_ifft = getenv("CSDRB_PLAN_WALK") && getenv("CSDRB_PLAN_WALK")[0] == 'i';       // A/B: the phasor walk behind the IFFT step instead of behind the fold
-    if (int rc = plan_enqueue_prepare(pl, q, walk_after_ifft ? pl->post_done[p] : pl->fold_done)) return rc;
+    // Measured at 592 blocks (r02 call 18): a chain walked NEXT TO the fold stretches the fold from 168 to 205 us (one chain warp per channel, 64 SMs with a guest
+    // that holds up every barrier of the fold CTA there), so chain and walk go behind the fold, next to the IFFT step and the caller's next forward FFT
+    // ('f', the default).  CSDRB_PLAN_ORDER for A/B: 'd' = chain at once, walk behind the fold; 'i' = chain at once, walk behind the IFFT step; 's' = both behind the IFFT step.
+    static const char order = getenv("CSDRB_PLAN_ORDER") ? getenv("CSDRB_PLAN_ORDER")[0] : 'f';
+    if (order == 'f') CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->fold_done, 0));
+    if (order == 's') CSDRB_CUDA(cudaStreamWaitEvent(pl->side, pl->post_done[p], 0));
+    if (int rc = plan_enqueue_prepare(pl, q, order == 'i' ? pl->post_done[p] : (order == 'd' ? pl->fold_done : nullptr))) return rc;
     pl->cur = q; pl->ahead = true;
     if (trace) {
         CSDRB_CUDA(cudaEventRecord(tev[4], pl->side));
@@ -577,6 +585,7 @@ int fastddc_inv_plan_set_channel(void* plan, int c, const void* h_chan_one)
     CSDRB_CUDA(cudaEventRecord(pl->chan_set, pl->side));
     pl->chan_dirty = true;
     pl->ahead = false;                                                    // set cur was prepared with the old parameters; the state it started from is still in the other set
+    pl->tables_built = false;
     return 0;
 }
 

@@ -304,49 +304,81 @@ struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per ch
 #define PI_F 3.14159265358979323846f
 __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph); }
 
-// per channel (one WARP each): walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158)
+// Walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158).  A chain is sequential and a step is ~400 cycles of dependent
+// latency (add, two votes, shuffles, a double add, the wrap loop's branches), so one WARP carries CPW channels side by side: their steps interleave in the
+// pipeline and the walk costs the same 0.2 us per block for four channels as for one (the consumers' look-ahead window is the IFFT step; r02 timelines).
+constexpr int CHAIN_CPW = 4;
+
 __global__ void __launch_bounds__(32)
 fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
                            int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
                            int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation,
-                           WrapTable* __restrict__ tables)
+                           WrapTable* __restrict__ tables, int build_tables)
 {
-    const int c = blockIdx.x, lane = threadIdx.x;
-    if (c >= channels) return;
-    int remain = remain_io[c], off = 0;
-    float ph = phase_io[c];
-    __syncwarp();                                                       // every lane has read the carried state before lane 0 overwrites it
-    const float rate = chan[c].rate;
-    // when post_decimation divides post_input_size (every fastddc geometry with an even scrap, e.g. 448/2) and the carried
-    // remainder is in range, both the per-block output count and the remainder are constants: no integer division in the loop
-    const bool steady = (post_input_size % post_decimation == 0) && remain >= 0 && remain < post_decimation;
+    const int c0 = blockIdx.x * CHAIN_CPW, lane = threadIdx.x;
+    if (c0 >= channels) return;
+    const int nc = min(CHAIN_CPW, channels - c0);
+    int remain[CHAIN_CPW], off[CHAIN_CPW];
+    float ph[CHAIN_CPW], adv_const[CHAIN_CPW], rate[CHAIN_CPW];
+    WrapLanes w[CHAIN_CPW];
     const int k_const = post_input_size / post_decimation;
-    const float adv_const = __fmul_rn(__fmul_rn(rate, PI_F), (float)k_const);
-    const bool tab = steady && tables != nullptr && nblocks > 96;      // a long steady chain runs on its increment's wrap table (phase_table.cuh)
-    WrapLanes w; w.n = 0; w.lo = w.hi = w.thr0 = w.thr1 = 0.f; w.K0 = w.K1 = 0.0;
-    if (tab) {
-        if (lane == 0) wrap_table_build(adv_const, tables + c);
+    bool all_tab = tables != nullptr && nblocks > 96 && (post_input_size % post_decimation == 0);
+#pragma unroll
+    for (int i = 0; i < CHAIN_CPW; i++) {
+        const int c = min(c0 + i, channels - 1);                        // slots past the bank shadow its last channel (they compute, they do not store)
+        remain[i] = remain_io[c]; ph[i] = phase_io[c]; off[i] = 0;
+        rate[i] = chan[c].rate;
+        adv_const[i] = __fmul_rn(__fmul_rn(rate[i], PI_F), (float)k_const);
+        // when post_decimation divides post_input_size (every fastddc geometry with an even scrap, e.g. 448/2) and the carried remainder is in range, both
+        // the per-block output count and the remainder are constants: no integer division in the loop, and the phase chain runs on its increment's wrap table
+        all_tab = all_tab && remain[i] >= 0 && remain[i] < post_decimation;
+    }
+    __syncwarp();                                                       // every lane has read the carried state before lane 0 overwrites it
+    if (all_tab) {
+        // the tables depend on the channel's increment only: a caller that keeps them (the plan object) has them built once; lane i builds channel c0 + i's
+        if (build_tables && lane < nc) wrap_table_build(__fmul_rn(__fmul_rn(chan[c0 + lane].rate, PI_F), (float)k_const), tables + c0 + lane);
         __syncwarp();
-        w = wrap_lanes_load(tables + c, lane);
-    }
-    for (int b = 0; b < nblocks; b++) {
-        if (lane == 0) {                                                // [block][channel] like the consumers index it
-            blk_remain[(long)b * channels + c] = remain;
-            blk_phase[(long)b * channels + c] = ph;
-            blk_offset[(long)b * channels + c] = off;
+#pragma unroll
+        for (int i = 0; i < CHAIN_CPW; i++) w[i] = wrap_lanes_load(tables + min(c0 + i, channels - 1), lane);
+        for (int b = 0; b < nblocks; b++) {
+            if (lane < nc) {                                            // lane i stores channel c0 + i: [block][channel] like the consumers index it
+                float phs = ph[0]; int rm = remain[0];
+#pragma unroll
+                for (int i = 1; i < CHAIN_CPW; i++) if (lane == i) { phs = ph[i]; rm = remain[i]; }
+                const long at = (long)b * channels + c0 + lane;
+                blk_remain[at] = rm; blk_phase[at] = phs; blk_offset[at] = b * k_const;
+            }
+#pragma unroll
+            for (int i = 0; i < CHAIN_CPW; i++) ph[i] = wrap_after_add_warp(__fadd_rn(ph[i], adv_const[i]), w[i]);
         }
-        if (steady) {
-            ph = tab ? wrap_after_add_warp(__fadd_rn(ph, adv_const), w) : ddc_wrap(__fadd_rn(ph, adv_const));
-            off += k_const;
-        } else {
-            int k = 0, pos = remain;
-            if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
-            remain = pos - post_input_size;
-            ph = ddc_wrap(__fadd_rn(ph, __fmul_rn(__fmul_rn(rate, PI_F), (float)k)));
-            off += k;
+#pragma unroll
+        for (int i = 0; i < CHAIN_CPW; i++) off[i] = nblocks * k_const;
+    } else {
+        for (int i = 0; i < nc; i++) {                                  // general form, one channel after the other
+            const bool steady = (post_input_size % post_decimation == 0) && remain[i] >= 0 && remain[i] < post_decimation;
+            for (int b = 0; b < nblocks; b++) {
+                if (lane == 0) {
+                    const long at = (long)b * channels + c0 + i;
+                    blk_remain[at] = remain[i]; blk_phase[at] = ph[i]; blk_offset[at] = off[i];
+                }
+                if (steady) {
+                    ph[i] = ddc_wrap(__fadd_rn(ph[i], adv_const[i]));
+                    off[i] += k_const;
+                } else {
+                    int k = 0, pos = remain[i];
+                    if (pos < post_input_size) { k = (post_input_size - pos + post_decimation - 1) / post_decimation; pos += k * post_decimation; }
+                    remain[i] = pos - post_input_size;
+                    ph[i] = ddc_wrap(__fadd_rn(ph[i], __fmul_rn(__fmul_rn(rate[i], PI_F), (float)k)));
+                    off[i] += k;
+                }
+            }
         }
     }
-    if (lane == 0) { remain_io[c] = remain; phase_io[c] = ph; out_total[c] = off; }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < CHAIN_CPW; i++)
+            if (i < nc) { remain_io[c0 + i] = remain[i]; phase_io[c0 + i] = ph[i]; out_total[c0 + i] = off[i]; }
+    }
 }
 
 template <int M>

@@ -39,29 +39,56 @@ __device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
 // instead of ~1 200; the build costs about as much as thirty direct steps).  The last, shorter chunk has its own increment: direct.
 constexpr int kChainTableMin = 96;
 
-// chain of nchunks starting phases, one WARP per channel: steps with the full-chunk increment go through the register-resident wrap table
-// (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases are stored at a time.  `step(ph, len)` is the direct form.
+// chains of nchunks starting phases, one WARP per CHAIN_CPW channels: steps with the full-chunk increment go through the register-resident wrap tables
+// (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases per channel are stored at a time.  A step is a few hundred cycles of
+// dependent latency, so the channels of a warp walk side by side at the price of one.  `step(slot, ph, len)` is the direct form for slot's channel.
+constexpr int CHAIN_CPW = 4;
+
 template <class Step>
-__device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, int c, int n, int chunk, int nchunks, float inc_full,
-                                           WrapTable* __restrict__ tables, Step step, bool build_table = true)
+__device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, long dst_stride, int c0, int channels, int n, int chunk, int nchunks,
+                                           const float (&inc_full)[CHAIN_CPW], WrapTable* __restrict__ tables, Step step, bool build_table = true)
 {
     const int lane = threadIdx.x;
+    const int nc = min(CHAIN_CPW, channels - c0);
     const bool tab = tables != nullptr;
-    WrapLanes w; w.n = 0; w.lo = w.hi = w.thr0 = w.thr1 = 0.f; w.K0 = w.K1 = 0.0;
+    WrapLanes w[CHAIN_CPW];
     if (tab) {
-        if (build_table && lane == 0) wrap_table_build(inc_full, tables + c);
+        if (build_table && lane < nc) {                                 // lane i builds channel c0 + i's table
+            float inc = inc_full[0];
+#pragma unroll
+            for (int i = 1; i < CHAIN_CPW; i++) if (lane == i) inc = inc_full[i];
+            wrap_table_build(inc, tables + c0 + lane);
+        }
         __syncwarp();
-        w = wrap_lanes_load(tables + c, lane);
+#pragma unroll
+        for (int i = 0; i < CHAIN_CPW; i++) w[i] = wrap_lanes_load(tables + min(c0 + i, channels - 1), lane);
     }
-    float ph = phase_io[c], mine = 0.f;
-    __syncwarp();                                                       // every lane has read the carried phase before lane 0 overwrites it
+    float ph[CHAIN_CPW], mine[CHAIN_CPW];
+#pragma unroll
+    for (int i = 0; i < CHAIN_CPW; i++) { ph[i] = phase_io[min(c0 + i, channels - 1)]; mine[i] = 0.f; }   // slots past the bank shadow its last channel
+    __syncwarp();                                                       // every lane has read the carried phases before lane 0 overwrites them
     for (int k = 0; k < nchunks; k++) {
-        if ((k & 31) == lane) mine = ph;
-        if ((k & 31) == 31 || k == nchunks - 1) { if ((k & ~31) + lane <= k) dst[(k & ~31) + lane] = mine; }
+        if ((k & 31) == lane) {
+#pragma unroll
+            for (int i = 0; i < CHAIN_CPW; i++) mine[i] = ph[i];
+        }
+        if (((k & 31) == 31 || k == nchunks - 1) && (k & ~31) + lane <= k) {
+#pragma unroll
+            for (int i = 0; i < CHAIN_CPW; i++) if (i < nc) dst[(long)(c0 + i) * dst_stride + (k & ~31) + lane] = mine[i];
+        }
         const int len = min(chunk, n - k * chunk);
-        ph = (tab && len == chunk) ? wrap_after_add_warp(__fadd_rn(ph, inc_full), w) : step(ph, len);
+        if (tab && len == chunk) {
+#pragma unroll
+            for (int i = 0; i < CHAIN_CPW; i++) ph[i] = wrap_after_add_warp(__fadd_rn(ph[i], inc_full[i]), w[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CHAIN_CPW; i++) ph[i] = step(i, ph[i], len);
+        }
     }
-    if (lane == 0) phase_io[c] = ph;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < CHAIN_CPW; i++) if (i < nc) phase_io[c0 + i] = ph[i];
+    }
 }
 
 // One slice of the chain: chunks k_first .. k_first + k_count - 1 of every channel (the launcher cuts a long chain into slices so that the main kernel can
@@ -70,13 +97,15 @@ __global__ void __launch_bounds__(32)
 shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                          int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables, int k_first, int k_count)
 {
-    const int c = blockIdx.x;
-    if (c >= channels) return;
-    const float rate2 = params[c].z;
+    const int c0 = blockIdx.x * CHAIN_CPW;
+    if (c0 >= channels) return;
     const int count = min(k_count, nchunks - k_first);
     if (count <= 0) return;
-    chain_walk(phase_io, chunk_phase + (long)c * nchunks + k_first, c, n - k_first * chunk, chunk, count, __fmul_rn(__fmul_rn(rate2, PI_F), (float)chunk), tables,
-               [rate2](float ph, int len) { return advance_phase(ph, rate2, len); }, k_first == 0);
+    float rate2[CHAIN_CPW], inc[CHAIN_CPW];
+#pragma unroll
+    for (int i = 0; i < CHAIN_CPW; i++) { rate2[i] = params[min(c0 + i, channels - 1)].z; inc[i] = __fmul_rn(__fmul_rn(rate2[i], PI_F), (float)chunk); }
+    chain_walk(phase_io, chunk_phase + k_first, nchunks, c0, channels, n - k_first * chunk, chunk, count, inc, tables,
+               [&rate2](int i, float ph, int len) { return advance_phase(ph, rate2[i], len); }, k_first == 0);
 }
 
 constexpr int SH_TILE = 32;                       // samples per lane per sub-step
@@ -100,23 +129,18 @@ __device__ __forceinline__ void tile_load_rows(float2* __restrict__ tile, const 
 }
 constexpr int SH_PITCH = SH_TILE + 1;             // odd pitch in 8-byte units: row-wise walks are conflict-free
 
-// Round 2, second form: 32 chunks x 16 samples per tile, the tile of step t+1 arriving by cp.async (8-byte pieces: the odd pitch that keeps the row walks
-// conflict-free rules out 16-byte ones) while step t is rotated in registers and stored.  ncu on the first form: 72 % of the stall samples on the tile loads, 46
-// instructions per sample, most of them index arithmetic and predicates; a 32 x 32 double-buffered tile (67 KB per CTA) halved the resident warps and was slower
-// (715 vs 616 us) -- hence half-width tiles: two of them are the first form's shared-memory footprint.  Every chunk of a warp but a channel's last is full, so
-// whole tiles take a check-free path with bumped pointers.  [k_first, k_end) is the launcher's slice of the chunk range.
-constexpr int SH_W = 16, SH_WP = SH_W + 1;                              // tile width in samples, padded pitch
-
+// (Two double-buffered forms were measured against this kernel in round 2 -- the tile of step t+1 arriving by 8-byte cp.async while step t is rotated: 32 x 32
+// tiles, 67 KB per CTA, 715 us for 64 x 2.4 M; 32 x 16 tiles in the same shared memory as here with the rotation in registers, 740 us -- against 616 us for this
+// plain load / rotate / store form with its 24 resident warps per SM.  profiles/r02_shift_bank_*_ncu_summary.json.)
 __global__ void __launch_bounds__(128)
 shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restrict__ out, long out_stride,
                   const float3* __restrict__ params, const float* __restrict__ chunk_phase, int n, int chunk, int nchunks, int k_first, int k_end)
 {
-    constexpr int TILE = 32 * SH_WP;
-    __shared__ float2 tiles[4][2][TILE];                                // 34.8 KB: two tiles per warp
+    __shared__ float2 tile_all[4][32 * SH_PITCH];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* buf = &tiles[warp][0][0];
+    float2* tile = tile_all[warp];
     const int ch = blockIdx.y;
-    const int k0 = k_first + (blockIdx.x * 4 + warp) * 32;              // first chunk of this warp
+    const int k0 = k_first + (blockIdx.x * 4 + warp) * 32;    // first chunk of this warp; [k_first, k_end) is the launcher's slice of the chunk range
     if (k0 >= k_end) return;
     const float2* x = in + (long)ch * in_stride;
     float2* y = out + (long)ch * out_stride;
@@ -132,70 +156,28 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
     }
     const int rows = min(32, k_end - k0);
     const int max_len = min(chunk, n - k0 * chunk);          // the first chunk of the warp is never the short one
-    const int last_len = min(chunk, n - (k0 + rows - 1) * chunk);       // only the last row can be shorter (the channel's last chunk)
-    // a copy / store instruction moves two rows: lanes 0..15 one row, lanes 16..31 the next
-    const int half = lane >> 4, col = lane & 15;
-    const float2* xw = x + (long)(k0 + half) * chunk + col;
-    float2* yw = y + (long)(k0 + half) * chunk + col;
-    const long step2 = 2L * chunk;
-    auto issue = [&](int t0, float2* tile) {
-        const float2* src = xw + t0;
-        float2* dst = tile + half * SH_WP + col;
-        if (rows == 32 && t0 + SH_W <= last_len) {
-#pragma unroll 4
-            for (int r = 0; r < 32; r += 2, src += step2, dst += 2 * SH_WP) cp_async8(dst, src);
-        } else {
-            for (int r = half; r < rows; r += 2, src += step2, dst += 2 * SH_WP)
-                if (t0 + col < (r == rows - 1 ? last_len : max_len)) cp_async8(dst, src);
-        }
-    };
-    issue(0, buf);
-    cp_async_commit();
-    for (int t0 = 0, it = 0; t0 < max_len; t0 += SH_W, it++) {
-        float2* tile = buf + (it & 1) * TILE;
-        if (t0 + SH_W < max_len) issue(t0 + SH_W, buf + ((it + 1) & 1) * TILE);
-        cp_async_commit();
-        cp_async_wait<1>();                                             // this step's tile has landed (the one just issued may still be in flight)
+    for (int t0 = 0; t0 < max_len; t0 += SH_TILE) {
+        // coalesced load: row r = chunk k0+r, 32 consecutive samples starting at t0
+        tile_load_rows(tile, x, rows, k0, chunk, n, t0, lane, SH_PITCH);
         __syncwarp();
         if (live) {
-            float2* row = tile + lane * SH_WP;
-            const int steps = min(SH_W, my_len - t0);
-            if (steps == SH_W) {
-                float2 v[SH_W];
-#pragma unroll
-                for (int j = 0; j < SH_W; j++) v[j] = row[j];
-#pragma unroll
-                for (int j = 0; j < SH_W; j++) {
-                    v[j] = make_float2(__fsub_rn(__fmul_rn(c, v[j].x), __fmul_rn(s, v[j].y)), __fadd_rn(__fmul_rn(s, v[j].x), __fmul_rn(c, v[j].y)));
-                    const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
-                    const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
-                    c = cn; s = sn;
-                }
-#pragma unroll
-                for (int j = 0; j < SH_W; j++) row[j] = v[j];
-            } else {
-                for (int j = 0; j < steps; j++) {
-                    const float2 v = row[j];
-                    row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
-                    const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
-                    const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
-                    c = cn; s = sn;
-                }
+            float2* row = tile + lane * SH_PITCH;
+            const int steps = min(SH_TILE, my_len - t0);
+            for (int j = 0; j < steps; j++) {
+                const float2 v = row[j];
+                row[j] = make_float2(__fsub_rn(__fmul_rn(c, v.x), __fmul_rn(s, v.y)), __fadd_rn(__fmul_rn(s, v.x), __fmul_rn(c, v.y)));
+                const float cn = __fsub_rn(__fmul_rn(c, cosd), __fmul_rn(s, sind));
+                const float sn = __fadd_rn(__fmul_rn(s, cosd), __fmul_rn(c, sind));
+                c = cn; s = sn;
             }
         }
         __syncwarp();
-        {
-            float2* dst = yw + t0;
-            const float2* src = tile + half * SH_WP + col;
-            if (rows == 32 && t0 + SH_W <= last_len) {
-#pragma unroll 4
-                for (int r = 0; r < 32; r += 2, dst += step2, src += 2 * SH_WP) *dst = *src;
-            } else {
-                for (int r = half; r < rows; r += 2, dst += step2, src += 2 * SH_WP)
-                    if (t0 + col < (r == rows - 1 ? last_len : max_len)) *dst = *src;
-            }
+        for (int r = 0; r < rows; r++) {
+            const long pos = (long)(k0 + r) * chunk + t0 + lane;
+            const int len_r = min(chunk, n - (k0 + r) * chunk);
+            if (t0 + lane < len_r) y[pos] = tile[r * SH_PITCH + lane];
         }
-        __syncwarp();                                                   // the tile is free again for the copy issued two steps from now
+        __syncwarp();
     }
 }
 
@@ -209,12 +191,14 @@ __global__ void __launch_bounds__(32)
 addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                            int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
 {
-    const int c = blockIdx.x;
-    if (c >= channels) return;
-    const float inc = params[c].inc;
+    const int c0 = blockIdx.x * CHAIN_CPW;
+    if (c0 >= channels) return;
+    float inc1[CHAIN_CPW], inc[CHAIN_CPW];
+#pragma unroll
+    for (int i = 0; i < CHAIN_CPW; i++) { inc1[i] = params[min(c0 + i, channels - 1)].inc; inc[i] = __fmul_rn((float)chunk, inc1[i]); }
     // starting_phase += input_size * d->phase_increment  (:428)
-    chain_walk(phase_io, chunk_phase + (long)c * nchunks, c, n, chunk, nchunks, __fmul_rn((float)chunk, inc), tables,
-               [inc](float ph, int len) { return wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc))); });
+    chain_walk(phase_io, chunk_phase, nchunks, c0, channels, n, chunk, nchunks, inc, tables,
+               [&inc1](int i, float ph, int len) { return wrap_pm_pi(__fadd_rn(ph, __fmul_rn((float)len, inc1[i]))); });
 }
 
 __global__ void __launch_bounds__(128)
@@ -472,7 +456,7 @@ int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, 
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+    shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
                                                                chain_tables(d_scratch, scratch_bytes, channels, nchunks), 0, nchunks);
     CSDRB_CUDA(cudaGetLastError());
     int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
@@ -523,7 +507,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     if (slices > max_slices) slices = max_slices;
     if (slices > kSideSlices) slices = kSideSlices;
     if (slices < 2) {
-        shift_phase_chain_kernel<<<channels, 32, 0, st>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, 0, nchunks);
+        shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, 0, nchunks);
         CSDRB_CUDA(cudaGetLastError());
         shift_bank_kernel<<<dim3((nchunks + 127) / 128, channels), 128, smem, st>>>(d_in, in_stride, d_out, out_stride, prm, chunk_phase, n, chunk, nchunks, 0, nchunks);
         CSDRB_CUDA(cudaGetLastError());
@@ -540,7 +524,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
         const int k_first = i * per;
         if (k_first >= nchunks) break;
         const int k_end = k_first + per < nchunks ? k_first + per : nchunks;
-        shift_phase_chain_kernel<<<channels, 32, 0, ss->stream>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, k_first, k_end - k_first);
+        shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, ss->stream>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, k_first, k_end - k_first);
         CSDRB_CUDA(cudaGetLastError());
         CSDRB_CUDA(cudaEventRecord(ss->slice[i], ss->stream));
         CSDRB_CUDA(cudaStreamWaitEvent(st, ss->slice[i], 0));
@@ -561,7 +545,7 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addfast bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
     const AddFastParams* params = reinterpret_cast<const AddFastParams*>(d_params);
-    addfast_phase_chain_kernel<<<channels, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
+    addfast_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);

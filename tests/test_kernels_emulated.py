@@ -530,12 +530,13 @@ def test_k9_golden_and_dropin_kernel(fft, oracle):
     assert rel_rms(out, want) < 2e-6
 
 
-def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle):
-    """csdrb_fastddc_inv_plan_* (state inside, next run prepared ahead) against launch_fastddc_inv_bank run for run, bit for bit: three channels,
-    five runs of three blocks, a retune of channel 1 after the second run and a set_state round trip; the last outputs also against the oracle."""
+@pytest.mark.parametrize("nb,runs,shifts", [(3, 5, [0.123, -0.31, 0.02]), (100, 4, [0.123, -0.31, 0.02, 0.4, -0.05, 0.33])])
+def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle, nb, runs, shifts):
+    """csdrb_fastddc_inv_plan_* (state inside, next run prepared ahead) against launch_fastddc_inv_bank run for run, bit for bit: a retune of channel 1
+    after the second run and a set_state round trip; the never-retuned channels' last outputs also against the oracle.  The second case has 100 blocks per
+    run (the state chain runs on its wrap tables, four channels per warp with a ragged last warp; the plan builds the tables once, the bank call every time)."""
     from oracle.pyoracle import _CF, _p, WINDOWS
-    bw, dec, nb, runs = 0.05, 8, 3, 5
-    shifts = [0.123, -0.31, 0.02]
+    bw, dec = 0.05, 8
     chan_dt = np.dtype([("offsetbin", np.int32), ("sindelta", np.float32), ("cosdelta", np.float32), ("rate", np.float32)])
 
     def design(shift):
@@ -566,7 +567,7 @@ def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle):
                 taps[1] = tf1; chan[1] = row1[0]
                 one = Z(1, chan_dt); one[:] = row1
                 assert fft.emul_fastddc_inv_plan_set_channel(plan, 1, P(one)) == 0
-            if r == 3:                                                                            # state out and back in: drops the look-ahead, changes nothing
+            if r == runs - 2:                                                                     # state out and back in: drops the look-ahead, changes nothing
                 hr = Z(nch, np.int32); hp = Z(nch, np.float32)
                 assert fft.emul_fastddc_inv_plan_get_state(plan, P(hr), P(hp)) == 0
                 assert np.array_equal(hr, remain) and np.array_equal(hp.view(np.uint32), phase.view(np.uint32))
@@ -584,9 +585,10 @@ def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle):
         assert np.array_equal(hr, remain) and np.array_equal(hp.view(np.uint32), phase.view(np.uint32))
     finally:
         fft.emul_fastddc_inv_plan_destroy(plan)
-    # channel 0 was never retuned: its stream over all runs is the oracle's
-    ref0 = oracle.fastddc_inv(list(spectra), bw, dec, shifts[0])
-    assert rel_rms(got[0, :gt[0]], ref0[-gt[0]:]) < 5e-6
+    # the channels that were never retuned: their stream over all runs is the oracle's
+    for c in [c for c in range(nch) if c != 1]:
+        ref = oracle.fastddc_inv(list(spectra), bw, dec, shifts[c])
+        assert rel_rms(got[c, :gt[c]], ref[-gt[c]:]) < 5e-6, c
 
 
 @pytest.mark.parametrize("bw,dec,shift", [(0.05, 8, 0.123), (0.05, 3, -0.2), (0.01, 6, 0.25), (0.05, 4, 0.2), (0.02, 4, 0.05), (0.05, 16, -0.3), (0.05, 32, 0.4)])
