@@ -61,28 +61,55 @@ ddc_wrap_tables_kernel(const float3* __restrict__ params, int chunk, WrapTable* 
     if (c < channels && threadIdx.x == 0) wrap_table_build(__fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk), tables + c);
 }
 
+// One warp walks DDC_CHAIN_CPW channels (1: more than one per warp does not interleave -- the wrap's branches and votes keep the chains in program order;
+// measured on the fastddc and shift chains, r02 call 19).
+constexpr int DDC_CHAIN_CPW = 1;
+
 __global__ void __launch_bounds__(32)
 ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                        int channels, int nchunks, int chunk, int next_chunk, const WrapTable* __restrict__ tables)
 {
-    const int c = blockIdx.x, lane = threadIdx.x;
-    if (c >= channels) return;
-    const float inc = __fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk);
-    const WrapLanes w = wrap_lanes_load(tables + c, lane);
-    float ph = phase_io[c], keep = ph, mine = 0.f;
-    __syncwarp();                                      // every lane has read the carried phase before lane 0 overwrites it
-    float* dst = chunk_phase + (long)c * nchunks;
+    const int c0 = blockIdx.x * DDC_CHAIN_CPW, lane = threadIdx.x;
+    if (c0 >= channels) return;
+    const int nc = min(DDC_CHAIN_CPW, channels - c0);
+    float inc[DDC_CHAIN_CPW], ph[DDC_CHAIN_CPW], keep[DDC_CHAIN_CPW], mine[DDC_CHAIN_CPW];
+    WrapLanes w[DDC_CHAIN_CPW];
+#pragma unroll
+    for (int i = 0; i < DDC_CHAIN_CPW; i++) {
+        const int c = min(c0 + i, channels - 1);                        // slots past the bank shadow its last channel (they compute, they do not store)
+        inc[i] = __fmul_rn(__fmul_rn(params[c].z, 3.14159265358979323846f), (float)chunk);
+        w[i] = wrap_lanes_load(tables + c, lane);
+        ph[i] = phase_io[c]; keep[i] = ph[i]; mine[i] = 0.f;
+    }
+    __syncwarp();                                      // every lane has read the carried phases before lane 0 overwrites them
     for (int k = 0; k < nchunks; k++) {
-        if ((k & 31) == lane) mine = ph;
-        if ((k & 31) == 31 || k == nchunks - 1) { if ((k & ~31) + lane <= k) dst[(k & ~31) + lane] = mine; }     // one coalesced store per 32 steps
-        if (k == next_chunk) keep = ph;
-        ph = wrap_after_add_warp(__fadd_rn(ph, inc), w);
+        if ((k & 31) == lane) {
+#pragma unroll
+            for (int i = 0; i < DDC_CHAIN_CPW; i++) mine[i] = ph[i];
+        }
+        if (((k & 31) == 31 || k == nchunks - 1) && (k & ~31) + lane <= k) {                             // one coalesced store per channel and 32 steps
+#pragma unroll
+            for (int i = 0; i < DDC_CHAIN_CPW; i++) if (i < nc) chunk_phase[(long)(c0 + i) * nchunks + (k & ~31) + lane] = mine[i];
+        }
+        if (k == next_chunk) {
+#pragma unroll
+            for (int i = 0; i < DDC_CHAIN_CPW; i++) keep[i] = ph[i];
+        }
+#pragma unroll
+        for (int i = 0; i < DDC_CHAIN_CPW; i++) ph[i] = wrap_after_add_warp(__fadd_rn(ph[i], inc[i]), w[i]);
     }
     if (next_chunk >= nchunks) {                       // the next block starts beyond the chunks this block touched
-        for (int k = nchunks; k < next_chunk; k++) ph = wrap_after_add_warp(__fadd_rn(ph, inc), w);
-        keep = ph;
+        for (int k = nchunks; k < next_chunk; k++) {
+#pragma unroll
+            for (int i = 0; i < DDC_CHAIN_CPW; i++) ph[i] = wrap_after_add_warp(__fadd_rn(ph[i], inc[i]), w[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < DDC_CHAIN_CPW; i++) keep[i] = ph[i];
     }
-    if (lane == 0) phase_io[c] = keep;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < DDC_CHAIN_CPW; i++) if (i < nc) phase_io[c0 + i] = keep[i];
+    }
 }
 
 // retune support: close the current chunk `n` samples in (every channel advances by n samples at its present rate), see csdrb_ddc_bank_process
@@ -482,7 +509,7 @@ int launch_ddc_prepass(int input_size, int channels, const float* d_params, floa
     }
     const long advance = (long)n_out * decimation;                      // the next block starts here (the caller re-presents the tail)
     const int next_chunk = (int)((offset + advance) / chunk);
-    ddc_phase_chain_kernel<<<channels, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
+    ddc_phase_chain_kernel<<<(channels + DDC_CHAIN_CPW - 1) / DDC_CHAIN_CPW, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
                                                              static_cast<const WrapTable*>(d_tables));
     CSDRB_CUDA(cudaGetLastError());
     const long total = (long)channels * nchunks;

@@ -304,10 +304,11 @@ struct DdcChan { int offsetbin; float sindelta, cosdelta, rate; };     // per ch
 #define PI_F 3.14159265358979323846f
 __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph); }
 
-// Walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158).  A chain is sequential and a step is ~400 cycles of dependent
-// latency (add, two votes, shuffles, a double add, the wrap loop's branches), so one WARP carries CPW channels side by side: their steps interleave in the
-// pipeline and the walk costs the same 0.2 us per block for four channels as for one (the consumers' look-ahead window is the IFFT step; r02 timelines).
-constexpr int CHAIN_CPW = 4;
+// Walk the block-to-block state of decimating_shift_addition_cc (libcsdr_gpl.c:154-158), one WARP per CHAIN_CPW channels.  A chain is sequential and a step
+// is ~400 cycles of dependent latency; letting one warp carry four channels "side by side" did NOT interleave them -- the wrap's warp-uniform branches and
+// votes keep the steps of different chains in program order, so four chains per warp ran four times as long on a quarter of the SMs (592 blocks: 211 us
+// against 130 us; r02 call 19).  The code stays generic, the constant is 1.
+constexpr int CHAIN_CPW = 1;
 
 __global__ void __launch_bounds__(32)
 fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,

@@ -40,9 +40,10 @@ __device__ __forceinline__ float advance_phase(float ph, float rate2, int n)
 constexpr int kChainTableMin = 96;
 
 // chains of nchunks starting phases, one WARP per CHAIN_CPW channels: steps with the full-chunk increment go through the register-resident wrap tables
-// (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases per channel are stored at a time.  A step is a few hundred cycles of
-// dependent latency, so the channels of a warp walk side by side at the price of one.  `step(slot, ph, len)` is the direct form for slot's channel.
-constexpr int CHAIN_CPW = 4;
+// (phase_table.cuh), the last, shorter chunk has its own increment (direct); 32 phases per channel are stored at a time.  `step(slot, ph, len)` is the direct
+// form for slot's channel.  (Four channels per warp were measured: the wrap's branches and votes keep the chains in program order, 526 us per slice of 782
+// chunks against 115 us with a warp per channel -- r02 call 19; the constant stays 1.)
+constexpr int CHAIN_CPW = 1;
 
 template <class Step>
 __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, long dst_stride, int c0, int channels, int n, int chunk, int nchunks,
