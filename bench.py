@@ -490,9 +490,9 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
 
     per_blk = ddc.post_input_size // ddc.post_decimation
     flops3 = nblocks * (5.0 * ddc.fft_size * 14 + c3 * (8.0 * ddc.fft_size + 5.0 * ddc.fft_inv_size * 9))
-    out.append(leg("cfg3_fastddc", step3, 3, nsamp, nsamp * 8.0 + c3 * nblocks * per_blk * 8.0, flops3, "hbm",
+    out.append(leg("cfg3_fastddc", step3, 3, nsamp, nsamp * 8.0 + c3 * nblocks * per_blk * 8.0, flops3, "fp32",
                    "forward 16384-pt FFT + inverse bank (csdrb_fastddc_inv_plan_run: fold + IFFT, the post-shift state chain of the next step prepared meanwhile) per step; algorithmic bytes = wideband samples in + channel outputs (SURVEY 8(d): 16 B/sample at 64 ch); "
-                   "the path is bound on chip (fold = 8*N flop per channel and block), fp32_tflops says how hard",
+                   "the dominant kernel is the fold (8*N flop per channel and block, FFMA2 on the FMA pipe), hence the FP32 roofline; flops = 5*N*log2(N) forward + per channel 8*N fold + 5*M*log2(M) inverse",
                    {"workload": "fastddc overlap-save: 16384-pt FFT, 64 output channels from one 61.44 Msps wideband stream (BASELINE configs[2])", "channels_per_gpu": c3,
                     "channels_total": c3 * world, "blocks_per_step": nblocks, "block_samples": ddc.input_size, "fft_size": ddc.fft_size, "fft_inv_size": ddc.fft_inv_size,
                     "collective": "ncclBroadcast of the time-domain block per step; every rank runs the forward FFT for its own channel slice" if world > 1 else "none (1 GPU)",
@@ -523,11 +523,11 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
             check(L.csdrb_bandpass_fir_fft_bank_cc(x5.data_ptr(), n5, y5.data_ptr(), n5, C5, NF, isz, nb, tf.data_ptr(), 0, tail.data_ptr(), cur_stream()),
                   "csdrb_bandpass_fir_fft_bank_cc")
 
-        e = leg(f"cfg5_olafir_L{Lsz}", step5, 3, C5 * n5, C5 * n5 * 16.0, C5 * nb * (2 * 5.0 * NF * 12 + 8.0 * NF), "hbm",
-                "16 algorithmic B/sample (8 in + 8 out); ~250 flop/sample keeps it on the FP32 side of the ridge",
+        e = leg(f"cfg5_olafir_L{Lsz}", step5, 3, C5 * n5, C5 * n5 * 16.0, C5 * nb * (2 * 5.0 * NF * 12 + 8.0 * NF), "fp32",
+                "16 algorithmic B/sample (8 in + 8 out) and ~250 flop/sample (two 4096-point transforms per 2098 new samples): the FP32 roof is the lower one (frac_of_hbm beside it)",
                 {"workload": "bandpass_fir_fft_cc overlap-add, 4096-pt, 512 channels (BASELINE configs[4])", "channels_per_gpu": C5, "channels_total": C5 * world,
                  "samples_per_channel": n5, "fft_size": NF, "input_size": isz, "taps": T5, "scaling": "strong" if world > 1 else "n/a"}, total_units_factor=world)
-        sweep.append({"block_samples": Lsz, "value": e["value"], "kernel_ms": e["kernel_ms"], "achieved_gbs": e["roofline"]["achieved"], "frac": e["roofline"]["frac"],
+        sweep.append({"block_samples": Lsz, "value": e["value"], "kernel_ms": e["kernel_ms"], "algorithmic_gbs": e["roofline"]["algorithmic_gbs"], "frac_of_hbm": e["roofline"]["frac_of_hbm"], "fp32_tflops": e["roofline"]["achieved"], "frac": e["roofline"]["frac"],
                       "sm_mhz": e["clocks"].get("sm_mhz")})
         best = e
         del x5, y5, tail
