@@ -353,7 +353,7 @@ def run_b200(args):
 
     # ---- BASELINE configs 3, 4, 5 ---------------------------------------------------------------------------
     if not args.no_extra:
-        extra += other_configs(torch, dist, csdr_b200, L, dev, world, rank, local, leg, check, cur_stream, fp, args)
+        extra += other_configs(torch, dist, csdr_b200, L, dev, world, rank, local, leg, check, cur_stream, fp, args, sustained=sustained, barrier=barrier)
 
     # ---- CPU baseline beside it (rank 0, N=1 only, bounded) --------------------------------------
     cpu = None
@@ -397,7 +397,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_stream, fp, args):
+def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_stream, fp, args, sustained=None, barrier=None):
     """BASELINE configs 3, 4, 5 as `extra` entries.  Shared-input banks (3, 4) move the wideband block with an NCCL broadcast per step at N > 1."""
     out = []
     vp = C.c_void_p
@@ -461,6 +461,20 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
                    {"workload": "1024-ch-class shift+fir_decimate_cc+fmdemod NFM bank, decim=50, 801 taps, 128 ch/GPU (BASELINE configs[3])", "channels_per_gpu": Cg,
                     "channels_total": Cg * world, "block_samples": N, "nco_chunk": 1024, "collective": "ncclBroadcast of the 16 MiB IQ block per step" if world > 1 else "none (1 GPU)",
                     "scaling": "weak"}))
+    if world > 1:
+        # the overlap in numbers (no nsys in this image): the broadcast alone, the kernel alone (every rank on its own copy of the block), and the leg above
+        # where block k+1 travels while block k is processed -- overlapped means step ~ max(broadcast, kernel), not their sum
+        def only_bcast(_k):
+            dist.broadcast(bc.bufs[_k & 1], src=0)
+
+        def only_kernel(_k):
+            check(L.csdrb_ddc_bank_process(bank.h, bc.bufs[0].data_ptr(), N, fo.data_ptr(), fo.stride(0), cur_stream()), "csdrb_ddc_bank_process")
+        torch.cuda.synchronize(); barrier()
+        b_ms, _ = sustained(only_bcast, min_seconds=0.3)
+        k_ms, _ = sustained(only_kernel, min_seconds=0.3)
+        out[-1]["overlap"] = {"broadcast_alone_ms": b_ms, "kernel_alone_ms": k_ms, "step_ms": out[-1]["kernel_ms"], "sum_ms": b_ms + k_ms,
+                              "broadcast_gbs": N * 8.0 / (b_ms * 1e-3) / 1e9,
+                              "note": "step_ms close to max(broadcast, kernel) = the broadcast of block k+1 runs under the kernel of block k"}
     torch.cuda.synchronize()
     bank.close()
     del wide, fo, bc

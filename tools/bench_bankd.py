@@ -57,7 +57,18 @@ def run_reference(k):
 
 t_b = run_bankd()
 print(f"csdr-bankd{' --devices ' + devices if devices else ''}: {channels} channels, {n / 1e6:.1f} M wideband samples in {t_b:.2f} s = {n / t_b / 1e6:.1f} Msps wideband "
-      f"= {n / t_b / FS:.1f} x real time at 2.4 Msps ({channels * n / t_b / 1e6:.0f} M channel-samples/s)", flush=True)
+      f"= {n / t_b / FS:.1f} x real time at 2.4 Msps ({channels * n / t_b / 1e6:.0f} M channel-samples/s), process start and CUDA context included", flush=True)
+# the same with a quarter of the signal: the difference is the streaming rate without the start-up
+iq_full = iq
+iq = tmp / "iq_quarter.u8"
+n_q = (n // 4) & ~1
+with open(iq_full, "rb") as f, open(iq, "wb") as g:
+    g.write(f.read(2 * n_q))
+t_q = run_bankd()
+iq = iq_full
+rate = (n - n_q) / max(t_b - t_q, 1e-9)
+print(f"csdr-bankd streaming rate (start-up taken out: {n / 1e6:.0f} M vs {n_q / 1e6:.0f} M samples, {t_b:.2f} s vs {t_q:.2f} s): {rate / 1e6:.0f} Msps wideband = {rate / FS:.0f} x real time, "
+      f"{channels * rate / 1e6:.0f} M channel-samples/s", flush=True)
 if REF.exists():
     cores = os.cpu_count() or 1
     for k in (1, 4, min(16, channels)):
