@@ -556,6 +556,8 @@ def test_k8_fastddc_inverse_plan_equals_the_stateless_bank(fft, oracle, nb, runs
     spectra = np.stack(oracle.fastddc_fwd(x, g)).astype(np.complex64)
     width = nb * (g.post_input_size // g.post_decimation + 1) + 2
     plan = C.c_void_p()
+    # a geometry the fold path does not cover is refused with a message (the stateless call handles it)
+    assert fft.emul_fastddc_inv_plan_create(C.addressof(plan), P(chan), nch, nb, 256, 32, 8, 4, 28, 1) < 0 and b"not covered" in fft.emul_last_error() and not plan.value
     assert fft.emul_fastddc_inv_plan_create(C.addressof(plan), P(chan), nch, nb, g.fft_size, g.fft_inv_size, g.pre_decimation, g.scrap, g.post_input_size, g.post_decimation) == 0, fft.emul_last_error()
     remain = Z(nch, np.int32); phase = Z(nch, np.float32)
     sb = fft.emul_fastddc_inv_scratch_bytes(nch, nb); scratch = Z(sb + 16, np.uint8)
