@@ -168,7 +168,8 @@ __device__ __forceinline__ WrapLanes wrap_lanes_load(const WrapTable* __restrict
     return w;
 }
 
-__device__ __forceinline__ float wrap_after_add_warp(float x, const WrapLanes& w)
+// Generic form: any table size, values outside the table's window (falls back to the exact loop fast-forward).
+static __device__ __noinline__ float wrap_after_add_warp_generic(float x, const WrapLanes& w)
 {
     const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;
     float a = fabsf(x);
@@ -185,6 +186,26 @@ __device__ __forceinline__ float wrap_after_add_warp(float x, const WrapLanes& w
     }
     while (a > PI_F32) a = __fsub_rn(a, TWO_PI_F32);
     return (__float_as_uint(x) >> 31) ? -a : a;
+}
+
+// The chain kernels' step.  A chain is pure latency, and the r02 SASS of the loop had seven branches per step (>= 16? in the window? more than 32 pieces?
+// the wrap loop's three iterations ...) at ~0.2 us per step; here the common case -- a table of at most 32 pieces, the value inside its window or already
+// below 16 -- is straight-line code: vote, popc, shuffle, one double subtraction, three predicated subtractions (below 16 at most three are left:
+// 16 - 3*2pi < pi).  Same operations in the same order as the generic form, which takes everything else.
+__device__ __forceinline__ float wrap_after_add_warp(float x, const WrapLanes& w)
+{
+    const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;
+    const float a = fabsf(x);
+    const bool below = a < 16.f;
+    const bool in = !below && w.n > 0 && w.n <= 32 && a >= w.lo && a <= w.hi;
+    if (!(below || in)) return wrap_after_add_warp_generic(x, w);       // warp-uniform (same x, same table in all lanes)
+    const int idx = __popc(__ballot_sync(0xffffffffu, a >= w.thr0)) - 1;
+    const double K = __shfl_sync(0xffffffffu, w.K0, idx & 31);
+    float r = in ? (float)((double)a - K) : a;                          // exact; the float the loop would hold when it first drops below 16
+    r = r > PI_F32 ? __fsub_rn(r, TWO_PI_F32) : r;
+    r = r > PI_F32 ? __fsub_rn(r, TWO_PI_F32) : r;
+    r = r > PI_F32 ? __fsub_rn(r, TWO_PI_F32) : r;
+    return (__float_as_uint(x) >> 31) ? -r : r;
 }
 
 #endif  // device (or emulated device) code

@@ -233,6 +233,9 @@ extern "C" int cuda_emul_take_launch_error(void);     // cuda_emul_runtime.cpp a
 #define CSDRB_DYN_SMEM(name) unsigned char* name = ::cuda_emul::dyn_smem()
 #define __launch_bounds__(...)
 #define __grid_constant__
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
 #undef __global__
 #define __global__
 #undef __shared__
