@@ -189,18 +189,21 @@ static __device__ __noinline__ float wrap_after_add_warp_generic(float x, const 
 }
 
 // The chain kernels' step.  A chain is pure latency, and the r02 SASS of the loop had seven branches per step (>= 16? in the window? more than 32 pieces?
-// the wrap loop's three iterations ...) at ~0.2 us per step; here the common case -- a table of at most 32 pieces, the value inside its window or already
-// below 16 -- is straight-line code: vote, popc, shuffle, one double subtraction, three predicated subtractions (below 16 at most three are left:
+// the wrap loop's three iterations ...) at ~0.2 us per step; here the common case -- the value inside the table's window or already below 16 -- is
+// straight-line code: two votes, popc, shuffles, one double subtraction, three predicated subtractions (below 16 at most three are left:
 // 16 - 3*2pi < pi).  Same operations in the same order as the generic form, which takes everything else.
 __device__ __forceinline__ float wrap_after_add_warp(float x, const WrapLanes& w)
 {
     const float PI_F32 = 3.14159265358979323846f, TWO_PI_F32 = 6.28318530717958647692f;
     const float a = fabsf(x);
     const bool below = a < 16.f;
-    const bool in = !below && w.n > 0 && w.n <= 32 && a >= w.lo && a <= w.hi;
-    if (!(below || in)) return wrap_after_add_warp_generic(x, w);       // warp-uniform (same x, same table in all lanes)
+    const bool in = !below && w.n > 0 && a >= w.lo && a <= w.hi;
+    if (!(below || in)) return wrap_after_add_warp_generic(x, w);       // outside the table's window: warp-uniform (same x, same table in all lanes), rare
+    // pieces 0..31 sit in thr0/K0, pieces 32.. in thr1/K1 (+inf beyond the table, so `more` is 0 for a table of at most 32 pieces): both look-ups, one select
     const int idx = __popc(__ballot_sync(0xffffffffu, a >= w.thr0)) - 1;
-    const double K = __shfl_sync(0xffffffffu, w.K0, idx & 31);
+    const int more = __popc(__ballot_sync(0xffffffffu, a >= w.thr1));
+    const double K0 = __shfl_sync(0xffffffffu, w.K0, idx & 31), K1 = __shfl_sync(0xffffffffu, w.K1, (more - 1) & 31);
+    const double K = more > 0 ? K1 : K0;
     float r = in ? (float)((double)a - K) : a;                          // exact; the float the loop would hold when it first drops below 16
     r = r > PI_F32 ? __fsub_rn(r, TWO_PI_F32) : r;
     r = r > PI_F32 ? __fsub_rn(r, TWO_PI_F32) : r;
