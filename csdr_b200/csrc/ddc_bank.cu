@@ -64,12 +64,13 @@ ddc_wrap_tables_kernel(const float3* __restrict__ params, int chunk, WrapTable* 
 // One warp walks DDC_CHAIN_CPW channels (1: more than one per warp does not interleave -- the wrap's branches and votes keep the chains in program order;
 // measured on the fastddc and shift chains, r02 call 19).
 constexpr int DDC_CHAIN_CPW = 1;
+constexpr int DDC_CHAIN_WARPS = 8;                 // chains per CTA: the pre-pass of block k+1 runs next to block k's main kernel; eight warps per CTA keep the guests on few SMs
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * DDC_CHAIN_WARPS)
 ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                        int channels, int nchunks, int chunk, int next_chunk, const WrapTable* __restrict__ tables)
 {
-    const int c0 = blockIdx.x * DDC_CHAIN_CPW, lane = threadIdx.x;
+    const int c0 = (blockIdx.x * DDC_CHAIN_WARPS + (threadIdx.x >> 5)) * DDC_CHAIN_CPW, lane = threadIdx.x & 31;
     if (c0 >= channels) return;
     const int nc = min(DDC_CHAIN_CPW, channels - c0);
     float inc[DDC_CHAIN_CPW], ph[DDC_CHAIN_CPW], keep[DDC_CHAIN_CPW], mine[DDC_CHAIN_CPW];
@@ -509,7 +510,7 @@ int launch_ddc_prepass(int input_size, int channels, const float* d_params, floa
     }
     const long advance = (long)n_out * decimation;                      // the next block starts here (the caller re-presents the tail)
     const int next_chunk = (int)((offset + advance) / chunk);
-    ddc_phase_chain_kernel<<<(channels + DDC_CHAIN_CPW - 1) / DDC_CHAIN_CPW, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
+    ddc_phase_chain_kernel<<<(channels + DDC_CHAIN_CPW * DDC_CHAIN_WARPS - 1) / (DDC_CHAIN_CPW * DDC_CHAIN_WARPS), 32 * DDC_CHAIN_WARPS, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, nchunks, chunk, next_chunk,
                                                              static_cast<const WrapTable*>(d_tables));
     CSDRB_CUDA(cudaGetLastError());
     const long total = (long)channels * nchunks;

@@ -272,7 +272,7 @@ bool fastddc_inv_fold_ok(int fft_size, int fft_inv_size)
 int launch_fastddc_inv_prepare(const void* d_chan, int channels, int nblocks, int post_input_size, int post_decimation, int* d_remain_io, float* d_phase_io,
                                int* d_out_total, const InvPrep& p, cudaStream_t s, cudaEvent_t before_phasors = nullptr, bool build_tables = true)
 {
-    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
+    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, s>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, p.blk_remain, p.blk_phase,
                                                        p.blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, p.tables, build_tables ? 1 : 0);
     CSDRB_CUDA(cudaGetLastError());
     // the chain (votes, shuffles, a double add per step) shares an SM with a running fold at no cost to either; the phasor walk is FMUL/FADD and does not --
@@ -385,7 +385,7 @@ int launch_fastddc_inv_bank(const float2* d_spectra, int nblocks, const float2* 
         CSDRB_CUDA(cudaFreeAsync(folded, st));
         return 4;
     }
-    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
+    fastddc_state_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, st>>>(static_cast<const DdcChan*>(d_chan), d_remain_io, d_phase_io, blk_remain, blk_phase,
                                                                     blk_offset, d_out_total, channels, nblocks, post_input_size, post_decimation, tables, 1);
     CSDRB_CUDA(cudaGetLastError());
     if (fft_inv_size <= 1024 && fft_inv_size >= 8 && (fft_size / fft_inv_size) % 2 == 0) {

@@ -310,13 +310,17 @@ __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph
 // against 130 us; r02 call 19).  The code stays generic, the constant is 1.
 constexpr int CHAIN_CPW = 1;
 
-__global__ void __launch_bounds__(32)
+// CHAIN_WARPS chains per CTA: the chains run NEXT TO other kernels (the fold, the IFFT step), and a guest warp slows its host SM's CTAs down -- eight warps per CTA put the 64
+// chains of config 3 on 8 SMs instead of 64.
+constexpr int CHAIN_WARPS = 8;
+
+__global__ void __launch_bounds__(32 * CHAIN_WARPS)
 fastddc_state_chain_kernel(const DdcChan* __restrict__ chan, int* __restrict__ remain_io, float* __restrict__ phase_io,
                            int* __restrict__ blk_remain, float* __restrict__ blk_phase, int* __restrict__ blk_offset,
                            int* __restrict__ out_total, int channels, int nblocks, int post_input_size, int post_decimation,
                            WrapTable* __restrict__ tables, int build_tables)
 {
-    const int c0 = blockIdx.x * CHAIN_CPW, lane = threadIdx.x;
+    const int c0 = (blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5)) * CHAIN_CPW, lane = threadIdx.x & 31;
     if (c0 >= channels) return;
     const int nc = min(CHAIN_CPW, channels - c0);
     int remain[CHAIN_CPW], off[CHAIN_CPW];

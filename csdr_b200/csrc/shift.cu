@@ -44,12 +44,13 @@ constexpr int kChainTableMin = 96;
 // form for slot's channel.  (Four channels per warp were measured: the wrap's branches and votes keep the chains in program order, 526 us per slice of 782
 // chunks against 115 us with a warp per channel -- r02 call 19; the constant stays 1.)
 constexpr int CHAIN_CPW = 1;
+constexpr int CHAIN_WARPS = 8;                    // chains per CTA: a chain slice runs next to the main kernel of the previous slice, eight warps per CTA keep the guests on few SMs
 
 template <class Step>
 __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, long dst_stride, int c0, int channels, int n, int chunk, int nchunks,
                                            const float (&inc_full)[CHAIN_CPW], WrapTable* __restrict__ tables, Step step, bool build_table = true)
 {
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const int nc = min(CHAIN_CPW, channels - c0);
     const bool tab = tables != nullptr;
     WrapLanes w[CHAIN_CPW];
@@ -94,11 +95,11 @@ __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* 
 
 // One slice of the chain: chunks k_first .. k_first + k_count - 1 of every channel (the launcher cuts a long chain into slices so that the main kernel can
 // start on slice 0 while slice 1 is still being walked); the carried phase in phase_io moves on slice by slice, the wrap table is built by the first one.
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * CHAIN_WARPS)
 shift_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                          int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables, int k_first, int k_count)
 {
-    const int c0 = blockIdx.x * CHAIN_CPW;
+    const int c0 = (blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5)) * CHAIN_CPW;
     if (c0 >= channels) return;
     const int count = min(k_count, nchunks - k_first);
     if (count <= 0) return;
@@ -188,11 +189,11 @@ shift_bank_kernel(const float2* __restrict__ in, long in_stride, float2* __restr
 // (channel, call) walking its own shared-memory row.  A call only touches input_size/4 groups: the n%4 tail is not written.
 struct AddFastParams { float dsin[4], dcos[4], inc; };                 // = shift_addfast_data_t (libcsdr.h:189-194)
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * CHAIN_WARPS)
 addfast_phase_chain_kernel(const AddFastParams* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,
                            int channels, int n, int chunk, int nchunks, WrapTable* __restrict__ tables)
 {
-    const int c0 = blockIdx.x * CHAIN_CPW;
+    const int c0 = (blockIdx.x * CHAIN_WARPS + (threadIdx.x >> 5)) * CHAIN_CPW;
     if (c0 >= channels) return;
     float inc1[CHAIN_CPW], inc[CHAIN_CPW];
 #pragma unroll
@@ -457,7 +458,7 @@ int launch_shift_unroll_bank(const float2* d_in, long in_stride, float2* d_out, 
     const int nchunks = (n + chunk - 1) / chunk;
     if (scratch_bytes < (size_t)channels * nchunks * sizeof(float) || !d_scratch) { set_error("shift_unroll bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
-    shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
+    shift_phase_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, st>>>(reinterpret_cast<const float3*>(d_params), d_phase_io, chunk_phase, channels, n, chunk, nchunks,
                                                                chain_tables(d_scratch, scratch_bytes, channels, nchunks), 0, nchunks);
     CSDRB_CUDA(cudaGetLastError());
     int gx = (n + 255) / 256; if (gx > 2048) gx = 2048;
@@ -508,7 +509,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     if (slices > max_slices) slices = max_slices;
     if (slices > kSideSlices) slices = kSideSlices;
     if (slices < 2) {
-        shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, 0, nchunks);
+        shift_phase_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, st>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, 0, nchunks);
         CSDRB_CUDA(cudaGetLastError());
         shift_bank_kernel<<<dim3((nchunks + 127) / 128, channels), 128, smem, st>>>(d_in, in_stride, d_out, out_stride, prm, chunk_phase, n, chunk, nchunks, 0, nchunks);
         CSDRB_CUDA(cudaGetLastError());
@@ -525,7 +526,7 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
         const int k_first = i * per;
         if (k_first >= nchunks) break;
         const int k_end = k_first + per < nchunks ? k_first + per : nchunks;
-        shift_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, ss->stream>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, k_first, k_end - k_first);
+        shift_phase_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, ss->stream>>>(prm, d_phase_io, chunk_phase, channels, n, chunk, nchunks, tables, k_first, k_end - k_first);
         CSDRB_CUDA(cudaGetLastError());
         CSDRB_CUDA(cudaEventRecord(ss->slice[i], ss->stream));
         CSDRB_CUDA(cudaStreamWaitEvent(st, ss->slice[i], 0));
@@ -546,7 +547,7 @@ int launch_shift_addfast_bank(const float2* d_in, long in_stride, float2* d_out,
     if (scratch_bytes < shift_bank_scratch_bytes(channels, n, chunk) || !d_scratch) { set_error("shift_addfast bank: scratch too small"); return -1; }
     float* chunk_phase = static_cast<float*>(d_scratch);
     const AddFastParams* params = reinterpret_cast<const AddFastParams*>(d_params);
-    addfast_phase_chain_kernel<<<(channels + CHAIN_CPW - 1) / CHAIN_CPW, 32, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
+    addfast_phase_chain_kernel<<<(channels + CHAIN_CPW * CHAIN_WARPS - 1) / (CHAIN_CPW * CHAIN_WARPS), 32 * CHAIN_WARPS, 0, st>>>(params, d_phase_io, chunk_phase, channels, n, chunk, nchunks, chain_tables(d_scratch, scratch_bytes, channels, nchunks));
     CSDRB_CUDA(cudaGetLastError());
     dim3 grid((nchunks + 127) / 128, channels);
     shift_addfast_bank_kernel<<<grid, 128, 0, st>>>(d_in, in_stride, d_out, out_stride, params, chunk_phase, n, chunk, nchunks);
