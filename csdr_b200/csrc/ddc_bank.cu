@@ -64,7 +64,8 @@ ddc_wrap_tables_kernel(const float3* __restrict__ params, int chunk, WrapTable* 
 // One warp walks DDC_CHAIN_CPW channels (1: more than one per warp does not interleave -- the wrap's branches and votes keep the chains in program order;
 // measured on the fastddc and shift chains, r02 call 19).
 constexpr int DDC_CHAIN_CPW = 1;
-constexpr int DDC_CHAIN_WARPS = 8;                 // chains per CTA: the pre-pass of block k+1 runs next to block k's main kernel; eight warps per CTA keep the guests on few SMs
+constexpr int DDC_CHAIN_WARPS = 1;                 // chains per CTA.  The pre-pass of block k+1 runs NEXT TO block k's main kernel, whose three CTAs leave ~10 K registers per SM: a one-warp
+                                                   // CTA slips in, an eight-warp CTA has to wait for an SM to drain and the pre-pass serialises behind the main kernel (0.88 instead of 0.64 ms per block)
 
 __global__ void __launch_bounds__(32 * DDC_CHAIN_WARPS)
 ddc_phase_chain_kernel(const float3* __restrict__ params, float* __restrict__ phase_io, float* __restrict__ chunk_phase,

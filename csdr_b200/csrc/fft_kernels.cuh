@@ -311,7 +311,8 @@ __device__ __forceinline__ float ddc_wrap(float ph) { return wrap_phase_pm_pi(ph
 constexpr int CHAIN_CPW = 1;
 
 // CHAIN_WARPS chains per CTA: the chains run NEXT TO other kernels (the fold, the IFFT step), and a guest warp slows its host SM's CTAs down -- eight warps per CTA put the 64
-// chains of config 3 on 8 SMs instead of 64.
+// chains of config 3 on 8 SMs instead of 64 (forward + plan loop at 592 blocks: 0.349 -> 0.331 ms; the fold's one CTA per SM leaves room for a 256-thread guest, which
+// the fused NFM bank's three CTAs per SM do not: its chain kernel keeps one warp per CTA).
 constexpr int CHAIN_WARPS = 8;
 
 __global__ void __launch_bounds__(32 * CHAIN_WARPS)

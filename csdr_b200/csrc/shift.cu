@@ -44,7 +44,7 @@ constexpr int kChainTableMin = 96;
 // form for slot's channel.  (Four channels per warp were measured: the wrap's branches and votes keep the chains in program order, 526 us per slice of 782
 // chunks against 115 us with a warp per channel -- r02 call 19; the constant stays 1.)
 constexpr int CHAIN_CPW = 1;
-constexpr int CHAIN_WARPS = 8;                    // chains per CTA: a chain slice runs next to the main kernel of the previous slice, eight warps per CTA keep the guests on few SMs
+constexpr int CHAIN_WARPS = 1;                    // chains per CTA: a chain slice runs next to the main kernel of the previous slice and must fit into what that leaves of an SM (see ddc_bank.cu)
 
 template <class Step>
 __device__ __forceinline__ void chain_walk(float* __restrict__ phase_io, float* __restrict__ dst, long dst_stride, int c0, int channels, int n, int chunk, int nchunks,
