@@ -293,17 +293,14 @@ int launch_fastddc_inv_apply(const float2* d_spectra, int nblocks, const float2*
     const size_t fsmem = sizeof(float2) * (size_t)FOLD_ST * 2 * (2 * FOLD_BT) * FOLD_R;
     static const bool wide_cta = getenv("CSDRB_FOLD_BT") && getenv("CSDRB_FOLD_BT")[0] == '4';     // A/B: 512-thread CTAs with 8 x 4 thread tiles
     static const bool x_first = getenv("CSDRB_FOLD_HFIRST") && getenv("CSDRB_FOLD_HFIRST")[0] == '0';   // A/B: the sample, not the tap pair, as first multiplicand
-    static bool attr_done = false;
-    if (!attr_done) {
-        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-        attr_done = true;
-    }
     const dim3 fgrid(fft_inv_size / FOLD_R, (channels + 2 * FOLD_CT - 1) / (2 * FOLD_CT), (nblocks + 2 * FOLD_BT - 1) / (2 * FOLD_BT));
     if (fgrid.y > 65535u || fgrid.z > 65535u) { set_error("fastddc_inv: bank too large for one call"); return -1; }
     const float inv_pre = 1.0f / (float)pre_decimation;
     const DdcChan* dc = static_cast<const DdcChan*>(d_chan);
+    // (the attribute belongs to the current device's context: set per call, not latched per process)
+    if (wide_cta) CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    else if (x_first) CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    else CSDRB_CUDA(cudaFuncSetAttribute(fastddc_fold_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     if (wide_cta) fastddc_fold_kernel<4, true><<<fgrid, 512, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
     else if (x_first) fastddc_fold_kernel<8, false><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
     else fastddc_fold_kernel<8, true><<<fgrid, 256, fsmem, st>>>(d_spectra, d_taps_fft, dc, folded, fft_size, fft_inv_size, nblocks, channels, inv_pre);
@@ -535,6 +532,8 @@ int fastddc_inv_plan_run(void* plan, const float2* d_spectra, const float2* d_ta
     auto* pl = static_cast<FastddcInvPlan*>(plan);
     if (!pl || !d_spectra || !d_taps_fft || !d_out || !d_out_total) { set_error("fastddc_inv_plan_run: null pointer"); return -1; }
     std::lock_guard<std::mutex> lk(pl->mu);
+    int dev_now = -1;
+    if (cudaGetDevice(&dev_now) != cudaSuccess || dev_now != pl->dev) { set_error("fastddc_inv_plan_run: the plan lives on device %d, the current device is %d", pl->dev, dev_now); return -1; }
     const int p = pl->cur;
     static const bool trace = getenv("CSDRB_INV_TRACE") && getenv("CSDRB_INV_TRACE")[0] == '1';      // tools only: timeline of this run, printed after a synchronize
     cudaEvent_t tev[5] = {};
