@@ -404,16 +404,11 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
 
     class Bcast:
         """double-buffered broadcast of a wideband block from rank 0: block k+1 travels on a side stream while block k is processed"""
-        def __init__(self, src, mode="overlap"):
+        def __init__(self, src):
             self.bufs = [src, torch.empty_like(src) if world > 1 else src]
             if world > 1 and rank == 0:
                 self.bufs[1].copy_(src)
-            # Where the broadcast of block k+1 runs: on a side stream next to block k's kernel ("overlap"), or in front of it on the same stream ("serial").
-            # Measured with the fused NFM bank (one wave that fills every SM): at N = 2 the side stream hides 0.013 ms of the 0.046 ms broadcast, at N = 8 NCCL's
-            # copy kernel next to the bank kernel costs 0.025 ms MORE than the two in sequence (profiles/r02_bench_n8_final.json) -- that leg goes serial from eight ranks on;
-            # the fastddc leg's 68 MB block per step stays on the side stream (the broadcast is as long as the compute there).
-            self.mode = mode if world > 1 else "none"
-            self.comm = (torch.cuda.current_stream() if mode == "serial" else torch.cuda.Stream()) if world > 1 else None
+            self.comm = torch.cuda.Stream() if world > 1 else None
             self.ready = [torch.cuda.Event(), torch.cuda.Event()]
             self.done = [torch.cuda.Event(), torch.cuda.Event()]
             self.k = 0
@@ -451,7 +446,7 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
     rates = np.ascontiguousarray(rates_all[rank * Cg:(rank + 1) * Cg])
     bank = cb.DdcBank(rates, D, taps, demod=True, chunk=1024)
     fo = torch.empty((Cg, n_out + (n_out & 1)), dtype=torch.float32, device=dev)
-    bc = Bcast(wide, os.environ.get("CSDRB_BENCH_BCAST", "serial" if world >= 8 else "overlap"))
+    bc = Bcast(wide)
 
     def step4(_k):
         w = bc.next()
@@ -462,10 +457,9 @@ def other_configs(torch, dist, cb, L, dev, world, rank, local, leg, check, cur_s
     out.append(leg("cfg4_nfm_bank", step4, 4, N, N * 8.0 + Cg * n_out * 4.0, Cg * N * (10.0 + 4.0 * M), "fp32",
                    "value = wideband Msamples/s through ALL channels of the job (every GPU sees the whole stream for its own 128 channels); "
                    "flops = (10 + 4*17) per channel-sample (rotation 4, phasor recursion 6, 17 tap FMAs on I and Q)"
-                   + (("; the block reaches ranks 1.. by NCCL broadcast from rank 0 each step, " + ("next to the previous block's kernel (side stream)" if bc.mode == "overlap" else "in front of its kernel (same stream)")) if world > 1 else ""),
+                   + ("; the block reaches ranks 1.. by NCCL broadcast from rank 0 each step, overlapped with the previous block's kernel" if world > 1 else ""),
                    {"workload": "1024-ch-class shift+fir_decimate_cc+fmdemod NFM bank, decim=50, 801 taps, 128 ch/GPU (BASELINE configs[3])", "channels_per_gpu": Cg,
-                    "channels_total": Cg * world, "block_samples": N, "nco_chunk": 1024,
-                    "collective": f"ncclBroadcast of the 16 MiB IQ block per step ({bc.mode})" if world > 1 else "none (1 GPU)",
+                    "channels_total": Cg * world, "block_samples": N, "nco_chunk": 1024, "collective": "ncclBroadcast of the 16 MiB IQ block per step" if world > 1 else "none (1 GPU)",
                     "scaling": "weak"}))
     if world > 1:
         # the overlap in numbers (no nsys in this image): the broadcast alone, the kernel alone (every rank on its own copy of the block), and the leg above
