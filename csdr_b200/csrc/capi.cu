@@ -668,6 +668,13 @@ int csdrb_copy2d_d2d(void* d_dst, size_t dst_pitch_bytes, const void* d_src, siz
     CSDRB_CUDA(cudaMemcpy2DAsync(d_dst, dst_pitch_bytes, d_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyDeviceToDevice, S(stream)));
     return 0;
 }
+int csdrb_copy2d_h2d(void* d_dst, size_t dst_pitch_bytes, const void* h_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
+{
+    if (!width_bytes || !rows) return 0;
+    if (null_io(h_src, d_dst, "copy2d_h2d")) return -1;
+    CSDRB_CUDA(cudaMemcpy2DAsync(d_dst, dst_pitch_bytes, h_src, src_pitch_bytes, width_bytes, rows, cudaMemcpyHostToDevice, S(stream)));
+    return 0;
+}
 int csdrb_copy2d_d2h(void* h_dst, size_t dst_pitch_bytes, const void* d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void* stream)
 {
     if (!width_bytes || !rows) return 0;

@@ -16,7 +16,8 @@
  *                   [--tail nfm|none] [--limit L] [--agc-ref R] [--device N | --devices N0,N1,...]  RATE:SINK [RATE:SINK ...]
  *   RATE  shift_addition_cc rate (fraction of the wideband sample rate), SINK a path (file or FIFO) or tcp:PORT (one listener).
  *   --devices: the channels are sliced over several GPUs of this node (csdrb_multi_bank_*: the block goes to the first device once and on to
- *   the others by NCCL broadcast); raw discriminator output only (--tail none), one block of latency more (two blocks are kept in flight).
+ *   the others by NCCL broadcast), one block of latency more (two blocks are kept in flight); the NFM tail, audio-rate work, runs on the first
+ *   device for all channels, through the same kernels as without --devices.
  * Sinks never hold the stream up: a sink that cannot take a block within 200 ms loses the rest of that block (counted on stderr at exit), one
  * that fails is dropped -- nmux's policy for slow clients (tsmpool.cpp:101-117, nmux.cpp:339-346).
  */
@@ -144,7 +145,79 @@ static int parse_devices(const char *list, int *dev, int max)
     return n;
 }
 
-static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *chan, int C, const float *rates, int D, const float *taps, int T, int block)
+
+/* ---- the NFM audio tail of README.md:87 behind the discriminator: limit_ff | deemphasis_nfm_ff 48000 | fastagc_ff | convert_f_s16 ------------------------
+ * Device buffers of ONE device (the single-GPU path's own, the first device of --devices):
+ *   demod   : [C][ds] float  : [Tn carried inputs of the de-emphasis FIR | new discriminator output]
+ *   agc_in  : [C][gs] float  : [remainder (< AGC_BLOCK) | new de-emphasised samples]
+ *   pcm     : [C][nb*AGC_BLOCK] s16 (contiguous so one flat copy serves all rows)
+ * The caller puts n_new discriminator samples per channel at demod + a_have (pitch ds) and calls nfm_tail_push. */
+typedef struct {
+    int C, Tn, a_have, g_have;
+    long ds, gs;
+    float limit, agc_ref;
+    float *d_demod, *d_carry, *d_agc_in;
+    short *d_pcm;
+    csdrb_fastagc_state_t *d_agc_state;
+    float *d_agc_hist;
+    void *d_agc_scratch;
+    size_t agc_sb;
+    unsigned char *h_out;
+} nfm_tail_t;
+
+static void nfm_tail_init(nfm_tail_t *t, int C, int out_cap, float limit, float agc_ref)
+{
+    memset(t, 0, sizeof *t);
+    t->C = C; t->limit = limit; t->agc_ref = agc_ref;
+    if (!csdrb_deemphasis_nfm_taps(NFM_RATE, &t->Tn)) die("no de-emphasis table");
+    t->ds = ((long)t->Tn + out_cap + 3) & ~3L;
+    t->gs = ((long)AGC_BLOCK + out_cap + 3) & ~3L;
+    t->d_demod = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)t->ds);
+    t->d_carry = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)(AGC_BLOCK + t->Tn + 4));
+    t->d_agc_in = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)t->gs);
+    t->d_pcm = csdrb_device_alloc(sizeof(short) * (size_t)C * (size_t)t->gs + 16);
+    t->d_agc_state = csdrb_device_alloc(sizeof(csdrb_fastagc_state_t) * (size_t)C);
+    t->d_agc_hist = csdrb_device_alloc(sizeof(float) * (size_t)C * 2 * AGC_BLOCK);
+    t->agc_sb = csdrb_fastagc_bank_scratch_bytes(C, (int)(t->gs / AGC_BLOCK) + 1);
+    t->d_agc_scratch = csdrb_device_alloc(t->agc_sb + 16);
+    t->h_out = csdrb_host_alloc((size_t)C * (size_t)t->gs * sizeof(float));
+    if (!t->d_demod || !t->d_carry || !t->d_agc_in || !t->d_pcm || !t->d_agc_state || !t->d_agc_hist || !t->d_agc_scratch || !t->h_out) die("out of memory");
+}
+
+/* n_new fresh discriminator samples per channel sit at d_demod + a_have: de-emphasis (limiter fused), AGC + s16 over the whole AGC blocks, audio to the sinks */
+static void nfm_tail_push(nfm_tail_t *t, channel_t *chan, int n_new, void *stream)
+{
+    const int C = t->C, Tn = t->Tn;
+    const long ds = t->ds, gs = t->gs;
+    const int a_n = t->a_have + n_new;
+    /* limit_ff fused into deemphasis_nfm_ff: a_n inputs -> a_n - Tn outputs behind the AGC remainder; keep the last Tn inputs */
+    int m = 0;
+    if (a_n > Tn) {
+        m = csdrb_deemphasis_nfm_bank_ff(t->d_demod, ds, t->d_agc_in + t->g_have, gs, C, a_n, NFM_RATE, t->limit, stream);
+        if (m < 0) die("csdrb_deemphasis_nfm_bank_ff failed");
+        OK(csdrb_copy2d_d2d(t->d_carry, sizeof(float) * (size_t)Tn, t->d_demod + m, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)Tn, (size_t)C, stream));
+        OK(csdrb_copy2d_d2d(t->d_demod, sizeof(float) * (size_t)ds, t->d_carry, sizeof(float) * (size_t)Tn, sizeof(float) * (size_t)Tn, (size_t)C, stream));
+        t->a_have = Tn;
+    } else t->a_have = a_n;
+    /* fastagc_ff over the whole AGC blocks available, then convert_f_s16 (one pass); the remainder waits for the next block */
+    const int g_n = t->g_have + m, nb = g_n / AGC_BLOCK, whole = nb * AGC_BLOCK;
+    if (nb > 0) {
+        OK(csdrb_fastagc_bank_f_s16(t->d_agc_in, gs, t->d_pcm, whole, C, AGC_BLOCK, nb, t->agc_ref, t->d_agc_state, t->d_agc_hist, t->d_agc_scratch, t->agc_sb + 16, stream));
+        OK(csdrb_copy_d2h(t->h_out, t->d_pcm, sizeof(short) * (size_t)C * (size_t)whole, stream));
+        const int rest = g_n - whole;
+        OK(csdrb_copy2d_d2d(t->d_carry, sizeof(float) * (size_t)AGC_BLOCK, t->d_agc_in + whole, sizeof(float) * (size_t)gs, sizeof(float) * (size_t)rest, (size_t)C, stream));
+        OK(csdrb_copy2d_d2d(t->d_agc_in, sizeof(float) * (size_t)gs, t->d_carry, sizeof(float) * (size_t)AGC_BLOCK, sizeof(float) * (size_t)rest, (size_t)C, stream));
+        t->g_have = rest;
+        OK(csdrb_stream_synchronize(stream));
+        for (int c = 0; c < C; c++) write_sink(&chan[c], t->h_out + sizeof(short) * (size_t)c * (size_t)whole, sizeof(short) * (size_t)whole);
+    } else {
+        t->g_have = g_n;
+        OK(csdrb_stream_synchronize(stream));
+    }
+}
+
+static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *chan, int C, const float *rates, int D, const float *taps, int T, int block,
+                     int nfm, float limit, float agc_ref)
 {
     csdrb_multi_bank_t *mb = csdrb_multi_bank_create(ndev, dev, C, rates, D, taps, T, 1, 1024, block);
     if (!mb) die("cannot create the multi-GPU bank");
@@ -155,6 +228,22 @@ static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *cha
     float *h_out[2] = {csdrb_host_alloc(sizeof(float) * (size_t)C * (size_t)n_out), csdrb_host_alloc(sizeof(float) * (size_t)C * (size_t)n_out)};
     unsigned char *raw = malloc((size_t)block * 2);
     if (!h_wide[0] || !h_wide[1] || !h_out[0] || !h_out[1] || !raw) die("out of memory");
+    /* --tail nfm: the audio tail is audio-rate work (C x 48 kHz): the discriminator rows every device returned go to the FIRST device once more and through
+     * the same kernels as in the single-GPU path */
+    nfm_tail_t tail_state; void *tail_stream = NULL;
+    if (nfm) {
+        OK(csdrb_set_device(dev[0]));
+        nfm_tail_init(&tail_state, C, n_out + 2, limit, agc_ref);
+        tail_stream = csdrb_stream_create();
+        if (!tail_stream) die("cannot create a stream");
+    }
+#define EMIT(slot_) do { \
+        if (nfm) { \
+            OK(csdrb_copy2d_h2d(tail_state.d_demod + tail_state.a_have, sizeof(float) * (size_t)tail_state.ds, h_out[slot_], sizeof(float) * (size_t)n_out, \
+                                sizeof(float) * (size_t)n_out, (size_t)C, tail_stream)); \
+            nfm_tail_push(&tail_state, chan, n_out, tail_stream); \
+        } else for (int c = 0; c < C; c++) write_sink(&chan[c], h_out[slot_] + (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out); \
+    } while (0)
     long blocks = 0;
     int ticket[2] = {-1, -1};
     for (int first = 1;; first = 0) {
@@ -163,7 +252,7 @@ static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *cha
         /* this buffer's previous block (two submits ago) must be done before it is overwritten; its results go out meanwhile */
         if (ticket[slot] >= 0) {
             if (csdrb_multi_bank_collect(mb, ticket[slot]) < 0) die("csdrb_multi_bank_collect failed");
-            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out[slot] + (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out);
+            EMIT(slot);
             ticket[slot] = -1;
         }
         if (!first) memcpy(w, h_wide[slot ^ 1] + consumed, sizeof(complexf) * (size_t)keep);   /* the unconsumed tail (csdr.c:1172-1174) */
@@ -182,8 +271,9 @@ static int run_multi(int in_fd, int u8, const int *dev, int ndev, channel_t *cha
         const int slot = (int)((blocks + k) & 1);
         if (ticket[slot] < 0) continue;
         if (csdrb_multi_bank_collect(mb, ticket[slot]) < 0) die("csdrb_multi_bank_collect failed");
-        for (int c = 0; c < C; c++) write_sink(&chan[c], h_out[slot] + (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out);
+        EMIT(slot);
     }
+#undef EMIT
     fprintf(stderr, "csdr-bankd: end of input after %ld blocks on %d devices, %ld kernel launches\n", blocks, ndev, csdrb_kernel_launches());
     csdrb_multi_bank_destroy(mb);
     return 0;
@@ -241,56 +331,46 @@ int main(int argc, char **argv)
     float *rates = malloc(sizeof(float) * (size_t)C);
     for (int c = 0; c < C; c++) rates[c] = chan[c].rate;
     if (ndev > 0) {
-        if (nfm) die("--devices runs the raw discriminator bank: add --tail none");
         if (ndev > C) die("more devices than channels");
         for (int c = 0; c < C; c++) { chan[c].fd = open_sink(chan[c].sink); sink_nonblocking(chan[c].fd); }
         const int fd = open_input(in_spec);
-        fprintf(stderr, "csdr-bankd: %d channels over %d devices, decimation %d, %d taps, %s input, blocks of %d samples\n", C, ndev, D, T, u8 ? "u8" : "f32", block);
-        const int rc = run_multi(fd, u8, devs, ndev, chan, C, rates, D, taps, T, block);
+        fprintf(stderr, "csdr-bankd: %d channels over %d devices, decimation %d, %d taps, %s input, blocks of %d samples, tail %s\n", C, ndev, D, T, u8 ? "u8" : "f32", block, tail);
+        const int rc = run_multi(fd, u8, devs, ndev, chan, C, rates, D, taps, T, block, nfm, limit, agc_ref);
         for (int c = 0; c < C; c++) { if (chan[c].dropped) fprintf(stderr, "csdr-bankd: sink %s lost %ld bytes (too slow)\n", chan[c].sink, chan[c].dropped); if (chan[c].fd >= 0) close(chan[c].fd); }
         return rc;
     }
     OK(csdrb_set_device(device));
     csdrb_ddc_bank_t *bank = csdrb_ddc_bank_create(C, rates, D, taps, T, 1, 1024);   /* 1024 = the CLI's shift_addition_cc call size (csdr.c:911) */
     if (!bank) die("cannot create the bank");
-    int Tn = 0;
-    if (nfm && !csdrb_deemphasis_nfm_taps(NFM_RATE, &Tn)) die("no de-emphasis table");
     void *stream = csdrb_stream_create();
     if (!stream) die("cannot create a stream");
 
     /* ---- buffers ----------------------------------------------------------------------------------------------------------------
      * wide[2]  : [tail of the previous block | new block] cf32, ping-pong so the tail copy never overlaps
-     * demod    : [C][ds] float  : [Tn carried inputs of the de-emphasis FIR | new discriminator output]
-     * agc_in   : [C][gs] float  : [remainder (< AGC_BLOCK) | new de-emphasised samples]
-     * agc_out  : [C][nb*AGC_BLOCK] float, pcm the same as s16 (contiguous so one flat conversion serves all rows) */
+     * with the NFM tail the discriminator output goes straight into nfm_tail_t's demod rows; without it into a plain [C][ds] array */
     const size_t in_bytes = (size_t)block * (u8 ? 2 : 8);
     unsigned char *h_in = csdrb_host_alloc(in_bytes);
     const int wide_cap = block + T + D + 16;
     complexf *d_wide[2] = {csdrb_device_alloc(sizeof(complexf) * (size_t)wide_cap), csdrb_device_alloc(sizeof(complexf) * (size_t)wide_cap)};
     unsigned char *d_raw = u8 ? csdrb_device_alloc(in_bytes + 16) : NULL;
     const int out_cap = wide_cap / D + 2;                          /* discriminator samples one block can add */
-    const long ds = ((long)Tn + out_cap + 3) & ~3L;
-    const long gs = ((long)AGC_BLOCK + out_cap + 3) & ~3L;
-    float *d_demod = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)ds);
-    float *d_carry = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)(AGC_BLOCK + Tn + 4));
-    float *d_agc_in = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)gs) : NULL;
-    float *d_agc_out = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)gs) : NULL;
-    short *d_pcm = nfm ? csdrb_device_alloc(sizeof(short) * (size_t)C * (size_t)gs + 16) : NULL;
-    csdrb_fastagc_state_t *d_agc_state = nfm ? csdrb_device_alloc(sizeof(csdrb_fastagc_state_t) * (size_t)C) : NULL;
-    float *d_agc_hist = nfm ? csdrb_device_alloc(sizeof(float) * (size_t)C * 2 * AGC_BLOCK) : NULL;
-    const size_t agc_sb = nfm ? csdrb_fastagc_bank_scratch_bytes(C, (int)(gs / AGC_BLOCK) + 1) : 0;
-    void *d_agc_scratch = nfm ? csdrb_device_alloc(agc_sb + 16) : NULL;
-    const size_t h_out_bytes = (size_t)C * (size_t)(gs > ds ? gs : ds) * sizeof(float);
-    unsigned char *h_out = csdrb_host_alloc(h_out_bytes);
-    if (!h_in || !d_wide[0] || !d_wide[1] || (u8 && !d_raw) || !d_demod || !d_carry || !h_out ||
-        (nfm && (!d_agc_in || !d_agc_out || !d_pcm || !d_agc_state || !d_agc_hist || !d_agc_scratch))) die("out of memory");
+    nfm_tail_t tl;
+    long ds = ((long)out_cap + 3) & ~3L;
+    float *d_demod = NULL;
+    unsigned char *h_out = NULL;
+    if (nfm) { nfm_tail_init(&tl, C, out_cap, limit, agc_ref); ds = tl.ds; d_demod = tl.d_demod; }
+    else {
+        d_demod = csdrb_device_alloc(sizeof(float) * (size_t)C * (size_t)ds);
+        h_out = csdrb_host_alloc((size_t)C * (size_t)ds * sizeof(float));
+    }
+    if (!h_in || !d_wide[0] || !d_wide[1] || (u8 && !d_raw) || !d_demod || (!nfm && !h_out)) die("out of memory");
 
     /* sinks last: tcp: sinks block until their listener arrives */
     for (int c = 0; c < C; c++) { chan[c].fd = open_sink(chan[c].sink); sink_nonblocking(chan[c].fd); }
     const int in_fd = open_input(in_spec);
     fprintf(stderr, "csdr-bankd: %d channels, decimation %d, %d taps, %s input, blocks of %d samples, tail %s\n", C, D, T, u8 ? "u8" : "f32", block, tail);
 
-    int cur = 0, keep = 0, a_have = 0, g_have = 0;
+    int cur = 0, keep = 0;
     long blocks = 0;
     /* Every call presents exactly `block` samples: the unconsumed tail plus as many new ones as the previous call consumed -- how csdr.c:1172-1174
      * feeds fir_decimate_cc.  A constant size keeps the bank's look-ahead pre-pass valid from block to block (a size that wobbles with
@@ -307,48 +387,20 @@ int main(int argc, char **argv)
         } else OK(csdrb_copy_h2d(fresh, h_in, fresh_bytes, stream));
         const int n_in = block;
 
-        /* 2. shift | fir_decimate | fmdemod for every channel, new discriminator samples behind the FIR's carried inputs */
+        /* 2. shift | fir_decimate | fmdemod for every channel, new discriminator samples behind the de-emphasis FIR's carried inputs */
+        const int a_have = nfm ? tl.a_have : 0;
         const int n_out = csdrb_ddc_bank_process(bank, d_wide[cur], n_in, d_demod + a_have, ds, stream);
         if (n_out < 0) die("csdrb_ddc_bank_process failed");
         const int consumed = n_out * D;
         keep = n_in - consumed;
         OK(csdrb_copy_d2d(d_wide[cur ^ 1], d_wide[cur] + consumed, sizeof(complexf) * (size_t)keep, stream));
         cur ^= 1;
-        const int a_n = a_have + n_out;
 
         if (!nfm) {                                                /* raw discriminator output, float */
-            OK(csdrb_copy2d_d2h(h_out, sizeof(float) * (size_t)a_n, d_demod, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)a_n, (size_t)C, stream));
+            OK(csdrb_copy2d_d2h(h_out, sizeof(float) * (size_t)n_out, d_demod, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)n_out, (size_t)C, stream));
             OK(csdrb_stream_synchronize(stream));
-            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out + sizeof(float) * (size_t)c * (size_t)a_n, sizeof(float) * (size_t)a_n);
-            a_have = 0; blocks++;
-            continue;
-        }
-
-        /* 3. limit_ff fused into deemphasis_nfm_ff: a_n inputs -> a_n - Tn outputs behind the AGC remainder; keep the last Tn inputs */
-        int m = 0;
-        if (a_n > Tn) {
-            m = csdrb_deemphasis_nfm_bank_ff(d_demod, ds, d_agc_in + g_have, gs, C, a_n, NFM_RATE, limit, stream);
-            if (m < 0) die("csdrb_deemphasis_nfm_bank_ff failed");
-            OK(csdrb_copy2d_d2d(d_carry, sizeof(float) * (size_t)Tn, d_demod + m, sizeof(float) * (size_t)ds, sizeof(float) * (size_t)Tn, (size_t)C, stream));
-            OK(csdrb_copy2d_d2d(d_demod, sizeof(float) * (size_t)ds, d_carry, sizeof(float) * (size_t)Tn, sizeof(float) * (size_t)Tn, (size_t)C, stream));
-            a_have = Tn;
-        } else a_have = a_n;
-
-        /* 4. fastagc_ff over the whole AGC blocks available, then convert_f_s16; the remainder waits for the next block */
-        const int g_n = g_have + m, nb = g_n / AGC_BLOCK, whole = nb * AGC_BLOCK;
-        if (nb > 0) {
-            OK(csdrb_fastagc_bank_f_s16(d_agc_in, gs, d_pcm, whole, C, AGC_BLOCK, nb, agc_ref, d_agc_state, d_agc_hist, d_agc_scratch, agc_sb + 16, stream));   /* AGC and s16 in one pass */
-            OK(csdrb_copy_d2h(h_out, d_pcm, sizeof(short) * (size_t)C * (size_t)whole, stream));
-            const int rest = g_n - whole;
-            OK(csdrb_copy2d_d2d(d_carry, sizeof(float) * (size_t)AGC_BLOCK, d_agc_in + whole, sizeof(float) * (size_t)gs, sizeof(float) * (size_t)rest, (size_t)C, stream));
-            OK(csdrb_copy2d_d2d(d_agc_in, sizeof(float) * (size_t)gs, d_carry, sizeof(float) * (size_t)AGC_BLOCK, sizeof(float) * (size_t)rest, (size_t)C, stream));
-            g_have = rest;
-            OK(csdrb_stream_synchronize(stream));
-            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out + sizeof(short) * (size_t)c * (size_t)whole, sizeof(short) * (size_t)whole);
-        } else {
-            g_have = g_n;
-            OK(csdrb_stream_synchronize(stream));
-        }
+            for (int c = 0; c < C; c++) write_sink(&chan[c], h_out + sizeof(float) * (size_t)c * (size_t)n_out, sizeof(float) * (size_t)n_out);
+        } else nfm_tail_push(&tl, chan, n_out, stream);           /* 3./4. limit | de-emphasis | AGC | s16, audio to the sinks */
         blocks++;
     }
     OK(csdrb_stream_synchronize(stream));

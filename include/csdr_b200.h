@@ -169,6 +169,7 @@ int csdrb_copy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int csdrb_copy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
 int csdrb_copy2d_d2d(void *d_dst, size_t dst_pitch_bytes, const void *d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void *stream);
 int csdrb_copy2d_d2h(void *h_dst, size_t dst_pitch_bytes, const void *d_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void *stream);
+int csdrb_copy2d_h2d(void *d_dst, size_t dst_pitch_bytes, const void *h_src, size_t src_pitch_bytes, size_t width_bytes, size_t rows, void *stream);
 
 /* K1 conversions on device buffers (16-byte aligned) */
 int csdrb_convert_u8_f(const unsigned char *d_in, float *d_out, long n, void *stream);

@@ -85,6 +85,14 @@ def test_nfm_bank_equals_the_readme_graph_per_channel(bankd, oracle, tmp_path, b
         want = oracle_channel(oracle, wide, rate, taps, "nfm")
         assert got.size == want.size and got.size >= 25 * 1024, (rate, got.size, want.size)
         assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1, rate       # floats equal to ~1e-6 -> s16 within one count
+    # --devices with the NFM tail: the channels' discriminator rows come back from their devices and go through the tail on the first one -- the same
+    # kernels on the same numbers, so the audio must be the single-device run's, byte for byte
+    if block == 100_000:
+        for devices in MULTI_DEVICES():
+            msinks = [tmp_path / f"m{devices.replace(',', '_')}_{k}.s16" for k in range(len(RATES))]
+            run(bankd, ["--block", str(block), "--devices", devices], u8.tobytes(), msinks)
+            for a, b in zip(sinks, msinks):
+                assert a.read_bytes() == b.read_bytes(), devices
 
 
 def test_raw_discriminator_output_and_f32_input(bankd, oracle, tmp_path):
