@@ -505,7 +505,8 @@ int launch_shift_addition_bank(const float2* d_in, long in_stride, float2* d_out
     // kernel follows slice by slice on the caller's stream.  A slice must still fill the machine (a warp walks its 32 chunks tile after tile, ~3 us per tile:
     // eight slices of 384 chunks x 64 channels ran the main kernel at 0.43 waves and gained nothing; r02 call 14).  CSDRB_SHIFT_SLICES=1: one stream.
     static const int max_slices = getenv("CSDRB_SHIFT_SLICES") ? atoi(getenv("CSDRB_SHIFT_SLICES")) : 3;
-    int slices = (int)(((long)nchunks * channels) / (768L * 64));       // >= 768 chunks x 64 channels (or as many chunk-channels) per slice
+    static const long slice_min = getenv("CSDRB_SHIFT_SLICE_MIN") ? atol(getenv("CSDRB_SHIFT_SLICE_MIN")) : 768L * 64;   // chunk-channels a slice needs to fill the machine (the CPU tier lowers it)
+    int slices = (int)(((long)nchunks * channels) / (slice_min > 0 ? slice_min : 1));
     if (slices > max_slices) slices = max_slices;
     if (slices > kSideSlices) slices = kSideSlices;
     if (slices < 2) {

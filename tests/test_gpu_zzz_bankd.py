@@ -88,11 +88,14 @@ def test_nfm_bank_equals_the_readme_graph_per_channel(bankd, oracle, tmp_path, b
     # --devices with the NFM tail: the channels' discriminator rows come back from their devices and go through the tail on the first one -- the same
     # kernels on the same numbers, so the audio must be the single-device run's, byte for byte
     if block == 100_000:
-        for devices in MULTI_DEVICES():
-            msinks = [tmp_path / f"m{devices.replace(',', '_')}_{k}.s16" for k in range(len(RATES))]
-            run(bankd, ["--block", str(block), "--devices", devices], u8.tobytes(), msinks)
-            for a, b in zip(sinks, msinks):
-                assert a.read_bytes() == b.read_bytes(), devices
+        devices = MULTI_DEVICES()[-1]                                  # two devices where the box (or the emulator) has them
+        short = u8[:2 * 7 * block].tobytes()                           # seven blocks: enough for several AGC blocks of audio per channel
+        ssinks = [tmp_path / f"s{k}.s16" for k in range(len(RATES))]
+        msinks = [tmp_path / f"m{k}.s16" for k in range(len(RATES))]
+        run(bankd, ["--block", str(block)], short, ssinks)
+        run(bankd, ["--block", str(block), "--devices", devices], short, msinks)
+        for a, b in zip(ssinks, msinks):
+            assert a.stat().st_size >= 4 * 2 * 1024 and a.read_bytes() == b.read_bytes(), devices
 
 
 def test_raw_discriminator_output_and_f32_input(bankd, oracle, tmp_path):

@@ -19,6 +19,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests" / "host_shim"))
+os.environ.setdefault("CSDRB_SHIFT_SLICE_MIN", "3000")      # the K2 launcher cuts its chain into slices from 2 x 3000 chunk-channels on (product default: 2 x 768 x 64)
 import emul_build  # noqa: E402
 
 from oracle.pyoracle import rel_rms  # noqa: E402
@@ -177,7 +178,7 @@ def test_ima_adpcm_rows_bit_exact(elementwise, oracle):
 
 
 # ------------------------------------------------------------------------------------------------------------------ K2 and shift variants
-@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37), (120 * 1024 + 5, 1024), (9000, 64), (9003, 8), (8 * 20_001 + 3, 8)])   # from the sixth on: > 96 chunks, the chain runs on its wrap table (phase_table.cuh); the last one: 20 002 chunks x 6 channels = two chain slices on the side stream
+@pytest.mark.parametrize("n,chunk", [(16384 + 777, 1024), (5000, 1000), (4096, 4096), (3000, 0), (1001, 37), (120 * 1024 + 5, 1024), (9000, 64), (9003, 8), (2 * 4_001 + 1, 2)])   # from the sixth on: > 96 chunks, the chain runs on its wrap table (phase_table.cuh); the last two: 1 126 / 4 002 chunks x 6 channels = two / three chain slices on the side stream (CSDRB_SHIFT_SLICE_MIN below)
 def test_k2_shift_bank_replays_reference_chain(shift, oracle, n, chunk):
     rng = np.random.default_rng(n)
     rates = np.array([-0.41, -0.085, 0.0, 0.2, 0.4999, 1e-4], np.float32)
